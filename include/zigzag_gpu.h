@@ -1,0 +1,167 @@
+/*
+ * zigzag_gpu.h — C ABI of the B200 (sm_100a) implementation of zigzag's per-gene MCMC sweep.
+ *
+ * The reference (ammonthompson/zigzag v1.0.0) is pure R and has no FFI; its seam is the method table
+ * `proposal_list` (R/zigzagInitialize.R:207-223) whose entries are called as proposal_list[[p]](tune=...)
+ * from burnin() (R/zigzagBurnin.R:66-67) and mcmc() (R/zigzagMCMC.R:172-173).  Every entry point below
+ * replaces one of those R methods (or a per-gene reduction inside one) and is what an R `.Call` shim
+ * (r_overlay/src/zz_shim.c) or the ctypes host (zigzag_b200/_capi.py) binds.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `const double*` / `double*` argument is a HOST pointer unless the
+ *     name ends in _dev; the library owns all device and pinned memory behind the opaque handle.
+ *   - Xg is G x R column-major (R's matrix layout == library-major struct-of-arrays), -Inf = not detected.
+ *   - integer vectors follow R: allocation_active_inactive in {0,1}, allocation_within_active in 1..K,
+ *     inactive_spike_allocation in {0,1}.
+ *   - per-chain arrays are length G (the local gene shard); multi-chain draw/decision tables are [n][C][G].
+ *   - return value: ZZ_OK (0) or a negative error code; the message is kept on the handle (zz_last_error).
+ *     No exceptions or longjmp cross this boundary.  CUDA errors are sticky.
+ *   - NaN acceptance ratios are treated as "reject" and raise the sticky NaN flag (zz_nan_flag); the reference
+ *     would poison the state with NA (R/zigzagProposals.R:302-310, guard at R/zigzagBurnin.R:69-78).
+ *   - random draws: `draws == NULL` => counter-based Philox4x32-10 keyed by (seed; chain, step, move slot,
+ *     global gene index), `draws != NULL` => "identical uniforms" test mode, the caller supplies every draw.
+ */
+#ifndef ZIGZAG_GPU_H
+#define ZIGZAG_GPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZZ_MAX_LIBS 64
+#define ZZ_MAX_COMP 8
+
+#define ZZ_OK 0
+#define ZZ_ERR_INVALID (-1)
+#define ZZ_ERR_CUDA (-2)
+#define ZZ_ERR_STATE (-3)
+#define ZZ_ERR_NOMEM (-4)
+
+/* move-slot ids used in the Philox counter (and by zz_philox_draws) */
+#define ZZ_SLOT_YG 1
+#define ZZ_SLOT_VARIANCE_G 2
+#define ZZ_SLOT_ALLOC 3
+#define ZZ_SLOT_ALLOC_WITHIN 4
+#define ZZ_SLOT_SPIKE 5
+
+/* bits of the `moves` mask of zz_sweep */
+#define ZZ_MOVE_YG 1u
+#define ZZ_MOVE_VARIANCE_G 2u
+#define ZZ_MOVE_ALLOC 4u
+#define ZZ_MOVE_ALLOC_WITHIN 8u
+#define ZZ_MOVE_SPIKE 16u
+#define ZZ_MOVE_FUSED (ZZ_MOVE_YG | ZZ_MOVE_VARIANCE_G | ZZ_MOVE_ALLOC | ZZ_MOVE_SPIKE)
+
+typedef struct zz_handle zz_handle;
+
+/* Scalar model parameters read by the per-gene moves: the RefClass fields s0, s1, tau, alpha_r, spike_probability,
+   inactive_means, inactive_variances, active_means, active_variances, weight_active, weight_within_active, beta,
+   temperature, variance_g_upper_bound (R/zigzag.R:117-338). */
+typedef struct zz_hyper {
+  int32_t num_libraries;
+  int32_t num_active_components;
+  double s0, s1, tau;
+  double alpha_r[ZZ_MAX_LIBS];
+  double spike_probability;
+  double inactive_means, inactive_variances;
+  double active_means[ZZ_MAX_COMP], active_variances[ZZ_MAX_COMP];
+  double weight_active, weight_within_active[ZZ_MAX_COMP];
+  double beta, temperature, variance_g_upper_bound;
+} zz_hyper;
+
+typedef struct zz_config {
+  int64_t num_genes;   /* genes held by this handle (the local shard) */
+  int64_t gene_offset; /* global index of local gene 0: Philox is keyed by the global index, so results do not depend on sharding */
+  int32_t num_libraries;
+  int32_t num_active_components;
+  int32_t num_chains;  /* independent chains batched over the same Xg (config 5) */
+  int32_t device;      /* CUDA device ordinal */
+  uint64_t seed;
+} zz_config;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+int zz_create(const zz_config *cfg, zz_handle **out);           /* replaces: zigzag$new() state allocation, R/zigzagInitialize.R:7-564 */
+void zz_destroy(zz_handle *h);
+const char *zz_last_error(const zz_handle *h);
+int zz_set_stream(zz_handle *h, void *cuda_stream);              /* run on the caller's stream (e.g. torch's current stream) */
+int zz_sync(zz_handle *h);
+uint64_t zz_launch_count(const zz_handle *h);                    /* kernels launched so far (bench.py gpu_launches) */
+
+/* ---- data and state ------------------------------------------------------------------------------------- */
+int zz_upload_data(zz_handle *h, const double *Xg, const double *gene_lengths);  /* fields Xg (I:52-56), gene_lengths (I:143-149) */
+/* Any pointer may be NULL (= leave untouched / do not fetch).  Fields: Yg, variance_g, allocation_active_inactive,
+   allocation_within_active[[1]], inactive_spike_allocation, XgLikelihood, variance_g_probability, tuningParam_yg,
+   tuningParam_variance_g, active_gene_set membership (R/zigzag.R:117-338).  no_detect_spike is derived from Xg. */
+int zz_set_state(zz_handle *h, int chain, const double *Yg, const double *variance_g, const int32_t *alloc_active_inactive,
+                 const int32_t *alloc_within_active, const int32_t *inactive_spike_allocation, const double *XgLikelihood,
+                 const double *variance_g_probability, const double *tuningParam_yg, const double *tuningParam_variance_g,
+                 const int32_t *pinned_active);
+int zz_get_state(zz_handle *h, int chain, double *Yg, double *variance_g, int32_t *alloc_active_inactive,
+                 int32_t *alloc_within_active, int32_t *inactive_spike_allocation, double *XgLikelihood,
+                 double *variance_g_probability, double *tuningParam_yg, double *tuningParam_variance_g);
+int zz_set_hyper(zz_handle *h, int chain, const zz_hyper *hy);
+int zz_get_hyper(zz_handle *h, int chain, zz_hyper *hy);
+/* XgLikelihood <- computeXgLikelihood(Xg,Yg,variance_g,p_x); variance_g_probability <- computeVarianceGPriorProbability (I:473, I:504) */
+int zz_refresh_caches(zz_handle *h);
+int zz_reset_windows(zz_handle *h);                              /* Yg_trace / variance_g_trace <- 77 zeros + 23 ones (I:460,466) */
+int zz_get_window_sums(zz_handle *h, int chain, int32_t *yg_sum, int32_t *vg_sum); /* rowSums(Yg_trace), rowSums(variance_g_trace) */
+
+/* ---- evaluators (north-star check 1): one double per gene ------------------------------------------------ */
+int zz_eval_xg_loglik(zz_handle *h, int chain, double *out);      /* computeXgLikelihood, R/zigzagProbability.R:57-127 (+ get_px U:150-159) */
+int zz_eval_varg_logprior(zz_handle *h, int chain, double *out);  /* computeVarianceGPriorProbability, P:11-31 (+ get_sigmax U:144-148) */
+int zz_eval_level2_loglik(zz_handle *h, int chain, double *out);  /* computeInactiveLikelihood / computeActiveLikelihood, P:210-273 */
+
+/* ---- per-gene moves (north-star check 2) ------------------------------------------------------------------ */
+/* draws layouts ([n][C][G], may be NULL => Philox):  yg: {z, u}; variance_g: {u_proposal, u_accept}; alloc: {u_ai, u_within};
+   alloc_within: {u_within}; spike: {z_y, z_v, u}.  decisions ([C][G] uint8, may be NULL): accept bit, or for the
+   allocation moves the new allocation word (0 = inactive, k = active component k). */
+int zz_mh_yg(zz_handle *h, uint64_t step, int tune, const double *draws, uint8_t *decisions);            /* mhYg, R/zigzagProposals.R:250-333 */
+int zz_mh_variance_g(zz_handle *h, uint64_t step, int tune, const double *draws, uint8_t *decisions);    /* mhVariance_g, Pr:7-56 (+ scale_move MP:3-13) */
+int zz_gibbs_alloc(zz_handle *h, uint64_t step, const double *draws, uint8_t *decisions);                /* gibbsAllocationActiveInactive (+ chained WithinActive), Pr:335-410 */
+int zz_gibbs_alloc_within(zz_handle *h, uint64_t step, const double *draws, uint8_t *decisions);         /* gibbsAllocationWithinActive, Pr:363-410 */
+int zz_mh_spike_alloc(zz_handle *h, uint64_t step, const double *draws, uint8_t *decisions);             /* mhSpikeAllocation, Pr:528-638 */
+/* Fused systematic-scan sweep: for every gene mhYg -> mhVariance_g -> allocation (AI + within) -> mhSpikeAllocation with the
+   gene's state held in registers.  `moves` selects a subset (ZZ_MOVE_*).  draws: [9][C][G] = {z_yg,u_yg,u1_vg,u2_vg,u_ai,
+   u_within,zy_spike,zv_spike,u_spike} or NULL; decisions: [4][C][G] or NULL. */
+int zz_sweep(zz_handle *h, uint64_t step, int tune, uint32_t moves, const double *draws, uint8_t *decisions);
+/* Exports the draws Philox would produce for (step, slot) in the layout of that move's `draws` argument. */
+int zz_philox_draws(zz_handle *h, uint64_t step, int slot, double *out);
+
+/* ---- reductions that feed the hyper-parameter moves (R/zigzagProposals.R:58-243, 412-526, 640-803) ------- */
+int zz_suffstats_len(int num_active_components);                 /* 3(K+1)+10 */
+/* out [C][len]: n_c (K+1) | sum y per component (K+1; inactive: out-of-spike only) | sum y^2 (K+1) | n_inspike, n_out,
+   sum z, sum z^2, sum y(out), sum y^2(out), sum y z (z = log variance_g, out-of-spike) | sum XgLikelihood | sum variance_g_probability(out) | nan count */
+int zz_suffstats(zz_handle *h, double *out);
+int zz_suffstats_dev(zz_handle *h, double *out_dev);             /* same, written to caller-owned device memory on the handle's stream (for an NCCL all-reduce) */
+/* out2 = { sum over out-of-spike genes of computeVarianceGPriorProbability(variance_g, exp(s0+s1*Yg), tau), sum of the cached variance_g_probability } ; Pr:84-87,126-130,167-170 */
+int zz_varg_hyper_sum(zz_handle *h, int chain, double s0, double s1, double tau, double *out2);
+int zz_commit_varg_hyper(zz_handle *h, int chain);               /* accepted mhTau/mhSg/mhS0Tau: overwrite variance_g_probability[out_spike_idx] (Pr:113,147,187) from the current hyper */
+/* out2 = { sum computeInactiveLikelihood over inactive genes, sum computeActiveLikelihood over active genes } at the given parameters; Pr:444-447,485-488,653-654,729-730,780-784 */
+int zz_level2_sums(zz_handle *h, int chain, double inactive_mean, double inactive_variance, const double *active_means,
+                   const double *active_variances, double *out2);
+/* out[r] = sum_g [ll_r(alpha_prop[r]) - ll_r(alpha_r[r])] for every library with lib_mask[r] != 0 (NULL = all); Pr:209-224 */
+int zz_px_delta(zz_handle *h, int chain, const double *alpha_prop, const uint8_t *lib_mask, double *out);
+int zz_px_commit(zz_handle *h, int chain, int lib, double alpha_new); /* accepted mhP_x: alpha_r[lib] and XgLikelihood update (Pr:213-215 / :219, :234-239) */
+int zz_lnl(zz_handle *h, int chain, double *out);                /* calculate_lnl, R/zigzagUtilities.R:70-75 */
+
+/* ---- sampling-time and tuning helpers ---------------------------------------------------------------------- */
+int zz_reset_alloc_trace(zz_handle *h);                          /* allocation_trace <- one-hot(current) is reset+accumulate (R/zigzagMCMC.R:142-145) */
+int zz_accumulate_alloc_trace(zz_handle *h);                     /* allocation_trace += one-hot(allocation), R/zigzagMCMC.R:194-199 */
+int zz_get_alloc_trace(zz_handle *h, int chain, uint32_t *out);  /* [K+1][G] */
+int zz_tune(zz_handle *h, double target);                        /* x_tune on Yg_trace / variance_g_trace, R/zigzagUtilities.R:161-181, 202-206 */
+int zz_nan_flag(zz_handle *h, int *flag);                        /* replaces the NA guard R/zigzagBurnin.R:69-78 */
+
+/* ---- host-buffer round trip (bench.py `e2e`) ---------------------------------------------------------------- */
+/* One fused sweep where the mutable per-gene state lives in HOST arrays, as it does in the R object between .Call()s:
+   uploads Yg, variance_g, tuning parameters, caches and allocations, runs zz_sweep, downloads the updated state.  Xg and
+   gene_lengths stay resident from zz_upload_data.  Chain 0 only.  Bytes moved are returned in h2d_bytes / d2h_bytes. */
+int zz_sweep_host(zz_handle *h, uint64_t step, int tune, double *Yg, double *variance_g, int32_t *alloc_active_inactive,
+                  int32_t *alloc_within_active, int32_t *inactive_spike_allocation, double *XgLikelihood,
+                  double *variance_g_probability, const double *tuningParam_yg, const double *tuningParam_variance_g,
+                  int64_t *h2d_bytes, int64_t *d2h_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

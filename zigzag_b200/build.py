@@ -1,0 +1,46 @@
+"""Builds the sm_100a CUDA library in-tree (zigzag_b200/libzigzag_gpu.so) with nvcc.  No GPU is needed to build."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = [os.path.join(HERE, "csrc", "zz_gpu.cu")]
+DEPS = SRC + [os.path.join(HERE, "csrc", "zz_device.cuh"), os.path.join(HERE, "..", "include", "zigzag_gpu.h")]
+OUT = os.path.join(HERE, "libzigzag_gpu.so")
+
+# -fmad=false: the kernels keep the reference's operation order (a*b+c is not contracted), see DESIGN.md "Numerics"
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
+              "--shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
+
+
+def nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
+    env = dict(os.environ)
+    env.pop("CC", None); env.pop("CXX", None)  # the image's $CC points at a gcc without the host libs nvcc needs
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if verbose:
+        sys.stderr.write(r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

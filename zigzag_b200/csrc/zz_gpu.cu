@@ -1,0 +1,920 @@
+// zz_gpu.cu — sm_100a kernels and the C ABI (include/zigzag_gpu.h) of zigzag's per-gene MCMC sweep.
+//
+// Layout in HBM (per handle = one gene shard on one GPU):
+//   Xg      double [R][G]        library-major (== R's column-major G x R matrix), shared by all chains
+//   gl      double [G]           gene_lengths (unit mean)
+//   per chain c (arrays are [C][G]): Yg, variance_g, XgLikelihood, variance_g_probability, tuningParam_yg,
+//   tuningParam_variance_g (double), flags (uint16: active | in-spike | all-zero | pinned | k-1<<8),
+//   win_y / win_v (2 x u64 accept windows, burn-in only), alloc_trace uint32 [C][K+1][G]
+//   hyper   zz_hyper [C]         read by every block into shared memory
+// One thread owns one gene; consecutive threads own consecutive genes so every array access is a coalesced
+// 8-byte-per-lane stream; the gene's state stays in registers across the moves of a sweep.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <new>
+#include "zz_device.cuh"
+
+using namespace zz;
+
+namespace {
+
+constexpr int BLOCK = 256;
+constexpr int RED_BLOCKS = 148 * 4;  // persistent-style reduction grid: 4 CTAs per SM
+
+// ------------------------------------------------------------------------------------------------ kernels
+
+struct SweepArgs {
+  int64_t G, g_begin, g_end, gene_offset;
+  int C, R, K, tune;
+  uint32_t moves;
+  uint64_t seed, step;
+  const double *Xg, *gl;
+  double *Yg, *vg, *xglik, *vgprob;
+  const double *ty, *tv;
+  uint16_t *flags;
+  ulonglong2 *win_y, *win_v;
+  const zz_hyper *hyper;
+  const double *draws[9];
+  uint8_t *dec[4];
+  int *nan_flag;
+};
+
+__global__ void __launch_bounds__(BLOCK) k_sweep(const SweepArgs a) {
+  __shared__ HyperS H;
+  const int chain = blockIdx.y;
+  load_hyper(H, a.hyper + chain);
+  const int64_t g = a.g_begin + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (g >= a.g_end) return;
+  const int64_t i = (int64_t)chain * a.G + g;
+  const uint64_t gid = (uint64_t)(a.gene_offset + g);
+  Gene gn;
+  gn.y = a.Yg[i]; gn.v = a.vg[i]; gn.xglik = a.xglik[i]; gn.vgprob = a.vgprob[i]; gn.f = a.flags[i];
+  const double gl = a.gl[g];
+  const double *xg = a.Xg + g;
+  bool saw_nan = false;
+
+  if (a.moves & ZZ_MOVE_YG) {
+    double z, u;
+    if (a.draws[0]) { z = a.draws[0][i]; u = a.draws[1][i]; }
+    else {
+      double ua, ub, z1, u1;
+      uniform2(a.seed, chain, a.step, ZZ_SLOT_YG, 0, gid, ua, ub); box_muller(ua, ub, z, z1);
+      uniform2(a.seed, chain, a.step, ZZ_SLOT_YG, 1, gid, u, u1);
+    }
+    const bool proposed = !(gn.f & F_INSPIKE);
+    double ratio;
+    const int acc = move_yg(H, gn, xg, a.G, gl, a.ty[i], z, u, ratio);
+    saw_nan |= proposed && isnan(ratio);
+    if (a.tune && proposed) { ulonglong2 w = a.win_y[i]; window_push(w, acc); a.win_y[i] = w; }  // Pr:312-322
+    if (a.dec[0]) a.dec[0][i] = (uint8_t)acc;
+  }
+  if (a.moves & ZZ_MOVE_VARIANCE_G) {
+    double u1, u2;
+    if (a.draws[2]) { u1 = a.draws[2][i]; u2 = a.draws[3][i]; }
+    else uniform2(a.seed, chain, a.step, ZZ_SLOT_VARIANCE_G, 0, gid, u1, u2);
+    const bool proposed = !(gn.f & F_INSPIKE);
+    double ratio;
+    const int acc = move_variance_g(H, gn, xg, a.G, gl, a.tv[i], u1, u2, ratio);
+    saw_nan |= proposed && isnan(ratio);
+    if (a.tune && proposed) { ulonglong2 w = a.win_v[i]; window_push(w, acc); a.win_v[i] = w; }  // Pr:40-50
+    if (a.dec[1]) a.dec[1][i] = (uint8_t)acc;
+  }
+  if (a.moves & ZZ_MOVE_ALLOC) {
+    double u_ai, u_w;
+    if (a.draws[4]) { u_ai = a.draws[4][i]; u_w = a.draws[5][i]; }
+    else uniform2(a.seed, chain, a.step, ZZ_SLOT_ALLOC, 0, gid, u_ai, u_w);
+    double pa;
+    const int word = move_alloc(H, gn, u_ai, u_w, pa);
+    if (a.dec[2]) a.dec[2][i] = (uint8_t)word;
+  } else if (a.moves & ZZ_MOVE_ALLOC_WITHIN) {
+    double u_w, u_x;
+    if (a.draws[5]) u_w = a.draws[5][i];
+    else uniform2(a.seed, chain, a.step, ZZ_SLOT_ALLOC_WITHIN, 0, gid, u_w, u_x);
+    if (gn.f & F_ACTIVE) { const int kn = within_active(H, gn.y, u_w); if (kn > 0) gn.f = flag_set_k(gn.f, kn); }
+    if (a.dec[2]) a.dec[2][i] = (uint8_t)((gn.f & F_ACTIVE) ? flag_k(gn.f) : 0);
+  }
+  if (a.moves & ZZ_MOVE_SPIKE) {
+    double zy, zv, u;
+    if (a.draws[6]) { zy = a.draws[6][i]; zv = a.draws[7][i]; u = a.draws[8][i]; }
+    else {
+      double ua, ub, u1;
+      uniform2(a.seed, chain, a.step, ZZ_SLOT_SPIKE, 0, gid, ua, ub); box_muller(ua, ub, zy, zv);
+      uniform2(a.seed, chain, a.step, ZZ_SLOT_SPIKE, 1, gid, u, u1);
+    }
+    const bool proposed = (gn.f & F_ALLZERO) && !(gn.f & F_ACTIVE);
+    double ratio;
+    const int acc = move_spike(H, gn, xg, a.G, gl, zy, zv, u, ratio);
+    saw_nan |= proposed && isnan(ratio);
+    if (a.dec[3]) a.dec[3][i] = (uint8_t)acc;
+  }
+  a.Yg[i] = gn.y; a.vg[i] = gn.v; a.xglik[i] = gn.xglik; a.vgprob[i] = gn.vgprob; a.flags[i] = (uint16_t)gn.f;
+  if (saw_nan) atomicOr(a.nan_flag, 1);
+}
+
+// exports the Philox draws of one move slot in the layout of that move's `draws` argument
+__global__ void __launch_bounds__(BLOCK) k_draws(int64_t G, int64_t gene_offset, int C, uint64_t seed, uint64_t step, int slot, double *out) {
+  const int chain = blockIdx.y;
+  const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (g >= G) return;
+  const int64_t i = (int64_t)chain * G + g, CG = (int64_t)C * G;
+  const uint64_t gid = (uint64_t)(gene_offset + g);
+  double a, b, c, d, z0, z1;
+  switch (slot) {
+    case ZZ_SLOT_YG:
+      uniform2(seed, chain, step, slot, 0, gid, a, b); box_muller(a, b, z0, z1);
+      uniform2(seed, chain, step, slot, 1, gid, c, d);
+      out[i] = z0; out[CG + i] = c; break;
+    case ZZ_SLOT_VARIANCE_G: case ZZ_SLOT_ALLOC:
+      uniform2(seed, chain, step, slot, 0, gid, a, b);
+      out[i] = a; out[CG + i] = b; break;
+    case ZZ_SLOT_ALLOC_WITHIN:
+      uniform2(seed, chain, step, slot, 0, gid, a, b);
+      out[i] = a; break;
+    case ZZ_SLOT_SPIKE:
+      uniform2(seed, chain, step, slot, 0, gid, a, b); box_muller(a, b, z0, z1);
+      uniform2(seed, chain, step, slot, 1, gid, c, d);
+      out[i] = z0; out[CG + i] = z1; out[2 * CG + i] = c; break;
+  }
+}
+
+enum { EVAL_XGLIK = 0, EVAL_VGPRIOR = 1, EVAL_LEVEL2 = 2, EVAL_REFRESH = 3, EVAL_COMMIT_VG = 4 };
+
+struct EvalArgs {
+  int64_t G; int which;
+  const double *Xg, *gl, *Yg, *vg;
+  const uint16_t *flags;
+  const zz_hyper *hyper;   // already offset to the chain (or base when grid.y spans chains)
+  double *out0, *out1;     // per-gene outputs (chain-offset applied by blockIdx.y * G)
+};
+
+__global__ void __launch_bounds__(BLOCK) k_eval(const EvalArgs a) {
+  __shared__ HyperS H;
+  const int chain = blockIdx.y;
+  load_hyper(H, a.hyper + chain);
+  const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (g >= a.G) return;
+  const int64_t i = (int64_t)chain * a.G + g;
+  const double y = a.Yg[i], v = a.vg[i];
+  const uint32_t f = a.flags[i];
+  const bool in_spike = f & F_INSPIKE;
+  if (a.which == EVAL_XGLIK || a.which == EVAL_REFRESH) {
+    a.out0[i] = in_spike ? xg_lik_inspike(H, f & F_ALLZERO) : xg_lik_out(H, a.Xg + g, a.G, y, v, a.gl[g]);
+  }
+  if (a.which == EVAL_VGPRIOR) a.out0[i] = varg_prior(H, v, get_sigmax(H.s0, H.s1, y), H.tau, H.rtau);
+  if (a.which == EVAL_REFRESH) a.out1[i] = varg_prior(H, v, get_sigmax(H.s0, H.s1, y), H.tau, H.rtau);   // I:504
+  if (a.which == EVAL_COMMIT_VG && !in_spike) a.out1[i] = varg_prior(H, v, get_sigmax(H.s0, H.s1, y), H.tau, H.rtau);  // Pr:113,147,187
+  if (a.which == EVAL_LEVEL2) a.out0[i] = level2_lik(H, y, f, in_spike);
+}
+
+enum { RED_VARG_HYPER = 0, RED_LEVEL2 = 1, RED_PXDELTA = 2, RED_LNL = 3 };
+
+struct RedArgs {
+  int64_t G; int op, chain;
+  const double *Xg, *gl, *Yg, *vg, *xglik, *vgprob;  // chain-offset applied by the launcher
+  const uint16_t *flags;
+  const zz_hyper *hyper;                              // this chain's
+  double s0, s1, tau, im, iv;
+  double am[ZZ_MAX_COMP], av[ZZ_MAX_COMP];
+  double alpha_prop[ZZ_MAX_LIBS];
+  uint8_t lib_mask[ZZ_MAX_LIBS];
+  double *partials;                                   // [grid.y][grid.x][2]
+};
+
+// Grid-stride per-gene reduction; blockIdx.y = library for RED_PXDELTA.  Two sums per gene at most.
+__global__ void __launch_bounds__(BLOCK) k_reduce(const RedArgs a) {
+  __shared__ HyperS H;
+  __shared__ double red[BLOCK / 32];
+  load_hyper(H, a.hyper);
+  const int lib = blockIdx.y;
+  double v0 = 0, v1 = 0;
+  const bool active_y = !(a.op == RED_PXDELTA && !a.lib_mask[lib]);
+  if (active_y) {
+    for (int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x; g < a.G; g += (int64_t)gridDim.x * BLOCK) {
+      const double y = a.Yg[g], v = a.vg[g];
+      const uint32_t f = a.flags[g];
+      const bool in_spike = f & F_INSPIKE;
+      if (a.op == RED_VARG_HYPER) {                  // Pr:84-87, 126-130, 167-170
+        if (!in_spike) {
+          v0 += varg_prior(H, v, get_sigmax(a.s0, a.s1, y), a.tau, sqrt(a.tau));
+          v1 += a.vgprob[g];
+        }
+      } else if (a.op == RED_LEVEL2) {               // Pr:444-447, 653-654, 780-784
+        if (f & F_ACTIVE) {
+          const int k = flag_k(f) - 1;
+          const double d = y - a.am[k];
+          v1 += -log(H.sqrt2pi * sqrt(a.av[k])) - (d * d) / (2 * a.av[k]);
+        } else {
+          v0 += inactive_lik_at(H, y, in_spike, a.im, a.iv);
+        }
+      } else if (a.op == RED_PXDELTA) {              // Pr:209-224
+        const double x = a.Xg[(int64_t)lib * a.G + g];
+        const double gl = a.gl[g];
+        v0 += xg_lik_onelib(H, x, y, v, gl, a.alpha_prop[lib], in_spike, f & F_ALLZERO) -
+              xg_lik_onelib(H, x, y, v, gl, H.alpha[lib], in_spike, f & F_ALLZERO);
+      } else {                                       // RED_LNL, U:70-75
+        v0 += in_spike ? xg_lik_inspike(H, f & F_ALLZERO) : xg_lik_out(H, a.Xg + g, a.G, y, v, a.gl[g]);
+      }
+    }
+  }
+  const double s0 = block_sum<BLOCK>(v0, red);
+  const double s1 = block_sum<BLOCK>(v1, red);
+  if (threadIdx.x == 0) {
+    double *p = a.partials + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 2;
+    p[0] = s0; p[1] = s1;
+  }
+}
+
+// partials [ny][nblk][nval] -> out [ny][nval], fixed summation order
+__global__ void __launch_bounds__(BLOCK) k_reduce_final(const double *partials, int nblk, int nval, double *out) {
+  __shared__ double red[BLOCK / 32];
+  const int y = blockIdx.x;
+  for (int s = 0; s < nval; ++s) {
+    double v = 0;
+    for (int b = threadIdx.x; b < nblk; b += BLOCK) v += partials[((int64_t)y * nblk + b) * nval + s];
+    const double t = block_sum<BLOCK>(v, red);
+    if (threadIdx.x == 0) out[(int64_t)y * nval + s] = t;
+  }
+}
+
+constexpr int NSTAT_FIXED = 10;
+constexpr int MAX_NSTAT = 3 * (ZZ_MAX_COMP + 1) + NSTAT_FIXED;
+
+struct StatArgs {
+  int64_t G; int K;
+  const double *Yg, *vg, *xglik, *vgprob;  // base pointers, chain = blockIdx.y
+  const uint16_t *flags;
+  double *partials;                         // [C][nblk][nstat]
+};
+
+// sufficient statistics for the hyper moves (layout documented at zz_suffstats in the header)
+__global__ void __launch_bounds__(BLOCK) k_suffstats(const StatArgs a) {
+  __shared__ double red[BLOCK / 32];
+  const int chain = blockIdx.y, K1 = a.K + 1, nstat = 3 * K1 + NSTAT_FIXED;
+  double cn[ZZ_MAX_COMP + 1], cy[ZZ_MAX_COMP + 1], cy2[ZZ_MAX_COMP + 1], fx[NSTAT_FIXED];
+#pragma unroll
+  for (int c = 0; c <= ZZ_MAX_COMP; ++c) { cn[c] = 0; cy[c] = 0; cy2[c] = 0; }
+#pragma unroll
+  for (int j = 0; j < NSTAT_FIXED; ++j) fx[j] = 0;
+  for (int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x; g < a.G; g += (int64_t)gridDim.x * BLOCK) {
+    const int64_t i = (int64_t)chain * a.G + g;
+    const double y = a.Yg[i], v = a.vg[i];
+    const uint32_t f = a.flags[i];
+    const bool act = f & F_ACTIVE, sp = f & F_INSPIKE;
+    const int comp = act ? flag_k(f) : 0;                          // Pr:415 all_allocations
+    const bool use_y = act || !sp;
+#pragma unroll
+    for (int c = 0; c <= ZZ_MAX_COMP; ++c) {
+      if (c == comp) { cn[c] += 1; if (use_y) { cy[c] += y; cy2[c] += y * y; } }
+    }
+    fx[0] += sp ? 1.0 : 0.0;
+    if (!sp) {
+      const double z = log(v);
+      fx[1] += 1; fx[2] += z; fx[3] += z * z; fx[4] += y; fx[5] += y * y; fx[6] += y * z;
+      fx[8] += a.vgprob[i];
+    }
+    fx[7] += a.xglik[i];
+    if (!isfinite(y) || !isfinite(v)) fx[9] += 1;
+  }
+  double *p = a.partials + ((int64_t)chain * gridDim.x + blockIdx.x) * nstat;
+#pragma unroll
+  for (int c = 0; c <= ZZ_MAX_COMP; ++c) {
+    if (c < K1) {
+      const double t0 = block_sum<BLOCK>(cn[c], red), t1 = block_sum<BLOCK>(cy[c], red), t2 = block_sum<BLOCK>(cy2[c], red);
+      if (threadIdx.x == 0) { p[c] = t0; p[K1 + c] = t1; p[2 * K1 + c] = t2; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NSTAT_FIXED; ++j) {
+    const double t = block_sum<BLOCK>(fx[j], red);
+    if (threadIdx.x == 0) p[3 * K1 + j] = t;
+  }
+}
+
+// accepted mhP_x with R > 2: XgLikelihood += ll_lib(alpha_new) - ll_lib(alpha_old), Pr:213-215, 239
+__global__ void __launch_bounds__(BLOCK) k_px_commit(int64_t G, int lib, double alpha_new, const double *Xg, const double *gl,
+                                                      const double *Yg, const double *vg, const uint16_t *flags,
+                                                      const zz_hyper *hyper, double *xglik) {
+  __shared__ HyperS H;
+  load_hyper(H, hyper);
+  const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (g >= G) return;
+  const uint32_t f = flags[g];
+  const double x = Xg[(int64_t)lib * G + g];
+  xglik[g] = xglik[g] + xg_lik_onelib(H, x, Yg[g], vg[g], gl[g], alpha_new, f & F_INSPIKE, f & F_ALLZERO) -
+             xg_lik_onelib(H, x, Yg[g], vg[g], gl[g], H.alpha[lib], f & F_INSPIKE, f & F_ALLZERO);
+}
+
+// allocation_trace += one-hot(allocation), M:194-199
+__global__ void __launch_bounds__(BLOCK) k_alloc_trace(int64_t G, int K, const uint16_t *flags, uint32_t *trace) {
+  const int chain = blockIdx.y;
+  const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (g >= G) return;
+  const uint32_t f = flags[(int64_t)chain * G + g];
+  const int comp = (f & F_ACTIVE) ? flag_k(f) : 0;
+  trace[((int64_t)chain * (K + 1) + comp) * G + g] += 1u;
+}
+
+// x_tune on the per-gene windows, U:161-181 with the clamps of U:202-206
+__device__ __forceinline__ double x_tune(double wsum, double t, double target, double lo, double hi) {
+  const double pjump = wsum / 100;
+  double nt = t * (tan(PI_D * pjump / 2) / tan(PI_D * target / 2));
+  if (nt < lo) nt = lo;
+  if (nt > hi) nt = hi;
+  return nt;
+}
+__global__ void __launch_bounds__(BLOCK) k_tune(int64_t n, double target, const ulonglong2 *win_y, const ulonglong2 *win_v, double *ty, double *tv) {
+  const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n) return;
+  tv[i] = x_tune(window_sum(win_v[i]), tv[i], target, 0.0001, 10);
+  ty[i] = x_tune(window_sum(win_y[i]), ty[i], target, 0.0001, 10);
+}
+__global__ void __launch_bounds__(BLOCK) k_window_init(int64_t n, ulonglong2 *win_y, ulonglong2 *win_v) {
+  const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n) return;
+  const ulonglong2 w = make_ulonglong2((1ULL << 23) - 1, 0ULL);   // c(rep(0,77), rep(1,23)), I:460,466
+  win_y[i] = w; win_v[i] = w;
+}
+__global__ void __launch_bounds__(BLOCK) k_window_sums(int64_t n, const ulonglong2 *win_y, const ulonglong2 *win_v, int32_t *sy, int32_t *sv) {
+  const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n) return;
+  sy[i] = window_sum(win_y[i]); sv[i] = window_sum(win_v[i]);
+}
+
+// int32 R-style allocation vectors <-> packed flag word
+__global__ void __launch_bounds__(BLOCK) k_pack_flags(int64_t n, const int32_t *ai, const int32_t *within, const int32_t *spike, uint16_t *flags) {
+  const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n) return;
+  uint32_t f = flags[i];
+  if (ai) f = (f & ~F_ACTIVE) | (ai[i] ? F_ACTIVE : 0u);
+  if (within) f = flag_set_k(f, within[i] < 1 ? 1 : within[i]);
+  if (spike) f = (f & ~F_INSPIKE) | (spike[i] ? F_INSPIKE : 0u);
+  flags[i] = (uint16_t)f;
+}
+__global__ void __launch_bounds__(BLOCK) k_unpack_flags(int64_t n, const uint16_t *flags, int32_t *ai, int32_t *within, int32_t *spike) {
+  const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t f = flags[i];
+  if (ai) ai[i] = (f & F_ACTIVE) ? 1 : 0;
+  if (within) within[i] = flag_k(f);
+  if (spike) spike[i] = (f & F_INSPIKE) ? 1 : 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ handle
+
+struct zz_handle {
+  zz_config cfg;
+  int64_t G; int C, R, K;
+  cudaStream_t stream; bool own_stream;
+  std::string err; bool sticky;
+  uint64_t launches;
+  // device
+  double *Xg, *gl, *Yg, *vg, *xglik, *vgprob, *ty, *tv;
+  uint16_t *flags;
+  ulonglong2 *win_y, *win_v;
+  uint32_t *trace;
+  zz_hyper *hyper;
+  double *partials, *red_out, *scratch;   // scratch: 9*C*G doubles for draw tables / eval output
+  uint8_t *dec;                            // 4*C*G
+  int32_t *iscratch;                       // 3*C*G
+  int *nan_flag;
+  bool have_data;
+  std::vector<zz_hyper> hyper_host;
+  double *pinned;                          // small pinned staging for reduction results
+};
+
+namespace {
+
+int fail(zz_handle *h, int code, const std::string &msg) {
+  if (h) { h->err = msg; if (code == ZZ_ERR_CUDA) h->sticky = true; }
+  return code;
+}
+#define ZZ_CUDA(h, expr)                                                                         \
+  do {                                                                                           \
+    cudaError_t e_ = (expr);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail(h, ZZ_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));           \
+  } while (0)
+#define ZZ_CHECK(h)                                                                              \
+  do {                                                                                           \
+    if (!(h)) return ZZ_ERR_INVALID;                                                             \
+    if ((h)->sticky) return ZZ_ERR_CUDA;                                                         \
+    ZZ_CUDA(h, cudaSetDevice((h)->cfg.device));                                                  \
+  } while (0)
+#define ZZ_LAUNCHED(h)                                                                           \
+  do { (h)->launches++; ZZ_CUDA(h, cudaGetLastError()); } while (0)
+
+inline dim3 gene_grid(const zz_handle *h, int64_t n, int ny = 1) { return dim3((unsigned)((n + BLOCK - 1) / BLOCK), (unsigned)ny); }
+inline int red_blocks(int64_t n) { int64_t b = (n + BLOCK - 1) / BLOCK; return (int)(b < RED_BLOCKS ? (b < 1 ? 1 : b) : RED_BLOCKS); }
+
+int chain_ok(zz_handle *h, int chain) {
+  if (chain < 0 || chain >= h->C) return fail(h, ZZ_ERR_INVALID, "chain index out of range");
+  return ZZ_OK;
+}
+
+template <class T> int up(zz_handle *h, T *dst, const T *src, int64_t n) {
+  if (!src) return ZZ_OK;
+  ZZ_CUDA(h, cudaMemcpyAsync(dst, src, sizeof(T) * n, cudaMemcpyHostToDevice, h->stream));
+  return ZZ_OK;
+}
+template <class T> int down(zz_handle *h, T *dst, const T *src, int64_t n) {
+  if (!dst) return ZZ_OK;
+  ZZ_CUDA(h, cudaMemcpyAsync(dst, src, sizeof(T) * n, cudaMemcpyDeviceToHost, h->stream));
+  return ZZ_OK;
+}
+
+int launch_sweep(zz_handle *h, uint64_t step, int tune, uint32_t moves, const double *const draws_dev[9], uint8_t *const dec_dev[4],
+                 int64_t g_begin, int64_t g_end) {
+  SweepArgs a;
+  a.G = h->G; a.g_begin = g_begin; a.g_end = g_end; a.gene_offset = h->cfg.gene_offset;
+  a.C = h->C; a.R = h->R; a.K = h->K; a.tune = tune; a.moves = moves; a.seed = h->cfg.seed; a.step = step;
+  a.Xg = h->Xg; a.gl = h->gl; a.Yg = h->Yg; a.vg = h->vg; a.xglik = h->xglik; a.vgprob = h->vgprob; a.ty = h->ty; a.tv = h->tv;
+  a.flags = h->flags; a.win_y = h->win_y; a.win_v = h->win_v; a.hyper = h->hyper;
+  for (int i = 0; i < 9; ++i) a.draws[i] = draws_dev ? draws_dev[i] : nullptr;
+  for (int i = 0; i < 4; ++i) a.dec[i] = dec_dev ? dec_dev[i] : nullptr;
+  a.nan_flag = h->nan_flag;
+  if (g_end <= g_begin) return ZZ_OK;
+  k_sweep<<<gene_grid(h, g_end - g_begin, h->C), BLOCK, 0, h->stream>>>(a);
+  ZZ_LAUNCHED(h);
+  return ZZ_OK;
+}
+
+// shared implementation of the five move entry points and zz_sweep
+int run_moves(zz_handle *h, uint64_t step, int tune, uint32_t moves, const double *draws, const int *draw_slots, int ndraw,
+              uint8_t *decisions, const int *dec_slots, int ndec) {
+  ZZ_CHECK(h);
+  if (!h->have_data) return fail(h, ZZ_ERR_STATE, "zz_upload_data has not been called");
+  const int64_t CG = (int64_t)h->C * h->G;
+  const double *dd[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint8_t *de[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (draws) {
+    ZZ_CUDA(h, cudaMemcpyAsync(h->scratch, draws, sizeof(double) * ndraw * CG, cudaMemcpyHostToDevice, h->stream));
+    for (int j = 0; j < ndraw; ++j) dd[draw_slots[j]] = h->scratch + (int64_t)j * CG;
+  }
+  if (decisions) for (int j = 0; j < ndec; ++j) de[dec_slots[j]] = h->dec + (int64_t)j * CG;
+  int rc = launch_sweep(h, step, tune, moves, dd, de, 0, h->G);
+  if (rc) return rc;
+  if (decisions) {
+    ZZ_CUDA(h, cudaMemcpyAsync(decisions, h->dec, (size_t)ndec * CG, cudaMemcpyDeviceToHost, h->stream));
+    ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  } else if (draws) {
+    ZZ_CUDA(h, cudaStreamSynchronize(h->stream));  // the caller may free `draws` on return
+  }
+  return ZZ_OK;
+}
+
+int reduce_to_host(zz_handle *h, RedArgs &a, int ny, double *out, int nout_per_y) {
+  const int nblk = red_blocks(h->G);
+  a.partials = h->partials;
+  k_reduce<<<dim3(nblk, ny), BLOCK, 0, h->stream>>>(a);
+  ZZ_LAUNCHED(h);
+  k_reduce_final<<<ny, BLOCK, 0, h->stream>>>(h->partials, nblk, 2, h->red_out);
+  ZZ_LAUNCHED(h);
+  ZZ_CUDA(h, cudaMemcpyAsync(h->pinned, h->red_out, sizeof(double) * 2 * ny, cudaMemcpyDeviceToHost, h->stream));
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int y = 0; y < ny; ++y)
+    for (int j = 0; j < nout_per_y; ++j) out[y * nout_per_y + j] = h->pinned[y * 2 + j];
+  return ZZ_OK;
+}
+
+void fill_red(zz_handle *h, RedArgs &a, int chain, int op) {
+  const int64_t off = (int64_t)chain * h->G;
+  memset(&a, 0, sizeof a);
+  a.G = h->G; a.op = op; a.chain = chain;
+  a.Xg = h->Xg; a.gl = h->gl; a.Yg = h->Yg + off; a.vg = h->vg + off; a.xglik = h->xglik + off; a.vgprob = h->vgprob + off;
+  a.flags = h->flags + off; a.hyper = h->hyper + chain;
+}
+
+int launch_eval(zz_handle *h, int which, int chain /* -1 = all chains */, double *out0, double *out1) {
+  EvalArgs a;
+  const int64_t off = chain < 0 ? 0 : (int64_t)chain * h->G;
+  a.G = h->G; a.which = which; a.Xg = h->Xg; a.gl = h->gl; a.Yg = h->Yg + off; a.vg = h->vg + off; a.flags = h->flags + off;
+  a.hyper = h->hyper + (chain < 0 ? 0 : chain); a.out0 = out0; a.out1 = out1;
+  k_eval<<<gene_grid(h, h->G, chain < 0 ? h->C : 1), BLOCK, 0, h->stream>>>(a);
+  ZZ_LAUNCHED(h);
+  return ZZ_OK;
+}
+
+int eval_to_host(zz_handle *h, int which, int chain, double *out) {
+  ZZ_CHECK(h);
+  if (int rc = chain_ok(h, chain)) return rc;
+  if (!out) return fail(h, ZZ_ERR_INVALID, "out is NULL");
+  if (int rc = launch_eval(h, which, chain, h->scratch, nullptr)) return rc;
+  ZZ_CUDA(h, cudaMemcpyAsync(out, h->scratch, sizeof(double) * h->G, cudaMemcpyDeviceToHost, h->stream));
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ZZ_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ C ABI
+
+extern "C" {
+
+int zz_create(const zz_config *cfg, zz_handle **out) {
+  if (!cfg || !out) return ZZ_ERR_INVALID;
+  *out = nullptr;
+  if (cfg->num_genes < 1 || cfg->num_libraries < 2 || cfg->num_libraries > ZZ_MAX_LIBS || cfg->num_active_components < 1 ||
+      cfg->num_active_components > ZZ_MAX_COMP || cfg->num_chains < 1 || cfg->num_chains > (1 << 20) ||
+      cfg->gene_offset < 0 || cfg->gene_offset + cfg->num_genes > 0xFFFFFFFFLL)
+    return ZZ_ERR_INVALID;
+  zz_handle *h = new (std::nothrow) zz_handle();
+  if (!h) return ZZ_ERR_NOMEM;
+  h->cfg = *cfg; h->G = cfg->num_genes; h->C = cfg->num_chains; h->R = cfg->num_libraries; h->K = cfg->num_active_components;
+  h->sticky = false; h->launches = 0; h->have_data = false; h->own_stream = false; h->stream = nullptr;
+  *out = h;  // returned even on failure so the caller can read zz_last_error and must zz_destroy
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev < 1)
+    return fail(h, ZZ_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(h, ZZ_ERR_INVALID, "device ordinal out of range");
+  ZZ_CUDA(h, cudaSetDevice(cfg->device));
+  ZZ_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->own_stream = true;
+  const int64_t G = h->G, CG = (int64_t)h->C * G;
+  const int nstat = 3 * (h->K + 1) + NSTAT_FIXED;
+  ZZ_CUDA(h, cudaMalloc(&h->Xg, sizeof(double) * G * h->R));
+  ZZ_CUDA(h, cudaMalloc(&h->gl, sizeof(double) * G));
+  double **d8[] = {&h->Yg, &h->vg, &h->xglik, &h->vgprob, &h->ty, &h->tv};
+  for (auto p : d8) { ZZ_CUDA(h, cudaMalloc(p, sizeof(double) * CG)); ZZ_CUDA(h, cudaMemsetAsync(*p, 0, sizeof(double) * CG, h->stream)); }
+  ZZ_CUDA(h, cudaMalloc(&h->flags, sizeof(uint16_t) * CG));
+  ZZ_CUDA(h, cudaMemsetAsync(h->flags, 0, sizeof(uint16_t) * CG, h->stream));
+  ZZ_CUDA(h, cudaMalloc(&h->win_y, sizeof(ulonglong2) * CG));
+  ZZ_CUDA(h, cudaMalloc(&h->win_v, sizeof(ulonglong2) * CG));
+  ZZ_CUDA(h, cudaMalloc(&h->trace, sizeof(uint32_t) * CG * (h->K + 1)));
+  ZZ_CUDA(h, cudaMemsetAsync(h->trace, 0, sizeof(uint32_t) * CG * (h->K + 1), h->stream));
+  ZZ_CUDA(h, cudaMalloc(&h->hyper, sizeof(zz_hyper) * h->C));
+  ZZ_CUDA(h, cudaMemsetAsync(h->hyper, 0, sizeof(zz_hyper) * h->C, h->stream));
+  const size_t npart = (size_t)RED_BLOCKS * (size_t)(h->C > ZZ_MAX_LIBS ? h->C : ZZ_MAX_LIBS) * MAX_NSTAT;
+  ZZ_CUDA(h, cudaMalloc(&h->partials, sizeof(double) * npart));
+  ZZ_CUDA(h, cudaMalloc(&h->red_out, sizeof(double) * (size_t)(h->C > ZZ_MAX_LIBS ? h->C : ZZ_MAX_LIBS) * MAX_NSTAT));
+  ZZ_CUDA(h, cudaMalloc(&h->scratch, sizeof(double) * 9 * CG));
+  ZZ_CUDA(h, cudaMalloc(&h->dec, (size_t)4 * CG));
+  ZZ_CUDA(h, cudaMalloc(&h->iscratch, sizeof(int32_t) * 3 * CG));
+  ZZ_CUDA(h, cudaMalloc(&h->nan_flag, sizeof(int)));
+  ZZ_CUDA(h, cudaMemsetAsync(h->nan_flag, 0, sizeof(int), h->stream));
+  ZZ_CUDA(h, cudaMallocHost(&h->pinned, sizeof(double) * (size_t)(h->C > ZZ_MAX_LIBS ? h->C : ZZ_MAX_LIBS) * MAX_NSTAT));
+  (void)nstat;
+  h->hyper_host.assign(h->C, zz_hyper());
+  k_window_init<<<gene_grid(h, CG), BLOCK, 0, h->stream>>>(CG, h->win_y, h->win_v);
+  ZZ_LAUNCHED(h);
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ZZ_OK;
+}
+
+void zz_destroy(zz_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  void *ptrs[] = {h->Xg, h->gl, h->Yg, h->vg, h->xglik, h->vgprob, h->ty, h->tv, h->flags, h->win_y, h->win_v, h->trace,
+                  h->hyper, h->partials, h->red_out, h->scratch, h->dec, h->iscratch, h->nan_flag};
+  for (void *p : ptrs) if (p) cudaFree(p);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char *zz_last_error(const zz_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+int zz_set_stream(zz_handle *h, void *cuda_stream) {
+  ZZ_CHECK(h);
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->own_stream && h->stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+  h->stream = (cudaStream_t)cuda_stream;
+  return ZZ_OK;
+}
+
+int zz_sync(zz_handle *h) {
+  ZZ_CHECK(h);
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ZZ_OK;
+}
+
+uint64_t zz_launch_count(const zz_handle *h) { return h ? h->launches : 0; }
+
+int zz_upload_data(zz_handle *h, const double *Xg, const double *gene_lengths) {
+  ZZ_CHECK(h);
+  if (!Xg || !gene_lengths) return fail(h, ZZ_ERR_INVALID, "Xg / gene_lengths is NULL");
+  const int64_t G = h->G;
+  ZZ_CUDA(h, cudaMemcpyAsync(h->Xg, Xg, sizeof(double) * G * h->R, cudaMemcpyHostToDevice, h->stream));
+  ZZ_CUDA(h, cudaMemcpyAsync(h->gl, gene_lengths, sizeof(double) * G, cudaMemcpyHostToDevice, h->stream));
+  // no_detect_spike (I:416-417): every library -Inf
+  std::vector<uint16_t> f((size_t)h->C * G);
+  ZZ_CUDA(h, cudaMemcpyAsync(f.data(), h->flags, sizeof(uint16_t) * f.size(), cudaMemcpyDeviceToHost, h->stream));
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int64_t g = 0; g < G; ++g) {
+    bool all = true;
+    for (int r = 0; r < h->R && all; ++r) all = (Xg[(int64_t)r * G + g] == -INFINITY);
+    for (int c = 0; c < h->C; ++c) {
+      uint16_t &w = f[(size_t)c * G + g];
+      w = (uint16_t)((w & ~F_ALLZERO) | (all ? F_ALLZERO : 0u));
+    }
+  }
+  ZZ_CUDA(h, cudaMemcpyAsync(h->flags, f.data(), sizeof(uint16_t) * f.size(), cudaMemcpyHostToDevice, h->stream));
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->have_data = true;
+  return ZZ_OK;
+}
+
+int zz_set_state(zz_handle *h, int chain, const double *Yg, const double *variance_g, const int32_t *ai, const int32_t *within,
+                 const int32_t *spike, const double *XgLikelihood, const double *variance_g_probability, const double *ty,
+                 const double *tv, const int32_t *pinned_active) {
+  ZZ_CHECK(h);
+  if (int rc = chain_ok(h, chain)) return rc;
+  const int64_t G = h->G, off = (int64_t)chain * G;
+  int rc;
+  if ((rc = up(h, h->Yg + off, Yg, G)) || (rc = up(h, h->vg + off, variance_g, G)) || (rc = up(h, h->xglik + off, XgLikelihood, G)) ||
+      (rc = up(h, h->vgprob + off, variance_g_probability, G)) || (rc = up(h, h->ty + off, ty, G)) || (rc = up(h, h->tv + off, tv, G)))
+    return rc;
+  if (ai || within || spike) {
+    int32_t *d_ai = h->iscratch, *d_w = h->iscratch + G, *d_s = h->iscratch + 2 * G;
+    if ((rc = up(h, d_ai, ai, G)) || (rc = up(h, d_w, within, G)) || (rc = up(h, d_s, spike, G))) return rc;
+    k_pack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, ai ? d_ai : nullptr, within ? d_w : nullptr, spike ? d_s : nullptr, h->flags + off);
+    ZZ_LAUNCHED(h);
+  }
+  if (pinned_active) {
+    std::vector<uint16_t> f(G);
+    ZZ_CUDA(h, cudaMemcpyAsync(f.data(), h->flags + off, sizeof(uint16_t) * G, cudaMemcpyDeviceToHost, h->stream));
+    ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int64_t g = 0; g < G; ++g) f[g] = (uint16_t)((f[g] & ~F_PINNED) | (pinned_active[g] ? F_PINNED : 0u));
+    ZZ_CUDA(h, cudaMemcpyAsync(h->flags + off, f.data(), sizeof(uint16_t) * G, cudaMemcpyHostToDevice, h->stream));
+  }
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ZZ_OK;
+}
+
+int zz_get_state(zz_handle *h, int chain, double *Yg, double *variance_g, int32_t *ai, int32_t *within, int32_t *spike,
+                 double *XgLikelihood, double *variance_g_probability, double *ty, double *tv) {
+  ZZ_CHECK(h);
+  if (int rc = chain_ok(h, chain)) return rc;
+  const int64_t G = h->G, off = (int64_t)chain * G;
+  int rc;
+  if ((rc = down(h, Yg, h->Yg + off, G)) || (rc = down(h, variance_g, h->vg + off, G)) || (rc = down(h, XgLikelihood, h->xglik + off, G)) ||
+      (rc = down(h, variance_g_probability, h->vgprob + off, G)) || (rc = down(h, ty, h->ty + off, G)) || (rc = down(h, tv, h->tv + off, G)))
+    return rc;
+  if (ai || within || spike) {
+    int32_t *d_ai = h->iscratch, *d_w = h->iscratch + G, *d_s = h->iscratch + 2 * G;
+    k_unpack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, h->flags + off, d_ai, d_w, d_s);
+    ZZ_LAUNCHED(h);
+    if ((rc = down(h, ai, d_ai, G)) || (rc = down(h, within, d_w, G)) || (rc = down(h, spike, d_s, G))) return rc;
+  }
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ZZ_OK;
+}
+
+int zz_set_hyper(zz_handle *h, int chain, const zz_hyper *hy) {
+  ZZ_CHECK(h);
+  if (int rc = chain_ok(h, chain)) return rc;
+  if (!hy) return fail(h, ZZ_ERR_INVALID, "hyper is NULL");
+  if (hy->num_libraries != h->R || hy->num_active_components != h->K)
+    return fail(h, ZZ_ERR_INVALID, "hyper dimensions do not match the handle");
+  h->hyper_host[chain] = *hy;
+  ZZ_CUDA(h, cudaMemcpyAsync(h->hyper + chain, &h->hyper_host[chain], sizeof(zz_hyper), cudaMemcpyHostToDevice, h->stream));
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ZZ_OK;
+}
+
+int zz_get_hyper(zz_handle *h, int chain, zz_hyper *hy) {
+  ZZ_CHECK(h);
+  if (int rc = chain_ok(h, chain)) return rc;
+  if (!hy) return fail(h, ZZ_ERR_INVALID, "hyper is NULL");
+  ZZ_CUDA(h, cudaMemcpyAsync(hy, h->hyper + chain, sizeof(zz_hyper), cudaMemcpyDeviceToHost, h->stream));
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ZZ_OK;
+}
+
+int zz_refresh_caches(zz_handle *h) {
+  ZZ_CHECK(h);
+  if (!h->have_data) return fail(h, ZZ_ERR_STATE, "zz_upload_data has not been called");
+  return launch_eval(h, EVAL_REFRESH, -1, h->xglik, h->vgprob);
+}
+
+int zz_reset_windows(zz_handle *h) {
+  ZZ_CHECK(h);
+  const int64_t CG = (int64_t)h->C * h->G;
+  k_window_init<<<gene_grid(h, CG), BLOCK, 0, h->stream>>>(CG, h->win_y, h->win_v);
+  ZZ_LAUNCHED(h);
+  return ZZ_OK;
+}
+
+int zz_get_window_sums(zz_handle *h, int chain, int32_t *yg_sum, int32_t *vg_sum) {
+  ZZ_CHECK(h);
+  if (int rc = chain_ok(h, chain)) return rc;
+  const int64_t G = h->G, off = (int64_t)chain * G;
+  k_window_sums<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, h->win_y + off, h->win_v + off, h->iscratch, h->iscratch + G);
+  ZZ_LAUNCHED(h);
+  int rc;
+  if ((rc = down(h, yg_sum, h->iscratch, G)) || (rc = down(h, vg_sum, h->iscratch + G, G))) return rc;
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ZZ_OK;
+}
+
+int zz_eval_xg_loglik(zz_handle *h, int chain, double *out) { return eval_to_host(h, EVAL_XGLIK, chain, out); }
+int zz_eval_varg_logprior(zz_handle *h, int chain, double *out) { return eval_to_host(h, EVAL_VGPRIOR, chain, out); }
+int zz_eval_level2_loglik(zz_handle *h, int chain, double *out) { return eval_to_host(h, EVAL_LEVEL2, chain, out); }
+
+int zz_mh_yg(zz_handle *h, uint64_t step, int tune, const double *draws, uint8_t *decisions) {
+  static const int ds[] = {0, 1}, es[] = {0};
+  return run_moves(h, step, tune, ZZ_MOVE_YG, draws, ds, 2, decisions, es, 1);
+}
+int zz_mh_variance_g(zz_handle *h, uint64_t step, int tune, const double *draws, uint8_t *decisions) {
+  static const int ds[] = {2, 3}, es[] = {1};
+  return run_moves(h, step, tune, ZZ_MOVE_VARIANCE_G, draws, ds, 2, decisions, es, 1);
+}
+int zz_gibbs_alloc(zz_handle *h, uint64_t step, const double *draws, uint8_t *decisions) {
+  static const int ds[] = {4, 5}, es[] = {2};
+  return run_moves(h, step, 0, ZZ_MOVE_ALLOC, draws, ds, 2, decisions, es, 1);
+}
+int zz_gibbs_alloc_within(zz_handle *h, uint64_t step, const double *draws, uint8_t *decisions) {
+  static const int ds[] = {5}, es[] = {2};
+  return run_moves(h, step, 0, ZZ_MOVE_ALLOC_WITHIN, draws, ds, 1, decisions, es, 1);
+}
+int zz_mh_spike_alloc(zz_handle *h, uint64_t step, const double *draws, uint8_t *decisions) {
+  static const int ds[] = {6, 7, 8}, es[] = {3};
+  return run_moves(h, step, 0, ZZ_MOVE_SPIKE, draws, ds, 3, decisions, es, 1);
+}
+int zz_sweep(zz_handle *h, uint64_t step, int tune, uint32_t moves, const double *draws, uint8_t *decisions) {
+  static const int ds[] = {0, 1, 2, 3, 4, 5, 6, 7, 8}, es[] = {0, 1, 2, 3};
+  if (moves == 0) moves = ZZ_MOVE_FUSED;
+  return run_moves(h, step, tune, moves, draws, ds, 9, decisions, es, 4);
+}
+
+int zz_philox_draws(zz_handle *h, uint64_t step, int slot, double *out) {
+  ZZ_CHECK(h);
+  int n = 0;
+  switch (slot) {
+    case ZZ_SLOT_YG: case ZZ_SLOT_VARIANCE_G: case ZZ_SLOT_ALLOC: n = 2; break;
+    case ZZ_SLOT_ALLOC_WITHIN: n = 1; break;
+    case ZZ_SLOT_SPIKE: n = 3; break;
+    default: return fail(h, ZZ_ERR_INVALID, "unknown move slot");
+  }
+  if (!out) return fail(h, ZZ_ERR_INVALID, "out is NULL");
+  const int64_t CG = (int64_t)h->C * h->G;
+  k_draws<<<gene_grid(h, h->G, h->C), BLOCK, 0, h->stream>>>(h->G, h->cfg.gene_offset, h->C, h->cfg.seed, step, slot, h->scratch);
+  ZZ_LAUNCHED(h);
+  ZZ_CUDA(h, cudaMemcpyAsync(out, h->scratch, sizeof(double) * n * CG, cudaMemcpyDeviceToHost, h->stream));
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ZZ_OK;
+}
+
+int zz_suffstats_len(int K) { return 3 * (K + 1) + NSTAT_FIXED; }
+
+int zz_suffstats_dev(zz_handle *h, double *out_dev) {
+  ZZ_CHECK(h);
+  if (!out_dev) return fail(h, ZZ_ERR_INVALID, "out_dev is NULL");
+  const int nblk = red_blocks(h->G), nstat = zz_suffstats_len(h->K);
+  StatArgs a;
+  a.G = h->G; a.K = h->K; a.Yg = h->Yg; a.vg = h->vg; a.xglik = h->xglik; a.vgprob = h->vgprob; a.flags = h->flags; a.partials = h->partials;
+  k_suffstats<<<dim3(nblk, h->C), BLOCK, 0, h->stream>>>(a);
+  ZZ_LAUNCHED(h);
+  k_reduce_final<<<h->C, BLOCK, 0, h->stream>>>(h->partials, nblk, nstat, out_dev);
+  ZZ_LAUNCHED(h);
+  return ZZ_OK;
+}
+
+int zz_suffstats(zz_handle *h, double *out) {
+  ZZ_CHECK(h);
+  if (!out) return fail(h, ZZ_ERR_INVALID, "out is NULL");
+  if (int rc = zz_suffstats_dev(h, h->red_out)) return rc;
+  const int n = zz_suffstats_len(h->K) * h->C;
+  ZZ_CUDA(h, cudaMemcpyAsync(h->pinned, h->red_out, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  memcpy(out, h->pinned, sizeof(double) * n);
+  return ZZ_OK;
+}
+
+int zz_varg_hyper_sum(zz_handle *h, int chain, double s0, double s1, double tau, double *out2) {
+  ZZ_CHECK(h);
+  if (int rc = chain_ok(h, chain)) return rc;
+  if (!out2) return fail(h, ZZ_ERR_INVALID, "out is NULL");
+  RedArgs a; fill_red(h, a, chain, RED_VARG_HYPER);
+  a.s0 = s0; a.s1 = s1; a.tau = tau;
+  return reduce_to_host(h, a, 1, out2, 2);
+}
+
+int zz_commit_varg_hyper(zz_handle *h, int chain) {
+  ZZ_CHECK(h);
+  if (int rc = chain_ok(h, chain)) return rc;
+  return launch_eval(h, EVAL_COMMIT_VG, chain, nullptr, h->vgprob + (int64_t)chain * h->G);
+}
+
+int zz_level2_sums(zz_handle *h, int chain, double im, double iv, const double *am, const double *av, double *out2) {
+  ZZ_CHECK(h);
+  if (int rc = chain_ok(h, chain)) return rc;
+  if (!am || !av || !out2) return fail(h, ZZ_ERR_INVALID, "NULL argument");
+  RedArgs a; fill_red(h, a, chain, RED_LEVEL2);
+  a.im = im; a.iv = iv;
+  for (int k = 0; k < h->K; ++k) { a.am[k] = am[k]; a.av[k] = av[k]; }
+  for (int k = h->K; k < ZZ_MAX_COMP; ++k) { a.am[k] = 0; a.av[k] = 1; }
+  return reduce_to_host(h, a, 1, out2, 2);
+}
+
+int zz_px_delta(zz_handle *h, int chain, const double *alpha_prop, const uint8_t *lib_mask, double *out) {
+  ZZ_CHECK(h);
+  if (int rc = chain_ok(h, chain)) return rc;
+  if (!alpha_prop || !out) return fail(h, ZZ_ERR_INVALID, "NULL argument");
+  RedArgs a; fill_red(h, a, chain, RED_PXDELTA);
+  for (int r = 0; r < h->R; ++r) { a.alpha_prop[r] = alpha_prop[r]; a.lib_mask[r] = lib_mask ? lib_mask[r] : 1; }
+  return reduce_to_host(h, a, h->R, out, 1);
+}
+
+int zz_px_commit(zz_handle *h, int chain, int lib, double alpha_new) {
+  ZZ_CHECK(h);
+  if (int rc = chain_ok(h, chain)) return rc;
+  if (lib < 0 || lib >= h->R) return fail(h, ZZ_ERR_INVALID, "library index out of range");
+  const int64_t off = (int64_t)chain * h->G;
+  if (h->R > 2) {  // Pr:213-215
+    k_px_commit<<<gene_grid(h, h->G), BLOCK, 0, h->stream>>>(h->G, lib, alpha_new, h->Xg, h->gl, h->Yg + off, h->vg + off,
+                                                            h->flags + off, h->hyper + chain, h->xglik + off);
+    ZZ_LAUNCHED(h);
+  }
+  h->hyper_host[chain].alpha_r[lib] = alpha_new;
+  ZZ_CUDA(h, cudaMemcpyAsync(h->hyper + chain, &h->hyper_host[chain], sizeof(zz_hyper), cudaMemcpyHostToDevice, h->stream));
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->R <= 2) {  // Pr:219: full recompute with the proposed p_x
+    if (int rc = launch_eval(h, EVAL_XGLIK, chain, h->xglik + off, nullptr)) return rc;
+  }
+  return ZZ_OK;
+}
+
+int zz_lnl(zz_handle *h, int chain, double *out) {
+  ZZ_CHECK(h);
+  if (int rc = chain_ok(h, chain)) return rc;
+  if (!out) return fail(h, ZZ_ERR_INVALID, "out is NULL");
+  RedArgs a; fill_red(h, a, chain, RED_LNL);
+  return reduce_to_host(h, a, 1, out, 1);
+}
+
+int zz_reset_alloc_trace(zz_handle *h) {
+  ZZ_CHECK(h);
+  ZZ_CUDA(h, cudaMemsetAsync(h->trace, 0, sizeof(uint32_t) * (size_t)h->C * h->G * (h->K + 1), h->stream));
+  return ZZ_OK;
+}
+
+int zz_accumulate_alloc_trace(zz_handle *h) {
+  ZZ_CHECK(h);
+  k_alloc_trace<<<gene_grid(h, h->G, h->C), BLOCK, 0, h->stream>>>(h->G, h->K, h->flags, h->trace);
+  ZZ_LAUNCHED(h);
+  return ZZ_OK;
+}
+
+int zz_get_alloc_trace(zz_handle *h, int chain, uint32_t *out) {
+  ZZ_CHECK(h);
+  if (int rc = chain_ok(h, chain)) return rc;
+  if (!out) return fail(h, ZZ_ERR_INVALID, "out is NULL");
+  const size_t n = (size_t)h->G * (h->K + 1);
+  ZZ_CUDA(h, cudaMemcpyAsync(out, h->trace + (size_t)chain * n, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ZZ_OK;
+}
+
+int zz_tune(zz_handle *h, double target) {
+  ZZ_CHECK(h);
+  const int64_t CG = (int64_t)h->C * h->G;
+  k_tune<<<gene_grid(h, CG), BLOCK, 0, h->stream>>>(CG, target, h->win_y, h->win_v, h->ty, h->tv);
+  ZZ_LAUNCHED(h);
+  return ZZ_OK;
+}
+
+int zz_nan_flag(zz_handle *h, int *flag) {
+  ZZ_CHECK(h);
+  if (!flag) return fail(h, ZZ_ERR_INVALID, "flag is NULL");
+  ZZ_CUDA(h, cudaMemcpyAsync(flag, h->nan_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ZZ_OK;
+}
+
+int zz_sweep_host(zz_handle *h, uint64_t step, int tune, double *Yg, double *variance_g, int32_t *ai, int32_t *within,
+                  int32_t *spike, double *XgLikelihood, double *variance_g_probability, const double *ty, const double *tv,
+                  int64_t *h2d_bytes, int64_t *d2h_bytes) {
+  ZZ_CHECK(h);
+  if (!h->have_data) return fail(h, ZZ_ERR_STATE, "zz_upload_data has not been called");
+  if (!Yg || !variance_g || !ai || !within || !spike || !XgLikelihood || !variance_g_probability || !ty || !tv)
+    return fail(h, ZZ_ERR_INVALID, "NULL state pointer");
+  const int64_t G = h->G;
+  int32_t *d_ai = h->iscratch, *d_w = h->iscratch + G, *d_s = h->iscratch + 2 * G;
+  int rc;
+  if ((rc = up(h, h->Yg, Yg, G)) || (rc = up(h, h->vg, variance_g, G)) || (rc = up(h, h->xglik, XgLikelihood, G)) ||
+      (rc = up(h, h->vgprob, variance_g_probability, G)) || (rc = up(h, h->ty, ty, G)) || (rc = up(h, h->tv, tv, G)) ||
+      (rc = up(h, d_ai, (const int32_t *)ai, G)) || (rc = up(h, d_w, (const int32_t *)within, G)) || (rc = up(h, d_s, (const int32_t *)spike, G)))
+    return rc;
+  k_pack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, d_ai, d_w, d_s, h->flags);
+  ZZ_LAUNCHED(h);
+  if ((rc = launch_sweep(h, step, tune, ZZ_MOVE_FUSED, nullptr, nullptr, 0, G))) return rc;
+  k_unpack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, h->flags, d_ai, d_w, d_s);
+  ZZ_LAUNCHED(h);
+  if ((rc = down(h, Yg, h->Yg, G)) || (rc = down(h, variance_g, h->vg, G)) || (rc = down(h, XgLikelihood, h->xglik, G)) ||
+      (rc = down(h, variance_g_probability, h->vgprob, G)) || (rc = down(h, ai, d_ai, G)) || (rc = down(h, within, d_w, G)) ||
+      (rc = down(h, spike, d_s, G)))
+    return rc;
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h2d_bytes) *h2d_bytes = G * (6 * 8 + 3 * 4);
+  if (d2h_bytes) *d2h_bytes = G * (4 * 8 + 3 * 4);
+  return ZZ_OK;
+}
+
+}  // extern "C"
