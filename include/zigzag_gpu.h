@@ -51,6 +51,7 @@ extern "C" {
 #define ZZ_MOVE_ALLOC 4u
 #define ZZ_MOVE_ALLOC_WITHIN 8u
 #define ZZ_MOVE_SPIKE 16u
+#define ZZ_MOVE_REFERENCE_ORDER 32u /* zz_sweep: use the reference-operation-order kernel instead of the production one */
 #define ZZ_MOVE_FUSED (ZZ_MOVE_YG | ZZ_MOVE_VARIANCE_G | ZZ_MOVE_ALLOC | ZZ_MOVE_SPIKE)
 
 typedef struct zz_handle zz_handle;
@@ -122,8 +123,12 @@ int zz_gibbs_alloc(zz_handle *h, uint64_t step, const double *draws, uint8_t *de
 int zz_gibbs_alloc_within(zz_handle *h, uint64_t step, const double *draws, uint8_t *decisions);         /* gibbsAllocationWithinActive, Pr:363-410 */
 int zz_mh_spike_alloc(zz_handle *h, uint64_t step, const double *draws, uint8_t *decisions);             /* mhSpikeAllocation, Pr:528-638 */
 /* Fused systematic-scan sweep: for every gene mhYg -> mhVariance_g -> allocation (AI + within) -> mhSpikeAllocation with the
-   gene's state held in registers.  `moves` selects a subset (ZZ_MOVE_*).  draws: [9][C][G] = {z_yg,u_yg,u1_vg,u2_vg,u_ai,
-   u_within,zy_spike,zv_spike,u_spike} or NULL; decisions: [4][C][G] or NULL. */
+   gene's state held in registers.  `moves` selects a subset (ZZ_MOVE_*; 0 = ZZ_MOVE_FUSED).  By default the production
+   kernels run (zz_fast.cuh: XgLikelihood split into a cached detection term and a closed-form normal term, table-driven
+   exp/log; results agree with the reference-order moves to O(1e-15) relative and decisions can differ only at floating-
+   point ties); ZZ_MOVE_REFERENCE_ORDER selects the kernel that keeps the reference's operation order, which is also what
+   the five per-move entry points above use.  draws: [9][C][G] = {z_yg,u_yg,u1_vg,u2_vg,u_ai,u_within,zy_spike,zv_spike,
+   u_spike} or NULL; decisions: [4][C][G] or NULL. */
 int zz_sweep(zz_handle *h, uint64_t step, int tune, uint32_t moves, const double *draws, uint8_t *decisions);
 /* Exports the draws Philox would produce for (step, slot) in the layout of that move's `draws` argument. */
 int zz_philox_draws(zz_handle *h, uint64_t step, int slot, double *out);

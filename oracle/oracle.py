@@ -109,7 +109,7 @@ def lib(omp=False):
         L.zzo_chain_hyper.argtypes = [C.c_void_p]
         L.zzo_chain_lnl.restype = C.c_double
         L.zzo_chain_lnl.argtypes = [C.c_void_p]
-        L.zzo_uniform2.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]
+        L.zzo_uniform4.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p]
         L.zzo_sweep_draws.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p]
         _libs[key] = L
     return _libs[key]
@@ -159,7 +159,7 @@ class State:
 
     def copy(self):
         o = State.__new__(State)
-        o.__dict__.update({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in self.__dict__.items() if k != "_keep"})
+        o.__dict__.update({k: (v.copy(order="K") if isinstance(v, np.ndarray) else v) for k, v in self.__dict__.items() if k != "_keep"})
         return o
 
     def window_sums(self, which="Yg_trace"):
@@ -263,8 +263,8 @@ def philox4x32_10(ctr, key):
     lib().zzo_philox4x32_10(c, k, o); return list(o)
 
 
-def uniform2(seed, chain, step, slot, blk, gene):
-    o = (C.c_double * 2)(); lib().zzo_uniform2(seed, chain, step, slot, blk, gene, o); return o[0], o[1]
+def uniform4(seed, chain, step, blk, gene):
+    o = (C.c_double * 4)(); lib().zzo_uniform4(seed, chain, step, blk, gene, o); return tuple(o)
 
 
 def sweep_draws(seed, chain, step, gene0, G):

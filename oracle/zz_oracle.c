@@ -482,20 +482,26 @@ void zzo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-static inline double u53(uint32_t hi, uint32_t lo) { /* (53-bit int + 0.5) * 2^-53, in (0,1) */
-  uint64_t b = (((uint64_t)hi << 32) | lo) >> 11;
-  return ((double)b + 0.5) * (1.0 / 9007199254740992.0);
+static inline double u32_open(uint32_t w) { /* (w + 0.5) * 2^-32: open interval, 32-bit resolution like R's unif_rand */
+  return ((double)w + 0.5) * (1.0 / 4294967296.0);
 }
 
-void zzo_uniform2(uint64_t seed, uint32_t chain, uint64_t step, uint32_t slot, uint32_t blk, uint64_t gene, double out[2]) {
-  /* counter = (gene index [global, < 2^32], slot | blk<<4 | chain<<8, step lo, step hi); key = seed */
-  uint32_t ctr[4] = { (uint32_t)gene, (slot & 15u) | ((blk & 15u) << 4) | (chain << 8),
-                      (uint32_t)step, (uint32_t)(step >> 32) };
+/* One Philox block = 4 words for (seed, chain, step, blk, global gene index).
+   counter = (gene [< 2^32], blk | chain<<8, step lo, step hi); key = (seed lo, seed hi).
+   Draw map of a sweep (DESIGN.md "RNG"):
+     blk 0: w0,w1 -> Box-Muller -> z of mhYg (cos branch) ; w2 -> u of mhYg ; w3 -> u_proposal of mhVariance_g
+     blk 1: w0 -> u_accept of mhVariance_g ; w1 -> u of the active/inactive Gibbs draw ; w2 -> u of the within-active draw
+     blk 2: w0,w1 -> Box-Muller -> (z_y, z_v) of mhSpikeAllocation ; w2 -> its u                                   */
+void zzo_philox_block(uint64_t seed, uint32_t chain, uint64_t step, uint32_t blk, uint64_t gene, uint32_t out[4]) {
+  uint32_t ctr[4] = { (uint32_t)gene, (blk & 255u) | (chain << 8), (uint32_t)step, (uint32_t)(step >> 32) };
   uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+  zzo_philox4x32_10(ctr, key, out);
+}
+
+void zzo_uniform4(uint64_t seed, uint32_t chain, uint64_t step, uint32_t blk, uint64_t gene, double out[4]) {
   uint32_t o[4];
-  zzo_philox4x32_10(ctr, key, o);
-  out[0] = u53(o[0], o[1]);
-  out[1] = u53(o[2], o[3]);
+  zzo_philox_block(seed, chain, step, blk, gene, o);
+  for (int i = 0; i < 4; ++i) out[i] = u32_open(o[i]);
 }
 
 void zzo_box_muller(double ua, double ub, double out[2]) {
@@ -504,20 +510,18 @@ void zzo_box_muller(double ua, double ub, double out[2]) {
   out[1] = r * sin(2.0 * PI_ * ub);
 }
 
-/* slots: 1 = mhYg, 2 = mhVariance_g, 3 = alloc active/inactive (+within), 4 = alloc within (standalone), 5 = mhSpikeAllocation */
 void zzo_sweep_draws(uint64_t seed, uint32_t chain, uint64_t step, uint64_t gene0, int64_t G, double *d) {
   for (int64_t g = 0; g < G; ++g) {
-    double a[2], b[2], n[2];
-    zzo_uniform2(seed, chain, step, 1, 0, gene0 + g, a); zzo_box_muller(a[0], a[1], n);
-    zzo_uniform2(seed, chain, step, 1, 1, gene0 + g, b);
-    d[0 * G + g] = n[0]; d[1 * G + g] = b[0];
-    zzo_uniform2(seed, chain, step, 2, 0, gene0 + g, a);
-    d[2 * G + g] = a[0]; d[3 * G + g] = a[1];
-    zzo_uniform2(seed, chain, step, 3, 0, gene0 + g, a);
-    d[4 * G + g] = a[0]; d[5 * G + g] = a[1];
-    zzo_uniform2(seed, chain, step, 5, 0, gene0 + g, a); zzo_box_muller(a[0], a[1], n);
-    zzo_uniform2(seed, chain, step, 5, 1, gene0 + g, b);
-    d[6 * G + g] = n[0]; d[7 * G + g] = n[1]; d[8 * G + g] = b[0];
+    double a[4], b[4], c[4], n[2];
+    zzo_uniform4(seed, chain, step, 0, gene0 + g, a);
+    zzo_uniform4(seed, chain, step, 1, gene0 + g, b);
+    zzo_uniform4(seed, chain, step, 2, gene0 + g, c);
+    zzo_box_muller(a[0], a[1], n);
+    d[0 * G + g] = n[0]; d[1 * G + g] = a[2];
+    d[2 * G + g] = a[3]; d[3 * G + g] = b[0];
+    d[4 * G + g] = b[1]; d[5 * G + g] = b[2];
+    zzo_box_muller(c[0], c[1], n);
+    d[6 * G + g] = n[0]; d[7 * G + g] = n[1]; d[8 * G + g] = c[2];
   }
 }
 
@@ -534,17 +538,18 @@ struct zzo_chain {
   uint8_t w_im[100], w_av[100], w_am[ZZO_MAX_COMP][100], w_s0[100], w_s1[100], w_tau[100], w_s0tau[100], w_alpha[ZZO_MAX_LIBS][100];
   double proposal_probs[15];
   uint64_t seed, hyper_ctr, step;
+  double hyper_buf[4];
   int64_t gen;
   uint32_t *alloc_trace; /* [K+1][G] */
   int64_t n_samples;
-  double *d_a, *d_b, *d_c; /* draw scratch */
+  double *draws; /* [9][G] draw table of the current step */
 };
 
-/* hyper-level draws: a private Philox stream (gene index 0xFFFFFFFF, slot 15) */
+/* hyper-level draws: a private Philox stream (gene index 0xFFFFFFFF, blk 255) */
 static double c_unif(zzo_chain *c) {
-  double o[2];
-  zzo_uniform2(c->seed, 0, c->hyper_ctr++, 15, 0, 0xFFFFFFFFull, o);
-  return o[0];
+  double o[4];
+  if ((c->hyper_ctr & 3) == 0) { zzo_uniform4(c->seed, 0, c->hyper_ctr >> 2, 255, 0xFFFFFFFFull, o); memcpy(c->hyper_buf, o, sizeof o); }
+  return c->hyper_buf[c->hyper_ctr++ & 3];
 }
 static double c_norm(zzo_chain *c) { double n[2]; double a = c_unif(c), b = c_unif(c); zzo_box_muller(a, b, n); return n[0]; }
 static double c_gamma(zzo_chain *c, double shape, double rate) { /* Marsaglia & Tsang 2000; distributionally = rgamma */
@@ -584,12 +589,12 @@ static double two_boundary_slide(zzo_chain *c, double p, double lo, double hi, d
   return lo + fabs(np - lo);
 }
 
-static void fill_draws(zzo_chain *c, double *d, int slot, int blk, int which, int normal) {
-  for (int64_t g = 0; g < c->G; ++g) {
-    double a[2]; zzo_uniform2(c->seed, 0, c->step, (uint32_t)slot, (uint32_t)blk, (uint64_t)g, a);
-    if (normal) { double n[2]; zzo_box_muller(a[0], a[1], n); d[g] = n[which]; } else d[g] = a[which];
-  }
+/* draws of one move for every gene, taken from the sweep draw map at the chain's current step */
+static void fill_sweep_draws(zzo_chain *c) {
+  if (!c->draws) c->draws = (double *)malloc(sizeof(double) * 9 * c->G);
+  zzo_sweep_draws(c->seed, 0, c->step, 0, c->G, c->draws);
 }
+#define DRAW(c, j) ((c)->draws + (int64_t)(j) * (c)->G)
 
 /* ---- the 15 proposal_list entries (I:207-223), numbered as in the reference (1-based) ---- */
 static void mv_gibbsMixtureWeights(zzo_chain *c) { /* Pr:412-431 */
@@ -607,12 +612,12 @@ static void mv_gibbsMixtureWeights(zzo_chain *c) { /* Pr:412-431 */
   }
 }
 static void mv_allocAI(zzo_chain *c) {
-  fill_draws(c, c->d_a, 3, 0, 0, 0); fill_draws(c, c->d_b, 3, 0, 1, 0);
-  zzo_gibbs_alloc_active_inactive(&c->h, &c->s, c->d_a, c->d_b, NULL, NULL);
+  fill_sweep_draws(c);
+  zzo_gibbs_alloc_active_inactive(&c->h, &c->s, DRAW(c, 4), DRAW(c, 5), NULL, NULL);
 }
 static void mv_allocWithin(zzo_chain *c) {
-  fill_draws(c, c->d_a, 4, 0, 0, 0);
-  zzo_gibbs_alloc_within_active(&c->h, &c->s, c->d_a, NULL);
+  fill_sweep_draws(c);
+  zzo_gibbs_alloc_within_active(&c->h, &c->s, DRAW(c, 5), NULL);
 }
 static void mv_mhInactiveMeans(zzo_chain *c, int tune) { /* Pr:433-471 */
   double thr = c->pr.threshold_i, im = c->h.inactive_means;
@@ -668,16 +673,16 @@ static void mv_gibbsSpikeProb(zzo_chain *c) { /* Pr:511-526 */
   if (!isnan(ns)) c->h.spike_probability = ns;
 }
 static void mv_mhSpikeAllocation(zzo_chain *c) {
-  fill_draws(c, c->d_a, 5, 0, 0, 1); fill_draws(c, c->d_b, 5, 0, 1, 1); fill_draws(c, c->d_c, 5, 1, 0, 0);
-  zzo_mh_spike_alloc(&c->h, &c->s, c->d_a, c->d_b, c->d_c, NULL, NULL);
+  fill_sweep_draws(c);
+  zzo_mh_spike_alloc(&c->h, &c->s, DRAW(c, 6), DRAW(c, 7), DRAW(c, 8), NULL, NULL);
 }
 static void mv_mhYg(zzo_chain *c, int tune) {
-  fill_draws(c, c->d_a, 1, 0, 0, 1); fill_draws(c, c->d_b, 1, 1, 0, 0);
-  zzo_mh_yg(&c->h, &c->s, c->d_a, c->d_b, tune, NULL, NULL);
+  fill_sweep_draws(c);
+  zzo_mh_yg(&c->h, &c->s, DRAW(c, 0), DRAW(c, 1), tune, NULL, NULL);
 }
 static void mv_mhVariance_g(zzo_chain *c, int tune) {
-  fill_draws(c, c->d_a, 2, 0, 0, 0); fill_draws(c, c->d_b, 2, 0, 1, 0);
-  zzo_mh_variance_g(&c->h, &c->s, c->d_a, c->d_b, tune, NULL, NULL);
+  fill_sweep_draws(c);
+  zzo_mh_variance_g(&c->h, &c->s, DRAW(c, 2), DRAW(c, 3), tune, NULL, NULL);
 }
 static double sum_vgprob_out(const zzo_chain *c) {
   acc_t a = 0; for (int64_t g = 0; g < c->G; ++g) if (!c->s.inactive_spike_allocation[g]) a += c->s.variance_g_probability[g];
@@ -779,7 +784,6 @@ zzo_chain *zzo_chain_new(int64_t G, int R, int K, const double *Xg, const double
   s->tuningParam_yg = (double *)calloc(G, 8); s->tuningParam_variance_g = (double *)calloc(G, 8);
   s->Yg_trace = (uint64_t *)calloc(2 * G, 8); s->variance_g_trace = (uint64_t *)calloc(2 * G, 8);
   c->alloc_trace = (uint32_t *)calloc((size_t)(K + 1) * G, 4);
-  c->d_a = (double *)malloc(8 * G); c->d_b = (double *)malloc(8 * G); c->d_c = (double *)malloc(8 * G);
   zzo_hyper *h = &c->h; h->num_libraries = R; h->num_active_components = K;
   h->beta = 1; h->temperature = 1; h->variance_g_upper_bound = INFINITY;
   /* I:185-199 */
@@ -862,7 +866,7 @@ void zzo_chain_free(zzo_chain *c) {
   free(c->Xg_own); free(c->gl_own); free(c->nd); free(s->Yg); free(s->variance_g); free(s->alloc_active_inactive);
   free(s->alloc_within_active); free(s->inactive_spike_allocation); free(s->XgLikelihood); free(s->variance_g_probability);
   free(s->tuningParam_yg); free(s->tuningParam_variance_g); free(s->Yg_trace); free(s->variance_g_trace);
-  free(c->alloc_trace); free(c->d_a); free(c->d_b); free(c->d_c); free(c);
+  free(c->alloc_trace); free(c->draws); free(c);
 }
 
 static void one_generation_ref(zzo_chain *c, int tune) { /* B:66-67 / M:172-173 */

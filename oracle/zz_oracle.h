@@ -117,8 +117,9 @@ void zzo_tune_per_gene(zzo_state *s, double target);               /* U:202-206 
 
 /* ---- counter-based RNG shared with the device (spec in DESIGN.md) ---- */
 void zzo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-/* two open-interval uniforms for (seed, chain, step, slot, blk, global gene index) */
-void zzo_uniform2(uint64_t seed, uint32_t chain, uint64_t step, uint32_t slot, uint32_t blk, uint64_t gene, double out[2]);
+/* one Philox block (4 words) / four 32-bit open-interval uniforms for (seed, chain, step, blk, global gene index) */
+void zzo_philox_block(uint64_t seed, uint32_t chain, uint64_t step, uint32_t blk, uint64_t gene, uint32_t out[4]);
+void zzo_uniform4(uint64_t seed, uint32_t chain, uint64_t step, uint32_t blk, uint64_t gene, double out[4]);
 void zzo_box_muller(double ua, double ub, double out[2]);
 /* fills the [9][G] draw table zzo_sweep consumes, for genes gene0..gene0+G-1 */
 void zzo_sweep_draws(uint64_t seed, uint32_t chain, uint64_t step, uint64_t gene0, int64_t G, double *draws);

@@ -13,6 +13,7 @@ MAX_LIBS, MAX_COMP = 64, 8
 
 SLOT_YG, SLOT_VARIANCE_G, SLOT_ALLOC, SLOT_ALLOC_WITHIN, SLOT_SPIKE = 1, 2, 3, 4, 5
 MOVE_YG, MOVE_VARIANCE_G, MOVE_ALLOC, MOVE_ALLOC_WITHIN, MOVE_SPIKE = 1, 2, 4, 8, 16
+MOVE_REFERENCE_ORDER = 32
 MOVE_FUSED = MOVE_YG | MOVE_VARIANCE_G | MOVE_ALLOC | MOVE_SPIKE
 
 

@@ -177,19 +177,18 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {  // (53-bit integer + 0.5) * 2^-53, open interval
-  const uint64_t b = (((uint64_t)hi << 32) | lo) >> 11;
-  return ((double)b + 0.5) * (1.0 / 9007199254740992.0);
+__device__ __forceinline__ double u32_open(uint32_t w) {  // (w + 0.5) * 2^-32: open interval, 32-bit resolution (like R's unif_rand)
+  return ((double)w + 0.5) * (1.0 / 4294967296.0);
 }
 
-// counter = (global gene index, slot | blk<<4 | chain<<8, step lo, step hi); key = seed
-__device__ __forceinline__ void uniform2(uint64_t seed, uint32_t chain, uint64_t step, uint32_t slot, uint32_t blk, uint64_t gene,
-                                          double &a, double &b) {
-  uint32_t o[4];
-  philox4x32_10((uint32_t)gene, (slot & 15u) | ((blk & 15u) << 4) | (chain << 8), (uint32_t)step, (uint32_t)(step >> 32),
-                (uint32_t)seed, (uint32_t)(seed >> 32), o);
-  a = u53(o[0], o[1]);
-  b = u53(o[2], o[3]);
+// One Philox block: counter = (global gene index, blk | chain<<8, step lo, step hi); key = seed.
+// Draw map of a sweep (identical in oracle/zz_oracle.c:zzo_sweep_draws and DESIGN.md "RNG"):
+//   blk 0: w0,w1 -> Box-Muller -> z of mhYg (cos branch); w2 -> u of mhYg; w3 -> u_proposal of mhVariance_g
+//   blk 1: w0 -> u_accept of mhVariance_g; w1 -> u of the active/inactive draw; w2 -> u of the within-active draw
+//   blk 2: w0,w1 -> Box-Muller -> (z_y, z_v) of mhSpikeAllocation; w2 -> its u
+__device__ __forceinline__ void philox_block(uint64_t seed, uint32_t chain, uint64_t step, uint32_t blk, uint64_t gene, uint32_t o[4]) {
+  philox4x32_10((uint32_t)gene, (blk & 255u) | (chain << 8), (uint32_t)step, (uint32_t)(step >> 32), (uint32_t)seed,
+                (uint32_t)(seed >> 32), o);
 }
 
 __device__ __forceinline__ void box_muller(double ua, double ub, double &z0, double &z1) {

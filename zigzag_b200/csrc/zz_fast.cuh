@@ -1,0 +1,199 @@
+// zz_fast.cuh — the production ("fast") formulation of the fused sweep for sm_100a.
+//
+// Same Markov kernel, same draws and — up to floating-point ties — the same decisions as the reference-order moves
+// in zz_device.cuh, reorganised so that one gene-update costs ~700 FP64-pipe instructions instead of ~4000
+// (B200: 64 FP64 lanes/clk/SM, so the 188 B/gene-update HBM roofline needs < ~860; profiles/r1_*.md):
+//   * computeXgLikelihood (P:57-127) is split as XgLik = beta * (A(y) + B(y, v)):
+//       A(y)    = sum_r log(1 - p_gr) | log(p_gr)           (needs exp+log per library; depends on y and alpha only)
+//       B(y, v) = -n_det (ln sqrt(2 pi) + 0.5 log v) - 0.5 D(y) / v,  D(y) = sum_detected (x_gr - y)^2
+//     A(current y) is carried per gene in HBM (`lps`), so mhYg evaluates exp/log only for the PROPOSED y and
+//     mhVariance_g needs no per-library transcendental at all.
+//   * log(Sg) = log(exp(s0 + s1 y)) (P:20 via U:146) is taken as s0 + s1 y; divisions by hyper-parameter constants
+//     become multiplications by reciprocals hoisted to shared memory; Lk of gibbsAllocationWithinActive (Pr:375) reuses
+//     the w_k * exp(.) terms of gibbsAllocationActiveInactive (Pr:344); floor(cum/u) == 0 (Pr:400-402) is evaluated
+//     as cum < u (exactly equivalent for cum >= 0, u > 0).
+//   * exp/log are the table-driven versions of zz_fastmath.cuh (<= 2 ulp).
+// Every reorganisation changes results by O(1e-15) relative, eight orders below the 1e-10 tolerance of north-star
+// check 1; decisions can differ from the oracle only when |log u - R| is itself O(1e-14) (reported by the tests).
+#pragma once
+#include "zz_device.cuh"
+#include "zz_fastmath.cuh"
+
+namespace zz {
+
+struct FastH {   // one chain's hyper-parameters + hoisted gene-independent sub-expressions (shared memory)
+  int R, K;
+  double s0, s1, tau, rtau, irt;          // irt = 1/sqrt(tau)
+  double c1;                              // log(sqrt(tau) * sqrt(2 pi)):  log(v * rt * sqrt2pi) = log v + c1   (P:20)
+  double sp, log_sp, log_1msp, log_norm_i;
+  double im, sd_i, inv2iv, c0;            // c0 = (1 - sp) / (sqrt2pi * sd_i):  L0 = c0 * exp(-(y-im)^2 / (2 iv))   (P:220)
+  double wa, one_m_wa, beta, temp, vub;
+  double alpha[ZZ_MAX_LIBS];
+  double am[ZZ_MAX_COMP], inv2av[ZZ_MAX_COMP], ck[ZZ_MAX_COMP];  // ck = w_k / (sqrt2pi * sqrt(av_k))           (Pr:344)
+};
+
+__device__ __forceinline__ void load_fast(FastH &H, MathTabs &T, const zz_hyper *__restrict__ hy,
+                                          const double *__restrict__ exp_tab, const double2 *__restrict__ log_tab) {
+  const int t = threadIdx.x, nt = blockDim.x;
+  for (int j = t; j < 256; j += nt) { T.exp_t[j] = exp_tab[j]; T.log_t[j] = log_tab[j]; }
+  if (t == 0) {
+    const double s2p = sqrt(2 * PI_D);
+    H.R = hy->num_libraries; H.K = hy->num_active_components;
+    H.s0 = hy->s0; H.s1 = hy->s1; H.tau = hy->tau; H.rtau = sqrt(hy->tau); H.irt = 1.0 / H.rtau;
+    H.c1 = log(H.rtau * s2p);
+    H.sp = hy->spike_probability; H.log_sp = log(H.sp); H.log_1msp = log(1 - H.sp);
+    H.im = hy->inactive_means; H.sd_i = sqrt(hy->inactive_variances);
+    H.log_norm_i = log(s2p * H.sd_i);
+    H.inv2iv = 1.0 / (2 * hy->inactive_variances);
+    H.c0 = (1 - H.sp) / (s2p * H.sd_i);
+    H.wa = hy->weight_active; H.one_m_wa = 1 - hy->weight_active;
+    H.beta = (hy->beta < 0.0000001) ? 0.0 : hy->beta;   // P:121-125: beta < 1e-7 => likelihood 0
+    H.temp = hy->temperature; H.vub = hy->variance_g_upper_bound;
+  }
+  for (int r = t; r < ZZ_MAX_LIBS; r += nt) H.alpha[r] = hy->alpha_r[r];
+  if (t < ZZ_MAX_COMP) {
+    const double s2p = sqrt(2 * PI_D);
+    H.am[t] = hy->active_means[t];
+    H.inv2av[t] = 1.0 / (2 * hy->active_variances[t]);
+    H.ck[t] = hy->weight_within_active[t] / (s2p * sqrt(hy->active_variances[t]));
+  }
+  __syncthreads();
+}
+
+// z = sqrt(-2 ln ua) * cos(2 pi ub)  (same draw as box_muller's z0; the sine branch is only needed by the spike move)
+__device__ __forceinline__ double normal_cos(double ua, double ub, const MathTabs &T) {
+  return sqrt(-2.0 * flog(ua, T.log_t)) * cospi(2.0 * ub);
+}
+
+// A(y') and the two squared-distance sums over one gene's libraries.  RT > 0: compile-time library count (unrolled).
+template <int RT>
+__device__ __forceinline__ void lib_loop(const FastH &H, const MathTabs &T, const double *__restrict__ xg, int64_t stride,
+                                         double y, double yp, double tp, double &Ap, double &D, double &Dp, int &ndet) {
+  const int R = RT > 0 ? RT : H.R;
+  Ap = 0; D = 0; Dp = 0; ndet = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const double x = __ldg(xg + (int64_t)r * stride);
+    const bool nd = (x == -INFINITY);
+    const double e = fexp_neg_clamped(tp * H.alpha[r], T.exp_t);
+    const double p = 1 - e;                           // U:157
+    const double q = nd ? (1 - p) : p;                // P:82 / P:84
+    Ap += flog(q, T.log_t);
+    if (!nd) {
+      const double d = x - y, dp = x - yp;
+      D = fma(d, d, D); Dp = fma(dp, dp, Dp);
+      ndet++;
+    }
+  }
+}
+
+// A(y) alone (cache refresh / spike proposals): sum_r log(nd ? 1-p : p)
+template <int RT>
+__device__ __forceinline__ double lps_only(const FastH &H, const MathTabs &T, const double *__restrict__ xg, int64_t stride,
+                                           double t, bool all_nd) {
+  const int R = RT > 0 ? RT : H.R;
+  double A = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const bool nd = all_nd || (__ldg(xg + (int64_t)r * stride) == -INFINITY);
+    const double e = fexp_neg_clamped(t * H.alpha[r], T.exp_t);
+    const double p = 1 - e;
+    A += flog(nd ? (1 - p) : p, T.log_t);
+  }
+  return A;
+}
+
+__device__ __forceinline__ double level2_quad(const FastH &H, double y, uint32_t f) {   // (y - mean)^2 / (2 var) of the gene's component
+  if (f & F_ACTIVE) { const int k = flag_k(f) - 1; const double d = y - H.am[k]; return d * d * H.inv2av[k]; }
+  const double d = y - H.im;
+  return d * d * H.inv2iv;
+}
+
+struct FastGene {
+  double y, v, lv, rv;     // Yg, variance_g, log(variance_g), 1/variance_g
+  double A;                // sum of the detection log-terms at y
+  double D;                // sum_detected (x - y)^2
+  int ndet;
+  uint32_t f;
+};
+
+// computeVarianceGPriorProbability's standardised residual  q = (log v - log Sg - tau) / sqrt(tau),  log Sg = s0 + s1 y
+__device__ __forceinline__ double vg_q(const FastH &H, double lv, double y) { return (lv - fma(H.s1, y, H.s0) - H.tau) * H.irt; }
+__device__ __forceinline__ double vg_prior_from_q(const FastH &H, double lv, double q) { return -(lv + H.c1) - 0.5 * (q * q); }
+
+__device__ __forceinline__ double plnorm_term(const FastH &H, double y) {   // only when variance_g_upper_bound < Inf (P:24-25)
+  return plnorm_log(H.vub, fma(H.s1, y, H.s0) + H.tau, H.rtau);
+}
+
+// mhYg (Pr:250-333).  On entry g.D / g.ndet are undefined; on exit they refer to the (possibly updated) g.y.
+template <int RT>
+__device__ __forceinline__ int fast_yg(const FastH &H, const MathTabs &T, FastGene &g, const double *__restrict__ xg, int64_t stride,
+                                       double gl, double ty, double z, double u, double &ratio) {
+  const double yp = g.y + ty * z;                                       // Pr:257
+  const double tp = gl * fexp(yp, T.exp_t);                             // U:157
+  double Ap, D, Dp; int ndet;
+  lib_loop<RT>(H, T, xg, stride, g.y, yp, tp, Ap, D, Dp, ndet);
+  const double dLX = H.beta * ((Ap - g.A) - 0.5 * (Dp - D) * g.rv);     // XgLik' - XgLik
+  const double q = vg_q(H, g.lv, g.y), qp = vg_q(H, g.lv, yp);
+  double dPV = -0.5 * (qp * qp - q * q);                                // Pr:267 - cache
+  if (H.vub != INFINITY) dPV -= plnorm_term(H, yp) - plnorm_term(H, g.y);
+  const double dL2 = -(level2_quad(H, yp, g.f) - level2_quad(H, g.y, g.f));  // Pr:271-291
+  ratio = H.temp * (dLX + dL2 + dPV);                                   // Pr:296
+  const int acc = (flog(u, T.log_t) < ratio);                           // Pr:302
+  g.ndet = ndet;
+  if (acc) { g.y = yp; g.A = Ap; g.D = Dp; } else { g.D = D; }
+  return acc;
+}
+
+// mhVariance_g (Pr:7-56): no per-library work, p_x does not depend on variance_g
+__device__ __forceinline__ int fast_vg(const FastH &H, const MathTabs &T, FastGene &g, double tv, double u1, double u2, double &ratio) {
+  const double arg = tv * (u1 - 0.5);                                   // MP:5; HR = log(sf) = arg (Pr:15)
+  const double sf = fexp(arg, T.exp_t);
+  const double vp = g.v * sf;                                           // MP:7
+  const double rvp = g.rv * fexp(-arg, T.exp_t);                        // 1 / v'
+  const double lvp = g.lv + arg;
+  const double dB = -(double)g.ndet * (0.5 * arg) - 0.5 * g.D * (rvp - g.rv);
+  const double q = vg_q(H, g.lv, g.y), qp = q + arg * H.irt;
+  const double dPV = -arg - 0.5 * (qp * qp - q * q);                    // the plnorm term (P:25) does not depend on v
+  ratio = H.temp * (H.beta * dB + dPV) + arg;                           // Pr:24
+  if (vp > H.vub) ratio = -INFINITY;                                    // Pr:26
+  const int acc = (flog(u2, T.log_t) < ratio);                          // Pr:35
+  if (acc) { g.v = vp; g.lv = lvp; g.rv = rvp; }
+  return acc;
+}
+
+// gibbsAllocationActiveInactive + gibbsAllocationWithinActive (Pr:335-410); returns the allocation word (0 or k)
+__device__ __forceinline__ int fast_alloc(const FastH &H, const MathTabs &T, double y, uint32_t &f, double u_ai, double u_w) {
+  const bool in_spike = (f & F_INSPIKE) != 0;
+  const double d0 = y - H.im;
+  const double L0 = in_spike ? H.sp : H.c0 * fexp(-(d0 * d0) * H.inv2iv, T.exp_t);   // Pr:339
+  double Lk[ZZ_MAX_COMP];
+  double L1 = 0;
+#pragma unroll
+  for (int k = 0; k < ZZ_MAX_COMP; ++k) {
+    if (k < H.K) {
+      const double d = y - H.am[k];
+      Lk[k] = H.ck[k] * fexp(-(d * d) * H.inv2av[k], T.exp_t);          // Pr:344 / Pr:375-395
+      L1 += Lk[k];
+    }
+  }
+  const double num = in_spike ? 0.0 : H.wa * L1;
+  double pa = num / (H.one_m_wa * L0 + num);                            // Pr:348
+  if (isnan(pa)) pa = H.wa;                                             // Pr:349
+  int a = (u_ai < pa) ? 1 : 0;                                          // Pr:353
+  if (f & F_PINNED) a = 1;                                              // Pr:355
+  f = (f & ~F_ACTIVE) | (a ? F_ACTIVE : 0u);
+  if (!a) return 0;
+  if (L1 > 0 && L1 < INFINITY) {                                        // NaN rows keep the old k, Pr:403
+    const double thr = u_w * L1;
+    double cum = 0; int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < ZZ_MAX_COMP; ++k)
+      if (k < H.K) { cum += Lk[k]; cnt += (cum < thr); }                // Pr:398-402
+    const int kn = cnt + 1 > H.K ? H.K : cnt + 1;
+    f = flag_set_k(f, kn);
+  }
+  return flag_k(f);
+}
+
+}  // namespace zz

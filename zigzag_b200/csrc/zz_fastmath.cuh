@@ -1,0 +1,106 @@
+// zz_fastmath.cuh — table-driven fp64 exp / log for the production sweep (host+device so the CPU test-suite can
+// check them against libm without a GPU; tests/test_fastmath.py).
+//
+// Why: the faithful sweep spends ~4000 FP64-pipe instructions per gene-update, almost all inside CUDA libm's exp/log
+// (profiles/r1_sweep_v0.md).  B200 issues 64 FP64 lanes/clk/SM, so the HBM roofline (188 B per gene-update) is only
+// reachable below ~860 FP64 instructions per gene-update.  These versions cost 9 (exp) and 10 (log) FP64 instructions
+// plus one shared-memory table read, with <= 2 ulp error (measured, tests/test_fastmath.py) — eight orders of magnitude
+// inside the 1e-10 relative tolerance of north-star check 1.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#include "zz_tables.h"
+
+#if defined(__CUDACC__)
+#define ZZ_HD __host__ __device__ __forceinline__
+#else
+#define ZZ_HD inline
+#endif
+
+namespace zz {
+
+ZZ_HD int d_hi(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2hiint(x);
+#else
+  uint64_t b; memcpy(&b, &x, 8); return (int)(b >> 32);
+#endif
+}
+ZZ_HD int d_lo(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2loint(x);
+#else
+  uint64_t b; memcpy(&b, &x, 8); return (int)(uint32_t)b;
+#endif
+}
+ZZ_HD double d_make(int hi, int lo) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(hi, lo);
+#else
+  uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &b, 8); return x;
+#endif
+}
+
+struct MathTabs {          // lives in shared memory on the device
+  double exp_t[256];       // 2^(j/256)
+  double2 log_t[256];      // {IC[i], LC[i]}
+};
+
+// exp(x) for -708 <= x <= 709 (callers clamp or take the libm path outside).  9 FP64 instructions.
+ZZ_HD double fexp_core(double x, const double *__restrict__ exp_t) {
+  const double magic = 6755399441055744.0;            // 1.5 * 2^52: the low word of (x*c + magic) is rint(x*c)
+  const double t = fma(x, ZZ_KINVL, magic);
+  const int n = d_lo(t);
+  const double nd = t - magic;
+  double r = fma(nd, -ZZ_KLHI, x);                    // exact: n has < 21 bits, L_hi has 32
+  r = fma(nd, -ZZ_KLLO, r);
+  double p = fma(r, ZZ_KE4, ZZ_KE3);                  // e^r = 1 + r (E1 + r (1/2 + r (E3 + r/24)))
+  p = fma(r, p, ZZ_KE2);
+  p = fma(r, p, ZZ_KE1);
+  p = fma(r, p, 1.0);
+  const double s = exp_t[n & 255] * p;
+  return d_make(d_hi(s) + ((n >> 8) << 20), d_lo(s)); // * 2^k by exponent-field addition (result is normal here)
+}
+
+// general exp: libm outside the range where the exponent-field trick is valid (rare, warp-divergent)
+ZZ_HD double fexp(double x, const double *__restrict__ exp_t) {
+  if (!(fabs(x) <= 708.0)) return exp(x);
+  return fexp_core(x, exp_t);
+}
+
+// exp(-a) for the detection probability p = 1 - exp(-a), a >= 0: for a > 40, exp(-a) < 2^-57 and 1 - exp(-a) rounds to
+// 1 whatever its value, so a is clamped at 700 through an integer min on the high word (a >= 0: high words order like
+// the values; +Inf clamps too; NaN cannot pass through here unnoticed because (x - y)^2 is NaN as well).
+ZZ_HD double fexp_neg_clamped(double a, const double *__restrict__ exp_t) {
+  const int hi = d_hi(a);
+  const int hc = hi < 0x4085E000 ? hi : 0x4085E000;   // 0x4085E000_00000000 = 700.0
+  const double ac = d_make(hc, hi < 0x4085E000 ? d_lo(a) : 0);
+  return fexp_core(-ac, exp_t);
+}
+
+// log(x) for positive normal finite x.  10 FP64 instructions.
+ZZ_HD double flog_core(double x, const double2 *__restrict__ log_t) {
+  const int hi = d_hi(x);
+  const int k = ((hi + 0x00096000) >> 20) - 1023;     // exponent, +1 when the mantissa is >= 1 + 106/256 (table entry is for m/2)
+  const int i = (hi >> 12) & 255;
+  const double m = d_make((hi & 0x000FFFFF) | 0x3FF00000, d_lo(x));
+  const double2 tc = log_t[i];
+  const double r = fma(m, tc.x, -1.0);                // exact (IC has <= 10 significant bits)
+  const double r2 = r * r;
+  double s = fma(r, -1.0 / 6, 1.0 / 5);               // log1p(r) = r + r^2 (-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6)
+  s = fma(r, s, -1.0 / 4);
+  s = fma(r, s, 1.0 / 3);
+  s = fma(r, s, -0.5);
+  const double lo = fma(r2, s, r);
+  const double kd = d_make(0x43300000, k ^ 0x80000000) - 4503601774854144.0;  // int -> double without I2F: 2^52 + 2^31 bias
+  return fma(kd, ZZ_KLN2, tc.y) + lo;
+}
+
+ZZ_HD double flog(double x, const double2 *__restrict__ log_t) {
+  const unsigned hi = (unsigned)d_hi(x);
+  if (hi - 0x00100000u >= 0x7FE00000u) return log(x);  // x <= 0 (incl. -0), subnormal, Inf, NaN: libm semantics
+  return flog_core(x, log_t);
+}
+
+}  // namespace zz

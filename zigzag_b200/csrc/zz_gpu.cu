@@ -17,6 +17,7 @@
 #include <vector>
 #include <new>
 #include "zz_device.cuh"
+#include "zz_fast.cuh"
 
 using namespace zz;
 
@@ -56,15 +57,14 @@ __global__ void __launch_bounds__(BLOCK) k_sweep(const SweepArgs a) {
   const double gl = a.gl[g];
   const double *xg = a.Xg + g;
   bool saw_nan = false;
+  uint32_t b0[4] = {0, 0, 0, 0}, b1[4] = {0, 0, 0, 0};
+  if (!a.draws[0] && (a.moves & (ZZ_MOVE_YG | ZZ_MOVE_VARIANCE_G))) philox_block(a.seed, chain, a.step, 0, gid, b0);
+  if (!a.draws[3] && (a.moves & (ZZ_MOVE_VARIANCE_G | ZZ_MOVE_ALLOC | ZZ_MOVE_ALLOC_WITHIN))) philox_block(a.seed, chain, a.step, 1, gid, b1);
 
   if (a.moves & ZZ_MOVE_YG) {
     double z, u;
     if (a.draws[0]) { z = a.draws[0][i]; u = a.draws[1][i]; }
-    else {
-      double ua, ub, z1, u1;
-      uniform2(a.seed, chain, a.step, ZZ_SLOT_YG, 0, gid, ua, ub); box_muller(ua, ub, z, z1);
-      uniform2(a.seed, chain, a.step, ZZ_SLOT_YG, 1, gid, u, u1);
-    }
+    else { double z1; box_muller(u32_open(b0[0]), u32_open(b0[1]), z, z1); u = u32_open(b0[2]); }
     const bool proposed = !(gn.f & F_INSPIKE);
     double ratio;
     const int acc = move_yg(H, gn, xg, a.G, gl, a.ty[i], z, u, ratio);
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(BLOCK) k_sweep(const SweepArgs a) {
   if (a.moves & ZZ_MOVE_VARIANCE_G) {
     double u1, u2;
     if (a.draws[2]) { u1 = a.draws[2][i]; u2 = a.draws[3][i]; }
-    else uniform2(a.seed, chain, a.step, ZZ_SLOT_VARIANCE_G, 0, gid, u1, u2);
+    else { u1 = u32_open(b0[3]); u2 = u32_open(b1[0]); }
     const bool proposed = !(gn.f & F_INSPIKE);
     double ratio;
     const int acc = move_variance_g(H, gn, xg, a.G, gl, a.tv[i], u1, u2, ratio);
@@ -86,14 +86,14 @@ __global__ void __launch_bounds__(BLOCK) k_sweep(const SweepArgs a) {
   if (a.moves & ZZ_MOVE_ALLOC) {
     double u_ai, u_w;
     if (a.draws[4]) { u_ai = a.draws[4][i]; u_w = a.draws[5][i]; }
-    else uniform2(a.seed, chain, a.step, ZZ_SLOT_ALLOC, 0, gid, u_ai, u_w);
+    else { u_ai = u32_open(b1[1]); u_w = u32_open(b1[2]); }
     double pa;
     const int word = move_alloc(H, gn, u_ai, u_w, pa);
     if (a.dec[2]) a.dec[2][i] = (uint8_t)word;
   } else if (a.moves & ZZ_MOVE_ALLOC_WITHIN) {
-    double u_w, u_x;
+    double u_w;
     if (a.draws[5]) u_w = a.draws[5][i];
-    else uniform2(a.seed, chain, a.step, ZZ_SLOT_ALLOC_WITHIN, 0, gid, u_w, u_x);
+    else u_w = u32_open(b1[2]);
     if (gn.f & F_ACTIVE) { const int kn = within_active(H, gn.y, u_w); if (kn > 0) gn.f = flag_set_k(gn.f, kn); }
     if (a.dec[2]) a.dec[2][i] = (uint8_t)((gn.f & F_ACTIVE) ? flag_k(gn.f) : 0);
   }
@@ -101,9 +101,9 @@ __global__ void __launch_bounds__(BLOCK) k_sweep(const SweepArgs a) {
     double zy, zv, u;
     if (a.draws[6]) { zy = a.draws[6][i]; zv = a.draws[7][i]; u = a.draws[8][i]; }
     else {
-      double ua, ub, u1;
-      uniform2(a.seed, chain, a.step, ZZ_SLOT_SPIKE, 0, gid, ua, ub); box_muller(ua, ub, zy, zv);
-      uniform2(a.seed, chain, a.step, ZZ_SLOT_SPIKE, 1, gid, u, u1);
+      uint32_t b2[4];
+      philox_block(a.seed, chain, a.step, 2, gid, b2);
+      box_muller(u32_open(b2[0]), u32_open(b2[1]), zy, zv); u = u32_open(b2[2]);
     }
     const bool proposed = (gn.f & F_ALLZERO) && !(gn.f & F_ACTIVE);
     double ratio;
@@ -115,6 +115,160 @@ __global__ void __launch_bounds__(BLOCK) k_sweep(const SweepArgs a) {
   if (saw_nan) atomicOr(a.nan_flag, 1);
 }
 
+// ---- production sweep: same moves and draws as k_sweep in the reorganised arithmetic of zz_fast.cuh -------------------
+struct FastArgs {
+  SweepArgs s;
+  double *lps;                      // [C][G] A(y): sum of the detection log-terms at the current Yg
+  const double *exp_tab; const double2 *log_tab;
+  const int32_t *allzero_idx; int64_t n_allzero;   // static list of genes with no reads in any library (I:416-421)
+};
+
+template <int RT>
+__global__ void __launch_bounds__(BLOCK) k_sweep_fast(const FastArgs fa) {
+  __shared__ FastH H;
+  __shared__ MathTabs T;
+  const SweepArgs &a = fa.s;
+  const int chain = blockIdx.y;
+  load_fast(H, T, a.hyper + chain, fa.exp_tab, fa.log_tab);
+  const int64_t g = a.g_begin + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (g >= a.g_end) return;
+  const int64_t i = (int64_t)chain * a.G + g;
+  const uint64_t gid = (uint64_t)(a.gene_offset + g);
+  FastGene gn;
+  gn.y = a.Yg[i]; gn.v = a.vg[i]; gn.A = fa.lps[i]; gn.f = a.flags[i];
+  gn.D = 0; gn.ndet = 0; gn.lv = 0; gn.rv = 0;
+  const double gl = a.gl[g];
+  const double *xg = a.Xg + g;
+  const bool in_spike = (gn.f & F_INSPIKE) != 0;   // mhYg / mhVariance_g only touch out_spike_idx (Pr:11, Pr:252-257)
+  bool saw_nan = false;
+  uint32_t b0[4] = {0, 0, 0, 0}, b1[4] = {0, 0, 0, 0};
+  if (!a.draws[0] && (a.moves & (ZZ_MOVE_YG | ZZ_MOVE_VARIANCE_G))) philox_block(a.seed, chain, a.step, 0, gid, b0);
+  if (!a.draws[3] && (a.moves & (ZZ_MOVE_VARIANCE_G | ZZ_MOVE_ALLOC))) philox_block(a.seed, chain, a.step, 1, gid, b1);
+  if (!in_spike) { gn.lv = flog(gn.v, T.log_t); gn.rv = 1.0 / gn.v; }
+
+  if (a.moves & ZZ_MOVE_YG) {
+    int acc = 0;
+    if (!in_spike) {
+      double z, u, ratio;
+      if (a.draws[0]) { z = a.draws[0][i]; u = a.draws[1][i]; }
+      else { z = normal_cos(u32_open(b0[0]), u32_open(b0[1]), T); u = u32_open(b0[2]); }
+      acc = fast_yg<RT>(H, T, gn, xg, a.G, gl, a.ty[i], z, u, ratio);
+      saw_nan |= isnan(ratio);
+      if (a.tune) { ulonglong2 w = a.win_y[i]; window_push(w, acc); a.win_y[i] = w; }   // Pr:312-322
+    }
+    if (a.dec[0]) a.dec[0][i] = (uint8_t)acc;
+  } else if (!in_spike) {            // D(y), n_det are still needed by mhVariance_g and the XgLikelihood cache
+    const int R = RT > 0 ? RT : H.R;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double x = __ldg(xg + (int64_t)r * a.G);
+      if (x != -INFINITY) { const double d = x - gn.y; gn.D = fma(d, d, gn.D); gn.ndet++; }
+    }
+  }
+  if (a.moves & ZZ_MOVE_VARIANCE_G) {
+    int acc = 0;
+    if (!in_spike) {
+      double u1, u2, ratio;
+      if (a.draws[2]) { u1 = a.draws[2][i]; u2 = a.draws[3][i]; }
+      else { u1 = u32_open(b0[3]); u2 = u32_open(b1[0]); }
+      acc = fast_vg(H, T, gn, a.tv[i], u1, u2, ratio);
+      saw_nan |= isnan(ratio);
+      if (a.tune) { ulonglong2 w = a.win_v[i]; window_push(w, acc); a.win_v[i] = w; }   // Pr:40-50
+    }
+    if (a.dec[1]) a.dec[1][i] = (uint8_t)acc;
+  }
+  if (a.moves & ZZ_MOVE_ALLOC) {
+    double u_ai, u_w;
+    if (a.draws[4]) { u_ai = a.draws[4][i]; u_w = a.draws[5][i]; }
+    else { u_ai = u32_open(b1[1]); u_w = u32_open(b1[2]); }
+    const int word = fast_alloc(H, T, gn.y, gn.f, u_ai, u_w);
+    if (a.dec[2]) a.dec[2][i] = (uint8_t)word;
+    a.flags[i] = (uint16_t)gn.f;
+  }
+  if (!in_spike) {
+    a.Yg[i] = gn.y; a.vg[i] = gn.v; fa.lps[i] = gn.A;
+    // the reference's caches, re-expressed: XgLikelihood = beta (A + B), variance_g_probability = prior(v | Sg(y))
+    a.xglik[i] = H.beta * (gn.A + (-(double)gn.ndet * (LN_SQRT_2PI + 0.5 * gn.lv) - 0.5 * gn.D * gn.rv));
+    const double q = vg_q(H, gn.lv, gn.y);
+    double pv = vg_prior_from_q(H, gn.lv, q);
+    if (H.vub != INFINITY) pv -= plnorm_term(H, gn.y);
+    a.vgprob[i] = pv;
+  }
+  if (saw_nan) atomicOr(a.nan_flag, 1);
+}
+
+// mhSpikeAllocation (Pr:528-638) over the static list of all-zero genes; their likelihood needs no Xg (every library is -Inf)
+template <int RT>
+__global__ void __launch_bounds__(BLOCK) k_spike_fast(const FastArgs fa) {
+  __shared__ FastH H;
+  __shared__ MathTabs T;
+  const SweepArgs &a = fa.s;
+  const int chain = blockIdx.y;
+  load_fast(H, T, a.hyper + chain, fa.exp_tab, fa.log_tab);
+  const int64_t j = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (j >= fa.n_allzero) return;
+  const int64_t g = fa.allzero_idx[j];
+  if (g < a.g_begin || g >= a.g_end) return;
+  const int64_t i = (int64_t)chain * a.G + g;
+  uint32_t f = a.flags[i];
+  if (f & F_ACTIVE) { if (a.dec[3]) a.dec[3][i] = 0; return; }          // Pr:533: all-zero AND inactive
+  const bool cur_in = (f & F_INSPIKE) != 0, prop_in = !cur_in;          // Pr:535
+  double zy, zv, u;
+  if (a.draws[6]) { zy = a.draws[6][i]; zv = a.draws[7][i]; u = a.draws[8][i]; }
+  else {
+    uint32_t b2[4];
+    philox_block(a.seed, chain, a.step, 2, (uint64_t)(a.gene_offset + g), b2);
+    box_muller(u32_open(b2[0]), u32_open(b2[1]), zy, zv); u = u32_open(b2[2]);
+  }
+  const double y = a.Yg[i], v = a.vg[i];
+  const double yp = fma(H.sd_i, zy, H.im);                              // Pr:545
+  const double lsp = fma(H.s1, yp, H.s0);                               // log(Sg_proposed), Pr:547
+  const double lvp = (lsp + H.tau) + H.rtau * zv;                       // Pr:549: variance_g' = exp(.)
+  const double vp = fexp(lvp, T.exp_t);
+  double PVp = vg_prior_from_q(H, lvp, vg_q(H, lvp, yp));               // Pr:556
+  const double lv = flog(v, T.log_t);
+  double PVc = vg_prior_from_q(H, lv, vg_q(H, lv, y));                  // Pr:558
+  if (H.vub != INFINITY) { PVp -= plnorm_term(H, yp); PVc -= plnorm_term(H, y); }
+  const double dp = yp - H.im, dc = y - H.im;
+  const double pygp = prop_in ? H.log_sp : H.log_1msp - H.log_norm_i - dp * dp * H.inv2iv;   // Pr:560
+  const double pyg = cur_in ? H.log_sp : H.log_1msp - H.log_norm_i - dc * dc * H.inv2iv;     // Pr:563
+  const double pp = prop_in ? H.log_sp : (pygp + PVp);                  // Pr:569-570
+  const double pc = cur_in ? H.log_sp : (pyg + PVc);                    // Pr:572-573
+  double Ap = 0;
+  if (!prop_in) Ap = lps_only<RT>(H, T, nullptr, 0, a.gl[g] * fexp(yp, T.exp_t), true);
+  double Lp = prop_in ? H.beta * 0.0 : H.beta * Ap;                     // Pr:579 (P:117 gives log(1*1) = 0 in the spike)
+  double Lc = a.xglik[i];                                               // Pr:581
+  if (Lp == -INFINITY && Lc == -INFINITY) { Lp = 0; Lc = 0; }           // Pr:583-585
+  const double HR = prop_in ? (pyg - H.log_1msp + PVc) : -(pygp - H.log_1msp + PVp);   // Pr:592-595
+  double ratio = H.temp * (Lp - Lc + pp - pc) + HR;                     // Pr:601
+  if (vp > H.vub) ratio = -INFINITY;                                    // Pr:603
+  const int acc = (flog(u, T.log_t) < ratio);                           // Pr:605
+  if (isnan(ratio)) atomicOr(a.nan_flag, 1);
+  if (acc) f ^= F_INSPIKE;                                              // Pr:616
+  a.flags[i] = (uint16_t)f;
+  if (!prop_in) {                                                       // [proposed_out_spike_idx], Pr:620-636
+    if (acc) { a.Yg[i] = yp; a.vg[i] = vp; fa.lps[i] = Ap; }
+    a.vgprob[i] = acc ? PVp : PVc;
+  }
+  a.xglik[i] = acc ? Lp : Lc;                                           // Pr:630-632
+  if (a.dec[3]) a.dec[3][i] = (uint8_t)acc;
+}
+
+// lps <- A(Yg) for every out-of-spike gene (after anything that changed Yg or alpha_r outside the fast sweep)
+template <int RT>
+__global__ void __launch_bounds__(BLOCK) k_refresh_lps(const FastArgs fa) {
+  __shared__ FastH H;
+  __shared__ MathTabs T;
+  const SweepArgs &a = fa.s;
+  const int chain = blockIdx.y;
+  load_fast(H, T, a.hyper + chain, fa.exp_tab, fa.log_tab);
+  const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (g >= a.G) return;
+  const int64_t i = (int64_t)chain * a.G + g;
+  if (a.flags[i] & F_INSPIKE) { fa.lps[i] = 0; return; }
+  fa.lps[i] = lps_only<RT>(H, T, a.Xg + g, a.G, a.gl[g] * fexp(a.Yg[i], T.exp_t), false);
+}
+
 // exports the Philox draws of one move slot in the layout of that move's `draws` argument
 __global__ void __launch_bounds__(BLOCK) k_draws(int64_t G, int64_t gene_offset, int C, uint64_t seed, uint64_t step, int slot, double *out) {
   const int chain = blockIdx.y;
@@ -122,22 +276,24 @@ __global__ void __launch_bounds__(BLOCK) k_draws(int64_t G, int64_t gene_offset,
   if (g >= G) return;
   const int64_t i = (int64_t)chain * G + g, CG = (int64_t)C * G;
   const uint64_t gid = (uint64_t)(gene_offset + g);
-  double a, b, c, d, z0, z1;
+  uint32_t b0[4], b1[4], b2[4];
+  double z0, z1;
   switch (slot) {
     case ZZ_SLOT_YG:
-      uniform2(seed, chain, step, slot, 0, gid, a, b); box_muller(a, b, z0, z1);
-      uniform2(seed, chain, step, slot, 1, gid, c, d);
-      out[i] = z0; out[CG + i] = c; break;
-    case ZZ_SLOT_VARIANCE_G: case ZZ_SLOT_ALLOC:
-      uniform2(seed, chain, step, slot, 0, gid, a, b);
-      out[i] = a; out[CG + i] = b; break;
+      philox_block(seed, chain, step, 0, gid, b0); box_muller(u32_open(b0[0]), u32_open(b0[1]), z0, z1);
+      out[i] = z0; out[CG + i] = u32_open(b0[2]); break;
+    case ZZ_SLOT_VARIANCE_G:
+      philox_block(seed, chain, step, 0, gid, b0); philox_block(seed, chain, step, 1, gid, b1);
+      out[i] = u32_open(b0[3]); out[CG + i] = u32_open(b1[0]); break;
+    case ZZ_SLOT_ALLOC:
+      philox_block(seed, chain, step, 1, gid, b1);
+      out[i] = u32_open(b1[1]); out[CG + i] = u32_open(b1[2]); break;
     case ZZ_SLOT_ALLOC_WITHIN:
-      uniform2(seed, chain, step, slot, 0, gid, a, b);
-      out[i] = a; break;
+      philox_block(seed, chain, step, 1, gid, b1);
+      out[i] = u32_open(b1[2]); break;
     case ZZ_SLOT_SPIKE:
-      uniform2(seed, chain, step, slot, 0, gid, a, b); box_muller(a, b, z0, z1);
-      uniform2(seed, chain, step, slot, 1, gid, c, d);
-      out[i] = z0; out[CG + i] = z1; out[2 * CG + i] = c; break;
+      philox_block(seed, chain, step, 2, gid, b2); box_muller(u32_open(b2[0]), u32_open(b2[1]), z0, z1);
+      out[i] = z0; out[CG + i] = z1; out[2 * CG + i] = u32_open(b2[2]); break;
   }
 }
 
@@ -384,6 +540,8 @@ struct zz_handle {
   int32_t *iscratch;                       // 3*C*G
   int *nan_flag;
   bool have_data;
+  double *lps; double *exp_tab; double2 *log_tab; int32_t *allzero_idx; int64_t n_allzero;
+  bool lps_valid;                          // lps == A(current Yg, alpha_r) for every out-of-spike gene
   std::vector<zz_hyper> hyper_host;
   double *pinned;                          // small pinned staging for reduction results
 };
@@ -428,9 +586,8 @@ template <class T> int down(zz_handle *h, T *dst, const T *src, int64_t n) {
   return ZZ_OK;
 }
 
-int launch_sweep(zz_handle *h, uint64_t step, int tune, uint32_t moves, const double *const draws_dev[9], uint8_t *const dec_dev[4],
-                 int64_t g_begin, int64_t g_end) {
-  SweepArgs a;
+void fill_sweep_args(zz_handle *h, SweepArgs &a, uint64_t step, int tune, uint32_t moves, const double *const draws_dev[9],
+                     uint8_t *const dec_dev[4], int64_t g_begin, int64_t g_end) {
   a.G = h->G; a.g_begin = g_begin; a.g_end = g_end; a.gene_offset = h->cfg.gene_offset;
   a.C = h->C; a.R = h->R; a.K = h->K; a.tune = tune; a.moves = moves; a.seed = h->cfg.seed; a.step = step;
   a.Xg = h->Xg; a.gl = h->gl; a.Yg = h->Yg; a.vg = h->vg; a.xglik = h->xglik; a.vgprob = h->vgprob; a.ty = h->ty; a.tv = h->tv;
@@ -438,9 +595,65 @@ int launch_sweep(zz_handle *h, uint64_t step, int tune, uint32_t moves, const do
   for (int i = 0; i < 9; ++i) a.draws[i] = draws_dev ? draws_dev[i] : nullptr;
   for (int i = 0; i < 4; ++i) a.dec[i] = dec_dev ? dec_dev[i] : nullptr;
   a.nan_flag = h->nan_flag;
+}
+
+// reference-order kernel (zz_device.cuh): the move-at-a-time path and ZZ_MOVE_REFERENCE_ORDER sweeps
+int launch_sweep(zz_handle *h, uint64_t step, int tune, uint32_t moves, const double *const draws_dev[9], uint8_t *const dec_dev[4],
+                 int64_t g_begin, int64_t g_end) {
   if (g_end <= g_begin) return ZZ_OK;
+  SweepArgs a;
+  fill_sweep_args(h, a, step, tune, moves, draws_dev, dec_dev, g_begin, g_end);
   k_sweep<<<gene_grid(h, g_end - g_begin, h->C), BLOCK, 0, h->stream>>>(a);
   ZZ_LAUNCHED(h);
+  if (moves & (ZZ_MOVE_YG | ZZ_MOVE_SPIKE)) h->lps_valid = false;   // Yg moved without its A(y) being maintained
+  return ZZ_OK;
+}
+
+#define ZZ_DISPATCH_R(h, KERNEL, grid, args)                                                     \
+  do {                                                                                           \
+    switch ((h)->R) {                                                                            \
+      case 2: KERNEL<2><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                           \
+      case 4: KERNEL<4><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                           \
+      case 8: KERNEL<8><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                           \
+      case 16: KERNEL<16><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                         \
+      default: KERNEL<0><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                          \
+    }                                                                                            \
+  } while (0)
+
+void fill_fast_args(zz_handle *h, FastArgs &fa) {
+  fa.lps = h->lps; fa.exp_tab = h->exp_tab; fa.log_tab = h->log_tab; fa.allzero_idx = h->allzero_idx; fa.n_allzero = h->n_allzero;
+}
+
+int ensure_lps(zz_handle *h) {
+  if (h->lps_valid) return ZZ_OK;
+  FastArgs fa;
+  fill_sweep_args(h, fa.s, 0, 0, 0, nullptr, nullptr, 0, h->G);
+  fill_fast_args(h, fa);
+  ZZ_DISPATCH_R(h, k_refresh_lps, gene_grid(h, h->G, h->C), fa);
+  ZZ_LAUNCHED(h);
+  h->lps_valid = true;
+  return ZZ_OK;
+}
+
+// production kernels (zz_fast.cuh): main sweep over all genes + spike move over the all-zero gene list
+int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, const double *const draws_dev[9], uint8_t *const dec_dev[4],
+                      int64_t g_begin, int64_t g_end) {
+  if (g_end <= g_begin) return ZZ_OK;
+  if (int rc = ensure_lps(h)) return rc;
+  FastArgs fa;
+  fill_sweep_args(h, fa.s, step, tune, moves, draws_dev, dec_dev, g_begin, g_end);
+  fill_fast_args(h, fa);
+  if (moves & (ZZ_MOVE_YG | ZZ_MOVE_VARIANCE_G | ZZ_MOVE_ALLOC)) {
+    ZZ_DISPATCH_R(h, k_sweep_fast, gene_grid(h, g_end - g_begin, h->C), fa);
+    ZZ_LAUNCHED(h);
+  }
+  if (moves & ZZ_MOVE_SPIKE) {
+    if (dec_dev && dec_dev[3]) ZZ_CUDA(h, cudaMemsetAsync(dec_dev[3], 0, (size_t)h->C * h->G, h->stream));
+    if (h->n_allzero > 0) {
+      ZZ_DISPATCH_R(h, k_spike_fast, gene_grid(h, h->n_allzero, h->C), fa);
+      ZZ_LAUNCHED(h);
+    }
+  }
   return ZZ_OK;
 }
 
@@ -457,7 +670,9 @@ int run_moves(zz_handle *h, uint64_t step, int tune, uint32_t moves, const doubl
     for (int j = 0; j < ndraw; ++j) dd[draw_slots[j]] = h->scratch + (int64_t)j * CG;
   }
   if (decisions) for (int j = 0; j < ndec; ++j) de[dec_slots[j]] = h->dec + (int64_t)j * CG;
-  int rc = launch_sweep(h, step, tune, moves, dd, de, 0, h->G);
+  const bool reference_order = (moves & ZZ_MOVE_REFERENCE_ORDER) || (moves & ZZ_MOVE_ALLOC_WITHIN);
+  int rc = reference_order ? launch_sweep(h, step, tune, moves & ~ZZ_MOVE_REFERENCE_ORDER, dd, de, 0, h->G)
+                           : launch_sweep_fast(h, step, tune, moves, dd, de, 0, h->G);
   if (rc) return rc;
   if (decisions) {
     ZZ_CUDA(h, cudaMemcpyAsync(decisions, h->dec, (size_t)ndec * CG, cudaMemcpyDeviceToHost, h->stream));
@@ -556,6 +771,14 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   ZZ_CUDA(h, cudaMalloc(&h->scratch, sizeof(double) * 9 * CG));
   ZZ_CUDA(h, cudaMalloc(&h->dec, (size_t)4 * CG));
   ZZ_CUDA(h, cudaMalloc(&h->iscratch, sizeof(int32_t) * 3 * CG));
+  ZZ_CUDA(h, cudaMalloc(&h->lps, sizeof(double) * CG));
+  ZZ_CUDA(h, cudaMemsetAsync(h->lps, 0, sizeof(double) * CG, h->stream));
+  ZZ_CUDA(h, cudaMalloc(&h->exp_tab, sizeof(kExpTab)));
+  ZZ_CUDA(h, cudaMalloc(&h->log_tab, sizeof(kLogTab)));
+  ZZ_CUDA(h, cudaMemcpyAsync(h->exp_tab, kExpTab, sizeof(kExpTab), cudaMemcpyHostToDevice, h->stream));
+  ZZ_CUDA(h, cudaMemcpyAsync(h->log_tab, kLogTab, sizeof(kLogTab), cudaMemcpyHostToDevice, h->stream));
+  ZZ_CUDA(h, cudaMalloc(&h->allzero_idx, sizeof(int32_t) * G));
+  h->n_allzero = 0; h->lps_valid = false;
   ZZ_CUDA(h, cudaMalloc(&h->nan_flag, sizeof(int)));
   ZZ_CUDA(h, cudaMemsetAsync(h->nan_flag, 0, sizeof(int), h->stream));
   ZZ_CUDA(h, cudaMallocHost(&h->pinned, sizeof(double) * (size_t)(h->C > ZZ_MAX_LIBS ? h->C : ZZ_MAX_LIBS) * MAX_NSTAT));
@@ -571,7 +794,8 @@ void zz_destroy(zz_handle *h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   void *ptrs[] = {h->Xg, h->gl, h->Yg, h->vg, h->xglik, h->vgprob, h->ty, h->tv, h->flags, h->win_y, h->win_v, h->trace,
-                  h->hyper, h->partials, h->red_out, h->scratch, h->dec, h->iscratch, h->nan_flag};
+                  h->hyper, h->partials, h->red_out, h->scratch, h->dec, h->iscratch, h->nan_flag, h->lps, h->exp_tab,
+                  h->log_tab, h->allzero_idx};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -604,19 +828,23 @@ int zz_upload_data(zz_handle *h, const double *Xg, const double *gene_lengths) {
   ZZ_CUDA(h, cudaMemcpyAsync(h->gl, gene_lengths, sizeof(double) * G, cudaMemcpyHostToDevice, h->stream));
   // no_detect_spike (I:416-417): every library -Inf
   std::vector<uint16_t> f((size_t)h->C * G);
+  std::vector<int32_t> az;
   ZZ_CUDA(h, cudaMemcpyAsync(f.data(), h->flags, sizeof(uint16_t) * f.size(), cudaMemcpyDeviceToHost, h->stream));
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
   for (int64_t g = 0; g < G; ++g) {
     bool all = true;
     for (int r = 0; r < h->R && all; ++r) all = (Xg[(int64_t)r * G + g] == -INFINITY);
+    if (all) az.push_back((int32_t)g);
     for (int c = 0; c < h->C; ++c) {
       uint16_t &w = f[(size_t)c * G + g];
       w = (uint16_t)((w & ~F_ALLZERO) | (all ? F_ALLZERO : 0u));
     }
   }
   ZZ_CUDA(h, cudaMemcpyAsync(h->flags, f.data(), sizeof(uint16_t) * f.size(), cudaMemcpyHostToDevice, h->stream));
+  h->n_allzero = (int64_t)az.size();
+  if (!az.empty()) ZZ_CUDA(h, cudaMemcpyAsync(h->allzero_idx, az.data(), sizeof(int32_t) * az.size(), cudaMemcpyHostToDevice, h->stream));
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
-  h->have_data = true;
+  h->have_data = true; h->lps_valid = false;
   return ZZ_OK;
 }
 
@@ -627,6 +855,7 @@ int zz_set_state(zz_handle *h, int chain, const double *Yg, const double *varian
   if (int rc = chain_ok(h, chain)) return rc;
   const int64_t G = h->G, off = (int64_t)chain * G;
   int rc;
+  if (Yg || spike) h->lps_valid = false;
   if ((rc = up(h, h->Yg + off, Yg, G)) || (rc = up(h, h->vg + off, variance_g, G)) || (rc = up(h, h->xglik + off, XgLikelihood, G)) ||
       (rc = up(h, h->vgprob + off, variance_g_probability, G)) || (rc = up(h, h->ty + off, ty, G)) || (rc = up(h, h->tv + off, tv, G)))
     return rc;
@@ -672,6 +901,7 @@ int zz_set_hyper(zz_handle *h, int chain, const zz_hyper *hy) {
   if (!hy) return fail(h, ZZ_ERR_INVALID, "hyper is NULL");
   if (hy->num_libraries != h->R || hy->num_active_components != h->K)
     return fail(h, ZZ_ERR_INVALID, "hyper dimensions do not match the handle");
+  if (memcmp(h->hyper_host[chain].alpha_r, hy->alpha_r, sizeof(double) * h->R) != 0) h->lps_valid = false;  // A depends on alpha_r
   h->hyper_host[chain] = *hy;
   ZZ_CUDA(h, cudaMemcpyAsync(h->hyper + chain, &h->hyper_host[chain], sizeof(zz_hyper), cudaMemcpyHostToDevice, h->stream));
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -719,27 +949,27 @@ int zz_eval_level2_loglik(zz_handle *h, int chain, double *out) { return eval_to
 
 int zz_mh_yg(zz_handle *h, uint64_t step, int tune, const double *draws, uint8_t *decisions) {
   static const int ds[] = {0, 1}, es[] = {0};
-  return run_moves(h, step, tune, ZZ_MOVE_YG, draws, ds, 2, decisions, es, 1);
+  return run_moves(h, step, tune, ZZ_MOVE_YG | ZZ_MOVE_REFERENCE_ORDER, draws, ds, 2, decisions, es, 1);
 }
 int zz_mh_variance_g(zz_handle *h, uint64_t step, int tune, const double *draws, uint8_t *decisions) {
   static const int ds[] = {2, 3}, es[] = {1};
-  return run_moves(h, step, tune, ZZ_MOVE_VARIANCE_G, draws, ds, 2, decisions, es, 1);
+  return run_moves(h, step, tune, ZZ_MOVE_VARIANCE_G | ZZ_MOVE_REFERENCE_ORDER, draws, ds, 2, decisions, es, 1);
 }
 int zz_gibbs_alloc(zz_handle *h, uint64_t step, const double *draws, uint8_t *decisions) {
   static const int ds[] = {4, 5}, es[] = {2};
-  return run_moves(h, step, 0, ZZ_MOVE_ALLOC, draws, ds, 2, decisions, es, 1);
+  return run_moves(h, step, 0, ZZ_MOVE_ALLOC | ZZ_MOVE_REFERENCE_ORDER, draws, ds, 2, decisions, es, 1);
 }
 int zz_gibbs_alloc_within(zz_handle *h, uint64_t step, const double *draws, uint8_t *decisions) {
   static const int ds[] = {5}, es[] = {2};
-  return run_moves(h, step, 0, ZZ_MOVE_ALLOC_WITHIN, draws, ds, 1, decisions, es, 1);
+  return run_moves(h, step, 0, ZZ_MOVE_ALLOC_WITHIN | ZZ_MOVE_REFERENCE_ORDER, draws, ds, 1, decisions, es, 1);
 }
 int zz_mh_spike_alloc(zz_handle *h, uint64_t step, const double *draws, uint8_t *decisions) {
   static const int ds[] = {6, 7, 8}, es[] = {3};
-  return run_moves(h, step, 0, ZZ_MOVE_SPIKE, draws, ds, 3, decisions, es, 1);
+  return run_moves(h, step, 0, ZZ_MOVE_SPIKE | ZZ_MOVE_REFERENCE_ORDER, draws, ds, 3, decisions, es, 1);
 }
 int zz_sweep(zz_handle *h, uint64_t step, int tune, uint32_t moves, const double *draws, uint8_t *decisions) {
   static const int ds[] = {0, 1, 2, 3, 4, 5, 6, 7, 8}, es[] = {0, 1, 2, 3};
-  if (moves == 0) moves = ZZ_MOVE_FUSED;
+  if ((moves & ~ZZ_MOVE_REFERENCE_ORDER) == 0) moves |= ZZ_MOVE_FUSED;
   return run_moves(h, step, tune, moves, draws, ds, 9, decisions, es, 4);
 }
 
@@ -833,6 +1063,7 @@ int zz_px_commit(zz_handle *h, int chain, int lib, double alpha_new) {
     ZZ_LAUNCHED(h);
   }
   h->hyper_host[chain].alpha_r[lib] = alpha_new;
+  h->lps_valid = false;
   ZZ_CUDA(h, cudaMemcpyAsync(h->hyper + chain, &h->hyper_host[chain], sizeof(zz_hyper), cudaMemcpyHostToDevice, h->stream));
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
   if (h->R <= 2) {  // Pr:219: full recompute with the proposed p_x
@@ -904,7 +1135,8 @@ int zz_sweep_host(zz_handle *h, uint64_t step, int tune, double *Yg, double *var
     return rc;
   k_pack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, d_ai, d_w, d_s, h->flags);
   ZZ_LAUNCHED(h);
-  if ((rc = launch_sweep(h, step, tune, ZZ_MOVE_FUSED, nullptr, nullptr, 0, G))) return rc;
+  h->lps_valid = false;  // Yg arrived from the host: A(y) is rebuilt on the device (one extra pass; PCIe dominates this entry point)
+  if ((rc = launch_sweep_fast(h, step, tune, ZZ_MOVE_FUSED, nullptr, nullptr, 0, G))) return rc;
   k_unpack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, h->flags, d_ai, d_w, d_s);
   ZZ_LAUNCHED(h);
   if ((rc = down(h, Yg, h->Yg, G)) || (rc = down(h, variance_g, h->vg, G)) || (rc = down(h, XgLikelihood, h->xglik, G)) ||
