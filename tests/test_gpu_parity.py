@@ -125,8 +125,10 @@ def test_fused_sweep_equals_sequential_moves(G, R, seed, K, mode):
     for it in range(4):
         d = draws_for(G, 9, 50 * seed + it, normal=(0, 6, 7))
         dec_o = O.sweep(ho, s, d, tune=True)
+        before = s.copy()
         dec_g = h.sweep(step=it, tune=True, moves=MODES[mode], draws=d, decisions=True)
-        assert np.array_equal(dec_g[:, 0, :], dec_o), [np.where(dec_g[j, 0] != dec_o[j])[0][:5] for j in range(4)]
+        bad = {j: np.where(dec_g[j, 0] != dec_o[j])[0][:5] for j in range(4) if not np.array_equal(dec_g[j, 0], dec_o[j])}
+        assert not bad, (bad, {j: (before.XgLikelihood[b], before.variance_g[b], before.Yg[b], before.inactive_spike_allocation[b]) for j, b in bad.items()})
         compare_state(h, s)
     assert np.array_equal(h.window_sums()[0], s.window_sums("Yg_trace"))
     assert np.array_equal(h.window_sums()[1], s.window_sums("variance_g_trace"))
@@ -152,7 +154,7 @@ def test_production_and_reference_kernels_interleave():
     """The cached detection term A(y) of the production kernel is rebuilt whenever a reference-order move, a new alpha_r or a
     host state upload changed what it depends on."""
     G, R = 2500, 4
-    X, gl, hd, ho, hg, s, h = setup_pair(G, R, 41)
+    X, gl, hd, ho, hg, s, h = setup_pair(G, R, 41, edge_cases=False)   # no -Inf rows: px_commit turns them into NaN (as R would)
     step = 0
     for rnd in range(3):
         d = draws_for(G, 9, 70 + rnd, normal=(0, 6, 7))

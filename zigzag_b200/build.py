@@ -6,7 +6,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", "zz_gpu.cu")]
-DEPS = SRC + [os.path.join(HERE, "csrc", "zz_device.cuh"), os.path.join(HERE, "..", "include", "zigzag_gpu.h")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(HERE, "csrc")))] + \
+       [os.path.join(HERE, "..", "include", "zigzag_gpu.h")]
 OUT = os.path.join(HERE, "libzigzag_gpu.so")
 
 # -fmad=false: the kernels keep the reference's operation order (a*b+c is not contracted), see DESIGN.md "Numerics"

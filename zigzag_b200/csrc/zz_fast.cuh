@@ -156,6 +156,9 @@ __device__ __forceinline__ int fast_vg(const FastH &H, const MathTabs &T, FastGe
   const double q = vg_q(H, g.lv, g.y), qp = q + arg * H.irt;
   const double dPV = -arg - 0.5 * (qp * qp - q * q);                    // the plnorm term (P:25) does not depend on v
   ratio = H.temp * (H.beta * dB + dPV) + arg;                           // Pr:24
+  // a current XgLikelihood of -Inf (or NaN) makes Lp - Lc NaN in the reference (both sides carry the same -Inf detection
+  // term): keep that behaviour (reject + NaN flag) although the term cancels analytically here
+  if (!(g.A > -INFINITY) && H.beta != 0.0) ratio = NAN;
   if (vp > H.vub) ratio = -INFINITY;                                    // Pr:26
   const int acc = (flog(u2, T.log_t) < ratio);                          // Pr:35
   if (acc) { g.v = vp; g.lv = lvp; g.rv = rvp; }
