@@ -62,10 +62,11 @@ __device__ __forceinline__ void load_fast(FastH &H, MathTabs &T, const zz_hyper 
 
 // z = sqrt(-2 ln ua) * cos(2 pi ub)  (same draw as box_muller's z0; the sine branch is only needed by the spike move)
 __device__ __forceinline__ double normal_cos(double ua, double ub, const MathTabs &T) {
-  return sqrt(-2.0 * flog(ua, T.log_t)) * cospi(2.0 * ub);
+  return sqrt(-2.0 * flog_core(ua, T.log_t)) * cospi(2.0 * ub);   // ua in (0,1): always a normal number
 }
 
 // A(y') and the two squared-distance sums over one gene's libraries.  RT > 0: compile-time library count (unrolled).
+// `xg` / `stride` address this gene's row either in global memory (stride G) or in the block's shared-memory tile (stride BLOCK).
 template <int RT>
 __device__ __forceinline__ void lib_loop(const FastH &H, const MathTabs &T, const double *__restrict__ xg, int64_t stride,
                                          double y, double yp, double tp, double &Ap, double &D, double &Dp, int &ndet) {
@@ -73,12 +74,12 @@ __device__ __forceinline__ void lib_loop(const FastH &H, const MathTabs &T, cons
   Ap = 0; D = 0; Dp = 0; ndet = 0;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const double x = __ldg(xg + (int64_t)r * stride);
+    const double x = xg[(int64_t)r * stride];
     const bool nd = (x == -INFINITY);
     const double e = fexp_neg_clamped(tp * H.alpha[r], T.exp_t);
     const double p = 1 - e;                           // U:157
     const double q = nd ? (1 - p) : p;                // P:82 / P:84
-    Ap += flog(q, T.log_t);
+    Ap += flog_prob(q, T.log_t);
     if (!nd) {
       const double d = x - y, dp = x - yp;
       D = fma(d, d, D); Dp = fma(dp, dp, Dp);
@@ -95,10 +96,10 @@ __device__ __forceinline__ double lps_only(const FastH &H, const MathTabs &T, co
   double A = 0;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const bool nd = all_nd || (__ldg(xg + (int64_t)r * stride) == -INFINITY);
+    const bool nd = all_nd || (xg[(int64_t)r * stride] == -INFINITY);
     const double e = fexp_neg_clamped(t * H.alpha[r], T.exp_t);
     const double p = 1 - e;
-    A += flog(nd ? (1 - p) : p, T.log_t);
+    A += flog_prob(nd ? (1 - p) : p, T.log_t);
   }
   return A;
 }
@@ -139,7 +140,7 @@ __device__ __forceinline__ int fast_yg(const FastH &H, const MathTabs &T, FastGe
   if (H.vub != INFINITY) dPV -= plnorm_term(H, yp) - plnorm_term(H, g.y);
   const double dL2 = -(level2_quad(H, yp, g.f) - level2_quad(H, g.y, g.f));  // Pr:271-291
   ratio = H.temp * (dLX + dL2 + dPV);                                   // Pr:296
-  const int acc = (flog(u, T.log_t) < ratio);                           // Pr:302
+  const int acc = (flog_core(u, T.log_t) < ratio);                      // Pr:302 (u in (0,1): normal)
   g.ndet = ndet;
   if (acc) { g.y = yp; g.A = Ap; g.D = Dp; } else { g.D = D; }
   return acc;
@@ -160,7 +161,7 @@ __device__ __forceinline__ int fast_vg(const FastH &H, const MathTabs &T, FastGe
   // term): keep that behaviour (reject + NaN flag) although the term cancels analytically here
   if (!(g.A > -INFINITY) && H.beta != 0.0) ratio = NAN;
   if (vp > H.vub) ratio = -INFINITY;                                    // Pr:26
-  const int acc = (flog(u2, T.log_t) < ratio);                          // Pr:35
+  const int acc = (flog_core(u2, T.log_t) < ratio);                     // Pr:35
   if (acc) { g.v = vp; g.lv = lvp; g.rv = rvp; }
   return acc;
 }

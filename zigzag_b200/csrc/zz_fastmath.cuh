@@ -42,6 +42,18 @@ ZZ_HD double d_make(int hi, int lo) {
 #endif
 }
 
+// Polynomial / reduction constants.  On the device they live in constant memory so that DFMA takes them as a constant-bank
+// operand; as literals every use costs two UMOV (64-bit immediates are not encodable), profiles/r1_sweep_v1.md.
+#if defined(__CUDA_ARCH__)
+#define ZZ_C(i, lit) kMathC[i]
+#else
+#define ZZ_C(i, lit) (lit)
+#endif
+#if defined(__CUDACC__)
+__constant__ double kMathC[16] = {ZZ_KINVL, -ZZ_KLHI, -ZZ_KLLO, ZZ_KE4, ZZ_KE3, ZZ_KE1, -1.0 / 6, 1.0 / 5, -1.0 / 4, 1.0 / 3,
+                                  ZZ_KLN2, 4503601774854144.0, 0, 0, 0, 0};
+#endif
+
 struct MathTabs {          // lives in shared memory on the device
   double exp_t[256];       // 2^(j/256)
   double2 log_t[256];      // {IC[i], LC[i]}
@@ -50,22 +62,42 @@ struct MathTabs {          // lives in shared memory on the device
 // exp(x) for -708 <= x <= 709 (callers clamp or take the libm path outside).  9 FP64 instructions.
 ZZ_HD double fexp_core(double x, const double *__restrict__ exp_t) {
   const double magic = 6755399441055744.0;            // 1.5 * 2^52: the low word of (x*c + magic) is rint(x*c)
-  const double t = fma(x, ZZ_KINVL, magic);
+  const double t = fma(x, ZZ_C(0, ZZ_KINVL), magic);
   const int n = d_lo(t);
   const double nd = t - magic;
-  double r = fma(nd, -ZZ_KLHI, x);                    // exact: n has < 21 bits, L_hi has 32
-  r = fma(nd, -ZZ_KLLO, r);
-  double p = fma(r, ZZ_KE4, ZZ_KE3);                  // e^r = 1 + r (E1 + r (1/2 + r (E3 + r/24)))
-  p = fma(r, p, ZZ_KE2);
-  p = fma(r, p, ZZ_KE1);
+  double r = fma(nd, ZZ_C(1, -ZZ_KLHI), x);           // exact: n has < 21 bits, L_hi has 32
+  r = fma(nd, ZZ_C(2, -ZZ_KLLO), r);
+  double p = fma(r, ZZ_C(3, ZZ_KE4), ZZ_C(4, ZZ_KE3)); // e^r = 1 + r (E1 + r (1/2 + r (E3 + r/24)))
+  p = fma(r, p, 0.5);
+  p = fma(r, p, ZZ_C(5, ZZ_KE1));
   p = fma(r, p, 1.0);
   const double s = exp_t[n & 255] * p;
   return d_make(d_hi(s) + ((n >> 8) << 20), d_lo(s)); // * 2^k by exponent-field addition (result is normal here)
 }
 
+// libm fallbacks, kept out of line so the (rare) special cases do not bloat the unrolled loops
+#if defined(__CUDACC__)
+__device__ __noinline__ double slow_exp(double x) { return exp(x); }
+__device__ __noinline__ double slow_log(double x) { return log(x); }
+#endif
+ZZ_HD double libm_exp(double x) {
+#if defined(__CUDA_ARCH__)
+  return slow_exp(x);
+#else
+  return exp(x);
+#endif
+}
+ZZ_HD double libm_log(double x) {
+#if defined(__CUDA_ARCH__)
+  return slow_log(x);
+#else
+  return log(x);
+#endif
+}
+
 // general exp: libm outside the range where the exponent-field trick is valid (rare, warp-divergent)
 ZZ_HD double fexp(double x, const double *__restrict__ exp_t) {
-  if (!(fabs(x) <= 708.0)) return exp(x);
+  if (!(fabs(x) <= 708.0)) return libm_exp(x);
   return fexp_core(x, exp_t);
 }
 
@@ -88,19 +120,25 @@ ZZ_HD double flog_core(double x, const double2 *__restrict__ log_t) {
   const double2 tc = log_t[i];
   const double r = fma(m, tc.x, -1.0);                // exact (IC has <= 10 significant bits)
   const double r2 = r * r;
-  double s = fma(r, -1.0 / 6, 1.0 / 5);               // log1p(r) = r + r^2 (-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6)
-  s = fma(r, s, -1.0 / 4);
-  s = fma(r, s, 1.0 / 3);
+  double s = fma(r, ZZ_C(6, -1.0 / 6), ZZ_C(7, 1.0 / 5));  // log1p(r) = r + r^2 (-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6)
+  s = fma(r, s, ZZ_C(8, -1.0 / 4));
+  s = fma(r, s, ZZ_C(9, 1.0 / 3));
   s = fma(r, s, -0.5);
   const double lo = fma(r2, s, r);
-  const double kd = d_make(0x43300000, k ^ 0x80000000) - 4503601774854144.0;  // int -> double without I2F: 2^52 + 2^31 bias
-  return fma(kd, ZZ_KLN2, tc.y) + lo;
+  const double kd = d_make(0x43300000, k ^ 0x80000000) - ZZ_C(11, 4503601774854144.0);  // int -> double without I2F: 2^52 + 2^31 bias
+  return fma(kd, ZZ_C(10, ZZ_KLN2), tc.y) + lo;
 }
 
 ZZ_HD double flog(double x, const double2 *__restrict__ log_t) {
   const unsigned hi = (unsigned)d_hi(x);
-  if (hi - 0x00100000u >= 0x7FE00000u) return log(x);  // x <= 0 (incl. -0), subnormal, Inf, NaN: libm semantics
+  if (hi - 0x00100000u >= 0x7FE00000u) return libm_log(x);  // x <= 0 (incl. -0), subnormal, Inf, NaN: libm semantics
   return flog_core(x, log_t);
+}
+
+// log(q) for q known to be +0 or a normal number in (0, 1] (a detection probability or its complement): branch-free
+ZZ_HD double flog_prob(double q, const double2 *__restrict__ log_t) {
+  const double l = flog_core(q, log_t);
+  return ((d_hi(q) | d_lo(q)) == 0) ? -INFINITY : l;
 }
 
 }  // namespace zz

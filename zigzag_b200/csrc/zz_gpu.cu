@@ -123,14 +123,26 @@ struct FastArgs {
   const int32_t *allzero_idx; int64_t n_allzero;   // static list of genes with no reads in any library (I:416-421)
 };
 
+// RT > 0: the block's Xg tile [RT][BLOCK] is staged in shared memory with cp.async issued before anything else, so its HBM
+// latency overlaps the hyper/table load, Philox and the proposal arithmetic; each thread only ever reads its own column, so
+// cp.async.wait_group is the only synchronisation needed.
 template <int RT>
 __global__ void __launch_bounds__(BLOCK) k_sweep_fast(const FastArgs fa) {
   __shared__ FastH H;
   __shared__ MathTabs T;
+  extern __shared__ double xtile[];
   const SweepArgs &a = fa.s;
   const int chain = blockIdx.y;
-  load_fast(H, T, a.hyper + chain, fa.exp_tab, fa.log_tab);
   const int64_t g = a.g_begin + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (RT > 0 && g < a.g_end) {
+    const double *src = a.Xg + g;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xtile + threadIdx.x);
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (uint32_t)(r * BLOCK * 8)), "l"(src + (int64_t)r * a.G));
+    asm volatile("cp.async.commit_group;");
+  }
+  load_fast(H, T, a.hyper + chain, fa.exp_tab, fa.log_tab);
   if (g >= a.g_end) return;
   const int64_t i = (int64_t)chain * a.G + g;
   const uint64_t gid = (uint64_t)(a.gene_offset + g);
@@ -138,7 +150,8 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_fast(const FastArgs fa) {
   gn.y = a.Yg[i]; gn.v = a.vg[i]; gn.A = fa.lps[i]; gn.f = a.flags[i];
   gn.D = 0; gn.ndet = 0; gn.lv = 0; gn.rv = 0;
   const double gl = a.gl[g];
-  const double *xg = a.Xg + g;
+  const double *xg = RT > 0 ? xtile + threadIdx.x : a.Xg + g;
+  const int64_t xstride = RT > 0 ? BLOCK : a.G;
   const bool in_spike = (gn.f & F_INSPIKE) != 0;   // mhYg / mhVariance_g only touch out_spike_idx (Pr:11, Pr:252-257)
   bool saw_nan = false;
   uint32_t b0[4] = {0, 0, 0, 0}, b1[4] = {0, 0, 0, 0};
@@ -152,16 +165,19 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_fast(const FastArgs fa) {
       double z, u, ratio;
       if (a.draws[0]) { z = a.draws[0][i]; u = a.draws[1][i]; }
       else { z = normal_cos(u32_open(b0[0]), u32_open(b0[1]), T); u = u32_open(b0[2]); }
-      acc = fast_yg<RT>(H, T, gn, xg, a.G, gl, a.ty[i], z, u, ratio);
+      const double ty = a.ty[i];
+      if (RT > 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+      acc = fast_yg<RT>(H, T, gn, xg, xstride, gl, ty, z, u, ratio);
       saw_nan |= isnan(ratio);
       if (a.tune) { ulonglong2 w = a.win_y[i]; window_push(w, acc); a.win_y[i] = w; }   // Pr:312-322
     }
     if (a.dec[0]) a.dec[0][i] = (uint8_t)acc;
   } else if (!in_spike) {            // D(y), n_det are still needed by mhVariance_g and the XgLikelihood cache
     const int R = RT > 0 ? RT : H.R;
+    if (RT > 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const double x = __ldg(xg + (int64_t)r * a.G);
+      const double x = xg[(int64_t)r * xstride];
       if (x != -INFINITY) { const double d = x - gn.y; gn.D = fma(d, d, gn.D); gn.ndet++; }
     }
   }
@@ -609,13 +625,13 @@ int launch_sweep(zz_handle *h, uint64_t step, int tune, uint32_t moves, const do
   return ZZ_OK;
 }
 
-#define ZZ_DISPATCH_R(h, KERNEL, grid, args)                                                     \
+#define ZZ_DISPATCH_R(h, KERNEL, grid, smem_per_lib, args)                                       \
   do {                                                                                           \
     switch ((h)->R) {                                                                            \
-      case 2: KERNEL<2><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                           \
-      case 4: KERNEL<4><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                           \
-      case 8: KERNEL<8><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                           \
-      case 16: KERNEL<16><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                         \
+      case 2: KERNEL<2><<<grid, BLOCK, 2 * (smem_per_lib), (h)->stream>>>(args); break;          \
+      case 4: KERNEL<4><<<grid, BLOCK, 4 * (smem_per_lib), (h)->stream>>>(args); break;          \
+      case 8: KERNEL<8><<<grid, BLOCK, 8 * (smem_per_lib), (h)->stream>>>(args); break;          \
+      case 16: KERNEL<16><<<grid, BLOCK, 16 * (smem_per_lib), (h)->stream>>>(args); break;       \
       default: KERNEL<0><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                          \
     }                                                                                            \
   } while (0)
@@ -629,7 +645,7 @@ int ensure_lps(zz_handle *h) {
   FastArgs fa;
   fill_sweep_args(h, fa.s, 0, 0, 0, nullptr, nullptr, 0, h->G);
   fill_fast_args(h, fa);
-  ZZ_DISPATCH_R(h, k_refresh_lps, gene_grid(h, h->G, h->C), fa);
+  ZZ_DISPATCH_R(h, k_refresh_lps, gene_grid(h, h->G, h->C), 0, fa);
   ZZ_LAUNCHED(h);
   h->lps_valid = true;
   return ZZ_OK;
@@ -644,13 +660,13 @@ int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, con
   fill_sweep_args(h, fa.s, step, tune, moves, draws_dev, dec_dev, g_begin, g_end);
   fill_fast_args(h, fa);
   if (moves & (ZZ_MOVE_YG | ZZ_MOVE_VARIANCE_G | ZZ_MOVE_ALLOC)) {
-    ZZ_DISPATCH_R(h, k_sweep_fast, gene_grid(h, g_end - g_begin, h->C), fa);
+    ZZ_DISPATCH_R(h, k_sweep_fast, gene_grid(h, g_end - g_begin, h->C), BLOCK * sizeof(double), fa);
     ZZ_LAUNCHED(h);
   }
   if (moves & ZZ_MOVE_SPIKE) {
     if (dec_dev && dec_dev[3]) ZZ_CUDA(h, cudaMemsetAsync(dec_dev[3], 0, (size_t)h->C * h->G, h->stream));
     if (h->n_allzero > 0) {
-      ZZ_DISPATCH_R(h, k_spike_fast, gene_grid(h, h->n_allzero, h->C), fa);
+      ZZ_DISPATCH_R(h, k_spike_fast, gene_grid(h, h->n_allzero, h->C), 0, fa);
       ZZ_LAUNCHED(h);
     }
   }
