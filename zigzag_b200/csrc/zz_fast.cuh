@@ -7,7 +7,8 @@
 //       A(y)    = sum_r log(1 - p_gr) | log(p_gr)           (needs exp+log per library; depends on y and alpha only)
 //       B(y, v) = -n_det (ln sqrt(2 pi) + 0.5 log v) - 0.5 D(y) / v,  D(y) = sum_detected (x_gr - y)^2
 //     A(current y) is carried per gene in HBM (`lps`), so mhYg evaluates exp/log only for the PROPOSED y and
-//     mhVariance_g needs no per-library transcendental at all.
+//     mhVariance_g needs no per-library transcendental at all.  D(y) = ss + n_det (xbar - y)^2 comes from per-gene data
+//     statistics prepared once at upload, so the sweep never re-reads the G x R matrix Xg.
 //   * log(Sg) = log(exp(s0 + s1 y)) (P:20 via U:146) is taken as s0 + s1 y; divisions by hyper-parameter constants
 //     become multiplications by reciprocals hoisted to shared memory; Lk of gibbsAllocationWithinActive (Pr:375) reuses
 //     the w_k * exp(.) terms of gibbsAllocationActiveInactive (Pr:344); floor(cum/u) == 0 (Pr:400-402) is evaluated
@@ -65,43 +66,35 @@ __device__ __forceinline__ double normal_cos(double ua, double ub, const MathTab
   return sqrt(-2.0 * flog_core(ua, T.log_t)) * cospi(2.0 * ub);   // ua in (0,1): always a normal number
 }
 
-// A(y') and the two squared-distance sums over one gene's libraries.  RT > 0: compile-time library count (unrolled).
-// `xg` / `stride` address this gene's row either in global memory (stride G) or in the block's shared-memory tile (stride BLOCK).
-template <int RT>
-__device__ __forceinline__ void lib_loop(const FastH &H, const MathTabs &T, const double *__restrict__ xg, int64_t stride,
-                                         double y, double yp, double tp, double &Ap, double &D, double &Dp, int &ndet) {
-  const int R = RT > 0 ? RT : H.R;
-  Ap = 0; D = 0; Dp = 0; ndet = 0;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const double x = xg[(int64_t)r * stride];
-    const bool nd = (x == -INFINITY);
-    const double e = fexp_neg_clamped(tp * H.alpha[r], T.exp_t);
-    const double p = 1 - e;                           // U:157
-    const double q = nd ? (1 - p) : p;                // P:82 / P:84
-    Ap += flog_prob(q, T.log_t);
-    if (!nd) {
-      const double d = x - y, dp = x - yp;
-      D = fma(d, d, D); Dp = fma(dp, dp, Dp);
-      ndet++;
-    }
-  }
+// Per-gene sufficient statistics of the DATA, computed once at zz_upload_data (k_prepare_data): the normal part of
+// computeXgLikelihood depends on Xg only through  sum_detected (x - y)^2 = ss + n_det (xbar - y)^2  (all terms >= 0, so no
+// cancellation), and the detection part only through which libraries are -Inf.  The sweep therefore never re-reads Xg.
+struct GeneData {
+  uint64_t nd_mask;   // bit r set <=> Xg[g, r] == -Inf
+  double xbar, ss;    // mean of the detected x, sum of squared deviations from it
+  int ndet;           // number of detected libraries
+};
+
+__device__ __forceinline__ double sqdist(const GeneData &d, double y) {   // D(y) = sum_detected (x - y)^2
+  const double t = d.xbar - y;
+  return fma((double)d.ndet * t, t, d.ss);
 }
 
-// A(y) alone (cache refresh / spike proposals): sum_r log(nd ? 1-p : p)
+// A(y) = sum_r log(nd_r ? 1 - p_r : p_r),  p_r = 1 - exp(-t alpha_r),  t = gl * exp(y)     (U:157, P:82-84)
 template <int RT>
-__device__ __forceinline__ double lps_only(const FastH &H, const MathTabs &T, const double *__restrict__ xg, int64_t stride,
-                                           double t, bool all_nd) {
+__device__ __forceinline__ double detect_logsum(const FastH &H, const MathTabs &T, uint64_t nd_mask, double t) {
   const int R = RT > 0 ? RT : H.R;
   double A = 0;
+  unsigned zero_seen = 0xFFFFFFFFu;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const bool nd = all_nd || (xg[(int64_t)r * stride] == -INFINITY);
     const double e = fexp_neg_clamped(t * H.alpha[r], T.exp_t);
     const double p = 1 - e;
-    A += flog_prob(nd ? (1 - p) : p, T.log_t);
+    const double q = ((nd_mask >> r) & 1ull) ? (1 - p) : p;
+    A += flog_core(q, T.log_t);                       // q is +0 or a normal number in (0, 1]
+    zero_seen = min(zero_seen, (unsigned)(d_hi(q) | d_lo(q)));
   }
-  return A;
+  return zero_seen == 0 ? -INFINITY : A;              // some q == 0: log(0) = -Inf (flog_core(0) itself is finite garbage)
 }
 
 __device__ __forceinline__ double level2_quad(const FastH &H, double y, uint32_t f) {   // (y - mean)^2 / (2 var) of the gene's component
@@ -113,8 +106,6 @@ __device__ __forceinline__ double level2_quad(const FastH &H, double y, uint32_t
 struct FastGene {
   double y, v, lv, rv;     // Yg, variance_g, log(variance_g), 1/variance_g
   double A;                // sum of the detection log-terms at y
-  double D;                // sum_detected (x - y)^2
-  int ndet;
   uint32_t f;
 };
 
@@ -126,34 +117,37 @@ __device__ __forceinline__ double plnorm_term(const FastH &H, double y) {   // o
   return plnorm_log(H.vub, fma(H.s1, y, H.s0) + H.tau, H.rtau);
 }
 
-// mhYg (Pr:250-333).  On entry g.D / g.ndet are undefined; on exit they refer to the (possibly updated) g.y.
+// XgLikelihood = beta (A + B),  B = -n_det (ln sqrt(2 pi) + 0.5 log v) - 0.5 D(y) / v      (P:57-127 re-expressed)
+__device__ __forceinline__ double xg_lik_fast(const FastH &H, const FastGene &g, const GeneData &d) {
+  return H.beta * (g.A + (-(double)d.ndet * (LN_SQRT_2PI + 0.5 * g.lv) - 0.5 * sqdist(d, g.y) * g.rv));
+}
+
+// mhYg (Pr:250-333)
 template <int RT>
-__device__ __forceinline__ int fast_yg(const FastH &H, const MathTabs &T, FastGene &g, const double *__restrict__ xg, int64_t stride,
-                                       double gl, double ty, double z, double u, double &ratio) {
+__device__ __forceinline__ int fast_yg(const FastH &H, const MathTabs &T, FastGene &g, const GeneData &d, double gl, double ty,
+                                       double z, double u, double &ratio) {
   const double yp = g.y + ty * z;                                       // Pr:257
-  const double tp = gl * fexp(yp, T.exp_t);                             // U:157
-  double Ap, D, Dp; int ndet;
-  lib_loop<RT>(H, T, xg, stride, g.y, yp, tp, Ap, D, Dp, ndet);
-  const double dLX = H.beta * ((Ap - g.A) - 0.5 * (Dp - D) * g.rv);     // XgLik' - XgLik
+  const double Ap = detect_logsum<RT>(H, T, d.nd_mask, gl * fexp(yp, T.exp_t));   // Pr:261-265
+  const double dLX = H.beta * ((Ap - g.A) - 0.5 * (sqdist(d, yp) - sqdist(d, g.y)) * g.rv);   // XgLik' - XgLik
   const double q = vg_q(H, g.lv, g.y), qp = vg_q(H, g.lv, yp);
   double dPV = -0.5 * (qp * qp - q * q);                                // Pr:267 - cache
   if (H.vub != INFINITY) dPV -= plnorm_term(H, yp) - plnorm_term(H, g.y);
   const double dL2 = -(level2_quad(H, yp, g.f) - level2_quad(H, g.y, g.f));  // Pr:271-291
   ratio = H.temp * (dLX + dL2 + dPV);                                   // Pr:296
   const int acc = (flog_core(u, T.log_t) < ratio);                      // Pr:302 (u in (0,1): normal)
-  g.ndet = ndet;
-  if (acc) { g.y = yp; g.A = Ap; g.D = Dp; } else { g.D = D; }
+  if (acc) { g.y = yp; g.A = Ap; }
   return acc;
 }
 
 // mhVariance_g (Pr:7-56): no per-library work, p_x does not depend on variance_g
-__device__ __forceinline__ int fast_vg(const FastH &H, const MathTabs &T, FastGene &g, double tv, double u1, double u2, double &ratio) {
+__device__ __forceinline__ int fast_vg(const FastH &H, const MathTabs &T, FastGene &g, const GeneData &d, double tv, double u1,
+                                       double u2, double &ratio) {
   const double arg = tv * (u1 - 0.5);                                   // MP:5; HR = log(sf) = arg (Pr:15)
   const double sf = fexp(arg, T.exp_t);
   const double vp = g.v * sf;                                           // MP:7
   const double rvp = g.rv * fexp(-arg, T.exp_t);                        // 1 / v'
   const double lvp = g.lv + arg;
-  const double dB = -(double)g.ndet * (0.5 * arg) - 0.5 * g.D * (rvp - g.rv);
+  const double dB = -(double)d.ndet * (0.5 * arg) - 0.5 * sqdist(d, g.y) * (rvp - g.rv);
   const double q = vg_q(H, g.lv, g.y), qp = q + arg * H.irt;
   const double dPV = -arg - 0.5 * (qp * qp - q * q);                    // the plnorm term (P:25) does not depend on v
   ratio = H.temp * (H.beta * dB + dPV) + arg;                           // Pr:24
@@ -198,6 +192,44 @@ __device__ __forceinline__ int fast_alloc(const FastH &H, const MathTabs &T, dou
     f = flag_set_k(f, kn);
   }
   return flag_k(f);
+}
+
+// ---- sufficient statistics accumulated by the sweep itself (layout: zz_suffstats in include/zigzag_gpu.h) --------------
+constexpr int NSTAT_FIXED_ = 10;
+constexpr int MAX_NSTAT_ = 3 * (ZZ_MAX_COMP + 1) + NSTAT_FIXED_;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp writes the sufficient statistics of its 32-gene tile to its own row of `partials` (no atomics, no block
+// barrier; k_reduce_final adds the rows in a fixed order, so the result does not depend on the dynamic tile schedule).
+__device__ __forceinline__ void stats_tile(double *row, int K, bool valid, double y, double lv, uint32_t f, double xglik,
+                                           double vgprob, bool finite_state) {
+  const int K1 = K + 1, lane = threadIdx.x & 31;
+  const bool act = f & F_ACTIVE, sp = f & F_INSPIKE;
+  const int comp = act ? flag_k(f) : 0;                                 // Pr:415 all_allocations
+  const bool use_y = valid && (act || !sp);
+  for (int c = 0; c < K1; ++c) {
+    const unsigned m = __ballot_sync(0xffffffffu, valid && comp == c);
+    const bool mine = use_y && comp == c;
+    const double sy = warp_sum(mine ? y : 0.0), sy2 = warp_sum(mine ? y * y : 0.0);
+    if (lane == 0) { row[c] = (double)__popc(m); row[K1 + c] = sy; row[2 * K1 + c] = sy2; }
+  }
+  const bool out = valid && !sp;
+  const unsigned m_sp = __ballot_sync(0xffffffffu, valid && sp), m_out = __ballot_sync(0xffffffffu, out);
+  const unsigned m_nan = __ballot_sync(0xffffffffu, valid && !finite_state);
+  const double z = out ? lv : 0.0, yo = out ? y : 0.0;
+  const double s2 = warp_sum(z), s3 = warp_sum(z * z), s4 = warp_sum(yo), s5 = warp_sum(yo * yo), s6 = warp_sum(yo * z);
+  const double s7 = warp_sum(valid ? xglik : 0.0), s8 = warp_sum(out ? vgprob : 0.0);
+  if (lane == 0) {
+    double *fx = row + 3 * K1;
+    fx[0] = (double)__popc(m_sp); fx[1] = (double)__popc(m_out);
+    fx[2] = s2; fx[3] = s3; fx[4] = s4; fx[5] = s5; fx[6] = s6; fx[7] = s7; fx[8] = s8;
+    fx[9] = (double)__popc(m_nan);
+  }
 }
 
 }  // namespace zz

@@ -42,17 +42,13 @@ ZZ_HD double d_make(int hi, int lo) {
 #endif
 }
 
-// Polynomial / reduction constants.  On the device they live in constant memory so that DFMA takes them as a constant-bank
-// operand; as literals every use costs two UMOV (64-bit immediates are not encodable), profiles/r1_sweep_v1.md.
-#if defined(__CUDA_ARCH__)
-#define ZZ_C(i, lit) kMathC[i]
-#else
-#define ZZ_C(i, lit) (lit)
-#endif
-#if defined(__CUDACC__)
-__constant__ double kMathC[16] = {ZZ_KINVL, -ZZ_KLHI, -ZZ_KLLO, ZZ_KE4, ZZ_KE3, ZZ_KE1, -1.0 / 6, 1.0 / 5, -1.0 / 4, 1.0 / 3,
-                                  ZZ_KLN2, 4503601774854144.0, 0, 0, 0, 0};
-#endif
+// Polynomial coefficients.  sm_100a FP64 instructions encode a double immediate only through its high 32 bits, any other
+// literal costs two UMOV (or an LDC) per use (profiles/r1_sweep_v1.md).  High-order coefficients are therefore rounded
+// to 20 fraction bits (their rounding error is multiplied by r^4..r^6 and vanishes below 1e-19); the few that need full
+// precision are kept in registers by the compiler.
+#define ZZ_E4_IMM 0x1.55555p-5    /* 1/24  (error * r^4 < 1e-19) */
+#define ZZ_L5_IMM 0x1.9999ap-3    /* 1/5   (error * r^5 < 1e-19) */
+#define ZZ_L6_IMM (-0x1.55555p-3) /* -1/6  (error * r^6 < 1e-21) */
 
 struct MathTabs {          // lives in shared memory on the device
   double exp_t[256];       // 2^(j/256)
@@ -62,14 +58,14 @@ struct MathTabs {          // lives in shared memory on the device
 // exp(x) for -708 <= x <= 709 (callers clamp or take the libm path outside).  9 FP64 instructions.
 ZZ_HD double fexp_core(double x, const double *__restrict__ exp_t) {
   const double magic = 6755399441055744.0;            // 1.5 * 2^52: the low word of (x*c + magic) is rint(x*c)
-  const double t = fma(x, ZZ_C(0, ZZ_KINVL), magic);
+  const double t = fma(x, ZZ_KINVL, magic);
   const int n = d_lo(t);
   const double nd = t - magic;
-  double r = fma(nd, ZZ_C(1, -ZZ_KLHI), x);           // exact: n has < 21 bits, L_hi has 32
-  r = fma(nd, ZZ_C(2, -ZZ_KLLO), r);
-  double p = fma(r, ZZ_C(3, ZZ_KE4), ZZ_C(4, ZZ_KE3)); // e^r = 1 + r (E1 + r (1/2 + r (E3 + r/24)))
+  double r = fma(nd, -ZZ_KLHI, x);                    // exact: n has < 21 bits, L_hi has 32
+  r = fma(nd, -ZZ_KLLO, r);
+  double p = fma(r, ZZ_E4_IMM, ZZ_KE3);               // e^r = 1 + r (1 + r (1/2 + r (E3 + r/24))); E3 carries the economised r^5 term
   p = fma(r, p, 0.5);
-  p = fma(r, p, ZZ_C(5, ZZ_KE1));
+  p = fma(r, p, 1.0);                                 // (the economised linear coefficient is 1 - 8.9e-15: taken as 1, error 1e-17)
   p = fma(r, p, 1.0);
   const double s = exp_t[n & 255] * p;
   return d_make(d_hi(s) + ((n >> 8) << 20), d_lo(s)); // * 2^k by exponent-field addition (result is normal here)
@@ -106,9 +102,8 @@ ZZ_HD double fexp(double x, const double *__restrict__ exp_t) {
 // the values; +Inf clamps too; NaN cannot pass through here unnoticed because (x - y)^2 is NaN as well).
 ZZ_HD double fexp_neg_clamped(double a, const double *__restrict__ exp_t) {
   const int hi = d_hi(a);
-  const int hc = hi < 0x4085E000 ? hi : 0x4085E000;   // 0x4085E000_00000000 = 700.0
-  const double ac = d_make(hc, hi < 0x4085E000 ? d_lo(a) : 0);
-  return fexp_core(-ac, exp_t);
+  const int hc = hi < 0x4085E000 ? hi : 0x4085E000;   // 0x4085E000_00000000 = 700.0; the low word is kept (< 700.0000002)
+  return fexp_core(-d_make(hc, d_lo(a)), exp_t);
 }
 
 // log(x) for positive normal finite x.  10 FP64 instructions.
@@ -120,13 +115,12 @@ ZZ_HD double flog_core(double x, const double2 *__restrict__ log_t) {
   const double2 tc = log_t[i];
   const double r = fma(m, tc.x, -1.0);                // exact (IC has <= 10 significant bits)
   const double r2 = r * r;
-  double s = fma(r, ZZ_C(6, -1.0 / 6), ZZ_C(7, 1.0 / 5));  // log1p(r) = r + r^2 (-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6)
-  s = fma(r, s, ZZ_C(8, -1.0 / 4));
-  s = fma(r, s, ZZ_C(9, 1.0 / 3));
+  double s = fma(r, ZZ_L6_IMM, ZZ_L5_IMM);            // log1p(r) = r + r^2 (-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6)
+  s = fma(r, s, -0.25);
+  s = fma(r, s, 1.0 / 3);
   s = fma(r, s, -0.5);
   const double lo = fma(r2, s, r);
-  const double kd = d_make(0x43300000, k ^ 0x80000000) - ZZ_C(11, 4503601774854144.0);  // int -> double without I2F: 2^52 + 2^31 bias
-  return fma(kd, ZZ_C(10, ZZ_KLN2), tc.y) + lo;
+  return fma((double)k, ZZ_KLN2, tc.y) + lo;           // (double)k: I2F on the otherwise idle XU pipe
 }
 
 ZZ_HD double flog(double x, const double2 *__restrict__ log_t) {
@@ -140,5 +134,8 @@ ZZ_HD double flog_prob(double q, const double2 *__restrict__ log_t) {
   const double l = flog_core(q, log_t);
   return ((d_hi(q) | d_lo(q)) == 0) ? -INFINITY : l;
 }
+
+// (w + 0.5) * 2^-32 in one fma (both products are exact, so this equals the two-step form bit for bit)
+ZZ_HD double u32_to_open01(uint32_t w) { return fma((double)w, 0x1p-32, 0x1p-33); }
 
 }  // namespace zz

@@ -25,6 +25,7 @@ namespace {
 
 constexpr int BLOCK = 256;
 constexpr int RED_BLOCKS = 148 * 4;  // persistent-style reduction grid: 4 CTAs per SM
+constexpr int SW_CHUNKS = 64;        // first-level chunks of the sweep-statistics reduction
 
 // ------------------------------------------------------------------------------------------------ kernels
 
@@ -121,99 +122,127 @@ struct FastArgs {
   double *lps;                      // [C][G] A(y): sum of the detection log-terms at the current Yg
   const double *exp_tab; const double2 *log_tab;
   const int32_t *allzero_idx; int64_t n_allzero;   // static list of genes with no reads in any library (I:416-421)
+  const uint64_t *nd_mask; const double *xbar, *xss;  // per-gene data statistics (k_prepare_data)
+  unsigned *tile_counter;           // [C] dynamic warp-tile scheduler (monotone; `tile_base` is its value at launch)
+  unsigned tile_base;
+  double *partials;                 // [C][rows][nstat] per-warp-tile sufficient statistics (rows = main tiles + spike tiles)
+  int64_t rows_per_chain, spike_row0;
+  int want_stats, do_spike_move;
 };
 
-// RT > 0: the block's Xg tile [RT][BLOCK] is staged in shared memory with cp.async issued before anything else, so its HBM
-// latency overlaps the hyper/table load, Philox and the proposal arithmetic; each thread only ever reads its own column, so
-// cp.async.wait_group is the only synchronisation needed.
+// Xg [R][G] -> per-gene (nd_mask, n_det via popcount, xbar, ss); run once per zz_upload_data
+__global__ void __launch_bounds__(BLOCK) k_prepare_data(int64_t G, int R, const double *__restrict__ Xg, uint64_t *nd_mask, double *xbar, double *xss) {
+  const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (g >= G) return;
+  uint64_t m = 0; double s = 0; int n = 0;
+  for (int r = 0; r < R; ++r) {
+    const double x = Xg[(int64_t)r * G + g];
+    if (x == -INFINITY) m |= (1ull << r); else { s += x; n++; }
+  }
+  const double mean = n > 0 ? s / n : 0.0;
+  double ss = 0, c = 0;
+  for (int r = 0; r < R; ++r) {
+    const double x = Xg[(int64_t)r * G + g];
+    if (x != -INFINITY) { const double d = x - mean; ss = fma(d, d, ss); c += d; }
+  }
+  // `mean` is rounded: sum (x - y)^2 = ss + 2 (mean - y) c + n (mean - y)^2 with c = sum (x - mean) ~ 1e-16; fold the exact
+  // correction of the mean so that the cross term vanishes to second order
+  const double mean2 = n > 0 ? mean + c / n : 0.0;
+  ss = n > 0 ? ss - c * c / n : 0.0;
+  nd_mask[g] = m; xbar[g] = mean2; xss[g] = ss < 0 ? 0.0 : ss;
+}
+
+// Persistent kernel: blockIdx.y = chain; every WARP pulls 32-gene tiles from the chain's atomic counter, so there is one
+// table/hyper load + one barrier per block for the whole sweep and warps never wait for each other afterwards.
 template <int RT>
-__global__ void __launch_bounds__(BLOCK) k_sweep_fast(const FastArgs fa) {
+__global__ void __launch_bounds__(BLOCK, 3) k_sweep_fast(const FastArgs fa) {
   __shared__ FastH H;
   __shared__ MathTabs T;
-  extern __shared__ double xtile[];
   const SweepArgs &a = fa.s;
-  const int chain = blockIdx.y;
-  const int64_t g = a.g_begin + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (RT > 0 && g < a.g_end) {
-    const double *src = a.Xg + g;
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xtile + threadIdx.x);
-#pragma unroll
-    for (int r = 0; r < RT; ++r)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (uint32_t)(r * BLOCK * 8)), "l"(src + (int64_t)r * a.G));
-    asm volatile("cp.async.commit_group;");
-  }
+  const int chain = blockIdx.y, lane = threadIdx.x & 31;
   load_fast(H, T, a.hyper + chain, fa.exp_tab, fa.log_tab);
-  if (g >= a.g_end) return;
-  const int64_t i = (int64_t)chain * a.G + g;
-  const uint64_t gid = (uint64_t)(a.gene_offset + g);
-  FastGene gn;
-  gn.y = a.Yg[i]; gn.v = a.vg[i]; gn.A = fa.lps[i]; gn.f = a.flags[i];
-  gn.D = 0; gn.ndet = 0; gn.lv = 0; gn.rv = 0;
-  const double gl = a.gl[g];
-  const double *xg = RT > 0 ? xtile + threadIdx.x : a.Xg + g;
-  const int64_t xstride = RT > 0 ? BLOCK : a.G;
-  const bool in_spike = (gn.f & F_INSPIKE) != 0;   // mhYg / mhVariance_g only touch out_spike_idx (Pr:11, Pr:252-257)
+  const int64_t n = a.g_end - a.g_begin;
+  const unsigned ntiles = (unsigned)((n + 31) / 32);
+  const int nstat = 3 * (a.K + 1) + NSTAT_FIXED_;
   bool saw_nan = false;
-  uint32_t b0[4] = {0, 0, 0, 0}, b1[4] = {0, 0, 0, 0};
-  if (!a.draws[0] && (a.moves & (ZZ_MOVE_YG | ZZ_MOVE_VARIANCE_G))) philox_block(a.seed, chain, a.step, 0, gid, b0);
-  if (!a.draws[3] && (a.moves & (ZZ_MOVE_VARIANCE_G | ZZ_MOVE_ALLOC))) philox_block(a.seed, chain, a.step, 1, gid, b1);
-  if (!in_spike) { gn.lv = flog(gn.v, T.log_t); gn.rv = 1.0 / gn.v; }
-
-  if (a.moves & ZZ_MOVE_YG) {
-    int acc = 0;
-    if (!in_spike) {
-      double z, u, ratio;
-      if (a.draws[0]) { z = a.draws[0][i]; u = a.draws[1][i]; }
-      else { z = normal_cos(u32_open(b0[0]), u32_open(b0[1]), T); u = u32_open(b0[2]); }
-      const double ty = a.ty[i];
-      if (RT > 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
-      acc = fast_yg<RT>(H, T, gn, xg, xstride, gl, ty, z, u, ratio);
-      saw_nan |= isnan(ratio);
-      if (a.tune) { ulonglong2 w = a.win_y[i]; window_push(w, acc); a.win_y[i] = w; }   // Pr:312-322
+  for (;;) {
+    unsigned tile = 0;
+    if (lane == 0) tile = atomicAdd(fa.tile_counter + chain, 1u) - fa.tile_base;
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= ntiles) break;
+    const int64_t g = a.g_begin + (int64_t)tile * 32 + lane;
+    const bool valid = g < a.g_end;
+    const int64_t i = (int64_t)chain * a.G + (valid ? g : a.g_begin);
+    const uint64_t gid = (uint64_t)(a.gene_offset + g);
+    FastGene gn;
+    gn.y = a.Yg[i]; gn.v = a.vg[i]; gn.A = fa.lps[i]; gn.f = a.flags[i];
+    GeneData gd;
+    const int64_t gi = valid ? g : a.g_begin;
+    gd.nd_mask = fa.nd_mask[gi]; gd.xbar = fa.xbar[gi]; gd.ss = fa.xss[gi];
+    gd.ndet = (RT > 0 ? RT : H.R) - __popcll(gd.nd_mask);
+    const double gl = a.gl[gi];
+    const bool in_spike = (gn.f & F_INSPIKE) != 0;   // mhYg / mhVariance_g only touch out_spike_idx (Pr:11, Pr:252-257)
+    const bool live = valid && !in_spike;
+    double xglik = 0, vgprob = 0;
+    gn.lv = 0; gn.rv = 0;
+    if (valid) {
+      uint32_t b0[4] = {0, 0, 0, 0}, b1[4] = {0, 0, 0, 0};
+      if (!a.draws[0] && (a.moves & (ZZ_MOVE_YG | ZZ_MOVE_VARIANCE_G))) philox_block(a.seed, chain, a.step, 0, gid, b0);
+      if (!a.draws[3] && (a.moves & (ZZ_MOVE_VARIANCE_G | ZZ_MOVE_ALLOC))) philox_block(a.seed, chain, a.step, 1, gid, b1);
+      if (live) { gn.lv = flog(gn.v, T.log_t); gn.rv = 1.0 / gn.v; }
+      if (a.moves & ZZ_MOVE_YG) {
+        int acc = 0;
+        if (live) {
+          double z, u, ratio;
+          if (a.draws[0]) { z = a.draws[0][i]; u = a.draws[1][i]; }
+          else { z = normal_cos(u32_to_open01(b0[0]), u32_to_open01(b0[1]), T); u = u32_to_open01(b0[2]); }
+          acc = fast_yg<RT>(H, T, gn, gd, gl, a.ty[i], z, u, ratio);
+          saw_nan |= isnan(ratio);
+          if (a.tune) { ulonglong2 w = a.win_y[i]; window_push(w, acc); a.win_y[i] = w; }   // Pr:312-322
+        }
+        if (a.dec[0]) a.dec[0][i] = (uint8_t)acc;
+      }
+      if (a.moves & ZZ_MOVE_VARIANCE_G) {
+        int acc = 0;
+        if (live) {
+          double u1, u2, ratio;
+          if (a.draws[2]) { u1 = a.draws[2][i]; u2 = a.draws[3][i]; }
+          else { u1 = u32_to_open01(b0[3]); u2 = u32_to_open01(b1[0]); }
+          acc = fast_vg(H, T, gn, gd, a.tv[i], u1, u2, ratio);
+          saw_nan |= isnan(ratio);
+          if (a.tune) { ulonglong2 w = a.win_v[i]; window_push(w, acc); a.win_v[i] = w; }   // Pr:40-50
+        }
+        if (a.dec[1]) a.dec[1][i] = (uint8_t)acc;
+      }
+      if (a.moves & ZZ_MOVE_ALLOC) {
+        double u_ai, u_w;
+        if (a.draws[4]) { u_ai = a.draws[4][i]; u_w = a.draws[5][i]; }
+        else { u_ai = u32_to_open01(b1[1]); u_w = u32_to_open01(b1[2]); }
+        const int word = fast_alloc(H, T, gn.y, gn.f, u_ai, u_w);
+        if (a.dec[2]) a.dec[2][i] = (uint8_t)word;
+        a.flags[i] = (uint16_t)gn.f;
+      }
+      if (live) {
+        a.Yg[i] = gn.y; a.vg[i] = gn.v; fa.lps[i] = gn.A;
+        // the reference's caches, re-expressed: XgLikelihood = beta (A + B), variance_g_probability = prior(v | Sg(y))
+        xglik = xg_lik_fast(H, gn, gd);
+        vgprob = vg_prior_from_q(H, gn.lv, vg_q(H, gn.lv, gn.y));
+        if (H.vub != INFINITY) vgprob -= plnorm_term(H, gn.y);
+        a.xglik[i] = xglik; a.vgprob[i] = vgprob;
+      } else {
+        xglik = H.beta * ((gn.f & F_ALLZERO) ? 0.0 : -INFINITY);          // P:117
+      }
     }
-    if (a.dec[0]) a.dec[0][i] = (uint8_t)acc;
-  } else if (!in_spike) {            // D(y), n_det are still needed by mhVariance_g and the XgLikelihood cache
-    const int R = RT > 0 ? RT : H.R;
-    if (RT > 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const double x = xg[(int64_t)r * xstride];
-      if (x != -INFINITY) { const double d = x - gn.y; gn.D = fma(d, d, gn.D); gn.ndet++; }
+    if (fa.want_stats) {   // all-zero genes are accounted for by k_spike_fast, after their spike move
+      double *row = fa.partials + ((int64_t)chain * fa.rows_per_chain + tile) * nstat;
+      stats_tile(row, a.K, valid && !(gn.f & F_ALLZERO), gn.y, gn.lv, gn.f, xglik, vgprob, isfinite(gn.y) && isfinite(gn.v));
     }
-  }
-  if (a.moves & ZZ_MOVE_VARIANCE_G) {
-    int acc = 0;
-    if (!in_spike) {
-      double u1, u2, ratio;
-      if (a.draws[2]) { u1 = a.draws[2][i]; u2 = a.draws[3][i]; }
-      else { u1 = u32_open(b0[3]); u2 = u32_open(b1[0]); }
-      acc = fast_vg(H, T, gn, a.tv[i], u1, u2, ratio);
-      saw_nan |= isnan(ratio);
-      if (a.tune) { ulonglong2 w = a.win_v[i]; window_push(w, acc); a.win_v[i] = w; }   // Pr:40-50
-    }
-    if (a.dec[1]) a.dec[1][i] = (uint8_t)acc;
-  }
-  if (a.moves & ZZ_MOVE_ALLOC) {
-    double u_ai, u_w;
-    if (a.draws[4]) { u_ai = a.draws[4][i]; u_w = a.draws[5][i]; }
-    else { u_ai = u32_open(b1[1]); u_w = u32_open(b1[2]); }
-    const int word = fast_alloc(H, T, gn.y, gn.f, u_ai, u_w);
-    if (a.dec[2]) a.dec[2][i] = (uint8_t)word;
-    a.flags[i] = (uint16_t)gn.f;
-  }
-  if (!in_spike) {
-    a.Yg[i] = gn.y; a.vg[i] = gn.v; fa.lps[i] = gn.A;
-    // the reference's caches, re-expressed: XgLikelihood = beta (A + B), variance_g_probability = prior(v | Sg(y))
-    a.xglik[i] = H.beta * (gn.A + (-(double)gn.ndet * (LN_SQRT_2PI + 0.5 * gn.lv) - 0.5 * gn.D * gn.rv));
-    const double q = vg_q(H, gn.lv, gn.y);
-    double pv = vg_prior_from_q(H, gn.lv, q);
-    if (H.vub != INFINITY) pv -= plnorm_term(H, gn.y);
-    a.vgprob[i] = pv;
   }
   if (saw_nan) atomicOr(a.nan_flag, 1);
 }
 
-// mhSpikeAllocation (Pr:528-638) over the static list of all-zero genes; their likelihood needs no Xg (every library is -Inf)
+// mhSpikeAllocation (Pr:528-638) over the static list of all-zero genes; their likelihood needs no Xg (every library is -Inf).
+// One warp per 32 list entries; also emits the sufficient statistics of every all-zero gene (after the move).
 template <int RT>
 __global__ void __launch_bounds__(BLOCK) k_spike_fast(const FastArgs fa) {
   __shared__ FastH H;
@@ -222,52 +251,63 @@ __global__ void __launch_bounds__(BLOCK) k_spike_fast(const FastArgs fa) {
   const int chain = blockIdx.y;
   load_fast(H, T, a.hyper + chain, fa.exp_tab, fa.log_tab);
   const int64_t j = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (j >= fa.n_allzero) return;
-  const int64_t g = fa.allzero_idx[j];
-  if (g < a.g_begin || g >= a.g_end) return;
-  const int64_t i = (int64_t)chain * a.G + g;
+  const int nstat = 3 * (a.K + 1) + NSTAT_FIXED_;
+  const int64_t g = j < fa.n_allzero ? fa.allzero_idx[j] : -1;
+  const bool valid = g >= a.g_begin && g < a.g_end;
+  const int64_t i = (int64_t)chain * a.G + (valid ? g : a.g_begin);
   uint32_t f = a.flags[i];
-  if (f & F_ACTIVE) { if (a.dec[3]) a.dec[3][i] = 0; return; }          // Pr:533: all-zero AND inactive
-  const bool cur_in = (f & F_INSPIKE) != 0, prop_in = !cur_in;          // Pr:535
-  double zy, zv, u;
-  if (a.draws[6]) { zy = a.draws[6][i]; zv = a.draws[7][i]; u = a.draws[8][i]; }
-  else {
-    uint32_t b2[4];
-    philox_block(a.seed, chain, a.step, 2, (uint64_t)(a.gene_offset + g), b2);
-    box_muller(u32_open(b2[0]), u32_open(b2[1]), zy, zv); u = u32_open(b2[2]);
+  double y = a.Yg[i], v = a.vg[i], xglik = a.xglik[i], vgprob = a.vgprob[i];
+  const bool eligible = valid && fa.do_spike_move && !(f & F_ACTIVE);   // Pr:533: all-zero AND inactive
+  int acc = 0;
+  if (eligible) {
+    const bool cur_in = (f & F_INSPIKE) != 0, prop_in = !cur_in;        // Pr:535
+    double zy, zv, u;
+    if (a.draws[6]) { zy = a.draws[6][i]; zv = a.draws[7][i]; u = a.draws[8][i]; }
+    else {
+      uint32_t b2[4];
+      philox_block(a.seed, chain, a.step, 2, (uint64_t)(a.gene_offset + g), b2);
+      box_muller(u32_open(b2[0]), u32_open(b2[1]), zy, zv); u = u32_open(b2[2]);
+    }
+    const double yp = fma(H.sd_i, zy, H.im);                            // Pr:545
+    const double lsp = fma(H.s1, yp, H.s0);                             // log(Sg_proposed), Pr:547
+    const double lvp = (lsp + H.tau) + H.rtau * zv;                     // Pr:549: variance_g' = exp(.)
+    const double vp = fexp(lvp, T.exp_t);
+    double PVp = vg_prior_from_q(H, lvp, vg_q(H, lvp, yp));             // Pr:556
+    const double lv = flog(v, T.log_t);
+    double PVc = vg_prior_from_q(H, lv, vg_q(H, lv, y));                // Pr:558
+    if (H.vub != INFINITY) { PVp -= plnorm_term(H, yp); PVc -= plnorm_term(H, y); }
+    const double dp = yp - H.im, dc = y - H.im;
+    const double pygp = prop_in ? H.log_sp : H.log_1msp - H.log_norm_i - dp * dp * H.inv2iv;   // Pr:560
+    const double pyg = cur_in ? H.log_sp : H.log_1msp - H.log_norm_i - dc * dc * H.inv2iv;     // Pr:563
+    const double pp = prop_in ? H.log_sp : (pygp + PVp);                // Pr:569-570
+    const double pc = cur_in ? H.log_sp : (pyg + PVc);                  // Pr:572-573
+    double Ap = 0;
+    if (!prop_in) Ap = detect_logsum<RT>(H, T, ~0ull, a.gl[g] * fexp(yp, T.exp_t));
+    double Lp = prop_in ? H.beta * 0.0 : H.beta * Ap;                   // Pr:579 (P:117 gives log(1*1) = 0 in the spike)
+    double Lc = xglik;                                                  // Pr:581
+    if (Lp == -INFINITY && Lc == -INFINITY) { Lp = 0; Lc = 0; }         // Pr:583-585
+    const double HR = prop_in ? (pyg - H.log_1msp + PVc) : -(pygp - H.log_1msp + PVp);   // Pr:592-595
+    double ratio = H.temp * (Lp - Lc + pp - pc) + HR;                   // Pr:601
+    if (vp > H.vub) ratio = -INFINITY;                                  // Pr:603
+    acc = (flog_core(u, T.log_t) < ratio);                              // Pr:605
+    if (isnan(ratio)) atomicOr(a.nan_flag, 1);
+    if (acc) f ^= F_INSPIKE;                                            // Pr:616
+    a.flags[i] = (uint16_t)f;
+    if (!prop_in) {                                                     // [proposed_out_spike_idx], Pr:620-636
+      if (acc) { y = yp; v = vp; a.Yg[i] = yp; a.vg[i] = vp; fa.lps[i] = Ap; }
+      vgprob = acc ? PVp : PVc;
+      a.vgprob[i] = vgprob;
+    }
+    xglik = acc ? Lp : Lc;                                              // Pr:630-632
+    a.xglik[i] = xglik;
   }
-  const double y = a.Yg[i], v = a.vg[i];
-  const double yp = fma(H.sd_i, zy, H.im);                              // Pr:545
-  const double lsp = fma(H.s1, yp, H.s0);                               // log(Sg_proposed), Pr:547
-  const double lvp = (lsp + H.tau) + H.rtau * zv;                       // Pr:549: variance_g' = exp(.)
-  const double vp = fexp(lvp, T.exp_t);
-  double PVp = vg_prior_from_q(H, lvp, vg_q(H, lvp, yp));               // Pr:556
-  const double lv = flog(v, T.log_t);
-  double PVc = vg_prior_from_q(H, lv, vg_q(H, lv, y));                  // Pr:558
-  if (H.vub != INFINITY) { PVp -= plnorm_term(H, yp); PVc -= plnorm_term(H, y); }
-  const double dp = yp - H.im, dc = y - H.im;
-  const double pygp = prop_in ? H.log_sp : H.log_1msp - H.log_norm_i - dp * dp * H.inv2iv;   // Pr:560
-  const double pyg = cur_in ? H.log_sp : H.log_1msp - H.log_norm_i - dc * dc * H.inv2iv;     // Pr:563
-  const double pp = prop_in ? H.log_sp : (pygp + PVp);                  // Pr:569-570
-  const double pc = cur_in ? H.log_sp : (pyg + PVc);                    // Pr:572-573
-  double Ap = 0;
-  if (!prop_in) Ap = lps_only<RT>(H, T, nullptr, 0, a.gl[g] * fexp(yp, T.exp_t), true);
-  double Lp = prop_in ? H.beta * 0.0 : H.beta * Ap;                     // Pr:579 (P:117 gives log(1*1) = 0 in the spike)
-  double Lc = a.xglik[i];                                               // Pr:581
-  if (Lp == -INFINITY && Lc == -INFINITY) { Lp = 0; Lc = 0; }           // Pr:583-585
-  const double HR = prop_in ? (pyg - H.log_1msp + PVc) : -(pygp - H.log_1msp + PVp);   // Pr:592-595
-  double ratio = H.temp * (Lp - Lc + pp - pc) + HR;                     // Pr:601
-  if (vp > H.vub) ratio = -INFINITY;                                    // Pr:603
-  const int acc = (flog(u, T.log_t) < ratio);                           // Pr:605
-  if (isnan(ratio)) atomicOr(a.nan_flag, 1);
-  if (acc) f ^= F_INSPIKE;                                              // Pr:616
-  a.flags[i] = (uint16_t)f;
-  if (!prop_in) {                                                       // [proposed_out_spike_idx], Pr:620-636
-    if (acc) { a.Yg[i] = yp; a.vg[i] = vp; fa.lps[i] = Ap; }
-    a.vgprob[i] = acc ? PVp : PVc;
+  if (valid && a.dec[3]) a.dec[3][i] = (uint8_t)acc;
+  if (fa.want_stats) {
+    const bool out = valid && !(f & F_INSPIKE);
+    const double lv = out ? flog(v, T.log_t) : 0.0;
+    double *row = fa.partials + ((int64_t)chain * fa.rows_per_chain + fa.spike_row0 + (j >> 5)) * nstat;
+    stats_tile(row, a.K, valid, y, lv, f, xglik, vgprob, isfinite(y) && isfinite(v));
   }
-  a.xglik[i] = acc ? Lp : Lc;                                           // Pr:630-632
-  if (a.dec[3]) a.dec[3][i] = (uint8_t)acc;
 }
 
 // lps <- A(Yg) for every out-of-spike gene (after anything that changed Yg or alpha_r outside the fast sweep)
@@ -282,7 +322,7 @@ __global__ void __launch_bounds__(BLOCK) k_refresh_lps(const FastArgs fa) {
   if (g >= a.G) return;
   const int64_t i = (int64_t)chain * a.G + g;
   if (a.flags[i] & F_INSPIKE) { fa.lps[i] = 0; return; }
-  fa.lps[i] = lps_only<RT>(H, T, a.Xg + g, a.G, a.gl[g] * fexp(a.Yg[i], T.exp_t), false);
+  fa.lps[i] = detect_logsum<RT>(H, T, fa.nd_mask[g], a.gl[g] * fexp(a.Yg[i], T.exp_t));
 }
 
 // exports the Philox draws of one move slot in the layout of that move's `draws` argument
@@ -409,6 +449,19 @@ __global__ void __launch_bounds__(BLOCK) k_reduce_final(const double *partials, 
     for (int b = threadIdx.x; b < nblk; b += BLOCK) v += partials[((int64_t)y * nblk + b) * nval + s];
     const double t = block_sum<BLOCK>(v, red);
     if (threadIdx.x == 0) out[(int64_t)y * nval + s] = t;
+  }
+}
+
+// first level of the sweep-statistics reduction: chunk b of the rows [C][nrows][nval] -> out [C][nchunks][nval]
+__global__ void __launch_bounds__(BLOCK) k_reduce_rows(const double *partials, int64_t nrows, int nval, double *out) {
+  __shared__ double red[BLOCK / 32];
+  const int chain = blockIdx.y, nchunks = gridDim.x;
+  const int64_t per = (nrows + nchunks - 1) / nchunks, r0 = (int64_t)blockIdx.x * per, r1 = r0 + per < nrows ? r0 + per : nrows;
+  for (int s = 0; s < nval; ++s) {
+    double v = 0;
+    for (int64_t r = r0 + threadIdx.x; r < r1; r += BLOCK) v += partials[((int64_t)chain * nrows + r) * nval + s];
+    const double t = block_sum<BLOCK>(v, red);
+    if (threadIdx.x == 0) out[((int64_t)chain * nchunks + blockIdx.x) * nval + s] = t;
   }
 }
 
@@ -557,6 +610,9 @@ struct zz_handle {
   int *nan_flag;
   bool have_data;
   double *lps; double *exp_tab; double2 *log_tab; int32_t *allzero_idx; int64_t n_allzero;
+  uint64_t *nd_mask; double *xbar, *xss;   // per-gene data statistics (k_prepare_data)
+  unsigned *tile_counter; unsigned tile_base; int persist_blocks;
+  double *sw_partials, *sw_partials2; int64_t sw_rows; bool stats_fresh;   // statistics emitted by the last production sweep
   bool lps_valid;                          // lps == A(current Yg, alpha_r) for every out-of-spike gene
   std::vector<zz_hyper> hyper_host;
   double *pinned;                          // small pinned staging for reduction results
@@ -622,22 +678,25 @@ int launch_sweep(zz_handle *h, uint64_t step, int tune, uint32_t moves, const do
   k_sweep<<<gene_grid(h, g_end - g_begin, h->C), BLOCK, 0, h->stream>>>(a);
   ZZ_LAUNCHED(h);
   if (moves & (ZZ_MOVE_YG | ZZ_MOVE_SPIKE)) h->lps_valid = false;   // Yg moved without its A(y) being maintained
+  h->stats_fresh = false;
   return ZZ_OK;
 }
 
-#define ZZ_DISPATCH_R(h, KERNEL, grid, smem_per_lib, args)                                       \
+#define ZZ_DISPATCH_R(h, KERNEL, grid, args)                                                     \
   do {                                                                                           \
     switch ((h)->R) {                                                                            \
-      case 2: KERNEL<2><<<grid, BLOCK, 2 * (smem_per_lib), (h)->stream>>>(args); break;          \
-      case 4: KERNEL<4><<<grid, BLOCK, 4 * (smem_per_lib), (h)->stream>>>(args); break;          \
-      case 8: KERNEL<8><<<grid, BLOCK, 8 * (smem_per_lib), (h)->stream>>>(args); break;          \
-      case 16: KERNEL<16><<<grid, BLOCK, 16 * (smem_per_lib), (h)->stream>>>(args); break;       \
+      case 2: KERNEL<2><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                           \
+      case 4: KERNEL<4><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                           \
+      case 8: KERNEL<8><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                           \
+      case 16: KERNEL<16><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                         \
       default: KERNEL<0><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                          \
     }                                                                                            \
   } while (0)
 
 void fill_fast_args(zz_handle *h, FastArgs &fa) {
   fa.lps = h->lps; fa.exp_tab = h->exp_tab; fa.log_tab = h->log_tab; fa.allzero_idx = h->allzero_idx; fa.n_allzero = h->n_allzero;
+  fa.nd_mask = h->nd_mask; fa.xbar = h->xbar; fa.xss = h->xss; fa.tile_counter = h->tile_counter; fa.tile_base = h->tile_base;
+  fa.partials = h->sw_partials; fa.rows_per_chain = 0; fa.spike_row0 = 0; fa.want_stats = 0; fa.do_spike_move = 0;
 }
 
 int ensure_lps(zz_handle *h) {
@@ -645,13 +704,32 @@ int ensure_lps(zz_handle *h) {
   FastArgs fa;
   fill_sweep_args(h, fa.s, 0, 0, 0, nullptr, nullptr, 0, h->G);
   fill_fast_args(h, fa);
-  ZZ_DISPATCH_R(h, k_refresh_lps, gene_grid(h, h->G, h->C), 0, fa);
+  ZZ_DISPATCH_R(h, k_refresh_lps, gene_grid(h, h->G, h->C), fa);
   ZZ_LAUNCHED(h);
   h->lps_valid = true;
   return ZZ_OK;
 }
 
-// production kernels (zz_fast.cuh): main sweep over all genes + spike move over the all-zero gene list
+// resident CTAs of the persistent sweep kernel on this device (blocks per SM from the occupancy calculator x SM count)
+int persistent_blocks(zz_handle *h) {
+  if (h->persist_blocks > 0) return h->persist_blocks;
+  int per_sm = 0, sms = 0;
+  cudaError_t e;
+  switch (h->R) {
+    case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<2>, BLOCK, 0); break;
+    case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<4>, BLOCK, 0); break;
+    case 8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<8>, BLOCK, 0); break;
+    case 16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<16>, BLOCK, 0); break;
+    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<0>, BLOCK, 0); break;
+  }
+  if (e != cudaSuccess || per_sm < 1) per_sm = 2;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device) != cudaSuccess || sms < 1) sms = 148;
+  h->persist_blocks = per_sm * sms;
+  return h->persist_blocks;
+}
+
+// production kernels (zz_fast.cuh): persistent main sweep + spike move over the all-zero gene list; when the whole shard is
+// swept they also leave the sufficient statistics in sw_partials (consumed by zz_suffstats[_dev] without another pass)
 int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, const double *const draws_dev[9], uint8_t *const dec_dev[4],
                       int64_t g_begin, int64_t g_end) {
   if (g_end <= g_begin) return ZZ_OK;
@@ -659,17 +737,29 @@ int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, con
   FastArgs fa;
   fill_sweep_args(h, fa.s, step, tune, moves, draws_dev, dec_dev, g_begin, g_end);
   fill_fast_args(h, fa);
-  if (moves & (ZZ_MOVE_YG | ZZ_MOVE_VARIANCE_G | ZZ_MOVE_ALLOC)) {
-    ZZ_DISPATCH_R(h, k_sweep_fast, gene_grid(h, g_end - g_begin, h->C), BLOCK * sizeof(double), fa);
+  const bool full = (g_begin == 0 && g_end == h->G);
+  const int64_t ntiles = (g_end - g_begin + 31) / 32;
+  const int64_t spike_blocks = h->n_allzero > 0 ? (h->n_allzero + BLOCK - 1) / BLOCK : 0;
+  fa.want_stats = full ? 1 : 0;
+  fa.rows_per_chain = ntiles + spike_blocks * (BLOCK / 32);
+  fa.spike_row0 = ntiles;
+  fa.do_spike_move = (moves & ZZ_MOVE_SPIKE) ? 1 : 0;
+  h->stats_fresh = false;
+  {
+    int64_t per_chain = (persistent_blocks(h) + h->C - 1) / h->C;
+    const int64_t need = (ntiles + BLOCK / 32 - 1) / (BLOCK / 32);
+    if (per_chain > need) per_chain = need;
+    if (per_chain < 1) per_chain = 1;
+    ZZ_DISPATCH_R(h, k_sweep_fast, dim3((unsigned)per_chain, (unsigned)h->C), fa);
+    ZZ_LAUNCHED(h);
+    h->tile_base += (unsigned)(ntiles + per_chain * (BLOCK / 32));   // every warp ends on one failed fetch
+  }
+  if (dec_dev && dec_dev[3] && (moves & ZZ_MOVE_SPIKE)) ZZ_CUDA(h, cudaMemsetAsync(dec_dev[3], 0, (size_t)h->C * h->G, h->stream));
+  if (spike_blocks > 0 && (fa.do_spike_move || fa.want_stats)) {
+    ZZ_DISPATCH_R(h, k_spike_fast, dim3((unsigned)spike_blocks, (unsigned)h->C), fa);
     ZZ_LAUNCHED(h);
   }
-  if (moves & ZZ_MOVE_SPIKE) {
-    if (dec_dev && dec_dev[3]) ZZ_CUDA(h, cudaMemsetAsync(dec_dev[3], 0, (size_t)h->C * h->G, h->stream));
-    if (h->n_allzero > 0) {
-      ZZ_DISPATCH_R(h, k_spike_fast, gene_grid(h, h->n_allzero, h->C), 0, fa);
-      ZZ_LAUNCHED(h);
-    }
-  }
+  if (full) { h->stats_fresh = true; h->sw_rows = fa.rows_per_chain; }
   return ZZ_OK;
 }
 
@@ -794,11 +884,20 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   ZZ_CUDA(h, cudaMemcpyAsync(h->exp_tab, kExpTab, sizeof(kExpTab), cudaMemcpyHostToDevice, h->stream));
   ZZ_CUDA(h, cudaMemcpyAsync(h->log_tab, kLogTab, sizeof(kLogTab), cudaMemcpyHostToDevice, h->stream));
   ZZ_CUDA(h, cudaMalloc(&h->allzero_idx, sizeof(int32_t) * G));
-  h->n_allzero = 0; h->lps_valid = false;
+  h->n_allzero = 0; h->lps_valid = false; h->stats_fresh = false; h->tile_base = 0; h->persist_blocks = 0; h->sw_rows = 0;
+  ZZ_CUDA(h, cudaMalloc(&h->nd_mask, sizeof(uint64_t) * G));
+  ZZ_CUDA(h, cudaMalloc(&h->xbar, sizeof(double) * G));
+  ZZ_CUDA(h, cudaMalloc(&h->xss, sizeof(double) * G));
+  ZZ_CUDA(h, cudaMalloc(&h->tile_counter, sizeof(unsigned) * h->C));
+  ZZ_CUDA(h, cudaMemsetAsync(h->tile_counter, 0, sizeof(unsigned) * h->C, h->stream));
+  {
+    const int64_t max_rows = (G + 31) / 32 + ((G + BLOCK - 1) / BLOCK) * (BLOCK / 32);
+    ZZ_CUDA(h, cudaMalloc(&h->sw_partials, sizeof(double) * (size_t)h->C * max_rows * nstat));
+    ZZ_CUDA(h, cudaMalloc(&h->sw_partials2, sizeof(double) * (size_t)h->C * SW_CHUNKS * nstat));
+  }
   ZZ_CUDA(h, cudaMalloc(&h->nan_flag, sizeof(int)));
   ZZ_CUDA(h, cudaMemsetAsync(h->nan_flag, 0, sizeof(int), h->stream));
   ZZ_CUDA(h, cudaMallocHost(&h->pinned, sizeof(double) * (size_t)(h->C > ZZ_MAX_LIBS ? h->C : ZZ_MAX_LIBS) * MAX_NSTAT));
-  (void)nstat;
   h->hyper_host.assign(h->C, zz_hyper());
   k_window_init<<<gene_grid(h, CG), BLOCK, 0, h->stream>>>(CG, h->win_y, h->win_v);
   ZZ_LAUNCHED(h);
@@ -811,7 +910,7 @@ void zz_destroy(zz_handle *h) {
   cudaSetDevice(h->cfg.device);
   void *ptrs[] = {h->Xg, h->gl, h->Yg, h->vg, h->xglik, h->vgprob, h->ty, h->tv, h->flags, h->win_y, h->win_v, h->trace,
                   h->hyper, h->partials, h->red_out, h->scratch, h->dec, h->iscratch, h->nan_flag, h->lps, h->exp_tab,
-                  h->log_tab, h->allzero_idx};
+                  h->log_tab, h->allzero_idx, h->nd_mask, h->xbar, h->xss, h->tile_counter, h->sw_partials, h->sw_partials2};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -859,8 +958,10 @@ int zz_upload_data(zz_handle *h, const double *Xg, const double *gene_lengths) {
   ZZ_CUDA(h, cudaMemcpyAsync(h->flags, f.data(), sizeof(uint16_t) * f.size(), cudaMemcpyHostToDevice, h->stream));
   h->n_allzero = (int64_t)az.size();
   if (!az.empty()) ZZ_CUDA(h, cudaMemcpyAsync(h->allzero_idx, az.data(), sizeof(int32_t) * az.size(), cudaMemcpyHostToDevice, h->stream));
+  k_prepare_data<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, h->R, h->Xg, h->nd_mask, h->xbar, h->xss);
+  ZZ_LAUNCHED(h);
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
-  h->have_data = true; h->lps_valid = false;
+  h->have_data = true; h->lps_valid = false; h->stats_fresh = false;
   return ZZ_OK;
 }
 
@@ -872,6 +973,7 @@ int zz_set_state(zz_handle *h, int chain, const double *Yg, const double *varian
   const int64_t G = h->G, off = (int64_t)chain * G;
   int rc;
   if (Yg || spike) h->lps_valid = false;
+  h->stats_fresh = false;
   if ((rc = up(h, h->Yg + off, Yg, G)) || (rc = up(h, h->vg + off, variance_g, G)) || (rc = up(h, h->xglik + off, XgLikelihood, G)) ||
       (rc = up(h, h->vgprob + off, variance_g_probability, G)) || (rc = up(h, h->ty + off, ty, G)) || (rc = up(h, h->tv + off, tv, G)))
     return rc;
@@ -935,6 +1037,7 @@ int zz_get_hyper(zz_handle *h, int chain, zz_hyper *hy) {
 
 int zz_refresh_caches(zz_handle *h) {
   ZZ_CHECK(h);
+  h->stats_fresh = false;
   if (!h->have_data) return fail(h, ZZ_ERR_STATE, "zz_upload_data has not been called");
   return launch_eval(h, EVAL_REFRESH, -1, h->xglik, h->vgprob);
 }
@@ -1012,6 +1115,14 @@ int zz_suffstats_len(int K) { return 3 * (K + 1) + NSTAT_FIXED; }
 int zz_suffstats_dev(zz_handle *h, double *out_dev) {
   ZZ_CHECK(h);
   if (!out_dev) return fail(h, ZZ_ERR_INVALID, "out_dev is NULL");
+  if (h->stats_fresh) {   // the last production sweep already emitted per-tile statistics: two tiny fixed-order reductions
+    const int nst = zz_suffstats_len(h->K);
+    k_reduce_rows<<<dim3(SW_CHUNKS, h->C), BLOCK, 0, h->stream>>>(h->sw_partials, h->sw_rows, nst, h->sw_partials2);
+    ZZ_LAUNCHED(h);
+    k_reduce_final<<<h->C, BLOCK, 0, h->stream>>>(h->sw_partials2, SW_CHUNKS, nst, out_dev);
+    ZZ_LAUNCHED(h);
+    return ZZ_OK;
+  }
   const int nblk = red_blocks(h->G), nstat = zz_suffstats_len(h->K);
   StatArgs a;
   a.G = h->G; a.K = h->K; a.Yg = h->Yg; a.vg = h->vg; a.xglik = h->xglik; a.vgprob = h->vgprob; a.flags = h->flags; a.partials = h->partials;
@@ -1044,6 +1155,7 @@ int zz_varg_hyper_sum(zz_handle *h, int chain, double s0, double s1, double tau,
 
 int zz_commit_varg_hyper(zz_handle *h, int chain) {
   ZZ_CHECK(h);
+  h->stats_fresh = false;
   if (int rc = chain_ok(h, chain)) return rc;
   return launch_eval(h, EVAL_COMMIT_VG, chain, nullptr, h->vgprob + (int64_t)chain * h->G);
 }
@@ -1079,7 +1191,7 @@ int zz_px_commit(zz_handle *h, int chain, int lib, double alpha_new) {
     ZZ_LAUNCHED(h);
   }
   h->hyper_host[chain].alpha_r[lib] = alpha_new;
-  h->lps_valid = false;
+  h->lps_valid = false; h->stats_fresh = false;
   ZZ_CUDA(h, cudaMemcpyAsync(h->hyper + chain, &h->hyper_host[chain], sizeof(zz_hyper), cudaMemcpyHostToDevice, h->stream));
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
   if (h->R <= 2) {  // Pr:219: full recompute with the proposed p_x
