@@ -85,13 +85,25 @@ template <int RT>
 __device__ __forceinline__ double detect_logsum(const FastH &H, const MathTabs &T, uint64_t nd_mask, double t) {
   const int R = RT > 0 ? RT : H.R;
   double A = 0;
-  unsigned zero_seen = 0xFFFFFFFFu;
+  if (RT > 0 && RT <= 18) {
+    // q is +0 or a normal number in [2^-53, 1].  flog_core(+0) returns -1023 ln 2 = -709.1 instead of -Inf, while a sum of
+    // at most 18 legitimate terms is >= 18 log(2^-53) = -661.3: "A < -700" therefore detects a zero q exactly, without a
+    // per-library test.
 #pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double e = fexp_neg_clamped(t * H.alpha[r], T.exp_t);
+      const double p = 1 - e;
+      const double q = ((nd_mask >> r) & 1ull) ? (1 - p) : p;
+      A += flog_core(q, T.log_t);
+    }
+    return A < -700.0 ? -INFINITY : A;
+  }
+  unsigned zero_seen = 0xFFFFFFFFu;
   for (int r = 0; r < R; ++r) {
     const double e = fexp_neg_clamped(t * H.alpha[r], T.exp_t);
     const double p = 1 - e;
     const double q = ((nd_mask >> r) & 1ull) ? (1 - p) : p;
-    A += flog_core(q, T.log_t);                       // q is +0 or a normal number in (0, 1]
+    A += flog_core(q, T.log_t);
     zero_seen = min(zero_seen, (unsigned)(d_hi(q) | d_lo(q)));
   }
   return zero_seen == 0 ? -INFINITY : A;              // some q == 0: log(0) = -Inf (flog_core(0) itself is finite garbage)
@@ -204,31 +216,35 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// One warp writes the sufficient statistics of its 32-gene tile to its own row of `partials` (no atomics, no block
-// barrier; k_reduce_final adds the rows in a fixed order, so the result does not depend on the dynamic tile schedule).
-__device__ __forceinline__ void stats_tile(double *row, int K, bool valid, double y, double lv, uint32_t f, double xglik,
-                                           double vgprob, bool finite_state) {
-  const int K1 = K + 1, lane = threadIdx.x & 31;
+// Sufficient statistics accumulated by the sweep: every thread owns one column of a [nstat][BLOCK] shared-memory array and
+// adds its gene's contribution after each tile (3 instructions per statistic, no shuffles); the block reduces the columns
+// once at the end.  Tiles are assigned to warps statically, so every sum has a fixed order and the result is reproducible.
+template <int BLOCK_>
+__device__ __forceinline__ void stats_add(double *acc /*[nstat][BLOCK_]*/, int K, bool valid, double y, double lv, uint32_t f,
+                                          double xglik, double vgprob, bool finite_state) {
+  if (!valid) return;
+  const int K1 = K + 1;
+  double *col = acc + threadIdx.x;
   const bool act = f & F_ACTIVE, sp = f & F_INSPIKE;
   const int comp = act ? flag_k(f) : 0;                                 // Pr:415 all_allocations
-  const bool use_y = valid && (act || !sp);
-  for (int c = 0; c < K1; ++c) {
-    const unsigned m = __ballot_sync(0xffffffffu, valid && comp == c);
-    const bool mine = use_y && comp == c;
-    const double sy = warp_sum(mine ? y : 0.0), sy2 = warp_sum(mine ? y * y : 0.0);
-    if (lane == 0) { row[c] = (double)__popc(m); row[K1 + c] = sy; row[2 * K1 + c] = sy2; }
+  col[comp * BLOCK_] += 1.0;
+  if (act || !sp) { col[(K1 + comp) * BLOCK_] += y; col[(2 * K1 + comp) * BLOCK_] += y * y; }
+  double *fx = col + 3 * K1 * BLOCK_;
+  if (sp) fx[0] += 1.0;
+  else {
+    fx[1 * BLOCK_] += 1.0; fx[2 * BLOCK_] += lv; fx[3 * BLOCK_] += lv * lv; fx[4 * BLOCK_] += y; fx[5 * BLOCK_] += y * y;
+    fx[6 * BLOCK_] += y * lv; fx[8 * BLOCK_] += vgprob;
   }
-  const bool out = valid && !sp;
-  const unsigned m_sp = __ballot_sync(0xffffffffu, valid && sp), m_out = __ballot_sync(0xffffffffu, out);
-  const unsigned m_nan = __ballot_sync(0xffffffffu, valid && !finite_state);
-  const double z = out ? lv : 0.0, yo = out ? y : 0.0;
-  const double s2 = warp_sum(z), s3 = warp_sum(z * z), s4 = warp_sum(yo), s5 = warp_sum(yo * yo), s6 = warp_sum(yo * z);
-  const double s7 = warp_sum(valid ? xglik : 0.0), s8 = warp_sum(out ? vgprob : 0.0);
-  if (lane == 0) {
-    double *fx = row + 3 * K1;
-    fx[0] = (double)__popc(m_sp); fx[1] = (double)__popc(m_out);
-    fx[2] = s2; fx[3] = s3; fx[4] = s4; fx[5] = s5; fx[6] = s6; fx[7] = s7; fx[8] = s8;
-    fx[9] = (double)__popc(m_nan);
+  fx[7 * BLOCK_] += xglik;
+  if (!finite_state) fx[9 * BLOCK_] += 1.0;
+}
+
+// column sums -> one row of `partials`; fixed order (warp butterfly, then warps in order)
+template <int BLOCK_>
+__device__ __forceinline__ void stats_flush(const double *acc, int nstat, double *row, double *red /*BLOCK_/32*/) {
+  for (int s = 0; s < nstat; ++s) {
+    const double t = block_sum<BLOCK_>(acc[s * BLOCK_ + threadIdx.x], red);
+    if (threadIdx.x == 0) row[s] = t;
   }
 }
 

@@ -93,7 +93,7 @@ ZZ_HD double libm_log(double x) {
 
 // general exp: libm outside the range where the exponent-field trick is valid (rare, warp-divergent)
 ZZ_HD double fexp(double x, const double *__restrict__ exp_t) {
-  if (!(fabs(x) <= 708.0)) return libm_exp(x);
+  if ((unsigned)(d_hi(x) & 0x7FFFFFFF) > 0x40862000u) return libm_exp(x);   // |x| > 708 (or NaN): integer test, no FP64 slot
   return fexp_core(x, exp_t);
 }
 

@@ -123,9 +123,7 @@ struct FastArgs {
   const double *exp_tab; const double2 *log_tab;
   const int32_t *allzero_idx; int64_t n_allzero;   // static list of genes with no reads in any library (I:416-421)
   const uint64_t *nd_mask; const double *xbar, *xss;  // per-gene data statistics (k_prepare_data)
-  unsigned *tile_counter;           // [C] dynamic warp-tile scheduler (monotone; `tile_base` is its value at launch)
-  unsigned tile_base;
-  double *partials;                 // [C][rows][nstat] per-warp-tile sufficient statistics (rows = main tiles + spike tiles)
+  double *partials;                 // [C][rows][nstat] per-block sufficient statistics (rows = main blocks + spike blocks)
   int64_t rows_per_chain, spike_row0;
   int want_stats, do_spike_move;
 };
@@ -152,161 +150,168 @@ __global__ void __launch_bounds__(BLOCK) k_prepare_data(int64_t G, int R, const 
   nd_mask[g] = m; xbar[g] = mean2; xss[g] = ss < 0 ? 0.0 : ss;
 }
 
-// Persistent kernel: blockIdx.y = chain; every WARP pulls 32-gene tiles from the chain's atomic counter, so there is one
-// table/hyper load + one barrier per block for the whole sweep and warps never wait for each other afterwards.
-template <int RT>
+// Persistent kernel: blockIdx.y = chain; warp w of the chain's grid handles the 32-gene tiles w, w + W, w + 2W, ...
+// One table/hyper load and one barrier per block for the whole sweep; warps never wait for each other afterwards.
+// PROD = true is the production instantiation (Philox draws, no decision export); PROD = false additionally serves the
+// "identical uniforms" test mode (explicit draws) and exports decisions.
+template <int RT, bool PROD>
 __global__ void __launch_bounds__(BLOCK, 3) k_sweep_fast(const FastArgs fa) {
   __shared__ FastH H;
   __shared__ MathTabs T;
+  __shared__ double red[BLOCK / 32];
+  extern __shared__ double acc[];                     // [nstat][BLOCK] when want_stats
   const SweepArgs &a = fa.s;
   const int chain = blockIdx.y, lane = threadIdx.x & 31;
+  const int nstat = 3 * (a.K + 1) + NSTAT_FIXED_;
+  if (fa.want_stats) for (int s = 0; s < nstat; ++s) acc[s * BLOCK + threadIdx.x] = 0.0;
   load_fast(H, T, a.hyper + chain, fa.exp_tab, fa.log_tab);
   const int64_t n = a.g_end - a.g_begin;
-  const unsigned ntiles = (unsigned)((n + 31) / 32);
-  const int nstat = 3 * (a.K + 1) + NSTAT_FIXED_;
+  const int64_t ntiles = (n + 31) / 32;
+  const int64_t warp0 = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * (BLOCK / 32);
   bool saw_nan = false;
-  for (;;) {
-    unsigned tile = 0;
-    if (lane == 0) tile = atomicAdd(fa.tile_counter + chain, 1u) - fa.tile_base;
-    tile = __shfl_sync(0xffffffffu, tile, 0);
-    if (tile >= ntiles) break;
-    const int64_t g = a.g_begin + (int64_t)tile * 32 + lane;
-    const bool valid = g < a.g_end;
-    const int64_t i = (int64_t)chain * a.G + (valid ? g : a.g_begin);
+  for (int64_t tile = warp0; tile < ntiles; tile += nwarps) {
+    const int64_t g = a.g_begin + tile * 32 + lane;
+    if (g >= a.g_end) continue;
+    const int64_t i = (int64_t)chain * a.G + g;
     const uint64_t gid = (uint64_t)(a.gene_offset + g);
     FastGene gn;
     gn.y = a.Yg[i]; gn.v = a.vg[i]; gn.A = fa.lps[i]; gn.f = a.flags[i];
     GeneData gd;
-    const int64_t gi = valid ? g : a.g_begin;
-    gd.nd_mask = fa.nd_mask[gi]; gd.xbar = fa.xbar[gi]; gd.ss = fa.xss[gi];
+    gd.nd_mask = fa.nd_mask[g]; gd.xbar = fa.xbar[g]; gd.ss = fa.xss[g];
     gd.ndet = (RT > 0 ? RT : H.R) - __popcll(gd.nd_mask);
-    const double gl = a.gl[gi];
-    const bool in_spike = (gn.f & F_INSPIKE) != 0;   // mhYg / mhVariance_g only touch out_spike_idx (Pr:11, Pr:252-257)
-    const bool live = valid && !in_spike;
+    const double gl = a.gl[g];
+    const bool live = !(gn.f & F_INSPIKE);            // mhYg / mhVariance_g only touch out_spike_idx (Pr:11, Pr:252-257)
     double xglik = 0, vgprob = 0;
     gn.lv = 0; gn.rv = 0;
-    if (valid) {
-      uint32_t b0[4] = {0, 0, 0, 0}, b1[4] = {0, 0, 0, 0};
-      if (!a.draws[0] && (a.moves & (ZZ_MOVE_YG | ZZ_MOVE_VARIANCE_G))) philox_block(a.seed, chain, a.step, 0, gid, b0);
-      if (!a.draws[3] && (a.moves & (ZZ_MOVE_VARIANCE_G | ZZ_MOVE_ALLOC))) philox_block(a.seed, chain, a.step, 1, gid, b1);
-      if (live) { gn.lv = flog(gn.v, T.log_t); gn.rv = 1.0 / gn.v; }
-      if (a.moves & ZZ_MOVE_YG) {
-        int acc = 0;
-        if (live) {
-          double z, u, ratio;
-          if (a.draws[0]) { z = a.draws[0][i]; u = a.draws[1][i]; }
-          else { z = normal_cos(u32_to_open01(b0[0]), u32_to_open01(b0[1]), T); u = u32_to_open01(b0[2]); }
-          acc = fast_yg<RT>(H, T, gn, gd, gl, a.ty[i], z, u, ratio);
-          saw_nan |= isnan(ratio);
-          if (a.tune) { ulonglong2 w = a.win_y[i]; window_push(w, acc); a.win_y[i] = w; }   // Pr:312-322
-        }
-        if (a.dec[0]) a.dec[0][i] = (uint8_t)acc;
-      }
-      if (a.moves & ZZ_MOVE_VARIANCE_G) {
-        int acc = 0;
-        if (live) {
-          double u1, u2, ratio;
-          if (a.draws[2]) { u1 = a.draws[2][i]; u2 = a.draws[3][i]; }
-          else { u1 = u32_to_open01(b0[3]); u2 = u32_to_open01(b1[0]); }
-          acc = fast_vg(H, T, gn, gd, a.tv[i], u1, u2, ratio);
-          saw_nan |= isnan(ratio);
-          if (a.tune) { ulonglong2 w = a.win_v[i]; window_push(w, acc); a.win_v[i] = w; }   // Pr:40-50
-        }
-        if (a.dec[1]) a.dec[1][i] = (uint8_t)acc;
-      }
-      if (a.moves & ZZ_MOVE_ALLOC) {
-        double u_ai, u_w;
-        if (a.draws[4]) { u_ai = a.draws[4][i]; u_w = a.draws[5][i]; }
-        else { u_ai = u32_to_open01(b1[1]); u_w = u32_to_open01(b1[2]); }
-        const int word = fast_alloc(H, T, gn.y, gn.f, u_ai, u_w);
-        if (a.dec[2]) a.dec[2][i] = (uint8_t)word;
-        a.flags[i] = (uint16_t)gn.f;
-      }
+    uint32_t b0[4] = {0, 0, 0, 0}, b1[4] = {0, 0, 0, 0};
+    const bool own_draws = PROD || !a.draws[0];
+    if (own_draws && (a.moves & (ZZ_MOVE_YG | ZZ_MOVE_VARIANCE_G))) philox_block(a.seed, chain, a.step, 0, gid, b0);
+    if (own_draws && (a.moves & (ZZ_MOVE_VARIANCE_G | ZZ_MOVE_ALLOC))) philox_block(a.seed, chain, a.step, 1, gid, b1);
+    if (live) { gn.lv = flog(gn.v, T.log_t); gn.rv = 1.0 / gn.v; }
+    if (a.moves & ZZ_MOVE_YG) {
+      int acc_y = 0;
       if (live) {
-        a.Yg[i] = gn.y; a.vg[i] = gn.v; fa.lps[i] = gn.A;
-        // the reference's caches, re-expressed: XgLikelihood = beta (A + B), variance_g_probability = prior(v | Sg(y))
-        xglik = xg_lik_fast(H, gn, gd);
-        vgprob = vg_prior_from_q(H, gn.lv, vg_q(H, gn.lv, gn.y));
-        if (H.vub != INFINITY) vgprob -= plnorm_term(H, gn.y);
-        a.xglik[i] = xglik; a.vgprob[i] = vgprob;
-      } else {
-        xglik = H.beta * ((gn.f & F_ALLZERO) ? 0.0 : -INFINITY);          // P:117
+        double z, u, ratio;
+        if (own_draws) { z = normal_cos(u32_to_open01(b0[0]), u32_to_open01(b0[1]), T); u = u32_to_open01(b0[2]); }
+        else { z = a.draws[0][i]; u = a.draws[1][i]; }
+        acc_y = fast_yg<RT>(H, T, gn, gd, gl, a.ty[i], z, u, ratio);
+        saw_nan |= isnan(ratio);
+        if (a.tune) { ulonglong2 w = a.win_y[i]; window_push(w, acc_y); a.win_y[i] = w; }   // Pr:312-322
       }
+      if (!PROD && a.dec[0]) a.dec[0][i] = (uint8_t)acc_y;
     }
-    if (fa.want_stats) {   // all-zero genes are accounted for by k_spike_fast, after their spike move
-      double *row = fa.partials + ((int64_t)chain * fa.rows_per_chain + tile) * nstat;
-      stats_tile(row, a.K, valid && !(gn.f & F_ALLZERO), gn.y, gn.lv, gn.f, xglik, vgprob, isfinite(gn.y) && isfinite(gn.v));
+    if (a.moves & ZZ_MOVE_VARIANCE_G) {
+      int acc_v = 0;
+      if (live) {
+        double u1, u2, ratio;
+        if (own_draws) { u1 = u32_to_open01(b0[3]); u2 = u32_to_open01(b1[0]); }
+        else { u1 = a.draws[2][i]; u2 = a.draws[3][i]; }
+        acc_v = fast_vg(H, T, gn, gd, a.tv[i], u1, u2, ratio);
+        saw_nan |= isnan(ratio);
+        if (a.tune) { ulonglong2 w = a.win_v[i]; window_push(w, acc_v); a.win_v[i] = w; }   // Pr:40-50
+      }
+      if (!PROD && a.dec[1]) a.dec[1][i] = (uint8_t)acc_v;
     }
+    if (a.moves & ZZ_MOVE_ALLOC) {
+      double u_ai, u_w;
+      if (own_draws) { u_ai = u32_to_open01(b1[1]); u_w = u32_to_open01(b1[2]); }
+      else { u_ai = a.draws[4][i]; u_w = a.draws[5][i]; }
+      const int word = fast_alloc(H, T, gn.y, gn.f, u_ai, u_w);
+      if (!PROD && a.dec[2]) a.dec[2][i] = (uint8_t)word;
+      a.flags[i] = (uint16_t)gn.f;
+    }
+    if (live) {
+      a.Yg[i] = gn.y; a.vg[i] = gn.v; fa.lps[i] = gn.A;
+      // the reference's caches, re-expressed: XgLikelihood = beta (A + B), variance_g_probability = prior(v | Sg(y))
+      xglik = xg_lik_fast(H, gn, gd);
+      vgprob = vg_prior_from_q(H, gn.lv, vg_q(H, gn.lv, gn.y));
+      if (H.vub != INFINITY) vgprob -= plnorm_term(H, gn.y);
+      a.xglik[i] = xglik; a.vgprob[i] = vgprob;
+    } else {
+      xglik = H.beta * ((gn.f & F_ALLZERO) ? 0.0 : -INFINITY);            // P:117
+    }
+    // all-zero genes are accounted for by k_spike_fast, after their spike move
+    if (fa.want_stats) stats_add<BLOCK>(acc, a.K, !(gn.f & F_ALLZERO), gn.y, gn.lv, gn.f, xglik, vgprob, isfinite(gn.y) && isfinite(gn.v));
   }
   if (saw_nan) atomicOr(a.nan_flag, 1);
+  if (fa.want_stats) {
+    __syncthreads();
+    stats_flush<BLOCK>(acc, nstat, fa.partials + ((int64_t)chain * fa.rows_per_chain + blockIdx.x) * nstat, red);
+  }
 }
 
 // mhSpikeAllocation (Pr:528-638) over the static list of all-zero genes; their likelihood needs no Xg (every library is -Inf).
-// One warp per 32 list entries; also emits the sufficient statistics of every all-zero gene (after the move).
+// Also emits the sufficient statistics of every all-zero gene (after the move), one partials row per block.
 template <int RT>
 __global__ void __launch_bounds__(BLOCK) k_spike_fast(const FastArgs fa) {
   __shared__ FastH H;
   __shared__ MathTabs T;
+  __shared__ double red[BLOCK / 32];
+  extern __shared__ double acc[];
   const SweepArgs &a = fa.s;
   const int chain = blockIdx.y;
+  const int nstat = 3 * (a.K + 1) + NSTAT_FIXED_;
+  if (fa.want_stats) for (int s = 0; s < nstat; ++s) acc[s * BLOCK + threadIdx.x] = 0.0;
   load_fast(H, T, a.hyper + chain, fa.exp_tab, fa.log_tab);
   const int64_t j = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-  const int nstat = 3 * (a.K + 1) + NSTAT_FIXED_;
   const int64_t g = j < fa.n_allzero ? fa.allzero_idx[j] : -1;
   const bool valid = g >= a.g_begin && g < a.g_end;
-  const int64_t i = (int64_t)chain * a.G + (valid ? g : a.g_begin);
-  uint32_t f = a.flags[i];
-  double y = a.Yg[i], v = a.vg[i], xglik = a.xglik[i], vgprob = a.vgprob[i];
-  const bool eligible = valid && fa.do_spike_move && !(f & F_ACTIVE);   // Pr:533: all-zero AND inactive
-  int acc = 0;
-  if (eligible) {
-    const bool cur_in = (f & F_INSPIKE) != 0, prop_in = !cur_in;        // Pr:535
-    double zy, zv, u;
-    if (a.draws[6]) { zy = a.draws[6][i]; zv = a.draws[7][i]; u = a.draws[8][i]; }
-    else {
-      uint32_t b2[4];
-      philox_block(a.seed, chain, a.step, 2, (uint64_t)(a.gene_offset + g), b2);
-      box_muller(u32_open(b2[0]), u32_open(b2[1]), zy, zv); u = u32_open(b2[2]);
+  if (valid) {
+    const int64_t i = (int64_t)chain * a.G + g;
+    uint32_t f = a.flags[i];
+    double y = a.Yg[i], v = a.vg[i], xglik = a.xglik[i], vgprob = a.vgprob[i];
+    int acc_s = 0;
+    if (fa.do_spike_move && !(f & F_ACTIVE)) {                          // Pr:533: all-zero AND inactive
+      const bool cur_in = (f & F_INSPIKE) != 0, prop_in = !cur_in;      // Pr:535
+      double zy, zv, u;
+      if (a.draws[6]) { zy = a.draws[6][i]; zv = a.draws[7][i]; u = a.draws[8][i]; }
+      else {
+        uint32_t b2[4];
+        philox_block(a.seed, chain, a.step, 2, (uint64_t)(a.gene_offset + g), b2);
+        box_muller(u32_open(b2[0]), u32_open(b2[1]), zy, zv); u = u32_open(b2[2]);
+      }
+      const double yp = fma(H.sd_i, zy, H.im);                          // Pr:545
+      const double lsp = fma(H.s1, yp, H.s0);                           // log(Sg_proposed), Pr:547
+      const double lvp = (lsp + H.tau) + H.rtau * zv;                   // Pr:549: variance_g' = exp(.)
+      const double vp = fexp(lvp, T.exp_t);
+      double PVp = vg_prior_from_q(H, lvp, vg_q(H, lvp, yp));           // Pr:556
+      const double lv = flog(v, T.log_t);
+      double PVc = vg_prior_from_q(H, lv, vg_q(H, lv, y));              // Pr:558
+      if (H.vub != INFINITY) { PVp -= plnorm_term(H, yp); PVc -= plnorm_term(H, y); }
+      const double dp = yp - H.im, dc = y - H.im;
+      const double pygp = prop_in ? H.log_sp : H.log_1msp - H.log_norm_i - dp * dp * H.inv2iv;   // Pr:560
+      const double pyg = cur_in ? H.log_sp : H.log_1msp - H.log_norm_i - dc * dc * H.inv2iv;     // Pr:563
+      const double pp = prop_in ? H.log_sp : (pygp + PVp);              // Pr:569-570
+      const double pc = cur_in ? H.log_sp : (pyg + PVc);                // Pr:572-573
+      double Ap = 0;
+      if (!prop_in) Ap = detect_logsum<RT>(H, T, ~0ull, a.gl[g] * fexp(yp, T.exp_t));
+      double Lp = prop_in ? H.beta * 0.0 : H.beta * Ap;                 // Pr:579 (P:117 gives log(1*1) = 0 in the spike)
+      double Lc = xglik;                                                // Pr:581
+      if (Lp == -INFINITY && Lc == -INFINITY) { Lp = 0; Lc = 0; }       // Pr:583-585
+      const double HR = prop_in ? (pyg - H.log_1msp + PVc) : -(pygp - H.log_1msp + PVp);   // Pr:592-595
+      double ratio = H.temp * (Lp - Lc + pp - pc) + HR;                 // Pr:601
+      if (vp > H.vub) ratio = -INFINITY;                                // Pr:603
+      acc_s = (flog_core(u, T.log_t) < ratio);                          // Pr:605
+      if (isnan(ratio)) atomicOr(a.nan_flag, 1);
+      if (acc_s) f ^= F_INSPIKE;                                        // Pr:616
+      a.flags[i] = (uint16_t)f;
+      if (!prop_in) {                                                   // [proposed_out_spike_idx], Pr:620-636
+        if (acc_s) { y = yp; v = vp; a.Yg[i] = yp; a.vg[i] = vp; fa.lps[i] = Ap; }
+        vgprob = acc_s ? PVp : PVc;
+        a.vgprob[i] = vgprob;
+      }
+      xglik = acc_s ? Lp : Lc;                                          // Pr:630-632
+      a.xglik[i] = xglik;
     }
-    const double yp = fma(H.sd_i, zy, H.im);                            // Pr:545
-    const double lsp = fma(H.s1, yp, H.s0);                             // log(Sg_proposed), Pr:547
-    const double lvp = (lsp + H.tau) + H.rtau * zv;                     // Pr:549: variance_g' = exp(.)
-    const double vp = fexp(lvp, T.exp_t);
-    double PVp = vg_prior_from_q(H, lvp, vg_q(H, lvp, yp));             // Pr:556
-    const double lv = flog(v, T.log_t);
-    double PVc = vg_prior_from_q(H, lv, vg_q(H, lv, y));                // Pr:558
-    if (H.vub != INFINITY) { PVp -= plnorm_term(H, yp); PVc -= plnorm_term(H, y); }
-    const double dp = yp - H.im, dc = y - H.im;
-    const double pygp = prop_in ? H.log_sp : H.log_1msp - H.log_norm_i - dp * dp * H.inv2iv;   // Pr:560
-    const double pyg = cur_in ? H.log_sp : H.log_1msp - H.log_norm_i - dc * dc * H.inv2iv;     // Pr:563
-    const double pp = prop_in ? H.log_sp : (pygp + PVp);                // Pr:569-570
-    const double pc = cur_in ? H.log_sp : (pyg + PVc);                  // Pr:572-573
-    double Ap = 0;
-    if (!prop_in) Ap = detect_logsum<RT>(H, T, ~0ull, a.gl[g] * fexp(yp, T.exp_t));
-    double Lp = prop_in ? H.beta * 0.0 : H.beta * Ap;                   // Pr:579 (P:117 gives log(1*1) = 0 in the spike)
-    double Lc = xglik;                                                  // Pr:581
-    if (Lp == -INFINITY && Lc == -INFINITY) { Lp = 0; Lc = 0; }         // Pr:583-585
-    const double HR = prop_in ? (pyg - H.log_1msp + PVc) : -(pygp - H.log_1msp + PVp);   // Pr:592-595
-    double ratio = H.temp * (Lp - Lc + pp - pc) + HR;                   // Pr:601
-    if (vp > H.vub) ratio = -INFINITY;                                  // Pr:603
-    acc = (flog_core(u, T.log_t) < ratio);                              // Pr:605
-    if (isnan(ratio)) atomicOr(a.nan_flag, 1);
-    if (acc) f ^= F_INSPIKE;                                            // Pr:616
-    a.flags[i] = (uint16_t)f;
-    if (!prop_in) {                                                     // [proposed_out_spike_idx], Pr:620-636
-      if (acc) { y = yp; v = vp; a.Yg[i] = yp; a.vg[i] = vp; fa.lps[i] = Ap; }
-      vgprob = acc ? PVp : PVc;
-      a.vgprob[i] = vgprob;
+    if (a.dec[3]) a.dec[3][i] = (uint8_t)acc_s;
+    if (fa.want_stats) {
+      const double lv = (f & F_INSPIKE) ? 0.0 : flog(v, T.log_t);
+      stats_add<BLOCK>(acc, a.K, true, y, lv, f, xglik, vgprob, isfinite(y) && isfinite(v));
     }
-    xglik = acc ? Lp : Lc;                                              // Pr:630-632
-    a.xglik[i] = xglik;
   }
-  if (valid && a.dec[3]) a.dec[3][i] = (uint8_t)acc;
   if (fa.want_stats) {
-    const bool out = valid && !(f & F_INSPIKE);
-    const double lv = out ? flog(v, T.log_t) : 0.0;
-    double *row = fa.partials + ((int64_t)chain * fa.rows_per_chain + fa.spike_row0 + (j >> 5)) * nstat;
-    stats_tile(row, a.K, valid, y, lv, f, xglik, vgprob, isfinite(y) && isfinite(v));
+    __syncthreads();
+    stats_flush<BLOCK>(acc, nstat, fa.partials + ((int64_t)chain * fa.rows_per_chain + fa.spike_row0 + blockIdx.x) * nstat, red);
   }
 }
 
@@ -695,7 +700,7 @@ int launch_sweep(zz_handle *h, uint64_t step, int tune, uint32_t moves, const do
 
 void fill_fast_args(zz_handle *h, FastArgs &fa) {
   fa.lps = h->lps; fa.exp_tab = h->exp_tab; fa.log_tab = h->log_tab; fa.allzero_idx = h->allzero_idx; fa.n_allzero = h->n_allzero;
-  fa.nd_mask = h->nd_mask; fa.xbar = h->xbar; fa.xss = h->xss; fa.tile_counter = h->tile_counter; fa.tile_base = h->tile_base;
+  fa.nd_mask = h->nd_mask; fa.xbar = h->xbar; fa.xss = h->xss;
   fa.partials = h->sw_partials; fa.rows_per_chain = 0; fa.spike_row0 = 0; fa.want_stats = 0; fa.do_spike_move = 0;
 }
 
@@ -710,17 +715,53 @@ int ensure_lps(zz_handle *h) {
   return ZZ_OK;
 }
 
+#define ZZ_DISPATCH_SWEEP(h, prod, grid, smem, args)                                             \
+  do {                                                                                           \
+    if (prod) {                                                                                  \
+      switch ((h)->R) {                                                                          \
+        case 2: k_sweep_fast<2, true><<<grid, BLOCK, smem, (h)->stream>>>(args); break;          \
+        case 4: k_sweep_fast<4, true><<<grid, BLOCK, smem, (h)->stream>>>(args); break;          \
+        case 8: k_sweep_fast<8, true><<<grid, BLOCK, smem, (h)->stream>>>(args); break;          \
+        case 16: k_sweep_fast<16, true><<<grid, BLOCK, smem, (h)->stream>>>(args); break;        \
+        default: k_sweep_fast<0, true><<<grid, BLOCK, smem, (h)->stream>>>(args); break;         \
+      }                                                                                          \
+    } else {                                                                                     \
+      switch ((h)->R) {                                                                          \
+        case 2: k_sweep_fast<2, false><<<grid, BLOCK, smem, (h)->stream>>>(args); break;         \
+        case 4: k_sweep_fast<4, false><<<grid, BLOCK, smem, (h)->stream>>>(args); break;         \
+        case 8: k_sweep_fast<8, false><<<grid, BLOCK, smem, (h)->stream>>>(args); break;         \
+        case 16: k_sweep_fast<16, false><<<grid, BLOCK, smem, (h)->stream>>>(args); break;       \
+        default: k_sweep_fast<0, false><<<grid, BLOCK, smem, (h)->stream>>>(args); break;        \
+      }                                                                                          \
+    }                                                                                            \
+  } while (0)
+
 // resident CTAs of the persistent sweep kernel on this device (blocks per SM from the occupancy calculator x SM count)
-int persistent_blocks(zz_handle *h) {
+template <int RT> void allow_big_smem(int bytes) {
+  cudaFuncSetAttribute(k_sweep_fast<RT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k_sweep_fast<RT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k_spike_fast<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+int persistent_blocks(zz_handle *h, size_t smem) {
   if (h->persist_blocks > 0) return h->persist_blocks;
   int per_sm = 0, sms = 0;
   cudaError_t e;
+  if (smem > 40 * 1024) {   // the statistics columns of large-K models exceed the default 48 KB dynamic shared memory limit
+    switch (h->R) {
+      case 2: allow_big_smem<2>((int)smem); break;
+      case 4: allow_big_smem<4>((int)smem); break;
+      case 8: allow_big_smem<8>((int)smem); break;
+      case 16: allow_big_smem<16>((int)smem); break;
+      default: allow_big_smem<0>((int)smem); break;
+    }
+  }
   switch (h->R) {
-    case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<2>, BLOCK, 0); break;
-    case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<4>, BLOCK, 0); break;
-    case 8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<8>, BLOCK, 0); break;
-    case 16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<16>, BLOCK, 0); break;
-    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<0>, BLOCK, 0); break;
+    case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<2, true>, BLOCK, smem); break;
+    case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<4, true>, BLOCK, smem); break;
+    case 8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<8, true>, BLOCK, smem); break;
+    case 16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<16, true>, BLOCK, smem); break;
+    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<0, true>, BLOCK, smem); break;
   }
   if (e != cudaSuccess || per_sm < 1) per_sm = 2;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device) != cudaSuccess || sms < 1) sms = 148;
@@ -729,7 +770,7 @@ int persistent_blocks(zz_handle *h) {
 }
 
 // production kernels (zz_fast.cuh): persistent main sweep + spike move over the all-zero gene list; when the whole shard is
-// swept they also leave the sufficient statistics in sw_partials (consumed by zz_suffstats[_dev] without another pass)
+// swept they also leave per-block sufficient statistics in sw_partials (consumed by zz_suffstats[_dev] without another pass)
 int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, const double *const draws_dev[9], uint8_t *const dec_dev[4],
                       int64_t g_begin, int64_t g_end) {
   if (g_end <= g_begin) return ZZ_OK;
@@ -738,25 +779,31 @@ int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, con
   fill_sweep_args(h, fa.s, step, tune, moves, draws_dev, dec_dev, g_begin, g_end);
   fill_fast_args(h, fa);
   const bool full = (g_begin == 0 && g_end == h->G);
+  const int nstat = zz_suffstats_len(h->K);
+  const size_t smem = full ? sizeof(double) * nstat * BLOCK : 0;
   const int64_t ntiles = (g_end - g_begin + 31) / 32;
   const int64_t spike_blocks = h->n_allzero > 0 ? (h->n_allzero + BLOCK - 1) / BLOCK : 0;
+  int64_t per_chain = (persistent_blocks(h, sizeof(double) * nstat * BLOCK) + h->C - 1) / h->C;
+  const int64_t need = (ntiles + BLOCK / 32 - 1) / (BLOCK / 32);
+  if (per_chain > need) per_chain = need;
+  if (per_chain < 1) per_chain = 1;
   fa.want_stats = full ? 1 : 0;
-  fa.rows_per_chain = ntiles + spike_blocks * (BLOCK / 32);
-  fa.spike_row0 = ntiles;
+  fa.rows_per_chain = per_chain + spike_blocks;
+  fa.spike_row0 = per_chain;
   fa.do_spike_move = (moves & ZZ_MOVE_SPIKE) ? 1 : 0;
   h->stats_fresh = false;
-  {
-    int64_t per_chain = (persistent_blocks(h) + h->C - 1) / h->C;
-    const int64_t need = (ntiles + BLOCK / 32 - 1) / (BLOCK / 32);
-    if (per_chain > need) per_chain = need;
-    if (per_chain < 1) per_chain = 1;
-    ZZ_DISPATCH_R(h, k_sweep_fast, dim3((unsigned)per_chain, (unsigned)h->C), fa);
-    ZZ_LAUNCHED(h);
-    h->tile_base += (unsigned)(ntiles + per_chain * (BLOCK / 32));   // every warp ends on one failed fetch
-  }
-  if (dec_dev && dec_dev[3] && (moves & ZZ_MOVE_SPIKE)) ZZ_CUDA(h, cudaMemsetAsync(dec_dev[3], 0, (size_t)h->C * h->G, h->stream));
+  const bool prod = !draws_dev[0] && !draws_dev[2] && !draws_dev[4] && !dec_dev[0] && !dec_dev[1] && !dec_dev[2];
+  ZZ_DISPATCH_SWEEP(h, prod, dim3((unsigned)per_chain, (unsigned)h->C), smem, fa);
+  ZZ_LAUNCHED(h);
+  if (dec_dev[3] && (moves & ZZ_MOVE_SPIKE)) ZZ_CUDA(h, cudaMemsetAsync(dec_dev[3], 0, (size_t)h->C * h->G, h->stream));
   if (spike_blocks > 0 && (fa.do_spike_move || fa.want_stats)) {
-    ZZ_DISPATCH_R(h, k_spike_fast, dim3((unsigned)spike_blocks, (unsigned)h->C), fa);
+    switch (h->R) {
+      case 2: k_spike_fast<2><<<dim3((unsigned)spike_blocks, (unsigned)h->C), BLOCK, smem, h->stream>>>(fa); break;
+      case 4: k_spike_fast<4><<<dim3((unsigned)spike_blocks, (unsigned)h->C), BLOCK, smem, h->stream>>>(fa); break;
+      case 8: k_spike_fast<8><<<dim3((unsigned)spike_blocks, (unsigned)h->C), BLOCK, smem, h->stream>>>(fa); break;
+      case 16: k_spike_fast<16><<<dim3((unsigned)spike_blocks, (unsigned)h->C), BLOCK, smem, h->stream>>>(fa); break;
+      default: k_spike_fast<0><<<dim3((unsigned)spike_blocks, (unsigned)h->C), BLOCK, smem, h->stream>>>(fa); break;
+    }
     ZZ_LAUNCHED(h);
   }
   if (full) { h->stats_fresh = true; h->sw_rows = fa.rows_per_chain; }
@@ -1116,10 +1163,7 @@ int zz_suffstats_dev(zz_handle *h, double *out_dev) {
   ZZ_CHECK(h);
   if (!out_dev) return fail(h, ZZ_ERR_INVALID, "out_dev is NULL");
   if (h->stats_fresh) {   // the last production sweep already emitted per-tile statistics: two tiny fixed-order reductions
-    const int nst = zz_suffstats_len(h->K);
-    k_reduce_rows<<<dim3(SW_CHUNKS, h->C), BLOCK, 0, h->stream>>>(h->sw_partials, h->sw_rows, nst, h->sw_partials2);
-    ZZ_LAUNCHED(h);
-    k_reduce_final<<<h->C, BLOCK, 0, h->stream>>>(h->sw_partials2, SW_CHUNKS, nst, out_dev);
+    k_reduce_final<<<h->C, BLOCK, 0, h->stream>>>(h->sw_partials, (int)h->sw_rows, zz_suffstats_len(h->K), out_dev);
     ZZ_LAUNCHED(h);
     return ZZ_OK;
   }
@@ -1264,7 +1308,11 @@ int zz_sweep_host(zz_handle *h, uint64_t step, int tune, double *Yg, double *var
   k_pack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, d_ai, d_w, d_s, h->flags);
   ZZ_LAUNCHED(h);
   h->lps_valid = false;  // Yg arrived from the host: A(y) is rebuilt on the device (one extra pass; PCIe dominates this entry point)
-  if ((rc = launch_sweep_fast(h, step, tune, ZZ_MOVE_FUSED, nullptr, nullptr, 0, G))) return rc;
+  {
+    const double *no_draws[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint8_t *no_dec[4] = {nullptr, nullptr, nullptr, nullptr};
+    if ((rc = launch_sweep_fast(h, step, tune, ZZ_MOVE_FUSED, no_draws, no_dec, 0, G))) return rc;
+  }
   k_unpack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, h->flags, d_ai, d_w, d_s);
   ZZ_LAUNCHED(h);
   if ((rc = down(h, Yg, h->Yg, G)) || (rc = down(h, variance_g, h->vg, G)) || (rc = down(h, XgLikelihood, h->xglik, G)) ||
