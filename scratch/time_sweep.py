@@ -1,0 +1,24 @@
+import sys, os, time, numpy as np
+sys.path.insert(0, ".")
+import torch
+from zigzag_b200 import _capi, synth
+name = sys.argv[1] if len(sys.argv) > 1 else "1m_x16"
+X, gl, hd, st, chains = synth.make_config(name)
+G, R = X.shape
+hg = _capi.Hyper.make(hd["alpha_r"], hd["active_means"], hd["active_variances"], hd["weight_within_active"],
+                      **{k: float(hd[k]) for k in ("s0","s1","tau","spike_probability","inactive_means","inactive_variances","weight_active","beta","temperature","variance_g_upper_bound")})
+h = _capi.Handle(G, R, 2, num_chains=chains, seed=1)
+h.set_stream(torch.cuda.current_stream().cuda_stream)
+h.upload_data(X, gl)
+for c in range(chains):
+    h.set_hyper(hg, c); h.set_state(c, **st)
+h.refresh_caches()
+for i in range(20): h.sweep(i)
+torch.cuda.synchronize()
+n = 200
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for i in range(n): h.sweep(100 + i)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / n
+print(f"{os.environ.get('ZIGZAG_GPU_LIB','default')}: {name} sweep+spike {ms*1e3:.1f} us  -> {G*chains/ms/1e6:.2f} G gene-updates/s, {G*chains*(8*R+60)/ms/1e6/6547.2*100:.1f}% of HBM roofline")

@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libzigzag_gpu.so")
+LIB_PATH = os.environ.get("ZIGZAG_GPU_LIB", os.path.join(HERE, "libzigzag_gpu.so"))   # override: kernel-tuning builds only
 MAX_LIBS, MAX_COMP = 64, 8
 
 SLOT_YG, SLOT_VARIANCE_G, SLOT_ALLOC, SLOT_ALLOC_WITHIN, SLOT_SPIKE = 1, 2, 3, 4, 5

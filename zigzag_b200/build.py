@@ -32,7 +32,8 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
+    extra = os.environ.get("ZZ_NVCC_EXTRA", "").split()     # e.g. -DZZ_ILP=4 for kernel-tuning experiments
+    cmd = [nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)  # the image's $CC points at a gcc without the host libs nvcc needs
     r = subprocess.run(cmd, capture_output=True, text=True, env=env)

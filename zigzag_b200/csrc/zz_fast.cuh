@@ -20,6 +20,13 @@
 #include "zz_device.cuh"
 #include "zz_fastmath.cuh"
 
+#ifndef ZZ_ILP
+#define ZZ_ILP 2
+#endif
+#ifndef ZZ_SWEEP_MINB
+#define ZZ_SWEEP_MINB 3
+#endif
+
 namespace zz {
 
 struct FastH {   // one chain's hyper-parameters + hoisted gene-independent sub-expressions (shared memory)
@@ -33,31 +40,37 @@ struct FastH {   // one chain's hyper-parameters + hoisted gene-independent sub-
   double am[ZZ_MAX_COMP], inv2av[ZZ_MAX_COMP], ck[ZZ_MAX_COMP];  // ck = w_k / (sqrt2pi * sqrt(av_k))           (Pr:344)
 };
 
-__device__ __forceinline__ void load_fast(FastH &H, MathTabs &T, const zz_hyper *__restrict__ hy,
+// FastH is derived from zz_hyper once per hyper-parameter change (k_prepare_hyper, one thread per chain) and kept in global
+// memory; the sweep kernels only copy it, together with the exp/log tables, into shared memory.
+__device__ __forceinline__ void derive_fast(FastH &H, const zz_hyper *__restrict__ hy) {
+  const double s2p = sqrt(2 * PI_D);
+  H.R = hy->num_libraries; H.K = hy->num_active_components;
+  H.s0 = hy->s0; H.s1 = hy->s1; H.tau = hy->tau; H.rtau = sqrt(hy->tau); H.irt = 1.0 / H.rtau;
+  H.c1 = log(H.rtau * s2p);
+  H.sp = hy->spike_probability; H.log_sp = log(H.sp); H.log_1msp = log(1 - H.sp);
+  H.im = hy->inactive_means; H.sd_i = sqrt(hy->inactive_variances);
+  H.log_norm_i = log(s2p * H.sd_i);
+  H.inv2iv = 1.0 / (2 * hy->inactive_variances);
+  H.c0 = (1 - H.sp) / (s2p * H.sd_i);
+  H.wa = hy->weight_active; H.one_m_wa = 1 - hy->weight_active;
+  H.beta = (hy->beta < 0.0000001) ? 0.0 : hy->beta;   // P:121-125: beta < 1e-7 => likelihood 0
+  H.temp = hy->temperature; H.vub = hy->variance_g_upper_bound;
+  for (int r = 0; r < ZZ_MAX_LIBS; ++r) H.alpha[r] = hy->alpha_r[r];
+  for (int k = 0; k < ZZ_MAX_COMP; ++k) {
+    H.am[k] = hy->active_means[k];
+    H.inv2av[k] = 1.0 / (2 * hy->active_variances[k]);
+    H.ck[k] = hy->weight_within_active[k] / (s2p * sqrt(hy->active_variances[k]));
+  }
+}
+
+__device__ __forceinline__ void load_fast(FastH &H, MathTabs &T, const FastH *__restrict__ src,
                                           const double *__restrict__ exp_tab, const double2 *__restrict__ log_tab) {
   const int t = threadIdx.x, nt = blockDim.x;
   for (int j = t; j < 256; j += nt) { T.exp_t[j] = exp_tab[j]; T.log_t[j] = log_tab[j]; }
-  if (t == 0) {
-    const double s2p = sqrt(2 * PI_D);
-    H.R = hy->num_libraries; H.K = hy->num_active_components;
-    H.s0 = hy->s0; H.s1 = hy->s1; H.tau = hy->tau; H.rtau = sqrt(hy->tau); H.irt = 1.0 / H.rtau;
-    H.c1 = log(H.rtau * s2p);
-    H.sp = hy->spike_probability; H.log_sp = log(H.sp); H.log_1msp = log(1 - H.sp);
-    H.im = hy->inactive_means; H.sd_i = sqrt(hy->inactive_variances);
-    H.log_norm_i = log(s2p * H.sd_i);
-    H.inv2iv = 1.0 / (2 * hy->inactive_variances);
-    H.c0 = (1 - H.sp) / (s2p * H.sd_i);
-    H.wa = hy->weight_active; H.one_m_wa = 1 - hy->weight_active;
-    H.beta = (hy->beta < 0.0000001) ? 0.0 : hy->beta;   // P:121-125: beta < 1e-7 => likelihood 0
-    H.temp = hy->temperature; H.vub = hy->variance_g_upper_bound;
-  }
-  for (int r = t; r < ZZ_MAX_LIBS; r += nt) H.alpha[r] = hy->alpha_r[r];
-  if (t < ZZ_MAX_COMP) {
-    const double s2p = sqrt(2 * PI_D);
-    H.am[t] = hy->active_means[t];
-    H.inv2av[t] = 1.0 / (2 * hy->active_variances[t]);
-    H.ck[t] = hy->weight_within_active[t] / (s2p * sqrt(hy->active_variances[t]));
-  }
+  static_assert(sizeof(FastH) % 8 == 0, "FastH is copied as 64-bit words");
+  const uint64_t *s = reinterpret_cast<const uint64_t *>(src);
+  uint64_t *d = reinterpret_cast<uint64_t *>(&H);
+  for (int j = t; j < (int)(sizeof(FastH) / 8); j += nt) d[j] = s[j];
   __syncthreads();
 }
 
@@ -88,13 +101,24 @@ __device__ __forceinline__ double detect_logsum(const FastH &H, const MathTabs &
   if (RT > 0 && RT <= 18) {
     // q is +0 or a normal number in [2^-53, 1].  flog_core(+0) returns -1023 ln 2 = -709.1 instead of -Inf, while a sum of
     // at most 18 legitimate terms is >= 18 log(2^-53) = -661.3: "A < -700" therefore detects a zero q exactly, without a
-    // per-library test.
+    // per-library test.  Libraries are processed ZZ_ILP at a time with separate temporaries so the scheduler can overlap
+    // their (long, strictly dependent) exp -> log chains; the additions into A stay in library order.
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const double e = fexp_neg_clamped(t * H.alpha[r], T.exp_t);
-      const double p = 1 - e;
-      const double q = ((nd_mask >> r) & 1ull) ? (1 - p) : p;
-      A += flog_core(q, T.log_t);
+    for (int r0 = 0; r0 < R; r0 += ZZ_ILP) {
+      double l[ZZ_ILP];
+#pragma unroll
+      for (int j = 0; j < ZZ_ILP; ++j) {
+        if (r0 + j < R) {
+          const int r = r0 + j;
+          const double e = fexp_neg_clamped(t * H.alpha[r], T.exp_t);
+          const double p = 1 - e;
+          const double q = ((nd_mask >> r) & 1ull) ? (1 - p) : p;
+          l[j] = flog_core(q, T.log_t);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < ZZ_ILP; ++j)
+        if (r0 + j < R) A += l[j];
     }
     return A < -700.0 ? -INFINITY : A;
   }
@@ -239,12 +263,18 @@ __device__ __forceinline__ void stats_add(double *acc /*[nstat][BLOCK_]*/, int K
   if (!finite_state) fx[9 * BLOCK_] += 1.0;
 }
 
-// column sums -> one row of `partials`; fixed order (warp butterfly, then warps in order)
+// column sums -> one row of `partials`: after one barrier, warp w reduces statistics w, w + nwarps, ...; each lane adds its
+// BLOCK_/32 columns in a fixed order, then a butterfly.  `red` is unused (kept for the signature).
 template <int BLOCK_>
-__device__ __forceinline__ void stats_flush(const double *acc, int nstat, double *row, double *red /*BLOCK_/32*/) {
-  for (int s = 0; s < nstat; ++s) {
-    const double t = block_sum<BLOCK_>(acc[s * BLOCK_ + threadIdx.x], red);
-    if (threadIdx.x == 0) row[s] = t;
+__device__ __forceinline__ void stats_flush(const double *acc, int nstat, double *row, double *red) {
+  (void)red;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int s = w; s < nstat; s += BLOCK_ / 32) {
+    double v = 0;
+#pragma unroll
+    for (int j = 0; j < BLOCK_ / 32; ++j) v += acc[s * BLOCK_ + j * 32 + lane];
+    v = warp_sum(v);
+    if (lane == 0) row[s] = v;
   }
 }
 

@@ -123,10 +123,16 @@ struct FastArgs {
   const double *exp_tab; const double2 *log_tab;
   const int32_t *allzero_idx; int64_t n_allzero;   // static list of genes with no reads in any library (I:416-421)
   const uint64_t *nd_mask; const double *xbar, *xss;  // per-gene data statistics (k_prepare_data)
+  const FastH *fasth;               // [C] derived hyper-parameters (k_prepare_hyper)
   double *partials;                 // [C][rows][nstat] per-block sufficient statistics (rows = main blocks + spike blocks)
   int64_t rows_per_chain, spike_row0;
   int want_stats, do_spike_move;
 };
+
+__global__ void k_prepare_hyper(int C, const zz_hyper *hyper, FastH *out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) derive_fast(out[c], hyper + c);
+}
 
 // Xg [R][G] -> per-gene (nd_mask, n_det via popcount, xbar, ss); run once per zz_upload_data
 __global__ void __launch_bounds__(BLOCK) k_prepare_data(int64_t G, int R, const double *__restrict__ Xg, uint64_t *nd_mask, double *xbar, double *xss) {
@@ -154,8 +160,10 @@ __global__ void __launch_bounds__(BLOCK) k_prepare_data(int64_t G, int R, const 
 // One table/hyper load and one barrier per block for the whole sweep; warps never wait for each other afterwards.
 // PROD = true is the production instantiation (Philox draws, no decision export); PROD = false additionally serves the
 // "identical uniforms" test mode (explicit draws) and exports decisions.
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 template <int RT, bool PROD>
-__global__ void __launch_bounds__(BLOCK, 3) k_sweep_fast(const FastArgs fa) {
+__global__ void __launch_bounds__(BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const FastArgs fa) {
   __shared__ FastH H;
   __shared__ MathTabs T;
   __shared__ double red[BLOCK / 32];
@@ -164,13 +172,22 @@ __global__ void __launch_bounds__(BLOCK, 3) k_sweep_fast(const FastArgs fa) {
   const int chain = blockIdx.y, lane = threadIdx.x & 31;
   const int nstat = 3 * (a.K + 1) + NSTAT_FIXED_;
   if (fa.want_stats) for (int s = 0; s < nstat; ++s) acc[s * BLOCK + threadIdx.x] = 0.0;
-  load_fast(H, T, a.hyper + chain, fa.exp_tab, fa.log_tab);
+  load_fast(H, T, fa.fasth + chain, fa.exp_tab, fa.log_tab);
   const int64_t n = a.g_end - a.g_begin;
   const int64_t ntiles = (n + 31) / 32;
   const int64_t warp0 = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * (BLOCK / 32);
   bool saw_nan = false;
   for (int64_t tile = warp0; tile < ntiles; tile += nwarps) {
     const int64_t g = a.g_begin + tile * 32 + lane;
+    {   // pull the next tile's inputs towards L1 while this tile computes (no registers, no shared memory)
+      const int64_t gn_ = g + nwarps * 32;
+      if (gn_ < a.g_end) {
+        const int64_t in_ = (int64_t)chain * a.G + gn_;
+        prefetch_l1(a.Yg + in_); prefetch_l1(a.vg + in_); prefetch_l1(fa.lps + in_); prefetch_l1(a.ty + in_); prefetch_l1(a.tv + in_);
+        prefetch_l1(fa.nd_mask + gn_); prefetch_l1(fa.xbar + gn_); prefetch_l1(fa.xss + gn_); prefetch_l1(a.gl + gn_);
+        if ((lane & 3) == 0) prefetch_l1(a.flags + in_);
+      }
+    }
     if (g >= a.g_end) continue;
     const int64_t i = (int64_t)chain * a.G + g;
     const uint64_t gid = (uint64_t)(a.gene_offset + g);
@@ -252,7 +269,7 @@ __global__ void __launch_bounds__(BLOCK) k_spike_fast(const FastArgs fa) {
   const int chain = blockIdx.y;
   const int nstat = 3 * (a.K + 1) + NSTAT_FIXED_;
   if (fa.want_stats) for (int s = 0; s < nstat; ++s) acc[s * BLOCK + threadIdx.x] = 0.0;
-  load_fast(H, T, a.hyper + chain, fa.exp_tab, fa.log_tab);
+  load_fast(H, T, fa.fasth + chain, fa.exp_tab, fa.log_tab);
   const int64_t j = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   const int64_t g = j < fa.n_allzero ? fa.allzero_idx[j] : -1;
   const bool valid = g >= a.g_begin && g < a.g_end;
@@ -322,7 +339,7 @@ __global__ void __launch_bounds__(BLOCK) k_refresh_lps(const FastArgs fa) {
   __shared__ MathTabs T;
   const SweepArgs &a = fa.s;
   const int chain = blockIdx.y;
-  load_fast(H, T, a.hyper + chain, fa.exp_tab, fa.log_tab);
+  load_fast(H, T, fa.fasth + chain, fa.exp_tab, fa.log_tab);
   const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (g >= a.G) return;
   const int64_t i = (int64_t)chain * a.G + g;
@@ -616,6 +633,7 @@ struct zz_handle {
   bool have_data;
   double *lps; double *exp_tab; double2 *log_tab; int32_t *allzero_idx; int64_t n_allzero;
   uint64_t *nd_mask; double *xbar, *xss;   // per-gene data statistics (k_prepare_data)
+  FastH *fasth; bool fasth_valid;           // derived hyper-parameters of the production kernels
   unsigned *tile_counter; unsigned tile_base; int persist_blocks;
   double *sw_partials, *sw_partials2; int64_t sw_rows; bool stats_fresh;   // statistics emitted by the last production sweep
   bool lps_valid;                          // lps == A(current Yg, alpha_r) for every out-of-spike gene
@@ -700,11 +718,20 @@ int launch_sweep(zz_handle *h, uint64_t step, int tune, uint32_t moves, const do
 
 void fill_fast_args(zz_handle *h, FastArgs &fa) {
   fa.lps = h->lps; fa.exp_tab = h->exp_tab; fa.log_tab = h->log_tab; fa.allzero_idx = h->allzero_idx; fa.n_allzero = h->n_allzero;
-  fa.nd_mask = h->nd_mask; fa.xbar = h->xbar; fa.xss = h->xss;
+  fa.nd_mask = h->nd_mask; fa.xbar = h->xbar; fa.xss = h->xss; fa.fasth = h->fasth;
   fa.partials = h->sw_partials; fa.rows_per_chain = 0; fa.spike_row0 = 0; fa.want_stats = 0; fa.do_spike_move = 0;
 }
 
+int ensure_fasth(zz_handle *h) {
+  if (h->fasth_valid) return ZZ_OK;
+  k_prepare_hyper<<<(h->C + 63) / 64, 64, 0, h->stream>>>(h->C, h->hyper, h->fasth);
+  ZZ_LAUNCHED(h);
+  h->fasth_valid = true;
+  return ZZ_OK;
+}
+
 int ensure_lps(zz_handle *h) {
+  if (int rc = ensure_fasth(h)) return rc;
   if (h->lps_valid) return ZZ_OK;
   FastArgs fa;
   fill_sweep_args(h, fa.s, 0, 0, 0, nullptr, nullptr, 0, h->G);
@@ -932,6 +959,8 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   ZZ_CUDA(h, cudaMemcpyAsync(h->log_tab, kLogTab, sizeof(kLogTab), cudaMemcpyHostToDevice, h->stream));
   ZZ_CUDA(h, cudaMalloc(&h->allzero_idx, sizeof(int32_t) * G));
   h->n_allzero = 0; h->lps_valid = false; h->stats_fresh = false; h->tile_base = 0; h->persist_blocks = 0; h->sw_rows = 0;
+  ZZ_CUDA(h, cudaMalloc(&h->fasth, sizeof(FastH) * h->C));
+  h->fasth_valid = false;
   ZZ_CUDA(h, cudaMalloc(&h->nd_mask, sizeof(uint64_t) * G));
   ZZ_CUDA(h, cudaMalloc(&h->xbar, sizeof(double) * G));
   ZZ_CUDA(h, cudaMalloc(&h->xss, sizeof(double) * G));
@@ -957,7 +986,7 @@ void zz_destroy(zz_handle *h) {
   cudaSetDevice(h->cfg.device);
   void *ptrs[] = {h->Xg, h->gl, h->Yg, h->vg, h->xglik, h->vgprob, h->ty, h->tv, h->flags, h->win_y, h->win_v, h->trace,
                   h->hyper, h->partials, h->red_out, h->scratch, h->dec, h->iscratch, h->nan_flag, h->lps, h->exp_tab,
-                  h->log_tab, h->allzero_idx, h->nd_mask, h->xbar, h->xss, h->tile_counter, h->sw_partials, h->sw_partials2};
+                  h->log_tab, h->allzero_idx, h->nd_mask, h->xbar, h->xss, h->tile_counter, h->sw_partials, h->sw_partials2, h->fasth};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -1067,6 +1096,7 @@ int zz_set_hyper(zz_handle *h, int chain, const zz_hyper *hy) {
   if (hy->num_libraries != h->R || hy->num_active_components != h->K)
     return fail(h, ZZ_ERR_INVALID, "hyper dimensions do not match the handle");
   if (memcmp(h->hyper_host[chain].alpha_r, hy->alpha_r, sizeof(double) * h->R) != 0) h->lps_valid = false;  // A depends on alpha_r
+  h->fasth_valid = false;
   h->hyper_host[chain] = *hy;
   ZZ_CUDA(h, cudaMemcpyAsync(h->hyper + chain, &h->hyper_host[chain], sizeof(zz_hyper), cudaMemcpyHostToDevice, h->stream));
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -1235,7 +1265,7 @@ int zz_px_commit(zz_handle *h, int chain, int lib, double alpha_new) {
     ZZ_LAUNCHED(h);
   }
   h->hyper_host[chain].alpha_r[lib] = alpha_new;
-  h->lps_valid = false; h->stats_fresh = false;
+  h->lps_valid = false; h->stats_fresh = false; h->fasth_valid = false;
   ZZ_CUDA(h, cudaMemcpyAsync(h->hyper + chain, &h->hyper_host[chain], sizeof(zz_hyper), cudaMemcpyHostToDevice, h->stream));
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
   if (h->R <= 2) {  // Pr:219: full recompute with the proposed p_x
