@@ -589,10 +589,30 @@ static double two_boundary_slide(zzo_chain *c, double p, double lo, double hi, d
   return lo + fabs(np - lo);
 }
 
-/* draws of one move for every gene, taken from the sweep draw map at the chain's current step */
-static void fill_sweep_draws(zzo_chain *c) {
-  if (!c->draws) c->draws = (double *)malloc(sizeof(double) * 9 * c->G);
-  zzo_sweep_draws(c->seed, 0, c->step, 0, c->G, c->draws);
+/* draws of one move for every gene, taken from the sweep draw map at the chain's current step; only the Philox blocks the
+   move needs are generated (mask bit b = block b) */
+static void fill_sweep_draws(zzo_chain *c, int blocks) {
+  int64_t G = c->G;
+  if (!c->draws) c->draws = (double *)malloc(sizeof(double) * 9 * G);
+  double *d = c->draws;
+#pragma omp parallel for schedule(static)
+  for (int64_t g = 0; g < G; ++g) {
+    double a[4], n[2];
+    if (blocks & 1) {
+      zzo_uniform4(c->seed, 0, c->step, 0, (uint64_t)g, a);
+      zzo_box_muller(a[0], a[1], n);
+      d[0 * G + g] = n[0]; d[1 * G + g] = a[2]; d[2 * G + g] = a[3];
+    }
+    if (blocks & 2) {
+      zzo_uniform4(c->seed, 0, c->step, 1, (uint64_t)g, a);
+      d[3 * G + g] = a[0]; d[4 * G + g] = a[1]; d[5 * G + g] = a[2];
+    }
+    if (blocks & 4) {
+      zzo_uniform4(c->seed, 0, c->step, 2, (uint64_t)g, a);
+      zzo_box_muller(a[0], a[1], n);
+      d[6 * G + g] = n[0]; d[7 * G + g] = n[1]; d[8 * G + g] = a[2];
+    }
+  }
 }
 #define DRAW(c, j) ((c)->draws + (int64_t)(j) * (c)->G)
 
@@ -612,11 +632,11 @@ static void mv_gibbsMixtureWeights(zzo_chain *c) { /* Pr:412-431 */
   }
 }
 static void mv_allocAI(zzo_chain *c) {
-  fill_sweep_draws(c);
+  fill_sweep_draws(c, 2);
   zzo_gibbs_alloc_active_inactive(&c->h, &c->s, DRAW(c, 4), DRAW(c, 5), NULL, NULL);
 }
 static void mv_allocWithin(zzo_chain *c) {
-  fill_sweep_draws(c);
+  fill_sweep_draws(c, 2);
   zzo_gibbs_alloc_within_active(&c->h, &c->s, DRAW(c, 5), NULL);
 }
 static void mv_mhInactiveMeans(zzo_chain *c, int tune) { /* Pr:433-471 */
@@ -673,15 +693,15 @@ static void mv_gibbsSpikeProb(zzo_chain *c) { /* Pr:511-526 */
   if (!isnan(ns)) c->h.spike_probability = ns;
 }
 static void mv_mhSpikeAllocation(zzo_chain *c) {
-  fill_sweep_draws(c);
+  fill_sweep_draws(c, 4);
   zzo_mh_spike_alloc(&c->h, &c->s, DRAW(c, 6), DRAW(c, 7), DRAW(c, 8), NULL, NULL);
 }
 static void mv_mhYg(zzo_chain *c, int tune) {
-  fill_sweep_draws(c);
+  fill_sweep_draws(c, 1);
   zzo_mh_yg(&c->h, &c->s, DRAW(c, 0), DRAW(c, 1), tune, NULL, NULL);
 }
 static void mv_mhVariance_g(zzo_chain *c, int tune) {
-  fill_sweep_draws(c);
+  fill_sweep_draws(c, 3);
   zzo_mh_variance_g(&c->h, &c->s, DRAW(c, 2), DRAW(c, 3), tune, NULL, NULL);
 }
 static double sum_vgprob_out(const zzo_chain *c) {

@@ -1,0 +1,46 @@
+"""Run-level pin of the oracle: the only numeric results the reference publishes are the tutorial's P(active) for the first
+ten genes of the bundled lung data (docs/tutorial.html:681-691, one unseeded chain).  The oracle's schedule-faithful chain
+(15 moves per generation drawn with the reference's weights, tuning every 400 generations) must reproduce them within
+Monte-Carlo error.  CPU only.  The full-length tutorial run (burnin 5000 + mcmc 20000, ~5 min) agrees to 0.01; the default
+here is shortened to keep the CPU suite at a few minutes (ZZ_LONG_TESTS=1 runs the full one)."""
+import os
+import numpy as np
+from oracle import oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lung():
+    d = np.load(os.path.join(HERE, "golden", "lung.npz"))
+    tpm = d["tpm"]
+    X = np.full(tpm.shape, -np.inf)
+    np.log(tpm, where=tpm > 0, out=X)
+    return d, X, d["gene_length"] / d["gene_length"].mean()
+
+
+def test_lung_fixture_matches_the_survey():
+    d, X, gl = lung()
+    assert X.shape == (5000, 4) and int(np.isneginf(X).all(1).sum()) == 289
+    assert list(np.isneginf(X).sum(0)) == [470, 543, 500, 556]
+    assert abs(gl.mean() - 1) < 1e-12
+
+
+def test_oracle_chain_reproduces_tutorial_prob_active():
+    d, X, gl = lung()
+    long_run = os.environ.get("ZZ_LONG_TESTS") == "1"
+    burn, ngen, tol = (5000, 20000, 0.03) if long_run else (2000, 5000, 0.08)
+    pr = O.Priors.defaults(float(d["threshold_i"]), d["threshold_a"])
+    c = O.Chain(X, gl, pr, 2, seed=1, omp=True)
+    c.burnin(burn)
+    c.mcmc(ngen, 10)
+    pa = c.prob_active()
+    pinned = d["tutorial_prob_active_first10"]
+    assert np.abs(pa[:10] - pinned).max() < tol, (pa[:10], pinned)
+    h = c.hyper
+    # posterior centres read off the tutorial's report figures
+    assert -10900 < c.lnl() < -10100
+    assert -2.4 < h.s0 < -1.7 and -0.45 < h.s1 < -0.27 and 0.7 < h.tau < 1.05
+    assert 0.05 < h.spike_probability < 0.2 and -2.5 < h.inactive_means < -1.4 and 1.3 < h.inactive_variances < 2.4
+    assert 2.2 < h.active_means[0] < 3.1 and 5.5 < h.active_means[1] < 9.5 and 0.64 < h.weight_active < 0.8
+    assert all(8 < h.alpha_r[r] < 25 for r in range(4))
+    assert 0.55 < pa.mean() < 0.8

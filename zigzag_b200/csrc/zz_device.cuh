@@ -182,7 +182,7 @@ __device__ __forceinline__ double u32_open(uint32_t w) {  // (w + 0.5) * 2^-32: 
 }
 
 // One Philox block: counter = (global gene index, blk | chain<<8, step lo, step hi); key = seed.
-// Draw map of a sweep (identical in oracle/zz_oracle.c:zzo_sweep_draws and DESIGN.md "RNG"):
+// Draw map of a sweep (specified in DESIGN.md "RNG"; the test oracle implements the same map):
 //   blk 0: w0,w1 -> Box-Muller -> z of mhYg (cos branch); w2 -> u of mhYg; w3 -> u_proposal of mhVariance_g
 //   blk 1: w0 -> u_accept of mhVariance_g; w1 -> u of the active/inactive draw; w2 -> u of the within-active draw
 //   blk 2: w0,w1 -> Box-Muller -> (z_y, z_v) of mhSpikeAllocation; w2 -> its u
