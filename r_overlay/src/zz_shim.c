@@ -1,0 +1,155 @@
+/*
+ * zz_shim.c — the `.Call` shim an R maintainer adds to the zigzag package (as src/zz_shim.c) to run the per-gene moves on
+ * the GPU through the C ABI of include/zigzag_gpu.h.  It cannot be compiled in this image (no R headers); it is the
+ * reference-side binding described in INTEGRATION.md.  Link with -lzigzag_gpu.
+ *
+ * Conventions: R numeric = double, R integer/logical = int32, matrices column-major (Xg goes through unchanged), the
+ * handle lives in an external pointer whose finalizer calls zz_destroy.  Errors are raised with Rf_error only after every
+ * C resource of the call has been released (Rf_error longjmps).
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <string.h>
+#include "zigzag_gpu.h"
+
+static zz_handle *H(SEXP ptr) {
+  zz_handle *h = (zz_handle *)R_ExternalPtrAddr(ptr);
+  if (!h) Rf_error("zigzag GPU handle is NULL (object was copied or already released)");
+  return h;
+}
+static void chk(zz_handle *h, int rc) { if (rc != ZZ_OK) Rf_error("zigzag_gpu: %s (code %d)", zz_last_error(h), rc); }
+static void fin(SEXP ptr) { zz_handle *h = (zz_handle *)R_ExternalPtrAddr(ptr); if (h) { zz_destroy(h); R_ClearExternalPtr(ptr); } }
+static const double *dbl(SEXP x) { return Rf_isNull(x) ? NULL : REAL(x); }
+static const int *intg(SEXP x) { return Rf_isNull(x) ? NULL : INTEGER(x); }
+
+/* zz_create + zz_upload_data: called once at the end of zigzag$new() (R/zigzagInitialize.R:564) */
+SEXP zzR_create(SEXP Xg, SEXP gene_lengths, SEXP K, SEXP seed, SEXP device) {
+  SEXP dim = Rf_getAttrib(Xg, R_DimSymbol);
+  zz_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.num_genes = INTEGER(dim)[0]; cfg.num_libraries = INTEGER(dim)[1]; cfg.num_active_components = Rf_asInteger(K);
+  cfg.num_chains = 1; cfg.device = Rf_asInteger(device); cfg.seed = (uint64_t)Rf_asReal(seed); cfg.gene_offset = 0;
+  zz_handle *h = NULL;
+  int rc = zz_create(&cfg, &h);
+  if (rc != ZZ_OK) { char msg[512]; strncpy(msg, h ? zz_last_error(h) : "invalid configuration", 511); msg[511] = 0; if (h) zz_destroy(h); Rf_error("zz_create: %s", msg); }
+  rc = zz_upload_data(h, REAL(Xg), REAL(gene_lengths));
+  if (rc != ZZ_OK) { char msg[512]; strncpy(msg, zz_last_error(h), 511); msg[511] = 0; zz_destroy(h); Rf_error("zz_upload_data: %s", msg); }
+  SEXP ptr = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(ptr, fin, TRUE);
+  UNPROTECT(1);
+  return ptr;
+}
+
+/* fields -> device; any argument may be NULL */
+SEXP zzR_set_state(SEXP ptr, SEXP Yg, SEXP vg, SEXP ai, SEXP within, SEXP spike, SEXP xglik, SEXP vgprob, SEXP ty, SEXP tv, SEXP pinned) {
+  zz_handle *h = H(ptr);
+  chk(h, zz_set_state(h, 0, dbl(Yg), dbl(vg), intg(ai), intg(within), intg(spike), dbl(xglik), dbl(vgprob), dbl(ty), dbl(tv), intg(pinned)));
+  return R_NilValue;
+}
+
+/* device -> a named list of the per-gene fields (lazy pull at sample / write time) */
+SEXP zzR_get_state(SEXP ptr, SEXP G_) {
+  zz_handle *h = H(ptr);
+  const int G = Rf_asInteger(G_);
+  const char *names[] = {"Yg", "variance_g", "allocation_active_inactive", "allocation_within_active", "inactive_spike_allocation",
+                         "XgLikelihood", "variance_g_probability", "tuningParam_yg", "tuningParam_variance_g", ""};
+  SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+  for (int i = 0; i < 9; ++i) SET_VECTOR_ELT(out, i, Rf_allocVector((i >= 2 && i <= 4) ? INTSXP : REALSXP, G));
+  int rc = zz_get_state(h, 0, REAL(VECTOR_ELT(out, 0)), REAL(VECTOR_ELT(out, 1)), INTEGER(VECTOR_ELT(out, 2)), INTEGER(VECTOR_ELT(out, 3)),
+                        INTEGER(VECTOR_ELT(out, 4)), REAL(VECTOR_ELT(out, 5)), REAL(VECTOR_ELT(out, 6)), REAL(VECTOR_ELT(out, 7)),
+                        REAL(VECTOR_ELT(out, 8)));
+  UNPROTECT(1);
+  chk(h, rc);
+  return out;
+}
+
+/* scalar fields -> zz_hyper; called by every accepted hyper-parameter move */
+SEXP zzR_set_hyper(SEXP ptr, SEXP s0, SEXP s1, SEXP tau, SEXP alpha_r, SEXP spike_p, SEXP im, SEXP iv, SEXP am, SEXP av, SEXP wa,
+                   SEXP ww, SEXP beta, SEXP temperature, SEXP vub) {
+  zz_handle *h = H(ptr);
+  zz_hyper hy;
+  memset(&hy, 0, sizeof hy);
+  hy.num_libraries = LENGTH(alpha_r); hy.num_active_components = LENGTH(am);
+  hy.s0 = Rf_asReal(s0); hy.s1 = Rf_asReal(s1); hy.tau = Rf_asReal(tau);
+  memcpy(hy.alpha_r, REAL(alpha_r), sizeof(double) * hy.num_libraries);
+  hy.spike_probability = Rf_asReal(spike_p); hy.inactive_means = Rf_asReal(im); hy.inactive_variances = Rf_asReal(iv);
+  memcpy(hy.active_means, REAL(am), sizeof(double) * hy.num_active_components);
+  memcpy(hy.active_variances, REAL(av), sizeof(double) * hy.num_active_components);
+  memcpy(hy.weight_within_active, REAL(ww), sizeof(double) * hy.num_active_components);
+  hy.weight_active = Rf_asReal(wa); hy.beta = Rf_asReal(beta); hy.temperature = Rf_asReal(temperature);
+  hy.variance_g_upper_bound = Rf_asReal(vub);
+  chk(h, zz_set_hyper(h, 0, &hy));
+  return R_NilValue;
+}
+
+/* the five per-gene moves: proposal_list[[10]], [[11]], [[2]], [[3]], [[9]] (R/zigzagInitialize.R:207-221) */
+SEXP zzR_mh_yg(SEXP ptr, SEXP step, SEXP tune) { zz_handle *h = H(ptr); chk(h, zz_mh_yg(h, (uint64_t)Rf_asReal(step), Rf_asLogical(tune), NULL, NULL)); return R_NilValue; }
+SEXP zzR_mh_variance_g(SEXP ptr, SEXP step, SEXP tune) { zz_handle *h = H(ptr); chk(h, zz_mh_variance_g(h, (uint64_t)Rf_asReal(step), Rf_asLogical(tune), NULL, NULL)); return R_NilValue; }
+SEXP zzR_gibbs_alloc(SEXP ptr, SEXP step) { zz_handle *h = H(ptr); chk(h, zz_gibbs_alloc(h, (uint64_t)Rf_asReal(step), NULL, NULL)); return R_NilValue; }
+SEXP zzR_gibbs_alloc_within(SEXP ptr, SEXP step) { zz_handle *h = H(ptr); chk(h, zz_gibbs_alloc_within(h, (uint64_t)Rf_asReal(step), NULL, NULL)); return R_NilValue; }
+SEXP zzR_mh_spike_alloc(SEXP ptr, SEXP step) { zz_handle *h = H(ptr); chk(h, zz_mh_spike_alloc(h, (uint64_t)Rf_asReal(step), NULL, NULL)); return R_NilValue; }
+SEXP zzR_sweep(SEXP ptr, SEXP step, SEXP tune) { zz_handle *h = H(ptr); chk(h, zz_sweep(h, (uint64_t)Rf_asReal(step), Rf_asLogical(tune), 0, NULL, NULL)); return R_NilValue; }
+
+/* reductions consumed by the hyper-parameter moves */
+SEXP zzR_suffstats(SEXP ptr, SEXP K) {
+  zz_handle *h = H(ptr);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, zz_suffstats_len(Rf_asInteger(K))));
+  int rc = zz_suffstats(h, REAL(out));
+  UNPROTECT(1); chk(h, rc);
+  return out;
+}
+SEXP zzR_varg_hyper_sum(SEXP ptr, SEXP s0, SEXP s1, SEXP tau) {
+  zz_handle *h = H(ptr);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, 2));
+  int rc = zz_varg_hyper_sum(h, 0, Rf_asReal(s0), Rf_asReal(s1), Rf_asReal(tau), REAL(out));
+  UNPROTECT(1); chk(h, rc);
+  return out;
+}
+SEXP zzR_commit_varg_hyper(SEXP ptr) { zz_handle *h = H(ptr); chk(h, zz_commit_varg_hyper(h, 0)); return R_NilValue; }
+SEXP zzR_level2_sums(SEXP ptr, SEXP im, SEXP iv, SEXP am, SEXP av) {
+  zz_handle *h = H(ptr);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, 2));
+  int rc = zz_level2_sums(h, 0, Rf_asReal(im), Rf_asReal(iv), REAL(am), REAL(av), REAL(out));
+  UNPROTECT(1); chk(h, rc);
+  return out;
+}
+SEXP zzR_px_delta(SEXP ptr, SEXP alpha_prop, SEXP lib) {   /* lib is 1-based */
+  zz_handle *h = H(ptr);
+  const int R = LENGTH(alpha_prop);
+  unsigned char mask[ZZ_MAX_LIBS];
+  memset(mask, 0, sizeof mask); mask[Rf_asInteger(lib) - 1] = 1;
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, R));
+  int rc = zz_px_delta(h, 0, REAL(alpha_prop), mask, REAL(out));
+  UNPROTECT(1); chk(h, rc);
+  return out;
+}
+SEXP zzR_px_commit(SEXP ptr, SEXP lib, SEXP alpha_new) { zz_handle *h = H(ptr); chk(h, zz_px_commit(h, 0, Rf_asInteger(lib) - 1, Rf_asReal(alpha_new))); return R_NilValue; }
+SEXP zzR_lnl(SEXP ptr) { zz_handle *h = H(ptr); double v = 0; chk(h, zz_lnl(h, 0, &v)); return Rf_ScalarReal(v); }
+SEXP zzR_tune(SEXP ptr, SEXP target) { zz_handle *h = H(ptr); chk(h, zz_tune(h, Rf_asReal(target))); return R_NilValue; }
+SEXP zzR_nan_flag(SEXP ptr) { zz_handle *h = H(ptr); int f = 0; chk(h, zz_nan_flag(h, &f)); return Rf_ScalarLogical(f); }
+SEXP zzR_accumulate_alloc_trace(SEXP ptr) { zz_handle *h = H(ptr); chk(h, zz_accumulate_alloc_trace(h)); return R_NilValue; }
+SEXP zzR_reset_alloc_trace(SEXP ptr) { zz_handle *h = H(ptr); chk(h, zz_reset_alloc_trace(h)); return R_NilValue; }
+SEXP zzR_get_alloc_trace(SEXP ptr, SEXP G_, SEXP K_) {   /* G x (K+1) numeric matrix, like the field allocation_trace */
+  zz_handle *h = H(ptr);
+  const int G = Rf_asInteger(G_), K1 = Rf_asInteger(K_) + 1;
+  uint32_t *buf = (uint32_t *)R_alloc((size_t)G * K1, sizeof(uint32_t));
+  chk(h, zz_get_alloc_trace(h, 0, buf));
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, G, K1));
+  for (size_t i = 0; i < (size_t)G * K1; ++i) REAL(out)[i] = buf[i];   /* [K+1][G] == column-major G x (K+1) */
+  UNPROTECT(1);
+  return out;
+}
+
+static const R_CallMethodDef calls[] = {
+  {"zzR_create", (DL_FUNC)&zzR_create, 5}, {"zzR_set_state", (DL_FUNC)&zzR_set_state, 11}, {"zzR_get_state", (DL_FUNC)&zzR_get_state, 2},
+  {"zzR_set_hyper", (DL_FUNC)&zzR_set_hyper, 15}, {"zzR_mh_yg", (DL_FUNC)&zzR_mh_yg, 3}, {"zzR_mh_variance_g", (DL_FUNC)&zzR_mh_variance_g, 3},
+  {"zzR_gibbs_alloc", (DL_FUNC)&zzR_gibbs_alloc, 2}, {"zzR_gibbs_alloc_within", (DL_FUNC)&zzR_gibbs_alloc_within, 2},
+  {"zzR_mh_spike_alloc", (DL_FUNC)&zzR_mh_spike_alloc, 2}, {"zzR_sweep", (DL_FUNC)&zzR_sweep, 3}, {"zzR_suffstats", (DL_FUNC)&zzR_suffstats, 2},
+  {"zzR_varg_hyper_sum", (DL_FUNC)&zzR_varg_hyper_sum, 4}, {"zzR_commit_varg_hyper", (DL_FUNC)&zzR_commit_varg_hyper, 1},
+  {"zzR_level2_sums", (DL_FUNC)&zzR_level2_sums, 5}, {"zzR_px_delta", (DL_FUNC)&zzR_px_delta, 3}, {"zzR_px_commit", (DL_FUNC)&zzR_px_commit, 3},
+  {"zzR_lnl", (DL_FUNC)&zzR_lnl, 1}, {"zzR_tune", (DL_FUNC)&zzR_tune, 2}, {"zzR_nan_flag", (DL_FUNC)&zzR_nan_flag, 1},
+  {"zzR_accumulate_alloc_trace", (DL_FUNC)&zzR_accumulate_alloc_trace, 1}, {"zzR_reset_alloc_trace", (DL_FUNC)&zzR_reset_alloc_trace, 1},
+  {"zzR_get_alloc_trace", (DL_FUNC)&zzR_get_alloc_trace, 3}, {NULL, NULL, 0}};
+
+void R_init_zigzag(DllInfo *dll) { R_registerRoutines(dll, NULL, calls, NULL, NULL); R_useDynamicSymbols(dll, FALSE); }
