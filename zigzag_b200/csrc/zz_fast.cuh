@@ -36,6 +36,7 @@ struct FastH {   // one chain's hyper-parameters + hoisted gene-independent sub-
   double sp, log_sp, log_1msp, log_norm_i;
   double im, sd_i, inv2iv, c0;            // c0 = (1 - sp) / (sqrt2pi * sd_i):  L0 = c0 * exp(-(y-im)^2 / (2 iv))   (P:220)
   double wa, one_m_wa, beta, temp, vub;
+  double alpha_min;                       // min_r alpha_r: t * alpha_min >= 37.5 => every p_x == 1 exactly
   double alpha[ZZ_MAX_LIBS];
   double am[ZZ_MAX_COMP], inv2av[ZZ_MAX_COMP], ck[ZZ_MAX_COMP];  // ck = w_k / (sqrt2pi * sqrt(av_k))           (Pr:344)
 };
@@ -55,7 +56,8 @@ __device__ __forceinline__ void derive_fast(FastH &H, const zz_hyper *__restrict
   H.wa = hy->weight_active; H.one_m_wa = 1 - hy->weight_active;
   H.beta = (hy->beta < 0.0000001) ? 0.0 : hy->beta;   // P:121-125: beta < 1e-7 => likelihood 0
   H.temp = hy->temperature; H.vub = hy->variance_g_upper_bound;
-  for (int r = 0; r < ZZ_MAX_LIBS; ++r) H.alpha[r] = hy->alpha_r[r];
+  H.alpha_min = INFINITY;
+  for (int r = 0; r < ZZ_MAX_LIBS; ++r) { H.alpha[r] = hy->alpha_r[r]; if (r < H.R && !(hy->alpha_r[r] >= H.alpha_min)) H.alpha_min = hy->alpha_r[r]; }
   for (int k = 0; k < ZZ_MAX_COMP; ++k) {
     H.am[k] = hy->active_means[k];
     H.inv2av[k] = 1.0 / (2 * hy->active_variances[k]);
@@ -159,11 +161,14 @@ __device__ __forceinline__ double xg_lik_fast(const FastH &H, const FastGene &g,
 }
 
 // mhYg (Pr:250-333)
+// `yp`, `tp` = proposed Yg (Pr:257) and gl * exp(yp) (U:157).  `saturated` is warp-uniform: every proposing lane of the warp has
+// tp * alpha_r >= 37.5 > 54 ln 2 for all r, so exp(-tp alpha_r) <= 2^-54 and p_x = 1 - exp(.) rounds to exactly 1: the
+// detection term is log(1) = 0 per detected library and log(0) = -Inf if any library is undetected — no exp/log needed.
+// (Genes are stored sorted by expression, so whole warps of highly expressed genes take this path.)
 template <int RT>
-__device__ __forceinline__ int fast_yg(const FastH &H, const MathTabs &T, FastGene &g, const GeneData &d, double gl, double ty,
-                                       double z, double u, double &ratio) {
-  const double yp = g.y + ty * z;                                       // Pr:257
-  const double Ap = detect_logsum<RT>(H, T, d.nd_mask, gl * fexp(yp, T.exp_t));   // Pr:261-265
+__device__ __forceinline__ int fast_yg(const FastH &H, const MathTabs &T, FastGene &g, const GeneData &d, double yp, double tp,
+                                       bool saturated, double u, double &ratio) {
+  const double Ap = saturated ? (d.nd_mask ? -INFINITY : 0.0) : detect_logsum<RT>(H, T, d.nd_mask, tp);   // Pr:261-265
   const double dLX = H.beta * ((Ap - g.A) - 0.5 * (sqdist(d, yp) - sqdist(d, g.y)) * g.rv);   // XgLik' - XgLik
   const double q = vg_q(H, g.lv, g.y), qp = vg_q(H, g.lv, yp);
   double dPV = -0.5 * (qp * qp - q * q);                                // Pr:267 - cache

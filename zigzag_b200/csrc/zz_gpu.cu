@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 #include <new>
+#include <algorithm>
 #include "zz_device.cuh"
 #include "zz_fast.cuh"
 
@@ -40,6 +41,7 @@ struct SweepArgs {
   uint16_t *flags;
   ulonglong2 *win_y, *win_v;
   const zz_hyper *hyper;
+  const int32_t *perm;              // device slot -> original (caller's) local gene index; Philox is keyed by the original index
   const double *draws[9];
   uint8_t *dec[4];
   int *nan_flag;
@@ -52,7 +54,7 @@ __global__ void __launch_bounds__(BLOCK) k_sweep(const SweepArgs a) {
   const int64_t g = a.g_begin + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (g >= a.g_end) return;
   const int64_t i = (int64_t)chain * a.G + g;
-  const uint64_t gid = (uint64_t)(a.gene_offset + g);
+  const uint64_t gid = (uint64_t)(a.gene_offset + a.perm[g]);
   Gene gn;
   gn.y = a.Yg[i]; gn.v = a.vg[i]; gn.xglik = a.xglik[i]; gn.vgprob = a.vgprob[i]; gn.f = a.flags[i];
   const double gl = a.gl[g];
@@ -121,7 +123,7 @@ struct FastArgs {
   SweepArgs s;
   double *lps;                      // [C][G] A(y): sum of the detection log-terms at the current Yg
   const double *exp_tab; const double2 *log_tab;
-  const int32_t *allzero_idx; int64_t n_allzero;   // static list of genes with no reads in any library (I:416-421)
+  int64_t allzero_begin, n_allzero; // genes with no reads in any library (I:416-421) occupy the last n_allzero slots
   const uint64_t *nd_mask; const double *xbar, *xss;  // per-gene data statistics (k_prepare_data)
   const FastH *fasth;               // [C] derived hyper-parameters (k_prepare_hyper)
   double *partials;                 // [C][rows][nstat] per-block sufficient statistics (rows = main blocks + spike blocks)
@@ -160,6 +162,63 @@ __global__ void __launch_bounds__(BLOCK) k_prepare_data(int64_t G, int R, const 
 // One table/hyper load and one barrier per block for the whole sweep; warps never wait for each other afterwards.
 // PROD = true is the production instantiation (Philox draws, no decision export); PROD = false additionally serves the
 // "identical uniforms" test mode (explicit draws) and exports decisions.
+// mhSpikeAllocation (Pr:528-638) for one all-zero, inactive gene; its likelihood needs no Xg (every library is -Inf).
+// Works on the gene's global-memory state (after the main moves stored it) and returns what the statistics need.  Out of
+// line: only the warps that own all-zero genes (the last slots of the sorted gene order) ever call it.
+struct SpikeOut { double y, lv, xglik, vgprob; uint32_t f; int acc; bool finite_state; };
+
+template <int RT>
+__device__ __noinline__ void spike_move(const FastH &H, const MathTabs &T, const FastArgs &fa, int chain, int64_t g, int64_t i, SpikeOut &o) {
+  const SweepArgs &a = fa.s;
+  uint32_t f = a.flags[i];
+  double y = a.Yg[i], v = a.vg[i], xglik = a.xglik[i], vgprob = a.vgprob[i];
+  int acc_s = 0;
+  if (!(f & F_ACTIVE)) {                                              // Pr:533: all-zero AND inactive
+    const bool cur_in = (f & F_INSPIKE) != 0, prop_in = !cur_in;      // Pr:535
+    double zy, zv, u;
+    if (a.draws[6]) { zy = a.draws[6][i]; zv = a.draws[7][i]; u = a.draws[8][i]; }
+    else {
+      uint32_t b2[4];
+      philox_block(a.seed, chain, a.step, 2, (uint64_t)(a.gene_offset + a.perm[g]), b2);
+      box_muller(u32_open(b2[0]), u32_open(b2[1]), zy, zv); u = u32_open(b2[2]);
+    }
+    const double yp = fma(H.sd_i, zy, H.im);                          // Pr:545
+    const double lsp = fma(H.s1, yp, H.s0);                           // log(Sg_proposed), Pr:547
+    const double lvp = (lsp + H.tau) + H.rtau * zv;                   // Pr:549: variance_g' = exp(.)
+    const double vp = fexp(lvp, T.exp_t);
+    double PVp = vg_prior_from_q(H, lvp, vg_q(H, lvp, yp));           // Pr:556
+    const double lv = flog(v, T.log_t);
+    double PVc = vg_prior_from_q(H, lv, vg_q(H, lv, y));              // Pr:558
+    if (H.vub != INFINITY) { PVp -= plnorm_term(H, yp); PVc -= plnorm_term(H, y); }
+    const double dp = yp - H.im, dc = y - H.im;
+    const double pygp = prop_in ? H.log_sp : H.log_1msp - H.log_norm_i - dp * dp * H.inv2iv;   // Pr:560
+    const double pyg = cur_in ? H.log_sp : H.log_1msp - H.log_norm_i - dc * dc * H.inv2iv;     // Pr:563
+    const double pp = prop_in ? H.log_sp : (pygp + PVp);              // Pr:569-570
+    const double pc = cur_in ? H.log_sp : (pyg + PVc);                // Pr:572-573
+    double Ap = 0;
+    if (!prop_in) Ap = detect_logsum<RT>(H, T, ~0ull, a.gl[g] * fexp(yp, T.exp_t));
+    double Lp = prop_in ? H.beta * 0.0 : H.beta * Ap;                 // Pr:579 (P:117 gives log(1*1) = 0 in the spike)
+    double Lc = xglik;                                                // Pr:581
+    if (Lp == -INFINITY && Lc == -INFINITY) { Lp = 0; Lc = 0; }       // Pr:583-585
+    const double HR = prop_in ? (pyg - H.log_1msp + PVc) : -(pygp - H.log_1msp + PVp);   // Pr:592-595
+    double ratio = H.temp * (Lp - Lc + pp - pc) + HR;                 // Pr:601
+    if (vp > H.vub) ratio = -INFINITY;                                // Pr:603
+    acc_s = (flog_core(u, T.log_t) < ratio);                          // Pr:605
+    if (isnan(ratio)) atomicOr(a.nan_flag, 1);
+    if (acc_s) f ^= F_INSPIKE;                                        // Pr:616
+    a.flags[i] = (uint16_t)f;
+    if (!prop_in) {                                                   // [proposed_out_spike_idx], Pr:620-636
+      if (acc_s) { y = yp; v = vp; a.Yg[i] = yp; a.vg[i] = vp; fa.lps[i] = Ap; }
+      vgprob = acc_s ? PVp : PVc;
+      a.vgprob[i] = vgprob;
+    }
+    xglik = acc_s ? Lp : Lc;                                          // Pr:630-632
+    a.xglik[i] = xglik;
+  }
+  o.y = y; o.lv = (f & F_INSPIKE) ? 0.0 : flog(v, T.log_t); o.xglik = xglik; o.vgprob = vgprob; o.f = f; o.acc = acc_s;
+  o.finite_state = isfinite(y) && isfinite(v);
+}
+
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 template <int RT, bool PROD>
@@ -177,11 +236,15 @@ __global__ void __launch_bounds__(BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const FastA
   const int64_t ntiles = (n + 31) / 32;
   const int64_t warp0 = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * (BLOCK / 32);
   bool saw_nan = false;
-  for (int64_t tile = warp0; tile < ntiles; tile += nwarps) {
+  // Tiles are taken from the END of the sorted gene order first: the all-zero genes (extra spike move) and the weakly
+  // expressed genes (full detection loop) run while every warp is busy; the last, partially filled round consists of
+  // highly expressed tiles whose detection term is saturated, which keeps the tail short.
+  for (int64_t t_ = warp0; t_ < ntiles; t_ += nwarps) {
+    const int64_t tile = ntiles - 1 - t_;
     const int64_t g = a.g_begin + tile * 32 + lane;
     {   // pull the next tile's inputs towards L1 while this tile computes (no registers, no shared memory)
-      const int64_t gn_ = g + nwarps * 32;
-      if (gn_ < a.g_end) {
+      const int64_t gn_ = g - nwarps * 32;
+      if (gn_ >= a.g_begin && gn_ < a.g_end) {
         const int64_t in_ = (int64_t)chain * a.G + gn_;
         prefetch_l1(a.Yg + in_); prefetch_l1(a.vg + in_); prefetch_l1(fa.lps + in_); prefetch_l1(a.ty + in_); prefetch_l1(a.tv + in_);
         prefetch_l1(fa.nd_mask + gn_); prefetch_l1(fa.xbar + gn_); prefetch_l1(fa.xss + gn_); prefetch_l1(a.gl + gn_);
@@ -190,7 +253,7 @@ __global__ void __launch_bounds__(BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const FastA
     }
     if (g >= a.g_end) continue;
     const int64_t i = (int64_t)chain * a.G + g;
-    const uint64_t gid = (uint64_t)(a.gene_offset + g);
+    const uint64_t gid = (uint64_t)(a.gene_offset + a.perm[g]);
     FastGene gn;
     gn.y = a.Yg[i]; gn.v = a.vg[i]; gn.A = fa.lps[i]; gn.f = a.flags[i];
     GeneData gd;
@@ -207,11 +270,14 @@ __global__ void __launch_bounds__(BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const FastA
     if (live) { gn.lv = flog(gn.v, T.log_t); gn.rv = 1.0 / gn.v; }
     if (a.moves & ZZ_MOVE_YG) {
       int acc_y = 0;
+      double z, u, ratio;
+      if (own_draws) { z = normal_cos(u32_to_open01(b0[0]), u32_to_open01(b0[1]), T); u = u32_to_open01(b0[2]); }
+      else { z = a.draws[0][i]; u = a.draws[1][i]; }
+      const double yp = gn.y + (live ? a.ty[i] : 0.0) * z;               // Pr:257
+      const double tp = gl * fexp(yp, T.exp_t);                         // U:157
+      const bool saturated = __all_sync(__activemask(), !live || tp * H.alpha_min >= 37.5);
       if (live) {
-        double z, u, ratio;
-        if (own_draws) { z = normal_cos(u32_to_open01(b0[0]), u32_to_open01(b0[1]), T); u = u32_to_open01(b0[2]); }
-        else { z = a.draws[0][i]; u = a.draws[1][i]; }
-        acc_y = fast_yg<RT>(H, T, gn, gd, gl, a.ty[i], z, u, ratio);
+        acc_y = fast_yg<RT>(H, T, gn, gd, yp, tp, saturated, u, ratio);
         saw_nan |= isnan(ratio);
         if (a.tune) { ulonglong2 w = a.win_y[i]; window_push(w, acc_y); a.win_y[i] = w; }   // Pr:312-322
       }
@@ -246,89 +312,21 @@ __global__ void __launch_bounds__(BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const FastA
       a.xglik[i] = xglik; a.vgprob[i] = vgprob;
     } else {
       xglik = H.beta * ((gn.f & F_ALLZERO) ? 0.0 : -INFINITY);            // P:117
+      if (fa.want_stats && (gn.f & F_ALLZERO)) xglik = a.xglik[i];       // the cache as the last spike move left it (Pr:583-585, 630-632)
     }
-    // all-zero genes are accounted for by k_spike_fast, after their spike move
-    if (fa.want_stats) stats_add<BLOCK>(acc, a.K, !(gn.f & F_ALLZERO), gn.y, gn.lv, gn.f, xglik, vgprob, isfinite(gn.y) && isfinite(gn.v));
+    bool finite_state = isfinite(gn.y) && isfinite(gn.v);
+    if ((gn.f & F_ALLZERO) && fa.do_spike_move) {     // the last slots of the sorted gene order: whole warps take this branch
+      SpikeOut so;
+      spike_move<RT>(H, T, fa, chain, g, i, so);
+      gn.y = so.y; gn.lv = so.lv; gn.f = so.f; xglik = so.xglik; vgprob = so.vgprob; finite_state = so.finite_state;
+      if (!PROD && a.dec[3]) a.dec[3][i] = (uint8_t)so.acc;
+    }
+    if (fa.want_stats) stats_add<BLOCK>(acc, a.K, true, gn.y, gn.lv, gn.f, xglik, vgprob, finite_state);
   }
   if (saw_nan) atomicOr(a.nan_flag, 1);
   if (fa.want_stats) {
     __syncthreads();
     stats_flush<BLOCK>(acc, nstat, fa.partials + ((int64_t)chain * fa.rows_per_chain + blockIdx.x) * nstat, red);
-  }
-}
-
-// mhSpikeAllocation (Pr:528-638) over the static list of all-zero genes; their likelihood needs no Xg (every library is -Inf).
-// Also emits the sufficient statistics of every all-zero gene (after the move), one partials row per block.
-template <int RT>
-__global__ void __launch_bounds__(BLOCK) k_spike_fast(const FastArgs fa) {
-  __shared__ FastH H;
-  __shared__ MathTabs T;
-  __shared__ double red[BLOCK / 32];
-  extern __shared__ double acc[];
-  const SweepArgs &a = fa.s;
-  const int chain = blockIdx.y;
-  const int nstat = 3 * (a.K + 1) + NSTAT_FIXED_;
-  if (fa.want_stats) for (int s = 0; s < nstat; ++s) acc[s * BLOCK + threadIdx.x] = 0.0;
-  load_fast(H, T, fa.fasth + chain, fa.exp_tab, fa.log_tab);
-  const int64_t j = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-  const int64_t g = j < fa.n_allzero ? fa.allzero_idx[j] : -1;
-  const bool valid = g >= a.g_begin && g < a.g_end;
-  if (valid) {
-    const int64_t i = (int64_t)chain * a.G + g;
-    uint32_t f = a.flags[i];
-    double y = a.Yg[i], v = a.vg[i], xglik = a.xglik[i], vgprob = a.vgprob[i];
-    int acc_s = 0;
-    if (fa.do_spike_move && !(f & F_ACTIVE)) {                          // Pr:533: all-zero AND inactive
-      const bool cur_in = (f & F_INSPIKE) != 0, prop_in = !cur_in;      // Pr:535
-      double zy, zv, u;
-      if (a.draws[6]) { zy = a.draws[6][i]; zv = a.draws[7][i]; u = a.draws[8][i]; }
-      else {
-        uint32_t b2[4];
-        philox_block(a.seed, chain, a.step, 2, (uint64_t)(a.gene_offset + g), b2);
-        box_muller(u32_open(b2[0]), u32_open(b2[1]), zy, zv); u = u32_open(b2[2]);
-      }
-      const double yp = fma(H.sd_i, zy, H.im);                          // Pr:545
-      const double lsp = fma(H.s1, yp, H.s0);                           // log(Sg_proposed), Pr:547
-      const double lvp = (lsp + H.tau) + H.rtau * zv;                   // Pr:549: variance_g' = exp(.)
-      const double vp = fexp(lvp, T.exp_t);
-      double PVp = vg_prior_from_q(H, lvp, vg_q(H, lvp, yp));           // Pr:556
-      const double lv = flog(v, T.log_t);
-      double PVc = vg_prior_from_q(H, lv, vg_q(H, lv, y));              // Pr:558
-      if (H.vub != INFINITY) { PVp -= plnorm_term(H, yp); PVc -= plnorm_term(H, y); }
-      const double dp = yp - H.im, dc = y - H.im;
-      const double pygp = prop_in ? H.log_sp : H.log_1msp - H.log_norm_i - dp * dp * H.inv2iv;   // Pr:560
-      const double pyg = cur_in ? H.log_sp : H.log_1msp - H.log_norm_i - dc * dc * H.inv2iv;     // Pr:563
-      const double pp = prop_in ? H.log_sp : (pygp + PVp);              // Pr:569-570
-      const double pc = cur_in ? H.log_sp : (pyg + PVc);                // Pr:572-573
-      double Ap = 0;
-      if (!prop_in) Ap = detect_logsum<RT>(H, T, ~0ull, a.gl[g] * fexp(yp, T.exp_t));
-      double Lp = prop_in ? H.beta * 0.0 : H.beta * Ap;                 // Pr:579 (P:117 gives log(1*1) = 0 in the spike)
-      double Lc = xglik;                                                // Pr:581
-      if (Lp == -INFINITY && Lc == -INFINITY) { Lp = 0; Lc = 0; }       // Pr:583-585
-      const double HR = prop_in ? (pyg - H.log_1msp + PVc) : -(pygp - H.log_1msp + PVp);   // Pr:592-595
-      double ratio = H.temp * (Lp - Lc + pp - pc) + HR;                 // Pr:601
-      if (vp > H.vub) ratio = -INFINITY;                                // Pr:603
-      acc_s = (flog_core(u, T.log_t) < ratio);                          // Pr:605
-      if (isnan(ratio)) atomicOr(a.nan_flag, 1);
-      if (acc_s) f ^= F_INSPIKE;                                        // Pr:616
-      a.flags[i] = (uint16_t)f;
-      if (!prop_in) {                                                   // [proposed_out_spike_idx], Pr:620-636
-        if (acc_s) { y = yp; v = vp; a.Yg[i] = yp; a.vg[i] = vp; fa.lps[i] = Ap; }
-        vgprob = acc_s ? PVp : PVc;
-        a.vgprob[i] = vgprob;
-      }
-      xglik = acc_s ? Lp : Lc;                                          // Pr:630-632
-      a.xglik[i] = xglik;
-    }
-    if (a.dec[3]) a.dec[3][i] = (uint8_t)acc_s;
-    if (fa.want_stats) {
-      const double lv = (f & F_INSPIKE) ? 0.0 : flog(v, T.log_t);
-      stats_add<BLOCK>(acc, a.K, true, y, lv, f, xglik, vgprob, isfinite(y) && isfinite(v));
-    }
-  }
-  if (fa.want_stats) {
-    __syncthreads();
-    stats_flush<BLOCK>(acc, nstat, fa.partials + ((int64_t)chain * fa.rows_per_chain + fa.spike_row0 + blockIdx.x) * nstat, red);
   }
 }
 
@@ -348,12 +346,12 @@ __global__ void __launch_bounds__(BLOCK) k_refresh_lps(const FastArgs fa) {
 }
 
 // exports the Philox draws of one move slot in the layout of that move's `draws` argument
-__global__ void __launch_bounds__(BLOCK) k_draws(int64_t G, int64_t gene_offset, int C, uint64_t seed, uint64_t step, int slot, double *out) {
+__global__ void __launch_bounds__(BLOCK) k_draws(int64_t G, int64_t gene_offset, const int32_t *perm, int C, uint64_t seed, uint64_t step, int slot, double *out) {
   const int chain = blockIdx.y;
   const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (g >= G) return;
   const int64_t i = (int64_t)chain * G + g, CG = (int64_t)C * G;
-  const uint64_t gid = (uint64_t)(gene_offset + g);
+  const uint64_t gid = (uint64_t)(gene_offset + perm[g]);
   uint32_t b0[4], b1[4], b2[4];
   double z0, z1;
   switch (slot) {
@@ -474,19 +472,6 @@ __global__ void __launch_bounds__(BLOCK) k_reduce_final(const double *partials, 
   }
 }
 
-// first level of the sweep-statistics reduction: chunk b of the rows [C][nrows][nval] -> out [C][nchunks][nval]
-__global__ void __launch_bounds__(BLOCK) k_reduce_rows(const double *partials, int64_t nrows, int nval, double *out) {
-  __shared__ double red[BLOCK / 32];
-  const int chain = blockIdx.y, nchunks = gridDim.x;
-  const int64_t per = (nrows + nchunks - 1) / nchunks, r0 = (int64_t)blockIdx.x * per, r1 = r0 + per < nrows ? r0 + per : nrows;
-  for (int s = 0; s < nval; ++s) {
-    double v = 0;
-    for (int64_t r = r0 + threadIdx.x; r < r1; r += BLOCK) v += partials[((int64_t)chain * nrows + r) * nval + s];
-    const double t = block_sum<BLOCK>(v, red);
-    if (threadIdx.x == 0) out[((int64_t)chain * nchunks + blockIdx.x) * nval + s] = t;
-  }
-}
-
 constexpr int NSTAT_FIXED = 10;
 constexpr int MAX_NSTAT = 3 * (ZZ_MAX_COMP + 1) + NSTAT_FIXED;
 
@@ -591,23 +576,40 @@ __global__ void __launch_bounds__(BLOCK) k_window_sums(int64_t n, const ulonglon
   sy[i] = window_sum(win_y[i]); sv[i] = window_sum(win_v[i]);
 }
 
-// int32 R-style allocation vectors <-> packed flag word
-__global__ void __launch_bounds__(BLOCK) k_pack_flags(int64_t n, const int32_t *ai, const int32_t *within, const int32_t *spike, uint16_t *flags) {
+
+// dst[p][j] = src[p][perm[j]]  (caller order -> device order) and its inverse; grid.y = plane
+template <class T>
+__global__ void __launch_bounds__(BLOCK) k_gather(int64_t n, const int32_t *__restrict__ perm, const T *__restrict__ src, T *__restrict__ dst) {
+  const int64_t j = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (j < n) dst[(int64_t)blockIdx.y * n + j] = src[(int64_t)blockIdx.y * n + perm[j]];
+}
+template <class T>
+__global__ void __launch_bounds__(BLOCK) k_scatter(int64_t n, const int32_t *__restrict__ perm, const T *__restrict__ src, T *__restrict__ dst) {
+  const int64_t j = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (j < n) dst[(int64_t)blockIdx.y * n + perm[j]] = src[(int64_t)blockIdx.y * n + j];
+}
+
+// int32 R-style allocation vectors (caller order) <-> packed flag word (device order)
+__global__ void __launch_bounds__(BLOCK) k_pack_flags(int64_t n, const int32_t *perm, const int32_t *ai, const int32_t *within, const int32_t *spike,
+                                                       const int32_t *pinned, uint16_t *flags) {
   const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (i >= n) return;
+  const int32_t o = perm[i];
   uint32_t f = flags[i];
-  if (ai) f = (f & ~F_ACTIVE) | (ai[i] ? F_ACTIVE : 0u);
-  if (within) f = flag_set_k(f, within[i] < 1 ? 1 : within[i]);
-  if (spike) f = (f & ~F_INSPIKE) | (spike[i] ? F_INSPIKE : 0u);
+  if (ai) f = (f & ~F_ACTIVE) | (ai[o] ? F_ACTIVE : 0u);
+  if (within) f = flag_set_k(f, within[o] < 1 ? 1 : within[o]);
+  if (spike) f = (f & ~F_INSPIKE) | (spike[o] ? F_INSPIKE : 0u);
+  if (pinned) f = (f & ~F_PINNED) | (pinned[o] ? F_PINNED : 0u);
   flags[i] = (uint16_t)f;
 }
-__global__ void __launch_bounds__(BLOCK) k_unpack_flags(int64_t n, const uint16_t *flags, int32_t *ai, int32_t *within, int32_t *spike) {
+__global__ void __launch_bounds__(BLOCK) k_unpack_flags(int64_t n, const int32_t *perm, const uint16_t *flags, int32_t *ai, int32_t *within, int32_t *spike) {
   const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (i >= n) return;
+  const int32_t o = perm[i];
   const uint32_t f = flags[i];
-  if (ai) ai[i] = (f & F_ACTIVE) ? 1 : 0;
-  if (within) within[i] = flag_k(f);
-  if (spike) spike[i] = (f & F_INSPIKE) ? 1 : 0;
+  if (ai) ai[o] = (f & F_ACTIVE) ? 1 : 0;
+  if (within) within[o] = flag_k(f);
+  if (spike) spike[o] = (f & F_INSPIKE) ? 1 : 0;
 }
 
 }  // namespace
@@ -631,7 +633,9 @@ struct zz_handle {
   int32_t *iscratch;                       // 3*C*G
   int *nan_flag;
   bool have_data;
-  double *lps; double *exp_tab; double2 *log_tab; int32_t *allzero_idx; int64_t n_allzero;
+  double *lps; double *exp_tab; double2 *log_tab; int64_t n_allzero;
+  int32_t *perm; std::vector<int32_t> perm_h;   // device slot -> caller's gene index (expression-sorted, all-zero genes last)
+  double *stage;                           // staging for permuted transfers, same size as scratch
   uint64_t *nd_mask; double *xbar, *xss;   // per-gene data statistics (k_prepare_data)
   FastH *fasth; bool fasth_valid;           // derived hyper-parameters of the production kernels
   unsigned *tile_counter; unsigned tile_base; int persist_blocks;
@@ -681,12 +685,31 @@ template <class T> int down(zz_handle *h, T *dst, const T *src, int64_t n) {
   return ZZ_OK;
 }
 
+// per-gene arrays cross the ABI in the caller's gene order and live on the device in sorted order
+template <class T> int up_g(zz_handle *h, T *dst, const T *src, int64_t n, int planes = 1) {
+  if (!src) return ZZ_OK;
+  T *st = reinterpret_cast<T *>(h->stage);
+  ZZ_CUDA(h, cudaMemcpyAsync(st, src, sizeof(T) * n * planes, cudaMemcpyHostToDevice, h->stream));
+  k_gather<T><<<dim3((unsigned)((n + BLOCK - 1) / BLOCK), (unsigned)planes), BLOCK, 0, h->stream>>>(n, h->perm, st, dst);
+  ZZ_LAUNCHED(h);
+  return ZZ_OK;
+}
+template <class T> int down_g(zz_handle *h, T *dst, const T *src, int64_t n, int planes = 1, bool sync = true) {
+  if (!dst) return ZZ_OK;
+  T *st = reinterpret_cast<T *>(h->stage);
+  k_scatter<T><<<dim3((unsigned)((n + BLOCK - 1) / BLOCK), (unsigned)planes), BLOCK, 0, h->stream>>>(n, h->perm, src, st);
+  ZZ_LAUNCHED(h);
+  ZZ_CUDA(h, cudaMemcpyAsync(dst, st, sizeof(T) * n * planes, cudaMemcpyDeviceToHost, h->stream));
+  if (sync) ZZ_CUDA(h, cudaStreamSynchronize(h->stream));   // the caller reads `dst` on return (stream order protects the staging buffer)
+  return ZZ_OK;
+}
+
 void fill_sweep_args(zz_handle *h, SweepArgs &a, uint64_t step, int tune, uint32_t moves, const double *const draws_dev[9],
                      uint8_t *const dec_dev[4], int64_t g_begin, int64_t g_end) {
   a.G = h->G; a.g_begin = g_begin; a.g_end = g_end; a.gene_offset = h->cfg.gene_offset;
   a.C = h->C; a.R = h->R; a.K = h->K; a.tune = tune; a.moves = moves; a.seed = h->cfg.seed; a.step = step;
   a.Xg = h->Xg; a.gl = h->gl; a.Yg = h->Yg; a.vg = h->vg; a.xglik = h->xglik; a.vgprob = h->vgprob; a.ty = h->ty; a.tv = h->tv;
-  a.flags = h->flags; a.win_y = h->win_y; a.win_v = h->win_v; a.hyper = h->hyper;
+  a.flags = h->flags; a.win_y = h->win_y; a.win_v = h->win_v; a.hyper = h->hyper; a.perm = h->perm;
   for (int i = 0; i < 9; ++i) a.draws[i] = draws_dev ? draws_dev[i] : nullptr;
   for (int i = 0; i < 4; ++i) a.dec[i] = dec_dev ? dec_dev[i] : nullptr;
   a.nan_flag = h->nan_flag;
@@ -717,7 +740,7 @@ int launch_sweep(zz_handle *h, uint64_t step, int tune, uint32_t moves, const do
   } while (0)
 
 void fill_fast_args(zz_handle *h, FastArgs &fa) {
-  fa.lps = h->lps; fa.exp_tab = h->exp_tab; fa.log_tab = h->log_tab; fa.allzero_idx = h->allzero_idx; fa.n_allzero = h->n_allzero;
+  fa.lps = h->lps; fa.exp_tab = h->exp_tab; fa.log_tab = h->log_tab; fa.allzero_begin = h->G - h->n_allzero; fa.n_allzero = h->n_allzero;
   fa.nd_mask = h->nd_mask; fa.xbar = h->xbar; fa.xss = h->xss; fa.fasth = h->fasth;
   fa.partials = h->sw_partials; fa.rows_per_chain = 0; fa.spike_row0 = 0; fa.want_stats = 0; fa.do_spike_move = 0;
 }
@@ -767,7 +790,6 @@ int ensure_lps(zz_handle *h) {
 template <int RT> void allow_big_smem(int bytes) {
   cudaFuncSetAttribute(k_sweep_fast<RT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   cudaFuncSetAttribute(k_sweep_fast<RT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  cudaFuncSetAttribute(k_spike_fast<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 int persistent_blocks(zz_handle *h, size_t smem) {
@@ -809,30 +831,19 @@ int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, con
   const int nstat = zz_suffstats_len(h->K);
   const size_t smem = full ? sizeof(double) * nstat * BLOCK : 0;
   const int64_t ntiles = (g_end - g_begin + 31) / 32;
-  const int64_t spike_blocks = h->n_allzero > 0 ? (h->n_allzero + BLOCK - 1) / BLOCK : 0;
   int64_t per_chain = (persistent_blocks(h, sizeof(double) * nstat * BLOCK) + h->C - 1) / h->C;
   const int64_t need = (ntiles + BLOCK / 32 - 1) / (BLOCK / 32);
   if (per_chain > need) per_chain = need;
   if (per_chain < 1) per_chain = 1;
   fa.want_stats = full ? 1 : 0;
-  fa.rows_per_chain = per_chain + spike_blocks;
+  fa.rows_per_chain = per_chain;
   fa.spike_row0 = per_chain;
   fa.do_spike_move = (moves & ZZ_MOVE_SPIKE) ? 1 : 0;
   h->stats_fresh = false;
-  const bool prod = !draws_dev[0] && !draws_dev[2] && !draws_dev[4] && !dec_dev[0] && !dec_dev[1] && !dec_dev[2];
+  const bool prod = !draws_dev[0] && !draws_dev[2] && !draws_dev[4] && !draws_dev[6] && !dec_dev[0] && !dec_dev[1] && !dec_dev[2] && !dec_dev[3];
+  if (dec_dev[3] && (moves & ZZ_MOVE_SPIKE)) ZZ_CUDA(h, cudaMemsetAsync(dec_dev[3], 0, (size_t)h->C * h->G, h->stream));
   ZZ_DISPATCH_SWEEP(h, prod, dim3((unsigned)per_chain, (unsigned)h->C), smem, fa);
   ZZ_LAUNCHED(h);
-  if (dec_dev[3] && (moves & ZZ_MOVE_SPIKE)) ZZ_CUDA(h, cudaMemsetAsync(dec_dev[3], 0, (size_t)h->C * h->G, h->stream));
-  if (spike_blocks > 0 && (fa.do_spike_move || fa.want_stats)) {
-    switch (h->R) {
-      case 2: k_spike_fast<2><<<dim3((unsigned)spike_blocks, (unsigned)h->C), BLOCK, smem, h->stream>>>(fa); break;
-      case 4: k_spike_fast<4><<<dim3((unsigned)spike_blocks, (unsigned)h->C), BLOCK, smem, h->stream>>>(fa); break;
-      case 8: k_spike_fast<8><<<dim3((unsigned)spike_blocks, (unsigned)h->C), BLOCK, smem, h->stream>>>(fa); break;
-      case 16: k_spike_fast<16><<<dim3((unsigned)spike_blocks, (unsigned)h->C), BLOCK, smem, h->stream>>>(fa); break;
-      default: k_spike_fast<0><<<dim3((unsigned)spike_blocks, (unsigned)h->C), BLOCK, smem, h->stream>>>(fa); break;
-    }
-    ZZ_LAUNCHED(h);
-  }
   if (full) { h->stats_fresh = true; h->sw_rows = fa.rows_per_chain; }
   return ZZ_OK;
 }
@@ -846,7 +857,7 @@ int run_moves(zz_handle *h, uint64_t step, int tune, uint32_t moves, const doubl
   const double *dd[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint8_t *de[4] = {nullptr, nullptr, nullptr, nullptr};
   if (draws) {
-    ZZ_CUDA(h, cudaMemcpyAsync(h->scratch, draws, sizeof(double) * ndraw * CG, cudaMemcpyHostToDevice, h->stream));
+    if (int rc = up_g(h, h->scratch, draws, h->G, ndraw * h->C)) return rc;
     for (int j = 0; j < ndraw; ++j) dd[draw_slots[j]] = h->scratch + (int64_t)j * CG;
   }
   if (decisions) for (int j = 0; j < ndec; ++j) de[dec_slots[j]] = h->dec + (int64_t)j * CG;
@@ -855,8 +866,7 @@ int run_moves(zz_handle *h, uint64_t step, int tune, uint32_t moves, const doubl
                            : launch_sweep_fast(h, step, tune, moves, dd, de, 0, h->G);
   if (rc) return rc;
   if (decisions) {
-    ZZ_CUDA(h, cudaMemcpyAsync(decisions, h->dec, (size_t)ndec * CG, cudaMemcpyDeviceToHost, h->stream));
-    ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (int rc2 = down_g(h, decisions, h->dec, h->G, ndec * h->C)) return rc2;
   } else if (draws) {
     ZZ_CUDA(h, cudaStreamSynchronize(h->stream));  // the caller may free `draws` on return
   }
@@ -900,9 +910,7 @@ int eval_to_host(zz_handle *h, int which, int chain, double *out) {
   if (int rc = chain_ok(h, chain)) return rc;
   if (!out) return fail(h, ZZ_ERR_INVALID, "out is NULL");
   if (int rc = launch_eval(h, which, chain, h->scratch, nullptr)) return rc;
-  ZZ_CUDA(h, cudaMemcpyAsync(out, h->scratch, sizeof(double) * h->G, cudaMemcpyDeviceToHost, h->stream));
-  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
-  return ZZ_OK;
+  return down_g(h, out, h->scratch, h->G);
 }
 
 }  // namespace
@@ -957,7 +965,11 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   ZZ_CUDA(h, cudaMalloc(&h->log_tab, sizeof(kLogTab)));
   ZZ_CUDA(h, cudaMemcpyAsync(h->exp_tab, kExpTab, sizeof(kExpTab), cudaMemcpyHostToDevice, h->stream));
   ZZ_CUDA(h, cudaMemcpyAsync(h->log_tab, kLogTab, sizeof(kLogTab), cudaMemcpyHostToDevice, h->stream));
-  ZZ_CUDA(h, cudaMalloc(&h->allzero_idx, sizeof(int32_t) * G));
+  ZZ_CUDA(h, cudaMalloc(&h->perm, sizeof(int32_t) * G));
+  ZZ_CUDA(h, cudaMalloc(&h->stage, sizeof(double) * 9 * CG));
+  h->perm_h.resize(G);
+  for (int64_t g = 0; g < G; ++g) h->perm_h[g] = (int32_t)g;
+  ZZ_CUDA(h, cudaMemcpyAsync(h->perm, h->perm_h.data(), sizeof(int32_t) * G, cudaMemcpyHostToDevice, h->stream));
   h->n_allzero = 0; h->lps_valid = false; h->stats_fresh = false; h->tile_base = 0; h->persist_blocks = 0; h->sw_rows = 0;
   ZZ_CUDA(h, cudaMalloc(&h->fasth, sizeof(FastH) * h->C));
   h->fasth_valid = false;
@@ -986,7 +998,7 @@ void zz_destroy(zz_handle *h) {
   cudaSetDevice(h->cfg.device);
   void *ptrs[] = {h->Xg, h->gl, h->Yg, h->vg, h->xglik, h->vgprob, h->ty, h->tv, h->flags, h->win_y, h->win_v, h->trace,
                   h->hyper, h->partials, h->red_out, h->scratch, h->dec, h->iscratch, h->nan_flag, h->lps, h->exp_tab,
-                  h->log_tab, h->allzero_idx, h->nd_mask, h->xbar, h->xss, h->tile_counter, h->sw_partials, h->sw_partials2, h->fasth};
+                  h->log_tab, h->perm, h->stage, h->nd_mask, h->xbar, h->xss, h->tile_counter, h->sw_partials, h->sw_partials2, h->fasth};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -1014,27 +1026,44 @@ uint64_t zz_launch_count(const zz_handle *h) { return h ? h->launches : 0; }
 int zz_upload_data(zz_handle *h, const double *Xg, const double *gene_lengths) {
   ZZ_CHECK(h);
   if (!Xg || !gene_lengths) return fail(h, ZZ_ERR_INVALID, "Xg / gene_lengths is NULL");
+  if (h->have_data) return fail(h, ZZ_ERR_STATE, "zz_upload_data may be called once per handle (the gene order on the device is fixed by it)");
   const int64_t G = h->G;
-  ZZ_CUDA(h, cudaMemcpyAsync(h->Xg, Xg, sizeof(double) * G * h->R, cudaMemcpyHostToDevice, h->stream));
-  ZZ_CUDA(h, cudaMemcpyAsync(h->gl, gene_lengths, sizeof(double) * G, cudaMemcpyHostToDevice, h->stream));
-  // no_detect_spike (I:416-417): every library -Inf
-  std::vector<uint16_t> f((size_t)h->C * G);
-  std::vector<int32_t> az;
-  ZZ_CUDA(h, cudaMemcpyAsync(f.data(), h->flags, sizeof(uint16_t) * f.size(), cudaMemcpyDeviceToHost, h->stream));
-  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  const int R = h->R;
+  // Device gene order: genes with at least one read sorted by decreasing (mean detected log-expression + log gene length), then the all-zero
+  // genes (no_detect_spike, I:416-417).  Warps therefore hold genes of similar expression: the detection term saturates
+  // (p_x == 1) for whole warps of highly expressed genes, and the spike-allocation candidates are contiguous.
+  std::vector<double> key(G);
+  std::vector<uint8_t> allzero(G);
   for (int64_t g = 0; g < G; ++g) {
-    bool all = true;
-    for (int r = 0; r < h->R && all; ++r) all = (Xg[(int64_t)r * G + g] == -INFINITY);
-    if (all) az.push_back((int32_t)g);
-    for (int c = 0; c < h->C; ++c) {
-      uint16_t &w = f[(size_t)c * G + g];
-      w = (uint16_t)((w & ~F_ALLZERO) | (all ? F_ALLZERO : 0u));
-    }
+    double sum = 0; int n = 0;
+    for (int r = 0; r < R; ++r) { const double x = Xg[(int64_t)r * G + g]; if (x != -INFINITY) { sum += x; n++; } }
+    allzero[g] = (n == 0);
+    key[g] = n ? sum / n + log(gene_lengths[g]) : -INFINITY;   // ~ log(gl * exp(y)): the quantity the detection term saturates in
   }
-  ZZ_CUDA(h, cudaMemcpyAsync(h->flags, f.data(), sizeof(uint16_t) * f.size(), cudaMemcpyHostToDevice, h->stream));
-  h->n_allzero = (int64_t)az.size();
-  if (!az.empty()) ZZ_CUDA(h, cudaMemcpyAsync(h->allzero_idx, az.data(), sizeof(int32_t) * az.size(), cudaMemcpyHostToDevice, h->stream));
-  k_prepare_data<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, h->R, h->Xg, h->nd_mask, h->xbar, h->xss);
+  std::vector<int32_t> &perm = h->perm_h;
+  for (int64_t g = 0; g < G; ++g) perm[g] = (int32_t)g;
+  std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) {
+    if (allzero[a] != allzero[b]) return allzero[a] < allzero[b];
+    return key[a] > key[b];
+  });
+  int64_t naz = 0;
+  for (int64_t g = 0; g < G; ++g) naz += allzero[g];
+  h->n_allzero = naz;
+  ZZ_CUDA(h, cudaMemcpyAsync(h->perm, perm.data(), sizeof(int32_t) * G, cudaMemcpyHostToDevice, h->stream));
+  {
+    std::vector<double> tmp((size_t)G * (R + 1));
+    for (int r = 0; r < R; ++r)
+      for (int64_t j = 0; j < G; ++j) tmp[(size_t)r * G + j] = Xg[(int64_t)r * G + perm[j]];
+    for (int64_t j = 0; j < G; ++j) tmp[(size_t)R * G + j] = gene_lengths[perm[j]];
+    ZZ_CUDA(h, cudaMemcpyAsync(h->Xg, tmp.data(), sizeof(double) * G * R, cudaMemcpyHostToDevice, h->stream));
+    ZZ_CUDA(h, cudaMemcpyAsync(h->gl, tmp.data() + (size_t)R * G, sizeof(double) * G, cudaMemcpyHostToDevice, h->stream));
+    std::vector<uint16_t> f((size_t)h->C * G);
+    for (int c = 0; c < h->C; ++c)
+      for (int64_t j = 0; j < G; ++j) f[(size_t)c * G + j] = allzero[perm[j]] ? (uint16_t)F_ALLZERO : (uint16_t)0;
+    ZZ_CUDA(h, cudaMemcpyAsync(h->flags, f.data(), sizeof(uint16_t) * f.size(), cudaMemcpyHostToDevice, h->stream));
+    ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  k_prepare_data<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, R, h->Xg, h->nd_mask, h->xbar, h->xss);
   ZZ_LAUNCHED(h);
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
   h->have_data = true; h->lps_valid = false; h->stats_fresh = false;
@@ -1050,21 +1079,16 @@ int zz_set_state(zz_handle *h, int chain, const double *Yg, const double *varian
   int rc;
   if (Yg || spike) h->lps_valid = false;
   h->stats_fresh = false;
-  if ((rc = up(h, h->Yg + off, Yg, G)) || (rc = up(h, h->vg + off, variance_g, G)) || (rc = up(h, h->xglik + off, XgLikelihood, G)) ||
-      (rc = up(h, h->vgprob + off, variance_g_probability, G)) || (rc = up(h, h->ty + off, ty, G)) || (rc = up(h, h->tv + off, tv, G)))
+  if (!h->have_data) return fail(h, ZZ_ERR_STATE, "zz_upload_data has not been called");
+  if ((rc = up_g(h, h->Yg + off, Yg, G)) || (rc = up_g(h, h->vg + off, variance_g, G)) || (rc = up_g(h, h->xglik + off, XgLikelihood, G)) ||
+      (rc = up_g(h, h->vgprob + off, variance_g_probability, G)) || (rc = up_g(h, h->ty + off, ty, G)) || (rc = up_g(h, h->tv + off, tv, G)))
     return rc;
-  if (ai || within || spike) {
-    int32_t *d_ai = h->iscratch, *d_w = h->iscratch + G, *d_s = h->iscratch + 2 * G;
-    if ((rc = up(h, d_ai, ai, G)) || (rc = up(h, d_w, within, G)) || (rc = up(h, d_s, spike, G))) return rc;
-    k_pack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, ai ? d_ai : nullptr, within ? d_w : nullptr, spike ? d_s : nullptr, h->flags + off);
+  if (ai || within || spike || pinned_active) {
+    int32_t *d_ai = h->iscratch, *d_w = h->iscratch + G, *d_s = h->iscratch + 2 * G, *d_p = reinterpret_cast<int32_t *>(h->stage);
+    if ((rc = up(h, d_ai, ai, G)) || (rc = up(h, d_w, within, G)) || (rc = up(h, d_s, spike, G)) || (rc = up(h, d_p, pinned_active, G))) return rc;
+    k_pack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, h->perm, ai ? d_ai : nullptr, within ? d_w : nullptr, spike ? d_s : nullptr,
+                                                         pinned_active ? d_p : nullptr, h->flags + off);
     ZZ_LAUNCHED(h);
-  }
-  if (pinned_active) {
-    std::vector<uint16_t> f(G);
-    ZZ_CUDA(h, cudaMemcpyAsync(f.data(), h->flags + off, sizeof(uint16_t) * G, cudaMemcpyDeviceToHost, h->stream));
-    ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
-    for (int64_t g = 0; g < G; ++g) f[g] = (uint16_t)((f[g] & ~F_PINNED) | (pinned_active[g] ? F_PINNED : 0u));
-    ZZ_CUDA(h, cudaMemcpyAsync(h->flags + off, f.data(), sizeof(uint16_t) * G, cudaMemcpyHostToDevice, h->stream));
   }
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
   return ZZ_OK;
@@ -1076,12 +1100,12 @@ int zz_get_state(zz_handle *h, int chain, double *Yg, double *variance_g, int32_
   if (int rc = chain_ok(h, chain)) return rc;
   const int64_t G = h->G, off = (int64_t)chain * G;
   int rc;
-  if ((rc = down(h, Yg, h->Yg + off, G)) || (rc = down(h, variance_g, h->vg + off, G)) || (rc = down(h, XgLikelihood, h->xglik + off, G)) ||
-      (rc = down(h, variance_g_probability, h->vgprob + off, G)) || (rc = down(h, ty, h->ty + off, G)) || (rc = down(h, tv, h->tv + off, G)))
+  if ((rc = down_g(h, Yg, h->Yg + off, G)) || (rc = down_g(h, variance_g, h->vg + off, G)) || (rc = down_g(h, XgLikelihood, h->xglik + off, G)) ||
+      (rc = down_g(h, variance_g_probability, h->vgprob + off, G)) || (rc = down_g(h, ty, h->ty + off, G)) || (rc = down_g(h, tv, h->tv + off, G)))
     return rc;
   if (ai || within || spike) {
     int32_t *d_ai = h->iscratch, *d_w = h->iscratch + G, *d_s = h->iscratch + 2 * G;
-    k_unpack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, h->flags + off, d_ai, d_w, d_s);
+    k_unpack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, h->perm, h->flags + off, d_ai, d_w, d_s);
     ZZ_LAUNCHED(h);
     if ((rc = down(h, ai, d_ai, G)) || (rc = down(h, within, d_w, G)) || (rc = down(h, spike, d_s, G))) return rc;
   }
@@ -1134,8 +1158,7 @@ int zz_get_window_sums(zz_handle *h, int chain, int32_t *yg_sum, int32_t *vg_sum
   k_window_sums<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, h->win_y + off, h->win_v + off, h->iscratch, h->iscratch + G);
   ZZ_LAUNCHED(h);
   int rc;
-  if ((rc = down(h, yg_sum, h->iscratch, G)) || (rc = down(h, vg_sum, h->iscratch + G, G))) return rc;
-  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  if ((rc = down_g(h, yg_sum, h->iscratch, G)) || (rc = down_g(h, vg_sum, h->iscratch + G, G))) return rc;
   return ZZ_OK;
 }
 
@@ -1180,11 +1203,10 @@ int zz_philox_draws(zz_handle *h, uint64_t step, int slot, double *out) {
   }
   if (!out) return fail(h, ZZ_ERR_INVALID, "out is NULL");
   const int64_t CG = (int64_t)h->C * h->G;
-  k_draws<<<gene_grid(h, h->G, h->C), BLOCK, 0, h->stream>>>(h->G, h->cfg.gene_offset, h->C, h->cfg.seed, step, slot, h->scratch);
+  k_draws<<<gene_grid(h, h->G, h->C), BLOCK, 0, h->stream>>>(h->G, h->cfg.gene_offset, h->perm, h->C, h->cfg.seed, step, slot, h->scratch);
   ZZ_LAUNCHED(h);
-  ZZ_CUDA(h, cudaMemcpyAsync(out, h->scratch, sizeof(double) * n * CG, cudaMemcpyDeviceToHost, h->stream));
-  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
-  return ZZ_OK;
+  (void)CG;
+  return down_g(h, out, h->scratch, h->G, n * h->C);
 }
 
 int zz_suffstats_len(int K) { return 3 * (K + 1) + NSTAT_FIXED; }
@@ -1300,9 +1322,8 @@ int zz_get_alloc_trace(zz_handle *h, int chain, uint32_t *out) {
   if (int rc = chain_ok(h, chain)) return rc;
   if (!out) return fail(h, ZZ_ERR_INVALID, "out is NULL");
   const size_t n = (size_t)h->G * (h->K + 1);
-  ZZ_CUDA(h, cudaMemcpyAsync(out, h->trace + (size_t)chain * n, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream));
-  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
-  return ZZ_OK;
+  (void)n;
+  return down_g(h, out, h->trace + (size_t)chain * n, h->G, h->K + 1);
 }
 
 int zz_tune(zz_handle *h, double target) {
@@ -1331,11 +1352,12 @@ int zz_sweep_host(zz_handle *h, uint64_t step, int tune, double *Yg, double *var
   const int64_t G = h->G;
   int32_t *d_ai = h->iscratch, *d_w = h->iscratch + G, *d_s = h->iscratch + 2 * G;
   int rc;
-  if ((rc = up(h, h->Yg, Yg, G)) || (rc = up(h, h->vg, variance_g, G)) || (rc = up(h, h->xglik, XgLikelihood, G)) ||
-      (rc = up(h, h->vgprob, variance_g_probability, G)) || (rc = up(h, h->ty, ty, G)) || (rc = up(h, h->tv, tv, G)) ||
+  if ((rc = up_g(h, h->Yg, (const double *)Yg, G)) || (rc = up_g(h, h->vg, (const double *)variance_g, G)) ||
+      (rc = up_g(h, h->xglik, (const double *)XgLikelihood, G)) || (rc = up_g(h, h->vgprob, (const double *)variance_g_probability, G)) ||
+      (rc = up_g(h, h->ty, ty, G)) || (rc = up_g(h, h->tv, tv, G)) ||
       (rc = up(h, d_ai, (const int32_t *)ai, G)) || (rc = up(h, d_w, (const int32_t *)within, G)) || (rc = up(h, d_s, (const int32_t *)spike, G)))
     return rc;
-  k_pack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, d_ai, d_w, d_s, h->flags);
+  k_pack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, h->perm, d_ai, d_w, d_s, nullptr, h->flags);
   ZZ_LAUNCHED(h);
   h->lps_valid = false;  // Yg arrived from the host: A(y) is rebuilt on the device (one extra pass; PCIe dominates this entry point)
   {
@@ -1343,11 +1365,11 @@ int zz_sweep_host(zz_handle *h, uint64_t step, int tune, double *Yg, double *var
     uint8_t *no_dec[4] = {nullptr, nullptr, nullptr, nullptr};
     if ((rc = launch_sweep_fast(h, step, tune, ZZ_MOVE_FUSED, no_draws, no_dec, 0, G))) return rc;
   }
-  k_unpack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, h->flags, d_ai, d_w, d_s);
+  k_unpack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, h->perm, h->flags, d_ai, d_w, d_s);
   ZZ_LAUNCHED(h);
-  if ((rc = down(h, Yg, h->Yg, G)) || (rc = down(h, variance_g, h->vg, G)) || (rc = down(h, XgLikelihood, h->xglik, G)) ||
-      (rc = down(h, variance_g_probability, h->vgprob, G)) || (rc = down(h, ai, d_ai, G)) || (rc = down(h, within, d_w, G)) ||
-      (rc = down(h, spike, d_s, G)))
+  if ((rc = down_g(h, Yg, h->Yg, G, 1, false)) || (rc = down_g(h, variance_g, h->vg, G, 1, false)) ||
+      (rc = down_g(h, XgLikelihood, h->xglik, G, 1, false)) || (rc = down_g(h, variance_g_probability, h->vgprob, G, 1, false)) ||
+      (rc = down(h, ai, d_ai, G)) || (rc = down(h, within, d_w, G)) || (rc = down(h, spike, d_s, G)))
     return rc;
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
   if (h2d_bytes) *h2d_bytes = G * (6 * 8 + 3 * 4);
