@@ -151,7 +151,7 @@ struct FastGene {
 __device__ __forceinline__ double vg_q(const FastH &H, double lv, double y) { return (lv - fma(H.s1, y, H.s0) - H.tau) * H.irt; }
 __device__ __forceinline__ double vg_prior_from_q(const FastH &H, double lv, double q) { return -(lv + H.c1) - 0.5 * (q * q); }
 
-__device__ __forceinline__ double plnorm_term(const FastH &H, double y) {   // only when variance_g_upper_bound < Inf (P:24-25)
+__device__ __noinline__ double plnorm_term(const FastH &H, double y) {   // only when variance_g_upper_bound < Inf (P:24-25); rare: kept out of line
   return plnorm_log(H.vub, fma(H.s1, y, H.s0) + H.tau, H.rtau);
 }
 

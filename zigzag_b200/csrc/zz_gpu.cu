@@ -25,6 +25,10 @@ using namespace zz;
 namespace {
 
 constexpr int BLOCK = 256;
+#ifndef ZZ_SWEEP_BLOCK
+#define ZZ_SWEEP_BLOCK 256
+#endif
+constexpr int SWEEP_BLOCK = ZZ_SWEEP_BLOCK;   // threads per CTA of the persistent sweep kernel
 constexpr int RED_BLOCKS = 148 * 4;  // persistent-style reduction grid: 4 CTAs per SM
 constexpr int SW_CHUNKS = 64;        // first-level chunks of the sweep-statistics reduction
 
@@ -222,19 +226,19 @@ __device__ __noinline__ void spike_move(const FastH &H, const MathTabs &T, const
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 template <int RT, bool PROD>
-__global__ void __launch_bounds__(BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const FastArgs fa) {
+__global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const FastArgs fa) {
   __shared__ FastH H;
   __shared__ MathTabs T;
-  __shared__ double red[BLOCK / 32];
+  __shared__ double red[SWEEP_BLOCK / 32];
   extern __shared__ double acc[];                     // [nstat][BLOCK] when want_stats
   const SweepArgs &a = fa.s;
   const int chain = blockIdx.y, lane = threadIdx.x & 31;
   const int nstat = 3 * (a.K + 1) + NSTAT_FIXED_;
-  if (fa.want_stats) for (int s = 0; s < nstat; ++s) acc[s * BLOCK + threadIdx.x] = 0.0;
+  if (fa.want_stats) for (int s = 0; s < nstat; ++s) acc[s * SWEEP_BLOCK + threadIdx.x] = 0.0;
   load_fast(H, T, fa.fasth + chain, fa.exp_tab, fa.log_tab);
   const int64_t n = a.g_end - a.g_begin;
   const int64_t ntiles = (n + 31) / 32;
-  const int64_t warp0 = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * (BLOCK / 32);
+  const int64_t warp0 = (int64_t)blockIdx.x * (SWEEP_BLOCK / 32) + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * (SWEEP_BLOCK / 32);
   bool saw_nan = false;
   // Tiles are taken from the END of the sorted gene order first: the all-zero genes (extra spike move) and the weakly
   // expressed genes (full detection loop) run while every warp is busy; the last, partially filled round consists of
@@ -321,12 +325,12 @@ __global__ void __launch_bounds__(BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const FastA
       gn.y = so.y; gn.lv = so.lv; gn.f = so.f; xglik = so.xglik; vgprob = so.vgprob; finite_state = so.finite_state;
       if (!PROD && a.dec[3]) a.dec[3][i] = (uint8_t)so.acc;
     }
-    if (fa.want_stats) stats_add<BLOCK>(acc, a.K, true, gn.y, gn.lv, gn.f, xglik, vgprob, finite_state);
+    if (fa.want_stats) stats_add<SWEEP_BLOCK>(acc, a.K, true, gn.y, gn.lv, gn.f, xglik, vgprob, finite_state);
   }
   if (saw_nan) atomicOr(a.nan_flag, 1);
   if (fa.want_stats) {
     __syncthreads();
-    stats_flush<BLOCK>(acc, nstat, fa.partials + ((int64_t)chain * fa.rows_per_chain + blockIdx.x) * nstat, red);
+    stats_flush<SWEEP_BLOCK>(acc, nstat, fa.partials + ((int64_t)chain * fa.rows_per_chain + blockIdx.x) * nstat, red);
   }
 }
 
@@ -769,19 +773,19 @@ int ensure_lps(zz_handle *h) {
   do {                                                                                           \
     if (prod) {                                                                                  \
       switch ((h)->R) {                                                                          \
-        case 2: k_sweep_fast<2, true><<<grid, BLOCK, smem, (h)->stream>>>(args); break;          \
-        case 4: k_sweep_fast<4, true><<<grid, BLOCK, smem, (h)->stream>>>(args); break;          \
-        case 8: k_sweep_fast<8, true><<<grid, BLOCK, smem, (h)->stream>>>(args); break;          \
-        case 16: k_sweep_fast<16, true><<<grid, BLOCK, smem, (h)->stream>>>(args); break;        \
-        default: k_sweep_fast<0, true><<<grid, BLOCK, smem, (h)->stream>>>(args); break;         \
+        case 2: k_sweep_fast<2, true><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;          \
+        case 4: k_sweep_fast<4, true><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;          \
+        case 8: k_sweep_fast<8, true><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;          \
+        case 16: k_sweep_fast<16, true><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;        \
+        default: k_sweep_fast<0, true><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;         \
       }                                                                                          \
     } else {                                                                                     \
       switch ((h)->R) {                                                                          \
-        case 2: k_sweep_fast<2, false><<<grid, BLOCK, smem, (h)->stream>>>(args); break;         \
-        case 4: k_sweep_fast<4, false><<<grid, BLOCK, smem, (h)->stream>>>(args); break;         \
-        case 8: k_sweep_fast<8, false><<<grid, BLOCK, smem, (h)->stream>>>(args); break;         \
-        case 16: k_sweep_fast<16, false><<<grid, BLOCK, smem, (h)->stream>>>(args); break;       \
-        default: k_sweep_fast<0, false><<<grid, BLOCK, smem, (h)->stream>>>(args); break;        \
+        case 2: k_sweep_fast<2, false><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;         \
+        case 4: k_sweep_fast<4, false><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;         \
+        case 8: k_sweep_fast<8, false><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;         \
+        case 16: k_sweep_fast<16, false><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;       \
+        default: k_sweep_fast<0, false><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;        \
       }                                                                                          \
     }                                                                                            \
   } while (0)
@@ -806,11 +810,11 @@ int persistent_blocks(zz_handle *h, size_t smem) {
     }
   }
   switch (h->R) {
-    case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<2, true>, BLOCK, smem); break;
-    case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<4, true>, BLOCK, smem); break;
-    case 8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<8, true>, BLOCK, smem); break;
-    case 16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<16, true>, BLOCK, smem); break;
-    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<0, true>, BLOCK, smem); break;
+    case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<2, true>, SWEEP_BLOCK, smem); break;
+    case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<4, true>, SWEEP_BLOCK, smem); break;
+    case 8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<8, true>, SWEEP_BLOCK, smem); break;
+    case 16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<16, true>, SWEEP_BLOCK, smem); break;
+    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<0, true>, SWEEP_BLOCK, smem); break;
   }
   if (e != cudaSuccess || per_sm < 1) per_sm = 2;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device) != cudaSuccess || sms < 1) sms = 148;
@@ -829,10 +833,10 @@ int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, con
   fill_fast_args(h, fa);
   const bool full = (g_begin == 0 && g_end == h->G);
   const int nstat = zz_suffstats_len(h->K);
-  const size_t smem = full ? sizeof(double) * nstat * BLOCK : 0;
+  const size_t smem = full ? sizeof(double) * nstat * SWEEP_BLOCK : 0;
   const int64_t ntiles = (g_end - g_begin + 31) / 32;
-  int64_t per_chain = (persistent_blocks(h, sizeof(double) * nstat * BLOCK) + h->C - 1) / h->C;
-  const int64_t need = (ntiles + BLOCK / 32 - 1) / (BLOCK / 32);
+  int64_t per_chain = (persistent_blocks(h, sizeof(double) * nstat * SWEEP_BLOCK) + h->C - 1) / h->C;
+  const int64_t need = (ntiles + SWEEP_BLOCK / 32 - 1) / (SWEEP_BLOCK / 32);
   if (per_chain > need) per_chain = need;
   if (per_chain < 1) per_chain = 1;
   fa.want_stats = full ? 1 : 0;
