@@ -464,15 +464,15 @@ __global__ void __launch_bounds__(BLOCK) k_reduce(const RedArgs a) {
   }
 }
 
-// partials [ny][nblk][nval] -> out [ny][nval], fixed summation order
+// partials [ny][nblk][nval] -> out [ny][nval], fixed summation order: warp w owns values w, w + 8, ...; lane l adds rows
+// l, l + 32, ... then a butterfly — no block barrier, so the whole reduction is one short latency chain
 __global__ void __launch_bounds__(BLOCK) k_reduce_final(const double *partials, int nblk, int nval, double *out) {
-  __shared__ double red[BLOCK / 32];
-  const int y = blockIdx.x;
-  for (int s = 0; s < nval; ++s) {
+  const int y = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int s = w; s < nval; s += BLOCK / 32) {
     double v = 0;
-    for (int b = threadIdx.x; b < nblk; b += BLOCK) v += partials[((int64_t)y * nblk + b) * nval + s];
-    const double t = block_sum<BLOCK>(v, red);
-    if (threadIdx.x == 0) out[(int64_t)y * nval + s] = t;
+    for (int b = lane; b < nblk; b += 32) v += partials[((int64_t)y * nblk + b) * nval + s];
+    v = warp_sum(v);
+    if (lane == 0) out[(int64_t)y * nval + s] = v;
   }
 }
 
