@@ -107,8 +107,9 @@ def cpu_sweep_rate(X, gl, hd, st, sample_genes, steps, warmup, seed=1):
     """Times the oracle's fused sweep (C port of the reference's R arithmetic, OpenMP over genes) on a bounded sample."""
     n = min(sample_genes, X.shape[0])
     sub = {k: v[:n] for k, v in st.items()}
+    from oracle import oracle as _O
+    cores = _O.set_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: ask for every host thread explicitly
     O, ho, s = make_oracle_case(np.asfortranarray(X[:n]), gl[:n], hd, sub)
-    cores = os.cpu_count() or 1
     times = []
     for it in range(warmup + steps):
         d = O.sweep_draws(seed, 0, it, 0, n)

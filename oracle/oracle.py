@@ -115,6 +115,11 @@ def lib(omp=False):
     return _libs[key]
 
 
+def set_threads(n, omp=True):
+    """Thread count of the OpenMP build (returns the count in effect)."""
+    return int(lib(omp).zzo_set_threads(int(n)))
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 

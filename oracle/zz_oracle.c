@@ -11,6 +11,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <float.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #ifdef ZZO_NO_LDOUBLE
 typedef double acc_t;
@@ -21,6 +24,16 @@ typedef long double acc_t; /* R's rowSums()/sum() accumulate in LDOUBLE (R runti
 #define M_LN_SQRT_2PI_ 0.918938533204672741780329736406 /* nmath/dnorm.c constant */
 static const double PI_ = 3.141592653589793238462643383280;
 static inline double sqrt2pi_(void) { return sqrt(2 * PI_); } /* I:126 */
+
+/* threads used by the OpenMP build (torchrun exports OMP_NUM_THREADS=1, the CPU-baseline legs of bench.py override it) */
+int zzo_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n; return 1;
+#endif
+}
 
 /* ------------------------------------------------------------------ building blocks */
 

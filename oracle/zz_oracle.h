@@ -58,6 +58,8 @@ typedef struct zzo_state {
   uint64_t *Yg_trace, *variance_g_trace; /* 100-wide accept windows, 2 x u64 per gene: [2g]=lo,[2g+1]=hi */
 } zzo_state;
 
+int zzo_set_threads(int n);  /* OpenMP build: set / query the thread count (returns the count in effect) */
+
 /* ---- scalar building blocks (one gene) ---- */
 void   zzo_get_px(const zzo_hyper *h, double y, double gl, double *px /*R*/);          /* U:150-159 */
 double zzo_get_sigmax(double s0, double s1, double y);                                 /* U:144-148 */

@@ -134,6 +134,46 @@ def test_fused_sweep_equals_sequential_moves(G, R, seed, K, mode):
     assert np.array_equal(h.window_sums()[1], s.window_sums("variance_g_trace"))
 
 
+VARIANTS = {"upper_bound": dict(variance_g_upper_bound=3.0), "tempered": dict(beta=0.5, temperature=0.7), "prior_only": dict(beta=0.0)}
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_model_switches_that_change_the_arithmetic(variant, mode):
+    """variance_g_upper_bound < Inf (plnorm term + hard reject, P:18-27, Pr:26, Pr:603), the likelihood power beta (P:121-125,
+    beta < 1e-7 => likelihood 0: the prior-recovery recipe of scripts/test_script.R:42-53) and the temperature."""
+    from zigzag_b200 import synth
+    G, R = 3000, 4
+    hd = dict(synth.truth_hyper_dict(R)); hd.update(VARIANTS[variant])
+    X, gl, hd, st = make_case(G, R, 23, hyper=hd)
+    if variant == "upper_bound":
+        st["variance_g"] = np.minimum(st["variance_g"], 3.0)                     # I:468
+    ho, hg = hyper_pair(hd)
+    s = oracle_state(X, gl, st); O.refresh_caches(ho, s)
+    h = gpu_handle(X, gl, hg, s)
+    rel_close(h.eval_xg_loglik(), O.eval_xg_loglik(ho, s), 1e-10, "XgLikelihood")
+    rel_close(h.eval_varg_logprior(), O.eval_varg_logprior(ho, s), 1e-10, "variance_g prior")
+    rejected_by_bound = 0
+    for it in range(4):
+        d = draws_for(G, 9, 300 + it, normal=(0, 6, 7))
+        v_before = s.variance_g.copy()
+        dec_o = O.sweep(ho, s, d, tune=True)
+        dec_g = h.sweep(step=it, tune=True, moves=MODES[mode], draws=d, decisions=True)
+        assert np.array_equal(dec_g[:, 0, :], dec_o), {j: np.where(dec_g[j, 0] != dec_o[j])[0][:5] for j in range(4)}
+        compare_state(h, s)
+        if variant == "upper_bound":
+            sf = np.exp(st["tuningParam_variance_g"] * (d[2] - 0.5))
+            rejected_by_bound += int(((v_before * sf > 3.0) & (s.inactive_spike_allocation == 0)).sum())
+            assert s.variance_g[(v_before <= 3.0)].max() <= 3.0
+    if variant == "upper_bound":
+        assert rejected_by_bound > 0
+    if variant == "prior_only":
+        assert np.all(s.XgLikelihood == 0)
+    st_o, st_g = O.suffstats(ho, s), h.suffstats()[0]
+    fin = np.isfinite(st_o)
+    assert np.allclose(st_g[fin], st_o[fin], rtol=1e-11, atol=1e-9)
+
+
 @pytest.mark.parametrize("moves", [_capi.MOVE_YG, _capi.MOVE_VARIANCE_G, _capi.MOVE_ALLOC, _capi.MOVE_SPIKE,
                                    _capi.MOVE_VARIANCE_G | _capi.MOVE_ALLOC])
 def test_production_kernel_move_subsets(moves):
@@ -410,3 +450,43 @@ def test_full_size_properties_1m_x16():
         dec_o = O.sweep(ho, sub, d)
         assert np.array_equal(decs[t][:, idx], dec_o)
     assert np.allclose(after["Yg"][idx], sub.Yg, rtol=1e-12)
+
+
+def test_committed_golden_vectors():
+    """tests/golden/moves_g512.npz (generated by make_golden_moves.py from the oracle, committed): the GPU reproduces the stored
+    likelihoods to 1e-10 and the stored decisions exactly, through both the per-move entry points and both sweep kernels."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "moves_g512.npz"))
+    hd = {k[2:]: (g[k] if g[k].ndim else float(g[k])) for k in g.files if k.startswith("h_")}
+    st = {k[3:]: g[k] for k in g.files if k.startswith("st_")}
+    ho, hg = hyper_pair(hd)
+    X, gl, d = g["X"], g["gl"], g["draws"]
+
+    def fresh():
+        s = oracle_state(X, gl, st)
+        s.XgLikelihood[:] = g["xglik"]; s.variance_g_probability[:] = g["vgprob"]
+        return gpu_handle(X, gl, hg, s)
+
+    h = fresh()
+    rel_close(h.eval_xg_loglik(), g["xglik"], 1e-10, "golden XgLikelihood")
+    rel_close(h.eval_varg_logprior(), g["vgprob"], 1e-10, "golden variance_g prior")
+    rel_close(h.eval_level2_loglik(), g["level2"], 1e-10, "golden level-2")
+    assert np.array_equal(h.mh_yg(0, draws=d[0:2], decisions=True), g["dec_yg"])
+    rel_close(h.get_state()["Yg"], g["yg_after"], 1e-12, "golden Yg")
+    h = fresh()
+    assert np.array_equal(h.mh_variance_g(0, draws=d[2:4], decisions=True), g["dec_vg"])
+    rel_close(h.get_state()["variance_g"], g["vg_after"], 1e-12, "golden variance_g")
+    h = fresh()
+    assert np.array_equal(h.gibbs_alloc(0, draws=d[4:6], decisions=True), g["dec_alloc"])
+    h = fresh()
+    assert np.array_equal(h.mh_spike_alloc(0, draws=d[6:9], decisions=True), g["dec_spike"])
+    assert np.array_equal(h.get_state()["inactive_spike_allocation"], g["spike_after"])
+    for mode in MODES.values():
+        h = fresh()
+        dec = h.sweep(0, moves=mode, draws=d, decisions=True)
+        assert np.array_equal(dec[:, 0], g["dec_sweep"])
+        stt = h.get_state()
+        rel_close(stt["Yg"], g["sweep_yg"], 1e-12, "golden sweep Yg"); rel_close(stt["variance_g"], g["sweep_vg"], 1e-12, "golden sweep variance_g")
+        rel_close(stt["XgLikelihood"], g["sweep_xglik"], 1e-10, "golden sweep XgLikelihood")
+        fin = np.isfinite(g["sweep_stats"])
+        assert np.allclose(h.suffstats()[0][fin], g["sweep_stats"][fin], rtol=1e-11, atol=1e-9)

@@ -136,3 +136,18 @@ def test_move_invariants_hold_on_the_oracle():
     assert ws.min() >= 0 and ws.max() <= 26 and (ws != 23).any()        # 3 tuned sweeps pushed 3 bits
     st_ = O.suffstats(ho, s)
     assert st_[:3].sum() == G and st_[9] == (s.inactive_spike_allocation == 1).sum()
+
+
+def test_oracle_reproduces_committed_golden_vectors():
+    """The committed golden file is what the oracle produces today (guards the checker against silent drift)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "moves_g512.npz"))
+    hd = {k[2:]: (g[k] if g[k].ndim else float(g[k])) for k in g.files if k.startswith("h_")}
+    st = {k[3:]: g[k] for k in g.files if k.startswith("st_")}
+    ho, _ = hyper_pair(hd)
+    s = oracle_state(g["X"], g["gl"], st)
+    O.refresh_caches(ho, s)
+    assert np.array_equal(s.XgLikelihood, g["xglik"]) and np.array_equal(s.variance_g_probability, g["vgprob"])
+    dec = O.sweep(ho, s, g["draws"])
+    assert np.array_equal(dec, g["dec_sweep"]) and np.array_equal(s.Yg, g["sweep_yg"]) and np.array_equal(s.variance_g, g["sweep_vg"])
+    assert float(g["sweep_lnl"]) == O.lnl(ho, s) or (np.isneginf(g["sweep_lnl"]) and np.isneginf(O.lnl(ho, s)))
