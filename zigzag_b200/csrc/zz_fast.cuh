@@ -155,9 +155,12 @@ __device__ __noinline__ double plnorm_term(const FastH &H, double y) {   // only
   return plnorm_log(H.vub, fma(H.s1, y, H.s0) + H.tau, H.rtau);
 }
 
+// beta * x with the reference's convention beta < 1e-7 => likelihood exactly 0 even where x is -Inf (P:121-125)
+__device__ __forceinline__ double times_beta(const FastH &H, double x) { return H.beta == 0.0 ? 0.0 : H.beta * x; }
+
 // XgLikelihood = beta (A + B),  B = -n_det (ln sqrt(2 pi) + 0.5 log v) - 0.5 D(y) / v      (P:57-127 re-expressed)
 __device__ __forceinline__ double xg_lik_fast(const FastH &H, const FastGene &g, const GeneData &d) {
-  return H.beta * (g.A + (-(double)d.ndet * (LN_SQRT_2PI + 0.5 * g.lv) - 0.5 * sqdist(d, g.y) * g.rv));
+  return times_beta(H, g.A + (-(double)d.ndet * (LN_SQRT_2PI + 0.5 * g.lv) - 0.5 * sqdist(d, g.y) * g.rv));
 }
 
 // mhYg (Pr:250-333)
@@ -169,7 +172,7 @@ template <int RT>
 __device__ __forceinline__ int fast_yg(const FastH &H, const MathTabs &T, FastGene &g, const GeneData &d, double yp, double tp,
                                        bool saturated, double u, double &ratio) {
   const double Ap = saturated ? (d.nd_mask ? -INFINITY : 0.0) : detect_logsum<RT>(H, T, d.nd_mask, tp);   // Pr:261-265
-  const double dLX = H.beta * ((Ap - g.A) - 0.5 * (sqdist(d, yp) - sqdist(d, g.y)) * g.rv);   // XgLik' - XgLik
+  const double dLX = times_beta(H, (Ap - g.A) - 0.5 * (sqdist(d, yp) - sqdist(d, g.y)) * g.rv);   // XgLik' - XgLik
   const double q = vg_q(H, g.lv, g.y), qp = vg_q(H, g.lv, yp);
   double dPV = -0.5 * (qp * qp - q * q);                                // Pr:267 - cache
   if (H.vub != INFINITY) dPV -= plnorm_term(H, yp) - plnorm_term(H, g.y);
@@ -191,7 +194,7 @@ __device__ __forceinline__ int fast_vg(const FastH &H, const MathTabs &T, FastGe
   const double dB = -(double)d.ndet * (0.5 * arg) - 0.5 * sqdist(d, g.y) * (rvp - g.rv);
   const double q = vg_q(H, g.lv, g.y), qp = q + arg * H.irt;
   const double dPV = -arg - 0.5 * (qp * qp - q * q);                    // the plnorm term (P:25) does not depend on v
-  ratio = H.temp * (H.beta * dB + dPV) + arg;                           // Pr:24
+  ratio = H.temp * (times_beta(H, dB) + dPV) + arg;                     // Pr:24
   // a current XgLikelihood of -Inf (or NaN) makes Lp - Lc NaN in the reference (both sides carry the same -Inf detection
   // term): keep that behaviour (reject + NaN flag) although the term cancels analytically here
   if (!(g.A > -INFINITY) && H.beta != 0.0) ratio = NAN;

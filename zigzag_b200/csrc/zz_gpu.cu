@@ -201,7 +201,7 @@ __device__ __noinline__ void spike_move(const FastH &H, const MathTabs &T, const
     const double pc = cur_in ? H.log_sp : (pyg + PVc);                // Pr:572-573
     double Ap = 0;
     if (!prop_in) Ap = detect_logsum<RT>(H, T, ~0ull, a.gl[g] * fexp(yp, T.exp_t));
-    double Lp = prop_in ? H.beta * 0.0 : H.beta * Ap;                 // Pr:579 (P:117 gives log(1*1) = 0 in the spike)
+    double Lp = prop_in ? 0.0 : times_beta(H, Ap);                    // Pr:579 (P:117 gives log(1*1) = 0 in the spike)
     double Lc = xglik;                                                // Pr:581
     if (Lp == -INFINITY && Lc == -INFINITY) { Lp = 0; Lc = 0; }       // Pr:583-585
     const double HR = prop_in ? (pyg - H.log_1msp + PVc) : -(pygp - H.log_1msp + PVp);   // Pr:592-595
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const
       if (H.vub != INFINITY) vgprob -= plnorm_term(H, gn.y);
       a.xglik[i] = xglik; a.vgprob[i] = vgprob;
     } else {
-      xglik = H.beta * ((gn.f & F_ALLZERO) ? 0.0 : -INFINITY);            // P:117
+      xglik = times_beta(H, (gn.f & F_ALLZERO) ? 0.0 : -INFINITY);       // P:117
       if (fa.want_stats && (gn.f & F_ALLZERO)) xglik = a.xglik[i];       // the cache as the last spike move left it (Pr:583-585, 630-632)
     }
     bool finite_state = isfinite(gn.y) && isfinite(gn.v);
