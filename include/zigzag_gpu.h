@@ -105,6 +105,7 @@ int zz_set_hyper(zz_handle *h, int chain, const zz_hyper *hy);
 int zz_get_hyper(zz_handle *h, int chain, zz_hyper *hy);
 /* XgLikelihood <- computeXgLikelihood(Xg,Yg,variance_g,p_x); variance_g_probability <- computeVarianceGPriorProbability (I:473, I:504) */
 int zz_refresh_caches(zz_handle *h);
+int zz_debug_refresh_lps(zz_handle *h);                          /* diagnostic: rebuild the production sweep's cached detection term A(Yg) now */
 int zz_reset_windows(zz_handle *h);                              /* Yg_trace / variance_g_trace <- 77 zeros + 23 ones (I:460,466) */
 int zz_get_window_sums(zz_handle *h, int chain, int32_t *yg_sum, int32_t *vg_sum); /* rowSums(Yg_trace), rowSums(variance_g_trace) */
 

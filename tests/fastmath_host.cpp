@@ -15,24 +15,34 @@ static double ulp_err(double got, long double ref) {
 int main(int argc, char **argv) {
   long n = argc > 1 ? atol(argv[1]) : 2000000;
   static MathTabs T;
-  for (int j = 0; j < 256; ++j) { memcpy(&T.exp_t[j], &kExpTab[j], 8); memcpy(&T.log_t[j].x, &kLogTab[2 * j], 8); memcpy(&T.log_t[j].y, &kLogTab[2 * j + 1], 8); }
+  for (int j = 0; j < 256; ++j) memcpy(&T.exp_t[j], &kExpTab[j], 8);
+  for (int j = 0; j < 512; ++j) { memcpy(&T.log_t[j].x, &kLogTab[2 * j], 8); memcpy(&T.log_t[j].y, &kLogTab[2 * j + 1], 8); }
   std::mt19937_64 g(1); std::uniform_real_distribution<double> U(0, 1);
-  double me = 0, ml = 0, mla = 0;
+  double me = 0, ml = 0, mla = 0, me2 = 0, mp2 = 0;
   for (long it = 0; it < n; ++it) {
     double x = (it & 1) ? (U(g) - 0.5) * 20 : (U(g) - 0.5) * 1416;
     double ue = ulp_err(fexp(x, T.exp_t), expl((long double)x)); if (ue > me) me = ue;
+    {  // base-2 detection exponential: 1 - 2^-b against 1 - exp(-a) with b = a * log2(e) (rounded)
+      double a = (it % 4 == 0) ? U(g) * 60 : U(g) * U(g) * 4;
+      double bb = a * ZZ_KLOG2E;
+      double e2 = fexp2_neg_clamped(bb, T.exp_t);
+      long double ref = exp2l(-(long double)bb);
+      double u2 = ulp_err(e2, ref); if (u2 > me2) me2 = u2;
+      double dp = fabs((1 - e2) - (double)(1 - expl(-(long double)a))); if (dp > mp2) mp2 = dp;
+    }
     double y = ldexp(U(g) + 1e-9, (int)(U(g) * 120) - 60);
     if (it % 3 == 0) y = 1 - U(g) * 1e-3 * U(g);
     if (it % 3 == 1) y = 1 + U(g) * 1e-2;
     long double rl = logl((long double)y); double l = flog(y, T.log_t);
     if (fabsl(rl) > 0.01L) { double ul = ulp_err(l, rl); if (ul > ml) ml = ul; } else { double ae = (double)fabsl((long double)l - rl); if (ae > mla) mla = ae; }
   }
-  printf("exp_max_ulp %.4f\nlog_max_ulp %.4f\nlog_max_abs_near_one %.4e\n", me, ml, mla);
+  printf("exp_max_ulp %.4f\nlog_max_ulp %.4f\nlog_max_abs_near_one %.4e\nexp2_max_ulp %.4f\npx_max_abs_err %.4e\n", me, ml, mla, me2, mp2);
   printf("log1 %.17g\nlog0 %.17g\nlogneg %.17g\nloginf %.17g\nlogsub %.17g %.17g\n", flog(1.0, T.log_t), flog(0.0, T.log_t), flog(-1.0, T.log_t), flog(INFINITY, T.log_t), flog(1e-310, T.log_t), log(1e-310));
   printf("exp_m800 %.17g\nexp_800 %.17g\nexp_m720 %.17g %.17g\nexp_nan %.17g\n", fexp(-800, T.exp_t), fexp(800, T.exp_t), fexp(-720, T.exp_t), exp(-720.), fexp(NAN, T.exp_t));
   const double a[] = {0, 1e-300, 1e-17, 0.5, 36.7, 36.8, 37.5, 40, 699, 700, 701, 1e5, INFINITY};
   int bad = 0;
-  for (double v : a) bad += ((1 - fexp_neg_clamped(v, T.exp_t)) != (1 - exp(-v))) && fabs((1 - fexp_neg_clamped(v, T.exp_t)) - (1 - exp(-v))) > 3e-16;
+  for (double v : a) bad += fabs((1 - fexp_neg_clamped(v, T.exp_t)) - (1 - exp(-v))) > 3e-16;
+  for (double v : a) bad += fabs((1 - fexp2_neg_clamped(v * ZZ_KLOG2E, T.exp_t)) - (1 - exp(-v))) > 3e-16;
   printf("px_mismatch %d\n", bad);
   return 0;
 }

@@ -14,7 +14,9 @@ def test_fast_exp_log_within_two_ulp(tmp_path):
     out = dict(line.split(None, 1) for line in subprocess.check_output([exe, "3000000"], text=True).splitlines())
     assert float(out["exp_max_ulp"]) < 2.5            # table + degree-4 economised polynomial
     assert float(out["log_max_ulp"]) < 2.5
-    assert float(out["log_max_abs_near_one"]) < 5e-18  # no cancellation blow-up around x = 1
+    assert float(out["log_max_abs_near_one"]) < 2e-17  # no cancellation blow-up around x = 1
+    assert float(out["exp2_max_ulp"]) < 2.5           # base-2 detection exponential
+    assert float(out["px_max_abs_err"]) < 2.3e-16      # 1 - 2^-b vs 1 - exp(-a): within one ulp of 1
     assert float(out["log1"]) == 0.0
     assert out["log0"].strip() == "-inf" and "nan" in out["logneg"] and out["loginf"].strip() == "inf"
     a, b = map(float, out["logsub"].split())

@@ -21,4 +21,8 @@ e0.record()
 for i in range(n): h.sweep(100 + i)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
+e0.record()
+for i in range(50): h.debug_refresh_lps()
+e1.record(); torch.cuda.synchronize()
+print(f"   detection-loop-only kernel (k_refresh_lps): {e0.elapsed_time(e1)/50*1e3:.1f} us")
 print(f"{os.environ.get('ZIGZAG_GPU_LIB','default')}: {name} sweep+spike {ms*1e3:.1f} us  -> {G*chains/ms/1e6:.2f} G gene-updates/s, {G*chains*(8*R+60)/ms/1e6/6547.2*100:.1f}% of HBM roofline")

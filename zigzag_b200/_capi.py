@@ -75,6 +75,7 @@ _SIG = {
     "zz_set_hyper": (C.c_int, [_P, C.c_int, C.POINTER(Hyper)]),
     "zz_get_hyper": (C.c_int, [_P, C.c_int, C.POINTER(Hyper)]),
     "zz_refresh_caches": (C.c_int, [_P]),
+    "zz_debug_refresh_lps": (C.c_int, [_P]),
     "zz_reset_windows": (C.c_int, [_P]),
     "zz_get_window_sums": (C.c_int, [_P, C.c_int, _P, _P]),
     "zz_eval_xg_loglik": (C.c_int, [_P, C.c_int, _P]),
@@ -214,6 +215,9 @@ class Handle:
 
     def refresh_caches(self):
         self._ck(self.L.zz_refresh_caches(self.h))
+
+    def debug_refresh_lps(self):
+        self._ck(self.L.zz_debug_refresh_lps(self.h))
 
     def reset_windows(self):
         self._ck(self.L.zz_reset_windows(self.h))

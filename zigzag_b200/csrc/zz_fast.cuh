@@ -21,7 +21,7 @@
 #include "zz_fastmath.cuh"
 
 #ifndef ZZ_ILP
-#define ZZ_ILP 2
+#define ZZ_ILP 4
 #endif
 #ifndef ZZ_SWEEP_MINB
 #define ZZ_SWEEP_MINB 3
@@ -38,6 +38,7 @@ struct FastH {   // one chain's hyper-parameters + hoisted gene-independent sub-
   double wa, one_m_wa, beta, temp, vub;
   double alpha_min;                       // min_r alpha_r: t * alpha_min >= 37.5 => every p_x == 1 exactly
   double alpha[ZZ_MAX_LIBS];
+  double alpha2[ZZ_MAX_LIBS];             // alpha_r * log2(e): the detection exponent in base 2 (fexp2_neg_clamped)
   double am[ZZ_MAX_COMP], inv2av[ZZ_MAX_COMP], ck[ZZ_MAX_COMP];  // ck = w_k / (sqrt2pi * sqrt(av_k))           (Pr:344)
 };
 
@@ -57,7 +58,7 @@ __device__ __forceinline__ void derive_fast(FastH &H, const zz_hyper *__restrict
   H.beta = (hy->beta < 0.0000001) ? 0.0 : hy->beta;   // P:121-125: beta < 1e-7 => likelihood 0
   H.temp = hy->temperature; H.vub = hy->variance_g_upper_bound;
   H.alpha_min = INFINITY;
-  for (int r = 0; r < ZZ_MAX_LIBS; ++r) { H.alpha[r] = hy->alpha_r[r]; if (r < H.R && !(hy->alpha_r[r] >= H.alpha_min)) H.alpha_min = hy->alpha_r[r]; }
+  for (int r = 0; r < ZZ_MAX_LIBS; ++r) { H.alpha[r] = hy->alpha_r[r]; H.alpha2[r] = hy->alpha_r[r] * ZZ_KLOG2E; if (r < H.R && !(hy->alpha_r[r] >= H.alpha_min)) H.alpha_min = hy->alpha_r[r]; }
   for (int k = 0; k < ZZ_MAX_COMP; ++k) {
     H.am[k] = hy->active_means[k];
     H.inv2av[k] = 1.0 / (2 * hy->active_variances[k]);
@@ -68,7 +69,8 @@ __device__ __forceinline__ void derive_fast(FastH &H, const zz_hyper *__restrict
 __device__ __forceinline__ void load_fast(FastH &H, MathTabs &T, const FastH *__restrict__ src,
                                           const double *__restrict__ exp_tab, const double2 *__restrict__ log_tab) {
   const int t = threadIdx.x, nt = blockDim.x;
-  for (int j = t; j < 256; j += nt) { T.exp_t[j] = exp_tab[j]; T.log_t[j] = log_tab[j]; }
+  for (int j = t; j < 256; j += nt) T.exp_t[j] = exp_tab[j];
+  for (int j = t; j < 512; j += nt) T.log_t[j] = log_tab[j];
   static_assert(sizeof(FastH) % 8 == 0, "FastH is copied as 64-bit words");
   const uint64_t *s = reinterpret_cast<const uint64_t *>(src);
   uint64_t *d = reinterpret_cast<uint64_t *>(&H);
@@ -112,7 +114,7 @@ __device__ __forceinline__ double detect_logsum(const FastH &H, const MathTabs &
       for (int j = 0; j < ZZ_ILP; ++j) {
         if (r0 + j < R) {
           const int r = r0 + j;
-          const double e = fexp_neg_clamped(t * H.alpha[r], T.exp_t);
+          const double e = fexp2_neg_clamped(t * H.alpha2[r], T.exp_t);
           const double p = 1 - e;
           const double q = ((nd_mask >> r) & 1ull) ? (1 - p) : p;
           l[j] = flog_core(q, T.log_t);
@@ -126,7 +128,7 @@ __device__ __forceinline__ double detect_logsum(const FastH &H, const MathTabs &
   }
   unsigned zero_seen = 0xFFFFFFFFu;
   for (int r = 0; r < R; ++r) {
-    const double e = fexp_neg_clamped(t * H.alpha[r], T.exp_t);
+    const double e = fexp2_neg_clamped(t * H.alpha2[r], T.exp_t);
     const double p = 1 - e;
     const double q = ((nd_mask >> r) & 1ull) ? (1 - p) : p;
     A += flog_core(q, T.log_t);

@@ -47,12 +47,12 @@ ZZ_HD double d_make(int hi, int lo) {
 // to 20 fraction bits (their rounding error is multiplied by r^4..r^6 and vanishes below 1e-19); the few that need full
 // precision are kept in registers by the compiler.
 #define ZZ_E4_IMM 0x1.55555p-5    /* 1/24  (error * r^4 < 1e-19) */
-#define ZZ_L5_IMM 0x1.9999ap-3    /* 1/5   (error * r^5 < 1e-19) */
-#define ZZ_L6_IMM (-0x1.55555p-3) /* -1/6  (error * r^6 < 1e-21) */
+#define ZZ_L5_IMM 0x1.9999ap-3    /* 1/5   (error * r^5 < 1e-20 for |r| <= 2^-9) */
+#define ZZ_P4_IMM 0x1.3b2abp-7    /* ln2^4/24 (error * r^4 < 1e-19 for |r| <= 2^-9) */
 
 struct MathTabs {          // lives in shared memory on the device
   double exp_t[256];       // 2^(j/256)
-  double2 log_t[256];      // {IC[i], LC[i]}
+  double2 log_t[512];      // {IC[i], LC[i]}
 };
 
 // exp(x) for -708 <= x <= 709 (callers clamp or take the libm path outside).  9 FP64 instructions.
@@ -106,17 +106,36 @@ ZZ_HD double fexp_neg_clamped(double a, const double *__restrict__ exp_t) {
   return fexp_core(-d_make(hc, d_lo(a)), exp_t);
 }
 
-// log(x) for positive normal finite x.  10 FP64 instructions.
+// 2^(-b) for b >= 0 (b = t * alpha_r * log2(e), the detection exponent in base 2): the reduction step nd/256 is exact, so
+// one fma fewer than the natural-base version.  b is clamped at 1010 (2^-1010 is still a normal number and 1 - 2^-b == 1
+// for every b > 54).  8 FP64 instructions.
+ZZ_HD double fexp2_neg_clamped(double b, const double *__restrict__ exp_t) {
+  const int hi = d_hi(b);
+  const int hc = hi < 0x408F9000 ? hi : 0x408F9000;   // 0x408F9000_00000000 = 1010.0
+  const double x = -d_make(hc, d_lo(b));
+  const double magic = 6755399441055744.0;
+  const double t = fma(x, 256.0, magic);
+  const int n = d_lo(t);
+  const double nd = t - magic;
+  const double r = fma(nd, -0.00390625, x);           // exact, |r| <= 2^-9 (log2 units)
+  double p = fma(r, ZZ_P4_IMM, ZZ_KP3);               // 2^r = 1 + r (P1 + r (P2 + r (P3 + r P4)))
+  p = fma(r, p, ZZ_KP2);
+  p = fma(r, p, ZZ_KP1);
+  p = fma(r, p, 1.0);
+  const double s = exp_t[n & 255] * p;
+  return d_make(d_hi(s) + ((n >> 8) << 20), d_lo(s));
+}
+
+// log(x) for positive normal finite x.  8 FP64 instructions + one int->double conversion.
 ZZ_HD double flog_core(double x, const double2 *__restrict__ log_t) {
   const int hi = d_hi(x);
-  const int k = ((hi + 0x00096000) >> 20) - 1023;     // exponent, +1 when the mantissa is >= 1 + 106/256 (table entry is for m/2)
-  const int i = (hi >> 12) & 255;
+  const int k = ((hi + 0x00096000) >> 20) - 1023;     // exponent, +1 when the mantissa is >= 1 + 212/512 (table entry is for m/2)
+  const int i = (hi >> 11) & 511;
   const double m = d_make((hi & 0x000FFFFF) | 0x3FF00000, d_lo(x));
   const double2 tc = log_t[i];
-  const double r = fma(m, tc.x, -1.0);                // exact (IC has <= 10 significant bits)
+  const double r = fma(m, tc.x, -1.0);                // exact (IC has <= 11 significant bits), |r| <= 2^-9
   const double r2 = r * r;
-  double s = fma(r, ZZ_L6_IMM, ZZ_L5_IMM);            // log1p(r) = r + r^2 (-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6)
-  s = fma(r, s, -0.25);
+  double s = fma(r, ZZ_L5_IMM, -0.25);                // log1p(r) = r + r^2 (-1/2 + r/3 - r^2/4 + r^3/5), |r^6/6| < 1e-17
   s = fma(r, s, 1.0 / 3);
   s = fma(r, s, -0.5);
   const double lo = fma(r2, s, r);

@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const
   for (int64_t t_ = warp0; t_ < ntiles; t_ += nwarps) {
     const int64_t tile = ntiles - 1 - t_;
     const int64_t g = a.g_begin + tile * 32 + lane;
+#ifndef ZZ_NO_PREFETCH
     {   // pull the next tile's inputs towards L1 while this tile computes (no registers, no shared memory)
       const int64_t gn_ = g - nwarps * 32;
       if (gn_ >= a.g_begin && gn_ < a.g_end) {
@@ -255,6 +256,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const
         if ((lane & 3) == 0) prefetch_l1(a.flags + in_);
       }
     }
+#endif
     if (g >= a.g_end) continue;
     const int64_t i = (int64_t)chain * a.G + g;
     const uint64_t gid = (uint64_t)(a.gene_offset + a.perm[g]);
@@ -800,7 +802,7 @@ int persistent_blocks(zz_handle *h, size_t smem) {
   if (h->persist_blocks > 0) return h->persist_blocks;
   int per_sm = 0, sms = 0;
   cudaError_t e;
-  if (smem > 40 * 1024) {   // the statistics columns of large-K models exceed the default 48 KB dynamic shared memory limit
+  {   // static tables (11.6 KB) + statistic columns exceed the default 48 KB shared-memory limit: opt in explicitly
     switch (h->R) {
       case 2: allow_big_smem<2>((int)smem); break;
       case 4: allow_big_smem<4>((int)smem); break;
@@ -1145,6 +1147,13 @@ int zz_refresh_caches(zz_handle *h) {
   h->stats_fresh = false;
   if (!h->have_data) return fail(h, ZZ_ERR_STATE, "zz_upload_data has not been called");
   return launch_eval(h, EVAL_REFRESH, -1, h->xglik, h->vgprob);
+}
+
+int zz_debug_refresh_lps(zz_handle *h) {
+  ZZ_CHECK(h);
+  if (!h->have_data) return fail(h, ZZ_ERR_STATE, "zz_upload_data has not been called");
+  h->lps_valid = false;
+  return ensure_lps(h);
 }
 
 int zz_reset_windows(zz_handle *h) {
