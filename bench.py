@@ -155,6 +155,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: statistics all-reduce fused into the reduction kernel over NVLink peer memory (default) or NCCL")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -208,11 +210,24 @@ def main():
     nstat = h.nstat
     stats = torch.zeros(chains * nstat, dtype=torch.float64, device=dev)
 
+    use_p2p = world > 1 and args.collective == "p2p"
+    if use_p2p:     # CUDA IPC handles of every rank's inbox, exchanged once over the process group
+        blobs = [None] * world
+        dist.all_gather_object(blobs, h.comm_init(rank, world))
+        h.comm_connect(blobs)
+        dist.barrier()
+
+    def reduce_stats():
+        if use_p2p:
+            h.suffstats_allreduce_dev(stats.data_ptr())   # 1 launch: final reduction + all-reduce over peer memory
+        else:
+            h.suffstats_dev(stats.data_ptr())             # 1 launch: k_reduce_final
+            if world > 1:
+                dist.all_reduce(stats)                    # the one collective of the path (NCCL)
+
     def step(i):
-        h.sweep(i)                              # 1 launch: k_sweep
-        h.suffstats_dev(stats.data_ptr())       # 2 launches: k_suffstats + k_reduce_final
-        if world > 1:
-            dist.all_reduce(stats)              # the one collective of the path
+        h.sweep(i)                              # 1 launch: k_sweep_fast (all four moves + per-CTA statistics)
+        reduce_stats()
 
     for i in range(args.warmup):
         step(i)
@@ -230,9 +245,7 @@ def main():
         sw[i][0].record()
         h.sweep(args.warmup + i)
         sw[i][1].record()
-        h.suffstats_dev(stats.data_ptr())
-        if world > 1:
-            dist.all_reduce(stats)
+        reduce_stats()
     ev1.record()
     torch.cuda.synchronize()
     t_wall1 = time.time()
@@ -249,6 +262,15 @@ def main():
     value = G_tot * chains * args.steps / (ms_total * 1e-3)
     st_host = stats.cpu().numpy().reshape(chains, nstat)
     assert abs(st_host[0][:3].sum() - G_tot) < 0.5, "component counts do not sum to the number of genes"
+    if use_p2p:     # the fused all-reduce must agree with NCCL on the same local vectors and be bit-identical on every rank
+        loc = torch.zeros_like(stats)
+        h.suffstats_dev(loc.data_ptr())
+        dist.all_reduce(loc)
+        assert torch.allclose(loc, stats, rtol=1e-12, atol=1e-9), "peer-memory all-reduce disagrees with NCCL"
+        both = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(both, stats)
+        assert all(torch.equal(both[0], b) for b in both), "ranks hold different reduced vectors"
+        assert h.nan_flag() == 0
 
     # ---- e2e: the same sweep through the host-buffer entry point (mutable state in pinned host memory, H2D + D2H every step)
     e2e = None
@@ -305,7 +327,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"synthetic {G_cfg} genes x {R} replicates, K=2 active components, {chains} chain(s) (BASELINE.json configs: {args.workload})",
                        "genes_per_gpu": G, "genes_total": G_tot, "libraries": R, "chains": chains,
-                       "step": "fused sweep (mhYg, mhVariance_g, allocation, spike allocation) + suff-stat reduction" + (" + NCCL all-reduce" if world > 1 else ""),
+                       "step": "fused sweep (mhYg, mhVariance_g, allocation, spike allocation) + suff-stat reduction" + ((" fused with a peer-memory all-reduce over NVLink" if use_p2p else " + NCCL all-reduce") if world > 1 else ""),
                        "l2": f"working set {(G * (8 * R + 8) + G * chains * 50) / 1e6:.0f} MB per GPU vs 126 MB L2: inputs larger than L2, no flush" if G * (8 * R + 58) > 126e6 else "working set fits in L2 (reported as-is; see DESIGN.md)",
                        "rng": "Philox4x32-10 on device"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

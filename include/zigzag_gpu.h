@@ -140,6 +140,15 @@ int zz_suffstats_len(int num_active_components);                 /* 3(K+1)+10 */
    sum z, sum z^2, sum y(out), sum y^2(out), sum y z (z = log variance_g, out-of-spike) | sum XgLikelihood | sum variance_g_probability(out) | nan count */
 int zz_suffstats(zz_handle *h, double *out);
 int zz_suffstats_dev(zz_handle *h, double *out_dev);             /* same, written to caller-owned device memory on the handle's stream (for an NCCL all-reduce) */
+/* ---- multi-GPU: the one collective of the path, fused with the final reduction over NVLink peer memory ----
+   One process per GPU.  Every rank calls zz_comm_init (allocates its inbox, returns zz_comm_handle_bytes() bytes of CUDA IPC
+   handles), the host framework all-gathers the handle blobs (rank order) and passes the concatenation to zz_comm_connect.
+   zz_suffstats_allreduce_dev then leaves on every rank the bit-identical sum over ranks (added in rank order) of the
+   statistics vectors, in one kernel launch.  A peer that does not show up within ~2 s raises bit 2 of zz_nan_flag. */
+int zz_comm_handle_bytes(void);
+int zz_comm_init(zz_handle *h, int rank, int world, void *handle_out);
+int zz_comm_connect(zz_handle *h, const void *all_handles);
+int zz_suffstats_allreduce_dev(zz_handle *h, double *out_dev);
 /* out2 = { sum over out-of-spike genes of computeVarianceGPriorProbability(variance_g, exp(s0+s1*Yg), tau), sum of the cached variance_g_probability } ; Pr:84-87,126-130,167-170 */
 int zz_varg_hyper_sum(zz_handle *h, int chain, double s0, double s1, double tau, double *out2);
 int zz_commit_varg_hyper(zz_handle *h, int chain);               /* accepted mhTau/mhSg/mhS0Tau: overwrite variance_g_probability[out_spike_idx] (Pr:113,147,187) from the current hyper */

@@ -91,6 +91,10 @@ _SIG = {
     "zz_suffstats_len": (C.c_int, [C.c_int]),
     "zz_suffstats": (C.c_int, [_P, _P]),
     "zz_suffstats_dev": (C.c_int, [_P, _P]),
+    "zz_comm_handle_bytes": (C.c_int, []),
+    "zz_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "zz_comm_connect": (C.c_int, [_P, _P]),
+    "zz_suffstats_allreduce_dev": (C.c_int, [_P, _P]),
     "zz_varg_hyper_sum": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double, _P]),
     "zz_commit_varg_hyper": (C.c_int, [_P, C.c_int]),
     "zz_level2_sums": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, _P, _P, _P]),
@@ -299,6 +303,21 @@ class Handle:
 
     def suffstats_dev(self, dev_ptr):
         self._ck(self.L.zz_suffstats_dev(self.h, _P(dev_ptr)))
+
+    def comm_init(self, rank, world):
+        """Allocates this rank's peer-memory inbox; returns the CUDA IPC handle blob to all-gather."""
+        buf = (C.c_ubyte * int(self.L.zz_comm_handle_bytes()))()
+        self._ck(self.L.zz_comm_init(self.h, int(rank), int(world), C.addressof(buf)))
+        return bytes(buf)
+
+    def comm_connect(self, blobs):
+        """blobs: the handle blobs of all ranks, in rank order."""
+        cat = b"".join(blobs)
+        buf = (C.c_ubyte * len(cat)).from_buffer_copy(cat)
+        self._ck(self.L.zz_comm_connect(self.h, C.addressof(buf)))
+
+    def suffstats_allreduce_dev(self, dev_ptr):
+        self._ck(self.L.zz_suffstats_allreduce_dev(self.h, _P(dev_ptr)))
 
     def varg_hyper_sum(self, s0, s1, tau, chain=0):
         out = np.empty(2)

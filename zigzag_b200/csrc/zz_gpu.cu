@@ -481,6 +481,69 @@ __global__ void __launch_bounds__(BLOCK) k_reduce_final(const double *partials, 
 constexpr int NSTAT_FIXED = 10;
 constexpr int MAX_NSTAT = 3 * (ZZ_MAX_COMP + 1) + NSTAT_FIXED;
 
+// ---- sufficient-statistics all-reduce fused into the final reduction, over NVLink peer memory ------------------------------
+// Every rank (one process per GPU) owns an inbox [2 slots][world][nval*C] and a flag row [2][world] in its own HBM, mapped into
+// every peer through CUDA IPC.  One CTA per rank: (1) reduce the sweep's per-CTA partial rows exactly like k_reduce_final,
+// (2) store the local vector into inbox[slot][my_rank] of EVERY rank (remote stores ride NVLink/NVSwitch), fence, then raise
+// flag[slot][my_rank] = epoch on every rank, (3) spin until all `world` flags of the local row reached `epoch`, (4) add the
+// `world` vectors in RANK ORDER, so every rank obtains the bit-identical sum (replicated hyper moves cannot diverge).
+// Slots alternate with the epoch; a rank cannot lap another by more than one epoch because it needs everybody's flag first.
+// The spin is bounded (~2 s of clock64): on timeout the kernel raises bit 2 of the NaN/err flag instead of hanging.
+struct CommArgs {
+  int rank, world, nvec;                 // nvec = nval * C doubles per rank
+  unsigned long long epoch;
+  double *inbox[8];                      // inbox[r]: base of rank r's inbox, as mapped in THIS process
+  unsigned long long *flags[8];          // flags[r]: base of rank r's flag array
+};
+
+__global__ void __launch_bounds__(BLOCK) k_reduce_allreduce(const double *partials, int nblk, int nval, int C, double *out, CommArgs cm,
+                                                             int *err_flag) {
+  __shared__ double vec[MAX_NSTAT * 8];   // local reduced vector (nvec <= MAX_NSTAT * 8 is checked by the host)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int idx = w; idx < cm.nvec; idx += BLOCK / 32) {
+    const int y = idx / nval, s = idx - y * nval;
+    double v = 0;
+    for (int b = lane; b < nblk; b += 32) v += partials[((int64_t)y * nblk + b) * nval + s];
+    v = warp_sum(v);
+    if (lane == 0) vec[idx] = v;
+  }
+  __syncthreads();
+  const int slot = (int)(cm.epoch & 1ull);
+  // (2) scatter my vector to every rank's inbox (thread t handles element t of rank r = blockIdx-free loop)
+  for (int r = 0; r < cm.world; ++r) {
+    double *dst = cm.inbox[r] + ((int64_t)slot * cm.world + cm.rank) * cm.nvec;
+    for (int idx = threadIdx.x; idx < cm.nvec; idx += BLOCK) dst[idx] = vec[idx];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < cm.world) {
+    volatile unsigned long long *f = cm.flags[threadIdx.x] + (int64_t)slot * cm.world + cm.rank;
+    *f = cm.epoch;
+  }
+  // (3) wait for everybody's flag in my own row
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
+  if (threadIdx.x < cm.world) {
+    volatile unsigned long long *f = cm.flags[cm.rank] + (int64_t)slot * cm.world + threadIdx.x;
+    const long long t0 = clock64();
+    while (*f < cm.epoch) {
+      if (clock64() - t0 > 4000000000LL) { timed_out = 1; break; }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (timed_out) { if (threadIdx.x == 0) atomicOr(err_flag, 4); return; }
+  // (4) sum in rank order
+  const double *in = cm.inbox[cm.rank] + (int64_t)slot * cm.world * cm.nvec;
+  for (int idx = threadIdx.x; idx < cm.nvec; idx += BLOCK) {
+    double v = 0;
+    for (int r = 0; r < cm.world; ++r) v += ((volatile const double *)in)[(int64_t)r * cm.nvec + idx];
+    out[idx] = v;
+  }
+}
+
+
 struct StatArgs {
   int64_t G; int K;
   const double *Yg, *vg, *xglik, *vgprob;  // base pointers, chain = blockIdx.y
@@ -644,6 +707,10 @@ struct zz_handle {
   double *stage;                           // staging for permuted transfers, same size as scratch
   uint64_t *nd_mask; double *xbar, *xss;   // per-gene data statistics (k_prepare_data)
   FastH *fasth; bool fasth_valid;           // derived hyper-parameters of the production kernels
+  // peer-memory all-reduce of the statistics vector (zz_comm_*)
+  int comm_rank, comm_world; unsigned long long comm_epoch; bool comm_ready;
+  double *comm_inbox; unsigned long long *comm_flags;        // this rank's inbox / flags (device memory, exported through CUDA IPC)
+  double *peer_inbox[8]; unsigned long long *peer_flags[8];  // every rank's buffers as mapped here (own entry = local pointers)
   unsigned *tile_counter; unsigned tile_base; int persist_blocks;
   double *sw_partials, *sw_partials2; int64_t sw_rows; bool stats_fresh;   // statistics emitted by the last production sweep
   bool lps_valid;                          // lps == A(current Yg, alpha_r) for every out-of-spike gene
@@ -976,6 +1043,8 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   h->perm_h.resize(G);
   for (int64_t g = 0; g < G; ++g) h->perm_h[g] = (int32_t)g;
   ZZ_CUDA(h, cudaMemcpyAsync(h->perm, h->perm_h.data(), sizeof(int32_t) * G, cudaMemcpyHostToDevice, h->stream));
+  h->comm_rank = 0; h->comm_world = 1; h->comm_epoch = 0; h->comm_ready = false; h->comm_inbox = nullptr; h->comm_flags = nullptr;
+  for (int r = 0; r < 8; ++r) { h->peer_inbox[r] = nullptr; h->peer_flags[r] = nullptr; }
   h->n_allzero = 0; h->lps_valid = false; h->stats_fresh = false; h->tile_base = 0; h->persist_blocks = 0; h->sw_rows = 0;
   ZZ_CUDA(h, cudaMalloc(&h->fasth, sizeof(FastH) * h->C));
   h->fasth_valid = false;
@@ -1002,6 +1071,12 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
 void zz_destroy(zz_handle *h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
+  for (int r = 0; r < 8; ++r) {
+    if (r != h->comm_rank && h->peer_inbox[r]) cudaIpcCloseMemHandle(h->peer_inbox[r]);
+    if (r != h->comm_rank && h->peer_flags[r]) cudaIpcCloseMemHandle(h->peer_flags[r]);
+  }
+  if (h->comm_inbox) cudaFree(h->comm_inbox);
+  if (h->comm_flags) cudaFree(h->comm_flags);
   void *ptrs[] = {h->Xg, h->gl, h->Yg, h->vg, h->xglik, h->vgprob, h->ty, h->tv, h->flags, h->win_y, h->win_v, h->trace,
                   h->hyper, h->partials, h->red_out, h->scratch, h->dec, h->iscratch, h->nan_flag, h->lps, h->exp_tab,
                   h->log_tab, h->perm, h->stage, h->nd_mask, h->xbar, h->xss, h->tile_counter, h->sw_partials, h->sw_partials2, h->fasth};
@@ -1250,6 +1325,65 @@ int zz_suffstats(zz_handle *h, double *out) {
   ZZ_CUDA(h, cudaMemcpyAsync(h->pinned, h->red_out, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
   memcpy(out, h->pinned, sizeof(double) * n);
+  return ZZ_OK;
+}
+
+
+int zz_comm_handle_bytes(void) { return 2 * (int)sizeof(cudaIpcMemHandle_t); }
+
+int zz_comm_init(zz_handle *h, int rank, int world, void *handle_out) {
+  ZZ_CHECK(h);
+  if (world < 1 || world > 8 || rank < 0 || rank >= world || !handle_out) return fail(h, ZZ_ERR_INVALID, "zz_comm_init: need 0 <= rank < world <= 8");
+  if (h->comm_inbox) return fail(h, ZZ_ERR_STATE, "zz_comm_init was already called on this handle");
+  const size_t nvec = (size_t)zz_suffstats_len(h->K) * h->C;
+  if (nvec > (size_t)MAX_NSTAT * 8) return fail(h, ZZ_ERR_INVALID, "zz_comm_init: too many chains for the fused all-reduce (nstat * chains <= 296)");
+  h->comm_rank = rank; h->comm_world = world; h->comm_epoch = 0;
+  ZZ_CUDA(h, cudaMalloc(&h->comm_inbox, sizeof(double) * 2 * world * nvec));
+  ZZ_CUDA(h, cudaMalloc(&h->comm_flags, sizeof(unsigned long long) * 2 * world));
+  ZZ_CUDA(h, cudaMemset(h->comm_inbox, 0, sizeof(double) * 2 * world * nvec));
+  ZZ_CUDA(h, cudaMemset(h->comm_flags, 0, sizeof(unsigned long long) * 2 * world));
+  cudaIpcMemHandle_t hs[2];
+  ZZ_CUDA(h, cudaIpcGetMemHandle(&hs[0], h->comm_inbox));
+  ZZ_CUDA(h, cudaIpcGetMemHandle(&hs[1], h->comm_flags));
+  memcpy(handle_out, hs, sizeof hs);
+  return ZZ_OK;
+}
+
+int zz_comm_connect(zz_handle *h, const void *all_handles) {
+  ZZ_CHECK(h);
+  if (!h->comm_inbox || !all_handles) return fail(h, ZZ_ERR_STATE, "zz_comm_connect: call zz_comm_init first");
+  const cudaIpcMemHandle_t *hs = reinterpret_cast<const cudaIpcMemHandle_t *>(all_handles);
+  for (int r = 0; r < h->comm_world; ++r) {
+    if (r == h->comm_rank) { h->peer_inbox[r] = h->comm_inbox; h->peer_flags[r] = h->comm_flags; continue; }
+    void *p0 = nullptr, *p1 = nullptr;
+    ZZ_CUDA(h, cudaIpcOpenMemHandle(&p0, hs[2 * r + 0], cudaIpcMemLazyEnablePeerAccess));
+    ZZ_CUDA(h, cudaIpcOpenMemHandle(&p1, hs[2 * r + 1], cudaIpcMemLazyEnablePeerAccess));
+    h->peer_inbox[r] = (double *)p0; h->peer_flags[r] = (unsigned long long *)p1;
+  }
+  h->comm_ready = true;
+  return ZZ_OK;
+}
+
+int zz_suffstats_allreduce_dev(zz_handle *h, double *out_dev) {
+  ZZ_CHECK(h);
+  if (!out_dev) return fail(h, ZZ_ERR_INVALID, "out_dev is NULL");
+  if (!h->comm_ready) return fail(h, ZZ_ERR_STATE, "zz_comm_connect has not been called");
+  const int nstat = zz_suffstats_len(h->K);
+  const double *partials; int nblk;
+  if (h->stats_fresh) { partials = h->sw_partials; nblk = (int)h->sw_rows; }
+  else {
+    nblk = red_blocks(h->G);
+    StatArgs a;
+    a.G = h->G; a.K = h->K; a.Yg = h->Yg; a.vg = h->vg; a.xglik = h->xglik; a.vgprob = h->vgprob; a.flags = h->flags; a.partials = h->partials;
+    k_suffstats<<<dim3(nblk, h->C), BLOCK, 0, h->stream>>>(a);
+    ZZ_LAUNCHED(h);
+    partials = h->partials;
+  }
+  CommArgs cm;
+  cm.rank = h->comm_rank; cm.world = h->comm_world; cm.nvec = nstat * h->C; cm.epoch = ++h->comm_epoch;
+  for (int r = 0; r < 8; ++r) { cm.inbox[r] = h->peer_inbox[r]; cm.flags[r] = h->peer_flags[r]; }
+  k_reduce_allreduce<<<1, BLOCK, 0, h->stream>>>(partials, nblk, nstat, h->C, out_dev, cm, h->nan_flag);
+  ZZ_LAUNCHED(h);
   return ZZ_OK;
 }
 
