@@ -217,16 +217,16 @@ def main():
         h.comm_connect(blobs)
         dist.barrier()
 
+    # the sweep kernel's last CTA reduces the per-CTA statistics (and all-reduces them over NVLink peer memory when N > 1)
+    # straight into `stats`: ONE launch per step
+    h.set_stats_output_dev(stats.data_ptr(), allreduce=use_p2p)
+
     def reduce_stats():
-        if use_p2p:
-            h.suffstats_allreduce_dev(stats.data_ptr())   # 1 launch: final reduction + all-reduce over peer memory
-        else:
-            h.suffstats_dev(stats.data_ptr())             # 1 launch: k_reduce_final
-            if world > 1:
-                dist.all_reduce(stats)                    # the one collective of the path (NCCL)
+        if world > 1 and not use_p2p:
+            dist.all_reduce(stats)                        # the one collective of the path, NCCL variant
 
     def step(i):
-        h.sweep(i)                              # 1 launch: k_sweep_fast (all four moves + per-CTA statistics)
+        h.sweep(i)                              # 1 launch: k_sweep_fast (four moves + statistics + final reduction [+ all-reduce])
         reduce_stats()
 
     for i in range(args.warmup):

@@ -149,6 +149,10 @@ int zz_comm_handle_bytes(void);
 int zz_comm_init(zz_handle *h, int rank, int world, void *handle_out);
 int zz_comm_connect(zz_handle *h, const void *all_handles);
 int zz_suffstats_allreduce_dev(zz_handle *h, double *out_dev);
+/* Fused epilogue: from now on every whole-shard production zz_sweep also leaves the statistics ([C][len], all-reduced over
+   ranks when `allreduce` != 0) in caller-owned device memory `out_dev`, written by the last CTA of the sweep kernel itself:
+   one launch per generation.  out_dev == NULL switches it off. */
+int zz_set_stats_output_dev(zz_handle *h, double *out_dev, int allreduce);
 /* out2 = { sum over out-of-spike genes of computeVarianceGPriorProbability(variance_g, exp(s0+s1*Yg), tau), sum of the cached variance_g_probability } ; Pr:84-87,126-130,167-170 */
 int zz_varg_hyper_sum(zz_handle *h, int chain, double s0, double s1, double tau, double *out2);
 int zz_commit_varg_hyper(zz_handle *h, int chain);               /* accepted mhTau/mhSg/mhS0Tau: overwrite variance_g_probability[out_spike_idx] (Pr:113,147,187) from the current hyper */

@@ -490,3 +490,27 @@ def test_committed_golden_vectors():
         rel_close(stt["XgLikelihood"], g["sweep_xglik"], 1e-10, "golden sweep XgLikelihood")
         fin = np.isfinite(g["sweep_stats"])
         assert np.allclose(h.suffstats()[0][fin], g["sweep_stats"][fin], rtol=1e-11, atol=1e-9)
+
+
+def test_fused_statistics_epilogue_matches_separate_reduction():
+    """zz_set_stats_output_dev: the sweep's last CTA leaves the same statistics (bit for bit) as zz_suffstats computes from the
+    per-CTA rows, for several chains, and they match the oracle."""
+    import torch
+    G, R, C = 6000, 4, 3
+    X, gl, hd, ho, hg, s, h0 = setup_pair(G, R, 19)
+    h0.close()
+    h = gpu_handle(X, gl, hg, s, chains=C, seed=5)
+    out = torch.zeros(C * h.nstat, dtype=torch.float64, device="cuda")
+    h.set_stream(torch.cuda.current_stream().cuda_stream)
+    h.set_stats_output_dev(out.data_ptr())
+    for step in range(3):
+        h.sweep(step)
+        torch.cuda.synchronize()
+        fused = out.cpu().numpy().reshape(C, -1).copy()
+        sep = h.suffstats()
+        assert np.array_equal(fused, sep)
+        assert np.all(fused[:, :3].sum(1) == G)
+    h.set_stats_output_dev(0)
+    out.zero_()
+    h.sweep(9); torch.cuda.synchronize()
+    assert float(out.abs().sum()) == 0.0          # switched off again

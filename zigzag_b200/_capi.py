@@ -95,6 +95,7 @@ _SIG = {
     "zz_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "zz_comm_connect": (C.c_int, [_P, _P]),
     "zz_suffstats_allreduce_dev": (C.c_int, [_P, _P]),
+    "zz_set_stats_output_dev": (C.c_int, [_P, _P, C.c_int]),
     "zz_varg_hyper_sum": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double, _P]),
     "zz_commit_varg_hyper": (C.c_int, [_P, C.c_int]),
     "zz_level2_sums": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, _P, _P, _P]),
@@ -315,6 +316,9 @@ class Handle:
         cat = b"".join(blobs)
         buf = (C.c_ubyte * len(cat)).from_buffer_copy(cat)
         self._ck(self.L.zz_comm_connect(self.h, C.addressof(buf)))
+
+    def set_stats_output_dev(self, dev_ptr, allreduce=False):
+        self._ck(self.L.zz_set_stats_output_dev(self.h, _P(dev_ptr) if dev_ptr else None, int(allreduce)))
 
     def suffstats_allreduce_dev(self, dev_ptr):
         self._ck(self.L.zz_suffstats_allreduce_dev(self.h, _P(dev_ptr)))

@@ -34,6 +34,77 @@ constexpr int SW_CHUNKS = 64;        // first-level chunks of the sweep-statisti
 
 // ------------------------------------------------------------------------------------------------ kernels
 
+constexpr int NSTAT_FIXED = 10;
+constexpr int MAX_NSTAT = 3 * (ZZ_MAX_COMP + 1) + NSTAT_FIXED;
+
+// ---- sufficient-statistics all-reduce over NVLink peer memory, fused with the final reduction -------------------------------
+// Every rank (one process per GPU) owns an inbox [2 slots][world][nvec] and a flag row [2][world] in its own HBM, mapped into
+// every peer through CUDA IPC.  The CTA that holds the rank's reduced vector (1) stores it into inbox[slot][my_rank] of EVERY
+// rank (remote stores ride NVLink/NVSwitch), fences, raises flag[slot][my_rank] = epoch on every rank, (2) spins until all
+// `world` flags of its own row reached `epoch`, (3) adds the `world` vectors in RANK ORDER, so every rank obtains the
+// bit-identical sum (replicated hyper moves cannot diverge).  Slots alternate with the epoch; a rank cannot lap another by
+// more than one epoch because it needs everybody's flag first.  The spin is bounded (~2 s of clock64): on timeout bit 2 of
+// the NaN/err flag is raised instead of hanging.
+struct CommArgs {
+  int rank, world, nvec;                 // nvec = nval * C doubles per rank
+  unsigned long long epoch;
+  double *inbox[8];                      // inbox[r]: base of rank r's inbox, as mapped in THIS process
+  unsigned long long *flags[8];          // flags[r]: base of rank r's flag array
+};
+
+// all threads of the CTA must call it; `vec` = the local vector in shared memory
+__device__ __forceinline__ void allreduce_exchange(const double *vec, const CommArgs &cm, double *out, int *err_flag) {
+  __shared__ int timed_out;
+  const int slot = (int)(cm.epoch & 1ull);
+  for (int r = 0; r < cm.world; ++r) {
+    double *dst = cm.inbox[r] + ((int64_t)slot * cm.world + cm.rank) * cm.nvec;
+    for (int idx = threadIdx.x; idx < cm.nvec; idx += blockDim.x) dst[idx] = vec[idx];
+  }
+  if (threadIdx.x == 0) timed_out = 0;
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < cm.world) {
+    volatile unsigned long long *f = cm.flags[threadIdx.x] + (int64_t)slot * cm.world + cm.rank;
+    *f = cm.epoch;
+    volatile unsigned long long *mine = cm.flags[cm.rank] + (int64_t)slot * cm.world + threadIdx.x;
+    const long long t0 = clock64();
+    while (*mine < cm.epoch) {
+      if (clock64() - t0 > 4000000000LL) { timed_out = 1; break; }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (timed_out) { if (threadIdx.x == 0) atomicOr(err_flag, 4); return; }
+  const double *in = cm.inbox[cm.rank] + (int64_t)slot * cm.world * cm.nvec;
+  for (int idx = threadIdx.x; idx < cm.nvec; idx += blockDim.x) {
+    double v = 0;
+    for (int r = 0; r < cm.world; ++r) v += ((volatile const double *)in)[(int64_t)r * cm.nvec + idx];
+    out[idx] = v;
+  }
+}
+
+// fixed-order reduction of the per-CTA rows [C][nblk][nval] into `vec` (shared memory, nvec = nval*C doubles); whole CTA
+__device__ __forceinline__ void reduce_rows_to_smem(const double *partials, int nblk, int nval, int nvec, double *vec) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int idx = w; idx < nvec; idx += nw) {
+    const int y = idx / nval, s = idx - y * nval;
+    double v = 0;
+    for (int b = lane; b < nblk; b += 32) v += ((volatile const double *)partials)[((int64_t)y * nblk + b) * nval + s];
+    v = warp_sum(v);
+    if (lane == 0) vec[idx] = v;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(BLOCK) k_reduce_allreduce(const double *partials, int nblk, int nval, int C, double *out, CommArgs cm,
+                                                             int *err_flag) {
+  __shared__ double vec[MAX_NSTAT * 8];   // local reduced vector (nvec <= MAX_NSTAT * 8 is checked by the host)
+  (void)C;
+  reduce_rows_to_smem(partials, nblk, nval, cm.nvec, vec);
+  allreduce_exchange(vec, cm, out, err_flag);
+}
+
+
 struct SweepArgs {
   int64_t G, g_begin, g_end, gene_offset;
   int C, R, K, tune;
@@ -133,6 +204,8 @@ struct FastArgs {
   double *partials;                 // [C][rows][nstat] per-block sufficient statistics (rows = main blocks + spike blocks)
   int64_t rows_per_chain, spike_row0;
   int want_stats, do_spike_move;
+  // fused epilogue: the last CTA to finish reduces the rows (and all-reduces them over peer memory when asked) into stats_out
+  unsigned *done_counter; double *stats_out; int do_allreduce; CommArgs cm;
 };
 
 __global__ void k_prepare_hyper(int C, const zz_hyper *hyper, FastH *out) {
@@ -333,6 +406,21 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const
   if (fa.want_stats) {
     __syncthreads();
     stats_flush<SWEEP_BLOCK>(acc, nstat, fa.partials + ((int64_t)chain * fa.rows_per_chain + blockIdx.x) * nstat, red);
+    if (fa.stats_out) {   // "last CTA done" epilogue: no second launch for the final reduction / the collective
+      __shared__ unsigned ticket;
+      __syncthreads();
+      if (threadIdx.x == 0) { __threadfence(); ticket = atomicAdd(fa.done_counter, 1u); }
+      __syncthreads();
+      if (ticket == gridDim.x * gridDim.y - 1) {
+        __threadfence();
+        double *vec = acc;                         // the statistic columns are dead now: reuse them as the reduced vector
+        const int nvec = nstat * (int)gridDim.y;
+        reduce_rows_to_smem(fa.partials, (int)fa.rows_per_chain, nstat, nvec, vec);
+        if (fa.do_allreduce) allreduce_exchange(vec, fa.cm, fa.stats_out, a.nan_flag);
+        else for (int idx = threadIdx.x; idx < nvec; idx += blockDim.x) fa.stats_out[idx] = vec[idx];
+        if (threadIdx.x == 0) *fa.done_counter = 0u;
+      }
+    }
   }
 }
 
@@ -478,70 +566,7 @@ __global__ void __launch_bounds__(BLOCK) k_reduce_final(const double *partials, 
   }
 }
 
-constexpr int NSTAT_FIXED = 10;
-constexpr int MAX_NSTAT = 3 * (ZZ_MAX_COMP + 1) + NSTAT_FIXED;
 
-// ---- sufficient-statistics all-reduce fused into the final reduction, over NVLink peer memory ------------------------------
-// Every rank (one process per GPU) owns an inbox [2 slots][world][nval*C] and a flag row [2][world] in its own HBM, mapped into
-// every peer through CUDA IPC.  One CTA per rank: (1) reduce the sweep's per-CTA partial rows exactly like k_reduce_final,
-// (2) store the local vector into inbox[slot][my_rank] of EVERY rank (remote stores ride NVLink/NVSwitch), fence, then raise
-// flag[slot][my_rank] = epoch on every rank, (3) spin until all `world` flags of the local row reached `epoch`, (4) add the
-// `world` vectors in RANK ORDER, so every rank obtains the bit-identical sum (replicated hyper moves cannot diverge).
-// Slots alternate with the epoch; a rank cannot lap another by more than one epoch because it needs everybody's flag first.
-// The spin is bounded (~2 s of clock64): on timeout the kernel raises bit 2 of the NaN/err flag instead of hanging.
-struct CommArgs {
-  int rank, world, nvec;                 // nvec = nval * C doubles per rank
-  unsigned long long epoch;
-  double *inbox[8];                      // inbox[r]: base of rank r's inbox, as mapped in THIS process
-  unsigned long long *flags[8];          // flags[r]: base of rank r's flag array
-};
-
-__global__ void __launch_bounds__(BLOCK) k_reduce_allreduce(const double *partials, int nblk, int nval, int C, double *out, CommArgs cm,
-                                                             int *err_flag) {
-  __shared__ double vec[MAX_NSTAT * 8];   // local reduced vector (nvec <= MAX_NSTAT * 8 is checked by the host)
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int idx = w; idx < cm.nvec; idx += BLOCK / 32) {
-    const int y = idx / nval, s = idx - y * nval;
-    double v = 0;
-    for (int b = lane; b < nblk; b += 32) v += partials[((int64_t)y * nblk + b) * nval + s];
-    v = warp_sum(v);
-    if (lane == 0) vec[idx] = v;
-  }
-  __syncthreads();
-  const int slot = (int)(cm.epoch & 1ull);
-  // (2) scatter my vector to every rank's inbox (thread t handles element t of rank r = blockIdx-free loop)
-  for (int r = 0; r < cm.world; ++r) {
-    double *dst = cm.inbox[r] + ((int64_t)slot * cm.world + cm.rank) * cm.nvec;
-    for (int idx = threadIdx.x; idx < cm.nvec; idx += BLOCK) dst[idx] = vec[idx];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x < cm.world) {
-    volatile unsigned long long *f = cm.flags[threadIdx.x] + (int64_t)slot * cm.world + cm.rank;
-    *f = cm.epoch;
-  }
-  // (3) wait for everybody's flag in my own row
-  __shared__ int timed_out;
-  if (threadIdx.x == 0) timed_out = 0;
-  __syncthreads();
-  if (threadIdx.x < cm.world) {
-    volatile unsigned long long *f = cm.flags[cm.rank] + (int64_t)slot * cm.world + threadIdx.x;
-    const long long t0 = clock64();
-    while (*f < cm.epoch) {
-      if (clock64() - t0 > 4000000000LL) { timed_out = 1; break; }
-    }
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (timed_out) { if (threadIdx.x == 0) atomicOr(err_flag, 4); return; }
-  // (4) sum in rank order
-  const double *in = cm.inbox[cm.rank] + (int64_t)slot * cm.world * cm.nvec;
-  for (int idx = threadIdx.x; idx < cm.nvec; idx += BLOCK) {
-    double v = 0;
-    for (int r = 0; r < cm.world; ++r) v += ((volatile const double *)in)[(int64_t)r * cm.nvec + idx];
-    out[idx] = v;
-  }
-}
 
 
 struct StatArgs {
@@ -712,6 +737,7 @@ struct zz_handle {
   double *comm_inbox; unsigned long long *comm_flags;        // this rank's inbox / flags (device memory, exported through CUDA IPC)
   double *peer_inbox[8]; unsigned long long *peer_flags[8];  // every rank's buffers as mapped here (own entry = local pointers)
   unsigned *tile_counter; unsigned tile_base; int persist_blocks;
+  double *stats_target; int stats_allreduce;   // zz_set_stats_output_dev: where the sweep's fused epilogue leaves the statistics
   double *sw_partials, *sw_partials2; int64_t sw_rows; bool stats_fresh;   // statistics emitted by the last production sweep
   bool lps_valid;                          // lps == A(current Yg, alpha_r) for every out-of-spike gene
   std::vector<zz_hyper> hyper_host;
@@ -816,6 +842,7 @@ void fill_fast_args(zz_handle *h, FastArgs &fa) {
   fa.lps = h->lps; fa.exp_tab = h->exp_tab; fa.log_tab = h->log_tab; fa.allzero_begin = h->G - h->n_allzero; fa.n_allzero = h->n_allzero;
   fa.nd_mask = h->nd_mask; fa.xbar = h->xbar; fa.xss = h->xss; fa.fasth = h->fasth;
   fa.partials = h->sw_partials; fa.rows_per_chain = 0; fa.spike_row0 = 0; fa.want_stats = 0; fa.do_spike_move = 0;
+  fa.done_counter = h->tile_counter; fa.stats_out = nullptr; fa.do_allreduce = 0; memset(&fa.cm, 0, sizeof fa.cm);
 }
 
 int ensure_fasth(zz_handle *h) {
@@ -913,6 +940,14 @@ int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, con
   fa.spike_row0 = per_chain;
   fa.do_spike_move = (moves & ZZ_MOVE_SPIKE) ? 1 : 0;
   h->stats_fresh = false;
+  if (full && h->stats_target) {
+    fa.stats_out = h->stats_target;
+    if (h->stats_allreduce && h->comm_ready) {
+      fa.do_allreduce = 1;
+      fa.cm.rank = h->comm_rank; fa.cm.world = h->comm_world; fa.cm.nvec = nstat * h->C; fa.cm.epoch = ++h->comm_epoch;
+      for (int r = 0; r < 8; ++r) { fa.cm.inbox[r] = h->peer_inbox[r]; fa.cm.flags[r] = h->peer_flags[r]; }
+    }
+  }
   const bool prod = !draws_dev[0] && !draws_dev[2] && !draws_dev[4] && !draws_dev[6] && !dec_dev[0] && !dec_dev[1] && !dec_dev[2] && !dec_dev[3];
   if (dec_dev[3] && (moves & ZZ_MOVE_SPIKE)) ZZ_CUDA(h, cudaMemsetAsync(dec_dev[3], 0, (size_t)h->C * h->G, h->stream));
   ZZ_DISPATCH_SWEEP(h, prod, dim3((unsigned)per_chain, (unsigned)h->C), smem, fa);
@@ -1043,6 +1078,7 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   h->perm_h.resize(G);
   for (int64_t g = 0; g < G; ++g) h->perm_h[g] = (int32_t)g;
   ZZ_CUDA(h, cudaMemcpyAsync(h->perm, h->perm_h.data(), sizeof(int32_t) * G, cudaMemcpyHostToDevice, h->stream));
+  h->stats_target = nullptr; h->stats_allreduce = 0;
   h->comm_rank = 0; h->comm_world = 1; h->comm_epoch = 0; h->comm_ready = false; h->comm_inbox = nullptr; h->comm_flags = nullptr;
   for (int r = 0; r < 8; ++r) { h->peer_inbox[r] = nullptr; h->peer_flags[r] = nullptr; }
   h->n_allzero = 0; h->lps_valid = false; h->stats_fresh = false; h->tile_base = 0; h->persist_blocks = 0; h->sw_rows = 0;
@@ -1361,6 +1397,14 @@ int zz_comm_connect(zz_handle *h, const void *all_handles) {
     h->peer_inbox[r] = (double *)p0; h->peer_flags[r] = (unsigned long long *)p1;
   }
   h->comm_ready = true;
+  return ZZ_OK;
+}
+
+int zz_set_stats_output_dev(zz_handle *h, double *out_dev, int allreduce) {
+  ZZ_CHECK(h);
+  if (allreduce && !h->comm_ready) return fail(h, ZZ_ERR_STATE, "zz_set_stats_output_dev: all-reduce requested before zz_comm_connect");
+  if ((size_t)zz_suffstats_len(h->K) * h->C > (size_t)MAX_NSTAT * 8) return fail(h, ZZ_ERR_INVALID, "too many chains for the fused statistics epilogue");
+  h->stats_target = out_dev; h->stats_allreduce = allreduce ? 1 : 0;
   return ZZ_OK;
 }
 
