@@ -298,7 +298,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         e2e = {"value": G_tot * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": nb[0] * world, "d2h_bytes_per_step": nb[1] * world,
-               "steps": args.e2e_steps, "what": "zz_sweep_host: per-gene state up from pinned host arrays, fused sweep, updated state back; Xg resident since zz_upload_data"}
+               "steps": args.e2e_steps, "what": "zz_sweep_host: mutable per-gene state (Yg, variance_g, tuning parameters, allocations) up from pinned host arrays, fused sweep, updated state + both likelihood caches back; Xg resident since zz_upload_data"}
 
     if rank != 0:
         if world > 1:

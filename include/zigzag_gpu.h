@@ -173,8 +173,9 @@ int zz_nan_flag(zz_handle *h, int *flag);                        /* replaces the
 
 /* ---- host-buffer round trip (bench.py `e2e`) ---------------------------------------------------------------- */
 /* One fused sweep where the mutable per-gene state lives in HOST arrays, as it does in the R object between .Call()s:
-   uploads Yg, variance_g, tuning parameters, caches and allocations, runs zz_sweep, downloads the updated state.  Xg and
-   gene_lengths stay resident from zz_upload_data.  Chain 0 only.  Bytes moved are returned in h2d_bytes / d2h_bytes. */
+   uploads Yg, variance_g, tuning parameters and allocations, runs zz_sweep, downloads the updated state including the two caches
+   (XgLikelihood / variance_g_probability are outputs only: they are functions of the uploaded state).  Xg and gene_lengths stay
+   resident from zz_upload_data.  Chain 0 only.  Bytes moved are returned in h2d_bytes / d2h_bytes. */
 int zz_sweep_host(zz_handle *h, uint64_t step, int tune, double *Yg, double *variance_g, int32_t *alloc_active_inactive,
                   int32_t *alloc_within_active, int32_t *inactive_spike_allocation, double *XgLikelihood,
                   double *variance_g_probability, const double *tuningParam_yg, const double *tuningParam_variance_g,

@@ -384,7 +384,7 @@ def test_sweep_host_round_trip_equals_resident_sweep():
     for step in range(2):
         h.sweep(step)
         nb = h2.sweep_host(step, False, *[host[k] for k in host])
-        assert nb == (G * 60, G * 44)
+        assert nb == (G * 44, G * 44)
     g = h.get_state()
     for k in host:
         if k == "alloc_within_active":

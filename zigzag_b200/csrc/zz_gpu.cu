@@ -435,8 +435,13 @@ __global__ void __launch_bounds__(BLOCK) k_refresh_lps(const FastArgs fa) {
   const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (g >= a.G) return;
   const int64_t i = (int64_t)chain * a.G + g;
-  if (a.flags[i] & F_INSPIKE) { fa.lps[i] = 0; return; }
-  fa.lps[i] = detect_logsum<RT>(H, T, fa.nd_mask[g], a.gl[g] * fexp(a.Yg[i], T.exp_t));
+  const uint32_t f = a.flags[i];
+  if (f & F_INSPIKE) { fa.lps[i] = 0; if (fa.want_stats && (f & F_ALLZERO)) a.xglik[i] = 0.0; return; }
+  const double A = detect_logsum<RT>(H, T, fa.nd_mask[g], a.gl[g] * fexp(a.Yg[i], T.exp_t));
+  fa.lps[i] = A;
+  // want_stats doubles as "also rebuild XgLikelihood of the all-zero genes" (n_det = 0 => XgLik = beta A): zz_sweep_host does not
+  // upload the caches, and the spike move reads this one (Pr:581)
+  if (fa.want_stats && (f & F_ALLZERO)) a.xglik[i] = times_beta(H, A);
 }
 
 // exports the Philox draws of one move slot in the layout of that move's `draws` argument
@@ -853,12 +858,13 @@ int ensure_fasth(zz_handle *h) {
   return ZZ_OK;
 }
 
-int ensure_lps(zz_handle *h) {
+int ensure_lps(zz_handle *h, bool rebuild_allzero_xglik = false) {
   if (int rc = ensure_fasth(h)) return rc;
   if (h->lps_valid) return ZZ_OK;
   FastArgs fa;
   fill_sweep_args(h, fa.s, 0, 0, 0, nullptr, nullptr, 0, h->G);
   fill_fast_args(h, fa);
+  fa.want_stats = rebuild_allzero_xglik ? 1 : 0;
   ZZ_DISPATCH_R(h, k_refresh_lps, gene_grid(h, h->G, h->C), fa);
   ZZ_LAUNCHED(h);
   h->lps_valid = true;
@@ -1544,13 +1550,15 @@ int zz_sweep_host(zz_handle *h, uint64_t step, int tune, double *Yg, double *var
   int32_t *d_ai = h->iscratch, *d_w = h->iscratch + G, *d_s = h->iscratch + 2 * G;
   int rc;
   if ((rc = up_g(h, h->Yg, (const double *)Yg, G)) || (rc = up_g(h, h->vg, (const double *)variance_g, G)) ||
-      (rc = up_g(h, h->xglik, (const double *)XgLikelihood, G)) || (rc = up_g(h, h->vgprob, (const double *)variance_g_probability, G)) ||
       (rc = up_g(h, h->ty, ty, G)) || (rc = up_g(h, h->tv, tv, G)) ||
       (rc = up(h, d_ai, (const int32_t *)ai, G)) || (rc = up(h, d_w, (const int32_t *)within, G)) || (rc = up(h, d_s, (const int32_t *)spike, G)))
     return rc;
   k_pack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, h->perm, d_ai, d_w, d_s, nullptr, h->flags);
   ZZ_LAUNCHED(h);
-  h->lps_valid = false;  // Yg arrived from the host: A(y) is rebuilt on the device (one extra pass; PCIe dominates this entry point)
+  // Yg arrived from the host: A(y) is rebuilt on the device (one extra pass; PCIe dominates this entry point).  The two caches
+  // are pure functions of the uploaded state, so they are not uploaded: the sweep recomputes them and they travel back only.
+  h->lps_valid = false;
+  if ((rc = ensure_lps(h, true))) return rc;
   {
     const double *no_draws[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint8_t *no_dec[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1563,7 +1571,7 @@ int zz_sweep_host(zz_handle *h, uint64_t step, int tune, double *Yg, double *var
       (rc = down(h, ai, d_ai, G)) || (rc = down(h, within, d_w, G)) || (rc = down(h, spike, d_s, G)))
     return rc;
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (h2d_bytes) *h2d_bytes = G * (6 * 8 + 3 * 4);
+  if (h2d_bytes) *h2d_bytes = G * (4 * 8 + 3 * 4);
   if (d2h_bytes) *d2h_bytes = G * (4 * 8 + 3 * 4);
   return ZZ_OK;
 }
