@@ -18,10 +18,17 @@ int main(int argc, char **argv) {
   for (int j = 0; j < 256; ++j) memcpy(&T.exp_t[j], &kExpTab[j], 8);
   for (int j = 0; j < 512; ++j) { memcpy(&T.log_t[j].x, &kLogTab[2 * j], 8); memcpy(&T.log_t[j].y, &kLogTab[2 * j + 1], 8); }
   std::mt19937_64 g(1); std::uniform_real_distribution<double> U(0, 1);
-  double me = 0, ml = 0, mla = 0, me2 = 0, mp2 = 0;
+  double me = 0, ml = 0, mla = 0, me2 = 0, mp2 = 0, mrc = 0, msq = 0, menb = 0;
   for (long it = 0; it < n; ++it) {
     double x = (it & 1) ? (U(g) - 0.5) * 20 : (U(g) - 0.5) * 1416;
     double ue = ulp_err(fexp(x, T.exp_t), expl((long double)x)); if (ue > me) me = ue;
+    {  // branch-free helpers
+      double xr = ldexp(1 + U(g), (int)(U(g) * 600) - 300);
+      double urc = ulp_err(frcp_nb(xr), 1.0L / (long double)xr); if (urc > mrc) mrc = urc;
+      double xs = (it & 1) ? U(g) * 44.4 + 4.6e-10 : U(g) * 1e-6 + 4.6e-10;
+      double usq = ulp_err(fsqrt_nb(xs), sqrtl((long double)xs)); if (usq > msq) msq = usq;
+      double xe = (U(g) - 0.5) * 1400; double uenb = ulp_err(fexp_nb(xe, T.exp_t), expl((long double)xe)); if (uenb > menb) menb = uenb;
+    }
     {  // base-2 detection exponential: 1 - 2^-b against 1 - exp(-a) with b = a * log2(e) (rounded)
       double a = (it % 4 == 0) ? U(g) * 60 : U(g) * U(g) * 4;
       double bb = a * ZZ_KLOG2E;
@@ -37,6 +44,7 @@ int main(int argc, char **argv) {
     if (fabsl(rl) > 0.01L) { double ul = ulp_err(l, rl); if (ul > ml) ml = ul; } else { double ae = (double)fabsl((long double)l - rl); if (ae > mla) mla = ae; }
   }
   printf("exp_max_ulp %.4f\nlog_max_ulp %.4f\nlog_max_abs_near_one %.4e\nexp2_max_ulp %.4f\npx_max_abs_err %.4e\n", me, ml, mla, me2, mp2);
+  printf("rcp_max_ulp %.4f\nsqrt_max_ulp %.4f\nexp_nb_max_ulp %.4f\nexp_nb_m750 %.17g\nexp_nb_m720 %.17g\nexp_nb_800 %.17g\n", mrc, msq, menb, fexp_nb(-750, T.exp_t), fexp_nb(-720, T.exp_t), fexp_nb(800, T.exp_t));
   printf("log1 %.17g\nlog0 %.17g\nlogneg %.17g\nloginf %.17g\nlogsub %.17g %.17g\n", flog(1.0, T.log_t), flog(0.0, T.log_t), flog(-1.0, T.log_t), flog(INFINITY, T.log_t), flog(1e-310, T.log_t), log(1e-310));
   printf("exp_m800 %.17g\nexp_800 %.17g\nexp_m720 %.17g %.17g\nexp_nan %.17g\n", fexp(-800, T.exp_t), fexp(800, T.exp_t), fexp(-720, T.exp_t), exp(-720.), fexp(NAN, T.exp_t));
   const double a[] = {0, 1e-300, 1e-17, 0.5, 36.7, 36.8, 37.5, 40, 699, 700, 701, 1e5, INFINITY};

@@ -514,3 +514,43 @@ def test_fused_statistics_epilogue_matches_separate_reduction():
     out.zero_()
     h.sweep(9); torch.cuda.synchronize()
     assert float(out.abs().sum()) == 0.0          # switched off again
+
+
+@pytest.mark.parametrize("tune", [False, True])
+@pytest.mark.parametrize("G,R,seed,K", CASES + [(5000, 16, 6, 2), (4000, 8, 7, 1)])
+def test_straight_line_production_tile_matches_oracle(G, R, seed, K, tune):
+    """The kernel bench.py times: zz_sweep with Philox draws and no decision export takes the straight-line tile (K <= 3) or
+    the generic production tile (K = 4).  Its draws are exported and replayed on the oracle; equality of every allocation word
+    and spike flag plus Yg / variance_g to 1e-12 means every accept/reject decision was identical."""
+    X, gl, hd, ho, hg, s, h = setup_pair(G, R, seed, K, pinned_frac=0.01)
+    for step in range(4):
+        d = np.concatenate([h.philox_draws(step, sl)[:, 0] for sl in
+                            (_capi.SLOT_YG, _capi.SLOT_VARIANCE_G, _capi.SLOT_ALLOC, _capi.SLOT_SPIKE)])
+        y_before = s.Yg.copy()
+        O.sweep(ho, s, d, tune=tune)
+        h.sweep(step, tune=tune)                     # draws=None, decisions=False  -> production instantiation
+        compare_state(h, s)
+        assert (s.Yg != y_before).mean() > 0.2
+    if tune:
+        assert np.array_equal(h.window_sums()[0], s.window_sums("Yg_trace"))
+        assert np.array_equal(h.window_sums()[1], s.window_sums("variance_g_trace"))
+    st_o, st_g = O.suffstats(ho, s), h.suffstats()[0]
+    fin = np.isfinite(st_o)
+    assert np.allclose(st_g[fin], st_o[fin], rtol=1e-11, atol=1e-9) and np.array_equal(st_g[:K + 1], st_o[:K + 1])
+    assert h.nan_flag() in (0, 1)
+
+
+def test_straight_line_tile_handles_beta_and_temperature():
+    from zigzag_b200 import synth
+    for variant in ("tempered", "prior_only"):
+        G, R = 3000, 4
+        hd = dict(synth.truth_hyper_dict(R)); hd.update(VARIANTS[variant])
+        X, gl, hd, st = make_case(G, R, 29, hyper=hd)
+        ho, hg = hyper_pair(hd)
+        s = oracle_state(X, gl, st); O.refresh_caches(ho, s)
+        h = gpu_handle(X, gl, hg, s)
+        for step in range(3):
+            d = np.concatenate([h.philox_draws(step, sl)[:, 0] for sl in
+                                (_capi.SLOT_YG, _capi.SLOT_VARIANCE_G, _capi.SLOT_ALLOC, _capi.SLOT_SPIKE)])
+            O.sweep(ho, s, d); h.sweep(step)
+            compare_state(h, s)

@@ -154,6 +154,53 @@ ZZ_HD double flog_prob(double q, const double2 *__restrict__ log_t) {
   return ((d_hi(q) | d_lo(q)) == 0) ? -INFINITY : l;
 }
 
+// ---- branch-free variants (the production tile is one straight-line block so that the scheduler can overlap its chains) ----
+
+// exp(x) without a libm path: |x| is clamped at 708 through the high word, and x < -745.2 (true result 0, below the smallest
+// subnormal) returns exactly 0.  Between -745.2 and -708 libm would return a subnormal; this returns exp(-708) = 3.3e-308.
+ZZ_HD double fexp_nb(double x, const double *__restrict__ exp_t) {
+  const int hi = d_hi(x);
+  const int mag = hi & 0x7FFFFFFF;
+  const int magc = mag < 0x40862000 ? mag : 0x40862000;            // 708.0
+  const double r = fexp_core(d_make(magc | (hi & 0x80000000), d_lo(x)), exp_t);
+  return ((unsigned)hi > 0xC0874999u) ? 0.0 : r;                   // x < -745.2 (negative: larger bit pattern = more negative)
+}
+
+// log(x) for x that the caller knows to be a positive normal number (no libm path; anything else gives finite garbage)
+ZZ_HD double flog_nb(double x, const double2 *__restrict__ log_t) { return flog_core(x, log_t); }
+
+// true when x is a positive normal finite double (integer test on the high word)
+ZZ_HD bool is_pos_normal(double x) { return (unsigned)d_hi(x) - 0x00100000u < 0x7FE00000u; }
+
+// 1/x for positive normal x: split off the exponent, float reciprocal seed of the mantissa, two Newton steps (<= 1 ulp)
+ZZ_HD double frcp_nb(double x) {
+  const int hi = d_hi(x);
+  const double m = d_make((hi & 0x000FFFFF) | 0x3FF00000, d_lo(x));   // [1, 2)
+#if defined(__CUDA_ARCH__)
+  double r = (double)__frcp_rn((float)m);
+#else
+  double r = (double)(1.0f / (float)m);
+#endif
+  r = r * fma(-m, r, 2.0);
+  r = r * fma(-m, r, 2.0);
+  r = fma(r, fma(-m, r, 1.0), r);                                   // final correction: r + r (1 - m r)
+  return d_make(d_hi(r) + ((1023 - ((hi >> 20) & 0x7FF)) << 20), d_lo(r));
+}
+
+// sqrt(x) for x in the float range (here x = -2 log u in (4.6e-10, 44.4]): float rsqrt seed + two Newton steps
+ZZ_HD double fsqrt_nb(double x) {
+#if defined(__CUDA_ARCH__)
+  double y = (double)rsqrtf((float)x);
+#else
+  double y = (double)(1.0f / sqrtf((float)x));
+#endif
+  const double h = 0.5 * x;
+  y = fma(y, fma(-h, y * y, 0.5), y);
+  y = fma(y, fma(-h, y * y, 0.5), y);
+  const double s = x * y;
+  return fma(fma(-s, s, x), 0.5 * y, s);                            // one correction step on the root itself
+}
+
 // (w + 0.5) * 2^-32 in one fma (both products are exact, so this equals the two-step form bit for bit)
 ZZ_HD double u32_to_open01(uint32_t w) { return fma((double)w, 0x1p-32, 0x1p-33); }
 

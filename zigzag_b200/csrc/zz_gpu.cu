@@ -298,7 +298,10 @@ __device__ __noinline__ void spike_move(const FastH &H, const MathTabs &T, const
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-template <int RT, bool PROD>
+// KT > 0 selects the straight-line production tile (all four moves, Philox draws, variance_g_upper_bound = Inf, K = KT active
+// components): every lane executes the same branch-free instruction stream (decisions are applied with selects), which lets
+// the scheduler overlap the independent exp/log/reciprocal chains of the three moves instead of serialising them.
+template <int RT, bool PROD, int KT>
 __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const FastArgs fa) {
   __shared__ FastH H;
   __shared__ MathTabs T;
@@ -333,6 +336,91 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const
     if (g >= a.g_end) continue;
     const int64_t i = (int64_t)chain * a.G + g;
     const uint64_t gid = (uint64_t)(a.gene_offset + a.perm[g]);
+    if constexpr (KT > 0) {
+      // ---------------- straight-line production tile ----------------
+      const double y0 = a.Yg[i], v0 = a.vg[i], A0 = fa.lps[i], ty = a.ty[i], tv = a.tv[i], gl = a.gl[g];
+      const double xbar = fa.xbar[g], ss = fa.xss[g];
+      const uint64_t mask = fa.nd_mask[g];
+      uint32_t f = a.flags[i];
+      const double nd_d = (double)((RT > 0 ? RT : H.R) - __popcll(mask));
+      const bool live = !(f & F_INSPIKE);
+      uint32_t b0[4], b1[4];
+      philox_block(a.seed, chain, a.step, 0, gid, b0);
+      philox_block(a.seed, chain, a.step, 1, gid, b1);
+      const double u_y = u32_to_open01(b0[2]), u1 = u32_to_open01(b0[3]), u2 = u32_to_open01(b1[0]);
+      const double u_ai = u32_to_open01(b1[1]), u_w = u32_to_open01(b1[2]);
+      const double z = fsqrt_nb(-2.0 * flog_nb(u32_to_open01(b0[0]), T.log_t)) * cospi(2.0 * u32_to_open01(b0[1]));
+      const double lv = flog_nb(v0, T.log_t), rv = frcp_nb(v0);
+      bool bad = !is_pos_normal(v0);                                      // poisoned state: reported through the NaN flag
+      // ---- mhYg (Pr:250-333)
+      const double yp = y0 + ty * z;                                     // Pr:257
+      const double tp = gl * fexp_nb(yp, T.exp_t);                       // U:157
+      const bool saturated = __all_sync(__activemask(), !live || tp * H.alpha_min >= 37.5);
+      const double Ap = saturated ? (mask ? -INFINITY : 0.0) : detect_logsum<RT>(H, T, mask, tp);
+      const double t0 = xbar - y0, t1 = xbar - yp;
+      const double D0 = fma(nd_d * t0, t0, ss), Dp = fma(nd_d * t1, t1, ss);
+      const double dLX = times_beta(H, (Ap - A0) - 0.5 * (Dp - D0) * rv);
+      const double q0 = vg_q(H, lv, y0), qp = vg_q(H, lv, yp);
+      const double dPV = -0.5 * (qp * qp - q0 * q0);
+      const bool act0 = (f & F_ACTIVE) != 0;
+      const int k0 = flag_k(f) - 1;
+      const double m2 = act0 ? H.am[k0] : H.im, i2 = act0 ? H.inv2av[k0] : H.inv2iv;
+      const double e0 = y0 - m2, e1 = yp - m2;
+      const double dL2 = -(e1 * e1 * i2 - e0 * e0 * i2);
+      const double ratio_y = H.temp * (dLX + dL2 + dPV);                 // Pr:296
+      const bool acc_y = live && (flog_nb(u_y, T.log_t) < ratio_y);      // Pr:302
+      const double y1 = acc_y ? yp : y0, A1 = acc_y ? Ap : A0, D1 = acc_y ? Dp : D0, q1 = acc_y ? qp : q0;
+      // ---- mhVariance_g (Pr:7-56)
+      const double arg = tv * (u1 - 0.5);                                // MP:5
+      const double sf = fexp_nb(arg, T.exp_t), vp = v0 * sf, rvp = rv * fexp_nb(-arg, T.exp_t);
+      const double dB = -nd_d * (0.5 * arg) - 0.5 * D1 * (rvp - rv);
+      const double qv = q1 + arg * H.irt;
+      double ratio_v = H.temp * (times_beta(H, dB) + (-arg - 0.5 * (qv * qv - q1 * q1))) + arg;   // Pr:24
+      if (!(A1 > -INFINITY) && H.beta != 0.0) ratio_v = NAN;             // -Inf current likelihood: as the reference, NaN => reject
+      const bool acc_v = live && (flog_nb(u2, T.log_t) < ratio_v);       // Pr:35
+      const double v1 = acc_v ? vp : v0, lv1 = acc_v ? lv + arg : lv, rv1 = acc_v ? rvp : rv;
+      // ---- gibbsAllocationActiveInactive + WithinActive (Pr:335-410)
+      const double dI = y1 - H.im;
+      const double L0 = live ? H.c0 * fexp_nb(-(dI * dI) * H.inv2iv, T.exp_t) : H.sp;
+      double Lk[KT], L1 = 0;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) { const double d = y1 - H.am[k]; Lk[k] = H.ck[k] * fexp_nb(-(d * d) * H.inv2av[k], T.exp_t); L1 += Lk[k]; }
+      const double num = live ? H.wa * L1 : 0.0, den = H.one_m_wa * L0 + num;
+      double pa = num * frcp_nb(den);                                    // Pr:348
+      if (!is_pos_normal(den)) { pa = num / den; if (isnan(pa)) pa = H.wa; }   // Pr:349 (rare)
+      const bool a_new = (f & F_PINNED) || (u_ai < pa);                  // Pr:353-355
+      const double thr = u_w * L1;
+      double cum = 0; int cnt = 0;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) { cum += Lk[k]; cnt += (cum < thr); } // Pr:398-402
+      const int kn = cnt + 1 > KT ? KT : cnt + 1;
+      const bool row_ok = L1 > 0 && L1 < INFINITY;                       // NaN rows keep the old k, Pr:403
+      f = (f & ~F_ACTIVE) | (a_new ? F_ACTIVE : 0u);
+      if (a_new && row_ok) f = flag_set_k(f, kn);
+      // ---- caches, stores
+      double xglik = times_beta(H, A1 + (-nd_d * (LN_SQRT_2PI + 0.5 * lv1) - 0.5 * D1 * rv1));
+      double vgprob = vg_prior_from_q(H, lv1, vg_q(H, lv1, y1));
+      a.flags[i] = (uint16_t)f;
+      if (live) { a.Yg[i] = y1; a.vg[i] = v1; fa.lps[i] = A1; a.xglik[i] = xglik; a.vgprob[i] = vgprob; }
+      else {
+        xglik = times_beta(H, (f & F_ALLZERO) ? 0.0 : -INFINITY);        // P:117
+        if (fa.want_stats && (f & F_ALLZERO)) xglik = a.xglik[i];        // the cache as the last spike move left it
+      }
+      if (a.tune && live) {                                              // Pr:312-322, Pr:40-50
+        ulonglong2 w = a.win_y[i]; window_push(w, acc_y); a.win_y[i] = w;
+        w = a.win_v[i]; window_push(w, acc_v); a.win_v[i] = w;
+      }
+      saw_nan |= live && (isnan(ratio_y) || isnan(ratio_v) || bad);
+      double ys = y1, lvs = lv1;
+      bool finite_state = isfinite(y1) && isfinite(v1);
+      if ((f & F_ALLZERO) && fa.do_spike_move) {
+        SpikeOut so;
+        spike_move<RT>(H, T, fa, chain, g, i, so);
+        ys = so.y; lvs = so.lv; f = so.f; xglik = so.xglik; vgprob = so.vgprob; finite_state = so.finite_state;
+      }
+      if (fa.want_stats) stats_add<SWEEP_BLOCK>(acc, a.K, true, ys, lvs, f, xglik, vgprob, finite_state);
+      continue;
+    }
     FastGene gn;
     gn.y = a.Yg[i]; gn.v = a.vg[i]; gn.A = fa.lps[i]; gn.f = a.flags[i];
     GeneData gd;
@@ -871,33 +959,33 @@ int ensure_lps(zz_handle *h, bool rebuild_allzero_xglik = false) {
   return ZZ_OK;
 }
 
-#define ZZ_DISPATCH_SWEEP(h, prod, grid, smem, args)                                             \
+#define ZZ_SWEEP_CASE_R(h, PRODV, KTV, grid, smem, args)                                         \
+  switch ((h)->R) {                                                                              \
+    case 2: k_sweep_fast<2, PRODV, KTV><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;   \
+    case 4: k_sweep_fast<4, PRODV, KTV><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;   \
+    case 8: k_sweep_fast<8, PRODV, KTV><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;   \
+    case 16: k_sweep_fast<16, PRODV, KTV><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break; \
+    default: k_sweep_fast<0, PRODV, KTV><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;  \
+  }
+// kt: 0 = generic tile (explicit draws / decisions / move subsets / finite variance bound / K > 3), 1..3 = straight-line tile
+#define ZZ_DISPATCH_SWEEP(h, prod, kt, grid, smem, args)                                         \
   do {                                                                                           \
-    if (prod) {                                                                                  \
-      switch ((h)->R) {                                                                          \
-        case 2: k_sweep_fast<2, true><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;          \
-        case 4: k_sweep_fast<4, true><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;          \
-        case 8: k_sweep_fast<8, true><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;          \
-        case 16: k_sweep_fast<16, true><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;        \
-        default: k_sweep_fast<0, true><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;         \
-      }                                                                                          \
-    } else {                                                                                     \
-      switch ((h)->R) {                                                                          \
-        case 2: k_sweep_fast<2, false><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;         \
-        case 4: k_sweep_fast<4, false><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;         \
-        case 8: k_sweep_fast<8, false><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;         \
-        case 16: k_sweep_fast<16, false><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;       \
-        default: k_sweep_fast<0, false><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;        \
-      }                                                                                          \
-    }                                                                                            \
+    if ((kt) == 1) { ZZ_SWEEP_CASE_R(h, true, 1, grid, smem, args) }                             \
+    else if ((kt) == 2) { ZZ_SWEEP_CASE_R(h, true, 2, grid, smem, args) }                        \
+    else if ((kt) == 3) { ZZ_SWEEP_CASE_R(h, true, 3, grid, smem, args) }                        \
+    else if (prod) { ZZ_SWEEP_CASE_R(h, true, 0, grid, smem, args) }                             \
+    else { ZZ_SWEEP_CASE_R(h, false, 0, grid, smem, args) }                                      \
   } while (0)
 
-// resident CTAs of the persistent sweep kernel on this device (blocks per SM from the occupancy calculator x SM count)
 template <int RT> void allow_big_smem(int bytes) {
-  cudaFuncSetAttribute(k_sweep_fast<RT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  cudaFuncSetAttribute(k_sweep_fast<RT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k_sweep_fast<RT, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k_sweep_fast<RT, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k_sweep_fast<RT, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k_sweep_fast<RT, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k_sweep_fast<RT, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
+// resident CTAs of the persistent sweep kernel on this device (blocks per SM from the occupancy calculator x SM count)
 int persistent_blocks(zz_handle *h, size_t smem) {
   if (h->persist_blocks > 0) return h->persist_blocks;
   int per_sm = 0, sms = 0;
@@ -912,11 +1000,11 @@ int persistent_blocks(zz_handle *h, size_t smem) {
     }
   }
   switch (h->R) {
-    case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<2, true>, SWEEP_BLOCK, smem); break;
-    case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<4, true>, SWEEP_BLOCK, smem); break;
-    case 8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<8, true>, SWEEP_BLOCK, smem); break;
-    case 16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<16, true>, SWEEP_BLOCK, smem); break;
-    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<0, true>, SWEEP_BLOCK, smem); break;
+    case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<2, true, 0>, SWEEP_BLOCK, smem); break;
+    case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<4, true, 0>, SWEEP_BLOCK, smem); break;
+    case 8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<8, true, 0>, SWEEP_BLOCK, smem); break;
+    case 16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<16, true, 0>, SWEEP_BLOCK, smem); break;
+    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<0, true, 0>, SWEEP_BLOCK, smem); break;
   }
   if (e != cudaSuccess || per_sm < 1) per_sm = 2;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device) != cudaSuccess || sms < 1) sms = 148;
@@ -956,7 +1044,15 @@ int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, con
   }
   const bool prod = !draws_dev[0] && !draws_dev[2] && !draws_dev[4] && !draws_dev[6] && !dec_dev[0] && !dec_dev[1] && !dec_dev[2] && !dec_dev[3];
   if (dec_dev[3] && (moves & ZZ_MOVE_SPIKE)) ZZ_CUDA(h, cudaMemsetAsync(dec_dev[3], 0, (size_t)h->C * h->G, h->stream));
-  ZZ_DISPATCH_SWEEP(h, prod, dim3((unsigned)per_chain, (unsigned)h->C), smem, fa);
+  int kt = 0;
+  if (prod && (moves & ~ZZ_MOVE_REFERENCE_ORDER) == ZZ_MOVE_FUSED && h->K <= 3) {
+    kt = h->K;
+    for (int c = 0; c < h->C; ++c) if (h->hyper_host[c].variance_g_upper_bound != INFINITY) kt = 0;
+  }
+#ifdef ZZ_NO_STRAIGHT_TILE
+  kt = 0;
+#endif
+  ZZ_DISPATCH_SWEEP(h, prod, kt, dim3((unsigned)per_chain, (unsigned)h->C), smem, fa);
   ZZ_LAUNCHED(h);
   if (full) { h->stats_fresh = true; h->sw_rows = fa.rows_per_chain; }
   return ZZ_OK;
