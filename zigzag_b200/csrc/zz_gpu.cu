@@ -298,6 +298,16 @@ __device__ __noinline__ void spike_move(const FastH &H, const MathTabs &T, const
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
+// cp.async of one lane's ten input words of gene slot g (chain `chain`) into its staging column `stg` ([slot * 32])
+__device__ __forceinline__ void stage_tile(const SweepArgs &a, const FastArgs &fa, int chain, int64_t g, double *stg) {
+  const int64_t i = (int64_t)chain * a.G + g;
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stg);
+  const void *src[9] = {a.Yg + i, a.vg + i, fa.lps + i, a.ty + i, a.tv + i, a.gl + g, fa.xbar + g, fa.xss + g, fa.nd_mask + g};
+#pragma unroll
+  for (int j = 0; j < 9; ++j) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + j * 256), "l"(src[j]) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 9 * 256), "l"(a.perm + g) : "memory");
+}
+
 // KT > 0 selects the straight-line production tile (all four moves, Philox draws, variance_g_upper_bound = Inf, K = KT active
 // components): every lane executes the same branch-free instruction stream (decisions are applied with selects), which lets
 // the scheduler overlap the independent exp/log/reciprocal chains of the three moves instead of serialising them.
@@ -316,32 +326,32 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const
   const int64_t ntiles = (n + 31) / 32;
   const int64_t warp0 = (int64_t)blockIdx.x * (SWEEP_BLOCK / 32) + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * (SWEEP_BLOCK / 32);
   bool saw_nan = false;
-  // Tiles are taken from the END of the sorted gene order first: the all-zero genes (extra spike move) and the weakly
-  // expressed genes (full detection loop) run while every warp is busy; the last, partially filled round consists of
-  // highly expressed tiles whose detection term is saturated, which keeps the tail short.
-  for (int64_t t_ = warp0; t_ < ntiles; t_ += nwarps) {
-    const int64_t tile = ntiles - 1 - t_;
-    const int64_t g = a.g_begin + tile * 32 + lane;
-#ifndef ZZ_NO_PREFETCH
-    {   // pull the next tile's inputs towards L1 while this tile computes (no registers, no shared memory)
-      const int64_t gn_ = g - nwarps * 32;
-      if (gn_ >= a.g_begin && gn_ < a.g_end) {
-        const int64_t in_ = (int64_t)chain * a.G + gn_;
-        prefetch_l1(a.Yg + in_); prefetch_l1(a.vg + in_); prefetch_l1(fa.lps + in_); prefetch_l1(a.ty + in_); prefetch_l1(a.tv + in_);
-        prefetch_l1(fa.nd_mask + gn_); prefetch_l1(fa.xbar + gn_); prefetch_l1(fa.xss + gn_); prefetch_l1(a.gl + gn_);
-        if ((lane & 3) == 0) prefetch_l1(a.flags + in_);
-      }
+  if constexpr (KT > 0) {
+    // per-warp staging slots [10][32] doubles behind the statistic columns: Yg, variance_g, lps, tuning parameters, gene length,
+    // xbar, ss, nd_mask, perm of the warp's NEXT tile arrive by cp.async while the current tile computes
+    double *stg = acc + (int64_t)nstat * SWEEP_BLOCK + (threadIdx.x >> 5) * 320 + lane;
+    uint32_t f_next = 0;
+    {
+      const int64_t g0 = a.g_begin + (ntiles - 1 - warp0) * 32 + lane;
+      if (warp0 < ntiles && g0 < a.g_end) { stage_tile(a, fa, chain, g0, stg); f_next = a.flags[(int64_t)chain * a.G + g0]; }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
-#endif
-    if (g >= a.g_end) continue;
-    const int64_t i = (int64_t)chain * a.G + g;
-    const uint64_t gid = (uint64_t)(a.gene_offset + a.perm[g]);
-    if constexpr (KT > 0) {
+    for (int64_t t_ = warp0; t_ < ntiles; t_ += nwarps) {
+      const int64_t tile = ntiles - 1 - t_;
+      const int64_t g = a.g_begin + tile * 32 + lane;
+      const int64_t i = (int64_t)chain * a.G + g;
+      if (g >= a.g_end) { asm volatile("cp.async.wait_group 0;" ::: "memory"); continue; }
       // ---------------- straight-line production tile ----------------
-      const double y0 = a.Yg[i], v0 = a.vg[i], A0 = fa.lps[i], ty = a.ty[i], tv = a.tv[i], gl = a.gl[g];
-      const double xbar = fa.xbar[g], ss = fa.xss[g];
-      const uint64_t mask = fa.nd_mask[g];
-      uint32_t f = a.flags[i];
+      asm volatile("cp.async.wait_group 0;" ::: "memory");            // this lane's copies of the current tile have landed
+      const double y0 = stg[0 * 32], v0 = stg[1 * 32], A0 = stg[2 * 32], ty = stg[3 * 32], tv = stg[4 * 32], gl = stg[5 * 32];
+      const double xbar = stg[6 * 32], ss = stg[7 * 32];
+      const uint64_t mask = (uint64_t)__double_as_longlong(stg[8 * 32]);
+      const uint64_t gid = (uint64_t)(a.gene_offset + (int64_t)(uint32_t)__double2loint(stg[9 * 32]));
+      uint32_t f = f_next;
+      const int64_t t_n = t_ + nwarps;
+      const int64_t g_n = a.g_begin + (ntiles - 1 - t_n) * 32 + lane;
+      const bool next_valid = t_n < ntiles && g_n < a.g_end;
+      if (next_valid) f_next = a.flags[(int64_t)chain * a.G + g_n];     // plain load, consumed one tile later
       const double nd_d = (double)((RT > 0 ? RT : H.R) - __popcll(mask));
       const bool live = !(f & F_INSPIKE);
       uint32_t b0[4], b1[4];
@@ -351,6 +361,10 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const
       const double u_ai = u32_to_open01(b1[1]), u_w = u32_to_open01(b1[2]);
       const double z = fsqrt_nb(-2.0 * flog_nb(u32_to_open01(b0[0]), T.log_t)) * cospi(2.0 * u32_to_open01(b0[1]));
       const double lv = flog_nb(v0, T.log_t), rv = frcp_nb(v0);
+      // every staged word of this tile has been consumed (z, lv depend on them): refill the slots with the warp's next tile, whose
+      // HBM latency then hides behind this tile's ~1600 instructions
+      if (next_valid) stage_tile(a, fa, chain, g_n, stg);
+      asm volatile("cp.async.commit_group;" ::: "memory");
       bool bad = !is_pos_normal(v0);                                      // poisoned state: reported through the NaN flag
       // ---- mhYg (Pr:250-333)
       const double yp = y0 + ty * z;                                     // Pr:257
@@ -419,8 +433,28 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const
         ys = so.y; lvs = so.lv; f = so.f; xglik = so.xglik; vgprob = so.vgprob; finite_state = so.finite_state;
       }
       if (fa.want_stats) stats_add<SWEEP_BLOCK>(acc, a.K, true, ys, lvs, f, xglik, vgprob, finite_state);
-      continue;
     }
+  } else {
+  // Tiles are taken from the END of the sorted gene order first: the all-zero genes (extra spike move) and the weakly
+  // expressed genes (full detection loop) run while every warp is busy; the last, partially filled round consists of
+  // highly expressed tiles whose detection term is saturated, which keeps the tail short.
+  for (int64_t t_ = warp0; t_ < ntiles; t_ += nwarps) {
+    const int64_t tile = ntiles - 1 - t_;
+    const int64_t g = a.g_begin + tile * 32 + lane;
+#ifndef ZZ_NO_PREFETCH
+    {   // pull the next tile's inputs towards L1 while this tile computes (no registers, no shared memory)
+      const int64_t gn_ = g - nwarps * 32;
+      if (gn_ >= a.g_begin && gn_ < a.g_end) {
+        const int64_t in_ = (int64_t)chain * a.G + gn_;
+        prefetch_l1(a.Yg + in_); prefetch_l1(a.vg + in_); prefetch_l1(fa.lps + in_); prefetch_l1(a.ty + in_); prefetch_l1(a.tv + in_);
+        prefetch_l1(fa.nd_mask + gn_); prefetch_l1(fa.xbar + gn_); prefetch_l1(fa.xss + gn_); prefetch_l1(a.gl + gn_);
+        if ((lane & 3) == 0) prefetch_l1(a.flags + in_);
+      }
+    }
+#endif
+    if (g >= a.g_end) continue;
+    const int64_t i = (int64_t)chain * a.G + g;
+    const uint64_t gid = (uint64_t)(a.gene_offset + a.perm[g]);
     FastGene gn;
     gn.y = a.Yg[i]; gn.v = a.vg[i]; gn.A = fa.lps[i]; gn.f = a.flags[i];
     GeneData gd;
@@ -489,6 +523,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const
       if (!PROD && a.dec[3]) a.dec[3][i] = (uint8_t)so.acc;
     }
     if (fa.want_stats) stats_add<SWEEP_BLOCK>(acc, a.K, true, gn.y, gn.lv, gn.f, xglik, vgprob, finite_state);
+  }
   }
   if (saw_nan) atomicOr(a.nan_flag, 1);
   if (fa.want_stats) {
@@ -1023,9 +1058,9 @@ int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, con
   fill_fast_args(h, fa);
   const bool full = (g_begin == 0 && g_end == h->G);
   const int nstat = zz_suffstats_len(h->K);
-  const size_t smem = full ? sizeof(double) * nstat * SWEEP_BLOCK : 0;
+  size_t smem = full ? sizeof(double) * nstat * SWEEP_BLOCK : 0;
   const int64_t ntiles = (g_end - g_begin + 31) / 32;
-  int64_t per_chain = (persistent_blocks(h, sizeof(double) * nstat * SWEEP_BLOCK) + h->C - 1) / h->C;
+  int64_t per_chain = (persistent_blocks(h, sizeof(double) * (nstat + 10) * SWEEP_BLOCK) + h->C - 1) / h->C;
   const int64_t need = (ntiles + SWEEP_BLOCK / 32 - 1) / (SWEEP_BLOCK / 32);
   if (per_chain > need) per_chain = need;
   if (per_chain < 1) per_chain = 1;
@@ -1052,6 +1087,7 @@ int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, con
 #ifdef ZZ_NO_STRAIGHT_TILE
   kt = 0;
 #endif
+  if (kt > 0) smem = sizeof(double) * (nstat + 10) * SWEEP_BLOCK;   // statistic columns + per-warp staging slots
   ZZ_DISPATCH_SWEEP(h, prod, kt, dim3((unsigned)per_chain, (unsigned)h->C), smem, fa);
   ZZ_LAUNCHED(h);
   if (full) { h->stats_fresh = true; h->sw_rows = fa.rows_per_chain; }
