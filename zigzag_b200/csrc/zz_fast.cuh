@@ -39,6 +39,10 @@ struct FastH {   // one chain's hyper-parameters + hoisted gene-independent sub-
   double alpha_min;                       // min_r alpha_r: t * alpha_min >= 37.5 => every p_x == 1 exactly
   double alpha[ZZ_MAX_LIBS];
   double alpha2[ZZ_MAX_LIBS];             // alpha_r * log2(e): the detection exponent in base 2 (fexp2_neg_clamped)
+  double am256[ZZ_MAX_LIBS];              // -256 alpha_r log2(e) (det_term)
+  double t_clamp;                         // 1010 / max_r alpha2_r: t <= t_clamp keeps every 2^(-t alpha2_r) normal (det_term)
+  int one_hi;                             // 0x3FF00000 (opaque_one_hi)
+  int uclamp_ok;                          // max alpha <= 16 min alpha: one clamp of t serves every library (detect_logsum_sl)
   double am[ZZ_MAX_COMP], inv2av[ZZ_MAX_COMP], ck[ZZ_MAX_COMP];  // ck = w_k / (sqrt2pi * sqrt(av_k))           (Pr:344)
 };
 
@@ -58,7 +62,16 @@ __device__ __forceinline__ void derive_fast(FastH &H, const zz_hyper *__restrict
   H.beta = (hy->beta < 0.0000001) ? 0.0 : hy->beta;   // P:121-125: beta < 1e-7 => likelihood 0
   H.temp = hy->temperature; H.vub = hy->variance_g_upper_bound;
   H.alpha_min = INFINITY;
-  for (int r = 0; r < ZZ_MAX_LIBS; ++r) { H.alpha[r] = hy->alpha_r[r]; H.alpha2[r] = hy->alpha_r[r] * ZZ_KLOG2E; if (r < H.R && !(hy->alpha_r[r] >= H.alpha_min)) H.alpha_min = hy->alpha_r[r]; }
+  double a2max = 0, amax = 0;
+  for (int r = 0; r < ZZ_MAX_LIBS; ++r) {
+    H.alpha[r] = hy->alpha_r[r]; H.alpha2[r] = hy->alpha_r[r] * ZZ_KLOG2E; H.am256[r] = -256.0 * H.alpha2[r];
+    if (r < H.R && !(hy->alpha_r[r] >= H.alpha_min)) H.alpha_min = hy->alpha_r[r];
+    if (r < H.R && H.alpha2[r] > a2max) a2max = H.alpha2[r];
+    if (r < H.R) amax = fmax(amax, hy->alpha_r[r]);
+  }
+  H.t_clamp = 1010.0 / a2max;
+  H.one_hi = 0x3FF00000;
+  H.uclamp_ok = (H.alpha_min > 0 && amax <= 16 * H.alpha_min) ? 1 : 0;   // same test as the host's kernel choice (launch_sweep_fast)
   for (int k = 0; k < ZZ_MAX_COMP; ++k) {
     H.am[k] = hy->active_means[k];
     H.inv2av[k] = 1.0 / (2 * hy->active_variances[k]);
@@ -97,11 +110,31 @@ __device__ __forceinline__ double sqdist(const GeneData &d, double y) {   // D(y
   return fma((double)d.ndet * t, t, d.ss);
 }
 
+// A(y) through det_term: exponent parts summed as integers, the undetected complement as a
+// predicated subtraction, one clamp of t instead of one per library.  Requires max alpha <= 16 min alpha (checked by the
+// host before this kernel is chosen): then t_clamp * alpha2_r >= 1010/16 > 54 for every r, so a clamped t yields p_x == 1
+// exactly where the unclamped one does.
+template <int RT>
+__device__ __forceinline__ double detect_logsum_sl(const FastH &H, const MathTabs &T, uint64_t nd_mask, double t) {
+  static_assert(RT > 0 && RT <= 18, "the zero test below needs <= 18 terms");
+  const double tc = fmin(t, H.t_clamp);                                 // +Inf clamps too
+  const uint32_t mlo = (uint32_t)nd_mask;
+  const int one_hi = opaque_one_hi(&H.one_hi);
+  double fsum = 0; int ksum = -1023 * RT;
+#pragma unroll
+  for (int r = 0; r < RT; ++r) det_term(tc, H.am256[r], mlo & (1u << r), T, fsum, ksum, one_hi);
+  const double A = fma((double)ksum, ZZ_KLN2, fsum);
+  return A < -700.0 ? -INFINITY : A;
+}
+
 // A(y) = sum_r log(nd_r ? 1 - p_r : p_r),  p_r = 1 - exp(-t alpha_r),  t = gl * exp(y)     (U:157, P:82-84)
 template <int RT>
 __device__ __forceinline__ double detect_logsum(const FastH &H, const MathTabs &T, uint64_t nd_mask, double t) {
   const int R = RT > 0 ? RT : H.R;
   double A = 0;
+  // every path that produces A(y) for the same hyper-parameters must use the same arithmetic (the value is cached in `lps`
+  // and compared bit for bit across kernels): det_term whenever it is applicable
+  if constexpr (RT > 0 && RT <= 18) { if (H.uclamp_ok) return detect_logsum_sl<RT>(H, T, nd_mask, t); }
   if (RT > 0 && RT <= 18) {
     // q is +0 or a normal number in [2^-53, 1].  flog_core(+0) returns -1023 ln 2 = -709.1 instead of -Inf, while a sum of
     // at most 18 legitimate terms is >= 18 log(2^-53) = -661.3: "A < -700" therefore detects a zero q exactly, without a

@@ -49,11 +49,26 @@ ZZ_HD double d_make(int hi, int lo) {
 #define ZZ_E4_IMM 0x1.55555p-5    /* 1/24  (error * r^4 < 1e-19) */
 #define ZZ_L5_IMM 0x1.9999ap-3    /* 1/5   (error * r^5 < 1e-20 for |r| <= 2^-9) */
 #define ZZ_P4_IMM 0x1.3b2abp-7    /* ln2^4/24 (error * r^4 < 1e-19 for |r| <= 2^-9) */
+#define ZZ_Q4_IMM 0x1.3b2abp-39   /* the same coefficient for r in units of 1/256 (det_term) */
 
 struct MathTabs {          // lives in shared memory on the device
-  double exp_t[256];       // 2^(j/256)
+  double exp_t[256];       // 2^(j/256) with the high word biased by -(j << 12): only meaningful through scale_tab()
   double2 log_t[512];      // {IC[i], LC[i]}
 };
+
+// 2^(n/256) = 2^k * 2^(j/256), n = 256 k + j: the table entry's high word carries -(j << 12), so adding (n << 12) =
+// (k << 20) + (j << 12) restores the mantissa and adds k to the exponent field in ONE integer instruction, off the
+// critical path of the polynomial (valid while the result is a normal number)
+ZZ_HD double scale_tab(const double *__restrict__ exp_t, int n) {
+#if defined(__CUDA_ARCH__)
+  int j;
+  asm("and.b32 %0, %1, 255;" : "=r"(j) : "r"(n));      // opaque to the optimiser: keeps (n & 255) separate so that the address
+  const double tj = exp_t[j];                          // is ONE lea (base + (j << 3)) instead of shl + and + add
+#else
+  const double tj = exp_t[n & 255];
+#endif
+  return d_make(d_hi(tj) + (int)((unsigned)n << 12), d_lo(tj));
+}
 
 // exp(x) for -708 <= x <= 709 (callers clamp or take the libm path outside).  9 FP64 instructions.
 ZZ_HD double fexp_core(double x, const double *__restrict__ exp_t) {
@@ -67,8 +82,7 @@ ZZ_HD double fexp_core(double x, const double *__restrict__ exp_t) {
   p = fma(r, p, 0.5);
   p = fma(r, p, 1.0);                                 // (the economised linear coefficient is 1 - 8.9e-15: taken as 1, error 1e-17)
   p = fma(r, p, 1.0);
-  const double s = exp_t[n & 255] * p;
-  return d_make(d_hi(s) + ((n >> 8) << 20), d_lo(s)); // * 2^k by exponent-field addition (result is normal here)
+  return scale_tab(exp_t, n) * p;                     // 2^k T[j] is exact, the product is normal here
 }
 
 // libm fallbacks, kept out of line so the (rare) special cases do not bloat the unrolled loops
@@ -122,8 +136,7 @@ ZZ_HD double fexp2_neg_clamped(double b, const double *__restrict__ exp_t) {
   p = fma(r, p, ZZ_KP2);
   p = fma(r, p, ZZ_KP1);
   p = fma(r, p, 1.0);
-  const double s = exp_t[n & 255] * p;
-  return d_make(d_hi(s) + ((n >> 8) << 20), d_lo(s));
+  return scale_tab(exp_t, n) * p;
 }
 
 // log(x) for positive normal finite x.  8 FP64 instructions + one int->double conversion.
@@ -140,6 +153,47 @@ ZZ_HD double flog_core(double x, const double2 *__restrict__ log_t) {
   s = fma(r, s, -0.5);
   const double lo = fma(r2, s, r);
   return fma((double)k, ZZ_KLN2, tc.y) + lo;           // (double)k: I2F on the otherwise idle XU pipe
+}
+
+#if defined(__CUDACC__)
+// 0x3FF00000 read back from shared memory: a value neither the compiler nor ptxas can fold into an immediate, so it
+// stays in a register for the whole tile (see det_term)
+__device__ __forceinline__ int opaque_one_hi(const volatile int *slot) { return *slot; }
+#endif
+
+// One library's detection term for the straight-line tile:  log(q),  q = undetected ? 1 - p : p,  p = 1 - 2^(-t a),
+// a = alpha_r log2(e), passed as am256 = -256 a.  The caller clamps t so that t a <= 1010 for every library (then 2^(-t a)
+// is a normal number; beyond 54 the value no longer matters because p rounds to 1).  Returns nothing: the term is
+// delivered as  log q = (kraw - 1023) ln 2 + frac  with `kraw` ADDED to the integer `ksum` and `frac` to the double `fsum`,
+// so the exponent parts of all libraries are summed as integers and converted once (saves an I2F and an fma per library).
+// q = +0 (log = -Inf) leaves kraw = 0 and frac = 0: the sum then lies below -709 + (R-1)*0, which no legitimate sum of
+// <= 18 terms (each >= log 2^-53) can reach — the caller tests that instead of every q.
+// 18 FP64 instructions, ~11 integer/select, 2 shared-memory reads.
+// `one_hi` must be 0x3FF00000; callers on the device pass it in a register (opaque_one_hi) so that the mantissa re-bias is one
+// LOP3 (and-immediate, or-register) instead of two.
+ZZ_HD void det_term(double t, double am256, unsigned undetected, const MathTabs &T, double &fsum, int &ksum, int one_hi = 0x3FF00000) {
+  const double magic = 6755399441055744.0;
+  const double w = fma(t, am256, magic);               // low word: n = rint(-256 t a)
+  const int n = d_lo(w);
+  const double nd = w - magic;
+  const double r = fma(t, am256, -nd);                 // -256 t a - n from the exact product: |r| <= 1/2 (units of 1/256)
+  double p = fma(r, ZZ_Q4_IMM, ZZ_KQ3);                // 2^(r/256) = 1 + r (Q1 + r (Q2 + r (Q3 + r Q4)))
+  p = fma(r, p, ZZ_KQ2);
+  p = fma(r, p, ZZ_KQ1);
+  p = fma(r, p, 1.0);
+  const double e = scale_tab(T.exp_t, n) * p;          // 2^(-t a)
+  double q = 1.0 - e;                                  // p_x (U:157)
+  if (undetected) q = 1.0 - q;                         // 1 - p_x as the reference forms it (P:84), not e itself
+  const int hi = d_hi(q);
+  ksum += (hi + 0x00096000) >> 20;
+  const double m = d_make((hi & 0x000FFFFF) | one_hi, d_lo(q));
+  const double2 tc = T.log_t[(hi >> 11) & 511];
+  const double x = fma(m, tc.x, -1.0);
+  const double x2 = x * x;
+  double s = fma(x, ZZ_L5_IMM, -0.25);
+  s = fma(x, s, 1.0 / 3);
+  s = fma(x, s, -0.5);
+  fsum += tc.y + fma(x2, s, x);
 }
 
 ZZ_HD double flog(double x, const double2 *__restrict__ log_t) {

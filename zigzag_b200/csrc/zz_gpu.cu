@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const
       const double yp = y0 + ty * z;                                     // Pr:257
       const double tp = gl * fexp_nb(yp, T.exp_t);                       // U:157
       const bool saturated = __all_sync(__activemask(), !live || tp * H.alpha_min >= 37.5);
-      const double Ap = saturated ? (mask ? -INFINITY : 0.0) : detect_logsum<RT>(H, T, mask, tp);
+      const double Ap = saturated ? (mask ? -INFINITY : 0.0) : detect_logsum_sl<(RT > 0 && RT <= 18) ? RT : 1>(H, T, mask, tp);
       const double t0 = xbar - y0, t1 = xbar - yp;
       const double D0 = fma(nd_d * t0, t0, ss), Dp = fma(nd_d * t1, t1, ss);
       const double dLX = times_beta(H, (Ap - A0) - 0.5 * (Dp - D0) * rv);
@@ -1082,7 +1082,14 @@ int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, con
   int kt = 0;
   if (prod && (moves & ~ZZ_MOVE_REFERENCE_ORDER) == ZZ_MOVE_FUSED && h->K <= 3) {
     kt = h->K;
-    for (int c = 0; c < h->C; ++c) if (h->hyper_host[c].variance_g_upper_bound != INFINITY) kt = 0;
+    if (h->R != 2 && h->R != 4 && h->R != 8 && h->R != 16) kt = 0;     // detect_logsum_sl is unrolled over the library count
+    for (int c = 0; c < h->C; ++c) {
+      const zz_hyper &hy = h->hyper_host[c];
+      if (hy.variance_g_upper_bound != INFINITY) kt = 0;
+      double amin = INFINITY, amax = 0;
+      for (int r = 0; r < h->R; ++r) { amin = fmin(amin, hy.alpha_r[r]); amax = fmax(amax, hy.alpha_r[r]); }
+      if (!(amin > 0 && amax <= 16 * amin)) kt = 0;                    // FastH::uclamp_ok: single clamp of t in detect_logsum_sl
+    }
   }
 #ifdef ZZ_NO_STRAIGHT_TILE
   kt = 0;
