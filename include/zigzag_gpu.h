@@ -173,9 +173,14 @@ int zz_nan_flag(zz_handle *h, int *flag);                        /* replaces the
 
 /* ---- host-buffer round trip (bench.py `e2e`) ---------------------------------------------------------------- */
 /* One fused sweep where the mutable per-gene state lives in HOST arrays, as it does in the R object between .Call()s:
-   uploads Yg, variance_g, tuning parameters and allocations, runs zz_sweep, downloads the updated state including the two caches
-   (XgLikelihood / variance_g_probability are outputs only: they are functions of the uploaded state).  Xg and gene_lengths stay
-   resident from zz_upload_data.  Chain 0 only.  Bytes moved are returned in h2d_bytes / d2h_bytes. */
+   takes Yg, variance_g, tuning parameters and allocations from the host arrays, runs zz_sweep, returns the updated state including
+   the two caches (XgLikelihood / variance_g_probability are outputs only: they are functions of the uploaded state).  Xg and
+   gene_lengths stay resident from zz_upload_data; the handle's resident state ends up equal to the returned arrays, so resident
+   calls can follow.  Chain 0 only.  Two transfer paths, same results bit for bit:
+     * all nine arrays in pinned, device-mapped host memory (cudaHostAlloc / cudaHostRegister, torch pin_memory()): ONE kernel
+       reads the arrays over PCIe, sweeps and writes them back — no staging copies, both PCIe directions busy at once;
+     * otherwise: staged cudaMemcpyAsync in chunks of ~256K genes on three streams (copy in / sweep / copy out overlap).
+   Bytes moved are returned in h2d_bytes / d2h_bytes (44 bytes per gene each way). */
 int zz_sweep_host(zz_handle *h, uint64_t step, int tune, double *Yg, double *variance_g, int32_t *alloc_active_inactive,
                   int32_t *alloc_within_active, int32_t *inactive_spike_allocation, double *XgLikelihood,
                   double *variance_g_probability, const double *tuningParam_yg, const double *tuningParam_variance_g,

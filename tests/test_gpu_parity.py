@@ -374,24 +374,40 @@ def test_batched_chains_are_independent_and_match_oracle():
     assert not np.array_equal(dec[0, 0], dec[0, 1])
 
 
-def test_sweep_host_round_trip_equals_resident_sweep():
+@pytest.mark.parametrize("mode", ["pageable", "pageable_3chunks", "pinned_zero_copy", "pinned_staged"])
+def test_sweep_host_round_trip_equals_resident_sweep(mode, monkeypatch):
+    """zz_sweep_host (state in host arrays, up and down every call) leaves exactly what the resident sweep leaves, on each of its
+    transfer paths: staged copies in one or several pipelined chunks, and the single kernel that reads / writes pinned host memory."""
+    import torch
     G, R = 4000, 4
     X, gl, hd, ho, hg, s, h = setup_pair(G, R, 17)
     h2 = gpu_handle(X, gl, hg, s)
-    host = {k: getattr(s, k).copy() for k in ("Yg", "variance_g", "alloc_active_inactive", "alloc_within_active",
-                                             "inactive_spike_allocation", "XgLikelihood", "variance_g_probability",
-                                             "tuningParam_yg", "tuningParam_variance_g")}
+    if mode == "pageable_3chunks":
+        monkeypatch.setenv("ZZ_HOST_CHUNKS", "3")
+    if mode == "pinned_staged":
+        monkeypatch.setenv("ZZ_HOST_NO_ZEROCOPY", "1")
+        monkeypatch.setenv("ZZ_HOST_CHUNKS", "2")
+    keys = ("Yg", "variance_g", "alloc_active_inactive", "alloc_within_active", "inactive_spike_allocation", "XgLikelihood",
+            "variance_g_probability", "tuningParam_yg", "tuningParam_variance_g")
+    host = {k: getattr(s, k).copy() for k in keys}
+    if mode.startswith("pinned"):
+        keep = {k: torch.from_numpy(host[k]).pin_memory() for k in keys}
+        host = {k: keep[k].numpy() for k in keys}                    # views of the pinned buffers
     for step in range(2):
         h.sweep(step)
         nb = h2.sweep_host(step, False, *[host[k] for k in host])
         assert nb == (G * 44, G * 44)
     g = h.get_state()
+    g2 = h2.get_state()                                              # the handle's resident state follows the host arrays
     for k in host:
         if k == "alloc_within_active":
             act = g["alloc_active_inactive"] == 1
             assert np.array_equal(host[k][act], g[k][act])
         else:
             assert np.array_equal(host[k], g[k]), k
+            assert np.array_equal(g2[k], g[k]), k
+    h2.sweep(2); h.sweep(2)                                          # ... and a resident sweep can follow directly
+    assert np.array_equal(h2.get_state()["Yg"], h.get_state()["Yg"])
 
 
 def test_nan_ratio_rejects_and_raises_flag():

@@ -193,6 +193,16 @@ __global__ void __launch_bounds__(BLOCK) k_sweep(const SweepArgs a) {
   if (saw_nan) atomicOr(a.nan_flag, 1);
 }
 
+// zz_sweep_host: per-gene state entering / leaving in the CALLER's gene order, either through staging planes in device memory
+// (filled / drained by cudaMemcpyAsync) or — when the caller's arrays are pinned, device-accessible host memory — directly.
+struct HostChunk {
+  int64_t c0, n;
+  const int32_t *inv;                                   // caller gene -> device slot
+  const double *sYg, *svg, *sty, *stv; const int32_t *sai, *sw, *ss;    // inbound planes  [G], caller order
+  double *dYg, *dvg, *dxl, *dvp; int32_t *dai, *dw, *ds;                // outbound planes [G], caller order
+  double *ty, *tv;                                      // the handle's tuning-parameter arrays (read-only in SweepArgs)
+};
+
 // ---- production sweep: same moves and draws as k_sweep in the reorganised arithmetic of zz_fast.cuh -------------------
 struct FastArgs {
   SweepArgs s;
@@ -204,6 +214,8 @@ struct FastArgs {
   double *partials;                 // [C][rows][nstat] per-block sufficient statistics (rows = main blocks + spike blocks)
   int64_t rows_per_chain, spike_row0;
   int want_stats, do_spike_move;
+  const int32_t *slot_list;         // list mode (zz_sweep_host chunks): position p in [g_begin, g_end) addresses gene slot slot_list[p]
+  int host_io; HostChunk hio;       // list mode + host_io: the tile itself reads its genes' state from hio.s* and writes hio.d* (caller order)
   // fused epilogue: the last CTA to finish reduces the rows (and all-reduces them over peer memory when asked) into stats_out
   unsigned *done_counter; double *stats_out; int do_allreduce; CommArgs cm;
 };
@@ -440,11 +452,11 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const
   // highly expressed tiles whose detection term is saturated, which keeps the tail short.
   for (int64_t t_ = warp0; t_ < ntiles; t_ += nwarps) {
     const int64_t tile = ntiles - 1 - t_;
-    const int64_t g = a.g_begin + tile * 32 + lane;
+    int64_t g = a.g_begin + tile * 32 + lane;
 #ifndef ZZ_NO_PREFETCH
     {   // pull the next tile's inputs towards L1 while this tile computes (no registers, no shared memory)
       const int64_t gn_ = g - nwarps * 32;
-      if (gn_ >= a.g_begin && gn_ < a.g_end) {
+      if (!fa.slot_list && gn_ >= a.g_begin && gn_ < a.g_end) {
         const int64_t in_ = (int64_t)chain * a.G + gn_;
         prefetch_l1(a.Yg + in_); prefetch_l1(a.vg + in_); prefetch_l1(fa.lps + in_); prefetch_l1(a.ty + in_); prefetch_l1(a.tv + in_);
         prefetch_l1(fa.nd_mask + gn_); prefetch_l1(fa.xbar + gn_); prefetch_l1(fa.xss + gn_); prefetch_l1(a.gl + gn_);
@@ -453,7 +465,26 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const
     }
 #endif
     if (g >= a.g_end) continue;
+    const int64_t pos = g;
+    if (fa.slot_list) g = fa.slot_list[g];            // a chunk of genes in the caller's order: scattered slots
     const int64_t i = (int64_t)chain * a.G + g;
+    if (fa.host_io) {
+      // The gene's state comes straight from the caller's (pinned, device-mapped) arrays: PCIe reads issued by this warp while
+      // other resident warps compute and write back (a cp.async double buffer of the next tile's words was measured: no gain,
+      // the PCIe link is the bound).  The same work as k_host_in follows, fused into the tile.
+      const HostChunk &hc = fa.hio;
+      const double y = hc.sYg[pos], v_in = hc.svg[pos], ty_in = hc.sty[pos], tv_in = hc.stv[pos];
+      const int ai_in = hc.sai[pos], w_in = hc.sw[pos], s_in = hc.ss[pos];
+      a.Yg[i] = y; a.vg[i] = v_in; hc.ty[i] = ty_in; hc.tv[i] = tv_in;
+      uint32_t f = a.flags[i];
+      f = (f & ~F_ACTIVE) | (ai_in ? F_ACTIVE : 0u);
+      f = flag_set_k(f, w_in < 1 ? 1 : w_in);
+      f = (f & ~F_INSPIKE) | (s_in ? F_INSPIKE : 0u);
+      a.flags[i] = (uint16_t)f;
+      const double A = (f & F_INSPIKE) ? 0.0 : detect_logsum<RT>(H, T, fa.nd_mask[g], a.gl[g] * fexp(y, T.exp_t));
+      fa.lps[i] = A;
+      if (f & F_ALLZERO) a.xglik[i] = (f & F_INSPIKE) ? 0.0 : times_beta(H, A);
+    }
     const uint64_t gid = (uint64_t)(a.gene_offset + a.perm[g]);
     FastGene gn;
     gn.y = a.Yg[i]; gn.v = a.vg[i]; gn.A = fa.lps[i]; gn.f = a.flags[i];
@@ -523,6 +554,12 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const
       if (!PROD && a.dec[3]) a.dec[3][i] = (uint8_t)so.acc;
     }
     if (fa.want_stats) stats_add<SWEEP_BLOCK>(acc, a.K, true, gn.y, gn.lv, gn.f, xglik, vgprob, finite_state);
+    if (fa.host_io) {                                 // k_host_out, fused: the updated state as the moves (and the spike move) left it
+      const HostChunk &hc = fa.hio;
+      hc.dYg[pos] = a.Yg[i]; hc.dvg[pos] = a.vg[i]; hc.dxl[pos] = a.xglik[i]; hc.dvp[pos] = a.vgprob[i];
+      const uint32_t fo = a.flags[i];
+      hc.dai[pos] = (fo & F_ACTIVE) ? 1 : 0; hc.dw[pos] = flag_k(fo); hc.ds[pos] = (fo & F_INSPIKE) ? 1 : 0;
+    }
   }
   }
   if (saw_nan) atomicOr(a.nan_flag, 1);
@@ -565,6 +602,43 @@ __global__ void __launch_bounds__(BLOCK) k_refresh_lps(const FastArgs fa) {
   // want_stats doubles as "also rebuild XgLikelihood of the all-zero genes" (n_det = 0 => XgLik = beta A): zz_sweep_host does not
   // upload the caches, and the spike move reads this one (Pr:581)
   if (fa.want_stats && (f & F_ALLZERO)) a.xglik[i] = times_beta(H, A);
+}
+
+// ---- zz_sweep_host: the state of a CHUNK of genes (caller order [c0, c0 + n)) enters and leaves through staging planes, so
+// that chunk k+1 can be on the PCIe bus (host -> device) and chunk k-1 on its way back while chunk k is being swept.
+
+// inbound: scatter the chunk's state into its slots, pack the allocation words and rebuild what the production sweep carries
+// but the host does not hold: A(Yg) (`lps`) and the XgLikelihood of all-zero genes (k_refresh_lps, chunk-wise)
+template <int RT>
+__global__ void __launch_bounds__(BLOCK) k_host_in(const FastArgs fa, const HostChunk hc) {
+  __shared__ FastH H;
+  __shared__ MathTabs T;
+  const SweepArgs &a = fa.s;
+  load_fast(H, T, fa.fasth, fa.exp_tab, fa.log_tab);
+  const int64_t j = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (j >= hc.n) return;
+  const int64_t c = hc.c0 + j, i = hc.inv[c];
+  const double y = hc.sYg[c];
+  a.Yg[i] = y; a.vg[i] = hc.svg[c]; hc.ty[i] = hc.sty[c]; hc.tv[i] = hc.stv[c];
+  uint32_t f = a.flags[i];
+  f = (f & ~F_ACTIVE) | (hc.sai[c] ? F_ACTIVE : 0u);
+  f = flag_set_k(f, hc.sw[c] < 1 ? 1 : hc.sw[c]);
+  f = (f & ~F_INSPIKE) | (hc.ss[c] ? F_INSPIKE : 0u);
+  a.flags[i] = (uint16_t)f;
+  if (f & F_INSPIKE) { fa.lps[i] = 0; if (f & F_ALLZERO) a.xglik[i] = 0.0; return; }
+  const double A = detect_logsum<RT>(H, T, fa.nd_mask[i], a.gl[i] * fexp(y, T.exp_t));
+  fa.lps[i] = A;
+  if (f & F_ALLZERO) a.xglik[i] = times_beta(H, A);
+}
+
+// outbound: the chunk's updated state, caches and allocation vectors back into caller order
+__global__ void __launch_bounds__(BLOCK) k_host_out(const SweepArgs a, const HostChunk hc) {
+  const int64_t j = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (j >= hc.n) return;
+  const int64_t c = hc.c0 + j, i = hc.inv[c];
+  hc.dYg[c] = a.Yg[i]; hc.dvg[c] = a.vg[i]; hc.dxl[c] = a.xglik[i]; hc.dvp[c] = a.vgprob[i];
+  const uint32_t f = a.flags[i];
+  hc.dai[c] = (f & F_ACTIVE) ? 1 : 0; hc.dw[c] = flag_k(f); hc.ds[c] = (f & F_INSPIKE) ? 1 : 0;
 }
 
 // exports the Philox draws of one move slot in the layout of that move's `draws` argument
@@ -838,6 +912,8 @@ __global__ void __launch_bounds__(BLOCK) k_unpack_flags(int64_t n, const int32_t
 
 // ------------------------------------------------------------------------------------------------ handle
 
+#define ZZ_HOST_MAX_CHUNKS 16
+
 struct zz_handle {
   zz_config cfg;
   int64_t G; int C, R, K;
@@ -870,6 +946,8 @@ struct zz_handle {
   bool lps_valid;                          // lps == A(current Yg, alpha_r) for every out-of-spike gene
   std::vector<zz_hyper> hyper_host;
   double *pinned;                          // small pinned staging for reduction results
+  // zz_sweep_host pipeline (created on first use)
+  int32_t *inv_perm; cudaStream_t s_up, s_down; cudaEvent_t ev_entry, ev_up[ZZ_HOST_MAX_CHUNKS], ev_done[ZZ_HOST_MAX_CHUNKS]; bool pipe_ready;
 };
 
 namespace {
@@ -955,14 +1033,14 @@ int launch_sweep(zz_handle *h, uint64_t step, int tune, uint32_t moves, const do
   return ZZ_OK;
 }
 
-#define ZZ_DISPATCH_R(h, KERNEL, grid, args)                                                     \
+#define ZZ_DISPATCH_R(h, KERNEL, grid, ...)                                                      \
   do {                                                                                           \
     switch ((h)->R) {                                                                            \
-      case 2: KERNEL<2><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                           \
-      case 4: KERNEL<4><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                           \
-      case 8: KERNEL<8><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                           \
-      case 16: KERNEL<16><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                         \
-      default: KERNEL<0><<<grid, BLOCK, 0, (h)->stream>>>(args); break;                          \
+      case 2: KERNEL<2><<<grid, BLOCK, 0, (h)->stream>>>(__VA_ARGS__); break;                           \
+      case 4: KERNEL<4><<<grid, BLOCK, 0, (h)->stream>>>(__VA_ARGS__); break;                           \
+      case 8: KERNEL<8><<<grid, BLOCK, 0, (h)->stream>>>(__VA_ARGS__); break;                           \
+      case 16: KERNEL<16><<<grid, BLOCK, 0, (h)->stream>>>(__VA_ARGS__); break;                         \
+      default: KERNEL<0><<<grid, BLOCK, 0, (h)->stream>>>(__VA_ARGS__); break;                          \
     }                                                                                            \
   } while (0)
 
@@ -971,6 +1049,7 @@ void fill_fast_args(zz_handle *h, FastArgs &fa) {
   fa.nd_mask = h->nd_mask; fa.xbar = h->xbar; fa.xss = h->xss; fa.fasth = h->fasth;
   fa.partials = h->sw_partials; fa.rows_per_chain = 0; fa.spike_row0 = 0; fa.want_stats = 0; fa.do_spike_move = 0;
   fa.done_counter = h->tile_counter; fa.stats_out = nullptr; fa.do_allreduce = 0; memset(&fa.cm, 0, sizeof fa.cm);
+  fa.slot_list = nullptr; fa.host_io = 0; memset(&fa.hio, 0, sizeof fa.hio);
 }
 
 int ensure_fasth(zz_handle *h) {
@@ -1050,13 +1129,15 @@ int persistent_blocks(zz_handle *h, size_t smem) {
 // production kernels (zz_fast.cuh): persistent main sweep + spike move over the all-zero gene list; when the whole shard is
 // swept they also leave per-block sufficient statistics in sw_partials (consumed by zz_suffstats[_dev] without another pass)
 int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, const double *const draws_dev[9], uint8_t *const dec_dev[4],
-                      int64_t g_begin, int64_t g_end) {
+                      int64_t g_begin, int64_t g_end, const int32_t *slot_list = nullptr, const HostChunk *host_io = nullptr) {
   if (g_end <= g_begin) return ZZ_OK;
-  if (int rc = ensure_lps(h)) return rc;
+  if (!slot_list) { if (int rc = ensure_lps(h)) return rc; }           // list mode: the caller (k_host_in) has just rebuilt lps
   FastArgs fa;
   fill_sweep_args(h, fa.s, step, tune, moves, draws_dev, dec_dev, g_begin, g_end);
   fill_fast_args(h, fa);
-  const bool full = (g_begin == 0 && g_end == h->G);
+  fa.slot_list = slot_list;
+  if (host_io) { fa.host_io = 1; fa.hio = *host_io; }
+  const bool full = (g_begin == 0 && g_end == h->G) && !slot_list;
   const int nstat = zz_suffstats_len(h->K);
   size_t smem = full ? sizeof(double) * nstat * SWEEP_BLOCK : 0;
   const int64_t ntiles = (g_end - g_begin + 31) / 32;
@@ -1094,8 +1175,9 @@ int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, con
 #ifdef ZZ_NO_STRAIGHT_TILE
   kt = 0;
 #endif
+  if (slot_list) kt = 0;                                            // scattered slots: generic tile, chain 0 only
   if (kt > 0) smem = sizeof(double) * (nstat + 10) * SWEEP_BLOCK;   // statistic columns + per-warp staging slots
-  ZZ_DISPATCH_SWEEP(h, prod, kt, dim3((unsigned)per_chain, (unsigned)h->C), smem, fa);
+  ZZ_DISPATCH_SWEEP(h, prod, kt, dim3((unsigned)per_chain, (unsigned)(slot_list ? 1 : h->C)), smem, fa);
   ZZ_LAUNCHED(h);
   if (full) { h->stats_fresh = true; h->sw_rows = fa.rows_per_chain; }
   return ZZ_OK;
@@ -1183,6 +1265,7 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   if (!h) return ZZ_ERR_NOMEM;
   h->cfg = *cfg; h->G = cfg->num_genes; h->C = cfg->num_chains; h->R = cfg->num_libraries; h->K = cfg->num_active_components;
   h->sticky = false; h->launches = 0; h->have_data = false; h->own_stream = false; h->stream = nullptr;
+  h->inv_perm = nullptr; h->pipe_ready = false; h->s_up = h->s_down = nullptr;
   *out = h;  // returned even on failure so the caller can read zz_last_error and must zz_destroy
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1263,6 +1346,11 @@ void zz_destroy(zz_handle *h) {
                   h->log_tab, h->perm, h->stage, h->nd_mask, h->xbar, h->xss, h->tile_counter, h->sw_partials, h->sw_partials2, h->fasth};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->inv_perm) cudaFree(h->inv_perm);
+  if (h->pipe_ready) {
+    cudaStreamDestroy(h->s_up); cudaStreamDestroy(h->s_down); cudaEventDestroy(h->ev_entry);
+    for (int k = 0; k < ZZ_HOST_MAX_CHUNKS; ++k) { cudaEventDestroy(h->ev_up[k]); cudaEventDestroy(h->ev_done[k]); }
+  }
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1686,30 +1774,101 @@ int zz_sweep_host(zz_handle *h, uint64_t step, int tune, double *Yg, double *var
   if (!Yg || !variance_g || !ai || !within || !spike || !XgLikelihood || !variance_g_probability || !ty || !tv)
     return fail(h, ZZ_ERR_INVALID, "NULL state pointer");
   const int64_t G = h->G;
-  int32_t *d_ai = h->iscratch, *d_w = h->iscratch + G, *d_s = h->iscratch + 2 * G;
   int rc;
-  if ((rc = up_g(h, h->Yg, (const double *)Yg, G)) || (rc = up_g(h, h->vg, (const double *)variance_g, G)) ||
-      (rc = up_g(h, h->ty, ty, G)) || (rc = up_g(h, h->tv, tv, G)) ||
-      (rc = up(h, d_ai, (const int32_t *)ai, G)) || (rc = up(h, d_w, (const int32_t *)within, G)) || (rc = up(h, d_s, (const int32_t *)spike, G)))
-    return rc;
-  k_pack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, h->perm, d_ai, d_w, d_s, nullptr, h->flags);
-  ZZ_LAUNCHED(h);
-  // Yg arrived from the host: A(y) is rebuilt on the device (one extra pass; PCIe dominates this entry point).  The two caches
-  // are pure functions of the uploaded state, so they are not uploaded: the sweep recomputes them and they travel back only.
-  h->lps_valid = false;
-  if ((rc = ensure_lps(h, true))) return rc;
-  {
-    const double *no_draws[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    uint8_t *no_dec[4] = {nullptr, nullptr, nullptr, nullptr};
-    if ((rc = launch_sweep_fast(h, step, tune, ZZ_MOVE_FUSED, no_draws, no_dec, 0, G))) return rc;
+  if (!h->pipe_ready) {
+    ZZ_CUDA(h, cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
+    ZZ_CUDA(h, cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking));
+    ZZ_CUDA(h, cudaEventCreateWithFlags(&h->ev_entry, cudaEventDisableTiming));
+    for (int k = 0; k < ZZ_HOST_MAX_CHUNKS; ++k) {
+      ZZ_CUDA(h, cudaEventCreateWithFlags(&h->ev_up[k], cudaEventDisableTiming));
+      ZZ_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming));
+    }
+    h->pipe_ready = true;
   }
-  k_unpack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, h->perm, h->flags, d_ai, d_w, d_s);
-  ZZ_LAUNCHED(h);
-  if ((rc = down_g(h, Yg, h->Yg, G, 1, false)) || (rc = down_g(h, variance_g, h->vg, G, 1, false)) ||
-      (rc = down_g(h, XgLikelihood, h->xglik, G, 1, false)) || (rc = down_g(h, variance_g_probability, h->vgprob, G, 1, false)) ||
-      (rc = down(h, ai, d_ai, G)) || (rc = down(h, within, d_w, G)) || (rc = down(h, spike, d_s, G)))
-    return rc;
+  if (!h->inv_perm) {                                   // caller gene -> device slot
+    std::vector<int32_t> inv((size_t)G);
+    for (int64_t g = 0; g < G; ++g) inv[(size_t)h->perm_h[(size_t)g]] = (int32_t)g;
+    ZZ_CUDA(h, cudaMalloc(&h->inv_perm, sizeof(int32_t) * G));
+    ZZ_CUDA(h, cudaMemcpyAsync(h->inv_perm, inv.data(), sizeof(int32_t) * G, cudaMemcpyHostToDevice, h->stream));
+    ZZ_CUDA(h, cudaStreamSynchronize(h->stream));      // `inv` is a local
+  }
+  if ((rc = ensure_fasth(h))) return rc;
+  // Three streams: copies in (s_up), kernels (the handle's stream), copies out (s_down); PCIe is full duplex, so in steady state
+  // chunk k+1 travels up and chunk k-1 travels down while chunk k is swept.  Staging planes are whole-G arrays in caller order
+  // (inbound in `stage`, outbound in `scratch`), each chunk owns its own sub-range: no buffer is reused within a call.
+  int nchunks = (int)((G + 131072) / 262144);           // ~256K genes per chunk: below that the per-copy cost of 14 copies per chunk dominates
+  if (const char *e = getenv("ZZ_HOST_CHUNKS")) nchunks = atoi(e);
+  if (nchunks < 1) nchunks = 1;
+  if (nchunks > ZZ_HOST_MAX_CHUNKS) nchunks = ZZ_HOST_MAX_CHUNKS;
+  const int64_t per = ((G + nchunks - 1) / nchunks + 31) / 32 * 32;
+  HostChunk hc;
+  hc.inv = h->inv_perm; hc.ty = h->ty; hc.tv = h->tv;
+  double *up8 = h->stage, *dn8 = h->scratch;
+  int32_t *up4 = reinterpret_cast<int32_t *>(up8 + 4 * G), *dn4 = reinterpret_cast<int32_t *>(dn8 + 4 * G);
+  hc.sYg = up8; hc.svg = up8 + G; hc.sty = up8 + 2 * G; hc.stv = up8 + 3 * G; hc.sai = up4; hc.sw = up4 + G; hc.ss = up4 + 2 * G;
+  hc.dYg = dn8; hc.dvg = dn8 + G; hc.dxl = dn8 + 2 * G; hc.dvp = dn8 + 3 * G; hc.dai = dn4; hc.dw = dn4 + G; hc.ds = dn4 + 2 * G;
+  {
+    // Caller arrays in pinned, device-mapped host memory (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory()): ONE kernel
+    // reads them, sweeps, and writes them back over PCIe itself — no staging copies, both directions busy at once.
+    void *hp[9] = {Yg, variance_g, (void *)ty, (void *)tv, ai, within, spike, XgLikelihood, variance_g_probability};
+    void *dp[9];
+    bool mapped = getenv("ZZ_HOST_NO_ZEROCOPY") == nullptr;
+    for (int j = 0; j < 9 && mapped; ++j) {
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, hp[j]) != cudaSuccess) { cudaGetLastError(); mapped = false; break; }
+      if (at.type != cudaMemoryTypeHost || !at.devicePointer) mapped = false;
+      dp[j] = at.devicePointer;
+    }
+    if (mapped) {
+      hc.c0 = 0; hc.n = G;
+      hc.sYg = (const double *)dp[0]; hc.svg = (const double *)dp[1]; hc.sty = (const double *)dp[2]; hc.stv = (const double *)dp[3];
+      hc.sai = (const int32_t *)dp[4]; hc.sw = (const int32_t *)dp[5]; hc.ss = (const int32_t *)dp[6];
+      hc.dYg = (double *)dp[0]; hc.dvg = (double *)dp[1]; hc.dxl = (double *)dp[7]; hc.dvp = (double *)dp[8];
+      hc.dai = (int32_t *)dp[4]; hc.dw = (int32_t *)dp[5]; hc.ds = (int32_t *)dp[6];
+      const double *nd[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+      uint8_t *ne[4] = {nullptr, nullptr, nullptr, nullptr};
+      h->lps_valid = false;
+      if ((rc = launch_sweep_fast(h, step, tune, ZZ_MOVE_FUSED, nd, ne, 0, G, h->inv_perm, &hc))) return rc;
+      ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+      h->lps_valid = true;
+      if (h2d_bytes) *h2d_bytes = G * (4 * 8 + 3 * 4);
+      if (d2h_bytes) *d2h_bytes = G * (4 * 8 + 3 * 4);
+      return ZZ_OK;
+    }
+  }
+  ZZ_CUDA(h, cudaEventRecord(h->ev_entry, h->stream));   // earlier work on the handle's stream may still use the staging buffers
+  ZZ_CUDA(h, cudaStreamWaitEvent(h->s_up, h->ev_entry, 0));
+  const double *no_draws[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint8_t *no_dec[4] = {nullptr, nullptr, nullptr, nullptr};
+  h->lps_valid = false;                                  // rebuilt chunk by chunk below; valid again once every chunk is through
+  int k = 0;
+  for (int64_t c0 = 0; c0 < G; c0 += per, ++k) {
+    const int64_t n = (G - c0 < per) ? G - c0 : per;
+    const double *h8[4] = {Yg, variance_g, ty, tv};
+    const int32_t *h4[3] = {ai, within, spike};
+    for (int j = 0; j < 4; ++j) ZZ_CUDA(h, cudaMemcpyAsync(up8 + j * G + c0, h8[j] + c0, sizeof(double) * n, cudaMemcpyHostToDevice, h->s_up));
+    for (int j = 0; j < 3; ++j) ZZ_CUDA(h, cudaMemcpyAsync(up4 + j * G + c0, h4[j] + c0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->s_up));
+    ZZ_CUDA(h, cudaEventRecord(h->ev_up[k], h->s_up));
+    ZZ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_up[k], 0));
+    hc.c0 = c0; hc.n = n;
+    FastArgs fa;
+    fill_sweep_args(h, fa.s, step, tune, ZZ_MOVE_FUSED, no_draws, no_dec, 0, G);
+    fill_fast_args(h, fa);
+    ZZ_DISPATCH_R(h, k_host_in, gene_grid(h, n), fa, hc);
+    ZZ_LAUNCHED(h);
+    if ((rc = launch_sweep_fast(h, step, tune, ZZ_MOVE_FUSED, no_draws, no_dec, c0, c0 + n, h->inv_perm))) return rc;
+    k_host_out<<<gene_grid(h, n), BLOCK, 0, h->stream>>>(fa.s, hc);
+    ZZ_LAUNCHED(h);
+    ZZ_CUDA(h, cudaEventRecord(h->ev_done[k], h->stream));
+    ZZ_CUDA(h, cudaStreamWaitEvent(h->s_down, h->ev_done[k], 0));
+    double *o8[4] = {Yg, variance_g, XgLikelihood, variance_g_probability};
+    int32_t *o4[3] = {ai, within, spike};
+    for (int j = 0; j < 4; ++j) ZZ_CUDA(h, cudaMemcpyAsync(o8[j] + c0, dn8 + j * G + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, h->s_down));
+    for (int j = 0; j < 3; ++j) ZZ_CUDA(h, cudaMemcpyAsync(o4[j] + c0, dn4 + j * G + c0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->s_down));
+  }
+  ZZ_CUDA(h, cudaStreamSynchronize(h->s_down));
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->lps_valid = true;
   if (h2d_bytes) *h2d_bytes = G * (4 * 8 + 3 * 4);
   if (d2h_bytes) *d2h_bytes = G * (4 * 8 + 3 * 4);
   return ZZ_OK;
