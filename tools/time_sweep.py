@@ -3,7 +3,7 @@ sys.path.insert(0, ".")
 import torch
 from zigzag_b200 import _capi, synth
 name = sys.argv[1] if len(sys.argv) > 1 else "1m_x16"
-X, gl, hd, st, chains = synth.make_config(name)
+X, gl, hd, st, chains = synth.make_config(name, int(sys.argv[2]) if len(sys.argv) > 2 else None)
 G, R = X.shape
 hg = _capi.Hyper.make(hd["alpha_r"], hd["active_means"], hd["active_variances"], hd["weight_within_active"],
                       **{k: float(hd[k]) for k in ("s0","s1","tau","spike_probability","inactive_means","inactive_variances","weight_active","beta","temperature","variance_g_upper_bound")})

@@ -79,16 +79,23 @@ __device__ __forceinline__ void derive_fast(FastH &H, const zz_hyper *__restrict
   }
 }
 
-__device__ __forceinline__ void load_fast(FastH &H, MathTabs &T, const FastH *__restrict__ src,
-                                          const double *__restrict__ exp_tab, const double2 *__restrict__ log_tab) {
+__device__ __forceinline__ void load_tabs(MathTabs &T, const double *__restrict__ exp_tab, const double2 *__restrict__ log_tab) {
   const int t = threadIdx.x, nt = blockDim.x;
   for (int j = t; j < 256; j += nt) T.exp_t[j] = exp_tab[j];
   for (int j = t; j < 512; j += nt) T.log_t[j] = log_tab[j];
+}
+__device__ __forceinline__ void load_hyper_fast(FastH &H, const FastH *__restrict__ src) {   // ends with a block barrier
+  const int t = threadIdx.x, nt = blockDim.x;
   static_assert(sizeof(FastH) % 8 == 0, "FastH is copied as 64-bit words");
   const uint64_t *s = reinterpret_cast<const uint64_t *>(src);
   uint64_t *d = reinterpret_cast<uint64_t *>(&H);
   for (int j = t; j < (int)(sizeof(FastH) / 8); j += nt) d[j] = s[j];
   __syncthreads();
+}
+__device__ __forceinline__ void load_fast(FastH &H, MathTabs &T, const FastH *__restrict__ src,
+                                          const double *__restrict__ exp_tab, const double2 *__restrict__ log_tab) {
+  load_tabs(T, exp_tab, log_tab);
+  load_hyper_fast(H, src);
 }
 
 // z = sqrt(-2 ln ua) * cos(2 pi ub)  (same draw as box_muller's z0; the sine branch is only needed by the spike move)
@@ -121,6 +128,8 @@ __device__ __forceinline__ double detect_logsum_sl(const FastH &H, const MathTab
   const uint32_t mlo = (uint32_t)nd_mask;
   const int one_hi = opaque_one_hi(&H.one_hi);
   double fsum = 0; int ksum = -1023 * RT;
+  // (statement-level interleaving of several libraries was measured: no gain — at 24 warps/SM the FP64 pipe, the shared-memory
+  // data pipe and the issue slots are all 50-65 % busy, profiles/r1_summary.md)
 #pragma unroll
   for (int r = 0; r < RT; ++r) det_term(tc, H.am256[r], mlo & (1u << r), T, fsum, ksum, one_hi);
   const double A = fma((double)ksum, ZZ_KLN2, fsum);

@@ -332,8 +332,11 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const
   const SweepArgs &a = fa.s;
   const int chain = blockIdx.y, lane = threadIdx.x & 31;
   const int nstat = 3 * (a.K + 1) + NSTAT_FIXED_;
+  asm volatile("griddepcontrol.launch_dependents;");   // see launch_pdl
   if (fa.want_stats) for (int s = 0; s < nstat; ++s) acc[s * SWEEP_BLOCK + threadIdx.x] = 0.0;
-  load_fast(H, T, fa.fasth + chain, fa.exp_tab, fa.log_tab);
+  load_tabs(T, fa.exp_tab, fa.log_tab);                // constants: may be read while the previous kernel still runs
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below reads state the previous kernel may have written
+  load_hyper_fast(H, fa.fasth + chain);
   const int64_t n = a.g_end - a.g_begin;
   const int64_t ntiles = (n + 31) / 32;
   const int64_t warp0 = (int64_t)blockIdx.x * (SWEEP_BLOCK / 32) + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * (SWEEP_BLOCK / 32);
@@ -1073,13 +1076,27 @@ int ensure_lps(zz_handle *h, bool rebuild_allzero_xglik = false) {
   return ZZ_OK;
 }
 
+// Programmatic dependent launch: the sweep kernels announce their dependents at once (griddepcontrol.launch_dependents) and
+// touch mutable state only after griddepcontrol.wait, so the next sweep's CTAs are scheduled as this one's exit and load their
+// tables while the last tiles and the statistics epilogue of this sweep are still running.
+template <class Kern>
+void launch_pdl(Kern kern, dim3 grid, size_t smem, cudaStream_t st, const FastArgs &fa) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(SWEEP_BLOCK); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, fa);
+}
+
 #define ZZ_SWEEP_CASE_R(h, PRODV, KTV, grid, smem, args)                                         \
   switch ((h)->R) {                                                                              \
-    case 2: k_sweep_fast<2, PRODV, KTV><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;   \
-    case 4: k_sweep_fast<4, PRODV, KTV><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;   \
-    case 8: k_sweep_fast<8, PRODV, KTV><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;   \
-    case 16: k_sweep_fast<16, PRODV, KTV><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break; \
-    default: k_sweep_fast<0, PRODV, KTV><<<grid, SWEEP_BLOCK, smem, (h)->stream>>>(args); break;  \
+    case 2: launch_pdl(k_sweep_fast<2, PRODV, KTV>, grid, smem, (h)->stream, args); break;   \
+    case 4: launch_pdl(k_sweep_fast<4, PRODV, KTV>, grid, smem, (h)->stream, args); break;   \
+    case 8: launch_pdl(k_sweep_fast<8, PRODV, KTV>, grid, smem, (h)->stream, args); break;   \
+    case 16: launch_pdl(k_sweep_fast<16, PRODV, KTV>, grid, smem, (h)->stream, args); break; \
+    default: launch_pdl(k_sweep_fast<0, PRODV, KTV>, grid, smem, (h)->stream, args); break;  \
   }
 // kt: 0 = generic tile (explicit draws / decisions / move subsets / finite variance bound / K > 3), 1..3 = straight-line tile
 #define ZZ_DISPATCH_SWEEP(h, prod, kt, grid, smem, args)                                         \
