@@ -13,6 +13,9 @@ h.upload_data(X, gl)
 for c in range(chains):
     h.set_hyper(hg, c); h.set_state(c, **st)
 h.refresh_caches()
+if os.environ.get("ZZ_TS_STATS"):      # also time the fused statistics epilogue (what bench.py's step runs)
+    stats = torch.zeros(chains * h.nstat, dtype=torch.float64, device="cuda")
+    h.set_stats_output_dev(stats.data_ptr(), allreduce=False)
 for i in range(20): h.sweep(i)
 torch.cuda.synchronize()
 n = 200

@@ -83,22 +83,45 @@ __device__ __forceinline__ void allreduce_exchange(const double *vec, const Comm
   }
 }
 
-// fixed-order reduction of the per-CTA rows [C][nblk][nval] into `vec` (shared memory, nvec = nval*C doubles); whole CTA
+// Fixed-order reduction of the per-CTA rows [C][nblk][nval] into `vec` (shared memory, nvec = nval*C doubles, followed by
+// RED_THREADS doubles of scratch); whole CTA (>= RED_THREADS threads).  The rows were written by other CTAs: they are read
+// through L2 (ld.cg).  Thread t owns statistic s = t % nval of row group j = t / nval, so the lanes of a warp read CONSECUTIVE
+// doubles (one or two whole rows per load instruction).  Mapping lanes to rows instead (stride nval*8 bytes: 32 different cache
+// lines per load) made the 384 loads of the final reduction cost 10 us per sweep.  The order is canonical — chain by chain,
+// group j adds rows j, j + ng, ... in ascending order, then one thread per statistic adds the ng partial sums in group order,
+// ng = RED_THREADS / nval — so every caller (sweep epilogue, k_reduce_final, k_reduce_allreduce) produces the same bits.
+constexpr int RED_THREADS = 256;
+static_assert(SWEEP_BLOCK >= RED_THREADS && BLOCK >= RED_THREADS, "reduce_rows_to_smem needs RED_THREADS threads");
 __device__ __forceinline__ void reduce_rows_to_smem(const double *partials, int nblk, int nval, int nvec, double *vec) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int idx = w; idx < nvec; idx += nw) {
-    const int y = idx / nval, s = idx - y * nval;
-    double v = 0;
-    for (int b = lane; b < nblk; b += 32) v += ((volatile const double *)partials)[((int64_t)y * nblk + b) * nval + s];
-    v = warp_sum(v);
-    if (lane == 0) vec[idx] = v;
+  double *scratch = vec + nvec;
+  const int C = nvec / nval, ng = RED_THREADS / nval;
+  const int t = threadIdx.x, s = t % nval, j = t / nval;
+  for (int y = 0; y < C; ++y) {
+    if (j < ng) {
+      const double *base = partials + (int64_t)y * nblk * nval + s;
+      double v = 0;
+      for (int r0 = j; r0 < nblk; r0 += ng * 8) {
+        double tt[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int r = r0 + u * ng; tt[u] = r < nblk ? __ldcg(base + (int64_t)r * nval) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v += tt[u];
+      }
+      scratch[j * nval + s] = v;
+    }
+    __syncthreads();
+    if (t < nval) {
+      double a = 0;
+      for (int k = 0; k < ng; ++k) a += scratch[k * nval + t];
+      vec[y * nval + t] = a;
+    }
+    __syncthreads();
   }
-  __syncthreads();
 }
 
 __global__ void __launch_bounds__(BLOCK) k_reduce_allreduce(const double *partials, int nblk, int nval, int C, double *out, CommArgs cm,
                                                              int *err_flag) {
-  __shared__ double vec[MAX_NSTAT * 8];   // local reduced vector (nvec <= MAX_NSTAT * 8 is checked by the host)
+  __shared__ double vec[MAX_NSTAT * 8 + RED_THREADS];   // local reduced vector (nvec <= MAX_NSTAT * 8 is checked by the host) + scratch
   (void)C;
   reduce_rows_to_smem(partials, nblk, nval, cm.nvec, vec);
   allreduce_exchange(vec, cm, out, err_flag);
@@ -762,13 +785,10 @@ __global__ void __launch_bounds__(BLOCK) k_reduce(const RedArgs a) {
 // partials [ny][nblk][nval] -> out [ny][nval], fixed summation order: warp w owns values w, w + 8, ...; lane l adds rows
 // l, l + 32, ... then a butterfly — no block barrier, so the whole reduction is one short latency chain
 __global__ void __launch_bounds__(BLOCK) k_reduce_final(const double *partials, int nblk, int nval, double *out) {
-  const int y = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int s = w; s < nval; s += BLOCK / 32) {
-    double v = 0;
-    for (int b = lane; b < nblk; b += 32) v += partials[((int64_t)y * nblk + b) * nval + s];
-    v = warp_sum(v);
-    if (lane == 0) out[(int64_t)y * nval + s] = v;
-  }
+  __shared__ double vec[MAX_NSTAT + RED_THREADS];
+  const int y = blockIdx.x;                          // one chain (or reduction slot) per block, canonical order of reduce_rows_to_smem
+  reduce_rows_to_smem(partials + (int64_t)y * nblk * nval, nblk, nval, nval, vec);
+  if ((int)threadIdx.x < nval) out[(int64_t)y * nval + threadIdx.x] = vec[threadIdx.x];
 }
 
 
@@ -1086,7 +1106,8 @@ void launch_pdl(Kern kern, dim3 grid, size_t smem, cudaStream_t st, const FastAr
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  static const bool no_pdl = getenv("ZZ_NO_PDL") != nullptr;   // measurement switch (profiles/r1_summary.md)
+  cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
   cudaLaunchKernelEx(&cfg, kern, fa);
 }
 
@@ -1332,8 +1353,8 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   ZZ_CUDA(h, cudaMalloc(&h->nd_mask, sizeof(uint64_t) * G));
   ZZ_CUDA(h, cudaMalloc(&h->xbar, sizeof(double) * G));
   ZZ_CUDA(h, cudaMalloc(&h->xss, sizeof(double) * G));
-  ZZ_CUDA(h, cudaMalloc(&h->tile_counter, sizeof(unsigned) * h->C));
-  ZZ_CUDA(h, cudaMemsetAsync(h->tile_counter, 0, sizeof(unsigned) * h->C, h->stream));
+  ZZ_CUDA(h, cudaMalloc(&h->tile_counter, sizeof(unsigned) * 32));
+  ZZ_CUDA(h, cudaMemsetAsync(h->tile_counter, 0, sizeof(unsigned) * 32, h->stream));
   {
     const int64_t max_rows = (G + 31) / 32 + ((G + BLOCK - 1) / BLOCK) * (BLOCK / 32);
     ZZ_CUDA(h, cudaMalloc(&h->sw_partials, sizeof(double) * (size_t)h->C * max_rows * nstat));
