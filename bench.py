@@ -249,18 +249,6 @@ def main():
         dist.barrier()
     launches = h.launch_count - launches0
     ms_total = ev0.elapsed_time(ev1)
-    if world == 1 or use_p2p:
-        # one launch per step and nothing else on the stream: the sweep kernel's average duration IS the step time
-        sweep_ms = ms_total / args.steps
-    else:
-        # NCCL variant: the step also holds the all-reduce kernel; time the sweep launches alone over the same number of steps
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        for i in range(args.steps):
-            h.sweep(args.warmup + args.steps + i)
-        k1.record()
-        torch.cuda.synchronize()
-        sweep_ms = k0.elapsed_time(k1) / args.steps
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -278,6 +266,19 @@ def main():
         dist.all_gather(both, stats)
         assert all(torch.equal(both[0], b) for b in both), "ranks hold different reduced vectors"
         assert h.nan_flag() == 0
+
+    if world == 1 or use_p2p:
+        # one launch per step and nothing else on the stream: the sweep kernel's average duration IS the step time
+        sweep_ms = ms_total / args.steps
+    else:
+        # NCCL variant: the step also holds the all-reduce kernel; time the sweep launches alone over the same number of steps
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for i in range(args.steps):
+            h.sweep(args.warmup + args.steps + i)
+        k1.record()
+        torch.cuda.synchronize()
+        sweep_ms = k0.elapsed_time(k1) / args.steps
 
     # ---- e2e: the same sweep through the host-buffer entry point (mutable state in pinned host memory, H2D + D2H every step)
     e2e = None
