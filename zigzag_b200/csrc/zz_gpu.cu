@@ -38,49 +38,62 @@ constexpr int NSTAT_FIXED = 10;
 constexpr int MAX_NSTAT = 3 * (ZZ_MAX_COMP + 1) + NSTAT_FIXED;
 
 // ---- sufficient-statistics all-reduce over NVLink peer memory, fused with the final reduction -------------------------------
-// Every rank (one process per GPU) owns an inbox [2 slots][world][nvec] and a flag row [2][world] in its own HBM, mapped into
-// every peer through CUDA IPC.  The CTA that holds the rank's reduced vector (1) stores it into inbox[slot][my_rank] of EVERY
-// rank (remote stores ride NVLink/NVSwitch), fences, raises flag[slot][my_rank] = epoch on every rank, (2) spins until all
-// `world` flags of its own row reached `epoch`, (3) adds the `world` vectors in RANK ORDER, so every rank obtains the
-// bit-identical sum (replicated hyper moves cannot diverge).  Slots alternate with the epoch; a rank cannot lap another by
-// more than one epoch because it needs everybody's flag first.  The spin is bounded (~2 s of clock64): on timeout bit 2 of
-// the NaN/err flag is raised instead of hanging.
+// Every rank (one process per GPU) owns an inbox [2 slots][world][2 * nvec] of 64-bit words in its own HBM, mapped into every
+// peer through CUDA IPC.  The vector travels in the "low-latency" format: each double is sent as two 8-byte words
+// {low half | epoch << 32}, {high half | epoch << 32}.  An aligned 8-byte store is single-copy atomic, so a word whose upper half
+// equals the current epoch carries valid data: no fence, no separate flag, ONE NVLink hop between "my vector is reduced" and
+// "every peer can read it".  The CTA that holds the rank's reduced vector (1) stores its 2 * nvec words into
+// inbox[slot][my_rank] of every peer (remote stores ride NVLink/NVSwitch), (2) polls its own inbox until the words of every peer
+// show the epoch, (3) adds the `world` vectors in RANK ORDER (its own straight from shared memory), so every rank obtains the
+// bit-identical sum (replicated hyper moves cannot diverge).  Slots alternate with the epoch; a rank cannot lap another by more
+// than one epoch because it needs everybody's words first.  The poll is bounded (~2 s of clock64): on timeout bit 2 of the
+// NaN/err flag is raised instead of hanging.  (The first version — plain stores, __threadfence_system, a flag per peer, a
+// second fence — cost 11-16 us per step at N = 2..8.)
 struct CommArgs {
   int rank, world, nvec;                 // nvec = nval * C doubles per rank
   unsigned long long epoch;
-  double *inbox[8];                      // inbox[r]: base of rank r's inbox, as mapped in THIS process
-  unsigned long long *flags[8];          // flags[r]: base of rank r's flag array
+  double *inbox[8];                      // inbox[r]: base of rank r's inbox (64-bit words), as mapped in THIS process
+  unsigned long long *flags[8];          // unused since the low-latency format (kept: part of the exchanged IPC handle pair)
 };
 
-// all threads of the CTA must call it; `vec` = the local vector in shared memory
+// all threads of the CTA must call it; `vec` = the local vector in shared memory (complete: the caller has synchronised)
 __device__ __forceinline__ void allreduce_exchange(const double *vec, const CommArgs &cm, double *out, int *err_flag) {
   __shared__ int timed_out;
-  const int slot = (int)(cm.epoch & 1ull);
-  for (int r = 0; r < cm.world; ++r) {
-    double *dst = cm.inbox[r] + ((int64_t)slot * cm.world + cm.rank) * cm.nvec;
-    for (int idx = threadIdx.x; idx < cm.nvec; idx += blockDim.x) dst[idx] = vec[idx];
-  }
   if (threadIdx.x == 0) timed_out = 0;
-  __threadfence_system();
   __syncthreads();
-  if ((int)threadIdx.x < cm.world) {
-    volatile unsigned long long *f = cm.flags[threadIdx.x] + (int64_t)slot * cm.world + cm.rank;
-    *f = cm.epoch;
-    volatile unsigned long long *mine = cm.flags[cm.rank] + (int64_t)slot * cm.world + threadIdx.x;
-    const long long t0 = clock64();
-    while (*mine < cm.epoch) {
-      if (clock64() - t0 > 4000000000LL) { timed_out = 1; break; }
+  const int slot = (int)(cm.epoch & 1ull), nw = 2 * cm.nvec;
+  const unsigned ep = (unsigned)cm.epoch;
+  for (int w = threadIdx.x; w < nw; w += blockDim.x) {
+    const double v = vec[w >> 1];
+    const unsigned half = (w & 1) ? (unsigned)__double2hiint(v) : (unsigned)__double2loint(v);
+    const unsigned long long word = ((unsigned long long)ep << 32) | half;
+    for (int r = 0; r < cm.world; ++r) {
+      if (r == cm.rank) continue;
+      unsigned long long *dst = reinterpret_cast<unsigned long long *>(cm.inbox[r]) + ((int64_t)slot * cm.world + cm.rank) * nw + w;
+      asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
     }
   }
-  __threadfence_system();
-  __syncthreads();
-  if (timed_out) { if (threadIdx.x == 0) atomicOr(err_flag, 4); return; }
-  const double *in = cm.inbox[cm.rank] + (int64_t)slot * cm.world * cm.nvec;
+  const unsigned long long *in = reinterpret_cast<const unsigned long long *>(cm.inbox[cm.rank]) + (int64_t)slot * cm.world * nw;
+  const long long t0 = clock64();
   for (int idx = threadIdx.x; idx < cm.nvec; idx += blockDim.x) {
     double v = 0;
-    for (int r = 0; r < cm.world; ++r) v += ((volatile const double *)in)[(int64_t)r * cm.nvec + idx];
+    for (int r = 0; r < cm.world; ++r) {
+      double x = vec[idx];
+      if (r != cm.rank) {
+        const volatile unsigned long long *p = in + (int64_t)r * nw + 2 * idx;
+        unsigned long long a = p[0], b = p[1];
+        while ((unsigned)(a >> 32) != ep || (unsigned)(b >> 32) != ep) {
+          if (clock64() - t0 > 4000000000LL) { timed_out = 1; break; }
+          a = p[0]; b = p[1];
+        }
+        x = __hiloint2double((int)(unsigned)b, (int)(unsigned)a);
+      }
+      v += x;
+    }
     out[idx] = v;
   }
+  __syncthreads();
+  if (timed_out && threadIdx.x == 0) atomicOr(err_flag, 4);
 }
 
 // Fixed-order reduction of the per-CTA rows [C][nblk][nval] into `vec` (shared memory, nvec = nval*C doubles, followed by
@@ -1645,9 +1658,9 @@ int zz_comm_init(zz_handle *h, int rank, int world, void *handle_out) {
   const size_t nvec = (size_t)zz_suffstats_len(h->K) * h->C;
   if (nvec > (size_t)MAX_NSTAT * 8) return fail(h, ZZ_ERR_INVALID, "zz_comm_init: too many chains for the fused all-reduce (nstat * chains <= 296)");
   h->comm_rank = rank; h->comm_world = world; h->comm_epoch = 0;
-  ZZ_CUDA(h, cudaMalloc(&h->comm_inbox, sizeof(double) * 2 * world * nvec));
+  ZZ_CUDA(h, cudaMalloc(&h->comm_inbox, sizeof(double) * 2 * world * 2 * nvec));   // [2 slots][world][2 words per double]
   ZZ_CUDA(h, cudaMalloc(&h->comm_flags, sizeof(unsigned long long) * 2 * world));
-  ZZ_CUDA(h, cudaMemset(h->comm_inbox, 0, sizeof(double) * 2 * world * nvec));
+  ZZ_CUDA(h, cudaMemset(h->comm_inbox, 0, sizeof(double) * 2 * world * 2 * nvec));
   ZZ_CUDA(h, cudaMemset(h->comm_flags, 0, sizeof(unsigned long long) * 2 * world));
   cudaIpcMemHandle_t hs[2];
   ZZ_CUDA(h, cudaIpcGetMemHandle(&hs[0], h->comm_inbox));
