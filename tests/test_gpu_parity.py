@@ -570,3 +570,25 @@ def test_straight_line_tile_handles_beta_and_temperature():
                                 (_capi.SLOT_YG, _capi.SLOT_VARIANCE_G, _capi.SLOT_ALLOC, _capi.SLOT_SPIKE)])
             O.sweep(ho, s, d); h.sweep(step)
             compare_state(h, s)
+
+
+@pytest.mark.parametrize("R,alpha_spread", [(4, 40.0), (16, 100.0), (3, 2.0), (6, 30.0)])
+def test_production_sweep_outside_the_straight_line_preconditions(R, alpha_spread):
+    """The straight-line tile needs max(alpha) <= 16 min(alpha) (one clamp of t serves every library) and R in {2,4,8,16}; anything
+    else must fall back to the generic production tile with the per-library clamp — same draws, same decisions, same caches."""
+    from zigzag_b200 import synth
+    G = 3000
+    hd = dict(synth.truth_hyper_dict(R))
+    hd["alpha_r"] = np.geomspace(0.5, 0.5 * alpha_spread, R)
+    X, gl, hd, st = make_case(G, R, 41, hyper=hd)
+    ho, hg = hyper_pair(hd)
+    s = oracle_state(X, gl, st); O.refresh_caches(ho, s)
+    h = gpu_handle(X, gl, hg, s)
+    for step in range(3):
+        d = np.concatenate([h.philox_draws(step, sl)[:, 0] for sl in
+                            (_capi.SLOT_YG, _capi.SLOT_VARIANCE_G, _capi.SLOT_ALLOC, _capi.SLOT_SPIKE)])
+        O.sweep(ho, s, d); h.sweep(step)
+        compare_state(h, s)
+    st_o, st_g = O.suffstats(ho, s), h.suffstats()[0]
+    fin = np.isfinite(st_o)
+    assert np.allclose(st_g[fin], st_o[fin], rtol=1e-11, atol=1e-9)
