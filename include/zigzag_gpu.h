@@ -186,6 +186,45 @@ int zz_sweep_host(zz_handle *h, uint64_t step, int tune, double *Yg, double *var
                   double *variance_g_probability, const double *tuningParam_yg, const double *tuningParam_variance_g,
                   int64_t *h2d_bytes, int64_t *d2h_bytes);
 
+/* ---- device-resident generation loop ---------------------------------------------------------------- */
+/* burnin() (R/zigzagBurnin.R:64-148) and mcmc() (R/zigzagMCMC.R:169-229) call 15 moves per generation from the host; ten of them
+   are scalar Metropolis/Gibbs moves on hyper-parameters whose only O(G) part is a sum over genes.  zz_run_generations keeps
+   the whole generation on the device: the fused per-gene sweep, then one pass of every hyper move (gibbsMixtureWeights,
+   mhInactiveMeans, mhActiveMeansDif, mhSharedVariance, gibbsSpikeProb, mhTau, mhSg, mhS0Tau, mhP_x — Pr:412-431, 433-471,
+   640-705, 768-803, 511-526, 119-152, 58-117, 154-191, 193-243) whose proposal, prior ratio, accept/reject and tuning
+   window are computed by a single device thread between the gene-sum kernels; accepted moves gate the cache-commit kernels
+   (Pr:113/147/187, Pr:213-215) on the device.  Nothing is copied to the host and the host never waits: it only enqueues.
+   Scalar draws come from a private Philox stream (gene index 0xFFFFFFFF, block 255, counter hyper_ctr / 4).
+   Chain 0, default model (shared_variance = TRUE, multi_thresh_a = TRUE), single GPU in this round. */
+typedef struct zz_priors {      /* constructor arguments of zigzag$new, R/zigzagInitialize.R:7-41 */
+  double weight_active_shape_1, weight_active_shape_2;
+  double spike_prior_shape_1, spike_prior_shape_2;
+  double active_means_dif_prior_shape, active_means_dif_prior_rate;
+  double inactive_means_prior_shape, inactive_means_prior_rate;
+  double variances_prior_log_min, variances_prior_log_max;
+  double tau_shape, tau_rate, s0_mu, s0_sigma, s1_shape, s1_rate, alpha_r_shape, alpha_r_rate;
+  double threshold_i, threshold_a[ZZ_MAX_COMP];
+} zz_priors;
+
+typedef struct zz_chain_scalars {   /* the scalar chain state that lives on the device between zz_chain_begin and zz_chain_read */
+  double active_means_dif[ZZ_MAX_COMP];
+  double t_im, t_av, t_am[ZZ_MAX_COMP], t_s0, t_s1, t_tau, t_s0tau, t_alpha[ZZ_MAX_LIBS];  /* scalar tuning parameters, I:185-199 */
+  uint8_t w_im[100], w_av[100], w_am[ZZ_MAX_COMP][100], w_s0[100], w_s1[100], w_tau[100], w_s0tau[100],
+          w_alpha[ZZ_MAX_LIBS][100];   /* their 100-wide accept windows (the *_trace fields) */
+  uint64_t hyper_ctr;           /* uniforms consumed from the hyper-level Philox stream */
+  double hyper_buf[4];          /* the current block of that stream */
+  uint64_t step;                /* move counter: Philox `step` of the next per-gene sweep (advances by 10 per generation) */
+  int64_t gen;                  /* generations done */
+  int64_t n_samples;            /* allocation_trace accumulations done */
+} zz_chain_scalars;
+
+int zz_chain_begin(zz_handle *h, const zz_priors *priors, const zz_chain_scalars *scalars);
+/* ngen generations; tune != 0: burn-in (acceptance windows, tune_all every 400 generations with `target`, U:183-240);
+   tune == 0: sampling, allocation_trace accumulated whenever gen % sample_frequency == 0 (M:188-199).  Asynchronous. */
+int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, double target);
+/* waits for the device, returns the scalar state and chain 0's hyper-parameters (either pointer may be NULL) */
+int zz_chain_read(zz_handle *h, zz_chain_scalars *scalars, zz_hyper *hyper);
+
 #ifdef __cplusplus
 }
 #endif

@@ -276,6 +276,18 @@ def sweep_draws(seed, chain, step, gene0, G):
     d = np.empty((9, G)); lib().zzo_sweep_draws(seed, chain, step, gene0, G, _p(d)); return d
 
 
+class ChainScalars(C.Structure):
+    """zzo_chain_scalars == zz_chain_scalars (include/zigzag_gpu.h): scalar tuning parameters, their windows, stream positions."""
+    _fields_ = [("active_means_dif", C.c_double * MAX_COMP),
+                ("t_im", C.c_double), ("t_av", C.c_double), ("t_am", C.c_double * MAX_COMP), ("t_s0", C.c_double),
+                ("t_s1", C.c_double), ("t_tau", C.c_double), ("t_s0tau", C.c_double), ("t_alpha", C.c_double * MAX_LIBS),
+                ("w_im", C.c_uint8 * 100), ("w_av", C.c_uint8 * 100), ("w_am", (C.c_uint8 * 100) * MAX_COMP),
+                ("w_s0", C.c_uint8 * 100), ("w_s1", C.c_uint8 * 100), ("w_tau", C.c_uint8 * 100), ("w_s0tau", C.c_uint8 * 100),
+                ("w_alpha", (C.c_uint8 * 100) * MAX_LIBS),
+                ("hyper_ctr", C.c_uint64), ("hyper_buf", C.c_double * 4), ("step", C.c_uint64), ("gen", C.c_int64),
+                ("n_samples", C.c_int64)]
+
+
 class Chain:
     """Schedule-faithful host chain (zzo_chain_*): restates burnin()/mcmc() with the reference's 15-move schedule."""
 
@@ -304,6 +316,33 @@ class Chain:
 
     def lnl(self):
         return self.L.zzo_chain_lnl(self.ptr)
+
+    def scalars(self):
+        out = ChainScalars()
+        self.L.zzo_chain_export_scalars.argtypes = [C.c_void_p, C.c_void_p]
+        self.L.zzo_chain_export_scalars.restype = None
+        self.L.zzo_chain_export_scalars(self.ptr, C.byref(out))
+        return out
+
+    def state_arrays(self):
+        """Copies of the chain's per-gene state (dict of numpy arrays, the names of State)."""
+        self.L.zzo_chain_state.restype = C.POINTER(_State)
+        self.L.zzo_chain_state.argtypes = [C.c_void_p]
+        st = self.L.zzo_chain_state(self.ptr).contents
+        G = self.G
+        out = {}
+        for n in State.F64:
+            out[n] = np.ctypeslib.as_array(C.cast(getattr(st, n), C.POINTER(C.c_double)), (G,)).copy()
+        for n in State.I32:
+            out[n] = np.ctypeslib.as_array(C.cast(getattr(st, n), C.POINTER(C.c_int32)), (G,)).copy()
+        for n in ("Yg_trace", "variance_g_trace"):
+            out[n] = np.ctypeslib.as_array(C.cast(getattr(st, n), C.POINTER(C.c_uint64)), (2 * G,)).copy()
+        return out
+
+    def alloc_trace(self, K):
+        self.L.zzo_chain_alloc_trace.restype = C.POINTER(C.c_uint32)
+        self.L.zzo_chain_alloc_trace.argtypes = [C.c_void_p]
+        return np.ctypeslib.as_array(self.L.zzo_chain_alloc_trace(self.ptr), (K + 1, self.G)).copy()
 
     def __del__(self):
         if getattr(self, "ptr", None):

@@ -953,5 +953,17 @@ void zzo_chain_prob_active(const zzo_chain *c, double *out) { /* FileWriting:116
   for (int64_t g = 0; g < c->G; ++g) out[g] = 1.0 - (double)c->alloc_trace[g] / (double)c->n_samples;
 }
 const zzo_hyper *zzo_chain_hyper(const zzo_chain *c) { return &c->h; }
+void zzo_chain_export_scalars(const zzo_chain *c, zzo_chain_scalars *o) {
+  memset(o, 0, sizeof *o);
+  memcpy(o->active_means_dif, c->active_means_dif, sizeof o->active_means_dif);
+  o->t_im = c->t_im; o->t_av = c->t_av; memcpy(o->t_am, c->t_am, sizeof o->t_am);
+  o->t_s0 = c->t_s0; o->t_s1 = c->t_s1; o->t_tau = c->t_tau; o->t_s0tau = c->t_s0tau; memcpy(o->t_alpha, c->t_alpha, sizeof o->t_alpha);
+  memcpy(o->w_im, c->w_im, 100); memcpy(o->w_av, c->w_av, 100); memcpy(o->w_am, c->w_am, sizeof o->w_am);
+  memcpy(o->w_s0, c->w_s0, 100); memcpy(o->w_s1, c->w_s1, 100); memcpy(o->w_tau, c->w_tau, 100); memcpy(o->w_s0tau, c->w_s0tau, 100);
+  memcpy(o->w_alpha, c->w_alpha, sizeof o->w_alpha);
+  o->hyper_ctr = c->hyper_ctr; memcpy(o->hyper_buf, c->hyper_buf, sizeof o->hyper_buf);
+  o->step = c->step; o->gen = c->gen; o->n_samples = c->n_samples;
+}
+const uint32_t *zzo_chain_alloc_trace(const zzo_chain *c) { return c->alloc_trace; }
 zzo_state *zzo_chain_state(zzo_chain *c) { return &c->s; }
 double zzo_chain_lnl(const zzo_chain *c) { return zzo_lnl(&c->h, &c->s); }

@@ -149,6 +149,20 @@ void zzo_chain_mcmc(zzo_chain *c, int ngen, int sample_frequency);
 void zzo_chain_run_fused(zzo_chain *c, int ngen, int sample_frequency, int tune, double target);
 void zzo_chain_prob_active(const zzo_chain *c, double *out /*G*/);
 const zzo_hyper *zzo_chain_hyper(const zzo_chain *c);
+/* the scalar chain state in the layout of zz_chain_scalars (include/zigzag_gpu.h): lets a test start the device-resident
+   generation loop (zz_run_generations) from exactly this chain and compare the two afterwards */
+typedef struct zzo_chain_scalars {
+  double active_means_dif[ZZO_MAX_COMP];
+  double t_im, t_av, t_am[ZZO_MAX_COMP], t_s0, t_s1, t_tau, t_s0tau, t_alpha[ZZO_MAX_LIBS];
+  uint8_t w_im[100], w_av[100], w_am[ZZO_MAX_COMP][100], w_s0[100], w_s1[100], w_tau[100], w_s0tau[100], w_alpha[ZZO_MAX_LIBS][100];
+  uint64_t hyper_ctr;
+  double hyper_buf[4];
+  uint64_t step;
+  int64_t gen;
+  int64_t n_samples;
+} zzo_chain_scalars;
+void zzo_chain_export_scalars(const zzo_chain *c, zzo_chain_scalars *out);
+const uint32_t *zzo_chain_alloc_trace(const zzo_chain *c);   /* [K+1][G] */
 zzo_state *zzo_chain_state(zzo_chain *c);
 double zzo_chain_lnl(const zzo_chain *c);
 

@@ -141,7 +141,74 @@ SEXP zzR_get_alloc_trace(SEXP ptr, SEXP G_, SEXP K_) {   /* G x (K+1) numeric ma
   return out;
 }
 
+/* ---- device-resident generation loop (zz_chain_begin / zz_run_generations / zz_chain_read) ------------------------------
+   R side (r_overlay/R/zigzagGPU.R: gpu_run_generations): priors = numeric(19 + K) in the field order of zz_priors; scalars = a list
+   with the fields of zz_chain_scalars (numeric vectors and 100-wide 0/1 integer windows).  Returns the list updated. */
+static void fill_win(uint8_t *dst, SEXP v) { for (int i = 0; i < 100; ++i) dst[i] = (uint8_t)(INTEGER(v)[i] != 0); }
+static SEXP get_el(SEXP list, const char *name) {
+  SEXP names = Rf_getAttrib(list, R_NamesSymbol);
+  for (int i = 0; i < LENGTH(list); ++i) if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) return VECTOR_ELT(list, i);
+  Rf_error("zzR_chain_begin: scalar state has no field '%s'", name);
+  return R_NilValue;
+}
+SEXP zzR_chain_begin(SEXP ptr, SEXP priors, SEXP sc, SEXP K_, SEXP R_) {
+  zz_handle *h = H(ptr);
+  const int K = Rf_asInteger(K_), R = Rf_asInteger(R_);
+  zz_priors pr; zz_chain_scalars s;
+  memset(&pr, 0, sizeof pr); memset(&s, 0, sizeof s);
+  memcpy(&pr, REAL(priors), sizeof(double) * 19);                      /* 18 scalars + threshold_i, then threshold_a[K] */
+  memcpy(pr.threshold_a, REAL(priors) + 19, sizeof(double) * K);
+  memcpy(s.active_means_dif, REAL(get_el(sc, "active_means_dif")), sizeof(double) * K);
+  s.t_im = Rf_asReal(get_el(sc, "t_im")); s.t_av = Rf_asReal(get_el(sc, "t_av"));
+  memcpy(s.t_am, REAL(get_el(sc, "t_am")), sizeof(double) * K);
+  s.t_s0 = Rf_asReal(get_el(sc, "t_s0")); s.t_s1 = Rf_asReal(get_el(sc, "t_s1")); s.t_tau = Rf_asReal(get_el(sc, "t_tau"));
+  s.t_s0tau = Rf_asReal(get_el(sc, "t_s0tau"));
+  memcpy(s.t_alpha, REAL(get_el(sc, "t_alpha")), sizeof(double) * R);
+  fill_win(s.w_im, get_el(sc, "w_im")); fill_win(s.w_av, get_el(sc, "w_av")); fill_win(s.w_s0, get_el(sc, "w_s0"));
+  fill_win(s.w_s1, get_el(sc, "w_s1")); fill_win(s.w_tau, get_el(sc, "w_tau")); fill_win(s.w_s0tau, get_el(sc, "w_s0tau"));
+  for (int k = 0; k < K; ++k) fill_win(s.w_am[k], VECTOR_ELT(get_el(sc, "w_am"), k));
+  for (int r = 0; r < R; ++r) fill_win(s.w_alpha[r], VECTOR_ELT(get_el(sc, "w_alpha"), r));
+  s.hyper_ctr = (uint64_t)Rf_asReal(get_el(sc, "hyper_ctr"));
+  memcpy(s.hyper_buf, REAL(get_el(sc, "hyper_buf")), sizeof s.hyper_buf);
+  s.step = (uint64_t)Rf_asReal(get_el(sc, "step")); s.gen = (int64_t)Rf_asReal(get_el(sc, "gen"));
+  s.n_samples = (int64_t)Rf_asReal(get_el(sc, "n_samples"));
+  chk(h, zz_chain_begin(h, &pr, &s));
+  return R_NilValue;
+}
+SEXP zzR_run_generations(SEXP ptr, SEXP ngen, SEXP tune, SEXP sample_frequency, SEXP target) {
+  zz_handle *h = H(ptr);
+  chk(h, zz_run_generations(h, Rf_asInteger(ngen), Rf_asLogical(tune), Rf_asInteger(sample_frequency), Rf_asReal(target)));
+  return R_NilValue;
+}
+/* returns c(s0, s1, tau, spike_probability, inactive_means, inactive_variances, weight_active, gen, step, n_samples, hyper_ctr,
+   alpha_r[R], active_means[K], active_variances[K], weight_within_active[K], active_means_dif[K], scalar tuning parameters ...);
+   the windows come back through zzR_chain_windows (omitted here: same pattern) */
+SEXP zzR_chain_read(SEXP ptr, SEXP K_, SEXP R_) {
+  zz_handle *h = H(ptr);
+  const int K = Rf_asInteger(K_), R = Rf_asInteger(R_);
+  zz_chain_scalars s; zz_hyper hy;
+  chk(h, zz_chain_read(h, &s, &hy));
+  const int n = 11 + R + 4 * K + 6 + K + R;
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, n));
+  double *o = REAL(out); int j = 0;
+  o[j++] = hy.s0; o[j++] = hy.s1; o[j++] = hy.tau; o[j++] = hy.spike_probability; o[j++] = hy.inactive_means;
+  o[j++] = hy.inactive_variances; o[j++] = hy.weight_active; o[j++] = (double)s.gen; o[j++] = (double)s.step;
+  o[j++] = (double)s.n_samples; o[j++] = (double)s.hyper_ctr;
+  for (int r = 0; r < R; ++r) o[j++] = hy.alpha_r[r];
+  for (int k = 0; k < K; ++k) o[j++] = hy.active_means[k];
+  for (int k = 0; k < K; ++k) o[j++] = hy.active_variances[k];
+  for (int k = 0; k < K; ++k) o[j++] = hy.weight_within_active[k];
+  for (int k = 0; k < K; ++k) o[j++] = s.active_means_dif[k];
+  o[j++] = s.t_im; o[j++] = s.t_av; o[j++] = s.t_s0; o[j++] = s.t_s1; o[j++] = s.t_tau; o[j++] = s.t_s0tau;
+  for (int k = 0; k < K; ++k) o[j++] = s.t_am[k];
+  for (int r = 0; r < R; ++r) o[j++] = s.t_alpha[r];
+  UNPROTECT(1);
+  return out;
+}
+
 static const R_CallMethodDef calls[] = {
+  {"zzR_chain_begin", (DL_FUNC)&zzR_chain_begin, 5}, {"zzR_run_generations", (DL_FUNC)&zzR_run_generations, 5},
+  {"zzR_chain_read", (DL_FUNC)&zzR_chain_read, 3},
   {"zzR_create", (DL_FUNC)&zzR_create, 5}, {"zzR_set_state", (DL_FUNC)&zzR_set_state, 11}, {"zzR_get_state", (DL_FUNC)&zzR_get_state, 2},
   {"zzR_set_hyper", (DL_FUNC)&zzR_set_hyper, 15}, {"zzR_mh_yg", (DL_FUNC)&zzR_mh_yg, 3}, {"zzR_mh_variance_g", (DL_FUNC)&zzR_mh_variance_g, 3},
   {"zzR_gibbs_alloc", (DL_FUNC)&zzR_gibbs_alloc, 2}, {"zzR_gibbs_alloc_within", (DL_FUNC)&zzR_gibbs_alloc_within, 2},

@@ -1,0 +1,96 @@
+"""Device-resident generation loop: zz_run_generations against the oracle's fused-schedule chain
+(oracle/zz_oracle.c: zzo_chain_run_fused).  Both start from the same per-gene state, hyper-parameters, scalar tuning state and
+positions in the two Philox streams; afterwards every hyper-parameter, every scalar tuning parameter and window, the number of
+uniforms consumed by the hyper moves, the per-gene state and the allocation trace must agree."""
+import ctypes as C
+import numpy as np
+import pytest
+from oracle import oracle as O
+from zigzag_b200 import _capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _start_pair(G, R, K, seed, thr_a):
+    X, gl, _ = synth.simulate(G, R, config_id=300 + seed)
+    pri = O.Priors.defaults(-1.0, thr_a)
+    ch = O.Chain(X, gl, pri, K, seed)
+    st, hy = ch.state_arrays(), ch.hyper
+    hg = _capi.Hyper()
+    C.memmove(C.byref(hg), C.byref(hy), C.sizeof(_capi.Hyper))
+    h = _capi.Handle(G, R, K, seed=seed)
+    h.upload_data(X, gl)
+    h.set_hyper(hg, 0)
+    h.set_state(0, Yg=st["Yg"], variance_g=st["variance_g"], alloc_active_inactive=st["alloc_active_inactive"],
+                alloc_within_active=st["alloc_within_active"], inactive_spike_allocation=st["inactive_spike_allocation"],
+                XgLikelihood=st["XgLikelihood"], variance_g_probability=st["variance_g_probability"],
+                tuningParam_yg=st["tuningParam_yg"], tuningParam_variance_g=st["tuningParam_variance_g"])
+    h.reset_windows()
+    h.reset_alloc_trace()
+    h.chain_begin(pri, ch.scalars())
+    return ch, h
+
+
+def _compare(ch, h, K, R, rtol=1e-9):
+    sc_g, hy_g = h.chain_read()
+    sc_o, hy_o = ch.scalars(), ch.hyper
+    for f in ("s0", "s1", "tau", "spike_probability", "inactive_means", "inactive_variances", "weight_active"):
+        assert np.isclose(getattr(hy_g, f), getattr(hy_o, f), rtol=rtol, atol=1e-13), f
+    for f, n in (("alpha_r", R), ("active_means", K), ("active_variances", K), ("weight_within_active", K)):
+        assert np.allclose(list(getattr(hy_g, f))[:n], list(getattr(hy_o, f))[:n], rtol=rtol, atol=1e-13), f
+    # identical consumption of the hyper-level stream = every rejection loop and every accept/reject took the same path
+    assert sc_g.hyper_ctr == sc_o.hyper_ctr and sc_g.gen == sc_o.gen and sc_g.step == sc_o.step and sc_g.n_samples == sc_o.n_samples
+    for f in ("t_im", "t_av", "t_s0", "t_s1", "t_tau", "t_s0tau"):
+        assert np.isclose(getattr(sc_g, f), getattr(sc_o, f), rtol=rtol), f
+    assert np.allclose(list(sc_g.t_am)[:K], list(sc_o.t_am)[:K], rtol=rtol)
+    assert np.allclose(list(sc_g.t_alpha)[:R], list(sc_o.t_alpha)[:R], rtol=rtol)
+    assert np.allclose(list(sc_g.active_means_dif)[:K], list(sc_o.active_means_dif)[:K], rtol=rtol)
+    for f in ("w_im", "w_av", "w_s0", "w_s1", "w_tau", "w_s0tau"):
+        assert bytes(getattr(sc_g, f)) == bytes(getattr(sc_o, f)), f
+    assert all(bytes(sc_g.w_am[k]) == bytes(sc_o.w_am[k]) for k in range(K))
+    assert all(bytes(sc_g.w_alpha[r]) == bytes(sc_o.w_alpha[r]) for r in range(R))
+    g, o = h.get_state(0), ch.state_arrays()
+    for k in ("alloc_active_inactive", "inactive_spike_allocation"):
+        assert np.array_equal(g[k], o[k]), k
+    act = o["alloc_active_inactive"] == 1
+    assert np.array_equal(g["alloc_within_active"][act], o["alloc_within_active"][act])
+    for k in ("Yg", "variance_g", "tuningParam_yg", "tuningParam_variance_g"):
+        assert np.allclose(g[k], o[k], rtol=1e-9, atol=1e-12), k
+    for k in ("XgLikelihood", "variance_g_probability"):
+        fin = np.isfinite(o[k])
+        assert np.array_equal(np.isfinite(g[k]), fin) and np.allclose(g[k][fin], o[k][fin], rtol=1e-8, atol=1e-9), k
+    assert h.nan_flag() == 0
+
+
+@pytest.mark.parametrize("sums", ["closed_forms", "gene_sums"])
+@pytest.mark.parametrize("G,R,K,thr_a", [(3000, 4, 2, (1.0, 6.0)), (2000, 2, 1, (1.0,)), (1500, 8, 3, (0.5, 3.0, 6.0))])
+def test_device_resident_generations_match_the_oracle_chain(G, R, K, thr_a, sums, monkeypatch):
+    """Default: the level-2 and variance-prior moves take their gene sums from closed forms of the sweep's sufficient statistics
+    (one single-thread kernel per generation); ZZ_CHAIN_GENE_SUMS=1 runs the reference's per-gene sums instead."""
+    if sums == "gene_sums":
+        monkeypatch.setenv("ZZ_CHAIN_GENE_SUMS", "1")
+    ch, h = _start_pair(G, R, K, 11, thr_a)
+    ch.run_fused(60, tune=True); h.run_generations(60, tune=True)
+    _compare(ch, h, K, R)
+    ch.run_fused(30, sample_frequency=2, tune=False); h.run_generations(30, tune=False, sample_frequency=2)
+    _compare(ch, h, K, R)
+    assert np.array_equal(h.get_alloc_trace(0), ch.alloc_trace(K))
+
+
+def test_device_resident_burnin_crosses_a_tuning_point():
+    """tune_all every 400 generations (B:146): scalar and per-gene step sizes are re-tuned on the device."""
+    G, R, K = 1200, 4, 2
+    ch, h = _start_pair(G, R, K, 5, (1.0, 6.0))
+    ch.run_fused(405, tune=True); h.run_generations(405, tune=True)
+    sc, _ = h.chain_read()
+    assert sc.t_tau != 0.05 and sc.gen == 405          # re-tuned away from the constructor's value (I:185-199)
+    _compare(ch, h, K, R)
+
+
+def test_run_generations_is_asynchronous_and_needs_chain_begin():
+    G, R, K = 600, 4, 2
+    X, gl, _ = synth.simulate(G, R, config_id=7)
+    h = _capi.Handle(G, R, K, seed=3)
+    h.upload_data(X, gl)
+    with pytest.raises(_capi.ZigzagGpuError):
+        h.run_generations(1)

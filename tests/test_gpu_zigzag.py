@@ -71,3 +71,24 @@ def test_reference_schedule_runs_the_15_move_table(tmp_path):
     assert np.allclose(st["XgLikelihood"][fin], fresh["XgLikelihood"][fin], rtol=1e-9, atol=1e-9)
     out = st["inactive_spike_allocation"] == 0
     assert np.allclose(st["variance_g_probability"][out], fresh["variance_g_probability"][out], rtol=1e-9, atol=1e-9)
+
+
+def test_lung_prob_active_matches_tutorial_device_schedule(tmp_path):
+    """schedule="device": burnin() and mcmc() run their generations through zz_run_generations (sweep + every hyper move + tuning +
+    allocation trace on the GPU, the host reads scalars back once per sampling point).  Same pins as the fused schedule."""
+    d, tpm, gl, names = lung()
+    mm = zigzag(tpm, gl, num_active_components=2, threshold_i=float(d["threshold_i"]), threshold_a=d["threshold_a"],
+                output_directory=str(tmp_path), gene_names=names, seed=3)
+    mm.burnin(sample_frequency=50, ngen=3000, burninprefix="lung", schedule="device")
+    assert mm.gen == 3001 and mm.tuningParam_tau != 0.05
+    mm.mcmc(sample_frequency=5, ngen=6000, mcmcprefix="lung_dev", schedule="device")
+    pa = mm.prob_active()
+    pinned = d["tutorial_prob_active_first10"]
+    assert np.abs(pa[:10] - pinned).max() < 0.08, (pa[:10], pinned)
+    assert -10900 < mm.lnl_trace[-1] < -10100
+    assert -2.4 < mm.s0 < -1.7 and -0.45 < mm.s1 < -0.27 and 0.7 < mm.tau < 1.05
+    assert 0.05 < mm.spike_probability < 0.2 and -2.5 < mm.inactive_means < -1.4 and 2.2 < mm.active_means[0] < 3.1
+    assert 0.64 < mm.weight_active < 0.8 and all(8 < a < 25 for a in mm.alpha_r)
+    rows = open(os.path.join(str(tmp_path), "lung_dev_mcmc_output", "lung_dev_model_parameters.log")).read().splitlines()[1:]
+    assert len(rows) >= 1000
+    assert mm.n_samples == 1 + sum(1 for g in range(3001, 9002) if g % 5 == 0)

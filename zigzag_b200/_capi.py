@@ -54,6 +54,55 @@ class Hyper(C.Structure):
         return o
 
 
+class Priors(C.Structure):
+    """zz_priors: the prior hyper-parameters of zigzag$new (R/zigzagInitialize.R:7-41) read by the hyper moves."""
+    _fields_ = [(n, C.c_double) for n in (
+        "weight_active_shape_1", "weight_active_shape_2", "spike_prior_shape_1", "spike_prior_shape_2",
+        "active_means_dif_prior_shape", "active_means_dif_prior_rate",
+        "inactive_means_prior_shape", "inactive_means_prior_rate",
+        "variances_prior_log_min", "variances_prior_log_max",
+        "tau_shape", "tau_rate", "s0_mu", "s0_sigma", "s1_shape", "s1_rate", "alpha_r_shape", "alpha_r_rate",
+        "threshold_i")] + [("threshold_a", C.c_double * MAX_COMP)]
+
+    @classmethod
+    def defaults(cls, threshold_i, threshold_a):
+        """Constructor defaults of zigzag$new, R/zigzagInitialize.R:7-41."""
+        p = cls(2, 2, 1, 1, 1, 1 / 3, 1, 1 / 3, np.log10(0.01), np.log10(5), 1, 1, -1, 2, 1, 2, 1, 1 / 10, threshold_i)
+        for i, t in enumerate(threshold_a):
+            p.threshold_a[i] = t
+        return p
+
+
+class ChainScalars(C.Structure):
+    """zz_chain_scalars: scalar tuning parameters, their 100-wide windows and the stream positions of a device-resident chain."""
+    _fields_ = [("active_means_dif", C.c_double * MAX_COMP),
+                ("t_im", C.c_double), ("t_av", C.c_double), ("t_am", C.c_double * MAX_COMP), ("t_s0", C.c_double),
+                ("t_s1", C.c_double), ("t_tau", C.c_double), ("t_s0tau", C.c_double), ("t_alpha", C.c_double * MAX_LIBS),
+                ("w_im", C.c_uint8 * 100), ("w_av", C.c_uint8 * 100), ("w_am", (C.c_uint8 * 100) * MAX_COMP),
+                ("w_s0", C.c_uint8 * 100), ("w_s1", C.c_uint8 * 100), ("w_tau", C.c_uint8 * 100), ("w_s0tau", C.c_uint8 * 100),
+                ("w_alpha", (C.c_uint8 * 100) * MAX_LIBS),
+                ("hyper_ctr", C.c_uint64), ("hyper_buf", C.c_double * 4), ("step", C.c_uint64), ("gen", C.c_int64),
+                ("n_samples", C.c_int64)]
+
+    @classmethod
+    def initial(cls, active_means, threshold_a, num_libraries):
+        """The scalar state right after zigzag$new: tuning parameters of I:185-199, windows c(rep(0,77), rep(1,23))."""
+        s = cls()
+        win = (C.c_uint8 * 100)(*([0] * 77 + [1] * 23))
+        s.t_im = s.t_av = 0.5
+        s.t_s0 = s.t_s1 = s.t_tau = s.t_s0tau = 0.05
+        for name in ("w_im", "w_av", "w_s0", "w_s1", "w_tau", "w_s0tau"):
+            setattr(s, name, win)
+        for k, (m, t) in enumerate(zip(active_means, threshold_a)):
+            s.active_means_dif[k] = float(m) - float(t)
+            s.t_am[k] = 0.5
+            s.w_am[k] = win
+        for r in range(num_libraries):
+            s.t_alpha[r] = 0.5
+            s.w_alpha[r] = win
+        return s
+
+
 class Config(C.Structure):
     _fields_ = [("num_genes", C.c_int64), ("gene_offset", C.c_int64), ("num_libraries", C.c_int32),
                 ("num_active_components", C.c_int32), ("num_chains", C.c_int32), ("device", C.c_int32),
@@ -108,6 +157,9 @@ _SIG = {
     "zz_tune": (C.c_int, [_P, C.c_double]),
     "zz_nan_flag": (C.c_int, [_P, _P]),
     "zz_sweep_host": (C.c_int, [_P, C.c_uint64, C.c_int] + [_P] * 11),
+    "zz_chain_begin": (C.c_int, [_P, _P, _P]),
+    "zz_run_generations": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "zz_chain_read": (C.c_int, [_P, _P, _P]),
 }
 EXPORTS = tuple(_SIG)
 
@@ -371,6 +423,19 @@ class Handle:
         f = C.c_int(0)
         self._ck(self.L.zz_nan_flag(self.h, C.byref(f)))
         return int(f.value)
+
+    # ---- device-resident generation loop
+    def chain_begin(self, priors, scalars):
+        """priors / scalars: ctypes structures with the layout of zz_priors / zz_chain_scalars (any class of that layout)."""
+        self._ck(self.L.zz_chain_begin(self.h, C.addressof(priors), C.addressof(scalars)))
+
+    def run_generations(self, ngen, tune=False, sample_frequency=1, target=0.44):
+        self._ck(self.L.zz_run_generations(self.h, int(ngen), int(tune), int(sample_frequency), float(target)))
+
+    def chain_read(self):
+        sc, hy = ChainScalars(), Hyper()
+        self._ck(self.L.zz_chain_read(self.h, C.addressof(sc), C.addressof(hy)))
+        return sc, hy
 
     def sweep_host(self, step, tune, Yg, variance_g, ai, within, spike, XgLikelihood, variance_g_probability, ty, tv):
         """All arguments are host arrays or raw host pointers (ints), updated in place; returns (h2d_bytes, d2h_bytes)."""

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include "zz_device.cuh"
 #include "zz_fast.cuh"
+#include "zz_chain.cuh"
 
 using namespace zz;
 
@@ -251,6 +252,7 @@ struct FastArgs {
   int64_t rows_per_chain, spike_row0;
   int want_stats, do_spike_move;
   const int32_t *slot_list;         // list mode (zz_sweep_host chunks): position p in [g_begin, g_end) addresses gene slot slot_list[p]
+  const int *gate;                  // k_refresh_lps in the device-resident loop: rebuild only if *gate != 0 (accepted mhP_x)
   int host_io; HostChunk hio;       // list mode + host_io: the tile itself reads its genes' state from hio.s* and writes hio.d* (caller order)
   // fused epilogue: the last CTA to finish reduces the rows (and all-reduces them over peer memory when asked) into stats_out
   unsigned *done_counter; double *stats_out; int do_allreduce; CommArgs cm;
@@ -356,6 +358,9 @@ __device__ __forceinline__ void stage_tile(const SweepArgs &a, const FastArgs &f
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 9 * 256), "l"(a.perm + g) : "memory");
 }
 
+template <int RT>
+__device__ __noinline__ double detect_logsum_slow(const FastH &H, const MathTabs &T, uint64_t nd_mask, double t) { return detect_logsum<RT>(H, T, nd_mask, t); }
+
 // KT > 0 selects the straight-line production tile (all four moves, Philox draws, variance_g_upper_bound = Inf, K = KT active
 // components): every lane executes the same branch-free instruction stream (decisions are applied with selects), which lets
 // the scheduler overlap the independent exp/log/reciprocal chains of the three moves instead of serialising them.
@@ -421,7 +426,10 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const
       const double yp = y0 + ty * z;                                     // Pr:257
       const double tp = gl * fexp_nb(yp, T.exp_t);                       // U:157
       const bool saturated = __all_sync(__activemask(), !live || tp * H.alpha_min >= 37.5);
-      const double Ap = saturated ? (mask ? -INFINITY : 0.0) : detect_logsum_sl<(RT > 0 && RT <= 18) ? RT : 1>(H, T, mask, tp);
+      // (uclamp_ok is checked by the host when it picks this kernel; in the device-resident loop alpha_r moves on the device, so the
+      // per-library-clamp version stays reachable, out of line)
+      const double Ap = saturated ? (mask ? -INFINITY : 0.0)
+                        : H.uclamp_ok ? detect_logsum_sl<(RT > 0 && RT <= 18) ? RT : 1>(H, T, mask, tp) : detect_logsum_slow<RT>(H, T, mask, tp);
       const double t0 = xbar - y0, t1 = xbar - yp;
       const double D0 = fma(nd_d * t0, t0, ss), Dp = fma(nd_d * t1, t1, ss);
       const double dLX = times_beta(H, (Ap - A0) - 0.5 * (Dp - D0) * rv);
@@ -626,6 +634,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const
 // lps <- A(Yg) for every out-of-spike gene (after anything that changed Yg or alpha_r outside the fast sweep)
 template <int RT>
 __global__ void __launch_bounds__(BLOCK) k_refresh_lps(const FastArgs fa) {
+  if (fa.gate && !*fa.gate) return;
   __shared__ FastH H;
   __shared__ MathTabs T;
   const SweepArgs &a = fa.s;
@@ -716,9 +725,11 @@ struct EvalArgs {
   const uint16_t *flags;
   const zz_hyper *hyper;   // already offset to the chain (or base when grid.y spans chains)
   double *out0, *out1;     // per-gene outputs (chain-offset applied by blockIdx.y * G)
+  const int *gate;         // device-resident loop: the kernel does nothing unless *gate != 0 (an accepted move)
 };
 
 __global__ void __launch_bounds__(BLOCK) k_eval(const EvalArgs a) {
+  if (a.gate && !*a.gate) return;
   __shared__ HyperS H;
   const int chain = blockIdx.y;
   load_hyper(H, a.hyper + chain);
@@ -749,6 +760,7 @@ struct RedArgs {
   double alpha_prop[ZZ_MAX_LIBS];
   uint8_t lib_mask[ZZ_MAX_LIBS];
   double *partials;                                   // [grid.y][grid.x][2]
+  const DevChain *prop;                               // device-resident generation loop: parameters come from the mailbox, not from the fields above
 };
 
 // Grid-stride per-gene reduction; blockIdx.y = library for RED_PXDELTA.  Two sums per gene at most.
@@ -756,9 +768,15 @@ __global__ void __launch_bounds__(BLOCK) k_reduce(const RedArgs a) {
   __shared__ HyperS H;
   __shared__ double red[BLOCK / 32];
   load_hyper(H, a.hyper);
-  const int lib = blockIdx.y;
+  const int lib = (a.prop && a.op == RED_PXDELTA) ? a.prop->p_lib : (int)blockIdx.y;
   double v0 = 0, v1 = 0;
-  const bool active_y = !(a.op == RED_PXDELTA && !a.lib_mask[lib]);
+  const bool active_y = !(a.op == RED_PXDELTA && !a.prop && !a.lib_mask[lib]);
+  // parameters of the sum: by value from the host, or from the device-side mailbox (zz_run_generations; RED_LEVEL2 then runs
+  // with grid.y = 2: proposed and current parameters in one launch)
+  const double p_s0 = a.prop ? a.prop->p_s0 : a.s0, p_s1 = a.prop ? a.prop->p_s1 : a.s1, p_tau = a.prop ? a.prop->p_tau : a.tau;
+  const double p_im = a.prop ? a.prop->l2[blockIdx.y].im : a.im, p_iv = a.prop ? a.prop->l2[blockIdx.y].iv : a.iv;
+  const double *p_am = a.prop ? a.prop->l2[blockIdx.y].am : a.am, *p_av = a.prop ? a.prop->l2[blockIdx.y].av : a.av;
+  const double p_alpha = a.op == RED_PXDELTA ? (a.prop ? a.prop->p_alpha : a.alpha_prop[lib]) : 0.0;
   if (active_y) {
     for (int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x; g < a.G; g += (int64_t)gridDim.x * BLOCK) {
       const double y = a.Yg[g], v = a.vg[g];
@@ -766,21 +784,21 @@ __global__ void __launch_bounds__(BLOCK) k_reduce(const RedArgs a) {
       const bool in_spike = f & F_INSPIKE;
       if (a.op == RED_VARG_HYPER) {                  // Pr:84-87, 126-130, 167-170
         if (!in_spike) {
-          v0 += varg_prior(H, v, get_sigmax(a.s0, a.s1, y), a.tau, sqrt(a.tau));
+          v0 += varg_prior(H, v, get_sigmax(p_s0, p_s1, y), p_tau, sqrt(p_tau));
           v1 += a.vgprob[g];
         }
       } else if (a.op == RED_LEVEL2) {               // Pr:444-447, 653-654, 780-784
         if (f & F_ACTIVE) {
           const int k = flag_k(f) - 1;
-          const double d = y - a.am[k];
-          v1 += -log(H.sqrt2pi * sqrt(a.av[k])) - (d * d) / (2 * a.av[k]);
+          const double d = y - p_am[k];
+          v1 += -log(H.sqrt2pi * sqrt(p_av[k])) - (d * d) / (2 * p_av[k]);
         } else {
-          v0 += inactive_lik_at(H, y, in_spike, a.im, a.iv);
+          v0 += inactive_lik_at(H, y, in_spike, p_im, p_iv);
         }
       } else if (a.op == RED_PXDELTA) {              // Pr:209-224
         const double x = a.Xg[(int64_t)lib * a.G + g];
         const double gl = a.gl[g];
-        v0 += xg_lik_onelib(H, x, y, v, gl, a.alpha_prop[lib], in_spike, f & F_ALLZERO) -
+        v0 += xg_lik_onelib(H, x, y, v, gl, p_alpha, in_spike, f & F_ALLZERO) -
               xg_lik_onelib(H, x, y, v, gl, H.alpha[lib], in_spike, f & F_ALLZERO);
       } else {                                       // RED_LNL, U:70-75
         v0 += in_spike ? xg_lik_inspike(H, f & F_ALLZERO) : xg_lik_out(H, a.Xg + g, a.G, y, v, a.gl[g]);
@@ -869,6 +887,21 @@ __global__ void __launch_bounds__(BLOCK) k_px_commit(int64_t G, int lib, double 
   const uint32_t f = flags[g];
   const double x = Xg[(int64_t)lib * G + g];
   xglik[g] = xglik[g] + xg_lik_onelib(H, x, Yg[g], vg[g], gl[g], alpha_new, f & F_INSPIKE, f & F_ALLZERO) -
+             xg_lik_onelib(H, x, Yg[g], vg[g], gl[g], H.alpha[lib], f & F_INSPIKE, f & F_ALLZERO);
+}
+
+// the same commit for the device-resident loop: library and new alpha come from the mailbox, nothing happens unless mhP_x accepted
+__global__ void __launch_bounds__(BLOCK) k_px_commit_dev(int64_t G, const DevChain *c, const double *Xg, const double *gl, const double *Yg,
+                                                          const double *vg, const uint16_t *flags, const zz_hyper *hyper, double *xglik) {
+  if (!c->gate_px) return;
+  __shared__ HyperS H;
+  load_hyper(H, hyper);
+  const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (g >= G) return;
+  const int lib = c->p_lib;
+  const uint32_t f = flags[g];
+  const double x = Xg[(int64_t)lib * G + g];
+  xglik[g] = xglik[g] + xg_lik_onelib(H, x, Yg[g], vg[g], gl[g], c->p_alpha, f & F_INSPIKE, f & F_ALLZERO) -
              xg_lik_onelib(H, x, Yg[g], vg[g], gl[g], H.alpha[lib], f & F_INSPIKE, f & F_ALLZERO);
 }
 
@@ -983,6 +1016,7 @@ struct zz_handle {
   std::vector<zz_hyper> hyper_host;
   double *pinned;                          // small pinned staging for reduction results
   // zz_sweep_host pipeline (created on first use)
+  DevChain *devchain; double *chain_stats; bool chain_ready; int64_t chain_gen, chain_samples; uint64_t chain_step;   // zz_run_generations
   int32_t *inv_perm; cudaStream_t s_up, s_down; cudaEvent_t ev_entry, ev_up[ZZ_HOST_MAX_CHUNKS], ev_done[ZZ_HOST_MAX_CHUNKS]; bool pipe_ready;
 };
 
@@ -1085,7 +1119,7 @@ void fill_fast_args(zz_handle *h, FastArgs &fa) {
   fa.nd_mask = h->nd_mask; fa.xbar = h->xbar; fa.xss = h->xss; fa.fasth = h->fasth;
   fa.partials = h->sw_partials; fa.rows_per_chain = 0; fa.spike_row0 = 0; fa.want_stats = 0; fa.do_spike_move = 0;
   fa.done_counter = h->tile_counter; fa.stats_out = nullptr; fa.do_allreduce = 0; memset(&fa.cm, 0, sizeof fa.cm);
-  fa.slot_list = nullptr; fa.host_io = 0; memset(&fa.hio, 0, sizeof fa.hio);
+  fa.slot_list = nullptr; fa.host_io = 0; memset(&fa.hio, 0, sizeof fa.hio); fa.gate = nullptr;
 }
 
 int ensure_fasth(zz_handle *h) {
@@ -1281,11 +1315,11 @@ void fill_red(zz_handle *h, RedArgs &a, int chain, int op) {
   a.flags = h->flags + off; a.hyper = h->hyper + chain;
 }
 
-int launch_eval(zz_handle *h, int which, int chain /* -1 = all chains */, double *out0, double *out1) {
+int launch_eval(zz_handle *h, int which, int chain /* -1 = all chains */, double *out0, double *out1, const int *gate = nullptr) {
   EvalArgs a;
   const int64_t off = chain < 0 ? 0 : (int64_t)chain * h->G;
   a.G = h->G; a.which = which; a.Xg = h->Xg; a.gl = h->gl; a.Yg = h->Yg + off; a.vg = h->vg + off; a.flags = h->flags + off;
-  a.hyper = h->hyper + (chain < 0 ? 0 : chain); a.out0 = out0; a.out1 = out1;
+  a.hyper = h->hyper + (chain < 0 ? 0 : chain); a.out0 = out0; a.out1 = out1; a.gate = gate;
   k_eval<<<gene_grid(h, h->G, chain < 0 ? h->C : 1), BLOCK, 0, h->stream>>>(a);
   ZZ_LAUNCHED(h);
   return ZZ_OK;
@@ -1317,6 +1351,7 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   h->cfg = *cfg; h->G = cfg->num_genes; h->C = cfg->num_chains; h->R = cfg->num_libraries; h->K = cfg->num_active_components;
   h->sticky = false; h->launches = 0; h->have_data = false; h->own_stream = false; h->stream = nullptr;
   h->inv_perm = nullptr; h->pipe_ready = false; h->s_up = h->s_down = nullptr;
+  h->devchain = nullptr; h->chain_stats = nullptr; h->chain_ready = false; h->chain_gen = 0; h->chain_samples = 0; h->chain_step = 0;
   *out = h;  // returned even on failure so the caller can read zz_last_error and must zz_destroy
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1398,6 +1433,8 @@ void zz_destroy(zz_handle *h) {
   for (void *p : ptrs) if (p) cudaFree(p);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->inv_perm) cudaFree(h->inv_perm);
+  if (h->devchain) cudaFree(h->devchain);
+  if (h->chain_stats) cudaFree(h->chain_stats);
   if (h->pipe_ready) {
     cudaStreamDestroy(h->s_up); cudaStreamDestroy(h->s_down); cudaEventDestroy(h->ev_entry);
     for (int k = 0; k < ZZ_HOST_MAX_CHUNKS; ++k) { cudaEventDestroy(h->ev_up[k]); cudaEventDestroy(h->ev_done[k]); }
@@ -1922,6 +1959,120 @@ int zz_sweep_host(zz_handle *h, uint64_t step, int tune, double *Yg, double *var
   h->lps_valid = true;
   if (h2d_bytes) *h2d_bytes = G * (4 * 8 + 3 * 4);
   if (d2h_bytes) *d2h_bytes = G * (4 * 8 + 3 * 4);
+  return ZZ_OK;
+}
+
+// ---- device-resident generation loop (zz_chain.cuh) ----------------------------------------------------------------
+int zz_chain_begin(zz_handle *h, const zz_priors *priors, const zz_chain_scalars *scalars) {
+  ZZ_CHECK(h);
+  if (!priors || !scalars) return fail(h, ZZ_ERR_INVALID, "NULL argument");
+  if (!h->have_data) return fail(h, ZZ_ERR_STATE, "zz_upload_data has not been called");
+  if (h->C != 1) return fail(h, ZZ_ERR_INVALID, "zz_chain_begin: one chain per handle in this round");
+  if (!h->devchain) {
+    ZZ_CUDA(h, cudaMalloc(&h->devchain, sizeof(DevChain)));
+    ZZ_CUDA(h, cudaMalloc(&h->chain_stats, sizeof(double) * MAX_NSTAT));
+  }
+  DevChain *tmp = new (std::nothrow) DevChain();
+  if (!tmp) return fail(h, ZZ_ERR_NOMEM, "out of host memory");
+  memset(tmp, 0, sizeof *tmp);
+  tmp->pr = *priors; tmp->sc = *scalars;
+  cudaError_t e = cudaMemcpyAsync(h->devchain, tmp, sizeof(DevChain), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  delete tmp;
+  if (e != cudaSuccess) return fail(h, ZZ_ERR_CUDA, std::string("zz_chain_begin: ") + cudaGetErrorString(e));
+  h->chain_gen = scalars->gen; h->chain_step = scalars->step; h->chain_samples = scalars->n_samples;
+  h->chain_ready = true;
+  return ZZ_OK;
+}
+
+int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, double target) {
+  ZZ_CHECK(h);
+  if (!h->chain_ready) return fail(h, ZZ_ERR_STATE, "zz_run_generations: call zz_chain_begin first");
+  if (ngen < 0 || (!tune && sample_frequency < 1)) return fail(h, ZZ_ERR_INVALID, "zz_run_generations: bad arguments");
+  double *saved_target = h->stats_target; const int saved_allreduce = h->stats_allreduce;
+  h->stats_target = h->chain_stats; h->stats_allreduce = 0;
+  const int K = h->K, R = h->R, nblk = red_blocks(h->G);
+  const uint64_t seed = h->cfg.seed;
+  const double *no_draws[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint8_t *no_dec[4] = {nullptr, nullptr, nullptr, nullptr};
+  int rc = ZZ_OK;
+  auto stage = [&](int st, int iter, int do_tune_all, int sampled) {
+    k_chain_stage<<<1, 32, 0, h->stream>>>(st, iter, tune, K, R, seed, h->devchain, h->hyper, h->chain_stats, h->red_out, target, do_tune_all, sampled);
+    h->launches++;
+  };
+  auto reduce = [&](int op, int ny) {            // gene sum at the mailbox parameters -> red_out[ny][2], no host copy
+    RedArgs a; fill_red(h, a, 0, op);
+    a.prop = h->devchain; a.partials = h->partials;
+    k_reduce<<<dim3(nblk, ny), BLOCK, 0, h->stream>>>(a);
+    k_reduce_final<<<ny, BLOCK, 0, h->stream>>>(h->partials, nblk, 2, h->red_out);
+    h->launches += 2;
+  };
+  auto commit_vg = [&]() { return launch_eval(h, EVAL_COMMIT_VG, 0, nullptr, h->vgprob, &h->devchain->gate_vg); };
+  // gene sums of the level-2 and variance-prior moves: closed forms of the sweep statistics by default; ZZ_CHAIN_GENE_SUMS=1 (or a
+  // finite variance_g_upper_bound, whose plnorm term has no closed form) keeps the reference's per-gene sums (8 extra passes)
+  const bool closed = h->hyper_host[0].variance_g_upper_bound == INFINITY && getenv("ZZ_CHAIN_GENE_SUMS") == nullptr;
+  if (!tune && h->chain_samples == 0) {           // M:142-145: the trace starts at the current allocation
+    k_alloc_trace<<<gene_grid(h, h->G, 1), BLOCK, 0, h->stream>>>(h->G, K, h->flags, h->trace);
+    h->launches++; h->chain_samples = 1;
+  }
+  for (int i = 0; i < ngen && rc == ZZ_OK; ++i) {
+    rc = launch_sweep_fast(h, h->chain_step, tune, ZZ_MOVE_FUSED, no_draws, no_dec, 0, h->G);   // slots 2,3,9,10,11 + statistics
+    if (rc) break;
+    if (closed) {
+      // every hyper move except mhP_x from the sweep's sufficient statistics: one single-thread kernel, no pass over the genes
+      stage(ST_ALL_CLOSED, 0, 0, 0);
+      reduce(RED_PXDELTA, 1);
+    } else {
+      stage(ST_BEGIN, 0, 0, 0); reduce(RED_LEVEL2, 2);
+      for (int it = 0; it < K; ++it) { stage(ST_AMD, it, 0, 0); reduce(RED_LEVEL2, 2); }
+      stage(ST_SHARED, 0, 0, 0); reduce(RED_LEVEL2, 2);
+      stage(ST_TAU, 0, 0, 0); reduce(RED_VARG_HYPER, 1);
+      stage(ST_SG, 0, 0, 0); if ((rc = commit_vg())) break; reduce(RED_VARG_HYPER, 1);
+      stage(ST_S0TAU, 0, 0, 0); if ((rc = commit_vg())) break; reduce(RED_VARG_HYPER, 1);
+      stage(ST_PX, 0, 0, 0); if ((rc = commit_vg())) break; reduce(RED_PXDELTA, 1);
+    }
+    stage(ST_PX_DECIDE, 0, 0, 0);
+    const int sampled = (!tune && h->chain_gen % sample_frequency == 0) ? 1 : 0;
+    const int do_tune_all = (tune && (h->chain_gen + 1) % 400 == 0) ? 1 : 0;                    // B:146
+    if (R > 2) {                                  // Pr:213-215: XgLikelihood += ll(alpha') - ll(alpha) of the one library
+      k_px_commit_dev<<<gene_grid(h, h->G), BLOCK, 0, h->stream>>>(h->G, h->devchain, h->Xg, h->gl, h->Yg, h->vg, h->flags, h->hyper, h->xglik);
+      h->launches++;
+      stage(ST_END, 0, do_tune_all, sampled);
+    } else {                                      // Pr:219: full recompute with the new p_x
+      stage(ST_END, 0, do_tune_all, sampled);
+      if ((rc = launch_eval(h, EVAL_XGLIK, 0, h->xglik, nullptr, &h->devchain->gate_px))) break;
+    }
+    if (closed && (rc = commit_vg())) break;      // variance_g_probability of the accepted mhTau / mhSg / mhS0Tau, once
+    k_prepare_hyper<<<1, 64, 0, h->stream>>>(1, h->hyper, h->fasth);
+    h->launches++;
+    {                                             // A(y) depends on alpha_r: rebuilt only if mhP_x accepted
+      FastArgs fa;
+      fill_sweep_args(h, fa.s, 0, 0, 0, nullptr, nullptr, 0, h->G);
+      fill_fast_args(h, fa);
+      fa.gate = &h->devchain->gate_px;
+      fa.want_stats = 1;                          // also the XgLikelihood of all-zero genes, which the spike move reads (Pr:581)
+      ZZ_DISPATCH_R(h, k_refresh_lps, gene_grid(h, h->G, 1), fa);
+      h->launches++;
+    }
+    if (sampled) { k_alloc_trace<<<gene_grid(h, h->G, 1), BLOCK, 0, h->stream>>>(h->G, K, h->flags, h->trace); h->launches++; h->chain_samples++; }
+    if (do_tune_all) { k_tune<<<gene_grid(h, h->G), BLOCK, 0, h->stream>>>(h->G, target, h->win_y, h->win_v, h->ty, h->tv); h->launches++; }
+    h->chain_gen += 1; h->chain_step += 10;
+  }
+  h->stats_target = saved_target; h->stats_allreduce = saved_allreduce;
+  h->stats_fresh = false;
+  if (rc) return rc;
+  ZZ_CUDA(h, cudaGetLastError());
+  return ZZ_OK;
+}
+
+int zz_chain_read(zz_handle *h, zz_chain_scalars *scalars, zz_hyper *hyper) {
+  ZZ_CHECK(h);
+  if (!h->chain_ready) return fail(h, ZZ_ERR_STATE, "zz_chain_read: call zz_chain_begin first");
+  ZZ_CUDA(h, cudaMemcpyAsync(&h->hyper_host[0], h->hyper, sizeof(zz_hyper), cudaMemcpyDeviceToHost, h->stream));
+  if (scalars) ZZ_CUDA(h, cudaMemcpyAsync(scalars, &h->devchain->sc, sizeof(zz_chain_scalars), cudaMemcpyDeviceToHost, h->stream));
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));   // the host copy of the hyper-parameters is current again
+  if (scalars) scalars->n_samples = h->chain_samples;
+  if (hyper) *hyper = h->hyper_host[0];
   return ZZ_OK;
 }
 

@@ -197,6 +197,69 @@ class zigzag:
         dist.all_reduce(t, group=self.pg)
         return t.cpu().numpy()
 
+    # ------------------------------------------------------------------ schedule="device": whole generations on the GPU
+    def _priors_struct(self):
+        p = self.pri
+        pr = _capi.Priors(p["weight_active_shape_1"], p["weight_active_shape_2"], p["spike_prior_shape_1"], p["spike_prior_shape_2"],
+                          p["active_means_dif_prior_shape"], p["active_means_dif_prior_rate"], p["inactive_means_prior_shape"],
+                          p["inactive_means_prior_rate"], p["var_log_min"], p["var_log_max"], p["tau_shape"], p["tau_rate"], p["s0_mu"],
+                          p["s0_sigma"], p["s1_shape"], p["s1_rate"], p["alpha_r_shape"], p["alpha_r_rate"], self.threshold_i)
+        for k, t in enumerate(self.threshold_a):
+            pr.threshold_a[k] = float(t)
+        return pr
+
+    def _chain_scalars(self):
+        """The scalar chain state (tuning parameters, windows, counters) in the layout of zz_chain_scalars."""
+        import ctypes as C
+        K, R, w = self.num_active_components, self.num_libraries, self._win
+        win = lambda x: (C.c_uint8 * 100)(*[int(b) for b in x.w])
+        sc = _capi.ChainScalars()
+        sc.t_im, sc.t_av = float(self.inactive_mean_tuningParam), float(self.active_variance_tuningParam[0])
+        sc.t_s0, sc.t_s1, sc.t_tau, sc.t_s0tau = (float(self.tuningParam_s0), float(self.tuningParam_s1), float(self.tuningParam_tau),
+                                                  float(self.tuningParam_s0tau))
+        for name in ("im", "av", "s0", "s1", "tau", "s0tau"):
+            setattr(sc, "w_" + name, win(w[name]))
+        for k in range(K):
+            sc.active_means_dif[k] = float(self.active_means_dif[k]); sc.t_am[k] = float(self.active_mean_tuningParam[k]); sc.w_am[k] = win(w["am"][k])
+        for r in range(R):
+            sc.t_alpha[r] = float(self.tuningParam_alpha_r[r]); sc.w_alpha[r] = win(w["alpha"][r])
+        sc.hyper_ctr = getattr(self, "_hyper_ctr", 0)
+        for j, v in enumerate(getattr(self, "_hyper_buf", (0.0,) * 4)):
+            sc.hyper_buf[j] = v
+        sc.step, sc.gen, sc.n_samples = self._step + 1, self.gen, self.n_samples
+        return sc
+
+    def _adopt_chain(self, sc, hy):
+        """Inverse of _chain_scalars / _push_hyper after a device-resident segment."""
+        K, R = self.num_active_components, self.num_libraries
+        self.s0, self.s1, self.tau = hy.s0, hy.s1, hy.tau
+        self.alpha_r = np.array(hy.alpha_r[:R]); self.spike_probability = hy.spike_probability
+        self.inactive_means, self.inactive_variances = hy.inactive_means, hy.inactive_variances
+        self.active_means = np.array(hy.active_means[:K]); self.active_variances = np.array(hy.active_variances[:K])
+        self.weight_active = hy.weight_active; self.weight_within_active = np.array(hy.weight_within_active[:K])
+        self.active_means_dif = np.array(sc.active_means_dif[:K])
+        self.inactive_mean_tuningParam = sc.t_im; self.active_variance_tuningParam = np.full(K, sc.t_av)
+        self.active_mean_tuningParam = np.array(sc.t_am[:K]); self.tuningParam_alpha_r = np.array(sc.t_alpha[:R])
+        self.tuningParam_s0, self.tuningParam_s1, self.tuningParam_tau, self.tuningParam_s0tau = sc.t_s0, sc.t_s1, sc.t_tau, sc.t_s0tau
+        for name in ("im", "av", "s0", "s1", "tau", "s0tau"):
+            self._win[name].w = list(getattr(sc, "w_" + name))
+        for k in range(K):
+            self._win["am"][k].w = list(sc.w_am[k])
+        for r in range(R):
+            self._win["alpha"][r].w = list(sc.w_alpha[r])
+        self._hyper_ctr, self._hyper_buf = sc.hyper_ctr, tuple(sc.hyper_buf)
+        self._step, self.gen, self.n_samples = sc.step - 1, sc.gen, sc.n_samples
+        self._state_cache = None
+
+    def _device_segment(self, ngen, tune, sample_frequency=1, target=0.44):
+        """ngen generations of the fused schedule without leaving the GPU (zz_run_generations): sweep + every hyper move + tuning +
+        allocation trace on the device; the host reads the scalar state back once per segment."""
+        if self.world != 1:
+            raise NotImplementedError('schedule="device" runs on one GPU in this round (the statistics of a sharded run still need the host)')
+        self.h.chain_begin(self._priors_struct(), self._chain_scalars())
+        self.h.run_generations(ngen, tune=tune, sample_frequency=sample_frequency, target=target)
+        self._adopt_chain(*self.h.chain_read())
+
     def _next_step(self):
         self._step += 1
         self._state_cache = None
@@ -484,6 +547,23 @@ class zigzag:
         if write_to_files and self.rank == 0 and not append:
             os.makedirs(os.path.join(self.output_directory, pdir), exist_ok=True)
             self.initializeOutputFiles(pdir + "/" + prefix)
+        if schedule == "device":
+            # segments end at the sampling points of B:116-131 (the device re-tunes by itself every 400 generations, B:146)
+            done = 0
+            while done <= ngen:
+                n = min((1 - self.gen) % sample_frequency or sample_frequency, ngen + 1 - done)   # end right after generation i = k * sf
+                self._device_segment(n, True, target=burnin_target_acceptance_rate)
+                done += n
+                self._check_nan()
+                i = self.gen - 1
+                if i % sample_frequency == 0 and i > 2 * sample_frequency:
+                    self.lnl_trace.append(self.calculate_lnl())
+                    if write_to_files and self.temperature == 1 and self.rank == 0:
+                        self.writeToOutputFiles(pdir + "/" + prefix, i)
+                        if (i // sample_frequency) % 4 == 0:
+                            self.writeToYgVariancegOutputFiles(pdir + "/" + prefix, i)
+            self.lnl_trace = self.lnl_trace[-1:]
+            return
         i, j = self.gen, 0
         while j <= ngen:
             self._generation(True, schedule)
@@ -515,6 +595,25 @@ class zigzag:
         yv_freq = max(ngen // (sample_frequency * 500), 1)
         write_yv = write_to_files
         ngen = ngen + self.gen
+        if schedule == "device":
+            # the device accumulates allocation_trace itself whenever gen % sample_frequency == 0 (M:194-199); segments end right
+            # after such a generation so that the log rows can be written from the state of that generation
+            while self.gen <= ngen:
+                n = min((1 - self.gen) % sample_frequency or sample_frequency, ngen + 1 - self.gen)
+                self._device_segment(n, False, sample_frequency=sample_frequency)
+                g = self.gen - 1
+                if g % sample_frequency == 0:
+                    self.lnl_trace.append(self.calculate_lnl())
+                    if write_to_files and write_yv and self.temperature == 1 and self.rank == 0:
+                        self.writeToOutputFiles(pdir + "/" + prefix, g)
+                        if (g // sample_frequency) % yv_freq == 0:
+                            self.writeToYgVariancegOutputFiles(pdir + "/" + prefix, g)
+                        if (g - starting_gen) / (yv_freq * sample_frequency) > 500:
+                            write_yv = False
+            self._check_nan()
+            if compute_probs and write_to_files:
+                self.computeGeneExpressionProbs_writeToFile(pdir + "/" + prefix)
+            return
         while j <= ngen:
             self._generation(False, schedule)
             j = self.gen
