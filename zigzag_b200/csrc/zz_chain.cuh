@@ -214,12 +214,11 @@ __device__ inline void propose_px(DevChain &c, const zz_hyper &h, uint64_t seed,
   double sf; const double ap = scale_move(c, seed, h.alpha_r[lib], c.sc.t_alpha[lib], sf);
   c.HR = log(sf);
   if (tune) win_push0(c.sc.w_alpha[lib]);
-  double pp = 0, pc = 0;
-  for (int r = 0; r < R; ++r) {
-    pp += dgamma_log(r == lib ? ap : h.alpha_r[r], c.pr.alpha_r_shape, c.pr.alpha_r_rate);
-    pc += dgamma_log(h.alpha_r[r], c.pr.alpha_r_shape, c.pr.alpha_r_rate);
-  }
-  c.pp = pp; c.pc = pc; c.p_lib = lib; c.p_alpha = ap;
+  // prior ratio: the reference sums dgamma over all R libraries for both vectors; the R - 1 unchanged terms are identical in the
+  // two sums and are left out here (64 logs + 32 lgammas per generation for a single thread otherwise)
+  c.pp = dgamma_log(ap, c.pr.alpha_r_shape, c.pr.alpha_r_rate);
+  c.pc = dgamma_log(h.alpha_r[lib], c.pr.alpha_r_shape, c.pr.alpha_r_rate);
+  c.p_lib = lib; c.p_alpha = ap;
 }
 __device__ inline void decide_px(DevChain &c, zz_hyper &h, uint64_t seed, const double *red, int tune) {
   const double Rr = h.temperature * (red[0] + c.pp - c.pc) + c.HR;
@@ -278,9 +277,24 @@ enum ChainStage {
 };
 
 __global__ void k_chain_stage(int stage, int iter, int tune, int K, int R, uint64_t seed, DevChain *cp, zz_hyper *hp,
-                              const double *stats, const double *red, double target, int do_tune_all, int sampled) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  DevChain &c = *cp; zz_hyper &h = *hp;
+                              const double *stats_g, const double *red, double target, int do_tune_all, int sampled) {
+  // One thread does the scalar work, but on a shared-memory copy of the chain state: the moves touch a few thousand bytes (100-wide
+  // windows shifted element by element, Philox buffer, mailbox) and a single thread pays the full DRAM/L2 latency for each access
+  // (measured: 150 us per generation on the global-memory version, most of it window shifts).
+  __shared__ DevChain c_s;
+  __shared__ zz_hyper h_s;
+  __shared__ double stats[3 * (ZZ_MAX_COMP + 1) + 10];
+  static_assert(sizeof(DevChain) % 8 == 0 && sizeof(zz_hyper) % 8 == 0, "copied as 64-bit words");
+  {
+    const uint64_t *s0 = reinterpret_cast<const uint64_t *>(cp), *s1 = reinterpret_cast<const uint64_t *>(hp);
+    uint64_t *d0 = reinterpret_cast<uint64_t *>(&c_s), *d1 = reinterpret_cast<uint64_t *>(&h_s);
+    for (int j = threadIdx.x; j < (int)(sizeof(DevChain) / 8); j += blockDim.x) d0[j] = s0[j];
+    for (int j = threadIdx.x; j < (int)(sizeof(zz_hyper) / 8); j += blockDim.x) d1[j] = s1[j];
+    for (int j = threadIdx.x; j < 3 * (K + 1) + 10; j += blockDim.x) stats[j] = stats_g[j];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+  DevChain &c = c_s; zz_hyper &h = h_s;
   switch (stage) {
     case ST_BEGIN:
       mv_mixture_weights(c, h, seed, stats, K);
@@ -339,6 +353,14 @@ __global__ void k_chain_stage(int stage, int iter, int tune, int K, int R, uint6
       if (sampled) c.sc.n_samples += 1;
       if (do_tune_all) tune_all_scalars(c, target, K, R);
       break;
+  }
+  }   // thread 0
+  __syncthreads();
+  {
+    uint64_t *d0 = reinterpret_cast<uint64_t *>(cp), *d1 = reinterpret_cast<uint64_t *>(hp);
+    const uint64_t *s0 = reinterpret_cast<const uint64_t *>(&c_s), *s1 = reinterpret_cast<const uint64_t *>(&h_s);
+    for (int j = threadIdx.x; j < (int)(sizeof(DevChain) / 8); j += blockDim.x) d0[j] = s0[j];
+    for (int j = threadIdx.x; j < (int)(sizeof(zz_hyper) / 8); j += blockDim.x) d1[j] = s1[j];
   }
 }
 

@@ -63,7 +63,7 @@ __device__ __forceinline__ void derive_fast(FastH &H, const zz_hyper *__restrict
   H.temp = hy->temperature; H.vub = hy->variance_g_upper_bound;
   H.alpha_min = INFINITY;
   double a2max = 0, amax = 0;
-  for (int r = 0; r < ZZ_MAX_LIBS; ++r) {
+  for (int r = 0; r < H.R; ++r) {                       // entries beyond R / K are never read
     H.alpha[r] = hy->alpha_r[r]; H.alpha2[r] = hy->alpha_r[r] * ZZ_KLOG2E; H.am256[r] = -256.0 * H.alpha2[r];
     if (r < H.R && !(hy->alpha_r[r] >= H.alpha_min)) H.alpha_min = hy->alpha_r[r];
     if (r < H.R && H.alpha2[r] > a2max) a2max = H.alpha2[r];
@@ -72,7 +72,7 @@ __device__ __forceinline__ void derive_fast(FastH &H, const zz_hyper *__restrict
   H.t_clamp = 1010.0 / a2max;
   H.one_hi = 0x3FF00000;
   H.uclamp_ok = (H.alpha_min > 0 && amax <= 16 * H.alpha_min) ? 1 : 0;   // same test as the host's kernel choice (launch_sweep_fast)
-  for (int k = 0; k < ZZ_MAX_COMP; ++k) {
+  for (int k = 0; k < H.K; ++k) {
     H.am[k] = hy->active_means[k];
     H.inv2av[k] = 1.0 / (2 * hy->active_variances[k]);
     H.ck[k] = hy->weight_within_active[k] / (s2p * sqrt(hy->active_variances[k]));

@@ -36,6 +36,7 @@ constexpr int SW_CHUNKS = 64;        // first-level chunks of the sweep-statisti
 // ------------------------------------------------------------------------------------------------ kernels
 
 constexpr int NSTAT_FIXED = 10;
+constexpr int COMM_SMALL_NVEC = 4;   // gene sums exchanged by zz_run_generations: at most [2 parameter sets][2 values]
 constexpr int MAX_NSTAT = 3 * (ZZ_MAX_COMP + 1) + NSTAT_FIXED;
 
 // ---- sufficient-statistics all-reduce over NVLink peer memory, fused with the final reduction -------------------------------
@@ -55,6 +56,9 @@ struct CommArgs {
   unsigned long long epoch;
   double *inbox[8];                      // inbox[r]: base of rank r's inbox (64-bit words), as mapped in THIS process
   unsigned long long *flags[8];          // unused since the low-latency format (kept: part of the exchanged IPC handle pair)
+  int64_t base;                          // first word of the inbox region used by this exchange (statistics: 0; small gene sums: behind them)
+  int stride;                            // words per (slot, rank) block of that region: fixed per region, so exchanges of different
+                                         // lengths in the same region never overlap each other's slots
 };
 
 // all threads of the CTA must call it; `vec` = the local vector in shared memory (complete: the caller has synchronised)
@@ -70,18 +74,18 @@ __device__ __forceinline__ void allreduce_exchange(const double *vec, const Comm
     const unsigned long long word = ((unsigned long long)ep << 32) | half;
     for (int r = 0; r < cm.world; ++r) {
       if (r == cm.rank) continue;
-      unsigned long long *dst = reinterpret_cast<unsigned long long *>(cm.inbox[r]) + ((int64_t)slot * cm.world + cm.rank) * nw + w;
+      unsigned long long *dst = reinterpret_cast<unsigned long long *>(cm.inbox[r]) + cm.base + ((int64_t)slot * cm.world + cm.rank) * cm.stride + w;
       asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
     }
   }
-  const unsigned long long *in = reinterpret_cast<const unsigned long long *>(cm.inbox[cm.rank]) + (int64_t)slot * cm.world * nw;
+  const unsigned long long *in = reinterpret_cast<const unsigned long long *>(cm.inbox[cm.rank]) + cm.base + (int64_t)slot * cm.world * cm.stride;
   const long long t0 = clock64();
   for (int idx = threadIdx.x; idx < cm.nvec; idx += blockDim.x) {
     double v = 0;
     for (int r = 0; r < cm.world; ++r) {
       double x = vec[idx];
       if (r != cm.rank) {
-        const volatile unsigned long long *p = in + (int64_t)r * nw + 2 * idx;
+        const volatile unsigned long long *p = in + (int64_t)r * cm.stride + 2 * idx;
         unsigned long long a = p[0], b = p[1];
         while ((unsigned)(a >> 32) != ep || (unsigned)(b >> 32) != ep) {
           if (clock64() - t0 > 4000000000LL) { timed_out = 1; break; }
@@ -1006,7 +1010,7 @@ struct zz_handle {
   uint64_t *nd_mask; double *xbar, *xss;   // per-gene data statistics (k_prepare_data)
   FastH *fasth; bool fasth_valid;           // derived hyper-parameters of the production kernels
   // peer-memory all-reduce of the statistics vector (zz_comm_*)
-  int comm_rank, comm_world; unsigned long long comm_epoch; bool comm_ready;
+  int comm_rank, comm_world; unsigned long long comm_epoch, comm_epoch_small; bool comm_ready;
   double *comm_inbox; unsigned long long *comm_flags;        // this rank's inbox / flags (device memory, exported through CUDA IPC)
   double *peer_inbox[8]; unsigned long long *peer_flags[8];  // every rank's buffers as mapped here (own entry = local pointers)
   unsigned *tile_counter; unsigned tile_base; int persist_blocks;
@@ -1239,7 +1243,7 @@ int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, con
     fa.stats_out = h->stats_target;
     if (h->stats_allreduce && h->comm_ready) {
       fa.do_allreduce = 1;
-      fa.cm.rank = h->comm_rank; fa.cm.world = h->comm_world; fa.cm.nvec = nstat * h->C; fa.cm.epoch = ++h->comm_epoch;
+      fa.cm.rank = h->comm_rank; fa.cm.world = h->comm_world; fa.cm.nvec = nstat * h->C; fa.cm.epoch = ++h->comm_epoch; fa.cm.base = 0; fa.cm.stride = 2 * fa.cm.nvec;
       for (int r = 0; r < 8; ++r) { fa.cm.inbox[r] = h->peer_inbox[r]; fa.cm.flags[r] = h->peer_flags[r]; }
     }
   }
@@ -1393,7 +1397,7 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   for (int64_t g = 0; g < G; ++g) h->perm_h[g] = (int32_t)g;
   ZZ_CUDA(h, cudaMemcpyAsync(h->perm, h->perm_h.data(), sizeof(int32_t) * G, cudaMemcpyHostToDevice, h->stream));
   h->stats_target = nullptr; h->stats_allreduce = 0;
-  h->comm_rank = 0; h->comm_world = 1; h->comm_epoch = 0; h->comm_ready = false; h->comm_inbox = nullptr; h->comm_flags = nullptr;
+  h->comm_rank = 0; h->comm_world = 1; h->comm_epoch = 0; h->comm_epoch_small = 0; h->comm_ready = false; h->comm_inbox = nullptr; h->comm_flags = nullptr;
   for (int r = 0; r < 8; ++r) { h->peer_inbox[r] = nullptr; h->peer_flags[r] = nullptr; }
   h->n_allzero = 0; h->lps_valid = false; h->stats_fresh = false; h->tile_base = 0; h->persist_blocks = 0; h->sw_rows = 0;
   ZZ_CUDA(h, cudaMalloc(&h->fasth, sizeof(FastH) * h->C));
@@ -1694,10 +1698,11 @@ int zz_comm_init(zz_handle *h, int rank, int world, void *handle_out) {
   if (h->comm_inbox) return fail(h, ZZ_ERR_STATE, "zz_comm_init was already called on this handle");
   const size_t nvec = (size_t)zz_suffstats_len(h->K) * h->C;
   if (nvec > (size_t)MAX_NSTAT * 8) return fail(h, ZZ_ERR_INVALID, "zz_comm_init: too many chains for the fused all-reduce (nstat * chains <= 296)");
-  h->comm_rank = rank; h->comm_world = world; h->comm_epoch = 0;
-  ZZ_CUDA(h, cudaMalloc(&h->comm_inbox, sizeof(double) * 2 * world * 2 * nvec));   // [2 slots][world][2 words per double]
+  h->comm_rank = rank; h->comm_world = world; h->comm_epoch = 0; h->comm_epoch_small = 0;
+  // [2 slots][world][2 words per double] for the statistics vector, then the same for the small gene sums of zz_run_generations
+  ZZ_CUDA(h, cudaMalloc(&h->comm_inbox, sizeof(double) * 2 * world * 2 * (nvec + COMM_SMALL_NVEC)));
   ZZ_CUDA(h, cudaMalloc(&h->comm_flags, sizeof(unsigned long long) * 2 * world));
-  ZZ_CUDA(h, cudaMemset(h->comm_inbox, 0, sizeof(double) * 2 * world * 2 * nvec));
+  ZZ_CUDA(h, cudaMemset(h->comm_inbox, 0, sizeof(double) * 2 * world * 2 * (nvec + COMM_SMALL_NVEC)));
   ZZ_CUDA(h, cudaMemset(h->comm_flags, 0, sizeof(unsigned long long) * 2 * world));
   cudaIpcMemHandle_t hs[2];
   ZZ_CUDA(h, cudaIpcGetMemHandle(&hs[0], h->comm_inbox));
@@ -1745,7 +1750,7 @@ int zz_suffstats_allreduce_dev(zz_handle *h, double *out_dev) {
     partials = h->partials;
   }
   CommArgs cm;
-  cm.rank = h->comm_rank; cm.world = h->comm_world; cm.nvec = nstat * h->C; cm.epoch = ++h->comm_epoch;
+  cm.rank = h->comm_rank; cm.world = h->comm_world; cm.nvec = nstat * h->C; cm.epoch = ++h->comm_epoch; cm.base = 0; cm.stride = 2 * cm.nvec;
   for (int r = 0; r < 8; ++r) { cm.inbox[r] = h->peer_inbox[r]; cm.flags[r] = h->peer_flags[r]; }
   k_reduce_allreduce<<<1, BLOCK, 0, h->stream>>>(partials, nblk, nstat, h->C, out_dev, cm, h->nan_flag);
   ZZ_LAUNCHED(h);
@@ -1990,21 +1995,33 @@ int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, d
   if (!h->chain_ready) return fail(h, ZZ_ERR_STATE, "zz_run_generations: call zz_chain_begin first");
   if (ngen < 0 || (!tune && sample_frequency < 1)) return fail(h, ZZ_ERR_INVALID, "zz_run_generations: bad arguments");
   double *saved_target = h->stats_target; const int saved_allreduce = h->stats_allreduce;
-  h->stats_target = h->chain_stats; h->stats_allreduce = 0;
+  // gene shards on several GPUs (zz_comm_connect done): the sweep's statistics and every gene sum are all-reduced over peer memory
+  // inside the kernels that produce them, so each rank's single-thread stage sees bit-identical inputs and takes the same decisions
+  const bool multi = h->comm_ready && h->comm_world > 1;
+  h->stats_target = h->chain_stats; h->stats_allreduce = multi ? 1 : 0;
   const int K = h->K, R = h->R, nblk = red_blocks(h->G);
   const uint64_t seed = h->cfg.seed;
   const double *no_draws[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint8_t *no_dec[4] = {nullptr, nullptr, nullptr, nullptr};
   int rc = ZZ_OK;
   auto stage = [&](int st, int iter, int do_tune_all, int sampled) {
-    k_chain_stage<<<1, 32, 0, h->stream>>>(st, iter, tune, K, R, seed, h->devchain, h->hyper, h->chain_stats, h->red_out, target, do_tune_all, sampled);
+    k_chain_stage<<<1, 128, 0, h->stream>>>(st, iter, tune, K, R, seed, h->devchain, h->hyper, h->chain_stats, h->red_out, target, do_tune_all, sampled);
     h->launches++;
   };
   auto reduce = [&](int op, int ny) {            // gene sum at the mailbox parameters -> red_out[ny][2], no host copy
     RedArgs a; fill_red(h, a, 0, op);
     a.prop = h->devchain; a.partials = h->partials;
     k_reduce<<<dim3(nblk, ny), BLOCK, 0, h->stream>>>(a);
-    k_reduce_final<<<ny, BLOCK, 0, h->stream>>>(h->partials, nblk, 2, h->red_out);
+    if (multi) {
+      CommArgs cm;
+      cm.rank = h->comm_rank; cm.world = h->comm_world; cm.nvec = 2 * ny; cm.epoch = ++h->comm_epoch_small;
+      cm.base = (int64_t)2 * h->comm_world * 2 * zz_suffstats_len(h->K) * h->C;      // behind the statistics region
+      cm.stride = 2 * COMM_SMALL_NVEC;
+      for (int r = 0; r < 8; ++r) { cm.inbox[r] = h->peer_inbox[r]; cm.flags[r] = h->peer_flags[r]; }
+      k_reduce_allreduce<<<1, BLOCK, 0, h->stream>>>(h->partials, nblk, 2, ny, h->red_out, cm, h->nan_flag);
+    } else {
+      k_reduce_final<<<ny, BLOCK, 0, h->stream>>>(h->partials, nblk, 2, h->red_out);
+    }
     h->launches += 2;
   };
   auto commit_vg = [&]() { return launch_eval(h, EVAL_COMMIT_VG, 0, nullptr, h->vgprob, &h->devchain->gate_vg); };

@@ -166,6 +166,16 @@ class zigzag:
         self.h.set_state(0, pinned_active=pinned, **st)
         self.h.refresh_caches()                                                                                # I:473, I:504
         self._state_cache = None
+        # gene shards on several GPUs of one node: peer-memory all-reduce inside the kernels (needed by schedule="device")
+        self._p2p = False
+        if self.world > 1:
+            import torch.distributed as dist
+            if dist.get_backend(self.pg) == "nccl":
+                blobs = [None] * self.world
+                dist.all_gather_object(blobs, self.h.comm_init(self.rank, self.world), group=self.pg)
+                self.h.comm_connect(blobs)
+                dist.barrier(group=self.pg)
+                self._p2p = True
         if write_settings and self.rank == 0:
             self._write_hyperparameter_settings()
 
@@ -254,8 +264,8 @@ class zigzag:
     def _device_segment(self, ngen, tune, sample_frequency=1, target=0.44):
         """ngen generations of the fused schedule without leaving the GPU (zz_run_generations): sweep + every hyper move + tuning +
         allocation trace on the device; the host reads the scalar state back once per segment."""
-        if self.world != 1:
-            raise NotImplementedError('schedule="device" runs on one GPU in this round (the statistics of a sharded run still need the host)')
+        if self.world != 1 and not self._p2p:
+            raise NotImplementedError('schedule="device" on gene shards needs the peer-memory all-reduce (one node, NCCL process group)')
         self.h.chain_begin(self._priors_struct(), self._chain_scalars())
         self.h.run_generations(ngen, tune=tune, sample_frequency=sample_frequency, target=target)
         self._adopt_chain(*self.h.chain_read())
