@@ -2051,15 +2051,21 @@ int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, d
     stage(ST_PX_DECIDE, 0, 0, 0);
     const int sampled = (!tune && h->chain_gen % sample_frequency == 0) ? 1 : 0;
     const int do_tune_all = (tune && (h->chain_gen + 1) % 400 == 0) ? 1 : 0;                    // B:146
+    // The two per-gene caches of the reference are rewritten by the next sweep for every out-of-spike gene (and A(y) / the all-zero
+    // genes by the gated k_refresh_lps below), and the closed-form moves never read them: with closed forms their commits
+    // (Pr:113/147/187, Pr:213-215/219) are only needed after the LAST generation of the call, when the state becomes visible.
+    const bool commit_now = !closed || i == ngen - 1;
     if (R > 2) {                                  // Pr:213-215: XgLikelihood += ll(alpha') - ll(alpha) of the one library
-      k_px_commit_dev<<<gene_grid(h, h->G), BLOCK, 0, h->stream>>>(h->G, h->devchain, h->Xg, h->gl, h->Yg, h->vg, h->flags, h->hyper, h->xglik);
-      h->launches++;
+      if (commit_now) {
+        k_px_commit_dev<<<gene_grid(h, h->G), BLOCK, 0, h->stream>>>(h->G, h->devchain, h->Xg, h->gl, h->Yg, h->vg, h->flags, h->hyper, h->xglik);
+        h->launches++;
+      }
       stage(ST_END, 0, do_tune_all, sampled);
     } else {                                      // Pr:219: full recompute with the new p_x
       stage(ST_END, 0, do_tune_all, sampled);
-      if ((rc = launch_eval(h, EVAL_XGLIK, 0, h->xglik, nullptr, &h->devchain->gate_px))) break;
+      if (commit_now && (rc = launch_eval(h, EVAL_XGLIK, 0, h->xglik, nullptr, &h->devchain->gate_px))) break;
     }
-    if (closed && (rc = commit_vg())) break;      // variance_g_probability of the accepted mhTau / mhSg / mhS0Tau, once
+    if (closed && commit_now && (rc = commit_vg())) break;   // variance_g_probability of the accepted mhTau / mhSg / mhS0Tau, once
     k_prepare_hyper<<<1, 64, 0, h->stream>>>(1, h->hyper, h->fasth);
     h->launches++;
     {                                             // A(y) depends on alpha_r: rebuilt only if mhP_x accepted
