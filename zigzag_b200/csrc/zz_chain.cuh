@@ -61,6 +61,11 @@ __device__ inline double dgamma_log(double x, double shape, double rate) {
   if (x < 0) return -INFINITY;
   return shape * log(rate) + (shape - 1) * log(x) - rate * x - lgamma(shape);
 }
+// dgamma_log(xp) - dgamma_log(xc): the normalising constant (lgamma, log rate) cancels; -Inf proposal outside the support
+__device__ inline double dgamma_log_diff(double xp, double xc, double shape, double rate) {
+  if (xp < 0) return -INFINITY;
+  return (shape - 1) * (log(xp) - log(xc)) - rate * (xp - xc);
+}
 __device__ inline double dunif_log(double x, double lo, double hi) { return (x >= lo && x <= hi) ? -log(hi - lo) : -INFINITY; }
 __device__ inline double dnorm_log(double x, double mu, double sigma) {
   const double z = (x - mu) / sigma;
@@ -116,8 +121,8 @@ __device__ inline void mv_spike_prob(DevChain &c, zz_hyper &h, uint64_t seed, co
 __device__ inline void propose_inactive_means(DevChain &c, const zz_hyper &h, uint64_t seed, int K) {   // Pr:433-471
   const double thr = c.pr.threshold_i, im = h.inactive_means;
   const double imp = thr - fabs(thr - im - c.sc.t_im * c_norm(c, seed));
-  c.pp = dgamma_log(thr - imp, c.pr.inactive_means_prior_shape, c.pr.inactive_means_prior_rate);
-  c.pc = dgamma_log(thr - im, c.pr.inactive_means_prior_shape, c.pr.inactive_means_prior_rate);
+  c.pp = dgamma_log_diff(thr - imp, thr - im, c.pr.inactive_means_prior_shape, c.pr.inactive_means_prior_rate);   // prior ratio
+  c.pc = 0;
   c.prop0 = imp;
   set_l2_current(c, h, K);
   c.l2[0].im = imp;
@@ -133,8 +138,8 @@ __device__ inline void propose_active_means_dif(DevChain &c, const zz_hyper &h, 
   const double difp = fabs(c.sc.active_means_dif[k] + c.sc.t_am[k] * c_norm(c, seed));
   set_l2_current(c, h, K);
   for (int j = 0; j < K; ++j) c.l2[0].am[j] = (j == k ? difp : c.sc.active_means_dif[j]) + c.pr.threshold_a[j];
-  c.pp = dgamma_log(difp, c.pr.active_means_dif_prior_shape, c.pr.active_means_dif_prior_rate);
-  c.pc = dgamma_log(c.sc.active_means_dif[k], c.pr.active_means_dif_prior_shape, c.pr.active_means_dif_prior_rate);
+  c.pp = dgamma_log_diff(difp, c.sc.active_means_dif[k], c.pr.active_means_dif_prior_shape, c.pr.active_means_dif_prior_rate);
+  c.pc = 0;
   c.k = k; c.difp = difp;
 }
 __device__ inline void decide_active_means_dif(DevChain &c, zz_hyper &h, uint64_t seed, const double *red, int tune, int K) {
@@ -165,14 +170,17 @@ __device__ inline void decide_shared_variance(DevChain &c, zz_hyper &h, uint64_t
   }
 }
 
-__device__ inline double s0_prior(const DevChain &c, double x) { return dnorm_log(x, c.pr.s0_mu, c.pr.s0_sigma); }            // P:33-39
+__device__ inline double s0_prior(const DevChain &c, double x) {   // P:33-39, up to the constant -log(sigma sqrt(2 pi)) that every use subtracts out
+  const double z = (x - c.pr.s0_mu) / c.pr.s0_sigma;
+  return -0.5 * z * z;
+}
 __device__ inline double s1_prior(const DevChain &c, double x) { return dgamma_log(fabs(x), c.pr.s1_shape, c.pr.s1_rate); }   // P:41-47
 __device__ inline double tau_prior(const DevChain &c, double x) { return dgamma_log(x, c.pr.tau_shape, c.pr.tau_rate); }       // P:3-9
 
 __device__ inline void propose_tau(DevChain &c, const zz_hyper &h, uint64_t seed) {   // Pr:119-152
   double sf; const double taup = scale_move(c, seed, h.tau, c.sc.t_tau, sf);
   c.HR = log(sf); c.p_s0 = h.s0; c.p_s1 = h.s1; c.p_tau = taup;
-  c.pp = tau_prior(c, taup); c.pc = tau_prior(c, h.tau);
+  c.pp = dgamma_log_diff(taup, h.tau, c.pr.tau_shape, c.pr.tau_rate); c.pc = 0;   // P:3-9
 }
 __device__ inline void decide_tau(DevChain &c, zz_hyper &h, uint64_t seed, const double *red, int tune) {
   const double Rr = h.temperature * (red[0] - red[1] + c.pp - c.pc) + c.HR;
@@ -186,7 +194,9 @@ __device__ inline void propose_sg(DevChain &c, const zz_hyper &h, uint64_t seed,
   if (c.sel == 1) { s0p = h.s0 + c.sc.t_s0 * c_norm(c, seed); if (tune) win_push0(c.sc.w_s0); }
   else { double sf; s1p = scale_move(c, seed, h.s1, c.sc.t_s1, sf); c.HR = log(sf); if (tune) win_push0(c.sc.w_s1); }
   c.p_s0 = s0p; c.p_s1 = s1p; c.p_tau = h.tau;
-  c.pp = s0_prior(c, s0p) + s1_prior(c, s1p); c.pc = s0_prior(c, h.s0) + s1_prior(c, h.s1);
+  // only one of s0 / s1 moved: the other prior term is identical on both sides
+  c.pp = c.sel == 1 ? s0_prior(c, s0p) - s0_prior(c, h.s0) : dgamma_log_diff(fabs(s1p), fabs(h.s1), c.pr.s1_shape, c.pr.s1_rate);
+  c.pc = 0;
 }
 __device__ inline void decide_sg(DevChain &c, zz_hyper &h, uint64_t seed, const double *red, int tune) {
   const double Rr = h.temperature * (red[0] - red[1] + c.pp - c.pc) + c.HR;
@@ -202,7 +212,7 @@ __device__ inline void propose_s0tau(DevChain &c, const zz_hyper &h, uint64_t se
   c.HR = log(sf);
   if (tune) win_push0(c.sc.w_s0tau);
   c.p_s0 = s0p; c.p_s1 = h.s1; c.p_tau = taup;
-  c.pp = s0_prior(c, s0p) + tau_prior(c, taup); c.pc = s0_prior(c, h.s0) + tau_prior(c, h.tau);
+  c.pp = s0_prior(c, s0p) - s0_prior(c, h.s0) + dgamma_log_diff(taup, h.tau, c.pr.tau_shape, c.pr.tau_rate); c.pc = 0;
 }
 __device__ inline void decide_s0tau(DevChain &c, zz_hyper &h, uint64_t seed, const double *red, int tune) {
   const double Rr = h.temperature * (red[0] - red[1] + c.pp - c.pc) + c.HR;
@@ -216,8 +226,8 @@ __device__ inline void propose_px(DevChain &c, const zz_hyper &h, uint64_t seed,
   if (tune) win_push0(c.sc.w_alpha[lib]);
   // prior ratio: the reference sums dgamma over all R libraries for both vectors; the R - 1 unchanged terms are identical in the
   // two sums and are left out here (64 logs + 32 lgammas per generation for a single thread otherwise)
-  c.pp = dgamma_log(ap, c.pr.alpha_r_shape, c.pr.alpha_r_rate);
-  c.pc = dgamma_log(h.alpha_r[lib], c.pr.alpha_r_shape, c.pr.alpha_r_rate);
+  c.pp = dgamma_log_diff(ap, h.alpha_r[lib], c.pr.alpha_r_shape, c.pr.alpha_r_rate);
+  c.pc = 0;
   c.p_lib = lib; c.p_alpha = ap;
 }
 __device__ inline void decide_px(DevChain &c, zz_hyper &h, uint64_t seed, const double *red, int tune) {
@@ -254,6 +264,23 @@ __device__ inline void closed_level2(const zz_hyper &h, const double *st, int K,
     la += -n * log(s2p * sqrt(av)) - (sy2 - 2 * am * sy + n * am * am) / (2 * av);
   }
   out2[1] = la;
+}
+// The same sums as DIFFERENCES proposed - current (what the moves need): the logarithms cancel unless a variance changes, and a
+// single thread pays ~0.4 us per double-precision libm call.  r[0] = inactive part, r[1] = active part; r[2] = r[3] = 0.
+__device__ inline void closed_level2_diff(const double *st, int K, const L2Params &p, const L2Params &c, double *r) {
+  const int K1 = K + 1;
+  const double n0out = st[0] - st[3 * K1];
+  const double qp = st[2 * K1] - 2 * p.im * st[K1] + n0out * p.im * p.im, qc = st[2 * K1] - 2 * c.im * st[K1] + n0out * c.im * c.im;
+  double li = -(qp / (2 * p.iv) - qc / (2 * c.iv));
+  if (p.iv != c.iv) li += -0.5 * n0out * (log(p.iv) - log(c.iv));
+  double la = 0;
+  for (int k = 1; k <= K; ++k) {
+    const double n = st[k], sy = st[K1 + k], sy2 = st[2 * K1 + k];
+    const double ap = p.am[k - 1], ac = c.am[k - 1], vp = p.av[k - 1], vc = c.av[k - 1];
+    la += -((sy2 - 2 * ap * sy + n * ap * ap) / (2 * vp) - (sy2 - 2 * ac * sy + n * ac * ac) / (2 * vc));
+    if (vp != vc) la += -0.5 * n * (log(vp) - log(vc));
+  }
+  r[0] = li; r[1] = la; r[2] = 0; r[3] = 0;
 }
 __device__ inline double closed_varg(const double *st, int K, double s0, double s1, double tau) {
   const double *fx = st + 3 * (K + 1);
@@ -321,15 +348,15 @@ __global__ void k_chain_stage(int stage, int iter, int tune, int K, int R, uint6
       double r[4];
       mv_mixture_weights(c, h, seed, stats, K);
       propose_inactive_means(c, h, seed, K);
-      closed_level2(h, stats, K, c.l2[0], r); closed_level2(h, stats, K, c.l2[1], r + 2);
+      closed_level2_diff(stats, K, c.l2[0], c.l2[1], r);
       decide_inactive_means(c, h, seed, r, tune);
       for (int it = 0; it < K; ++it) {
         propose_active_means_dif(c, h, seed, K);
-        closed_level2(h, stats, K, c.l2[0], r); closed_level2(h, stats, K, c.l2[1], r + 2);
+        closed_level2_diff(stats, K, c.l2[0], c.l2[1], r);
         decide_active_means_dif(c, h, seed, r, tune, K);
       }
       propose_shared_variance(c, h, seed, tune, K);
-      closed_level2(h, stats, K, c.l2[0], r); closed_level2(h, stats, K, c.l2[1], r + 2);
+      closed_level2_diff(stats, K, c.l2[0], c.l2[1], r);
       decide_shared_variance(c, h, seed, r, tune, K);
       mv_spike_prob(c, h, seed, stats, K);
       int any = 0;
