@@ -225,6 +225,29 @@ int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, d
 /* waits for the device, returns the scalar state and chain 0's hyper-parameters (either pointer may be NULL) */
 int zz_chain_read(zz_handle *h, zz_chain_scalars *scalars, zz_hyper *hyper);
 
+/* ---- sample-time outputs without stopping the device loop (R/zigzagMCMC.R:188-220, R/zigzagFileWriting.R:60-109) ----
+   While zz_run_generations samples (tune == 0, gen % sample_frequency == 0) the device itself appends one row per sample to
+   rings of pinned host memory (zero-copy stores over PCIe; the host never waits):
+     param_rows[row] = { gen, lnl (calculate_lnl, U:70-75), s0, s1, tau, alpha_r[R], spike_probability, inactive_means,
+                         inactive_variances, active_means[K], active_variances[K], weight_active, weight_within_active[K] }
+                       — the columns of <prefix>_model_parameters.log, zz_param_row_len(R, K) doubles;
+     yg_rows[row] / vg_rows[row] = { gen, value of every candidate gene } as <prefix>_yg_candidate_genes.log /
+                       _varianceg_candidate_genes.log print them (in-spike genes: -10 / 0), one row whenever
+                       (gen / sample_frequency) % yv_every == 0, until yv_capacity rows exist (the reference stops after 500).
+   All row buffers must come from zz_pinned_alloc (or any pinned, device-mapped allocation).  The writer that formats the log
+   files stays on the host and reads the rows after zz_sync / zz_chain_read (or concurrently, rows complete in order). */
+typedef struct zz_sample_sink {
+  double *param_rows; int64_t param_capacity;          /* [param_capacity][zz_param_row_len(R, K)] */
+  double *yg_rows, *vg_rows; int64_t yv_capacity;      /* [yv_capacity][1 + n_candidates] each; NULL: no per-gene rows */
+  const int32_t *candidates; int64_t n_candidates;     /* caller's (local) gene indices, host array, copied */
+  int32_t yv_every;
+} zz_sample_sink;
+int zz_param_row_len(int num_libraries, int num_active_components);
+void *zz_pinned_alloc(size_t bytes);                   /* cudaHostAlloc (portable, mapped); NULL on failure */
+void zz_pinned_free(void *p);
+int zz_set_sample_sink(zz_handle *h, const zz_sample_sink *sink);   /* NULL detaches; row counters restart at 0 */
+int zz_sample_rows_written(zz_handle *h, int64_t *param_rows, int64_t *yv_rows);   /* rows enqueued so far */
+
 #ifdef __cplusplus
 }
 #endif

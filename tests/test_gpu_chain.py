@@ -94,3 +94,38 @@ def test_run_generations_is_asynchronous_and_needs_chain_begin():
     h.upload_data(X, gl)
     with pytest.raises(_capi.ZigzagGpuError):
         h.run_generations(1)
+
+
+def test_sample_rows_are_written_by_the_device():
+    """zz_set_sample_sink: during a sampling segment the device appends the rows of the three log files to pinned host rings
+    (parameters + calculate_lnl at every sample; Yg / variance_g of the candidate genes every yv_every-th sample, capped)."""
+    G, R, K = 2500, 4, 2
+    ch, h = _start_pair(G, R, K, 21, (1.0, 6.0))
+    h.run_generations(30, tune=True)
+    cand = np.arange(0, G, 7, dtype=np.int32)
+    h.set_sample_sink(param_capacity=16, candidates=cand, yv_capacity=3, yv_every=2)
+    h.run_generations(30, tune=False, sample_frequency=2)            # generations 30..59: samples at 30, 32, ..., 58
+    prow, yrow, vrow = h.sample_rows()
+    assert prow.shape == (15, 9 + R + 3 * K) and list(prow[:, 0]) == list(range(30, 60, 2))
+    assert yrow.shape == (3, 1 + len(cand)) and list(yrow[:, 0]) == [32, 36, 40] and list(vrow[:, 0]) == [32, 36, 40]   # (gen/2) % 2 == 0, 3 rows max
+    with pytest.raises(_capi.ZigzagGpuError):
+        h.run_generations(10, tune=False, sample_frequency=2)          # only one parameter row left: refused before anything runs
+    # the last generation (59) was not a sample: run one more sampled generation and compare the row with the state it describes
+    h.run_generations(1, tune=False, sample_frequency=2)
+    prow, _, _ = h.sample_rows()
+    sc, hy = h.chain_read()
+    last = prow[-1]
+    assert last[0] == 60 and sc.gen == 61
+    assert np.isclose(last[1], h.lnl(), rtol=1e-12)
+    want = [hy.s0, hy.s1, hy.tau, *hy.alpha_r[:R], hy.spike_probability, hy.inactive_means, hy.inactive_variances, *hy.active_means[:K],
+            *hy.active_variances[:K], hy.weight_active, *hy.weight_within_active[:K]]
+    assert np.array_equal(last[2:], np.array(want))
+    # a fresh sink: per-gene rows of the current state, in the masked form the log files use
+    h.set_sample_sink(param_capacity=2, candidates=cand, yv_capacity=2, yv_every=1)
+    h.run_generations(1, tune=False, sample_frequency=1)
+    _, yrow, vrow = h.sample_rows()
+    st = h.get_state(0)
+    sp = st["inactive_spike_allocation"][cand] == 1
+    assert np.array_equal(yrow[0, 1:], np.where(sp, -10.0, st["Yg"][cand]))
+    assert np.array_equal(vrow[0, 1:], np.where(sp, 0.0, st["variance_g"][cand]))
+    h.clear_sample_sink()

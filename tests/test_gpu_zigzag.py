@@ -92,3 +92,7 @@ def test_lung_prob_active_matches_tutorial_device_schedule(tmp_path):
     rows = open(os.path.join(str(tmp_path), "lung_dev_mcmc_output", "lung_dev_model_parameters.log")).read().splitlines()[1:]
     assert len(rows) >= 1000
     assert mm.n_samples == 1 + sum(1 for g in range(3001, 9002) if g % 5 == 0)
+    # the rows were written by the device during ONE segment (zz_set_sample_sink) and formatted afterwards
+    assert len(rows) == sum(1 for g in range(3001, 9002) if g % 5 == 0) and rows[0].split("\t")[0] == "3005"
+    yg = open(os.path.join(str(tmp_path), "lung_dev_mcmc_output", "lung_dev_yg_candidate_genes.log")).read().splitlines()
+    assert len(yg[0].split("\t")) == 5001 and 400 <= len(yg) - 1 <= 501 and len(yg[1].split("\t")) == 5001

@@ -103,6 +103,12 @@ class ChainScalars(C.Structure):
         return s
 
 
+class SampleSink(C.Structure):
+    """zz_sample_sink: rings of pinned host memory the device appends the sample-time log rows to."""
+    _fields_ = [("param_rows", C.c_void_p), ("param_capacity", C.c_int64), ("yg_rows", C.c_void_p), ("vg_rows", C.c_void_p),
+                ("yv_capacity", C.c_int64), ("candidates", C.c_void_p), ("n_candidates", C.c_int64), ("yv_every", C.c_int32)]
+
+
 class Config(C.Structure):
     _fields_ = [("num_genes", C.c_int64), ("gene_offset", C.c_int64), ("num_libraries", C.c_int32),
                 ("num_active_components", C.c_int32), ("num_chains", C.c_int32), ("device", C.c_int32),
@@ -160,6 +166,11 @@ _SIG = {
     "zz_chain_begin": (C.c_int, [_P, _P, _P]),
     "zz_run_generations": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double]),
     "zz_chain_read": (C.c_int, [_P, _P, _P]),
+    "zz_param_row_len": (C.c_int, [C.c_int, C.c_int]),
+    "zz_pinned_alloc": (C.c_void_p, [C.c_size_t]),
+    "zz_pinned_free": (None, [_P]),
+    "zz_set_sample_sink": (C.c_int, [_P, _P]),
+    "zz_sample_rows_written": (C.c_int, [_P, _P, _P]),
 }
 EXPORTS = tuple(_SIG)
 
@@ -216,6 +227,10 @@ class Handle:
 
     def close(self):
         if getattr(self, "h", None):
+            try:
+                self.clear_sample_sink()
+            except Exception:
+                pass
             self.L.zz_destroy(self.h)
             self.h = None
 
@@ -436,6 +451,47 @@ class Handle:
         sc, hy = ChainScalars(), Hyper()
         self._ck(self.L.zz_chain_read(self.h, C.addressof(sc), C.addressof(hy)))
         return sc, hy
+
+    # ---- sample-time rows written by the device
+    def _pinned(self, rows, cols):
+        p = self.L.zz_pinned_alloc(max(1, rows * cols) * 8)
+        if not p:
+            raise ZigzagGpuError("zz_pinned_alloc failed")
+        self._sink_ptrs.append(p)
+        return p, np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), (rows, cols))
+
+    def set_sample_sink(self, param_capacity, candidates=None, yv_capacity=0, yv_every=1):
+        """Allocates the pinned rings and attaches them; returns nothing, read with sample_rows()."""
+        self.clear_sample_sink()
+        self._sink_ptrs = []
+        plen = int(self.L.zz_param_row_len(self.R, self.K))
+        sk = SampleSink()
+        sk.param_rows, self._sink_param = self._pinned(param_capacity, plen)
+        sk.param_capacity = param_capacity
+        self._sink_yg = self._sink_vg = None
+        if candidates is not None and yv_capacity > 0:
+            cand = np.ascontiguousarray(candidates, dtype=np.int32)
+            sk.yg_rows, self._sink_yg = self._pinned(yv_capacity, 1 + len(cand))
+            sk.vg_rows, self._sink_vg = self._pinned(yv_capacity, 1 + len(cand))
+            sk.yv_capacity, sk.candidates, sk.n_candidates, sk.yv_every = yv_capacity, cand.ctypes.data, len(cand), int(yv_every)
+        self._ck(self.L.zz_set_sample_sink(self.h, C.addressof(sk)))
+
+    def sample_rows(self):
+        """(parameter rows, Yg rows, variance_g rows) written so far (copies); waits for the device."""
+        self.sync()
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.zz_sample_rows_written(self.h, C.addressof(a), C.addressof(b)))
+        yg = None if self._sink_yg is None else self._sink_yg[:b.value].copy()
+        vg = None if self._sink_vg is None else self._sink_vg[:b.value].copy()
+        return self._sink_param[:a.value].copy(), yg, vg
+
+    def clear_sample_sink(self):
+        if getattr(self, "_sink_ptrs", None):
+            self._ck(self.L.zz_set_sample_sink(self.h, None))
+            for p in self._sink_ptrs:
+                self.L.zz_pinned_free(p)
+        self._sink_ptrs = []
+        self._sink_param = self._sink_yg = self._sink_vg = None
 
     def sweep_host(self, step, tune, Yg, variance_g, ai, within, spike, XgLikelihood, variance_g_probability, ty, tv):
         """All arguments are host arrays or raw host pointers (ints), updated in place; returns (h2d_bytes, d2h_bytes)."""

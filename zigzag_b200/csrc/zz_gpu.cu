@@ -909,6 +909,31 @@ __global__ void __launch_bounds__(BLOCK) k_px_commit_dev(int64_t G, const DevCha
              xg_lik_onelib(H, x, Yg[g], vg[g], gl[g], H.alpha[lib], f & F_INSPIKE, f & F_ALLZERO);
 }
 
+// one sample: the _model_parameters.log row (thread 0) and, when due, the candidate genes' Yg / variance_g rows, written straight
+// into pinned host memory (zz_set_sample_sink)
+__global__ void __launch_bounds__(BLOCK) k_sample_row(double gen, const zz_hyper *hy, const double *lnl, int R, int K, double *prow,
+                                                       const int32_t *cand_slots, int64_t n_cand, const double *Yg, const double *vg,
+                                                       const uint16_t *flags, double *ygrow, double *vgrow) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int j = 0;
+    prow[j++] = gen; prow[j++] = lnl[0]; prow[j++] = hy->s0; prow[j++] = hy->s1; prow[j++] = hy->tau;
+    for (int r = 0; r < R; ++r) prow[j++] = hy->alpha_r[r];
+    prow[j++] = hy->spike_probability; prow[j++] = hy->inactive_means; prow[j++] = hy->inactive_variances;
+    for (int k = 0; k < K; ++k) prow[j++] = hy->active_means[k];
+    for (int k = 0; k < K; ++k) prow[j++] = hy->active_variances[k];
+    prow[j++] = hy->weight_active;
+    for (int k = 0; k < K; ++k) prow[j++] = hy->weight_within_active[k];
+    if (ygrow) { ygrow[0] = gen; vgrow[0] = gen; }
+  }
+  if (!ygrow) return;
+  for (int64_t c = (int64_t)blockIdx.x * BLOCK + threadIdx.x; c < n_cand; c += (int64_t)gridDim.x * BLOCK) {
+    const int64_t i = cand_slots[c];
+    const bool sp = flags[i] & F_INSPIKE;
+    ygrow[1 + c] = sp ? -10.0 : Yg[i];                  // FileWriting:93: Yg * (1 - spike) + (-10) * spike
+    vgrow[1 + c] = sp ? 0.0 : vg[i];                    // FileWriting:100
+  }
+}
+
 // allocation_trace += one-hot(allocation), M:194-199
 __global__ void __launch_bounds__(BLOCK) k_alloc_trace(int64_t G, int K, const uint16_t *flags, uint32_t *trace) {
   const int chain = blockIdx.y;
@@ -1020,6 +1045,7 @@ struct zz_handle {
   std::vector<zz_hyper> hyper_host;
   double *pinned;                          // small pinned staging for reduction results
   // zz_sweep_host pipeline (created on first use)
+  bool sink_on; zz_sample_sink sink; double *sink_p, *sink_y, *sink_v; int32_t *cand_slots; int64_t sink_prow, sink_yrow;   // zz_set_sample_sink
   DevChain *devchain; double *chain_stats; bool chain_ready; int64_t chain_gen, chain_samples; uint64_t chain_step;   // zz_run_generations
   int32_t *inv_perm; cudaStream_t s_up, s_down; cudaEvent_t ev_entry, ev_up[ZZ_HOST_MAX_CHUNKS], ev_done[ZZ_HOST_MAX_CHUNKS]; bool pipe_ready;
 };
@@ -1355,6 +1381,7 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   h->cfg = *cfg; h->G = cfg->num_genes; h->C = cfg->num_chains; h->R = cfg->num_libraries; h->K = cfg->num_active_components;
   h->sticky = false; h->launches = 0; h->have_data = false; h->own_stream = false; h->stream = nullptr;
   h->inv_perm = nullptr; h->pipe_ready = false; h->s_up = h->s_down = nullptr;
+  h->sink_on = false; h->cand_slots = nullptr; h->sink_prow = h->sink_yrow = 0;
   h->devchain = nullptr; h->chain_stats = nullptr; h->chain_ready = false; h->chain_gen = 0; h->chain_samples = 0; h->chain_step = 0;
   *out = h;  // returned even on failure so the caller can read zz_last_error and must zz_destroy
   int ndev = 0;
@@ -1438,6 +1465,7 @@ void zz_destroy(zz_handle *h) {
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->inv_perm) cudaFree(h->inv_perm);
   if (h->devchain) cudaFree(h->devchain);
+  if (h->cand_slots) cudaFree(h->cand_slots);
   if (h->chain_stats) cudaFree(h->chain_stats);
   if (h->pipe_ready) {
     cudaStreamDestroy(h->s_up); cudaStreamDestroy(h->s_down); cudaEventDestroy(h->ev_entry);
@@ -2028,6 +2056,14 @@ int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, d
   // gene sums of the level-2 and variance-prior moves: closed forms of the sweep statistics by default; ZZ_CHAIN_GENE_SUMS=1 (or a
   // finite variance_g_upper_bound, whose plnorm term has no closed form) keeps the reference's per-gene sums (8 extra passes)
   const bool closed = h->hyper_host[0].variance_g_upper_bound == INFINITY && getenv("ZZ_CHAIN_GENE_SUMS") == nullptr;
+  if (!tune && h->sink_on) {                      // every sample of this call needs a parameter row
+    int64_t need = 0;
+    for (int i = 0; i < ngen; ++i) need += ((h->chain_gen + i) % sample_frequency == 0);
+    if (h->sink_prow + need > h->sink.param_capacity) {
+      h->stats_target = saved_target; h->stats_allreduce = saved_allreduce;
+      return fail(h, ZZ_ERR_INVALID, "zz_run_generations: the sample sink has too few parameter rows for this call");
+    }
+  }
   if (!tune && h->chain_samples == 0) {           // M:142-145: the trace starts at the current allocation
     k_alloc_trace<<<gene_grid(h, h->G, 1), BLOCK, 0, h->stream>>>(h->G, K, h->flags, h->trace);
     h->launches++; h->chain_samples = 1;
@@ -2078,6 +2114,19 @@ int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, d
       h->launches++;
     }
     if (sampled) { k_alloc_trace<<<gene_grid(h, h->G, 1), BLOCK, 0, h->stream>>>(h->G, K, h->flags, h->trace); h->launches++; h->chain_samples++; }
+    if (sampled && h->sink_on) {                  // M:202-220: lnl and the log rows of this sample, written by the device
+      reduce(RED_LNL, 1);
+      const bool yv = h->sink_y && ((h->chain_gen / sample_frequency) % h->sink.yv_every == 0) && h->sink_yrow < h->sink.yv_capacity;
+      const int plen = zz_param_row_len(R, K);
+      const int64_t nc = h->sink.n_candidates;
+      int64_t nb = yv ? (nc + BLOCK - 1) / BLOCK : 1;
+      if (nb < 1) nb = 1;
+      if (nb > 4 * 148) nb = 4 * 148;
+      k_sample_row<<<(unsigned)nb, BLOCK, 0, h->stream>>>((double)h->chain_gen, h->hyper, h->red_out, R, K, h->sink_p + h->sink_prow * plen,
+                                                          h->cand_slots, nc, h->Yg, h->vg, h->flags,
+                                                          yv ? h->sink_y + h->sink_yrow * (1 + nc) : nullptr, yv ? h->sink_v + h->sink_yrow * (1 + nc) : nullptr);
+      h->launches++; h->sink_prow++; if (yv) h->sink_yrow++;
+    }
     if (do_tune_all) { k_tune<<<gene_grid(h, h->G), BLOCK, 0, h->stream>>>(h->G, target, h->win_y, h->win_v, h->ty, h->tv); h->launches++; }
     h->chain_gen += 1; h->chain_step += 10;
   }
@@ -2096,6 +2145,57 @@ int zz_chain_read(zz_handle *h, zz_chain_scalars *scalars, zz_hyper *hyper) {
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));   // the host copy of the hyper-parameters is current again
   if (scalars) scalars->n_samples = h->chain_samples;
   if (hyper) *hyper = h->hyper_host[0];
+  return ZZ_OK;
+}
+
+// ---- sample-time outputs written by the device (zz_set_sample_sink) -------------------------------------------------
+int zz_param_row_len(int R, int K) { return 9 + R + 3 * K; }
+
+void *zz_pinned_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void zz_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+
+int zz_set_sample_sink(zz_handle *h, const zz_sample_sink *sink) {
+  ZZ_CHECK(h);
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));        // rows of earlier calls are complete before the rings change
+  h->sink_on = false; h->sink_prow = h->sink_yrow = 0;
+  if (h->cand_slots) { cudaFree(h->cand_slots); h->cand_slots = nullptr; }
+  if (!sink) return ZZ_OK;
+  if (!h->have_data) return fail(h, ZZ_ERR_STATE, "zz_upload_data has not been called");
+  if (!sink->param_rows || sink->param_capacity < 1) return fail(h, ZZ_ERR_INVALID, "zz_set_sample_sink: no parameter rows");
+  const bool yv = sink->yg_rows && sink->vg_rows && sink->yv_capacity > 0 && sink->n_candidates > 0;
+  if (yv && (!sink->candidates || sink->yv_every < 1)) return fail(h, ZZ_ERR_INVALID, "zz_set_sample_sink: candidates / yv_every");
+  auto dev_ptr = [&](double *host, double **out) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) { cudaGetLastError(); return false; }
+    *out = (double *)at.devicePointer; return true;
+  };
+  h->sink_y = h->sink_v = nullptr;
+  if (!dev_ptr(sink->param_rows, &h->sink_p) || (yv && (!dev_ptr(sink->yg_rows, &h->sink_y) || !dev_ptr(sink->vg_rows, &h->sink_v))))
+    return fail(h, ZZ_ERR_INVALID, "zz_set_sample_sink: row buffers must be pinned, device-mapped host memory (zz_pinned_alloc)");
+  if (yv) {
+    std::vector<int32_t> inv((size_t)h->G), slots((size_t)sink->n_candidates);
+    for (int64_t g = 0; g < h->G; ++g) inv[(size_t)h->perm_h[(size_t)g]] = (int32_t)g;
+    for (int64_t c = 0; c < sink->n_candidates; ++c) {
+      if (sink->candidates[c] < 0 || sink->candidates[c] >= h->G) return fail(h, ZZ_ERR_INVALID, "zz_set_sample_sink: candidate index out of range");
+      slots[(size_t)c] = inv[(size_t)sink->candidates[c]];
+    }
+    ZZ_CUDA(h, cudaMalloc(&h->cand_slots, sizeof(int32_t) * sink->n_candidates));
+    ZZ_CUDA(h, cudaMemcpy(h->cand_slots, slots.data(), sizeof(int32_t) * sink->n_candidates, cudaMemcpyHostToDevice));
+  }
+  h->sink = *sink;
+  if (!yv) { h->sink.n_candidates = 0; h->sink.yv_capacity = 0; }
+  h->sink_on = true;
+  return ZZ_OK;
+}
+
+int zz_sample_rows_written(zz_handle *h, int64_t *param_rows, int64_t *yv_rows) {
+  ZZ_CHECK(h);
+  if (param_rows) *param_rows = h->sink_prow;
+  if (yv_rows) *yv_rows = h->sink_yrow;
   return ZZ_OK;
 }
 

@@ -605,6 +605,31 @@ class zigzag:
         yv_freq = max(ngen // (sample_frequency * 500), 1)
         write_yv = write_to_files
         ngen = ngen + self.gen
+        if schedule == "device" and self.world == 1:
+            # ONE device-resident segment for the whole run: the device accumulates allocation_trace (M:194-199) and appends the rows
+            # of the three log files to pinned host rings at every sampling point (zz_set_sample_sink); the host formats them afterwards
+            first, last = self.gen, ngen
+            samples = [g for g in range(first, last + 1) if g % sample_frequency == 0]
+            logging = write_to_files and self.temperature == 1
+            self.h.set_sample_sink(max(1, len(samples)), self._cand_idx if logging else None, 501 if logging else 0, yv_freq)
+            self._device_segment(last - first + 1, False, sample_frequency=sample_frequency)
+            prow, yrow, vrow = self.h.sample_rows()
+            self.h.clear_sample_sink()
+            self.lnl_trace.extend(float(r[1]) for r in prow)
+            if logging:
+                with open(self._path(pdir + "/" + prefix, "_model_parameters.log"), "a") as f:
+                    for r in prow:
+                        f.write("\t".join([_rnum(r[0])] + [_rnum(round(float(x), 4)) for x in r[1:]]) + "\n")
+                with open(self._path(pdir + "/" + prefix, "_yg_candidate_genes.log"), "a") as f:
+                    for r in yrow:
+                        f.write("\t".join([_rnum(r[0])] + [_rnum(round(float(x), 3)) for x in r[1:]]) + "\n")
+                with open(self._path(pdir + "/" + prefix, "_varianceg_candidate_genes.log"), "a") as f:
+                    for r in vrow:
+                        f.write("\t".join([_rnum(r[0])] + [_rnum(round(float(x), 4)) for x in r[1:]]) + "\n")
+            self._check_nan()
+            if compute_probs and write_to_files:
+                self.computeGeneExpressionProbs_writeToFile(pdir + "/" + prefix)
+            return
         if schedule == "device":
             # the device accumulates allocation_trace itself whenever gen % sample_frequency == 0 (M:194-199); segments end right
             # after such a generation so that the log rows can be written from the state of that generation
