@@ -23,6 +23,7 @@
  */
 #ifndef ZIGZAG_GPU_H
 #define ZIGZAG_GPU_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
