@@ -64,5 +64,43 @@ zigzag$methods(
     }
   },
 
-  calculate_lnl = function(num_libs) .Call("zzR_lnl", gpu)
+  calculate_lnl = function(num_libs) .Call("zzR_lnl", gpu),
+
+  # ---- device-resident segments: n generations (fused sweep + every hyper move + tune_all + allocation trace) without returning
+  # to R between moves (zz_run_generations).  burnin()/mcmc() call this between two sampling points instead of looping over
+  # proposal_list; the fields the hyper moves mutate travel once per segment.
+  gpu_run_generations = function(n, tune = FALSE, sample_frequency = 1, target = 0.44){
+    pri <- c(weight_active_shape_1, weight_active_shape_2, spike_prior_shape_1, spike_prior_shape_2,
+             active_means_dif_prior_shape, active_means_dif_prior_rate, inactive_means_prior_shape, inactive_means_prior_rate,
+             shared_variance_prior_log_min, shared_variance_prior_log_max, tau_shape, tau_rate, s0_mu, s0_sigma, s1_shape, s1_rate,
+             alpha_r_shape, alpha_r_rate, threshold_i, threshold_a)
+    K <- num_active_components; R <- num_libraries
+    sc <- list(active_means_dif = active_means_dif, t_im = inactive_mean_tuningParam, t_av = active_variance_tuningParam[1],
+               t_am = active_mean_tuningParam, t_s0 = tuningParam_s0, t_s1 = tuningParam_s1, t_tau = tuningParam_tau,
+               t_s0tau = tuningParam_s0tau, t_alpha = tuningParam_alpha_r,
+               w_im = as.integer(inactive_means_trace[[1]][[1]]), w_av = as.integer(active_variances_trace[[1]][[1]]),
+               w_am = lapply(seq(K), function(k) as.integer(active_means_trace[[k]][[1]])),
+               w_s0 = as.integer(s0_trace[[1]][[1]]), w_s1 = as.integer(s1_trace[[1]][[1]]), w_tau = as.integer(tau_trace[[1]][[1]]),
+               w_s0tau = as.integer(s0tau_trace[[1]][[1]]),
+               w_alpha = lapply(seq(R), function(r) as.integer(alpha_r_trace[[r]][[1]])),
+               hyper_ctr = gpu_hyper_ctr, hyper_buf = gpu_hyper_buf, step = gpu_step + 1, gen = gen, n_samples = gpu_n_samples)
+    .Call("zzR_chain_begin", gpu, pri, sc, K, R)
+    .Call("zzR_run_generations", gpu, as.integer(n), tune, as.integer(sample_frequency), target)
+    out <- .Call("zzR_chain_read", gpu, K, R)
+    .self$s0 <- out[1]; .self$s1 <- out[2]; .self$tau <- out[3]; .self$spike_probability <- out[4]
+    .self$inactive_means <- out[5]; .self$inactive_variances <- out[6]; .self$weight_active <- out[7]
+    .self$gen <- out[8]; .self$gpu_step <- out[9] - 1; .self$gpu_n_samples <- out[10]; .self$gpu_hyper_ctr <- out[11]
+    j <- 11
+    .self$alpha_r <- out[j + seq(R)]; j <- j + R
+    .self$active_means <- out[j + seq(K)]; j <- j + K
+    .self$active_variances <- out[j + seq(K)]; j <- j + K
+    .self$weight_within_active <- out[j + seq(K)]; j <- j + K
+    .self$active_means_dif <- out[j + seq(K)]; j <- j + K
+    .self$inactive_mean_tuningParam <- out[j + 1]; .self$active_variance_tuningParam <- rep(out[j + 2], K)
+    .self$tuningParam_s0 <- out[j + 3]; .self$tuningParam_s1 <- out[j + 4]; .self$tuningParam_tau <- out[j + 5]
+    .self$tuningParam_s0tau <- out[j + 6]; j <- j + 6
+    .self$active_mean_tuningParam <- out[j + seq(K)]; j <- j + K
+    .self$tuningParam_alpha_r <- out[j + seq(R)]
+    # (the *_trace windows come back the same way through zzR_chain_windows; per-gene fields through gpu_pull())
+  }
 )

@@ -31,7 +31,6 @@ constexpr int BLOCK = 256;
 #endif
 constexpr int SWEEP_BLOCK = ZZ_SWEEP_BLOCK;   // threads per CTA of the persistent sweep kernel
 constexpr int RED_BLOCKS = 148 * 4;  // persistent-style reduction grid: 4 CTAs per SM
-constexpr int SW_CHUNKS = 64;        // first-level chunks of the sweep-statistics reduction
 
 // ------------------------------------------------------------------------------------------------ kernels
 
@@ -249,11 +248,10 @@ struct FastArgs {
   SweepArgs s;
   double *lps;                      // [C][G] A(y): sum of the detection log-terms at the current Yg
   const double *exp_tab; const double2 *log_tab;
-  int64_t allzero_begin, n_allzero; // genes with no reads in any library (I:416-421) occupy the last n_allzero slots
   const uint64_t *nd_mask; const double *xbar, *xss;  // per-gene data statistics (k_prepare_data)
   const FastH *fasth;               // [C] derived hyper-parameters (k_prepare_hyper)
   double *partials;                 // [C][rows][nstat] per-block sufficient statistics (rows = main blocks + spike blocks)
-  int64_t rows_per_chain, spike_row0;
+  int64_t rows_per_chain;
   int want_stats, do_spike_move;
   const int32_t *slot_list;         // list mode (zz_sweep_host chunks): position p in [g_begin, g_end) addresses gene slot slot_list[p]
   const int *gate;                  // k_refresh_lps in the device-resident loop: rebuild only if *gate != 0 (accepted mhP_x)
@@ -1038,9 +1036,9 @@ struct zz_handle {
   int comm_rank, comm_world; unsigned long long comm_epoch, comm_epoch_small; bool comm_ready;
   double *comm_inbox; unsigned long long *comm_flags;        // this rank's inbox / flags (device memory, exported through CUDA IPC)
   double *peer_inbox[8]; unsigned long long *peer_flags[8];  // every rank's buffers as mapped here (own entry = local pointers)
-  unsigned *tile_counter; unsigned tile_base; int persist_blocks;
+  unsigned *tile_counter; int persist_blocks;       // tile_counter: ticket of the "last CTA done" epilogue
   double *stats_target; int stats_allreduce;   // zz_set_stats_output_dev: where the sweep's fused epilogue leaves the statistics
-  double *sw_partials, *sw_partials2; int64_t sw_rows; bool stats_fresh;   // statistics emitted by the last production sweep
+  double *sw_partials; int64_t sw_rows; bool stats_fresh;   // statistics emitted by the last production sweep
   bool lps_valid;                          // lps == A(current Yg, alpha_r) for every out-of-spike gene
   std::vector<zz_hyper> hyper_host;
   double *pinned;                          // small pinned staging for reduction results
@@ -1145,9 +1143,9 @@ int launch_sweep(zz_handle *h, uint64_t step, int tune, uint32_t moves, const do
   } while (0)
 
 void fill_fast_args(zz_handle *h, FastArgs &fa) {
-  fa.lps = h->lps; fa.exp_tab = h->exp_tab; fa.log_tab = h->log_tab; fa.allzero_begin = h->G - h->n_allzero; fa.n_allzero = h->n_allzero;
+  fa.lps = h->lps; fa.exp_tab = h->exp_tab; fa.log_tab = h->log_tab;
   fa.nd_mask = h->nd_mask; fa.xbar = h->xbar; fa.xss = h->xss; fa.fasth = h->fasth;
-  fa.partials = h->sw_partials; fa.rows_per_chain = 0; fa.spike_row0 = 0; fa.want_stats = 0; fa.do_spike_move = 0;
+  fa.partials = h->sw_partials; fa.rows_per_chain = 0; fa.want_stats = 0; fa.do_spike_move = 0;
   fa.done_counter = h->tile_counter; fa.stats_out = nullptr; fa.do_allreduce = 0; memset(&fa.cm, 0, sizeof fa.cm);
   fa.slot_list = nullptr; fa.host_io = 0; memset(&fa.hio, 0, sizeof fa.hio); fa.gate = nullptr;
 }
@@ -1262,7 +1260,6 @@ int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, con
   if (per_chain < 1) per_chain = 1;
   fa.want_stats = full ? 1 : 0;
   fa.rows_per_chain = per_chain;
-  fa.spike_row0 = per_chain;
   fa.do_spike_move = (moves & ZZ_MOVE_SPIKE) ? 1 : 0;
   h->stats_fresh = false;
   if (full && h->stats_target) {
@@ -1426,7 +1423,7 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   h->stats_target = nullptr; h->stats_allreduce = 0;
   h->comm_rank = 0; h->comm_world = 1; h->comm_epoch = 0; h->comm_epoch_small = 0; h->comm_ready = false; h->comm_inbox = nullptr; h->comm_flags = nullptr;
   for (int r = 0; r < 8; ++r) { h->peer_inbox[r] = nullptr; h->peer_flags[r] = nullptr; }
-  h->n_allzero = 0; h->lps_valid = false; h->stats_fresh = false; h->tile_base = 0; h->persist_blocks = 0; h->sw_rows = 0;
+  h->n_allzero = 0; h->lps_valid = false; h->stats_fresh = false; h->persist_blocks = 0; h->sw_rows = 0;
   ZZ_CUDA(h, cudaMalloc(&h->fasth, sizeof(FastH) * h->C));
   h->fasth_valid = false;
   ZZ_CUDA(h, cudaMalloc(&h->nd_mask, sizeof(uint64_t) * G));
@@ -1437,7 +1434,6 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   {
     const int64_t max_rows = (G + 31) / 32 + ((G + BLOCK - 1) / BLOCK) * (BLOCK / 32);
     ZZ_CUDA(h, cudaMalloc(&h->sw_partials, sizeof(double) * (size_t)h->C * max_rows * nstat));
-    ZZ_CUDA(h, cudaMalloc(&h->sw_partials2, sizeof(double) * (size_t)h->C * SW_CHUNKS * nstat));
   }
   ZZ_CUDA(h, cudaMalloc(&h->nan_flag, sizeof(int)));
   ZZ_CUDA(h, cudaMemsetAsync(h->nan_flag, 0, sizeof(int), h->stream));
@@ -1460,7 +1456,7 @@ void zz_destroy(zz_handle *h) {
   if (h->comm_flags) cudaFree(h->comm_flags);
   void *ptrs[] = {h->Xg, h->gl, h->Yg, h->vg, h->xglik, h->vgprob, h->ty, h->tv, h->flags, h->win_y, h->win_v, h->trace,
                   h->hyper, h->partials, h->red_out, h->scratch, h->dec, h->iscratch, h->nan_flag, h->lps, h->exp_tab,
-                  h->log_tab, h->perm, h->stage, h->nd_mask, h->xbar, h->xss, h->tile_counter, h->sw_partials, h->sw_partials2, h->fasth};
+                  h->log_tab, h->perm, h->stage, h->nd_mask, h->xbar, h->xss, h->tile_counter, h->sw_partials, h->fasth};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->inv_perm) cudaFree(h->inv_perm);
