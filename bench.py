@@ -316,6 +316,26 @@ def main():
         e2e = {"value": G_tot * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": nb[0] * world, "d2h_bytes_per_step": nb[1] * world,
                "steps": args.e2e_steps, "what": "zz_sweep_host: mutable per-gene state (Yg, variance_g, tuning parameters, allocations) up from pinned host arrays, fused sweep, updated state + both likelihood caches back; Xg resident since zz_upload_data"}
 
+    # ---- informational: a WHOLE generation (sweep + the nine hyper-parameter moves + commits) device-resident (zz_run_generations)
+    chain = None
+    if chains == 1:
+        try:
+            thr_a = (1.0, 6.0)[:len(hd["active_means"])]
+            h.chain_begin(_capi.Priors.defaults(-1.0, thr_a), _capi.ChainScalars.initial(hd["active_means"], thr_a, R))
+            h.run_generations(10, tune=False, sample_frequency=10)
+            h.sync()
+            if world > 1:
+                dist.barrier()
+            l0, t0 = h.launch_count, time.perf_counter()
+            h.run_generations(100, tune=False, sample_frequency=10)
+            h.sync()
+            dtg = (time.perf_counter() - t0) / 100
+            chain = {"generation_us": dtg * 1e6, "generations_per_sec": 1.0 / dtg, "launches_per_generation": (h.launch_count - l0) / 100,
+                     "what": "zz_run_generations: fused sweep + gibbsMixtureWeights, mhInactiveMeans, mhActiveMeansDif, mhSharedVariance, "
+                             "gibbsSpikeProb, mhTau, mhSg, mhS0Tau, mhP_x on the device, host only enqueues (this rank's wall clock)"}
+        except Exception as e:      # never let the informational leg break the contract line
+            chain = {"error": str(e)[:200]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -348,7 +368,7 @@ def main():
                        "rng": "Philox4x32-10 on device"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_sweep_fast", "kernel_ms": sweep_ms, "bytes_per_gene_update": balg, "peak_source": peak_src},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "chain": chain}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
