@@ -249,6 +249,15 @@ void zz_pinned_free(void *p);
 int zz_set_sample_sink(zz_handle *h, const zz_sample_sink *sink);   /* NULL detaches; row counters restart at 0 */
 int zz_sample_rows_written(zz_handle *h, int64_t *param_rows, int64_t *yv_rows);   /* rows enqueued so far */
 
+/* ---- posterior-predictive discrepancies (R/zigzagPostPredictiveSimulation.R:3-156) ----------------------------
+   Simulates one data set from the current state (x_sim ~ N(Yg, variance_g), dropped with probability 1 - p_x, all -Inf in the
+   spike; Yg_sim from the gene's mixture component; Philox blocks 16 + r and 15 of `step`) and returns the realised discrepancy
+   statistics the reference appends to <prefix>.post_predictive_output.log and .library_specific_post_predictive_output.log:
+     out = { W_L, W_U, B_rumsfeld[1], W_L_r[R], B_rumsfeld[2..R+1] }   (3 + 2 R doubles)
+   `bins` = seq(min(ranges) - 2, max(ranges) + 2, by = 0.1) as posteriorPredictiveSimulation builds it (PostPred:9-17).
+   Chain 0; synchronous (the histograms come back to the host, where the per-bin functionals are formed). */
+int zz_post_predictive(zz_handle *h, uint64_t step, const double *bins, int nbins, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -276,6 +276,18 @@ def sweep_draws(seed, chain, step, gene0, G):
     d = np.empty((9, G)); lib().zzo_sweep_draws(seed, chain, step, gene0, G, _p(d)); return d
 
 
+def post_predictive(h, s, seed, step, bins):
+    """zzo_post_predictive: (W_L, W_U, B, W_L_r[R], B_r[R]) of one simulated data set."""
+    bins = np.ascontiguousarray(bins, dtype=np.float64)
+    R = h.num_libraries
+    out = np.empty(3 + 2 * R)
+    L = lib()
+    L.zzo_post_predictive.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]
+    L.zzo_post_predictive.restype = None
+    L.zzo_post_predictive(C.byref(h), s.c(), seed, step, _p(bins), len(bins), _p(out))
+    return dict(W_L=out[0], W_U=out[1], B=out[2], W_L_r=out[3:3 + R].copy(), B_r=out[3 + R:].copy())
+
+
 class ChainScalars(C.Structure):
     """zzo_chain_scalars == zz_chain_scalars (include/zigzag_gpu.h): scalar tuning parameters, their windows, stream positions."""
     _fields_ = [("active_means_dif", C.c_double * MAX_COMP),

@@ -967,3 +967,104 @@ void zzo_chain_export_scalars(const zzo_chain *c, zzo_chain_scalars *o) {
 const uint32_t *zzo_chain_alloc_trace(const zzo_chain *c) { return c->alloc_trace; }
 zzo_state *zzo_chain_state(zzo_chain *c) { return &c->s; }
 double zzo_chain_lnl(const zzo_chain *c) { return zzo_lnl(&c->h, &c->s); }
+
+/* ------------------------------------------------------------------ posterior-predictive discrepancies
+   R/zigzagPostPredictiveSimulation.R:3-156 restated with explicit Philox draws (DESIGN.md RNG): for gene g and library r,
+   block 16 + r gives z = Box-Muller(w0, w1) (cos branch) of rnorm(Yg, sqrt(variance_g)) and u = w2 of the detection draw;
+   block 15 gives the z of the simulated Yg.  `bins` = seq(min(ranges) - 2, max(ranges) + 2, by = 0.1), built by the caller
+   (PostPred:9-17).  out = { W_L, W_U, B_rumsfeld[1], W_L_r[R], B_rumsfeld[2..R+1] } (the rows of the two log files). */
+static int upper_idx(const double *bins, int nb, double x) { /* number of bins <= x, so that (x < bins[b]) <=> b >= idx */
+  int lo = 0, hi = nb;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (bins[mid] <= x) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+static double trapz(const double *x, const double *y, int n) { /* U:3-9 */
+  acc_t a = 0; for (int i = 1; i < n; ++i) a += (x[i] - x[i - 1]) * (y[i] + y[i - 1]);
+  return 0.5 * (double)a;
+}
+/* get_lowerLevel_wasserstein (PostPred:120-144) from per-library histograms: cnt[r][i] = #{detected x with upper_idx == i},
+   ndet[r], model[r][i] = sum of p_x[g, r] over out-of-spike genes with upper_idx(Yg) == i, for the libraries lo..hi-1 */
+static double lower_wass(const double *bins, int nb, int R, int lo, int hi, const double *cnt, const double *ndet, const double *model, double n_out) {
+  double *diff = (double *)calloc(nb, sizeof(double)), *mx = (double *)calloc(nb, sizeof(double)), *mm = (double *)calloc(nb, sizeof(double));
+  (void)R;
+  for (int r = lo; r < hi; ++r) {
+    acc_t cx = 0, cm = 0; double maxm = -INFINITY;
+    double *mc = (double *)malloc(sizeof(double) * nb);
+    for (int b = 0; b < nb; ++b) { cm += model[(size_t)r * (nb + 1) + b]; mc[b] = (double)cm / n_out; if (mc[b] > maxm) maxm = mc[b]; }
+    for (int b = 0; b < nb; ++b) {
+      cx += cnt[(size_t)r * (nb + 1) + b];
+      mx[b] += ((double)cx / ndet[r]) / (hi - lo);
+      mm[b] += (mc[b] / maxm) / (hi - lo);
+    }
+    free(mc);
+  }
+  for (int b = 0; b < nb; ++b) diff[b] = fabs(mx[b] - mm[b]);
+  double w = trapz(bins, diff, nb);
+  free(diff); free(mx); free(mm);
+  return w;
+}
+void zzo_post_predictive(const zzo_hyper *h, const zzo_state *s, uint64_t seed, uint64_t step, const double *bins, int nb, double *out) {
+  const int R = h->num_libraries, K = h->num_active_components; const int64_t G = s->G; const size_t H = (size_t)(nb + 1);
+  double *cd = (double *)calloc(R * H, 8), *cs = (double *)calloc(R * H, 8), *cds = (double *)calloc(R * H, 8), *css = (double *)calloc(R * H, 8);
+  double *md = (double *)calloc(R * H, 8), *hy = (double *)calloc(H, 8), *hsy = (double *)calloc(H, 8);
+  double ndd[ZZO_MAX_LIBS] = {0}, nds[ZZO_MAX_LIBS] = {0}, zd[ZZO_MAX_LIBS] = {0}, zs[ZZO_MAX_LIBS] = {0}, n_out = 0;
+  acc_t sxd[ZZO_MAX_LIBS] = {0}, sxs[ZZO_MAX_LIBS] = {0}, s1mp[ZZO_MAX_LIBS] = {0};
+  double *sim = (double *)malloc(sizeof(double) * G * R);
+  for (int64_t g = 0; g < G; ++g) {
+    const int sp = s->inactive_spike_allocation[g]; const double y = s->Yg[g], sd = sqrt(s->variance_g[g]);
+    double px[ZZO_MAX_LIBS]; zzo_get_px(h, y, s->gene_lengths[g], px);
+    if (!sp) { n_out += 1; hy[upper_idx(bins, nb, y)] += 1; }
+    { double a[4], n[2]; zzo_uniform4(seed, 0, step, 15, (uint64_t)g, a); zzo_box_muller(a[0], a[1], n);   /* PostPred:79-84 */
+      double sy;
+      if (s->alloc_active_inactive[g]) { int k = s->alloc_within_active[g] - 1; sy = h->active_means[k] + sqrt(h->active_variances[k]) * n[0]; }
+      else sy = h->inactive_means + sqrt(h->inactive_variances) * n[0];
+      if (!sp) hsy[upper_idx(bins, nb, sy)] += 1; }
+    for (int r = 0; r < R; ++r) {
+      const double x = s->Xg[(int64_t)r * G + g];
+      if (x == -INFINITY) zd[r] += 1; else { cd[r * H + upper_idx(bins, nb, x)] += 1; ndd[r] += 1; sxd[r] += x; }
+      if (!sp) { md[r * H + upper_idx(bins, nb, y)] += px[r]; s1mp[r] += 1 - px[r]; }
+      double a[4], n[2]; zzo_uniform4(seed, 0, step, 16 + r, (uint64_t)g, a); zzo_box_muller(a[0], a[1], n);
+      double sx = y + sd * n[0];                                         /* PostPred:24 */
+      if (a[2] < 1 - px[r]) sx = -INFINITY;                              /* PostPred:30-31 */
+      if (sp) sx = -INFINITY;                                            /* PostPred:38 */
+      sim[(int64_t)r * G + g] = sx;
+      if (sx == -INFINITY) zs[r] += 1; else { cs[r * H + upper_idx(bins, nb, sx)] += 1; nds[r] += 1; sxs[r] += sx; }
+    }
+  }
+  /* scaled copies: x - lib mean + grand mean (PostPred:52-58) */
+  double lmd[ZZO_MAX_LIBS], lms[ZZO_MAX_LIBS], gmd = 0, gms = 0;
+  for (int r = 0; r < R; ++r) { lmd[r] = (double)sxd[r] / ndd[r]; lms[r] = (double)sxs[r] / nds[r]; gmd += lmd[r] / R; gms += lms[r] / R; }
+  for (int64_t g = 0; g < G; ++g) for (int r = 0; r < R; ++r) {
+    const double x = s->Xg[(int64_t)r * G + g], sx = sim[(int64_t)r * G + g];
+    if (x != -INFINITY) cds[r * H + upper_idx(bins, nb, x - lmd[r] + gmd)] += 1;
+    if (sx != -INFINITY) css[r * H + upper_idx(bins, nb, sx - lms[r] + gms)] += 1;
+  }
+  out[0] = lower_wass(bins, nb, R, 0, R, cd, ndd, md, n_out) - lower_wass(bins, nb, R, 0, R, cs, nds, md, n_out);     /* W_L, PostPred:43-44 */
+  for (int r = 0; r < R; ++r)                                                                                         /* W_L_r, PostPred:61-66 */
+    out[3 + r] = lower_wass(bins, nb, R, r, r + 1, cds, ndd, md, n_out) - lower_wass(bins, nb, R, r, r + 1, css, nds, md, n_out);
+  /* get_rumsfeld (PostPred:107-118) */
+  { const double c = h->spike_probability * (1 - h->weight_active); double md_ = 0, ms_ = 0, dd[ZZO_MAX_LIBS], ds[ZZO_MAX_LIBS];
+    for (int r = 0; r < R; ++r) {
+      const double model = (1 - c) * ((double)s1mp[r] / n_out) + c;
+      dd[r] = fabs(zd[r] / (double)G - model); ds[r] = fabs(zs[r] / (double)G - model); md_ += dd[r] / R; ms_ += ds[r] / R;
+    }
+    out[2] = md_ - ms_;
+    for (int r = 0; r < R; ++r) out[3 + R + r] = dd[r] - ds[r]; }
+  /* get_upperLevel_wasserstein (PostPred:146-154) with get_model_cumulative (U:20-40) */
+  { double *dens = (double *)malloc(8 * nb), *mc = (double *)malloc(8 * nb), *dy = (double *)malloc(8 * nb), *dsy = (double *)malloc(8 * nb);
+    const double wi = (1 - h->weight_active) * (1 - h->spike_probability), wa = h->weight_active;
+    for (int b = 0; b < nb; ++b) {
+      acc_t a = 0;
+      for (int k = 0; k < K; ++k) a += h->weight_within_active[k] * exp(zzo_dnorm_log(bins[b], h->active_means[k], sqrt(h->active_variances[k])));
+      dens[b] = (wi * exp(zzo_dnorm_log(bins[b], h->inactive_means, sqrt(h->inactive_variances))) + wa * (double)a) / (wi + wa);
+    }
+    acc_t cum = 0, cy = hy[0], csy = hsy[0];
+    for (int b = 1; b < nb; ++b) {
+      cum += (bins[b] - bins[b - 1]) * (dens[b] + dens[b - 1]); mc[b] = 0.5 * (double)cum;
+      cy += hy[b]; csy += hsy[b];
+      dy[b] = fabs((double)cy / n_out - mc[b]); dsy[b] = fabs((double)csy / n_out - mc[b]);
+    }
+    out[1] = trapz(bins + 1, dy + 1, nb - 1) - trapz(bins + 1, dsy + 1, nb - 1);
+    free(dens); free(mc); free(dy); free(dsy); }
+  free(cd); free(cs); free(cds); free(css); free(md); free(hy); free(hsy); free(sim);
+}

@@ -166,6 +166,10 @@ const uint32_t *zzo_chain_alloc_trace(const zzo_chain *c);   /* [K+1][G] */
 zzo_state *zzo_chain_state(zzo_chain *c);
 double zzo_chain_lnl(const zzo_chain *c);
 
+/* posterior-predictive discrepancies of one simulated data set (R/zigzagPostPredictiveSimulation.R:3-156);
+   out = { W_L, W_U, B_rumsfeld_mean, W_L_r[R], B_rumsfeld_r[R] } */
+void zzo_post_predictive(const zzo_hyper *h, const zzo_state *s, uint64_t seed, uint64_t step, const double *bins, int nbins, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -592,3 +592,35 @@ def test_production_sweep_outside_the_straight_line_preconditions(R, alpha_sprea
     st_o, st_g = O.suffstats(ho, s), h.suffstats()[0]
     fin = np.isfinite(st_o)
     assert np.allclose(st_g[fin], st_o[fin], rtol=1e-11, atol=1e-9)
+
+
+def pp_bins(hd, Yg, spike, X):
+    """bins of posteriorPredictiveSimulation (PostPred:9-17)."""
+    from statistics import NormalDist
+    K = len(hd["active_means"])
+    lo_m = NormalDist(hd["inactive_means"], np.sqrt(hd["inactive_variances"])).inv_cdf(0.000001)
+    hi_m = NormalDist(hd["active_means"][K - 1], np.sqrt(hd["active_variances"][K - 1])).inv_cdf(0.999999)
+    yo = Yg[spike == 0]
+    xf = X[np.isfinite(X)]
+    r = [lo_m, hi_m, yo.min(), yo.max(), xf.min(), xf.max()]
+    return np.arange(min(r) - 2, max(r) + 2, 0.1)
+
+
+@pytest.mark.parametrize("G,R,seed", [(6000, 4, 51), (3000, 16, 52), (2500, 2, 53)])
+def test_post_predictive_discrepancies_match_oracle(G, R, seed):
+    """zz_post_predictive: histograms on the device (integer atomics, fixed-point model weights), functionals on the host; the
+    oracle simulates the same data set from the same Philox draws and forms the statistics gene by gene."""
+    X, gl, hd, ho, hg, s, h = setup_pair(G, R, seed)
+    for step in range(2):
+        d = np.concatenate([h.philox_draws(step, sl)[:, 0] for sl in (_capi.SLOT_YG, _capi.SLOT_VARIANCE_G, _capi.SLOT_ALLOC, _capi.SLOT_SPIKE)])
+        O.sweep(ho, s, d); h.sweep(step)
+    bins = pp_bins(hd, s.Yg, s.inactive_spike_allocation, X)
+    for step in (100, 101):
+        g = h.post_predictive(step, bins)
+        o = O.post_predictive(ho, s, 1234, step, bins)      # 1234: the Philox key of gpu_handle()
+        for k in ("W_L", "W_U", "B"):
+            assert np.isclose(g[k], o[k], rtol=1e-9, atol=1e-11), (k, g[k], o[k])
+        assert np.allclose(g["W_L_r"], o["W_L_r"], rtol=1e-9, atol=1e-11) and np.allclose(g["B_r"], o["B_r"], rtol=1e-9, atol=1e-11)
+    assert g["W_L"] != 0 and np.all(np.isfinite(g["W_L_r"]))
+    g2 = h.post_predictive(100, bins)                       # counter-based draws: the same step reproduces the same data set
+    assert g2["W_L"] != g["W_L"] and g2["W_L"] == h.post_predictive(100, bins)["W_L"]

@@ -96,3 +96,24 @@ def test_lung_prob_active_matches_tutorial_device_schedule(tmp_path):
     assert len(rows) == sum(1 for g in range(3001, 9002) if g % 5 == 0) and rows[0].split("\t")[0] == "3005"
     yg = open(os.path.join(str(tmp_path), "lung_dev_mcmc_output", "lung_dev_yg_candidate_genes.log")).read().splitlines()
     assert len(yg[0].split("\t")) == 5001 and 400 <= len(yg) - 1 <= 501 and len(yg[1].split("\t")) == 5001
+
+
+@pytest.mark.parametrize("schedule", ["fused", "device"])
+def test_posterior_predictive_logs(tmp_path, schedule):
+    """mcmc(run_posterior_predictive=TRUE): one simulated data set per (postpred_freq * sample_frequency) generations, realised
+    discrepancies appended to the two log files with the reference's headers (FileWriting:44-55, PostPred:82-88)."""
+    d, tpm, gl, names = lung()
+    mm = zigzag(tpm, gl, num_active_components=2, threshold_i=float(d["threshold_i"]), threshold_a=d["threshold_a"],
+                output_directory=str(tmp_path), gene_names=names, seed=4, write_settings=False)
+    mm.burnin(sample_frequency=50, ngen=800, write_to_files=False, schedule="device")
+    mm.mcmc(sample_frequency=5, ngen=200, mcmcprefix="pp", schedule=schedule, run_posterior_predictive=True, compute_probs=False)
+    out = os.path.join(str(tmp_path), "pp_mcmc_output")
+    a = open(os.path.join(out, "pp.post_predictive_output.log")).read().splitlines()
+    b = open(os.path.join(out, "pp.library_specific_post_predictive_output.log")).read().splitlines()
+    assert a[0].split("\t") == ["gen", "Wass_Lower", "Wass_Upper", "Rums"]
+    assert b[0].split("\t") == ["gen"] + [f"Scaled_Wass_Lower_library_{r}" for r in (1, 2, 3, 4)] + [f"Rums_library_{r}" for r in (1, 2, 3, 4)]
+    rows = np.array([[float(x) for x in l.split("\t")] for l in a[1:]])
+    assert len(rows) == 40 and len(b) == 41 and np.all(rows[:, 0] % 5 == 0) and np.all(np.isfinite(rows))
+    # realised minus simulated discrepancies of an (almost) converged chain scatter around zero, far from the scale of the data
+    assert np.abs(rows[:, 1]).max() < 1.0 and np.abs(rows[:, 2]).max() < 1.0 and np.abs(rows[:, 3]).max() < 0.1
+    assert np.std(rows[:, 1]) > 0

@@ -151,3 +151,31 @@ def test_oracle_reproduces_committed_golden_vectors():
     dec = O.sweep(ho, s, g["draws"])
     assert np.array_equal(dec, g["dec_sweep"]) and np.array_equal(s.Yg, g["sweep_yg"]) and np.array_equal(s.variance_g, g["sweep_vg"])
     assert float(g["sweep_lnl"]) == O.lnl(ho, s) or (np.isneginf(g["sweep_lnl"]) and np.isneginf(O.lnl(ho, s)))
+
+
+def test_post_predictive_restatement_sanity():
+    """zzo_post_predictive (R/zigzagPostPredictiveSimulation.R:3-156): data simulated FROM the model at the simulation truth gives
+    realised-minus-simulated discrepancies that scatter around zero; a wrong detection model (alpha / 20) shows up in the Rumsfeld
+    statistic; the draws are counter-based (same step -> same answer)."""
+    import numpy as np
+    from statistics import NormalDist
+    from zigzag_b200 import synth
+    from oracle import oracle as O
+    G, R = 4000, 4
+    X, gl, _ = synth.simulate(G, R, config_id=77)
+    hd = synth.truth_hyper_dict(R)
+    st = synth.initial_state(X, gl, hd, 5)
+    kw = {k: float(hd[k]) for k in ("s0", "s1", "tau", "spike_probability", "inactive_means", "inactive_variances", "weight_active",
+                                    "beta", "temperature", "variance_g_upper_bound")}
+    ho = O.Hyper.make(hd["alpha_r"], hd["active_means"], hd["active_variances"], hd["weight_within_active"], **kw)
+    s = O.State(X, gl, st["Yg"], st["variance_g"], st["alloc_active_inactive"], st["alloc_within_active"], st["inactive_spike_allocation"])
+    yo, xf = s.Yg[s.inactive_spike_allocation == 0], X[np.isfinite(X)]
+    r = [NormalDist(hd["inactive_means"], hd["inactive_variances"] ** 0.5).inv_cdf(1e-6),
+         NormalDist(hd["active_means"][-1], hd["active_variances"][-1] ** 0.5).inv_cdf(1 - 1e-6), yo.min(), yo.max(), xf.min(), xf.max()]
+    bins = np.arange(min(r) - 2, max(r) + 2, 0.1)
+    a = O.post_predictive(ho, s, 9, 1, bins)
+    assert a["W_L"] == O.post_predictive(ho, s, 9, 1, bins)["W_L"] != O.post_predictive(ho, s, 9, 2, bins)["W_L"]
+    ws = np.array([[O.post_predictive(ho, s, 9, k, bins)[n] for n in ("W_L", "W_U", "B")] for k in range(8)])
+    assert np.abs(ws[:, 0]).max() < 0.5 and np.abs(ws[:, 1]).max() < 0.5 and np.abs(ws[:, 2]).max() < 0.05
+    bad = O.Hyper.make(np.asarray(hd["alpha_r"]) / 20, hd["active_means"], hd["active_variances"], hd["weight_within_active"], **kw)
+    assert O.post_predictive(bad, s, 9, 1, bins)["B"] > 10 * np.abs(ws[:, 2]).max()

@@ -171,6 +171,7 @@ _SIG = {
     "zz_pinned_free": (None, [_P]),
     "zz_set_sample_sink": (C.c_int, [_P, _P]),
     "zz_sample_rows_written": (C.c_int, [_P, _P, _P]),
+    "zz_post_predictive": (C.c_int, [_P, C.c_uint64, _P, C.c_int, _P]),
 }
 EXPORTS = tuple(_SIG)
 
@@ -451,6 +452,13 @@ class Handle:
         sc, hy = ChainScalars(), Hyper()
         self._ck(self.L.zz_chain_read(self.h, C.addressof(sc), C.addressof(hy)))
         return sc, hy
+
+    def post_predictive(self, step, bins):
+        """Realised discrepancies of one simulated data set: dict(W_L, W_U, B, W_L_r[R], B_r[R]) (PostPred:3-156)."""
+        bins = np.ascontiguousarray(bins, dtype=np.float64)
+        out = np.empty(3 + 2 * self.R)
+        self._ck(self.L.zz_post_predictive(self.h, step, _ptr(bins), len(bins), _ptr(out)))
+        return dict(W_L=out[0], W_U=out[1], B=out[2], W_L_r=out[3:3 + self.R].copy(), B_r=out[3 + self.R:].copy())
 
     # ---- sample-time rows written by the device
     def _pinned(self, rows, cols):

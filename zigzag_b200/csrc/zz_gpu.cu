@@ -943,6 +943,90 @@ __global__ void __launch_bounds__(BLOCK) k_sample_row(double gen, const zz_hyper
   }
 }
 
+// ---- posterior-predictive discrepancies (R/zigzagPostPredictiveSimulation.R:3-156) -------------------------
+// One simulated data set per call: x_sim[g, r] ~ N(Yg, variance_g), dropped with probability 1 - p_x[g, r], all -Inf for in-spike
+// genes; Yg_sim from the gene's mixture component.  The reference's statistics are functionals of binned cumulative
+// distributions, so the O(G R) work is histograms: integer counts through atomics (exact, order-free), the p_x-weighted model
+// histogram in 2^-40 fixed point (exact sums again; quantisation <= 4.5e-13 relative at 1 M genes), and three per-library
+// floating-point sums through fixed-order block partials.  Pass 2 repeats the (counter-based) draws to bin the mean-centred copies.
+struct PPArgs {
+  int64_t G; int R, nb, pass;
+  uint64_t seed, step; int64_t gene_offset;
+  const double *Xg, *gl, *Yg, *vg; const uint16_t *flags; const int32_t *perm; const zz_hyper *hyper; const double *bins;
+  unsigned *cd, *cs, *cds, *css, *hy, *hsy;          // [R][nb+1] x 4, [nb+1] x 2
+  unsigned long long *md;                            // [R][nb+1], 2^-40 fixed point
+  double *partials;                                  // [R][gridDim.x][4]: sum x (data), sum x (sim), sum (1 - p_x) over out-of-spike genes
+  double shift_d[ZZ_MAX_LIBS], shift_s[ZZ_MAX_LIBS]; // pass 2: grand mean - library mean
+};
+__device__ __forceinline__ int upper_idx(const double *bins, int nb, double x) {   // number of bins <= x: (x < bins[b]) <=> b >= idx
+  int lo = 0, hi = nb;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (bins[mid] <= x) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+__global__ void __launch_bounds__(BLOCK) k_post_pred(const PPArgs a) {
+  // one library per blockIdx.y: the CTA's histograms of that library live in shared memory and reach global memory as one atomic
+  // per non-empty bin at the end (48 M global atomics per call at 1 M x 16 otherwise)
+  extern __shared__ double sbins[];                   // [nb] bins, then [nb+1] u64 model weights, then 4 x [nb+1] u32 counts
+  __shared__ HyperS H;
+  __shared__ double red[BLOCK / 32];
+  const int r = blockIdx.y, Hn = a.nb + 1;
+  unsigned long long *s_md = reinterpret_cast<unsigned long long *>(sbins + a.nb);
+  unsigned *s_c0 = reinterpret_cast<unsigned *>(s_md + Hn), *s_c1 = s_c0 + Hn, *s_hy = s_c1 + Hn, *s_hsy = s_hy + Hn;
+  load_hyper(H, a.hyper);
+  for (int b = threadIdx.x; b < a.nb; b += BLOCK) sbins[b] = a.bins[b];
+  for (int b = threadIdx.x; b < Hn; b += BLOCK) { s_md[b] = 0; s_c0[b] = 0; s_c1[b] = 0; s_hy[b] = 0; s_hsy[b] = 0; }
+  __syncthreads();
+  double sxd = 0, sxs = 0, s1mp = 0;
+  for (int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x; g < a.G; g += (int64_t)gridDim.x * BLOCK) {
+    const double y = a.Yg[g], sd = sqrt(a.vg[g]);
+    const uint32_t f = a.flags[g];
+    const bool sp = f & F_INSPIKE;
+    const uint64_t gid = (uint64_t)(a.gene_offset + a.perm[g]);
+    const double px = 1 - exp(-((a.gl[g] * exp(y)) * H.alpha[r]));                    // U:150-159
+    const double x = a.Xg[(int64_t)r * a.G + g];
+    uint32_t w[4];
+    philox_block(a.seed, 0, a.step, 16 + r, gid, w);
+    double z0, z1;
+    box_muller(u32_open(w[0]), u32_open(w[1]), z0, z1);
+    double sx = y + sd * z0;                                                          // PostPred:24
+    if (u32_open(w[2]) < 1 - px) sx = -INFINITY;                                      // PostPred:30-31
+    if (sp) sx = -INFINITY;                                                           // PostPred:38
+    if (a.pass == 1) {
+      if (x != -INFINITY) { atomicAdd(s_c0 + upper_idx(sbins, a.nb, x), 1u); sxd += x; }
+      if (sx != -INFINITY) { atomicAdd(s_c1 + upper_idx(sbins, a.nb, sx), 1u); sxs += sx; }
+      if (!sp) {
+        const int iy = upper_idx(sbins, a.nb, y);
+        atomicAdd(s_md + iy, (unsigned long long)(px * 1099511627776.0 + 0.5));
+        s1mp += 1 - px;
+        if (r == 0) {
+          atomicAdd(s_hy + iy, 1u);
+          philox_block(a.seed, 0, a.step, 15, gid, w);
+          box_muller(u32_open(w[0]), u32_open(w[1]), z0, z1);
+          const double sy = (f & F_ACTIVE) ? H.am[flag_k(f) - 1] + sqrt(0.5 * H.two_av[flag_k(f) - 1]) * z0 : H.im + H.sd_i * z0;   // PostPred:79-84
+          atomicAdd(s_hsy + upper_idx(sbins, a.nb, sy), 1u);
+        }
+      }
+    } else {
+      if (x != -INFINITY) atomicAdd(s_c0 + upper_idx(sbins, a.nb, x + a.shift_d[r]), 1u);      // PostPred:52-58
+      if (sx != -INFINITY) atomicAdd(s_c1 + upper_idx(sbins, a.nb, sx + a.shift_s[r]), 1u);
+    }
+  }
+  __syncthreads();
+  unsigned *g0 = (a.pass == 1 ? a.cd : a.cds) + (size_t)r * Hn, *g1 = (a.pass == 1 ? a.cs : a.css) + (size_t)r * Hn;
+  for (int b = threadIdx.x; b < Hn; b += BLOCK) {
+    if (s_c0[b]) atomicAdd(g0 + b, s_c0[b]);
+    if (s_c1[b]) atomicAdd(g1 + b, s_c1[b]);
+    if (a.pass == 1) {
+      if (s_md[b]) atomicAdd(a.md + (size_t)r * Hn + b, s_md[b]);
+      if (r == 0) { if (s_hy[b]) atomicAdd(a.hy + b, s_hy[b]); if (s_hsy[b]) atomicAdd(a.hsy + b, s_hsy[b]); }
+    }
+  }
+  if (a.pass == 1) {
+    const double t0 = block_sum<BLOCK>(sxd, red), t1 = block_sum<BLOCK>(sxs, red), t2 = block_sum<BLOCK>(s1mp, red);
+    if (threadIdx.x == 0) { double *p = a.partials + ((int64_t)r * gridDim.x + blockIdx.x) * 4; p[0] = t0; p[1] = t1; p[2] = t2; p[3] = 0; }
+  }
+}
+
 // allocation_trace += one-hot(allocation), M:194-199
 __global__ void __launch_bounds__(BLOCK) k_alloc_trace(int64_t G, int K, const uint16_t *flags, uint32_t *trace) {
   const int chain = blockIdx.y;
@@ -1054,6 +1138,7 @@ struct zz_handle {
   std::vector<zz_hyper> hyper_host;
   double *pinned;                          // small pinned staging for reduction results
   // zz_sweep_host pipeline (created on first use)
+  void *pp_buf; int pp_nb;                 // zz_post_predictive: histograms + bins on the device
   bool sink_on; zz_sample_sink sink; double *sink_p, *sink_y, *sink_v; int32_t *cand_slots; int64_t sink_prow, sink_yrow;   // zz_set_sample_sink
   DevChain *devchain; double *chain_stats; bool chain_ready; int64_t chain_gen, chain_samples; uint64_t chain_step;   // zz_run_generations
   int32_t *inv_perm; cudaStream_t s_up, s_down; cudaEvent_t ev_entry, ev_up[ZZ_HOST_MAX_CHUNKS], ev_done[ZZ_HOST_MAX_CHUNKS]; bool pipe_ready;
@@ -1389,6 +1474,7 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   h->cfg = *cfg; h->G = cfg->num_genes; h->C = cfg->num_chains; h->R = cfg->num_libraries; h->K = cfg->num_active_components;
   h->sticky = false; h->launches = 0; h->have_data = false; h->own_stream = false; h->stream = nullptr;
   h->inv_perm = nullptr; h->pipe_ready = false; h->s_up = h->s_down = nullptr;
+  h->pp_buf = nullptr; h->pp_nb = 0;
   h->sink_on = false; h->cand_slots = nullptr; h->sink_prow = h->sink_yrow = 0;
   h->devchain = nullptr; h->chain_stats = nullptr; h->chain_ready = false; h->chain_gen = 0; h->chain_samples = 0; h->chain_step = 0;
   *out = h;  // returned even on failure so the caller can read zz_last_error and must zz_destroy
@@ -1473,6 +1559,7 @@ void zz_destroy(zz_handle *h) {
   if (h->inv_perm) cudaFree(h->inv_perm);
   if (h->devchain) cudaFree(h->devchain);
   if (h->cand_slots) cudaFree(h->cand_slots);
+  if (h->pp_buf) cudaFree(h->pp_buf);
   if (h->chain_stats) cudaFree(h->chain_stats);
   if (h->pipe_ready) {
     cudaStreamDestroy(h->s_up); cudaStreamDestroy(h->s_down); cudaEventDestroy(h->ev_entry);
@@ -2203,6 +2290,110 @@ int zz_sample_rows_written(zz_handle *h, int64_t *param_rows, int64_t *yv_rows) 
   ZZ_CHECK(h);
   if (param_rows) *param_rows = h->sink_prow;
   if (yv_rows) *yv_rows = h->sink_yrow;
+  return ZZ_OK;
+}
+
+// ---- posterior-predictive discrepancies (k_post_pred) ---------------------------------------------------------------
+int zz_post_predictive(zz_handle *h, uint64_t step, const double *bins, int nbins, double *out) {
+  ZZ_CHECK(h);
+  if (!h->have_data) return fail(h, ZZ_ERR_STATE, "zz_upload_data has not been called");
+  if (!bins || !out || nbins < 3 || nbins > 1400) return fail(h, ZZ_ERR_INVALID, "zz_post_predictive: need 3 <= nbins <= 1400 (shared-memory histograms)");
+  const int R = h->R, K = h->K, nb = nbins, Hn = nb + 1;
+  const int64_t G = h->G;
+  const size_t n_u32 = (size_t)4 * R * Hn + 2 * Hn, n_u64 = (size_t)R * Hn;
+  const size_t bytes = n_u64 * 8 + (size_t)nb * 8 + n_u32 * 4;
+  if (!h->pp_buf || h->pp_nb < nb) {
+    if (h->pp_buf) cudaFree(h->pp_buf);
+    h->pp_buf = nullptr;
+    ZZ_CUDA(h, cudaMalloc(&h->pp_buf, bytes));
+    h->pp_nb = nb;
+  }
+  unsigned long long *md = reinterpret_cast<unsigned long long *>(h->pp_buf);
+  double *dbins = reinterpret_cast<double *>(md + n_u64);
+  unsigned *u32 = reinterpret_cast<unsigned *>(dbins + nb);
+  ZZ_CUDA(h, cudaMemsetAsync(h->pp_buf, 0, bytes, h->stream));
+  ZZ_CUDA(h, cudaMemcpyAsync(dbins, bins, sizeof(double) * nb, cudaMemcpyHostToDevice, h->stream));
+  ZZ_CUDA(h, cudaMemcpyAsync(&h->hyper_host[0], h->hyper, sizeof(zz_hyper), cudaMemcpyDeviceToHost, h->stream));   // may have moved on the device
+  PPArgs a;
+  memset(&a, 0, sizeof a);
+  a.G = G; a.R = R; a.nb = nb; a.pass = 1; a.seed = h->cfg.seed; a.step = step; a.gene_offset = h->cfg.gene_offset;
+  a.Xg = h->Xg; a.gl = h->gl; a.Yg = h->Yg; a.vg = h->vg; a.flags = h->flags; a.perm = h->perm; a.hyper = h->hyper; a.bins = dbins;
+  a.cd = u32; a.cs = u32 + (size_t)R * Hn; a.cds = u32 + (size_t)2 * R * Hn; a.css = u32 + (size_t)3 * R * Hn;
+  a.hy = u32 + (size_t)4 * R * Hn; a.hsy = a.hy + Hn; a.md = md; a.partials = h->partials;
+  const int nblk = red_blocks(G);
+  const size_t pp_smem = sizeof(double) * nb + (size_t)Hn * (8 + 4 * 4);
+  k_post_pred<<<dim3(nblk, R), BLOCK, pp_smem, h->stream>>>(a);
+  ZZ_LAUNCHED(h);
+  k_reduce_final<<<R, BLOCK, 0, h->stream>>>(h->partials, nblk, 4, h->red_out);
+  ZZ_LAUNCHED(h);
+  std::vector<double> sums((size_t)4 * R);
+  std::vector<unsigned> hu(n_u32);
+  std::vector<unsigned long long> hm(n_u64);
+  ZZ_CUDA(h, cudaMemcpyAsync(sums.data(), h->red_out, sizeof(double) * 4 * R, cudaMemcpyDeviceToHost, h->stream));
+  ZZ_CUDA(h, cudaMemcpyAsync(hu.data(), u32, sizeof(unsigned) * ((size_t)2 * R * Hn), cudaMemcpyDeviceToHost, h->stream));   // cd, cs
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  // library means of the detected values (PostPred:52-57) -> pass 2 bins the mean-centred copies
+  std::vector<double> ndd(R), nds(R);
+  double gmd = 0, gms = 0, lmd[ZZ_MAX_LIBS], lms[ZZ_MAX_LIBS];
+  for (int r = 0; r < R; ++r) {
+    double cdn = 0, csn = 0;
+    for (int i = 0; i < Hn; ++i) { cdn += hu[(size_t)r * Hn + i]; csn += hu[(size_t)(R + r) * Hn + i]; }
+    ndd[r] = cdn; nds[r] = csn;
+    lmd[r] = sums[4 * r + 0] / cdn; lms[r] = sums[4 * r + 1] / csn; gmd += lmd[r] / R; gms += lms[r] / R;
+  }
+  for (int r = 0; r < R; ++r) { a.shift_d[r] = -lmd[r] + gmd; a.shift_s[r] = -lms[r] + gms; }
+  a.pass = 2;
+  k_post_pred<<<dim3(nblk, R), BLOCK, pp_smem, h->stream>>>(a);
+  ZZ_LAUNCHED(h);
+  ZZ_CUDA(h, cudaMemcpyAsync(hu.data(), u32, sizeof(unsigned) * n_u32, cudaMemcpyDeviceToHost, h->stream));
+  ZZ_CUDA(h, cudaMemcpyAsync(hm.data(), md, sizeof(unsigned long long) * n_u64, cudaMemcpyDeviceToHost, h->stream));
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  // ---- the functionals of the histograms (small: R x nbins), as the reference forms them
+  const zz_hyper &hy = h->hyper_host[0];
+  const unsigned *cd = hu.data(), *cs = cd + (size_t)R * Hn, *cds = cs + (size_t)R * Hn, *css = cds + (size_t)R * Hn, *hyh = css + (size_t)R * Hn, *hsy = hyh + Hn;
+  double n_out = 0;
+  for (int i = 0; i < Hn; ++i) n_out += hyh[i];
+  auto trapz = [&](const double *x, const double *y, int n) { long double s = 0; for (int i = 1; i < n; ++i) s += (long double)(x[i] - x[i - 1]) * (y[i] + y[i - 1]); return (double)(0.5L * s); };
+  auto lower = [&](const unsigned *cnt, const std::vector<double> &ndet, int lo, int hi2) {   // get_lowerLevel_wasserstein, PostPred:120-144
+    std::vector<double> mx(nb, 0.0), mm(nb, 0.0), mc(nb), diff(nb);
+    for (int r = lo; r < hi2; ++r) {
+      long double cm = 0, cx = 0; double maxm = -INFINITY;
+      for (int b = 0; b < nb; ++b) { cm += (long double)hm[(size_t)r * Hn + b] / 1099511627776.0L; mc[b] = (double)cm / n_out; if (mc[b] > maxm) maxm = mc[b]; }
+      for (int b = 0; b < nb; ++b) { cx += cnt[(size_t)r * Hn + b]; mx[b] += ((double)cx / ndet[r]) / (hi2 - lo); mm[b] += (mc[b] / maxm) / (hi2 - lo); }
+    }
+    for (int b = 0; b < nb; ++b) diff[b] = fabs(mx[b] - mm[b]);
+    return trapz(bins, diff.data(), nb);
+  };
+  out[0] = lower(cd, ndd, 0, R) - lower(cs, nds, 0, R);                                            // W_L, PostPred:43-44
+  for (int r = 0; r < R; ++r) out[3 + r] = lower(cds, ndd, r, r + 1) - lower(css, nds, r, r + 1);  // W_L_r, PostPred:61-66
+  {   // get_rumsfeld, PostPred:107-118
+    const double c = hy.spike_probability * (1 - hy.weight_active);
+    double md_ = 0, ms_ = 0;
+    for (int r = 0; r < R; ++r) {
+      const double model = (1 - c) * (sums[4 * r + 2] / n_out) + c;
+      const double dd = fabs(((double)G - ndd[r]) / (double)G - model), ds = fabs(((double)G - nds[r]) / (double)G - model);
+      md_ += dd / R; ms_ += ds / R; out[3 + R + r] = dd - ds;
+    }
+    out[2] = md_ - ms_;
+  }
+  {   // get_upperLevel_wasserstein (PostPred:146-154) with get_model_cumulative (U:20-40)
+    std::vector<double> dens(nb), dy(nb, 0.0), dsy(nb, 0.0);
+    const double wi = (1 - hy.weight_active) * (1 - hy.spike_probability), wa = hy.weight_active, s2p = sqrt(2 * 3.14159265358979323846);
+    auto dnorm = [&](double x, double mu, double sd) { const double z = (x - mu) / sd; return exp(-0.5 * z * z) / (sd * s2p); };
+    for (int b = 0; b < nb; ++b) {
+      long double acc = 0;
+      for (int k = 0; k < K; ++k) acc += hy.weight_within_active[k] * dnorm(bins[b], hy.active_means[k], sqrt(hy.active_variances[k]));
+      dens[b] = (wi * dnorm(bins[b], hy.inactive_means, sqrt(hy.inactive_variances)) + wa * (double)acc) / (wi + wa);
+    }
+    long double cum = 0, cy = hyh[0], csy = hsy[0];
+    for (int b = 1; b < nb; ++b) {
+      cum += (long double)(bins[b] - bins[b - 1]) * (dens[b] + dens[b - 1]);
+      const double mc = (double)(0.5L * cum);
+      cy += hyh[b]; csy += hsy[b];
+      dy[b] = fabs((double)cy / n_out - mc); dsy[b] = fabs((double)csy / n_out - mc);
+    }
+    out[1] = trapz(bins + 1, dy.data() + 1, nb - 1) - trapz(bins + 1, dsy.data() + 1, nb - 1);
+  }
   return ZZ_OK;
 }
 

@@ -592,20 +592,22 @@ class zigzag:
         self.lnl_trace = self.lnl_trace[-1:]
 
     def mcmc(self, sample_frequency=100, ngen=10000, write_to_files=True, mcmcprefix="out", compute_probs=True, append=False,
-             schedule="reference"):
+             schedule="reference", run_posterior_predictive=False):
         """R/zigzagMCMC.R:26-311 (posterior-predictive simulation and the PDF reports are out of scope)."""
         prefix = mcmcprefix.split("/")[-1]
         pdir = mcmcprefix + "_mcmc_output"
         if write_to_files and self.rank == 0 and not append:
             os.makedirs(os.path.join(self.output_directory, pdir), exist_ok=True)
-            self.initializeOutputFiles(pdir + "/" + prefix)
+            self.initializeOutputFiles(pdir + "/" + prefix, post_pred=run_posterior_predictive)
+        postpred_every = max(int(round(ngen / (500 * sample_frequency))), 1) * sample_frequency       # M:83-84, M:250
+        pp_prefix = (pdir + "/" + prefix) if write_to_files else None
         self.h.reset_alloc_trace(); self.h.accumulate_alloc_trace(); self.n_samples = 1       # M:142-145
         self.lnl_trace.append(self.calculate_lnl())
         j, starting_gen = self.gen, self.gen
         yv_freq = max(ngen // (sample_frequency * 500), 1)
         write_yv = write_to_files
         ngen = ngen + self.gen
-        if schedule == "device" and self.world == 1:
+        if schedule == "device" and self.world == 1 and not run_posterior_predictive:
             # ONE device-resident segment for the whole run: the device accumulates allocation_trace (M:194-199) and appends the rows
             # of the three log files to pinned host rings at every sampling point (zz_set_sample_sink); the host formats them afterwards
             first, last = self.gen, ngen
@@ -645,6 +647,8 @@ class zigzag:
                             self.writeToYgVariancegOutputFiles(pdir + "/" + prefix, g)
                         if (g - starting_gen) / (yv_freq * sample_frequency) > 500:
                             write_yv = False
+                if run_posterior_predictive and g % postpred_every == 0:                          # M:250-252
+                    self.posteriorPredictiveSimulation(pp_prefix, gen=g)
             self._check_nan()
             if compute_probs and write_to_files:
                 self.computeGeneExpressionProbs_writeToFile(pdir + "/" + prefix)
@@ -662,6 +666,8 @@ class zigzag:
                         self.writeToYgVariancegOutputFiles(pdir + "/" + prefix, self.gen)
                     if (self.gen - starting_gen) / (yv_freq * sample_frequency) > 500:
                         write_yv = False
+            if run_posterior_predictive and self.gen % postpred_every == 0:                       # M:250-252
+                self.posteriorPredictiveSimulation(pp_prefix)
             self.gen += 1
         self._check_nan()
         if compute_probs and write_to_files:
@@ -695,8 +701,14 @@ class zigzag:
             for k, v in rows:
                 f.write(f"{k}\t{v if isinstance(v, str) else _rnum(v)}\n")
 
-    def initializeOutputFiles(self, prefix):                                             # FileWriting:3-58
+    def initializeOutputFiles(self, prefix, post_pred=False):                            # FileWriting:3-58
         K = self.num_active_components
+        if post_pred:                                                                    # FileWriting:44-55
+            R = self.num_libraries
+            with open(self._path(prefix, ".post_predictive_output.log"), "w") as f:
+                f.write("\t".join(["gen", "Wass_Lower", "Wass_Upper", "Rums"]) + "\n")
+            with open(self._path(prefix, ".library_specific_post_predictive_output.log"), "w") as f:
+                f.write("\t".join(["gen"] + [f"Scaled_Wass_Lower_library_{r + 1}" for r in range(R)] + [f"Rums_library_{r + 1}" for r in range(R)]) + "\n")
         cols = ["gen", "lnl", "s0", "s1", "tau"] + [f"alpha_r_library_{r + 1}" for r in range(self.num_libraries)] + \
             ["spike_probability", "inactive_mean", "inactive_variance"] + [f"active_mean_component{k + 1}" for k in range(K)] + \
             [f"active_variance_component{k + 1}" for k in range(K)] + ["weight_active"] + [f"weight_within_active_component_{k + 1}" for k in range(K)]
@@ -705,6 +717,29 @@ class zigzag:
         for suf in ("_yg_candidate_genes.log", "_varianceg_candidate_genes.log"):
             with open(self._path(prefix, suf), "w") as f:
                 f.write("\t".join(["gen"] + list(self.candidate_gene_list)) + "\n")
+
+    def posteriorPredictiveSimulation(self, prefix=None, gen=None):                      # PostPred:3-90
+        """Simulates one data set from the current state on the device and returns / logs the realised discrepancy statistics
+        (lower- and upper-level Wasserstein distances, Rumsfeld zero-fraction discrepancy, and their per-library versions)."""
+        from statistics import NormalDist
+        if self.world != 1:
+            raise NotImplementedError("posterior-predictive statistics are functionals of global histograms: one GPU in this round")
+        K = self.num_active_components
+        st = self.state()
+        yo = st["Yg"][st["inactive_spike_allocation"] == 0]
+        xf = self.Xg[np.isfinite(self.Xg)]
+        rng_ = [NormalDist(self.inactive_means, math.sqrt(self.inactive_variances)).inv_cdf(0.000001),
+                NormalDist(self.active_means[K - 1], math.sqrt(self.active_variances[K - 1])).inv_cdf(0.999999),
+                yo.min(), yo.max(), xf.min(), xf.max()]                                  # PostPred:9-15
+        bins = np.arange(min(rng_) - 2, max(rng_) + 2, 0.1)                              # PostPred:17 (binwidth 0.1)
+        out = self.h.post_predictive(self._next_step(), bins)
+        if prefix is not None:
+            g = self.gen if gen is None else gen
+            with open(self._path(prefix, ".post_predictive_output.log"), "a") as f:      # PostPred:82-84
+                f.write("\t".join(_rnum(x) for x in (g, out["W_L"], out["W_U"], out["B"])) + "\n")
+            with open(self._path(prefix, ".library_specific_post_predictive_output.log"), "a") as f:   # PostPred:86-88
+                f.write("\t".join(_rnum(x) for x in (g, *out["W_L_r"], *out["B_r"])) + "\n")
+        return out
 
     def writeToOutputFiles(self, prefix, gen):                                           # FileWriting:60-86
         row = [self.lnl_trace[-1], self.s0, self.s1, self.tau, *self.alpha_r, self.spike_probability, self.inactive_means,
