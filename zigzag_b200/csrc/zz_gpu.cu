@@ -1140,6 +1140,7 @@ struct zz_handle {
   // zz_sweep_host pipeline (created on first use)
   void *pp_buf; int pp_nb;                 // zz_post_predictive: histograms + bins on the device
   bool sink_on; zz_sample_sink sink; double *sink_p, *sink_y, *sink_v; int32_t *cand_slots; int64_t sink_prow, sink_yrow;   // zz_set_sample_sink
+  bool hyper_host_stale;                   // zz_run_generations moved the hyper-parameters on the device; hyper_host is refreshed by zz_chain_read
   DevChain *devchain; double *chain_stats; bool chain_ready; int64_t chain_gen, chain_samples; uint64_t chain_step;   // zz_run_generations
   int32_t *inv_perm; cudaStream_t s_up, s_down; cudaEvent_t ev_entry, ev_up[ZZ_HOST_MAX_CHUNKS], ev_done[ZZ_HOST_MAX_CHUNKS]; bool pipe_ready;
 };
@@ -1476,6 +1477,7 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   h->inv_perm = nullptr; h->pipe_ready = false; h->s_up = h->s_down = nullptr;
   h->pp_buf = nullptr; h->pp_nb = 0;
   h->sink_on = false; h->cand_slots = nullptr; h->sink_prow = h->sink_yrow = 0;
+  h->hyper_host_stale = false;
   h->devchain = nullptr; h->chain_stats = nullptr; h->chain_ready = false; h->chain_gen = 0; h->chain_samples = 0; h->chain_step = 0;
   *out = h;  // returned even on failure so the caller can read zz_last_error and must zz_destroy
   int ndev = 0;
@@ -1683,7 +1685,8 @@ int zz_set_hyper(zz_handle *h, int chain, const zz_hyper *hy) {
   if (!hy) return fail(h, ZZ_ERR_INVALID, "hyper is NULL");
   if (hy->num_libraries != h->R || hy->num_active_components != h->K)
     return fail(h, ZZ_ERR_INVALID, "hyper dimensions do not match the handle");
-  if (memcmp(h->hyper_host[chain].alpha_r, hy->alpha_r, sizeof(double) * h->R) != 0) h->lps_valid = false;  // A depends on alpha_r
+  if (h->hyper_host_stale || memcmp(h->hyper_host[chain].alpha_r, hy->alpha_r, sizeof(double) * h->R) != 0) h->lps_valid = false;  // A depends on alpha_r
+  h->hyper_host_stale = false;
   h->fasth_valid = false;
   h->hyper_host[chain] = *hy;
   ZZ_CUDA(h, cudaMemcpyAsync(h->hyper + chain, &h->hyper_host[chain], sizeof(zz_hyper), cudaMemcpyHostToDevice, h->stream));
@@ -1919,6 +1922,11 @@ int zz_px_commit(zz_handle *h, int chain, int lib, double alpha_new) {
   ZZ_CHECK(h);
   if (int rc = chain_ok(h, chain)) return rc;
   if (lib < 0 || lib >= h->R) return fail(h, ZZ_ERR_INVALID, "library index out of range");
+  if (h->hyper_host_stale) {   // a device-resident segment moved the hyper-parameters: this entry uploads the host copy below
+    ZZ_CUDA(h, cudaMemcpyAsync(&h->hyper_host[0], h->hyper, sizeof(zz_hyper), cudaMemcpyDeviceToHost, h->stream));
+    ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->hyper_host_stale = false;
+  }
   const int64_t off = (int64_t)chain * h->G;
   if (h->R > 2) {  // Pr:213-215
     k_px_commit<<<gene_grid(h, h->G), BLOCK, 0, h->stream>>>(h->G, lib, alpha_new, h->Xg, h->gl, h->Yg + off, h->vg + off,
@@ -2226,6 +2234,7 @@ int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, d
   }
   h->stats_target = saved_target; h->stats_allreduce = saved_allreduce;
   h->stats_fresh = false;
+  if (ngen > 0) h->hyper_host_stale = true;
   if (rc) return rc;
   ZZ_CUDA(h, cudaGetLastError());
   return ZZ_OK;
@@ -2237,6 +2246,7 @@ int zz_chain_read(zz_handle *h, zz_chain_scalars *scalars, zz_hyper *hyper) {
   ZZ_CUDA(h, cudaMemcpyAsync(&h->hyper_host[0], h->hyper, sizeof(zz_hyper), cudaMemcpyDeviceToHost, h->stream));
   if (scalars) ZZ_CUDA(h, cudaMemcpyAsync(scalars, &h->devchain->sc, sizeof(zz_chain_scalars), cudaMemcpyDeviceToHost, h->stream));
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));   // the host copy of the hyper-parameters is current again
+  h->hyper_host_stale = false;
   if (scalars) scalars->n_samples = h->chain_samples;
   if (hyper) *hyper = h->hyper_host[0];
   return ZZ_OK;
