@@ -196,7 +196,9 @@ int zz_sweep_host(zz_handle *h, uint64_t step, int tune, double *Yg, double *var
    window are computed by a single device thread between the gene-sum kernels; accepted moves gate the cache-commit kernels
    (Pr:113/147/187, Pr:213-215) on the device.  Nothing is copied to the host and the host never waits: it only enqueues.
    Scalar draws come from a private Philox stream (gene index 0xFFFFFFFF, block 255, counter hyper_ctr / 4).
-   Chain 0, default model (shared_variance = TRUE, multi_thresh_a = TRUE), single GPU in this round. */
+   Default model (shared_variance = TRUE, multi_thresh_a = TRUE).  A handle with several chains advances all of them in the same
+   launches (one stage block, one reduction slice, one commit gate per chain; every chain draws with its own chain index);
+   gene shards on several GPUs (zz_comm_connect) and the sample sink need a one-chain handle. */
 typedef struct zz_priors {      /* constructor arguments of zigzag$new, R/zigzagInitialize.R:7-41 */
   double weight_active_shape_1, weight_active_shape_2;
   double spike_prior_shape_1, spike_prior_shape_2;
@@ -219,11 +221,11 @@ typedef struct zz_chain_scalars {   /* the scalar chain state that lives on the 
   int64_t n_samples;            /* allocation_trace accumulations done */
 } zz_chain_scalars;
 
-int zz_chain_begin(zz_handle *h, const zz_priors *priors, const zz_chain_scalars *scalars);
+int zz_chain_begin(zz_handle *h, const zz_priors *priors, const zz_chain_scalars *scalars);   /* scalars: one struct per chain (gen, step, n_samples equal) */
 /* ngen generations; tune != 0: burn-in (acceptance windows, tune_all every 400 generations with `target`, U:183-240);
    tune == 0: sampling, allocation_trace accumulated whenever gen % sample_frequency == 0 (M:188-199).  Asynchronous. */
 int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, double target);
-/* waits for the device, returns the scalar state and chain 0's hyper-parameters (either pointer may be NULL) */
+/* waits for the device, returns the scalar state and the hyper-parameters of every chain ([num_chains] each; either may be NULL) */
 int zz_chain_read(zz_handle *h, zz_chain_scalars *scalars, zz_hyper *hyper);
 
 /* ---- sample-time outputs without stopping the device loop (R/zigzagMCMC.R:188-220, R/zigzagFileWriting.R:60-109) ----

@@ -329,6 +329,11 @@ class Chain:
     def lnl(self):
         return self.L.zzo_chain_lnl(self.ptr)
 
+    def set_stream(self, seed, chain_index):
+        self.L.zzo_chain_set_stream.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
+        self.L.zzo_chain_set_stream.restype = None
+        self.L.zzo_chain_set_stream(self.ptr, seed, chain_index)
+
     def scalars(self):
         out = ChainScalars()
         self.L.zzo_chain_export_scalars.argtypes = [C.c_void_p, C.c_void_p]

@@ -551,6 +551,7 @@ struct zzo_chain {
   uint8_t w_im[100], w_av[100], w_am[ZZO_MAX_COMP][100], w_s0[100], w_s1[100], w_tau[100], w_s0tau[100], w_alpha[ZZO_MAX_LIBS][100];
   double proposal_probs[15];
   uint64_t seed, hyper_ctr, step;
+  uint32_t chain_index; /* chain field of every Philox counter (0 unless zzo_chain_set_stream) */
   double hyper_buf[4];
   int64_t gen;
   uint32_t *alloc_trace; /* [K+1][G] */
@@ -561,7 +562,7 @@ struct zzo_chain {
 /* hyper-level draws: a private Philox stream (gene index 0xFFFFFFFF, blk 255) */
 static double c_unif(zzo_chain *c) {
   double o[4];
-  if ((c->hyper_ctr & 3) == 0) { zzo_uniform4(c->seed, 0, c->hyper_ctr >> 2, 255, 0xFFFFFFFFull, o); memcpy(c->hyper_buf, o, sizeof o); }
+  if ((c->hyper_ctr & 3) == 0) { zzo_uniform4(c->seed, c->chain_index, c->hyper_ctr >> 2, 255, 0xFFFFFFFFull, o); memcpy(c->hyper_buf, o, sizeof o); }
   return c->hyper_buf[c->hyper_ctr++ & 3];
 }
 static double c_norm(zzo_chain *c) { double n[2]; double a = c_unif(c), b = c_unif(c); zzo_box_muller(a, b, n); return n[0]; }
@@ -612,16 +613,16 @@ static void fill_sweep_draws(zzo_chain *c, int blocks) {
   for (int64_t g = 0; g < G; ++g) {
     double a[4], n[2];
     if (blocks & 1) {
-      zzo_uniform4(c->seed, 0, c->step, 0, (uint64_t)g, a);
+      zzo_uniform4(c->seed, c->chain_index, c->step, 0, (uint64_t)g, a);
       zzo_box_muller(a[0], a[1], n);
       d[0 * G + g] = n[0]; d[1 * G + g] = a[2]; d[2 * G + g] = a[3];
     }
     if (blocks & 2) {
-      zzo_uniform4(c->seed, 0, c->step, 1, (uint64_t)g, a);
+      zzo_uniform4(c->seed, c->chain_index, c->step, 1, (uint64_t)g, a);
       d[3 * G + g] = a[0]; d[4 * G + g] = a[1]; d[5 * G + g] = a[2];
     }
     if (blocks & 4) {
-      zzo_uniform4(c->seed, 0, c->step, 2, (uint64_t)g, a);
+      zzo_uniform4(c->seed, c->chain_index, c->step, 2, (uint64_t)g, a);
       zzo_box_muller(a[0], a[1], n);
       d[6 * G + g] = n[0]; d[7 * G + g] = n[1]; d[8 * G + g] = a[2];
     }
@@ -937,7 +938,7 @@ void zzo_chain_run_fused(zzo_chain *c, int ngen, int sample_frequency, int tune,
   double *draws = (double *)malloc(sizeof(double) * 9 * c->G);
   if (!tune && c->n_samples == 0) accumulate_trace(c);
   for (int i = 0; i < ngen; ++i) {
-    zzo_sweep_draws(c->seed, 0, c->step, 0, c->G, draws);
+    zzo_sweep_draws(c->seed, c->chain_index, c->step, 0, c->G, draws);
     zzo_sweep(&c->h, &c->s, draws, tune, NULL);
     c->step++;
     static const int hyper_slots[] = {1, 4, 6, 7, 8, 12, 13, 14, 15};
@@ -965,6 +966,7 @@ void zzo_chain_export_scalars(const zzo_chain *c, zzo_chain_scalars *o) {
   o->step = c->step; o->gen = c->gen; o->n_samples = c->n_samples;
 }
 const uint32_t *zzo_chain_alloc_trace(const zzo_chain *c) { return c->alloc_trace; }
+void zzo_chain_set_stream(zzo_chain *c, uint64_t seed, uint32_t chain_index) { c->seed = seed; c->chain_index = chain_index; }
 zzo_state *zzo_chain_state(zzo_chain *c) { return &c->s; }
 double zzo_chain_lnl(const zzo_chain *c) { return zzo_lnl(&c->h, &c->s); }
 

@@ -163,6 +163,8 @@ typedef struct zzo_chain_scalars {
 } zzo_chain_scalars;
 void zzo_chain_export_scalars(const zzo_chain *c, zzo_chain_scalars *out);
 const uint32_t *zzo_chain_alloc_trace(const zzo_chain *c);   /* [K+1][G] */
+/* from now on the chain draws with Philox key `seed` and chain field `chain_index` (batched chains of one GPU handle share the key) */
+void zzo_chain_set_stream(zzo_chain *c, uint64_t seed, uint32_t chain_index);
 zzo_state *zzo_chain_state(zzo_chain *c);
 double zzo_chain_lnl(const zzo_chain *c);
 

@@ -129,3 +129,43 @@ def test_sample_rows_are_written_by_the_device():
     assert np.array_equal(yrow[0, 1:], np.where(sp, -10.0, st["Yg"][cand]))
     assert np.array_equal(vrow[0, 1:], np.where(sp, 0.0, st["variance_g"][cand]))
     h.clear_sample_sink()
+
+
+@pytest.mark.parametrize("G,C_", [(1800, 3), (500, 17)])
+def test_batched_chains_run_device_resident_and_match_their_oracle_chains(G, C_):
+    """A handle with several chains (shared data, per-chain state and hyper-parameters, chain index in every Philox counter):
+    zz_run_generations advances all of them in the same launches — one stage block, one reduction slice and one gate per chain.
+    17 chains exceed the fused statistics epilogue (296 doubles): the sweep's per-CTA rows are reduced per chain instead."""
+    R, K = 4, 2
+    X, gl, _ = synth.simulate(G, R, config_id=333)
+    pri = O.Priors.defaults(-1.0, (1.0, 6.0))
+    chains = [O.Chain(X, gl, pri, K, 100 + c) for c in range(C_)]          # different seeds: different initial states / hypers
+    h = _capi.Handle(G, R, K, num_chains=C_, seed=2024)
+    h.upload_data(X, gl)
+    scs = []
+    for c, ch in enumerate(chains):
+        st, hy = ch.state_arrays(), ch.hyper
+        hg = _capi.Hyper(); C.memmove(C.byref(hg), C.byref(hy), C.sizeof(_capi.Hyper))
+        h.set_hyper(hg, c)
+        h.set_state(c, **{k: st[k] for k in ("Yg", "variance_g", "alloc_active_inactive", "alloc_within_active", "inactive_spike_allocation",
+                                             "XgLikelihood", "variance_g_probability", "tuningParam_yg", "tuningParam_variance_g")})
+        ch.set_stream(2024, c)                                             # from here on: the handle's key, this chain's index
+        scs.append(ch.scalars())
+    # the constructors consumed different numbers of uniforms; batched chains only need gen / step / n_samples in lock-step
+    h.reset_windows(); h.reset_alloc_trace()
+    h.chain_begin(pri, scs)
+    for ch in chains:
+        ch.run_fused(40, tune=True); ch.run_fused(12, sample_frequency=3, tune=False)
+    h.run_generations(40, tune=True); h.run_generations(12, tune=False, sample_frequency=3)
+    sc_g, hy_g = h.chain_read()
+    for c, ch in enumerate(chains):
+        sc_o, hy_o = ch.scalars(), ch.hyper
+        assert sc_g[c].hyper_ctr == sc_o.hyper_ctr and sc_g[c].gen == sc_o.gen == 52
+        for f in ("s0", "s1", "tau", "spike_probability", "inactive_means", "inactive_variances", "weight_active"):
+            assert np.isclose(getattr(hy_g[c], f), getattr(hy_o, f), rtol=1e-9, atol=1e-13), (c, f)
+        assert np.allclose(list(hy_g[c].alpha_r)[:R], list(hy_o.alpha_r)[:R], rtol=1e-9)
+        g, o = h.get_state(c), ch.state_arrays()
+        assert np.array_equal(g["alloc_active_inactive"], o["alloc_active_inactive"])
+        assert np.allclose(g["Yg"], o["Yg"], rtol=1e-9, atol=1e-12) and np.allclose(g["variance_g"], o["variance_g"], rtol=1e-9)
+        assert np.array_equal(h.get_alloc_trace(c), ch.alloc_trace(K))
+    assert hy_g[0].tau != hy_g[1].tau

@@ -14,9 +14,12 @@ K = len(hd["active_means"])
 hg = _capi.Hyper.make(hd["alpha_r"], hd["active_means"], hd["active_variances"], hd["weight_within_active"],
                       **{k: float(hd[k]) for k in ("s0","s1","tau","spike_probability","inactive_means","inactive_variances","weight_active","beta","temperature","variance_g_upper_bound")})
 thr_a = (1.0, 6.0)[:K]
-h = _capi.Handle(G, R, K, num_chains=1, seed=1)
-h.upload_data(X, gl); h.set_hyper(hg, 0); h.set_state(0, **st); h.refresh_caches()
-h.chain_begin(_capi.Priors.defaults(-1.0, thr_a), _capi.ChainScalars.initial(hd["active_means"], thr_a, R))
+h = _capi.Handle(G, R, K, num_chains=chains, seed=1)
+h.upload_data(X, gl)
+for c in range(chains):
+    h.set_hyper(hg, c); h.set_state(c, **st)
+h.refresh_caches()
+h.chain_begin(_capi.Priors.defaults(-1.0, thr_a), [_capi.ChainScalars.initial(hd["active_means"], thr_a, R) for _ in range(chains)])
 for tune in (True, False):
     h.run_generations(20, tune=tune); h.sync()
     l0 = h.launch_count
@@ -24,8 +27,9 @@ for tune in (True, False):
     h.run_generations(ngen, tune=tune, sample_frequency=10); h.sync()
     dt = (time.perf_counter() - t0) / ngen
     print(f"{name}: device-resident {'burn-in' if tune else 'sampling'} generation {dt*1e6:.1f} us "
-          f"({(h.launch_count-l0)/ngen:.1f} launches) -> {1/dt:.0f} generations/s, {G/dt/1e9:.2f} G gene-updates/s inside a full chain")
+          f"({(h.launch_count-l0)/ngen:.1f} launches, {chains} chain(s)) -> {1/dt:.0f} generations/s, {G*chains/dt/1e9:.2f} G gene-updates/s inside full chains")
 sc, hy = h.chain_read()
+if chains > 1: sc, hy = sc[0], hy[0]
 print("   after", sc.gen, "generations: tau %.4f s0 %.4f s1 %.4f w_active %.4f spike %.4f alpha[0] %.3f" % (hy.tau, hy.s0, hy.s1, hy.weight_active, hy.spike_probability, hy.alpha_r[0]))
 if "--host" in sys.argv:
     # the same generation driven from the host: zigzag_b200/zigzag.py (schedule="fused"): every hyper move is Python + a device

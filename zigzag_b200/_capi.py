@@ -442,16 +442,26 @@ class Handle:
 
     # ---- device-resident generation loop
     def chain_begin(self, priors, scalars):
-        """priors / scalars: ctypes structures with the layout of zz_priors / zz_chain_scalars (any class of that layout)."""
-        self._ck(self.L.zz_chain_begin(self.h, C.addressof(priors), C.addressof(scalars)))
+        """priors: ctypes structure with the layout of zz_priors; scalars: one structure with the layout of zz_chain_scalars per
+        chain of the handle (a single structure when the handle has one chain)."""
+        if not isinstance(scalars, (list, tuple)):
+            scalars = [scalars]
+        assert len(scalars) == self.C, "one zz_chain_scalars per chain"
+        arr = (ChainScalars * self.C)()
+        for c, sc in enumerate(scalars):
+            C.memmove(C.byref(arr, c * C.sizeof(ChainScalars)), C.addressof(sc), C.sizeof(ChainScalars))
+        self._ck(self.L.zz_chain_begin(self.h, C.addressof(priors), C.addressof(arr)))
 
     def run_generations(self, ngen, tune=False, sample_frequency=1, target=0.44):
         self._ck(self.L.zz_run_generations(self.h, int(ngen), int(tune), int(sample_frequency), float(target)))
 
     def chain_read(self):
-        sc, hy = ChainScalars(), Hyper()
+        """(scalars, hyper) of chain 0 for a one-chain handle, else two lists with one entry per chain."""
+        sc, hy = (ChainScalars * self.C)(), (Hyper * self.C)()
         self._ck(self.L.zz_chain_read(self.h, C.addressof(sc), C.addressof(hy)))
-        return sc, hy
+        if self.C == 1:
+            return sc[0], hy[0]
+        return list(sc), list(hy)
 
     def post_predictive(self, step, bins):
         """Realised discrepancies of one simulated data set: dict(W_L, W_U, B, W_L_r[R], B_r[R]) (PostPred:3-156)."""

@@ -24,13 +24,14 @@ struct DevChain {
   // the pending move, between its "propose" and its "decide" stage
   double HR, pp, pc, difp, prop0, prop1;
   int sel, k;
+  int chain, pad2_;               // index of this chain in the handle (chain field of its Philox counters)
 };
 
 // ---- scalar draws: private Philox stream, four uniforms per block (Marsaglia-Tsang gamma, beta from two gammas) ----
 __device__ inline double c_unif(DevChain &c, uint64_t seed) {
   if ((c.sc.hyper_ctr & 3) == 0) {
     uint32_t o[4];
-    philox_block(seed, 0, c.sc.hyper_ctr >> 2, 255, 0xFFFFFFFFull, o);
+    philox_block(seed, (uint32_t)c.chain, c.sc.hyper_ctr >> 2, 255, 0xFFFFFFFFull, o);
     for (int j = 0; j < 4; ++j) c.sc.hyper_buf[j] = u32_open(o[j]);
   }
   return c.sc.hyper_buf[c.sc.hyper_ctr++ & 3];
@@ -303,8 +304,11 @@ enum ChainStage {
   ST_ALL_CLOSED     // slots 1, 4, 6, 7, 8, 12, 13, 14 in one go from the closed forms, then propose mhP_x -> detection delta
 };
 
-__global__ void k_chain_stage(int stage, int iter, int tune, int K, int R, uint64_t seed, DevChain *cp, zz_hyper *hp,
-                              const double *stats_g, const double *red, double target, int do_tune_all, int sampled) {
+__global__ void k_chain_stage(int stage, int iter, int tune, int K, int R, uint64_t seed, DevChain *cp_all, zz_hyper *hp_all,
+                              const double *stats_all, const double *red_all, int red_stride, double target, int do_tune_all, int sampled) {
+  // one block per chain of the handle (batched chains run their scalar stages side by side)
+  DevChain *cp = cp_all + blockIdx.x; zz_hyper *hp = hp_all + blockIdx.x;
+  const double *stats_g = stats_all + (size_t)blockIdx.x * (3 * (K + 1) + 10), *red = red_all + (size_t)blockIdx.x * red_stride;
   // One thread does the scalar work, but on a shared-memory copy of the chain state: the moves touch a few thousand bytes (100-wide
   // windows shifted element by element, Philox buffer, mailbox) and a single thread pays the full DRAM/L2 latency for each access
   // (measured: 150 us per generation on the global-memory version, most of it window shifts).

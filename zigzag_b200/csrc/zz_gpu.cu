@@ -254,7 +254,7 @@ struct FastArgs {
   int64_t rows_per_chain;
   int want_stats, do_spike_move;
   const int32_t *slot_list;         // list mode (zz_sweep_host chunks): position p in [g_begin, g_end) addresses gene slot slot_list[p]
-  const int *gate;                  // k_refresh_lps in the device-resident loop: rebuild only if *gate != 0 (accepted mhP_x)
+  const int *gate; int gate_stride; // k_refresh_lps in the device-resident loop: chain c is rebuilt only if gate[c * gate_stride] != 0 (accepted mhP_x)
   int host_io; HostChunk hio;       // list mode + host_io: the tile itself reads its genes' state from hio.s* and writes hio.d* (caller order)
   // fused epilogue: the last CTA to finish reduces the rows (and all-reduces them over peer memory when asked) into stats_out
   unsigned *done_counter; double *stats_out; int do_allreduce; CommArgs cm;
@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const
 // lps <- A(Yg) for every out-of-spike gene (after anything that changed Yg or alpha_r outside the fast sweep)
 template <int RT>
 __global__ void __launch_bounds__(BLOCK) k_refresh_lps(const FastArgs fa) {
-  if (fa.gate && !*fa.gate) return;
+  if (fa.gate && !fa.gate[(size_t)blockIdx.y * fa.gate_stride]) return;
   __shared__ FastH H;
   __shared__ MathTabs T;
   const SweepArgs &a = fa.s;
@@ -727,11 +727,12 @@ struct EvalArgs {
   const uint16_t *flags;
   const zz_hyper *hyper;   // already offset to the chain (or base when grid.y spans chains)
   double *out0, *out1;     // per-gene outputs (chain-offset applied by blockIdx.y * G)
-  const int *gate;         // device-resident loop: the kernel does nothing unless *gate != 0 (an accepted move)
+  const int *gate;         // device-resident loop: chain c does nothing unless gate[c * gate_stride] != 0 (an accepted move)
+  int gate_stride;
 };
 
 __global__ void __launch_bounds__(BLOCK) k_eval(const EvalArgs a) {
-  if (a.gate && !*a.gate) return;
+  if (a.gate && !a.gate[(size_t)blockIdx.y * a.gate_stride]) return;
   __shared__ HyperS H;
   const int chain = blockIdx.y;
   load_hyper(H, a.hyper + chain);
@@ -769,25 +770,31 @@ struct RedArgs {
 __global__ void __launch_bounds__(BLOCK) k_reduce(const RedArgs a) {
   __shared__ HyperS H;
   __shared__ double red[BLOCK / 32];
-  load_hyper(H, a.hyper);
-  const int lib = (a.prop && a.op == RED_PXDELTA) ? a.prop->p_lib : (int)blockIdx.y;
+  // blockIdx.z = chain of a batched launch (zz_run_generations on several chains); the host entry points launch with grid.z = 1 and
+  // pointers already offset to their chain
+  const int64_t coff = (int64_t)blockIdx.z * a.G;
+  const double *Yg = a.Yg + coff, *vg = a.vg + coff, *vgprob = a.vgprob + coff;
+  const uint16_t *flags = a.flags + coff;
+  const DevChain *prop = a.prop ? a.prop + blockIdx.z : nullptr;
+  load_hyper(H, a.hyper + blockIdx.z);
+  const int lib = (prop && a.op == RED_PXDELTA) ? prop->p_lib : (int)blockIdx.y;
   double v0 = 0, v1 = 0;
-  const bool active_y = !(a.op == RED_PXDELTA && !a.prop && !a.lib_mask[lib]);
+  const bool active_y = !(a.op == RED_PXDELTA && !prop && !a.lib_mask[lib]);
   // parameters of the sum: by value from the host, or from the device-side mailbox (zz_run_generations; RED_LEVEL2 then runs
   // with grid.y = 2: proposed and current parameters in one launch)
-  const double p_s0 = a.prop ? a.prop->p_s0 : a.s0, p_s1 = a.prop ? a.prop->p_s1 : a.s1, p_tau = a.prop ? a.prop->p_tau : a.tau;
-  const double p_im = a.prop ? a.prop->l2[blockIdx.y].im : a.im, p_iv = a.prop ? a.prop->l2[blockIdx.y].iv : a.iv;
-  const double *p_am = a.prop ? a.prop->l2[blockIdx.y].am : a.am, *p_av = a.prop ? a.prop->l2[blockIdx.y].av : a.av;
-  const double p_alpha = a.op == RED_PXDELTA ? (a.prop ? a.prop->p_alpha : a.alpha_prop[lib]) : 0.0;
+  const double p_s0 = prop ? prop->p_s0 : a.s0, p_s1 = prop ? prop->p_s1 : a.s1, p_tau = prop ? prop->p_tau : a.tau;
+  const double p_im = prop ? prop->l2[blockIdx.y].im : a.im, p_iv = prop ? prop->l2[blockIdx.y].iv : a.iv;
+  const double *p_am = prop ? prop->l2[blockIdx.y].am : a.am, *p_av = prop ? prop->l2[blockIdx.y].av : a.av;
+  const double p_alpha = a.op == RED_PXDELTA ? (prop ? prop->p_alpha : a.alpha_prop[lib]) : 0.0;
   if (active_y) {
     for (int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x; g < a.G; g += (int64_t)gridDim.x * BLOCK) {
-      const double y = a.Yg[g], v = a.vg[g];
-      const uint32_t f = a.flags[g];
+      const double y = Yg[g], v = vg[g];
+      const uint32_t f = flags[g];
       const bool in_spike = f & F_INSPIKE;
       if (a.op == RED_VARG_HYPER) {                  // Pr:84-87, 126-130, 167-170
         if (!in_spike) {
           v0 += varg_prior(H, v, get_sigmax(p_s0, p_s1, y), p_tau, sqrt(p_tau));
-          v1 += a.vgprob[g];
+          v1 += vgprob[g];
         }
       } else if (a.op == RED_LEVEL2) {               // Pr:444-447, 653-654, 780-784
         if (f & F_ACTIVE) {
@@ -800,7 +807,7 @@ __global__ void __launch_bounds__(BLOCK) k_reduce(const RedArgs a) {
       } else if (a.op == RED_PXDELTA) {              // Pr:209-224
         const double x = a.Xg[(int64_t)lib * a.G + g];
         const double gl = a.gl[g];
-        if (a.prop) {
+        if (prop) {
           // device-resident loop: the normal density of the library is the same on both sides and exp(y) is shared — only the
           // detection terms are evaluated (5 libm calls per gene instead of 12)
           if (!in_spike && !(H.beta < 0.0000001)) {
@@ -821,7 +828,7 @@ __global__ void __launch_bounds__(BLOCK) k_reduce(const RedArgs a) {
   const double s0 = block_sum<BLOCK>(v0, red);
   const double s1 = block_sum<BLOCK>(v1, red);
   if (threadIdx.x == 0) {
-    double *p = a.partials + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 2;
+    double *p = a.partials + (((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 2;
     p[0] = s0; p[1] = s1;
   }
 }
@@ -906,6 +913,8 @@ __global__ void __launch_bounds__(BLOCK) k_px_commit(int64_t G, int lib, double 
 // the same commit for the device-resident loop: library and new alpha come from the mailbox, nothing happens unless mhP_x accepted
 __global__ void __launch_bounds__(BLOCK) k_px_commit_dev(int64_t G, const DevChain *c, const double *Xg, const double *gl, const double *Yg,
                                                           const double *vg, const uint16_t *flags, const zz_hyper *hyper, double *xglik) {
+  c += blockIdx.y; hyper += blockIdx.y;                 // blockIdx.y = chain
+  { const int64_t coff = (int64_t)blockIdx.y * G; Yg += coff; vg += coff; flags += coff; xglik += coff; }
   if (!c->gate_px) return;
   __shared__ HyperS H;
   load_hyper(H, hyper);
@@ -1244,7 +1253,7 @@ void fill_fast_args(zz_handle *h, FastArgs &fa) {
   fa.nd_mask = h->nd_mask; fa.xbar = h->xbar; fa.xss = h->xss; fa.fasth = h->fasth;
   fa.partials = h->sw_partials; fa.rows_per_chain = 0; fa.want_stats = 0; fa.do_spike_move = 0;
   fa.done_counter = h->tile_counter; fa.stats_out = nullptr; fa.do_allreduce = 0; memset(&fa.cm, 0, sizeof fa.cm);
-  fa.slot_list = nullptr; fa.host_io = 0; memset(&fa.hio, 0, sizeof fa.hio); fa.gate = nullptr;
+  fa.slot_list = nullptr; fa.host_io = 0; memset(&fa.hio, 0, sizeof fa.hio); fa.gate = nullptr; fa.gate_stride = 0;
 }
 
 int ensure_fasth(zz_handle *h) {
@@ -1443,7 +1452,7 @@ int launch_eval(zz_handle *h, int which, int chain /* -1 = all chains */, double
   EvalArgs a;
   const int64_t off = chain < 0 ? 0 : (int64_t)chain * h->G;
   a.G = h->G; a.which = which; a.Xg = h->Xg; a.gl = h->gl; a.Yg = h->Yg + off; a.vg = h->vg + off; a.flags = h->flags + off;
-  a.hyper = h->hyper + (chain < 0 ? 0 : chain); a.out0 = out0; a.out1 = out1; a.gate = gate;
+  a.hyper = h->hyper + (chain < 0 ? 0 : chain); a.out0 = out0; a.out1 = out1; a.gate = gate; a.gate_stride = (int)(sizeof(DevChain) / sizeof(int));
   k_eval<<<gene_grid(h, h->G, chain < 0 ? h->C : 1), BLOCK, 0, h->stream>>>(a);
   ZZ_LAUNCHED(h);
   return ZZ_OK;
@@ -2102,18 +2111,19 @@ int zz_chain_begin(zz_handle *h, const zz_priors *priors, const zz_chain_scalars
   ZZ_CHECK(h);
   if (!priors || !scalars) return fail(h, ZZ_ERR_INVALID, "NULL argument");
   if (!h->have_data) return fail(h, ZZ_ERR_STATE, "zz_upload_data has not been called");
-  if (h->C != 1) return fail(h, ZZ_ERR_INVALID, "zz_chain_begin: one chain per handle in this round");
+  const int C = h->C;
+  for (int c = 1; c < C; ++c)
+    if (scalars[c].gen != scalars[0].gen || scalars[c].step != scalars[0].step || scalars[c].n_samples != scalars[0].n_samples)
+      return fail(h, ZZ_ERR_INVALID, "zz_chain_begin: batched chains advance in lock-step (same gen, step, n_samples)");
   if (!h->devchain) {
-    ZZ_CUDA(h, cudaMalloc(&h->devchain, sizeof(DevChain)));
-    ZZ_CUDA(h, cudaMalloc(&h->chain_stats, sizeof(double) * MAX_NSTAT));
+    ZZ_CUDA(h, cudaMalloc(&h->devchain, sizeof(DevChain) * C));
+    ZZ_CUDA(h, cudaMalloc(&h->chain_stats, sizeof(double) * MAX_NSTAT * C));
   }
-  DevChain *tmp = new (std::nothrow) DevChain();
-  if (!tmp) return fail(h, ZZ_ERR_NOMEM, "out of host memory");
-  memset(tmp, 0, sizeof *tmp);
-  tmp->pr = *priors; tmp->sc = *scalars;
-  cudaError_t e = cudaMemcpyAsync(h->devchain, tmp, sizeof(DevChain), cudaMemcpyHostToDevice, h->stream);
+  std::vector<DevChain> tmp((size_t)C);
+  memset(tmp.data(), 0, sizeof(DevChain) * C);
+  for (int c = 0; c < C; ++c) { tmp[c].pr = *priors; tmp[c].sc = scalars[c]; tmp[c].chain = c; }
+  cudaError_t e = cudaMemcpyAsync(h->devchain, tmp.data(), sizeof(DevChain) * C, cudaMemcpyHostToDevice, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  delete tmp;
   if (e != cudaSuccess) return fail(h, ZZ_ERR_CUDA, std::string("zz_chain_begin: ") + cudaGetErrorString(e));
   h->chain_gen = scalars->gen; h->chain_step = scalars->step; h->chain_samples = scalars->n_samples;
   h->chain_ready = true;
@@ -2129,35 +2139,45 @@ int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, d
   // inside the kernels that produce them, so each rank's single-thread stage sees bit-identical inputs and takes the same decisions
   const bool multi = h->comm_ready && h->comm_world > 1;
   h->stats_target = h->chain_stats; h->stats_allreduce = multi ? 1 : 0;
-  const int K = h->K, R = h->R, nblk = red_blocks(h->G);
+  const int K = h->K, R = h->R, C = h->C, nblk = red_blocks(h->G), nstat = zz_suffstats_len(h->K);
+  const bool fused_stats = (size_t)nstat * C <= (size_t)MAX_NSTAT * 8;      // else: per-chain reduction of the sweep's rows after it
+  if (!fused_stats) h->stats_target = nullptr;
   const uint64_t seed = h->cfg.seed;
   const double *no_draws[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint8_t *no_dec[4] = {nullptr, nullptr, nullptr, nullptr};
-  int rc = ZZ_OK;
+  int rc = ZZ_OK, red_stride = 2;
   auto stage = [&](int st, int iter, int do_tune_all, int sampled) {
-    k_chain_stage<<<1, 128, 0, h->stream>>>(st, iter, tune, K, R, seed, h->devchain, h->hyper, h->chain_stats, h->red_out, target, do_tune_all, sampled);
+    k_chain_stage<<<C, 128, 0, h->stream>>>(st, iter, tune, K, R, seed, h->devchain, h->hyper, h->chain_stats, h->red_out, red_stride, target, do_tune_all, sampled);
     h->launches++;
   };
-  auto reduce = [&](int op, int ny) {            // gene sum at the mailbox parameters -> red_out[ny][2], no host copy
+  auto reduce = [&](int op, int ny) {            // gene sums at the mailbox parameters -> red_out[chain][ny][2], no host copy
     RedArgs a; fill_red(h, a, 0, op);
     a.prop = h->devchain; a.partials = h->partials;
-    k_reduce<<<dim3(nblk, ny), BLOCK, 0, h->stream>>>(a);
+    red_stride = 2 * ny;
+    // batched chains: keep the whole launch near two waves of CTAs (every CTA derives its chain's constants first)
+    const int nb_r = C > 1 ? std::max(1, std::min(nblk, 2 * RED_BLOCKS / (C * ny))) : nblk;
+    k_reduce<<<dim3(nb_r, ny, C), BLOCK, 0, h->stream>>>(a);
     if (multi) {
       CommArgs cm;
       cm.rank = h->comm_rank; cm.world = h->comm_world; cm.nvec = 2 * ny; cm.epoch = ++h->comm_epoch_small;
       cm.base = (int64_t)2 * h->comm_world * 2 * zz_suffstats_len(h->K) * h->C;      // behind the statistics region
       cm.stride = 2 * COMM_SMALL_NVEC;
       for (int r = 0; r < 8; ++r) { cm.inbox[r] = h->peer_inbox[r]; cm.flags[r] = h->peer_flags[r]; }
-      k_reduce_allreduce<<<1, BLOCK, 0, h->stream>>>(h->partials, nblk, 2, ny, h->red_out, cm, h->nan_flag);
+      k_reduce_allreduce<<<1, BLOCK, 0, h->stream>>>(h->partials, nb_r, 2, ny, h->red_out, cm, h->nan_flag);
     } else {
-      k_reduce_final<<<ny, BLOCK, 0, h->stream>>>(h->partials, nblk, 2, h->red_out);
+      k_reduce_final<<<ny * C, BLOCK, 0, h->stream>>>(h->partials, nb_r, 2, h->red_out);
     }
     h->launches += 2;
   };
-  auto commit_vg = [&]() { return launch_eval(h, EVAL_COMMIT_VG, 0, nullptr, h->vgprob, &h->devchain->gate_vg); };
+  auto commit_vg = [&]() { return launch_eval(h, EVAL_COMMIT_VG, C > 1 ? -1 : 0, nullptr, h->vgprob, &h->devchain->gate_vg); };
   // gene sums of the level-2 and variance-prior moves: closed forms of the sweep statistics by default; ZZ_CHAIN_GENE_SUMS=1 (or a
   // finite variance_g_upper_bound, whose plnorm term has no closed form) keeps the reference's per-gene sums (8 extra passes)
-  const bool closed = h->hyper_host[0].variance_g_upper_bound == INFINITY && getenv("ZZ_CHAIN_GENE_SUMS") == nullptr;
+  bool closed = getenv("ZZ_CHAIN_GENE_SUMS") == nullptr;
+  for (int c = 0; c < C; ++c) if (h->hyper_host[c].variance_g_upper_bound != INFINITY) closed = false;
+  if (C > 1 && (multi || h->sink_on)) {
+    h->stats_target = saved_target; h->stats_allreduce = saved_allreduce;
+    return fail(h, ZZ_ERR_INVALID, "zz_run_generations: batched chains run on one GPU and without a sample sink in this round");
+  }
   if (!tune && h->sink_on) {                      // every sample of this call needs a parameter row
     int64_t need = 0;
     for (int i = 0; i < ngen; ++i) need += ((h->chain_gen + i) % sample_frequency == 0);
@@ -2167,12 +2187,16 @@ int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, d
     }
   }
   if (!tune && h->chain_samples == 0) {           // M:142-145: the trace starts at the current allocation
-    k_alloc_trace<<<gene_grid(h, h->G, 1), BLOCK, 0, h->stream>>>(h->G, K, h->flags, h->trace);
+    k_alloc_trace<<<gene_grid(h, h->G, C), BLOCK, 0, h->stream>>>(h->G, K, h->flags, h->trace);
     h->launches++; h->chain_samples = 1;
   }
   for (int i = 0; i < ngen && rc == ZZ_OK; ++i) {
     rc = launch_sweep_fast(h, h->chain_step, tune, ZZ_MOVE_FUSED, no_draws, no_dec, 0, h->G);   // slots 2,3,9,10,11 + statistics
     if (rc) break;
+    if (!fused_stats) {                           // many chains: the sweep left per-CTA rows, one fixed-order reduction per chain
+      k_reduce_final<<<C, BLOCK, 0, h->stream>>>(h->sw_partials, (int)h->sw_rows, nstat, h->chain_stats);
+      h->launches++;
+    }
     if (closed) {
       // every hyper move except mhP_x from the sweep's sufficient statistics: one single-thread kernel, no pass over the genes
       stage(ST_ALL_CLOSED, 0, 0, 0);
@@ -2195,27 +2219,27 @@ int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, d
     const bool commit_now = !closed || i == ngen - 1;
     if (R > 2) {                                  // Pr:213-215: XgLikelihood += ll(alpha') - ll(alpha) of the one library
       if (commit_now) {
-        k_px_commit_dev<<<gene_grid(h, h->G), BLOCK, 0, h->stream>>>(h->G, h->devchain, h->Xg, h->gl, h->Yg, h->vg, h->flags, h->hyper, h->xglik);
+        k_px_commit_dev<<<gene_grid(h, h->G, C), BLOCK, 0, h->stream>>>(h->G, h->devchain, h->Xg, h->gl, h->Yg, h->vg, h->flags, h->hyper, h->xglik);
         h->launches++;
       }
       stage(ST_END, 0, do_tune_all, sampled);
     } else {                                      // Pr:219: full recompute with the new p_x
       stage(ST_END, 0, do_tune_all, sampled);
-      if (commit_now && (rc = launch_eval(h, EVAL_XGLIK, 0, h->xglik, nullptr, &h->devchain->gate_px))) break;
+      if (commit_now && (rc = launch_eval(h, EVAL_XGLIK, C > 1 ? -1 : 0, h->xglik, nullptr, &h->devchain->gate_px))) break;
     }
     if (closed && commit_now && (rc = commit_vg())) break;   // variance_g_probability of the accepted mhTau / mhSg / mhS0Tau, once
-    k_prepare_hyper<<<1, 64, 0, h->stream>>>(1, h->hyper, h->fasth);
+    k_prepare_hyper<<<(C + 63) / 64, 64, 0, h->stream>>>(C, h->hyper, h->fasth);
     h->launches++;
     {                                             // A(y) depends on alpha_r: rebuilt only if mhP_x accepted
       FastArgs fa;
       fill_sweep_args(h, fa.s, 0, 0, 0, nullptr, nullptr, 0, h->G);
       fill_fast_args(h, fa);
-      fa.gate = &h->devchain->gate_px;
+      fa.gate = &h->devchain->gate_px; fa.gate_stride = (int)(sizeof(DevChain) / sizeof(int));
       fa.want_stats = 1;                          // also the XgLikelihood of all-zero genes, which the spike move reads (Pr:581)
-      ZZ_DISPATCH_R(h, k_refresh_lps, gene_grid(h, h->G, 1), fa);
+      ZZ_DISPATCH_R(h, k_refresh_lps, gene_grid(h, h->G, C), fa);
       h->launches++;
     }
-    if (sampled) { k_alloc_trace<<<gene_grid(h, h->G, 1), BLOCK, 0, h->stream>>>(h->G, K, h->flags, h->trace); h->launches++; h->chain_samples++; }
+    if (sampled) { k_alloc_trace<<<gene_grid(h, h->G, C), BLOCK, 0, h->stream>>>(h->G, K, h->flags, h->trace); h->launches++; h->chain_samples++; }
     if (sampled && h->sink_on) {                  // M:202-220: lnl and the log rows of this sample, written by the device
       reduce(RED_LNL, 1);
       const bool yv = h->sink_y && ((h->chain_gen / sample_frequency) % h->sink.yv_every == 0) && h->sink_yrow < h->sink.yv_capacity;
@@ -2229,7 +2253,7 @@ int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, d
                                                           yv ? h->sink_y + h->sink_yrow * (1 + nc) : nullptr, yv ? h->sink_v + h->sink_yrow * (1 + nc) : nullptr);
       h->launches++; h->sink_prow++; if (yv) h->sink_yrow++;
     }
-    if (do_tune_all) { k_tune<<<gene_grid(h, h->G), BLOCK, 0, h->stream>>>(h->G, target, h->win_y, h->win_v, h->ty, h->tv); h->launches++; }
+    if (do_tune_all) { const int64_t CG = (int64_t)C * h->G; k_tune<<<gene_grid(h, CG), BLOCK, 0, h->stream>>>(CG, target, h->win_y, h->win_v, h->ty, h->tv); h->launches++; }
     h->chain_gen += 1; h->chain_step += 10;
   }
   h->stats_target = saved_target; h->stats_allreduce = saved_allreduce;
@@ -2243,12 +2267,16 @@ int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, d
 int zz_chain_read(zz_handle *h, zz_chain_scalars *scalars, zz_hyper *hyper) {
   ZZ_CHECK(h);
   if (!h->chain_ready) return fail(h, ZZ_ERR_STATE, "zz_chain_read: call zz_chain_begin first");
-  ZZ_CUDA(h, cudaMemcpyAsync(&h->hyper_host[0], h->hyper, sizeof(zz_hyper), cudaMemcpyDeviceToHost, h->stream));
-  if (scalars) ZZ_CUDA(h, cudaMemcpyAsync(scalars, &h->devchain->sc, sizeof(zz_chain_scalars), cudaMemcpyDeviceToHost, h->stream));
+  ZZ_CUDA(h, cudaMemcpyAsync(h->hyper_host.data(), h->hyper, sizeof(zz_hyper) * h->C, cudaMemcpyDeviceToHost, h->stream));
+  if (scalars)
+    for (int c = 0; c < h->C; ++c)
+      ZZ_CUDA(h, cudaMemcpyAsync(scalars + c, &h->devchain[c].sc, sizeof(zz_chain_scalars), cudaMemcpyDeviceToHost, h->stream));
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));   // the host copy of the hyper-parameters is current again
   h->hyper_host_stale = false;
-  if (scalars) scalars->n_samples = h->chain_samples;
-  if (hyper) *hyper = h->hyper_host[0];
+  for (int c = 0; c < h->C; ++c) {
+    if (scalars) scalars[c].n_samples = h->chain_samples;
+    if (hyper) hyper[c] = h->hyper_host[c];
+  }
   return ZZ_OK;
 }
 
