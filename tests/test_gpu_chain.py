@@ -169,3 +169,64 @@ def test_batched_chains_run_device_resident_and_match_their_oracle_chains(G, C_)
         assert np.allclose(g["Yg"], o["Yg"], rtol=1e-9, atol=1e-12) and np.allclose(g["variance_g"], o["variance_g"], rtol=1e-9)
         assert np.array_equal(h.get_alloc_trace(c), ch.alloc_trace(K))
     assert hy_g[0].tau != hy_g[1].tau
+
+
+def test_device_loop_reproduces_the_golden_chain_trajectory():
+    """The committed trajectory of the fused-schedule chain (tests/golden/chain_g400.npz): started from the same constructor state,
+    zz_run_generations lands on the same hyper-parameters, tuning parameters, stream positions and allocation-trace totals."""
+    import os
+    want = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "chain_g400.npz"))
+    G, R, K = 400, 4, 2
+    X, gl, _ = synth.simulate(G, R, config_id=4242)
+    pri = O.Priors.defaults(-1.0, (1.0, 6.0))
+    ch = O.Chain(X, gl, pri, K, 31)                                      # the constructor only: initial state and stream positions
+    st, hy = ch.state_arrays(), ch.hyper
+    hg = _capi.Hyper(); C.memmove(C.byref(hg), C.byref(hy), C.sizeof(_capi.Hyper))
+    h = _capi.Handle(G, R, K, seed=31)
+    h.upload_data(X, gl); h.set_hyper(hg, 0)
+    h.set_state(0, **{k: st[k] for k in ("Yg", "variance_g", "alloc_active_inactive", "alloc_within_active", "inactive_spike_allocation",
+                                         "XgLikelihood", "variance_g_probability", "tuningParam_yg", "tuningParam_variance_g")})
+    h.reset_windows(); h.reset_alloc_trace()
+    h.chain_begin(pri, ch.scalars())
+    for tag, n, tune in (("burn", 420, True), ("samp", 30, False)):
+        h.run_generations(n, tune=tune, sample_frequency=3)
+        sc, hyg = h.chain_read()
+        got = np.array([hyg.s0, hyg.s1, hyg.tau, hyg.spike_probability, hyg.inactive_means, hyg.inactive_variances, hyg.weight_active,
+                        *hyg.alpha_r[:R], *hyg.active_means[:K], *hyg.active_variances[:K], *hyg.weight_within_active[:K]])
+        assert np.allclose(got, want[tag + "_hyper"], rtol=1e-9, atol=1e-12), tag
+        assert [sc.hyper_ctr, sc.gen, sc.step, sc.n_samples] == list(want[tag + "_ctr"]), tag
+        tun = np.array([sc.t_im, sc.t_av, sc.t_s0, sc.t_s1, sc.t_tau, sc.t_s0tau, *sc.t_am[:K], *sc.t_alpha[:R]])
+        assert np.allclose(tun, want[tag + "_tuning"], rtol=1e-9), tag
+        s = h.get_state(0)
+        chk = np.array([s["Yg"].sum(), s["variance_g"].sum(), s["alloc_active_inactive"].sum(), s["inactive_spike_allocation"].sum(),
+                        s["tuningParam_yg"].sum()])
+        assert np.allclose(chk, want[tag + "_state"], rtol=1e-9), tag
+    assert np.array_equal(h.get_alloc_trace(0).sum(axis=1), want["trace"])
+
+
+def test_device_loop_full_size_invariants():
+    """BASELINE.json's 1 M x 16 workload through the device-resident loop: counts add up, nothing non-finite, hyper-parameters stay in
+    the neighbourhood of the simulation truth they started from, the allocation trace counts every gene once per sample."""
+    X, gl, hd, st, _ = synth.make_config("1m_x16")
+    G, R = X.shape
+    hg = _capi.Hyper.make(hd["alpha_r"], hd["active_means"], hd["active_variances"], hd["weight_within_active"],
+                          **{k: float(hd[k]) for k in ("s0", "s1", "tau", "spike_probability", "inactive_means", "inactive_variances",
+                                                       "weight_active", "beta", "temperature", "variance_g_upper_bound")})
+    h = _capi.Handle(G, R, 2, seed=8)
+    h.upload_data(X, gl); h.set_hyper(hg, 0); h.set_state(0, **st); h.refresh_caches(); h.reset_alloc_trace()
+    thr_a = (1.0, 6.0)
+    h.chain_begin(_capi.Priors.defaults(-1.0, thr_a), _capi.ChainScalars.initial(hd["active_means"], thr_a, R))
+    h.run_generations(30, tune=True)
+    h.run_generations(10, tune=False, sample_frequency=2)
+    sc, hy = h.chain_read()
+    assert sc.gen == 40 and sc.n_samples == 1 + 5 and h.nan_flag() == 0
+    # 40 generations from a freshly drawn per-gene state: variance_g is still equilibrating, so (s0, tau) are on their transient;
+    # the allocation-level parameters, which 1 M genes pin tightly, are already at the simulation truth
+    assert 0.3 < hy.tau < 1.5 and abs(hy.s0 - hd["s0"]) < 1.0 and abs(hy.weight_active - hd["weight_active"]) < 0.02
+    assert abs(hy.spike_probability - hd["spike_probability"]) < 0.02 and np.allclose(hy.alpha_r[:R], hd["alpha_r"], rtol=0.2)
+    s = h.get_state(0)
+    assert np.isfinite(s["Yg"]).all() and (s["variance_g"] > 0).all()
+    tr = h.get_alloc_trace(0)
+    assert tr.sum() == 6 * G and np.array_equal(tr.sum(axis=0), np.full(G, 6))
+    st_ = h.suffstats()[0]
+    assert st_[:3].sum() == G

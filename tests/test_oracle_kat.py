@@ -179,3 +179,19 @@ def test_post_predictive_restatement_sanity():
     assert np.abs(ws[:, 0]).max() < 0.5 and np.abs(ws[:, 1]).max() < 0.5 and np.abs(ws[:, 2]).max() < 0.05
     bad = O.Hyper.make(np.asarray(hd["alpha_r"]) / 20, hd["active_means"], hd["active_variances"], hd["weight_within_active"], **kw)
     assert O.post_predictive(bad, s, 9, 1, bins)["B"] > 10 * np.abs(ws[:, 2]).max()
+
+
+def test_oracle_fused_chain_matches_its_golden_trajectory():
+    """tests/golden/chain_g400.npz (make_golden_chain.py): hyper-parameters, scalar tuning, stream positions and state checksums of
+    the oracle's fused-schedule chain after 420 burn-in (one tune_all) + 30 sampling generations."""
+    import importlib.util, os
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_chain", os.path.join(here, "golden", "make_golden_chain.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    got, want = mod.run(), np.load(os.path.join(here, "golden", "chain_g400.npz"))
+    for k in want.files:
+        if want[k].dtype.kind == "i":
+            assert np.array_equal(got[k], want[k]), k
+        else:
+            assert np.allclose(got[k], want[k], rtol=1e-9, atol=1e-12), k
