@@ -8,6 +8,7 @@
 // segment can be replayed on the CPU decision for decision (tests/test_gpu_chain.py).
 #pragma once
 #include "zz_device.cuh"
+#include "zz_fast.cuh"
 
 namespace zz {
 
@@ -19,7 +20,7 @@ struct DevChain {
   // mailbox read by the gene-sum kernels
   L2Params l2[2];                 // RED_LEVEL2 with grid.y = 2: [0] proposed, [1] current parameters (Pr:444-447, 653-654, 780-784)
   double p_s0, p_s1, p_tau;       // RED_VARG_HYPER proposal (Pr:84-87, 126-130, 167-170)
-  double p_alpha; int p_lib;      // RED_PXDELTA proposal (Pr:209-224)
+  double p_alpha, p_alpha_old; int p_lib, pad0_;   // RED_PXDELTA proposal (Pr:209-224); the replaced alpha_r for the XgLikelihood commit
   int gate_vg, gate_px, pad_;     // accepted mhTau/mhSg/mhS0Tau -> commit variance_g_probability; accepted mhP_x -> commit XgLikelihood
   // the pending move, between its "propose" and its "decide" stage
   double HR, pp, pc, difp, prop0, prop1;
@@ -234,8 +235,8 @@ __device__ inline void propose_px(DevChain &c, const zz_hyper &h, uint64_t seed,
 __device__ inline void decide_px(DevChain &c, zz_hyper &h, uint64_t seed, const double *red, int tune) {
   const double Rr = h.temperature * (red[0] + c.pp - c.pc) + c.HR;
   c.gate_px = 0;
+  c.p_alpha_old = h.alpha_r[c.p_lib];                   // k_px_commit_dev evaluates ll(alpha') - ll(alpha) from the mailbox (Pr:213-215)
   if (log(c_unif(c, seed)) < Rr && Rr != INFINITY) { c.gate_px = 1; if (tune) c.sc.w_alpha[c.p_lib][99] = 1; }
-  // alpha_r[lib] itself is replaced by k_chain_stage(ST_END), after the XgLikelihood commit has used the old value (Pr:213-215)
 }
 __device__ inline void tune_all_scalars(DevChain &c, double target, int K, int R) {   // U:183-240, scalar part
   zz_chain_scalars &s = c.sc;
@@ -305,7 +306,8 @@ enum ChainStage {
 };
 
 __global__ void k_chain_stage(int stage, int iter, int tune, int K, int R, uint64_t seed, DevChain *cp_all, zz_hyper *hp_all,
-                              const double *stats_all, const double *red_all, int red_stride, double target, int do_tune_all, int sampled) {
+                              const double *stats_all, const double *red_all, int red_stride, double target, int do_tune_all, int sampled,
+                              FastH *fasth_all) {
   // one block per chain of the handle (batched chains run their scalar stages side by side)
   DevChain *cp = cp_all + blockIdx.x; zz_hyper *hp = hp_all + blockIdx.x;
   const double *stats_g = stats_all + (size_t)blockIdx.x * (3 * (K + 1) + 10), *red = red_all + (size_t)blockIdx.x * red_stride;
@@ -347,7 +349,15 @@ __global__ void k_chain_stage(int stage, int iter, int tune, int K, int R, uint6
     case ST_SG: decide_tau(c, h, seed, red, tune); propose_sg(c, h, seed, tune); break;
     case ST_S0TAU: decide_sg(c, h, seed, red, tune); propose_s0tau(c, h, seed, tune); break;
     case ST_PX: decide_s0tau(c, h, seed, red, tune); propose_px(c, h, seed, tune, R); break;
-    case ST_PX_DECIDE: decide_px(c, h, seed, red, tune); break;
+    case ST_PX_DECIDE:                                   // ... and the end of the generation in the same launch
+      decide_px(c, h, seed, red, tune);
+      if (c.gate_px) h.alpha_r[c.p_lib] = c.p_alpha;
+      c.sc.step += 10;                                   // the sweep and nine hyper slots, one `step` each
+      c.sc.gen += 1;
+      if (sampled) c.sc.n_samples += 1;
+      if (do_tune_all) tune_all_scalars(c, target, K, R);
+      derive_fast(fasth_all[blockIdx.x], &h);            // the sweep kernels' derived constants (k_prepare_hyper, fused here)
+      break;
     case ST_ALL_CLOSED: {
       double r[4];
       mv_mixture_weights(c, h, seed, stats, K);

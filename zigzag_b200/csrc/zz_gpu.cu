@@ -924,7 +924,7 @@ __global__ void __launch_bounds__(BLOCK) k_px_commit_dev(int64_t G, const DevCha
   const uint32_t f = flags[g];
   const double x = Xg[(int64_t)lib * G + g];
   xglik[g] = xglik[g] + xg_lik_onelib(H, x, Yg[g], vg[g], gl[g], c->p_alpha, f & F_INSPIKE, f & F_ALLZERO) -
-             xg_lik_onelib(H, x, Yg[g], vg[g], gl[g], H.alpha[lib], f & F_INSPIKE, f & F_ALLZERO);
+             xg_lik_onelib(H, x, Yg[g], vg[g], gl[g], c->p_alpha_old, f & F_INSPIKE, f & F_ALLZERO);
 }
 
 // one sample: the _model_parameters.log row (thread 0) and, when due, the candidate genes' Yg / variance_g rows, written straight
@@ -2147,7 +2147,7 @@ int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, d
   uint8_t *no_dec[4] = {nullptr, nullptr, nullptr, nullptr};
   int rc = ZZ_OK, red_stride = 2;
   auto stage = [&](int st, int iter, int do_tune_all, int sampled) {
-    k_chain_stage<<<C, 128, 0, h->stream>>>(st, iter, tune, K, R, seed, h->devchain, h->hyper, h->chain_stats, h->red_out, red_stride, target, do_tune_all, sampled);
+    k_chain_stage<<<C, 128, 0, h->stream>>>(st, iter, tune, K, R, seed, h->devchain, h->hyper, h->chain_stats, h->red_out, red_stride, target, do_tune_all, sampled, h->fasth);
     h->launches++;
   };
   auto reduce = [&](int op, int ny) {            // gene sums at the mailbox parameters -> red_out[chain][ny][2], no host copy
@@ -2210,26 +2210,20 @@ int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, d
       stage(ST_S0TAU, 0, 0, 0); if ((rc = commit_vg())) break; reduce(RED_VARG_HYPER, 1);
       stage(ST_PX, 0, 0, 0); if ((rc = commit_vg())) break; reduce(RED_PXDELTA, 1);
     }
-    stage(ST_PX_DECIDE, 0, 0, 0);
     const int sampled = (!tune && h->chain_gen % sample_frequency == 0) ? 1 : 0;
     const int do_tune_all = (tune && (h->chain_gen + 1) % 400 == 0) ? 1 : 0;                    // B:146
+    stage(ST_PX_DECIDE, 0, do_tune_all, sampled);   // decide mhP_x, install alpha_r, counters, tune_all scalars, derived constants (FastH)
     // The two per-gene caches of the reference are rewritten by the next sweep for every out-of-spike gene (and A(y) / the all-zero
     // genes by the gated k_refresh_lps below), and the closed-form moves never read them: with closed forms their commits
     // (Pr:113/147/187, Pr:213-215/219) are only needed after the LAST generation of the call, when the state becomes visible.
     const bool commit_now = !closed || i == ngen - 1;
-    if (R > 2) {                                  // Pr:213-215: XgLikelihood += ll(alpha') - ll(alpha) of the one library
-      if (commit_now) {
+    if (commit_now) {
+      if (R > 2) {                                // Pr:213-215: XgLikelihood += ll(alpha') - ll(alpha) of the one library (both alphas in the mailbox)
         k_px_commit_dev<<<gene_grid(h, h->G, C), BLOCK, 0, h->stream>>>(h->G, h->devchain, h->Xg, h->gl, h->Yg, h->vg, h->flags, h->hyper, h->xglik);
         h->launches++;
-      }
-      stage(ST_END, 0, do_tune_all, sampled);
-    } else {                                      // Pr:219: full recompute with the new p_x
-      stage(ST_END, 0, do_tune_all, sampled);
-      if (commit_now && (rc = launch_eval(h, EVAL_XGLIK, C > 1 ? -1 : 0, h->xglik, nullptr, &h->devchain->gate_px))) break;
+      } else if ((rc = launch_eval(h, EVAL_XGLIK, C > 1 ? -1 : 0, h->xglik, nullptr, &h->devchain->gate_px))) break;   // Pr:219: full recompute
     }
     if (closed && commit_now && (rc = commit_vg())) break;   // variance_g_probability of the accepted mhTau / mhSg / mhS0Tau, once
-    k_prepare_hyper<<<(C + 63) / 64, 64, 0, h->stream>>>(C, h->hyper, h->fasth);
-    h->launches++;
     {                                             // A(y) depends on alpha_r: rebuilt only if mhP_x accepted
       FastArgs fa;
       fill_sweep_args(h, fa.s, 0, 0, 0, nullptr, nullptr, 0, h->G);
