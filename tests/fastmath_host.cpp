@@ -52,24 +52,31 @@ int main(int argc, char **argv) {
   for (double v : a) bad += fabs((1 - fexp_neg_clamped(v, T.exp_t)) - (1 - exp(-v))) > 3e-16;
   for (double v : a) bad += fabs((1 - fexp2_neg_clamped(v * ZZ_KLOG2E, T.exp_t)) - (1 - exp(-v))) > 3e-16;
   printf("px_mismatch %d\n", bad);
-  {  // det_term (straight-line tile) against the per-library path it replaces: log(q), q = undetected ? 1 - p : p
-    double worst = 0; int zero_bad = 0;
-    for (long it = 0; it < n / 4; ++it) {
-      const double alpha = 0.05 + U(g) * 3, a2 = alpha * ZZ_KLOG2E;
-      double t = (it % 5 == 0) ? U(g) * 1e-6 : (it % 5 == 1) ? U(g) * 900 : U(g) * 30;
-      if (t * a2 > 1010) t = 1010 / a2;
-      const unsigned nd = it & 1;
-      const double e = fexp2_neg_clamped(t * a2, T.exp_t), p = 1 - e, q = nd ? 1 - p : p;
-      double fs = 0; int ks = -1023;
-      det_term(t, -256.0 * a2, nd, T, fs, ks);
-      const double got = fma((double)ks, ZZ_KLN2, fs);
-      if (q == 0) { zero_bad += !(got < -700); continue; }
-      const double want = flog_core(q, T.log_t);
-      // the two exponent roundings differ by <= 1 ulp of e, i.e. <= 2^-53 absolute on q
-      const double tol = 1e-15 * fabs(want) + 2.3e-16 / q + 1e-300;
-      const double err = fabs(got - want) / tol; if (err > worst) worst = err;
+  {  // det_q / det_log_product (straight-line tile) against the per-library path it replaces: sum_r log(q_r), q = undetected ? 1 - p : p
+    double worst = 0, worst_q = 0; int zero_bad = 0;
+    for (long it = 0; it < n / 16; ++it) {
+      const int R = 2 + (int)(U(g) * 17);                  // 2..18 libraries
+      double t = (it % 5 == 0) ? U(g) * 1e-6 : (it % 5 == 1) ? U(g) * 40 : U(g) * 3;
+      long double want = 0; double P = 1; bool zero = false;
+      for (int r = 0; r < R; ++r) {
+        const double alpha = 0.5 + U(g) * 3, a2 = alpha * ZZ_KLOG2E;
+        const unsigned nd = (U(g) < 0.2);
+        const double tt = t * a2 > 1010 ? 1010 / a2 : t;
+        const double e = fexp2_neg_clamped(tt * a2, T.exp_t), p = 1 - e, qref = nd ? 1 - p : p;
+        const double q = det_q(tt, -256.0 * a2, nd, T);
+        // the two exponent roundings differ by <= 1 ulp of e, i.e. <= 2^-53 absolute on q
+        const double dq = fabs(q - qref) / 1.2e-16; if (dq > worst_q) worst_q = dq;
+        if (q == 0) zero = true; else want += logl((long double)q);
+        P *= q;
+      }
+      const double got = det_log_product(P, T.log_t);
+      if (zero) { zero_bad += !(got == -INFINITY); continue; }
+      zero_bad += !(got > -INFINITY);
+      // R roundings of the product (2^-53 relative each) + the logarithm's own 2 ulp
+      const double tol = (R + 1) * 1.2e-16 + 3e-16 * fabsl(want);
+      const double err = (double)fabsl((long double)got - want) / tol; if (err > worst) worst = err;
     }
-    printf("det_term_worst %.4f\ndet_term_zero_bad %d\n", worst, zero_bad);
+    printf("det_product_worst %.4f\ndet_q_worst %.4f\ndet_product_zero_bad %d\n", worst, worst_q, zero_bad);
   }
   return 0;
 }

@@ -17,8 +17,9 @@ def test_fast_exp_log_within_two_ulp(tmp_path):
     assert float(out["log_max_abs_near_one"]) < 2e-17  # no cancellation blow-up around x = 1
     assert float(out["exp2_max_ulp"]) < 2.5           # base-2 detection exponential
     assert float(out["px_max_abs_err"]) < 2.3e-16      # 1 - 2^-b vs 1 - exp(-a): within one ulp of 1
-    assert float(out["det_term_worst"]) < 1.0          # straight-line detection term == per-library exp2 + log path
-    assert int(out["det_term_zero_bad"]) == 0          # q == 0 is still recognisable from the sum
+    assert float(out["det_product_worst"]) < 1.0       # log of the product of the detection factors == sum of the per-library logs
+    assert float(out["det_q_worst"]) <= 2.0            # each factor within 2^-52 of the per-library exp2 path (1 ulp of e, re-rounded by 1 - p)
+    assert int(out["det_product_zero_bad"]) == 0       # a zero factor gives exactly -Inf, nothing else does
     assert float(out["log1"]) == 0.0
     assert out["log0"].strip() == "-inf" and "nan" in out["logneg"] and out["loginf"].strip() == "inf"
     a, b = map(float, out["logsub"].split())

@@ -117,23 +117,22 @@ __device__ __forceinline__ double sqdist(const GeneData &d, double y) {   // D(y
   return fma((double)d.ndet * t, t, d.ss);
 }
 
-// A(y) through det_term: exponent parts summed as integers, the undetected complement as a
-// predicated subtraction, one clamp of t instead of one per library.  Requires max alpha <= 16 min alpha (checked by the
-// host before this kernel is chosen): then t_clamp * alpha2_r >= 1010/16 > 54 for every r, so a clamped t yields p_x == 1
-// exactly where the unclamped one does.
+// A(y) through det_q: the factors q_r of all libraries are multiplied (four independent partial products, so the per-library
+// chains overlap) and ONE logarithm is taken; one clamp of t instead of one per library.  Requires max alpha <= 16 min alpha
+// (checked by the host before this kernel is chosen): then t_clamp * alpha2_r >= 1010/16 > 54 for every r, so a clamped t
+// yields p_x == 1 exactly where the unclamped one does.
 template <int RT>
 __device__ __forceinline__ double detect_logsum_sl(const FastH &H, const MathTabs &T, uint64_t nd_mask, double t) {
-  static_assert(RT > 0 && RT <= 18, "the zero test below needs <= 18 terms");
+  static_assert(RT > 0 && RT <= 18, "the product of the factors must stay a normal number");
   const double tc = fmin(t, H.t_clamp);                                 // +Inf clamps too
   const uint32_t mlo = (uint32_t)nd_mask;
-  const int one_hi = opaque_one_hi(&H.one_hi);
-  double fsum = 0; int ksum = -1023 * RT;
-  // (statement-level interleaving of several libraries was measured: no gain — at 24 warps/SM the FP64 pipe, the shared-memory
-  // data pipe and the issue slots are all 50-65 % busy, profiles/r1_summary.md)
+  double P[4] = {1.0, 1.0, 1.0, 1.0};
 #pragma unroll
-  for (int r = 0; r < RT; ++r) det_term(tc, H.am256[r], mlo & (1u << r), T, fsum, ksum, one_hi);
-  const double A = fma((double)ksum, ZZ_KLN2, fsum);
-  return A < -700.0 ? -INFINITY : A;
+  for (int r = 0; r < RT; ++r) {
+    const double q = det_q(tc, H.am256[r], mlo & (1u << r), T);
+    P[r & 3] = (r < 4) ? q : P[r & 3] * q;
+  }
+  return det_log_product((P[0] * P[1]) * (P[2] * P[3]), T.log_t);
 }
 
 // A(y) = sum_r log(nd_r ? 1 - p_r : p_r),  p_r = 1 - exp(-t alpha_r),  t = gl * exp(y)     (U:157, P:82-84)
@@ -142,7 +141,7 @@ __device__ __forceinline__ double detect_logsum(const FastH &H, const MathTabs &
   const int R = RT > 0 ? RT : H.R;
   double A = 0;
   // every path that produces A(y) for the same hyper-parameters must use the same arithmetic (the value is cached in `lps`
-  // and compared bit for bit across kernels): det_term whenever it is applicable
+  // and compared bit for bit across kernels): the product form whenever it is applicable
   if constexpr (RT > 0 && RT <= 18) { if (H.uclamp_ok) return detect_logsum_sl<RT>(H, T, nd_mask, t); }
   if (RT > 0 && RT <= 18) {
     // q is +0 or a normal number in [2^-53, 1].  flog_core(+0) returns -1023 ln 2 = -709.1 instead of -Inf, while a sum of

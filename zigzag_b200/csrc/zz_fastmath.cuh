@@ -161,17 +161,17 @@ ZZ_HD double flog_core(double x, const double2 *__restrict__ log_t) {
 __device__ __forceinline__ int opaque_one_hi(const volatile int *slot) { return *slot; }
 #endif
 
-// One library's detection term for the straight-line tile:  log(q),  q = undetected ? 1 - p : p,  p = 1 - 2^(-t a),
+// One library's detection factor for the straight-line tile:  q = undetected ? 1 - p : p,  p = 1 - 2^(-t a),
 // a = alpha_r log2(e), passed as am256 = -256 a.  The caller clamps t so that t a <= 1010 for every library (then 2^(-t a)
-// is a normal number; beyond 54 the value no longer matters because p rounds to 1).  Returns nothing: the term is
-// delivered as  log q = (kraw - 1023) ln 2 + frac  with `kraw` ADDED to the integer `ksum` and `frac` to the double `fsum`,
-// so the exponent parts of all libraries are summed as integers and converted once (saves an I2F and an fma per library).
-// q = +0 (log = -Inf) leaves kraw = 0 and frac = 0: the sum then lies below -709 + (R-1)*0, which no legitimate sum of
-// <= 18 terms (each >= log 2^-53) can reach — the caller tests that instead of every q.
-// 18 FP64 instructions, ~11 integer/select, 2 shared-memory reads.
-// `one_hi` must be 0x3FF00000; callers on the device pass it in a register (opaque_one_hi) so that the mantissa re-bias is one
-// LOP3 (and-immediate, or-register) instead of two.
-ZZ_HD void det_term(double t, double am256, unsigned undetected, const MathTabs &T, double &fsum, int &ksum, int one_hi = 0x3FF00000) {
+// is a normal number; beyond 54 the value no longer matters because p rounds to 1).  q is +0 or a multiple of 2^-53 in
+// [2^-53, 1].  The caller multiplies the factors of all libraries and takes ONE logarithm of the product:
+//   A(y) = sum_r log q_r = log prod_r q_r.
+// With <= 18 libraries the product of non-zero factors is >= 2^-954, still a normal number, and each multiplication adds
+// <= 2^-53 relative error to the product, i.e. <= 1.1e-16 absolute error to A — the size of the rounding of a single
+// log q_r in the per-library form (the reference's own log(1 - p_x) carries the same absolute error through 1 - p_x).
+// 10 FP64 instructions, ~6 integer/select, 1 shared-memory read per library (the per-library logarithm cost 8 more FP64,
+// ~6 integer and a second table read).
+ZZ_HD double det_q(double t, double am256, unsigned undetected, const MathTabs &T) {
   const double magic = 6755399441055744.0;
   const double w = fma(t, am256, magic);               // low word: n = rint(-256 t a)
   const int n = d_lo(w);
@@ -184,16 +184,13 @@ ZZ_HD void det_term(double t, double am256, unsigned undetected, const MathTabs 
   const double e = scale_tab(T.exp_t, n) * p;          // 2^(-t a)
   double q = 1.0 - e;                                  // p_x (U:157)
   if (undetected) q = 1.0 - q;                         // 1 - p_x as the reference forms it (P:84), not e itself
-  const int hi = d_hi(q);
-  ksum += (hi + 0x00096000) >> 20;
-  const double m = d_make((hi & 0x000FFFFF) | one_hi, d_lo(q));
-  const double2 tc = T.log_t[(hi >> 11) & 511];
-  const double x = fma(m, tc.x, -1.0);
-  const double x2 = x * x;
-  double s = fma(x, ZZ_L5_IMM, -0.25);
-  s = fma(x, s, 1.0 / 3);
-  s = fma(x, s, -0.5);
-  fsum += tc.y + fma(x2, s, x);
+  return q;
+}
+
+// log of a product of det_q factors: -Inf when some factor was +0 (the product of <= 18 non-zero factors is >= 2^-954)
+ZZ_HD double det_log_product(double P, const double2 *__restrict__ log_t) {
+  const double l = flog_core(P, log_t);
+  return (d_hi(P) < 0x00100000) ? -INFINITY : l;       // P == +0 (or subnormal, which no legitimate product is)
 }
 
 ZZ_HD double flog(double x, const double2 *__restrict__ log_t) {

@@ -1292,6 +1292,9 @@ void launch_pdl(Kern kern, dim3 grid, size_t smem, cudaStream_t st, const FastAr
   cudaLaunchKernelEx(&cfg, kern, fa);
 }
 
+#ifdef ZZ_DEV_R16   /* kernel-tuning builds (tools/): only the R = 16 instantiations, a fifth of the compile time */
+#define ZZ_SWEEP_CASE_R(h, PRODV, KTV, grid, smem, args) launch_pdl(k_sweep_fast<16, PRODV, KTV>, grid, smem, (h)->stream, args);
+#else
 #define ZZ_SWEEP_CASE_R(h, PRODV, KTV, grid, smem, args)                                         \
   switch ((h)->R) {                                                                              \
     case 2: launch_pdl(k_sweep_fast<2, PRODV, KTV>, grid, smem, (h)->stream, args); break;   \
@@ -1300,6 +1303,7 @@ void launch_pdl(Kern kern, dim3 grid, size_t smem, cudaStream_t st, const FastAr
     case 16: launch_pdl(k_sweep_fast<16, PRODV, KTV>, grid, smem, (h)->stream, args); break; \
     default: launch_pdl(k_sweep_fast<0, PRODV, KTV>, grid, smem, (h)->stream, args); break;  \
   }
+#endif
 // kt: 0 = generic tile (explicit draws / decisions / move subsets / finite variance bound / K > 3), 1..3 = straight-line tile
 #define ZZ_DISPATCH_SWEEP(h, prod, kt, grid, smem, args)                                         \
   do {                                                                                           \
