@@ -225,6 +225,12 @@ int zz_chain_begin(zz_handle *h, const zz_priors *priors, const zz_chain_scalars
 /* ngen generations; tune != 0: burn-in (acceptance windows, tune_all every 400 generations with `target`, U:183-240);
    tune == 0: sampling, allocation_trace accumulated whenever gen % sample_frequency == 0 (M:188-199).  Asynchronous. */
 int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, double target);
+/* `nsweeps` fused sweeps with the hyper-parameters held fixed, steps step, step + 1, ..., in ONE cooperative launch of the
+   device-resident kernel (no hyper-parameter moves; zz_chain_begin is not needed).  After every sweep the sufficient statistics
+   — all-reduced over the ranks once zz_comm_connect is done — are left in the buffer of zz_set_stats_output_dev, if any
+   (zz_suffstats layout, except that entries 3(K+1)+7 and +8, the sums of the two likelihood caches, are 0 here).  Asynchronous. */
+int zz_run_sweeps(zz_handle *h, uint64_t step, int nsweeps, int tune);
+int zz_debug_gen_times(zz_handle *h, double *out2);   /* diagnostic: ns the releasing CTA spent in the last device-resident launch {ticket -> release, scalar stage} */
 /* waits for the device, returns the scalar state and the hyper-parameters of every chain ([num_chains] each; either may be NULL) */
 int zz_chain_read(zz_handle *h, zz_chain_scalars *scalars, zz_hyper *hyper);
 

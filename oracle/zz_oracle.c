@@ -557,11 +557,25 @@ struct zzo_chain {
   uint32_t *alloc_trace; /* [K+1][G] */
   int64_t n_samples;
   double *draws; /* [9][G] draw table of the current step */
+  /* hyper-level draws of the fused schedule: one counter-based sub-stream per move (see sub_begin) */
+  int sub_on; uint32_t sub_slot, sub_blk; int sub_pos; double sub_buf[4]; uint64_t sub_step;
 };
+
+/* Sub-streams of the fused schedule (zzo_chain_run_fused == the device-resident loop zz_run_generations): the scalar draws of
+   hyper move `slot` in a generation are the uniforms of the Philox blocks (gene index 0xFFFFFF00 + slot, blk = 0, 1, 2, ...,
+   step = the step of that generation's per-gene sweep), consumed in order.  Counter-based, so every move's draws are independent
+   of how many uniforms any other move consumed: the device evaluates independent moves side by side (zz_chain.cuh). */
+enum { SUB_MIXW = 0x00 /* + component 0..K */, SUB_SP0 = 0x10, SUB_SP1 = 0x11, SUB_IM = 0x20, SUB_AMD = 0x21, SUB_SV = 0x22,
+       SUB_TAU = 0x23, SUB_SG = 0x24, SUB_S0TAU = 0x25, SUB_PX = 0x26 };
+static void sub_begin(zzo_chain *c, uint32_t slot) { c->sub_slot = slot; c->sub_blk = 0; c->sub_pos = 4; }
 
 /* hyper-level draws: a private Philox stream (gene index 0xFFFFFFFF, blk 255) */
 static double c_unif(zzo_chain *c) {
   double o[4];
+  if (c->sub_on) {
+    if (c->sub_pos == 4) { zzo_uniform4(c->seed, c->chain_index, c->sub_step, c->sub_blk++ & 255u, 0xFFFFFF00ull + c->sub_slot, c->sub_buf); c->sub_pos = 0; }
+    return c->sub_buf[c->sub_pos++];
+  }
   if ((c->hyper_ctr & 3) == 0) { zzo_uniform4(c->seed, c->chain_index, c->hyper_ctr >> 2, 255, 0xFFFFFFFFull, o); memcpy(c->hyper_buf, o, sizeof o); }
   return c->hyper_buf[c->hyper_ctr++ & 3];
 }
@@ -577,6 +591,23 @@ static double c_gamma(zzo_chain *c, double shape, double rate) { /* Marsaglia & 
     if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return d * v / rate;
   }
 }
+/* the same sampler on a sub-stream of its own: attempt j uses block j of `slot` (w0, w1 -> normal, w2 -> accept), the boost
+   uniform of shape < 1 is w3 of block 0 */
+static double c_gamma_slot(zzo_chain *c, uint32_t slot, double shape, double rate) {
+  double a[4], n[2], boost = 1;
+  if (shape < 1) { zzo_uniform4(c->seed, c->chain_index, c->sub_step, 0, 0xFFFFFF00ull + slot, a); boost = pow(a[3], 1.0 / shape); shape += 1; }
+  double d = shape - 1.0 / 3, cc = 1 / sqrt(9 * d);
+  for (uint32_t j = 0; j < 255; ++j) {
+    zzo_uniform4(c->seed, c->chain_index, c->sub_step, j, 0xFFFFFF00ull + slot, a);
+    zzo_box_muller(a[0], a[1], n);
+    double x = n[0], v = 1 + cc * x;
+    if (v <= 0) continue;
+    v = v * v * v;
+    if (log(a[2]) < 0.5 * x * x + d - d * v + d * log(v)) return d * v / rate * boost;
+  }
+  return d / rate * boost;
+}
+static double c_gamma_at(zzo_chain *c, uint32_t slot, double shape, double rate) { return c->sub_on ? c_gamma_slot(c, slot, shape, rate) : c_gamma(c, shape, rate); }
 static double c_beta(zzo_chain *c, double a, double b) { double x = c_gamma(c, a, 1), y = c_gamma(c, b, 1); return x / (x + y); }
 static int c_sample_w(zzo_chain *c, const double *w, int n) { /* sample(n, 1, prob = w) */
   double tot = 0; for (int i = 0; i < n; ++i) tot += w[i];
@@ -636,7 +667,7 @@ static void mv_gibbsMixtureWeights(zzo_chain *c) { /* Pr:412-431 */
   for (int64_t g = 0; g < c->G; ++g) cnt[c->s.alloc_active_inactive[g] ? c->s.alloc_within_active[g] : 0] += 1;
   for (int k = 0; k <= K; ++k) {
     double a = (k == 0 ? c->pr.weight_active_shape_2 : c->pr.weight_active_shape_1 / K) + cnt[k] * c->h.beta;
-    g_[k] = c_gamma(c, a, 1); tot += g_[k];
+    g_[k] = c_gamma_at(c, SUB_MIXW + k, a, 1); tot += g_[k];
   }
   double nw0 = g_[0] / tot;
   if (!isnan(nw0)) {
@@ -703,7 +734,8 @@ static void mv_mhSharedVariance(zzo_chain *c, int tune) { /* Pr:768-803 */
 static void mv_gibbsSpikeProb(zzo_chain *c) { /* Pr:511-526 */
   double nin = 0, ninact = 0;
   for (int64_t g = 0; g < c->G; ++g) { nin += c->s.inactive_spike_allocation[g]; ninact += (c->s.alloc_active_inactive[g] == 0); }
-  double ns = c_beta(c, nin + c->pr.spike_prior_shape_1, (ninact - nin) + c->pr.spike_prior_shape_2);
+  double gx = c_gamma_at(c, SUB_SP0, nin + c->pr.spike_prior_shape_1, 1), gy = c_gamma_at(c, SUB_SP1, (ninact - nin) + c->pr.spike_prior_shape_2, 1);
+  double ns = gx / (gx + gy);                                        /* rbeta as a ratio of gammas, as c_beta */
   if (!isnan(ns)) c->h.spike_probability = ns;
 }
 static void mv_mhSpikeAllocation(zzo_chain *c) {
@@ -940,9 +972,12 @@ void zzo_chain_run_fused(zzo_chain *c, int ngen, int sample_frequency, int tune,
   for (int i = 0; i < ngen; ++i) {
     zzo_sweep_draws(c->seed, c->chain_index, c->step, 0, c->G, draws);
     zzo_sweep(&c->h, &c->s, draws, tune, NULL);
+    c->sub_step = c->step; c->sub_on = 1;                          /* hyper draws: sub-streams of this generation's sweep step */
     c->step++;
     static const int hyper_slots[] = {1, 4, 6, 7, 8, 12, 13, 14, 15};
-    for (unsigned j = 0; j < sizeof hyper_slots / sizeof hyper_slots[0]; ++j) run_slot(c, hyper_slots[j], tune);
+    static const uint32_t sub_of[] = {SUB_MIXW, SUB_IM, SUB_AMD, SUB_SV, SUB_SP0, SUB_TAU, SUB_SG, SUB_S0TAU, SUB_PX};
+    for (unsigned j = 0; j < sizeof hyper_slots / sizeof hyper_slots[0]; ++j) { sub_begin(c, sub_of[j]); run_slot(c, hyper_slots[j], tune); }
+    c->sub_on = 0;
     if (!tune && c->gen % sample_frequency == 0) accumulate_trace(c);
     c->gen++;
     if (tune && c->gen % 400 == 0) tune_all(c, target);

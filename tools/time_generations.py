@@ -28,6 +28,11 @@ for tune in (True, False):
     dt = (time.perf_counter() - t0) / ngen
     print(f"{name}: device-resident {'burn-in' if tune else 'sampling'} generation {dt*1e6:.1f} us "
           f"({(h.launch_count-l0)/ngen:.1f} launches, {chains} chain(s)) -> {1/dt:.0f} generations/s, {G*chains/dt/1e9:.2f} G gene-updates/s inside full chains")
+    tl = h.debug_gen_times() / (ngen if tune else 10) / 1e3
+    print(f"   last segment: releasing CTA {tl[0]:.1f} us per generation between its ticket and the release, {tl[1]:.1f} us of it in the scalar stage")
+h.run_sweeps(10**6, 20); h.sync()
+t0 = time.perf_counter(); h.run_sweeps(10**6 + 20, ngen); h.sync(); dt = (time.perf_counter() - t0) / ngen
+print(f"{name}: zz_run_sweeps (fixed hyper-parameters, statistics every sweep) {dt*1e6:.1f} us per sweep -> {G*chains/dt/1e9:.2f} G gene-updates/s; releasing CTA {h.debug_gen_times()[0]/ngen/1e3:.1f} us")
 sc, hy = h.chain_read()
 if chains > 1: sc, hy = sc[0], hy[0]
 print("   after", sc.gen, "generations: tau %.4f s0 %.4f s1 %.4f w_active %.4f spike %.4f alpha[0] %.3f" % (hy.tau, hy.s0, hy.s1, hy.weight_active, hy.spike_probability, hy.alpha_r[0]))

@@ -165,6 +165,8 @@ _SIG = {
     "zz_sweep_host": (C.c_int, [_P, C.c_uint64, C.c_int] + [_P] * 11),
     "zz_chain_begin": (C.c_int, [_P, _P, _P]),
     "zz_run_generations": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "zz_run_sweeps": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int]),
+    "zz_debug_gen_times": (C.c_int, [_P, _P]),
     "zz_chain_read": (C.c_int, [_P, _P, _P]),
     "zz_param_row_len": (C.c_int, [C.c_int, C.c_int]),
     "zz_pinned_alloc": (C.c_void_p, [C.c_size_t]),
@@ -454,6 +456,15 @@ class Handle:
 
     def run_generations(self, ngen, tune=False, sample_frequency=1, target=0.44):
         self._ck(self.L.zz_run_generations(self.h, int(ngen), int(tune), int(sample_frequency), float(target)))
+
+    def run_sweeps(self, step, nsweeps, tune=False):
+        """`nsweeps` fused sweeps with fixed hyper-parameters in one cooperative launch (statistics after every sweep)."""
+        self._ck(self.L.zz_run_sweeps(self.h, int(step), int(nsweeps), int(tune)))
+
+    def debug_gen_times(self):
+        out = np.zeros(2)
+        self._ck(self.L.zz_debug_gen_times(self.h, _ptr(out)))
+        return out
 
     def chain_read(self):
         """(scalars, hyper) of chain 0 for a one-chain handle, else two lists with one entry per chain."""

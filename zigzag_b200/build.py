@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", "zz_gpu.cu")]
 DEPS = [os.path.join(HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(HERE, "csrc")))] + \
        [os.path.join(HERE, "..", "include", "zigzag_gpu.h")]
-OUT = os.path.join(HERE, "libzigzag_gpu.so")
+OUT = os.environ.get("ZZ_BUILD_OUT", os.path.join(HERE, "libzigzag_gpu.so"))   # kernel-tuning builds go elsewhere
 
 # -fmad=false: the kernels keep the reference's operation order (a*b+c is not contracted), see DESIGN.md "Numerics"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",

@@ -44,39 +44,69 @@ struct FastH {   // one chain's hyper-parameters + hoisted gene-independent sub-
   int one_hi;                             // 0x3FF00000 (opaque_one_hi)
   int uclamp_ok;                          // max alpha <= 16 min alpha: one clamp of t serves every library (detect_logsum_sl)
   double am[ZZ_MAX_COMP], inv2av[ZZ_MAX_COMP], ck[ZZ_MAX_COMP];  // ck = w_k / (sqrt2pi * sqrt(av_k))           (Pr:344)
+  // device-resident generations (zz_persist.cuh): the mhP_x proposal whose gene sum this sweep accumulates (Pr:209-224)
+  int px_on, px_lib;                      // proposal pending for library px_lib
+  int px_prev_acc, pad_;                  // the previous generation's proposal was accepted: A(y) += its stored per-gene term
+  double px_am256, px_amin, t_clamp_px;   // -256 alpha' log2(e); min(alpha, alpha'); clamp of t valid for both
 };
 
-// FastH is derived from zz_hyper once per hyper-parameter change (k_prepare_hyper, one thread per chain) and kept in global
-// memory; the sweep kernels only copy it, together with the exp/log tables, into shared memory.
-__device__ __forceinline__ void derive_fast(FastH &H, const zz_hyper *__restrict__ hy) {
+// FastH is derived from zz_hyper once per hyper-parameter change (k_prepare_hyper / k_gen_prepare: one thread per chain; inside
+// k_generations: the releasing CTA, one group of fields per thread) and kept in global memory; the sweep kernels only copy it,
+// together with the exp/log tables, into shared memory.  Both forms evaluate the same expressions: bit-identical constants.
+__device__ __forceinline__ void derive_scalars(FastH &H, const zz_hyper *hy, int group) {
   const double s2p = sqrt(2 * PI_D);
-  H.R = hy->num_libraries; H.K = hy->num_active_components;
-  H.s0 = hy->s0; H.s1 = hy->s1; H.tau = hy->tau; H.rtau = sqrt(hy->tau); H.irt = 1.0 / H.rtau;
-  H.c1 = log(H.rtau * s2p);
-  H.sp = hy->spike_probability; H.log_sp = log(H.sp); H.log_1msp = log(1 - H.sp);
-  H.im = hy->inactive_means; H.sd_i = sqrt(hy->inactive_variances);
-  H.log_norm_i = log(s2p * H.sd_i);
-  H.inv2iv = 1.0 / (2 * hy->inactive_variances);
-  H.c0 = (1 - H.sp) / (s2p * H.sd_i);
-  H.wa = hy->weight_active; H.one_m_wa = 1 - hy->weight_active;
-  H.beta = (hy->beta < 0.0000001) ? 0.0 : hy->beta;   // P:121-125: beta < 1e-7 => likelihood 0
-  H.temp = hy->temperature; H.vub = hy->variance_g_upper_bound;
-  H.alpha_min = INFINITY;
-  double a2max = 0, amax = 0;
-  for (int r = 0; r < H.R; ++r) {                       // entries beyond R / K are never read
-    H.alpha[r] = hy->alpha_r[r]; H.alpha2[r] = hy->alpha_r[r] * ZZ_KLOG2E; H.am256[r] = -256.0 * H.alpha2[r];
-    if (r < H.R && !(hy->alpha_r[r] >= H.alpha_min)) H.alpha_min = hy->alpha_r[r];
-    if (r < H.R && H.alpha2[r] > a2max) a2max = H.alpha2[r];
-    if (r < H.R) amax = fmax(amax, hy->alpha_r[r]);
+  if (group == 0) {
+    H.R = hy->num_libraries; H.K = hy->num_active_components;
+    H.s0 = hy->s0; H.s1 = hy->s1; H.tau = hy->tau; H.rtau = sqrt(hy->tau); H.irt = 1.0 / H.rtau;
+    H.c1 = log(H.rtau * s2p);
+  } else if (group == 1) {
+    H.sp = hy->spike_probability; H.log_sp = log(H.sp); H.log_1msp = log(1 - H.sp);
+    H.wa = hy->weight_active; H.one_m_wa = 1 - hy->weight_active;
+    H.beta = (hy->beta < 0.0000001) ? 0.0 : hy->beta;   // P:121-125: beta < 1e-7 => likelihood 0
+    H.temp = hy->temperature; H.vub = hy->variance_g_upper_bound;
+    H.one_hi = 0x3FF00000;
+  } else {
+    const double sd_i = sqrt(hy->inactive_variances);
+    H.im = hy->inactive_means; H.sd_i = sd_i;
+    H.log_norm_i = log(s2p * sd_i);
+    H.inv2iv = 1.0 / (2 * hy->inactive_variances);
+    H.c0 = (1 - hy->spike_probability) / (s2p * sd_i);
   }
+}
+__device__ __forceinline__ void derive_comp(FastH &H, const zz_hyper *hy, int k) {
+  const double s2p = sqrt(2 * PI_D);
+  H.am[k] = hy->active_means[k];
+  H.inv2av[k] = 1.0 / (2 * hy->active_variances[k]);
+  H.ck[k] = hy->weight_within_active[k] / (s2p * sqrt(hy->active_variances[k]));
+}
+__device__ __forceinline__ void derive_lib(FastH &H, const zz_hyper *hy, int r) {
+  H.alpha[r] = hy->alpha_r[r]; H.alpha2[r] = hy->alpha_r[r] * ZZ_KLOG2E; H.am256[r] = -256.0 * H.alpha2[r];
+}
+__device__ __forceinline__ void derive_fin(FastH &H, const zz_hyper *hy) {      // after every derive_lib
+  const int R = hy->num_libraries;
+  double amin = INFINITY, a2max = 0, amax = 0;
+  for (int r = 0; r < R; ++r) {
+    const double a = hy->alpha_r[r], a2 = a * ZZ_KLOG2E;
+    if (!(a >= amin)) amin = a;
+    if (a2 > a2max) a2max = a2;
+    amax = fmax(amax, a);
+  }
+  H.alpha_min = amin;
   H.t_clamp = 1010.0 / a2max;
-  H.one_hi = 0x3FF00000;
-  H.uclamp_ok = (H.alpha_min > 0 && amax <= 16 * H.alpha_min) ? 1 : 0;   // same test as the host's kernel choice (launch_sweep_fast)
-  for (int k = 0; k < H.K; ++k) {
-    H.am[k] = hy->active_means[k];
-    H.inv2av[k] = 1.0 / (2 * hy->active_variances[k]);
-    H.ck[k] = hy->weight_within_active[k] / (s2p * sqrt(hy->active_variances[k]));
-  }
+  H.uclamp_ok = (amin > 0 && amax <= 16 * amin) ? 1 : 0;   // same test as the host's kernel choice (launch_sweep_fast)
+  H.px_on = 0; H.px_lib = 0; H.px_prev_acc = 0; H.pad_ = 0; H.px_am256 = 0; H.px_amin = 0; H.t_clamp_px = H.t_clamp;
+}
+__device__ __forceinline__ void derive_fast(FastH &H, const zz_hyper *hy) {
+  for (int g = 0; g < 3; ++g) derive_scalars(H, hy, g);
+  for (int r = 0; r < hy->num_libraries; ++r) derive_lib(H, hy, r);     // entries beyond R / K are never read
+  for (int k = 0; k < hy->num_active_components; ++k) derive_comp(H, hy, k);
+  derive_fin(H, hy);
+}
+// the same by a whole CTA: call, __syncthreads(), then one thread calls derive_fin
+__device__ __forceinline__ void derive_fast_par(FastH &H, const zz_hyper *hy, int tid) {
+  if (tid < 3) derive_scalars(H, hy, tid);
+  else if (tid >= 8 && tid < 8 + hy->num_active_components) derive_comp(H, hy, tid - 8);
+  else if (tid >= 32 && tid < 32 + hy->num_libraries) derive_lib(H, hy, tid - 32);
 }
 
 __device__ __forceinline__ void load_tabs(MathTabs &T, const double *__restrict__ exp_tab, const double2 *__restrict__ log_tab) {

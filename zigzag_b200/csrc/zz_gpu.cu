@@ -654,6 +654,30 @@ __global__ void __launch_bounds__(BLOCK) k_refresh_lps(const FastArgs fa) {
   if (fa.want_stats && (f & F_ALLZERO)) a.xglik[i] = times_beta(H, A);
 }
 
+}  // namespace
+#include "zz_persist.cuh"
+namespace {
+
+// before a segment of generations: proposes the first generation's mhP_x (Pr:193-243, first half) and derives the sweep constants
+__global__ void k_gen_prepare(int C, int R, int tune, int hyper_moves, uint64_t seed, zz_hyper *hyper, ChainDev *chain, FastH *fasth) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  derive_fast(fasth[c], hyper + c);
+  if (!hyper_moves) return;
+  ChainDev &cd = chain[c];
+  cd.px_prev_acc = 0;
+  px_propose(cd, hyper[c], seed, cd.step, tune, R);
+  set_px(fasth[c], hyper[c], cd);
+}
+// after a segment whose last generation accepted its mhP_x: A(y) += the stored per-gene term (inside a segment the next sweep does it)
+__global__ void __launch_bounds__(BLOCK) k_apply_dlt(int64_t G, const ChainDev *chain, const uint16_t *flags, const double *dlt, double *lps) {
+  if (!chain[blockIdx.y].px_prev_acc) return;
+  const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (g >= G) return;
+  const int64_t i = (int64_t)blockIdx.y * G + g;
+  if (!(flags[i] & F_INSPIKE)) lps[i] += dlt[i];
+}
+
 // ---- zz_sweep_host: the state of a CHUNK of genes (caller order [c0, c0 + n)) enters and leaves through staging planes, so
 // that chunk k+1 can be on the PCIe bus (host -> device) and chunk k-1 on its way back while chunk k is being swept.
 
@@ -763,29 +787,24 @@ struct RedArgs {
   double alpha_prop[ZZ_MAX_LIBS];
   uint8_t lib_mask[ZZ_MAX_LIBS];
   double *partials;                                   // [grid.y][grid.x][2]
-  const DevChain *prop;                               // device-resident generation loop: parameters come from the mailbox, not from the fields above
 };
 
 // Grid-stride per-gene reduction; blockIdx.y = library for RED_PXDELTA.  Two sums per gene at most.
 __global__ void __launch_bounds__(BLOCK) k_reduce(const RedArgs a) {
   __shared__ HyperS H;
   __shared__ double red[BLOCK / 32];
-  // blockIdx.z = chain of a batched launch (zz_run_generations on several chains); the host entry points launch with grid.z = 1 and
+  // blockIdx.z = chain of a batched launch (the sample rows of zz_run_generations); the host entry points launch with grid.z = 1 and
   // pointers already offset to their chain
   const int64_t coff = (int64_t)blockIdx.z * a.G;
   const double *Yg = a.Yg + coff, *vg = a.vg + coff, *vgprob = a.vgprob + coff;
   const uint16_t *flags = a.flags + coff;
-  const DevChain *prop = a.prop ? a.prop + blockIdx.z : nullptr;
   load_hyper(H, a.hyper + blockIdx.z);
-  const int lib = (prop && a.op == RED_PXDELTA) ? prop->p_lib : (int)blockIdx.y;
+  const int lib = (int)blockIdx.y;
   double v0 = 0, v1 = 0;
-  const bool active_y = !(a.op == RED_PXDELTA && !prop && !a.lib_mask[lib]);
-  // parameters of the sum: by value from the host, or from the device-side mailbox (zz_run_generations; RED_LEVEL2 then runs
-  // with grid.y = 2: proposed and current parameters in one launch)
-  const double p_s0 = prop ? prop->p_s0 : a.s0, p_s1 = prop ? prop->p_s1 : a.s1, p_tau = prop ? prop->p_tau : a.tau;
-  const double p_im = prop ? prop->l2[blockIdx.y].im : a.im, p_iv = prop ? prop->l2[blockIdx.y].iv : a.iv;
-  const double *p_am = prop ? prop->l2[blockIdx.y].am : a.am, *p_av = prop ? prop->l2[blockIdx.y].av : a.av;
-  const double p_alpha = a.op == RED_PXDELTA ? (prop ? prop->p_alpha : a.alpha_prop[lib]) : 0.0;
+  const bool active_y = !(a.op == RED_PXDELTA && !a.lib_mask[lib]);
+  const double p_s0 = a.s0, p_s1 = a.s1, p_tau = a.tau, p_im = a.im, p_iv = a.iv;
+  const double *p_am = a.am, *p_av = a.av;
+  const double p_alpha = a.op == RED_PXDELTA ? a.alpha_prop[lib] : 0.0;
   if (active_y) {
     for (int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x; g < a.G; g += (int64_t)gridDim.x * BLOCK) {
       const double y = Yg[g], v = vg[g];
@@ -806,20 +825,8 @@ __global__ void __launch_bounds__(BLOCK) k_reduce(const RedArgs a) {
         }
       } else if (a.op == RED_PXDELTA) {              // Pr:209-224
         const double x = a.Xg[(int64_t)lib * a.G + g];
-        const double gl = a.gl[g];
-        if (prop) {
-          // device-resident loop: the normal density of the library is the same on both sides and exp(y) is shared — only the
-          // detection terms are evaluated (5 libm calls per gene instead of 12)
-          if (!in_spike && !(H.beta < 0.0000001)) {
-            const double t = gl * exp(y);
-            const double pp = 1 - exp(-(t * p_alpha)), pc = 1 - exp(-(t * H.alpha[lib]));
-            const bool nd = (x == -INFINITY);
-            v0 += H.beta * (log(nd ? (1 - pp) : pp) - log(nd ? (1 - pc) : pc));
-          }
-        } else {
-          v0 += xg_lik_onelib(H, x, y, v, gl, p_alpha, in_spike, f & F_ALLZERO) -
-                xg_lik_onelib(H, x, y, v, gl, H.alpha[lib], in_spike, f & F_ALLZERO);
-        }
+        v0 += xg_lik_onelib(H, x, y, v, a.gl[g], p_alpha, in_spike, f & F_ALLZERO) -
+              xg_lik_onelib(H, x, y, v, a.gl[g], H.alpha[lib], in_spike, f & F_ALLZERO);
       } else {                                       // RED_LNL, U:70-75
         v0 += in_spike ? xg_lik_inspike(H, f & F_ALLZERO) : xg_lik_out(H, a.Xg + g, a.G, y, v, a.gl[g]);
       }
@@ -908,23 +915,6 @@ __global__ void __launch_bounds__(BLOCK) k_px_commit(int64_t G, int lib, double 
   const double x = Xg[(int64_t)lib * G + g];
   xglik[g] = xglik[g] + xg_lik_onelib(H, x, Yg[g], vg[g], gl[g], alpha_new, f & F_INSPIKE, f & F_ALLZERO) -
              xg_lik_onelib(H, x, Yg[g], vg[g], gl[g], H.alpha[lib], f & F_INSPIKE, f & F_ALLZERO);
-}
-
-// the same commit for the device-resident loop: library and new alpha come from the mailbox, nothing happens unless mhP_x accepted
-__global__ void __launch_bounds__(BLOCK) k_px_commit_dev(int64_t G, const DevChain *c, const double *Xg, const double *gl, const double *Yg,
-                                                          const double *vg, const uint16_t *flags, const zz_hyper *hyper, double *xglik) {
-  c += blockIdx.y; hyper += blockIdx.y;                 // blockIdx.y = chain
-  { const int64_t coff = (int64_t)blockIdx.y * G; Yg += coff; vg += coff; flags += coff; xglik += coff; }
-  if (!c->gate_px) return;
-  __shared__ HyperS H;
-  load_hyper(H, hyper);
-  const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (g >= G) return;
-  const int lib = c->p_lib;
-  const uint32_t f = flags[g];
-  const double x = Xg[(int64_t)lib * G + g];
-  xglik[g] = xglik[g] + xg_lik_onelib(H, x, Yg[g], vg[g], gl[g], c->p_alpha, f & F_INSPIKE, f & F_ALLZERO) -
-             xg_lik_onelib(H, x, Yg[g], vg[g], gl[g], c->p_alpha_old, f & F_INSPIKE, f & F_ALLZERO);
 }
 
 // one sample: the _model_parameters.log row (thread 0) and, when due, the candidate genes' Yg / variance_g rows, written straight
@@ -1150,7 +1140,9 @@ struct zz_handle {
   void *pp_buf; int pp_nb;                 // zz_post_predictive: histograms + bins on the device
   bool sink_on; zz_sample_sink sink; double *sink_p, *sink_y, *sink_v; int32_t *cand_slots; int64_t sink_prow, sink_yrow;   // zz_set_sample_sink
   bool hyper_host_stale;                   // zz_run_generations moved the hyper-parameters on the device; hyper_host is refreshed by zz_chain_read
-  DevChain *devchain; double *chain_stats; bool chain_ready; int64_t chain_gen, chain_samples; uint64_t chain_step;   // zz_run_generations
+  ChainDev *devchain; double *chain_stats; bool chain_ready; int64_t chain_gen, chain_samples; uint64_t chain_step;   // zz_run_generations
+  double *dlt; GenCtl *genctl; long long *genacc; int gen_blocks;   // k_generations: per-gene mhP_x terms, grid-barrier words, fixed-point totals
+  bool caches_valid;                       // XgLikelihood / variance_g_probability are current (device-resident segments do not maintain them)
   int32_t *inv_perm; cudaStream_t s_up, s_down; cudaEvent_t ev_entry, ev_up[ZZ_HOST_MAX_CHUNKS], ev_done[ZZ_HOST_MAX_CHUNKS]; bool pipe_ready;
 };
 
@@ -1177,6 +1169,8 @@ int fail(zz_handle *h, int code, const std::string &msg) {
 
 inline dim3 gene_grid(const zz_handle *h, int64_t n, int ny = 1) { return dim3((unsigned)((n + BLOCK - 1) / BLOCK), (unsigned)ny); }
 inline int red_blocks(int64_t n) { int64_t b = (n + BLOCK - 1) / BLOCK; return (int)(b < RED_BLOCKS ? (b < 1 ? 1 : b) : RED_BLOCKS); }
+
+int ensure_caches(zz_handle *h);   // XgLikelihood / variance_g_probability current again after a device-resident segment
 
 int chain_ok(zz_handle *h, int chain) {
   if (chain < 0 || chain >= h->C) return fail(h, ZZ_ERR_INVALID, "chain index out of range");
@@ -1228,6 +1222,7 @@ void fill_sweep_args(zz_handle *h, SweepArgs &a, uint64_t step, int tune, uint32
 int launch_sweep(zz_handle *h, uint64_t step, int tune, uint32_t moves, const double *const draws_dev[9], uint8_t *const dec_dev[4],
                  int64_t g_begin, int64_t g_end) {
   if (g_end <= g_begin) return ZZ_OK;
+  if (int rc = ensure_caches(h)) return rc;
   SweepArgs a;
   fill_sweep_args(h, a, step, tune, moves, draws_dev, dec_dev, g_begin, g_end);
   k_sweep<<<gene_grid(h, g_end - g_begin, h->C), BLOCK, 0, h->stream>>>(a);
@@ -1237,6 +1232,9 @@ int launch_sweep(zz_handle *h, uint64_t step, int tune, uint32_t moves, const do
   return ZZ_OK;
 }
 
+#ifdef ZZ_DEV_R16
+#define ZZ_DISPATCH_R(h, KERNEL, grid, ...) KERNEL<16><<<grid, BLOCK, 0, (h)->stream>>>(__VA_ARGS__)
+#else
 #define ZZ_DISPATCH_R(h, KERNEL, grid, ...)                                                      \
   do {                                                                                           \
     switch ((h)->R) {                                                                            \
@@ -1247,6 +1245,7 @@ int launch_sweep(zz_handle *h, uint64_t step, int tune, uint32_t moves, const do
       default: KERNEL<0><<<grid, BLOCK, 0, (h)->stream>>>(__VA_ARGS__); break;                          \
     }                                                                                            \
   } while (0)
+#endif
 
 void fill_fast_args(zz_handle *h, FastArgs &fa) {
   fa.lps = h->lps; fa.exp_tab = h->exp_tab; fa.log_tab = h->log_tab;
@@ -1327,6 +1326,10 @@ int persistent_blocks(zz_handle *h, size_t smem) {
   if (h->persist_blocks > 0) return h->persist_blocks;
   int per_sm = 0, sms = 0;
   cudaError_t e;
+#ifdef ZZ_DEV_R16
+  allow_big_smem<16>((int)smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<16, true, 0>, SWEEP_BLOCK, smem);
+#else
   {   // static tables (11.6 KB) + statistic columns exceed the default 48 KB shared-memory limit: opt in explicitly
     switch (h->R) {
       case 2: allow_big_smem<2>((int)smem); break;
@@ -1343,6 +1346,7 @@ int persistent_blocks(zz_handle *h, size_t smem) {
     case 16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<16, true, 0>, SWEEP_BLOCK, smem); break;
     default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<0, true, 0>, SWEEP_BLOCK, smem); break;
   }
+#endif
   if (e != cudaSuccess || per_sm < 1) per_sm = 2;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device) != cudaSuccess || sms < 1) sms = 148;
   h->persist_blocks = per_sm * sms;
@@ -1354,6 +1358,7 @@ int persistent_blocks(zz_handle *h, size_t smem) {
 int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, const double *const draws_dev[9], uint8_t *const dec_dev[4],
                       int64_t g_begin, int64_t g_end, const int32_t *slot_list = nullptr, const HostChunk *host_io = nullptr) {
   if (g_end <= g_begin) return ZZ_OK;
+  if (int rc = ensure_caches(h)) return rc;
   if (!slot_list) { if (int rc = ensure_lps(h)) return rc; }           // list mode: the caller (k_host_in) has just rebuilt lps
   FastArgs fa;
   fill_sweep_args(h, fa.s, step, tune, moves, draws_dev, dec_dev, g_begin, g_end);
@@ -1456,10 +1461,18 @@ int launch_eval(zz_handle *h, int which, int chain /* -1 = all chains */, double
   EvalArgs a;
   const int64_t off = chain < 0 ? 0 : (int64_t)chain * h->G;
   a.G = h->G; a.which = which; a.Xg = h->Xg; a.gl = h->gl; a.Yg = h->Yg + off; a.vg = h->vg + off; a.flags = h->flags + off;
-  a.hyper = h->hyper + (chain < 0 ? 0 : chain); a.out0 = out0; a.out1 = out1; a.gate = gate; a.gate_stride = (int)(sizeof(DevChain) / sizeof(int));
+  a.hyper = h->hyper + (chain < 0 ? 0 : chain); a.out0 = out0; a.out1 = out1; a.gate = gate; a.gate_stride = 0;
   k_eval<<<gene_grid(h, h->G, chain < 0 ? h->C : 1), BLOCK, 0, h->stream>>>(a);
   ZZ_LAUNCHED(h);
   return ZZ_OK;
+}
+
+// Device-resident segments (k_generations) do not maintain the reference's two per-gene caches; whoever reads them next has them
+// rebuilt from the state in the reference's operation order (I:473, I:504)
+int ensure_caches(zz_handle *h) {
+  if (h->caches_valid) return ZZ_OK;
+  h->caches_valid = true;
+  return launch_eval(h, EVAL_REFRESH, -1, h->xglik, h->vgprob);
 }
 
 int eval_to_host(zz_handle *h, int which, int chain, double *out) {
@@ -1481,7 +1494,7 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   *out = nullptr;
   if (cfg->num_genes < 1 || cfg->num_libraries < 2 || cfg->num_libraries > ZZ_MAX_LIBS || cfg->num_active_components < 1 ||
       cfg->num_active_components > ZZ_MAX_COMP || cfg->num_chains < 1 || cfg->num_chains > (1 << 20) ||
-      cfg->gene_offset < 0 || cfg->gene_offset + cfg->num_genes > 0xFFFFFFFFLL)
+      cfg->gene_offset < 0 || cfg->gene_offset + cfg->num_genes > 0xFFFFFF00LL)   /* gene ids 0xFFFFFF00.. are the scalar sub-streams (zz_chain.cuh) */
     return ZZ_ERR_INVALID;
   zz_handle *h = new (std::nothrow) zz_handle();
   if (!h) return ZZ_ERR_NOMEM;
@@ -1492,6 +1505,7 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   h->sink_on = false; h->cand_slots = nullptr; h->sink_prow = h->sink_yrow = 0;
   h->hyper_host_stale = false;
   h->devchain = nullptr; h->chain_stats = nullptr; h->chain_ready = false; h->chain_gen = 0; h->chain_samples = 0; h->chain_step = 0;
+  h->dlt = nullptr; h->genctl = nullptr; h->genacc = nullptr; h->gen_blocks = 0; h->caches_valid = true;
   *out = h;  // returned even on failure so the caller can read zz_last_error and must zz_destroy
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1576,6 +1590,9 @@ void zz_destroy(zz_handle *h) {
   if (h->cand_slots) cudaFree(h->cand_slots);
   if (h->pp_buf) cudaFree(h->pp_buf);
   if (h->chain_stats) cudaFree(h->chain_stats);
+  if (h->dlt) cudaFree(h->dlt);
+  if (h->genctl) cudaFree(h->genctl);
+  if (h->genacc) cudaFree(h->genacc);
   if (h->pipe_ready) {
     cudaStreamDestroy(h->s_up); cudaStreamDestroy(h->s_down); cudaEventDestroy(h->ev_entry);
     for (int k = 0; k < ZZ_HOST_MAX_CHUNKS; ++k) { cudaEventDestroy(h->ev_up[k]); cudaEventDestroy(h->ev_done[k]); }
@@ -1658,6 +1675,7 @@ int zz_set_state(zz_handle *h, int chain, const double *Yg, const double *varian
   int rc;
   if (Yg || spike) h->lps_valid = false;
   h->stats_fresh = false;
+  if (XgLikelihood && variance_g_probability && h->C == 1) h->caches_valid = true;
   if (!h->have_data) return fail(h, ZZ_ERR_STATE, "zz_upload_data has not been called");
   if ((rc = up_g(h, h->Yg + off, Yg, G)) || (rc = up_g(h, h->vg + off, variance_g, G)) || (rc = up_g(h, h->xglik + off, XgLikelihood, G)) ||
       (rc = up_g(h, h->vgprob + off, variance_g_probability, G)) || (rc = up_g(h, h->ty + off, ty, G)) || (rc = up_g(h, h->tv + off, tv, G)))
@@ -1679,6 +1697,7 @@ int zz_get_state(zz_handle *h, int chain, double *Yg, double *variance_g, int32_
   if (int rc = chain_ok(h, chain)) return rc;
   const int64_t G = h->G, off = (int64_t)chain * G;
   int rc;
+  if ((XgLikelihood || variance_g_probability) && (rc = ensure_caches(h))) return rc;
   if ((rc = down_g(h, Yg, h->Yg + off, G)) || (rc = down_g(h, variance_g, h->vg + off, G)) || (rc = down_g(h, XgLikelihood, h->xglik + off, G)) ||
       (rc = down_g(h, variance_g_probability, h->vgprob + off, G)) || (rc = down_g(h, ty, h->ty + off, G)) || (rc = down_g(h, tv, h->tv + off, G)))
     return rc;
@@ -1720,6 +1739,7 @@ int zz_refresh_caches(zz_handle *h) {
   ZZ_CHECK(h);
   h->stats_fresh = false;
   if (!h->have_data) return fail(h, ZZ_ERR_STATE, "zz_upload_data has not been called");
+  h->caches_valid = true;
   return launch_eval(h, EVAL_REFRESH, -1, h->xglik, h->vgprob);
 }
 
@@ -1807,6 +1827,7 @@ int zz_suffstats_dev(zz_handle *h, double *out_dev) {
     return ZZ_OK;
   }
   const int nblk = red_blocks(h->G), nstat = zz_suffstats_len(h->K);
+  if (int rc = ensure_caches(h)) return rc;
   StatArgs a;
   a.G = h->G; a.K = h->K; a.Yg = h->Yg; a.vg = h->vg; a.xglik = h->xglik; a.vgprob = h->vgprob; a.flags = h->flags; a.partials = h->partials;
   k_suffstats<<<dim3(nblk, h->C), BLOCK, 0, h->stream>>>(a);
@@ -1880,6 +1901,7 @@ int zz_suffstats_allreduce_dev(zz_handle *h, double *out_dev) {
   const double *partials; int nblk;
   if (h->stats_fresh) { partials = h->sw_partials; nblk = (int)h->sw_rows; }
   else {
+    if (int rc = ensure_caches(h)) return rc;
     nblk = red_blocks(h->G);
     StatArgs a;
     a.G = h->G; a.K = h->K; a.Yg = h->Yg; a.vg = h->vg; a.xglik = h->xglik; a.vgprob = h->vgprob; a.flags = h->flags; a.partials = h->partials;
@@ -1899,6 +1921,7 @@ int zz_varg_hyper_sum(zz_handle *h, int chain, double s0, double s1, double tau,
   ZZ_CHECK(h);
   if (int rc = chain_ok(h, chain)) return rc;
   if (!out2) return fail(h, ZZ_ERR_INVALID, "out is NULL");
+  if (int rc = ensure_caches(h)) return rc;
   RedArgs a; fill_red(h, a, chain, RED_VARG_HYPER);
   a.s0 = s0; a.s1 = s1; a.tau = tau;
   return reduce_to_host(h, a, 1, out2, 2);
@@ -1908,6 +1931,7 @@ int zz_commit_varg_hyper(zz_handle *h, int chain) {
   ZZ_CHECK(h);
   h->stats_fresh = false;
   if (int rc = chain_ok(h, chain)) return rc;
+  if (int rc = ensure_caches(h)) return rc;
   return launch_eval(h, EVAL_COMMIT_VG, chain, nullptr, h->vgprob + (int64_t)chain * h->G);
 }
 
@@ -1940,6 +1964,7 @@ int zz_px_commit(zz_handle *h, int chain, int lib, double alpha_new) {
     ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
     h->hyper_host_stale = false;
   }
+  if (int rc = ensure_caches(h)) return rc;
   const int64_t off = (int64_t)chain * h->G;
   if (h->R > 2) {  // Pr:213-215
     k_px_commit<<<gene_grid(h, h->G), BLOCK, 0, h->stream>>>(h->G, lib, alpha_new, h->Xg, h->gl, h->Yg + off, h->vg + off,
@@ -2110,7 +2135,15 @@ int zz_sweep_host(zz_handle *h, uint64_t step, int tune, double *Yg, double *var
   return ZZ_OK;
 }
 
-// ---- device-resident generation loop (zz_chain.cuh) ----------------------------------------------------------------
+// ---- device-resident generation loop (zz_chain.cuh, zz_persist.cuh) ---------------------------------------------------
+static void win_pack(const uint8_t *w, Win100 &o) {          // trace[0] oldest ... trace[99] newest -> bit 0 = newest
+  o.lo = 0; o.hi = 0;
+  for (int j = 0; j < 100; ++j) if (w[99 - j]) { if (j < 64) o.lo |= 1ULL << j; else o.hi |= 1ULL << (j - 64); }
+}
+static void win_unpack(const Win100 &w, uint8_t *o) {
+  for (int j = 0; j < 100; ++j) o[99 - j] = (uint8_t)((j < 64 ? (w.lo >> j) : (w.hi >> (j - 64))) & 1ULL);
+}
+
 int zz_chain_begin(zz_handle *h, const zz_priors *priors, const zz_chain_scalars *scalars) {
   ZZ_CHECK(h);
   if (!priors || !scalars) return fail(h, ZZ_ERR_INVALID, "NULL argument");
@@ -2119,14 +2152,23 @@ int zz_chain_begin(zz_handle *h, const zz_priors *priors, const zz_chain_scalars
   for (int c = 1; c < C; ++c)
     if (scalars[c].gen != scalars[0].gen || scalars[c].step != scalars[0].step || scalars[c].n_samples != scalars[0].n_samples)
       return fail(h, ZZ_ERR_INVALID, "zz_chain_begin: batched chains advance in lock-step (same gen, step, n_samples)");
-  if (!h->devchain) {
-    ZZ_CUDA(h, cudaMalloc(&h->devchain, sizeof(DevChain) * C));
-    ZZ_CUDA(h, cudaMalloc(&h->chain_stats, sizeof(double) * MAX_NSTAT * C));
+  if (!h->devchain) ZZ_CUDA(h, cudaMalloc(&h->devchain, sizeof(ChainDev) * C));
+  std::vector<ChainDev> tmp((size_t)C);
+  memset(tmp.data(), 0, sizeof(ChainDev) * C);
+  for (int c = 0; c < C; ++c) {
+    ChainDev &d = tmp[c]; const zz_chain_scalars &sc = scalars[c];
+    d.pr = *priors; d.chain = c;
+    memcpy(d.active_means_dif, sc.active_means_dif, sizeof d.active_means_dif);
+    d.t_im = sc.t_im; d.t_av = sc.t_av; memcpy(d.t_am, sc.t_am, sizeof d.t_am);
+    d.t_s0 = sc.t_s0; d.t_s1 = sc.t_s1; d.t_tau = sc.t_tau; d.t_s0tau = sc.t_s0tau; memcpy(d.t_alpha, sc.t_alpha, sizeof d.t_alpha);
+    win_pack(sc.w_im, d.w_im); win_pack(sc.w_av, d.w_av); win_pack(sc.w_s0, d.w_s0); win_pack(sc.w_s1, d.w_s1);
+    win_pack(sc.w_tau, d.w_tau); win_pack(sc.w_s0tau, d.w_s0tau);
+    for (int k = 0; k < ZZ_MAX_COMP; ++k) win_pack(sc.w_am[k], d.w_am[k]);
+    for (int r = 0; r < ZZ_MAX_LIBS; ++r) win_pack(sc.w_alpha[r], d.w_alpha[r]);
+    d.hyper_ctr = sc.hyper_ctr; memcpy(d.hyper_buf, sc.hyper_buf, sizeof d.hyper_buf);
+    d.step = sc.step; d.gen = sc.gen; d.n_samples = sc.n_samples;
   }
-  std::vector<DevChain> tmp((size_t)C);
-  memset(tmp.data(), 0, sizeof(DevChain) * C);
-  for (int c = 0; c < C; ++c) { tmp[c].pr = *priors; tmp[c].sc = scalars[c]; tmp[c].chain = c; }
-  cudaError_t e = cudaMemcpyAsync(h->devchain, tmp.data(), sizeof(DevChain) * C, cudaMemcpyHostToDevice, h->stream);
+  cudaError_t e = cudaMemcpyAsync(h->devchain, tmp.data(), sizeof(ChainDev) * C, cudaMemcpyHostToDevice, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   if (e != cudaSuccess) return fail(h, ZZ_ERR_CUDA, std::string("zz_chain_begin: ") + cudaGetErrorString(e));
   h->chain_gen = scalars->gen; h->chain_step = scalars->step; h->chain_samples = scalars->n_samples;
@@ -2134,129 +2176,201 @@ int zz_chain_begin(zz_handle *h, const zz_priors *priors, const zz_chain_scalars
   return ZZ_OK;
 }
 
+}  // extern "C"
+namespace {
+
+template <int RT> cudaError_t launch_generations_k(int K, dim3 grid, size_t smem, cudaStream_t st, GenArgs &ga) {
+  void *args[] = {&ga};
+  const void *fn = nullptr;
+  switch (K) {
+    case 1: fn = (const void *)k_generations<RT, 1>; break;
+    case 2: fn = (const void *)k_generations<RT, 2>; break;
+    case 3: fn = (const void *)k_generations<RT, 3>; break;
+    default: return cudaErrorInvalidValue;
+  }
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaLaunchCooperativeKernel(fn, grid, dim3(SWEEP_BLOCK), args, smem, st);
+}
+
+// whether k_generations serves this handle: straight-line tile (K <= 3, no variance_g upper bound), library loop unrolled
+const char *generations_unsupported(zz_handle *h) {
+  if (h->K > 3) return "more than 3 active components";
+#ifdef ZZ_DEV_R16
+  if (h->R != 16) return "ZZ_DEV_R16 build";
+#endif
+  for (int c = 0; c < h->C; ++c) if (h->hyper_host[c].variance_g_upper_bound != INFINITY) return "finite variance_g_upper_bound (its plnorm term has no closed form in the sufficient statistics)";
+  return nullptr;
+}
+
+// one cooperative launch: `ngen` generations (hyper_moves) or fused sweeps with frozen hyper-parameters (!hyper_moves)
+int launch_generations(zz_handle *h, uint64_t step0, int ngen, int tune, int hyper_moves, int step_stride, int do_tune_all_last, double target) {
+  if (ngen <= 0) return ZZ_OK;
+  const int C = h->C, nstat = zz_suffstats_len(h->K);
+  if (!h->genctl) {
+    ZZ_CUDA(h, cudaMalloc(&h->genctl, sizeof(GenCtl) * C));
+    ZZ_CUDA(h, cudaMalloc(&h->genacc, sizeof(long long) * (size_t)C * nstat));
+    ZZ_CUDA(h, cudaMalloc(&h->dlt, sizeof(double) * (size_t)C * h->G));
+    ZZ_CUDA(h, cudaMemsetAsync(h->dlt, 0, sizeof(double) * (size_t)C * h->G, h->stream));
+  }
+  if (int rc = ensure_lps(h)) return rc;
+  const size_t smem = sizeof(double) * (nstat + 10) * SWEEP_BLOCK;
+  if (h->gen_blocks == 0) {    // co-resident CTAs of k_generations (cooperative launch): from the occupancy calculator
+    int per_sm = 0, sms = 0;
+    cudaError_t e = cudaSuccess;
+#define ZZ_OCC(RT_) { const void *fn = h->K == 1 ? (const void *)k_generations<RT_, 1> : h->K == 2 ? (const void *)k_generations<RT_, 2> : (const void *)k_generations<RT_, 3>; \
+      e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SWEEP_BLOCK, smem); }
+#ifdef ZZ_DEV_R16
+    ZZ_OCC(16)
+#else
+    switch (h->R) { case 2: ZZ_OCC(2) break; case 4: ZZ_OCC(4) break; case 8: ZZ_OCC(8) break; case 16: ZZ_OCC(16) break; default: ZZ_OCC(0) break; }
+#endif
+#undef ZZ_OCC
+    ZZ_CUDA(h, e);
+    ZZ_CUDA(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+    if (per_sm < 1) return fail(h, ZZ_ERR_CUDA, "k_generations does not fit on an SM");
+    h->gen_blocks = per_sm * sms;
+    if (const char *e2 = getenv("ZZ_GEN_BLOCKS")) { const int n = atoi(e2); if (n >= 1 && n < h->gen_blocks) h->gen_blocks = n; }   // tests: a smaller grid
+  }
+  const int64_t ntiles = (h->G + 31) / 32, need = (ntiles + SWEEP_BLOCK / 32 - 1) / (SWEEP_BLOCK / 32);
+  int64_t per_chain = h->gen_blocks / C;
+  if (per_chain < 1) return fail(h, ZZ_ERR_INVALID, "too many chains for the co-resident grid of the device-resident loop");
+  if (per_chain > need) per_chain = need;
+  GenArgs ga;
+  memset(&ga, 0, sizeof ga);
+  const double *no_draws[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint8_t *no_dec[4] = {nullptr, nullptr, nullptr, nullptr};
+  fill_sweep_args(h, ga.fa.s, step0, tune, ZZ_MOVE_FUSED, no_draws, no_dec, 0, h->G);
+  fill_fast_args(h, ga.fa);
+  ga.fa.do_spike_move = 1;
+  ga.dlt = h->dlt; ga.hyper = h->hyper; ga.chain = h->devchain; ga.fasth_rw = h->fasth; ga.ctl = h->genctl; ga.acc = h->genacc;
+  ga.ngen = ngen; ga.hyper_moves = hyper_moves; ga.do_tune_all_last = do_tune_all_last; ga.step_stride = step_stride; ga.target = target;
+  ga.stats_out = h->stats_target;
+  static const int dyn_tiles = getenv("ZZ_GEN_STATIC_TILES") ? 0 : 1;   // measurement switch (profiles/r2_summary.md)
+  ga.dyn_tiles = dyn_tiles;
+  static const long long timeout_s = getenv("ZZ_GEN_TIMEOUT_S") ? atoll(getenv("ZZ_GEN_TIMEOUT_S")) : 20;
+  ga.timeout_ns = timeout_s * 1000000000LL;
+  if (h->comm_ready && h->comm_world > 1) {
+    ga.do_allreduce = 1;
+    ga.cm.rank = h->comm_rank; ga.cm.world = h->comm_world; ga.cm.nvec = nstat; ga.cm.epoch = h->comm_epoch; ga.cm.base = 0; ga.cm.stride = 2 * nstat;
+    for (int r = 0; r < 8; ++r) { ga.cm.inbox[r] = h->peer_inbox[r]; ga.cm.flags[r] = h->peer_flags[r]; }
+    h->comm_epoch += (unsigned long long)ngen;
+    if ((unsigned)h->comm_epoch < (unsigned)ngen) h->comm_epoch += (unsigned long long)ngen + 1;   // keep the 32-bit epoch away from 0 (the zero-initialised inbox)
+  }
+  ZZ_CUDA(h, cudaMemsetAsync(h->genctl, 0, sizeof(GenCtl) * C, h->stream));
+  ZZ_CUDA(h, cudaMemsetAsync(h->genacc, 0, sizeof(long long) * (size_t)C * nstat, h->stream));
+  const dim3 grid((unsigned)per_chain, (unsigned)C);
+  cudaError_t e;
+#ifdef ZZ_DEV_R16
+  e = launch_generations_k<16>(h->K, grid, smem, h->stream, ga);
+#else
+  switch (h->R) {
+    case 2: e = launch_generations_k<2>(h->K, grid, smem, h->stream, ga); break;
+    case 4: e = launch_generations_k<4>(h->K, grid, smem, h->stream, ga); break;
+    case 8: e = launch_generations_k<8>(h->K, grid, smem, h->stream, ga); break;
+    case 16: e = launch_generations_k<16>(h->K, grid, smem, h->stream, ga); break;
+    default: e = launch_generations_k<0>(h->K, grid, smem, h->stream, ga); break;
+  }
+#endif
+  ZZ_CUDA(h, e);
+  h->launches++;
+  h->caches_valid = false; h->stats_fresh = false;
+  return ZZ_OK;
+}
+
+}  // namespace
+extern "C" {
+
+int zz_debug_gen_times(zz_handle *h, double *out2) {   // diagnostic: ns the releasing CTA of chain 0 spent per launch {ticket -> release, scalar stage}
+  ZZ_CHECK(h);
+  if (!h->genctl || !out2) return fail(h, ZZ_ERR_STATE, "no device-resident launch yet");
+  GenCtl c;
+  ZZ_CUDA(h, cudaMemcpyAsync(&c, h->genctl, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+  ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  out2[0] = (double)c.ns_leader; out2[1] = (double)c.ns_stage;
+  return ZZ_OK;
+}
+
+int zz_run_sweeps(zz_handle *h, uint64_t step, int nsweeps, int tune) {
+  ZZ_CHECK(h);
+  if (!h->have_data) return fail(h, ZZ_ERR_STATE, "zz_upload_data has not been called");
+  if (nsweeps < 0) return fail(h, ZZ_ERR_INVALID, "zz_run_sweeps: bad arguments");
+  if (const char *why = generations_unsupported(h)) return fail(h, ZZ_ERR_INVALID, std::string("zz_run_sweeps: ") + why);
+  if (int rc = ensure_fasth(h)) return rc;
+  return launch_generations(h, step, nsweeps, tune, 0, 1, 0, 0.44);
+}
+
 int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, double target) {
   ZZ_CHECK(h);
   if (!h->chain_ready) return fail(h, ZZ_ERR_STATE, "zz_run_generations: call zz_chain_begin first");
   if (ngen < 0 || (!tune && sample_frequency < 1)) return fail(h, ZZ_ERR_INVALID, "zz_run_generations: bad arguments");
-  double *saved_target = h->stats_target; const int saved_allreduce = h->stats_allreduce;
-  // gene shards on several GPUs (zz_comm_connect done): the sweep's statistics and every gene sum are all-reduced over peer memory
-  // inside the kernels that produce them, so each rank's single-thread stage sees bit-identical inputs and takes the same decisions
-  const bool multi = h->comm_ready && h->comm_world > 1;
-  h->stats_target = h->chain_stats; h->stats_allreduce = multi ? 1 : 0;
-  const int K = h->K, R = h->R, C = h->C, nblk = red_blocks(h->G), nstat = zz_suffstats_len(h->K);
-  const bool fused_stats = (size_t)nstat * C <= (size_t)MAX_NSTAT * 8;      // else: per-chain reduction of the sweep's rows after it
-  if (!fused_stats) h->stats_target = nullptr;
-  const uint64_t seed = h->cfg.seed;
-  const double *no_draws[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  uint8_t *no_dec[4] = {nullptr, nullptr, nullptr, nullptr};
-  int rc = ZZ_OK, red_stride = 2;
-  auto stage = [&](int st, int iter, int do_tune_all, int sampled) {
-    k_chain_stage<<<C, 128, 0, h->stream>>>(st, iter, tune, K, R, seed, h->devchain, h->hyper, h->chain_stats, h->red_out, red_stride, target, do_tune_all, sampled, h->fasth);
-    h->launches++;
-  };
-  auto reduce = [&](int op, int ny) {            // gene sums at the mailbox parameters -> red_out[chain][ny][2], no host copy
-    RedArgs a; fill_red(h, a, 0, op);
-    a.prop = h->devchain; a.partials = h->partials;
-    red_stride = 2 * ny;
-    // batched chains: keep the whole launch near two waves of CTAs (every CTA derives its chain's constants first)
-    const int nb_r = C > 1 ? std::max(1, std::min(nblk, 2 * RED_BLOCKS / (C * ny))) : nblk;
-    k_reduce<<<dim3(nb_r, ny, C), BLOCK, 0, h->stream>>>(a);
-    if (multi) {
-      CommArgs cm;
-      cm.rank = h->comm_rank; cm.world = h->comm_world; cm.nvec = 2 * ny; cm.epoch = ++h->comm_epoch_small;
-      cm.base = (int64_t)2 * h->comm_world * 2 * zz_suffstats_len(h->K) * h->C;      // behind the statistics region
-      cm.stride = 2 * COMM_SMALL_NVEC;
-      for (int r = 0; r < 8; ++r) { cm.inbox[r] = h->peer_inbox[r]; cm.flags[r] = h->peer_flags[r]; }
-      k_reduce_allreduce<<<1, BLOCK, 0, h->stream>>>(h->partials, nb_r, 2, ny, h->red_out, cm, h->nan_flag);
-    } else {
-      k_reduce_final<<<ny * C, BLOCK, 0, h->stream>>>(h->partials, nb_r, 2, h->red_out);
-    }
-    h->launches += 2;
-  };
-  auto commit_vg = [&]() { return launch_eval(h, EVAL_COMMIT_VG, C > 1 ? -1 : 0, nullptr, h->vgprob, &h->devchain->gate_vg); };
-  // gene sums of the level-2 and variance-prior moves: closed forms of the sweep statistics by default; ZZ_CHAIN_GENE_SUMS=1 (or a
-  // finite variance_g_upper_bound, whose plnorm term has no closed form) keeps the reference's per-gene sums (8 extra passes)
-  bool closed = getenv("ZZ_CHAIN_GENE_SUMS") == nullptr;
-  for (int c = 0; c < C; ++c) if (h->hyper_host[c].variance_g_upper_bound != INFINITY) closed = false;
-  if (C > 1 && (multi || h->sink_on)) {
-    h->stats_target = saved_target; h->stats_allreduce = saved_allreduce;
-    return fail(h, ZZ_ERR_INVALID, "zz_run_generations: batched chains run on one GPU and without a sample sink in this round");
+  if (h->hyper_host_stale) {                    // the unsupported-model test below reads the host copy
+    ZZ_CUDA(h, cudaMemcpyAsync(h->hyper_host.data(), h->hyper, sizeof(zz_hyper) * h->C, cudaMemcpyDeviceToHost, h->stream));
+    ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->hyper_host_stale = false;
   }
+  if (const char *why = generations_unsupported(h)) return fail(h, ZZ_ERR_INVALID, std::string("zz_run_generations: ") + why + " — use the host-driven schedule");
+  const int K = h->K, R = h->R, C = h->C;
+  if (C > 1 && h->sink_on) return fail(h, ZZ_ERR_INVALID, "zz_run_generations: the sample sink serves a one-chain handle");
   if (!tune && h->sink_on) {                      // every sample of this call needs a parameter row
     int64_t need = 0;
     for (int i = 0; i < ngen; ++i) need += ((h->chain_gen + i) % sample_frequency == 0);
-    if (h->sink_prow + need > h->sink.param_capacity) {
-      h->stats_target = saved_target; h->stats_allreduce = saved_allreduce;
+    if (h->sink_prow + need > h->sink.param_capacity)
       return fail(h, ZZ_ERR_INVALID, "zz_run_generations: the sample sink has too few parameter rows for this call");
-    }
   }
-  if (!tune && h->chain_samples == 0) {           // M:142-145: the trace starts at the current allocation
+  double *saved_target = h->stats_target;
+  h->stats_target = nullptr;                      // the statistics of a generation are consumed on the device
+  int rc = ZZ_OK;
+  if (!tune && h->chain_samples == 0 && ngen > 0) {   // M:142-145: the trace starts at the current allocation
     k_alloc_trace<<<gene_grid(h, h->G, C), BLOCK, 0, h->stream>>>(h->G, K, h->flags, h->trace);
     h->launches++; h->chain_samples = 1;
   }
-  for (int i = 0; i < ngen && rc == ZZ_OK; ++i) {
-    rc = launch_sweep_fast(h, h->chain_step, tune, ZZ_MOVE_FUSED, no_draws, no_dec, 0, h->G);   // slots 2,3,9,10,11 + statistics
-    if (rc) break;
-    if (!fused_stats) {                           // many chains: the sweep left per-CTA rows, one fixed-order reduction per chain
-      k_reduce_final<<<C, BLOCK, 0, h->stream>>>(h->sw_partials, (int)h->sw_rows, nstat, h->chain_stats);
-      h->launches++;
+  // Segments end at the generations after which something other than the next sweep looks at the per-gene state: a sample
+  // (allocation trace, log rows: M:188-220) or tune_all (B:146).  Everything in between is ONE cooperative launch.
+  int done = 0;
+  while (done < ngen && rc == ZZ_OK) {
+    int len = 0; bool sampled = false, tune_pt = false;
+    while (done + len < ngen) {
+      const int64_t g = h->chain_gen + len;
+      ++len;
+      sampled = !tune && g % sample_frequency == 0;
+      tune_pt = tune && (g + 1) % 400 == 0;
+      if (sampled || tune_pt || len >= 100000) break;
     }
-    if (closed) {
-      // every hyper move except mhP_x from the sweep's sufficient statistics: one single-thread kernel, no pass over the genes
-      stage(ST_ALL_CLOSED, 0, 0, 0);
-      reduce(RED_PXDELTA, 1);
-    } else {
-      stage(ST_BEGIN, 0, 0, 0); reduce(RED_LEVEL2, 2);
-      for (int it = 0; it < K; ++it) { stage(ST_AMD, it, 0, 0); reduce(RED_LEVEL2, 2); }
-      stage(ST_SHARED, 0, 0, 0); reduce(RED_LEVEL2, 2);
-      stage(ST_TAU, 0, 0, 0); reduce(RED_VARG_HYPER, 1);
-      stage(ST_SG, 0, 0, 0); if ((rc = commit_vg())) break; reduce(RED_VARG_HYPER, 1);
-      stage(ST_S0TAU, 0, 0, 0); if ((rc = commit_vg())) break; reduce(RED_VARG_HYPER, 1);
-      stage(ST_PX, 0, 0, 0); if ((rc = commit_vg())) break; reduce(RED_PXDELTA, 1);
+    k_gen_prepare<<<(C + 63) / 64, 64, 0, h->stream>>>(C, R, tune, 1, h->cfg.seed, h->hyper, h->devchain, h->fasth);
+    h->launches++; h->fasth_valid = true;
+    if ((rc = launch_generations(h, h->chain_step, len, tune, 1, 10, tune_pt ? 1 : 0, target))) break;
+    k_apply_dlt<<<gene_grid(h, h->G, C), BLOCK, 0, h->stream>>>(h->G, h->devchain, h->flags, h->dlt, h->lps);
+    h->launches++;
+    h->chain_gen += len; h->chain_step += 10ull * (uint64_t)len; done += len;
+    if (tune_pt) { const int64_t CG = (int64_t)C * h->G; k_tune<<<gene_grid(h, CG), BLOCK, 0, h->stream>>>(CG, target, h->win_y, h->win_v, h->ty, h->tv); h->launches++; }
+    if (sampled) {
+      k_alloc_trace<<<gene_grid(h, h->G, C), BLOCK, 0, h->stream>>>(h->G, K, h->flags, h->trace); h->launches++; h->chain_samples++;
+      if (h->sink_on) {                           // M:202-220: lnl and the log rows of this sample, written by the device
+        const int64_t gen = h->chain_gen - 1;
+        const int nblk = red_blocks(h->G);
+        RedArgs ra; fill_red(h, ra, 0, RED_LNL);
+        ra.partials = h->partials;
+        k_reduce<<<dim3(nblk, 1, 1), BLOCK, 0, h->stream>>>(ra);
+        k_reduce_final<<<1, BLOCK, 0, h->stream>>>(h->partials, nblk, 2, h->red_out);
+        h->launches += 2;
+        const bool yv = h->sink_y && ((gen / sample_frequency) % h->sink.yv_every == 0) && h->sink_yrow < h->sink.yv_capacity;
+        const int plen = zz_param_row_len(R, K);
+        const int64_t nc = h->sink.n_candidates;
+        int64_t nb = yv ? (nc + BLOCK - 1) / BLOCK : 1;
+        if (nb < 1) nb = 1;
+        if (nb > 4 * 148) nb = 4 * 148;
+        k_sample_row<<<(unsigned)nb, BLOCK, 0, h->stream>>>((double)gen, h->hyper, h->red_out, R, K, h->sink_p + h->sink_prow * plen,
+                                                            h->cand_slots, nc, h->Yg, h->vg, h->flags,
+                                                            yv ? h->sink_y + h->sink_yrow * (1 + nc) : nullptr, yv ? h->sink_v + h->sink_yrow * (1 + nc) : nullptr);
+        h->launches++; h->sink_prow++; if (yv) h->sink_yrow++;
+      }
     }
-    const int sampled = (!tune && h->chain_gen % sample_frequency == 0) ? 1 : 0;
-    const int do_tune_all = (tune && (h->chain_gen + 1) % 400 == 0) ? 1 : 0;                    // B:146
-    stage(ST_PX_DECIDE, 0, do_tune_all, sampled);   // decide mhP_x, install alpha_r, counters, tune_all scalars, derived constants (FastH)
-    // The two per-gene caches of the reference are rewritten by the next sweep for every out-of-spike gene (and A(y) / the all-zero
-    // genes by the gated k_refresh_lps below), and the closed-form moves never read them: with closed forms their commits
-    // (Pr:113/147/187, Pr:213-215/219) are only needed after the LAST generation of the call, when the state becomes visible.
-    const bool commit_now = !closed || i == ngen - 1;
-    if (commit_now) {
-      if (R > 2) {                                // Pr:213-215: XgLikelihood += ll(alpha') - ll(alpha) of the one library (both alphas in the mailbox)
-        k_px_commit_dev<<<gene_grid(h, h->G, C), BLOCK, 0, h->stream>>>(h->G, h->devchain, h->Xg, h->gl, h->Yg, h->vg, h->flags, h->hyper, h->xglik);
-        h->launches++;
-      } else if ((rc = launch_eval(h, EVAL_XGLIK, C > 1 ? -1 : 0, h->xglik, nullptr, &h->devchain->gate_px))) break;   // Pr:219: full recompute
-    }
-    if (closed && commit_now && (rc = commit_vg())) break;   // variance_g_probability of the accepted mhTau / mhSg / mhS0Tau, once
-    {                                             // A(y) depends on alpha_r: rebuilt only if mhP_x accepted
-      FastArgs fa;
-      fill_sweep_args(h, fa.s, 0, 0, 0, nullptr, nullptr, 0, h->G);
-      fill_fast_args(h, fa);
-      fa.gate = &h->devchain->gate_px; fa.gate_stride = (int)(sizeof(DevChain) / sizeof(int));
-      fa.want_stats = 1;                          // also the XgLikelihood of all-zero genes, which the spike move reads (Pr:581)
-      ZZ_DISPATCH_R(h, k_refresh_lps, gene_grid(h, h->G, C), fa);
-      h->launches++;
-    }
-    if (sampled) { k_alloc_trace<<<gene_grid(h, h->G, C), BLOCK, 0, h->stream>>>(h->G, K, h->flags, h->trace); h->launches++; h->chain_samples++; }
-    if (sampled && h->sink_on) {                  // M:202-220: lnl and the log rows of this sample, written by the device
-      reduce(RED_LNL, 1);
-      const bool yv = h->sink_y && ((h->chain_gen / sample_frequency) % h->sink.yv_every == 0) && h->sink_yrow < h->sink.yv_capacity;
-      const int plen = zz_param_row_len(R, K);
-      const int64_t nc = h->sink.n_candidates;
-      int64_t nb = yv ? (nc + BLOCK - 1) / BLOCK : 1;
-      if (nb < 1) nb = 1;
-      if (nb > 4 * 148) nb = 4 * 148;
-      k_sample_row<<<(unsigned)nb, BLOCK, 0, h->stream>>>((double)h->chain_gen, h->hyper, h->red_out, R, K, h->sink_p + h->sink_prow * plen,
-                                                          h->cand_slots, nc, h->Yg, h->vg, h->flags,
-                                                          yv ? h->sink_y + h->sink_yrow * (1 + nc) : nullptr, yv ? h->sink_v + h->sink_yrow * (1 + nc) : nullptr);
-      h->launches++; h->sink_prow++; if (yv) h->sink_yrow++;
-    }
-    if (do_tune_all) { const int64_t CG = (int64_t)C * h->G; k_tune<<<gene_grid(h, CG), BLOCK, 0, h->stream>>>(CG, target, h->win_y, h->win_v, h->ty, h->tv); h->launches++; }
-    h->chain_gen += 1; h->chain_step += 10;
   }
-  h->stats_target = saved_target; h->stats_allreduce = saved_allreduce;
+  h->stats_target = saved_target;
   h->stats_fresh = false;
-  if (ngen > 0) h->hyper_host_stale = true;
+  if (ngen > 0) { h->hyper_host_stale = true; h->fasth_valid = true; }
   if (rc) return rc;
   ZZ_CUDA(h, cudaGetLastError());
   return ZZ_OK;
@@ -2265,14 +2379,25 @@ int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, d
 int zz_chain_read(zz_handle *h, zz_chain_scalars *scalars, zz_hyper *hyper) {
   ZZ_CHECK(h);
   if (!h->chain_ready) return fail(h, ZZ_ERR_STATE, "zz_chain_read: call zz_chain_begin first");
+  std::vector<ChainDev> tmp((size_t)h->C);
   ZZ_CUDA(h, cudaMemcpyAsync(h->hyper_host.data(), h->hyper, sizeof(zz_hyper) * h->C, cudaMemcpyDeviceToHost, h->stream));
-  if (scalars)
-    for (int c = 0; c < h->C; ++c)
-      ZZ_CUDA(h, cudaMemcpyAsync(scalars + c, &h->devchain[c].sc, sizeof(zz_chain_scalars), cudaMemcpyDeviceToHost, h->stream));
+  ZZ_CUDA(h, cudaMemcpyAsync(tmp.data(), h->devchain, sizeof(ChainDev) * h->C, cudaMemcpyDeviceToHost, h->stream));
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));   // the host copy of the hyper-parameters is current again
   h->hyper_host_stale = false;
   for (int c = 0; c < h->C; ++c) {
-    if (scalars) scalars[c].n_samples = h->chain_samples;
+    if (scalars) {
+      zz_chain_scalars &sc = scalars[c]; const ChainDev &d = tmp[c];
+      memset(&sc, 0, sizeof sc);
+      memcpy(sc.active_means_dif, d.active_means_dif, sizeof sc.active_means_dif);
+      sc.t_im = d.t_im; sc.t_av = d.t_av; memcpy(sc.t_am, d.t_am, sizeof sc.t_am);
+      sc.t_s0 = d.t_s0; sc.t_s1 = d.t_s1; sc.t_tau = d.t_tau; sc.t_s0tau = d.t_s0tau; memcpy(sc.t_alpha, d.t_alpha, sizeof sc.t_alpha);
+      win_unpack(d.w_im, sc.w_im); win_unpack(d.w_av, sc.w_av); win_unpack(d.w_s0, sc.w_s0); win_unpack(d.w_s1, sc.w_s1);
+      win_unpack(d.w_tau, sc.w_tau); win_unpack(d.w_s0tau, sc.w_s0tau);
+      for (int k = 0; k < ZZ_MAX_COMP; ++k) win_unpack(d.w_am[k], sc.w_am[k]);
+      for (int r = 0; r < ZZ_MAX_LIBS; ++r) win_unpack(d.w_alpha[r], sc.w_alpha[r]);
+      sc.hyper_ctr = d.hyper_ctr; memcpy(sc.hyper_buf, d.hyper_buf, sizeof sc.hyper_buf);
+      sc.step = d.step; sc.gen = d.gen; sc.n_samples = h->chain_samples;
+    }
     if (hyper) hyper[c] = h->hyper_host[c];
   }
   return ZZ_OK;

@@ -1,0 +1,486 @@
+// zz_persist.cuh — k_generations: whole segments of burnin() / mcmc() generations in ONE cooperative launch (SURVEY §8 f1;
+// R/zigzagBurnin.R:64-148, R/zigzagMCMC.R:169-229).  Included by zz_gpu.cu after the sweep kernels (uses their argument structs).
+//
+// Per generation, every persistent CTA (3 per SM, co-resident by cooperative launch):
+//   1. waits until the hyper-parameters of this generation are published, copies the derived constants (FastH) to shared memory;
+//   2. sweeps its 32-gene tiles: mhYg -> mhVariance_g -> allocation Gibbs -> mhSpikeAllocation as one straight-line block per
+//      tile (same arithmetic as k_sweep_fast's production tile), plus the gene's term of the pending mhP_x likelihood ratio
+//      (Pr:209-224) at its final Yg — the separate pass over all genes that move used to need is gone;
+//   3. adds its genes' sufficient statistics to the chain's accumulators.  Statistics are FIXED-POINT integers (Q31.32): integer
+//      addition is associative, so the totals do not depend on which warp took which tile, on the grid size or on the number of
+//      GPUs — results are bit-identical for any sharding, and tiles may be scheduled dynamically;
+//   4. takes a ticket.  The LAST CTA to arrive reads the totals, exchanges them with the other GPUs over NVLink peer memory
+//      (gene shards: same low-latency inbox format as allreduce_exchange, integer payload), runs every hyper-parameter move of the
+//      generation on four of its warps (zz_chain.cuh), derives the next generation's constants and releases the grid.
+// Critical path per generation: sweep + one grid barrier (2 us) + the scalar stage; no launch, no host.
+#pragma once
+
+namespace {
+
+constexpr double FX_SCALE = 4294967296.0;          // statistics carry 32 fraction bits: per-gene rounding 1.2e-10 absolute
+constexpr long long FX_ONE = 1LL << 32;
+__device__ __forceinline__ long long to_fx(double x) { return __double2ll_rn(x * FX_SCALE); }
+
+// slots 7 and 8 of the zz_suffstats layout (sum XgLikelihood, sum variance_g_probability: the two caches this kernel does not
+// maintain) carry the mhP_x gene sum and its count of non-finite terms instead
+constexpr int FXS_PXDELTA = 7, FXS_PXBAD = 8;
+
+// Tiles are handed out dynamically after two static rounds: a 32-gene tile takes a warp ~7 us and the tiles of one sweep differ
+// in cost (the detection loop is skipped where p_x saturates; whether it does depends on the proposed Yg), so with a static
+// assignment the last warp finishes ~20 us after the first — time every CTA would spend at the generation's grid barrier.
+// One shared counter cannot serve 31 250 tickets per 50 us sweep (1.2 ns per same-address atomic, measured: profiles/r2_ubench.txt),
+// so the dynamic tiles are dealt round-robin into GEN_NQ queues with a counter each; a warp drains its home queue, then the others.
+constexpr int GEN_NQ = 16;
+struct GenCtl {                     // one per chain, device memory
+  unsigned arrive;                  // tickets taken (monotone across launches)
+  unsigned release;                 // generations published (monotone); GEN_ABORT = give up (time-out)
+  unsigned long long ns_leader, ns_stage;   // diagnostics (zz_debug_gen_times): time the last CTA spent between its ticket and the release / in the scalar stage
+  unsigned pad_[26];
+  unsigned tile_q[GEN_NQ * 32];     // dynamic tile scheduling: tickets handed out by each tile queue in the current generation, one
+                                    // 128-byte line per counter (same-line atomics serialise in one L2 slice)
+};
+constexpr unsigned GEN_ABORT = 0xFFFFFFFFu;
+
+struct GenArgs {
+  FastArgs fa;                      // arrays, tables, fasth; fa.s.step = step of the first generation's sweep
+  double *dlt;                      // [C][G] per-gene term of the last mhP_x ratio (added to lps when that move was accepted)
+  zz_hyper *hyper; ChainDev *chain; // [C]
+  FastH *fasth_rw;                  // == fa.fasth: the leader writes the next generation's constants
+  GenCtl *ctl; long long *acc;      // [C] (zeroed by the host before every launch), [C][nstat]
+  int ngen, hyper_moves, do_tune_all_last, step_stride; double target;
+  double *stats_out;                // [C][nstat] or NULL: the (all-reduced) statistics of the last generation run, as doubles
+  int do_allreduce; CommArgs cm;    // cm.epoch = epoch of the first generation - 1
+  long long timeout_ns;
+  int dyn_tiles;                    // 0: static tile assignment (warp w: tiles w, w + W, ...); 1: static for two rounds, then from the queues
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// integer all-reduce of `n` 64-bit values over the peer inboxes (see allreduce_exchange): every value travels as two words
+// {half | epoch << 32}; the sum is exact, so the order of the ranks does not matter.  Returns false on time-out.
+__device__ __forceinline__ bool allreduce_exchange_i64(long long *vec /* shared memory, in/out */, int n, const CommArgs &cm, long long timeout_ns) {
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
+  const int slot = (int)(cm.epoch & 1ull), nw = 2 * n;
+  const unsigned ep = (unsigned)cm.epoch;
+  for (int w = threadIdx.x; w < nw; w += blockDim.x) {
+    const unsigned long long v = (unsigned long long)vec[w >> 1];
+    const unsigned half = (w & 1) ? (unsigned)(v >> 32) : (unsigned)v;
+    const unsigned long long word = ((unsigned long long)ep << 32) | half;
+    for (int r = 0; r < cm.world; ++r) {
+      if (r == cm.rank) continue;
+      unsigned long long *dst = reinterpret_cast<unsigned long long *>(cm.inbox[r]) + cm.base + ((int64_t)slot * cm.world + cm.rank) * cm.stride + w;
+      asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+    }
+  }
+  const unsigned long long *in = reinterpret_cast<const unsigned long long *>(cm.inbox[cm.rank]) + cm.base + (int64_t)slot * cm.world * cm.stride;
+  const unsigned long long t0 = globaltimer_ns();
+  long long mine = 0;
+  const int idx = threadIdx.x;
+  if (idx < n) {
+    mine = vec[idx];
+    for (int r = 0; r < cm.world; ++r) {
+      if (r == cm.rank) continue;
+      const volatile unsigned long long *p = in + (int64_t)r * cm.stride + 2 * idx;
+      unsigned long long a = p[0], b = p[1];
+      while ((unsigned)(a >> 32) != ep || (unsigned)(b >> 32) != ep) {
+        if ((long long)(globaltimer_ns() - t0) > timeout_ns) { timed_out = 1; break; }
+        a = p[0]; b = p[1];
+      }
+      mine += (long long)(((b & 0xFFFFFFFFull) << 32) | (a & 0xFFFFFFFFull));
+    }
+  }
+  __syncthreads();
+  if (idx < n) vec[idx] = mine;
+  __syncthreads();
+  return timed_out == 0;
+}
+
+// mhSpikeAllocation (Pr:528-638) for one all-zero, inactive gene of the persistent kernel.  Works on the gene's global-memory
+// state as the main moves stored it.  XgLikelihood is not cached here: for an all-zero gene it is beta * A(y) out of the spike
+// (no detected library: the normal part is empty) and 0 inside (P:117), so the current value comes from `lps`.
+struct SpikeOutP { double y, lv, t; uint32_t f; bool finite_state, moved; };
+template <int RT>
+__device__ __noinline__ void spike_move_p(const FastH &H, const MathTabs &T, const FastArgs &fa, int chain, int64_t g, int64_t i, uint64_t step, SpikeOutP &o) {
+  const SweepArgs &a = fa.s;
+  uint32_t f = a.flags[i];
+  double y = a.Yg[i], v = a.vg[i];
+  o.moved = false; o.t = 0;
+  if (!(f & F_ACTIVE)) {                                              // Pr:533: all-zero AND inactive
+    const bool cur_in = (f & F_INSPIKE) != 0, prop_in = !cur_in;      // Pr:535
+    uint32_t b2[4];
+    double zy, zv;
+    philox_block(a.seed, chain, step, 2, (uint64_t)(a.gene_offset + a.perm[g]), b2);
+    box_muller(u32_open(b2[0]), u32_open(b2[1]), zy, zv);
+    const double u = u32_open(b2[2]);
+    const double yp = fma(H.sd_i, zy, H.im);                          // Pr:545
+    const double lsp = fma(H.s1, yp, H.s0);                           // log(Sg_proposed), Pr:547
+    const double lvp = (lsp + H.tau) + H.rtau * zv;                   // Pr:549: variance_g' = exp(.)
+    const double vp = fexp(lvp, T.exp_t);
+    const double PVp = vg_prior_from_q(H, lvp, vg_q(H, lvp, yp));     // Pr:556
+    const double lv = flog(v, T.log_t);
+    const double PVc = vg_prior_from_q(H, lv, vg_q(H, lv, y));        // Pr:558
+    const double dp = yp - H.im, dc = y - H.im;
+    const double pygp = prop_in ? H.log_sp : H.log_1msp - H.log_norm_i - dp * dp * H.inv2iv;   // Pr:560
+    const double pyg = cur_in ? H.log_sp : H.log_1msp - H.log_norm_i - dc * dc * H.inv2iv;     // Pr:563
+    const double pp = prop_in ? H.log_sp : (pygp + PVp);              // Pr:569-570
+    const double pc = cur_in ? H.log_sp : (pyg + PVc);                // Pr:572-573
+    double Ap = 0, tp = 0;
+    if (!prop_in) { tp = a.gl[g] * fexp(yp, T.exp_t); Ap = detect_logsum<RT>(H, T, ~0ull, tp); }
+    double Lp = prop_in ? 0.0 : times_beta(H, Ap);                    // Pr:579 (P:117 gives log(1*1) = 0 in the spike)
+    double Lc = cur_in ? 0.0 : times_beta(H, fa.lps[i]);              // Pr:581: the cache, re-derived
+    if (Lp == -INFINITY && Lc == -INFINITY) { Lp = 0; Lc = 0; }       // Pr:583-585
+    const double HR = prop_in ? (pyg - H.log_1msp + PVc) : -(pygp - H.log_1msp + PVp);   // Pr:592-595
+    const double ratio = H.temp * (Lp - Lc + pp - pc) + HR;           // Pr:601
+    const int acc_s = (flog_core(u, T.log_t) < ratio);                // Pr:605
+    if (isnan(ratio)) atomicOr(a.nan_flag, 1);
+    if (acc_s) {
+      f ^= F_INSPIKE;                                                 // Pr:616
+      a.flags[i] = (uint16_t)f;
+      if (!prop_in) { y = yp; v = vp; a.Yg[i] = yp; a.vg[i] = vp; fa.lps[i] = Ap; o.moved = true; o.t = tp; }   // Pr:620-636
+    }
+  }
+  o.y = y; o.lv = (f & F_INSPIKE) ? 0.0 : flog(v, T.log_t); o.f = f;
+  o.finite_state = isfinite(y) && isfinite(v);
+}
+
+template <int RT, int KT>
+__global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(const __grid_constant__ GenArgs ga) {
+  __shared__ FastH H;
+  __shared__ MathTabs T;
+  __shared__ unsigned sh_rel, sh_ticket;
+  extern __shared__ double dyn_smem[];                 // [nstat][BLOCK] int64 statistic columns, then [8 warps][10][32] staging
+  const FastArgs &fa = ga.fa;
+  const SweepArgs &a = fa.s;
+  const int chain = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int K1 = a.K + 1, nstat = 3 * K1 + NSTAT_FIXED_;
+  long long *acc = reinterpret_cast<long long *>(dyn_smem);
+  GenCtl *ctl = ga.ctl + chain;
+  long long *gacc = ga.acc + (int64_t)chain * nstat;
+  for (int s = 0; s < nstat; ++s) acc[s * SWEEP_BLOCK + threadIdx.x] = 0;
+  load_tabs(T, fa.exp_tab, fa.log_tab);
+  const int ntiles = (int)((a.g_end - a.g_begin + 31) / 32);
+  const int warp0 = (int)blockIdx.x * (SWEEP_BLOCK / 32) + wid, nwarps = (int)gridDim.x * (SWEEP_BLOCK / 32);
+  double *stg = dyn_smem + (int64_t)nstat * SWEEP_BLOCK + wid * 320 + lane;
+  bool saw_nan = false;
+  const unsigned n_cta = gridDim.x;
+
+  for (int gi = 0; gi < ga.ngen; ++gi) {
+    const unsigned gen_no = (unsigned)gi;
+    // ---- 1. this generation's hyper-parameters are published once release >= gen_no
+    if (threadIdx.x == 0) {
+      unsigned r = ld_acquire_u32(&ctl->release);
+      if (r < gen_no) {
+        const unsigned long long t0 = globaltimer_ns();
+        while ((r = ld_acquire_u32(&ctl->release)) < gen_no) {
+          if ((long long)(globaltimer_ns() - t0) > ga.timeout_ns) { r = GEN_ABORT; break; }
+          __nanosleep(40);
+        }
+      }
+      sh_rel = r;
+    }
+    __syncthreads();
+    if (sh_rel == GEN_ABORT) break;
+    {   // FastH was written by another SM: read it through L2
+      const uint64_t *src = reinterpret_cast<const uint64_t *>(fa.fasth + chain);
+      uint64_t *dst = reinterpret_cast<uint64_t *>(&H);
+      for (int j = threadIdx.x; j < (int)(sizeof(FastH) / 8); j += blockDim.x) dst[j] = __ldcg(src + j);
+      __syncthreads();
+    }
+    const uint64_t step = a.step + (uint64_t)ga.step_stride * (uint64_t)gi;
+    const bool px_on = H.px_on != 0;
+
+    // ---- 2. the sweep: tiles are taken from the END of the sorted gene order first (the all-zero genes with their extra move and
+    // the weakly expressed genes with the full detection loop run while every warp is busy)
+    uint32_t f_next = 0;
+    const int n_static = 2 * nwarps, n_dyn = ntiles > n_static ? ntiles - n_static : 0;
+    int tq = warp0 % GEN_NQ, tq_tries = 0;
+    int t_ = warp0 < ntiles ? warp0 : -1;
+    int t_n = (t_ >= 0 && warp0 + nwarps < ntiles) ? warp0 + nwarps : -1;
+    unsigned ticket = 0;
+    if (t_ >= 0) {
+      const int64_t g0 = a.g_begin + (int64_t)(ntiles - 1 - t_) * 32 + lane;
+      if (g0 < a.g_end) { stage_tile(a, fa, chain, g0, stg); f_next = a.flags[(int64_t)chain * a.G + g0]; }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    while (t_ >= 0) {
+      const int64_t g = a.g_begin + (int64_t)(ntiles - 1 - t_) * 32 + lane;
+      const int64_t i = (int64_t)chain * a.G + g;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");            // this lane's copies of the current tile have landed
+      const bool valid = g < a.g_end;                                  // only the last (first processed) tile can be ragged
+      const double y0 = stg[0 * 32], v0 = stg[1 * 32], ty = stg[3 * 32], tv = stg[4 * 32], gl = stg[5 * 32];
+      double A0 = stg[2 * 32];
+      const double xbar = stg[6 * 32], ss = stg[7 * 32];
+      const uint64_t mask = (uint64_t)__double_as_longlong(stg[8 * 32]);
+      const uint64_t gid = (uint64_t)(a.gene_offset + (int64_t)(uint32_t)__double2loint(stg[9 * 32]));
+      uint32_t f = f_next;
+      const int64_t g_n = a.g_begin + (int64_t)(ntiles - 1 - t_n) * 32 + lane;
+      const bool next_valid = t_n >= 0 && g_n < a.g_end;
+      if (next_valid) {                                                 // consumed one tile later (pinned here: volatile asm)
+        unsigned short fw;
+        asm volatile("ld.global.u16 %0, [%1];" : "=h"(fw) : "l"(a.flags + (int64_t)chain * a.G + g_n) : "memory");
+        f_next = fw;
+      }
+      // every staged word of this tile is in registers: refill the slots with the warp's next tile, whose HBM latency then hides
+      // behind this tile's ~1300 instructions (also for the lanes beyond the end of a ragged tile: their next tile is a full one)
+      if (next_valid) stage_tile(a, fa, chain, g_n, stg);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      // the tile after the next one: ask the home queue now, read the answer when this tile is done
+      // (inline asm: the compiler would otherwise sink the atomic down to the shuffle that reads it and expose its whole latency)
+      const bool asked = ga.dyn_tiles && t_n >= 0 && n_dyn > 0 && tq_tries < GEN_NQ;
+      if (asked && lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(&ctl->tile_q[tq * 32]) : "memory");
+      if (valid) {
+      const double nd_d = (double)((RT > 0 ? RT : H.R) - __popcll(mask));
+      const bool live = !(f & F_INSPIKE);
+      if (H.px_prev_acc && live) A0 += ga.dlt[i];                       // the accepted alpha_r of the previous generation (Pr:213-215, as an increment)
+      uint32_t b0[4], b1[4];
+      philox_block(a.seed, chain, step, 0, gid, b0);
+      philox_block(a.seed, chain, step, 1, gid, b1);
+      const double u_y = u32_to_open01(b0[2]), u1 = u32_to_open01(b0[3]), u2 = u32_to_open01(b1[0]);
+      const double u_ai = u32_to_open01(b1[1]), u_w = u32_to_open01(b1[2]);
+      const double z = fsqrt_nb(-2.0 * flog_nb(u32_to_open01(b0[0]), T.log_t)) * cospi(2.0 * u32_to_open01(b0[1]));
+      const double lv = flog_nb(v0, T.log_t), rv = frcp_nb(v0);
+      const bool bad = !is_pos_normal(v0);                              // poisoned state: reported through the NaN flag
+      // ---- mhYg (Pr:250-333)
+      const double yp = y0 + ty * z;                                     // Pr:257
+      const double tp = gl * fexp_nb(yp, T.exp_t);                       // U:157
+      const bool saturated = __all_sync(__activemask(), !live || tp * H.alpha_min >= 37.5);
+      const double Ap = saturated ? (mask ? -INFINITY : 0.0)
+                        : (RT > 0 && H.uclamp_ok) ? detect_logsum_sl<(RT > 0 && RT <= 18) ? RT : 1>(H, T, mask, tp) : detect_logsum_slow<RT>(H, T, mask, tp);
+      const double t0 = xbar - y0, t1 = xbar - yp;
+      const double D0 = fma(nd_d * t0, t0, ss), Dp = fma(nd_d * t1, t1, ss);
+      const double dLX = times_beta(H, (Ap - A0) - 0.5 * (Dp - D0) * rv);
+      const double q0 = vg_q(H, lv, y0), qp = vg_q(H, lv, yp);
+      const double dPV = -0.5 * (qp * qp - q0 * q0);
+      const bool act0 = (f & F_ACTIVE) != 0;
+      const int k0 = flag_k(f) - 1;
+      const double m2 = act0 ? H.am[k0] : H.im, i2 = act0 ? H.inv2av[k0] : H.inv2iv;
+      const double e0 = y0 - m2, e1 = yp - m2;
+      const double dL2 = -(e1 * e1 * i2 - e0 * e0 * i2);
+      const double ratio_y = H.temp * (dLX + dL2 + dPV);                 // Pr:296
+      const bool acc_y = live && (flog_nb(u_y, T.log_t) < ratio_y);      // Pr:302
+      const double y1 = acc_y ? yp : y0, A1 = acc_y ? Ap : A0, D1 = acc_y ? Dp : D0, q1 = acc_y ? qp : q0;
+      // ---- mhVariance_g (Pr:7-56)
+      const double arg = tv * (u1 - 0.5);                                // MP:5
+      const double sf = fexp_nb(arg, T.exp_t), vp = v0 * sf, rvp = rv * fexp_nb(-arg, T.exp_t);
+      const double dB = -nd_d * (0.5 * arg) - 0.5 * D1 * (rvp - rv);
+      const double qv = q1 + arg * H.irt;
+      double ratio_v = H.temp * (times_beta(H, dB) + (-arg - 0.5 * (qv * qv - q1 * q1))) + arg;   // Pr:24
+      if (!(A1 > -INFINITY) && H.beta != 0.0) ratio_v = NAN;             // -Inf current likelihood: as the reference, NaN => reject
+      const bool acc_v = live && (flog_nb(u2, T.log_t) < ratio_v);       // Pr:35
+      const double v1 = acc_v ? vp : v0, lv1 = acc_v ? lv + arg : lv;
+      // ---- gibbsAllocationActiveInactive + WithinActive (Pr:335-410)
+      const double dI = y1 - H.im;
+      const double L0 = live ? H.c0 * fexp_nb(-(dI * dI) * H.inv2iv, T.exp_t) : H.sp;
+      double Lk[KT], L1 = 0;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) { const double d = y1 - H.am[k]; Lk[k] = H.ck[k] * fexp_nb(-(d * d) * H.inv2av[k], T.exp_t); L1 += Lk[k]; }
+      const double num = live ? H.wa * L1 : 0.0, den = H.one_m_wa * L0 + num;
+      double pa = num * frcp_nb(den);                                    // Pr:348
+      if (!is_pos_normal(den)) { pa = num / den; if (isnan(pa)) pa = H.wa; }   // Pr:349 (rare)
+      const bool a_new = (f & F_PINNED) || (u_ai < pa);                  // Pr:353-355
+      const double thr = u_w * L1;
+      double cum = 0; int cnt = 0;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) { cum += Lk[k]; cnt += (cum < thr); } // Pr:398-402
+      const int kn = cnt + 1 > KT ? KT : cnt + 1;
+      const bool row_ok = L1 > 0 && L1 < INFINITY;                       // NaN rows keep the old k, Pr:403
+      f = (f & ~F_ACTIVE) | (a_new ? F_ACTIVE : 0u);
+      if (a_new && row_ok) f = flag_set_k(f, kn);
+      // ---- stores (the two likelihood caches of the reference are not maintained inside a device-resident segment)
+      a.flags[i] = (uint16_t)f;
+      if (live) { a.Yg[i] = y1; a.vg[i] = v1; fa.lps[i] = A1; }
+      if (a.tune && live) {                                              // Pr:312-322, Pr:40-50
+        ulonglong2 w = a.win_y[i]; window_push(w, acc_y); a.win_y[i] = w;
+        w = a.win_v[i]; window_push(w, acc_v); a.win_v[i] = w;
+      }
+      saw_nan |= live && (isnan(ratio_y) || isnan(ratio_v) || bad);
+      double ys = y1, lvs = lv1;
+      bool finite_state = isfinite(y1) && isfinite(v1);
+      bool live_f = live;
+      double t_fin = tp; bool t_known = acc_y;                           // gl * exp(final Yg), known when the proposal was accepted
+      if ((f & F_ALLZERO) && fa.do_spike_move) {
+        SpikeOutP so;
+        spike_move_p<RT>(H, T, fa, chain, g, i, step, so);
+        ys = so.y; lvs = so.lv; f = so.f; finite_state = so.finite_state; live_f = !(f & F_INSPIKE);
+        if (so.moved) { t_fin = so.t; t_known = true; }
+      }
+      // ---- the gene's term of the pending mhP_x ratio: log q(alpha') - log q(alpha) of library px_lib at the final Yg (Pr:209-224)
+      double pxd = 0; bool pxbad = false;
+      if (px_on) {
+        if (__any_sync(__activemask(), live_f && !t_known)) { const double tc = gl * fexp_nb(ys, T.exp_t); if (!t_known) t_fin = tc; }
+        const bool px_sat = __all_sync(__activemask(), !live_f || t_fin * H.px_amin >= 37.5);
+        const bool nd_lib = (((uint32_t)mask >> H.px_lib) & 1u) != 0;
+        double d = 0;
+        if (!px_sat) {
+          const double tc = fmin(t_fin, H.t_clamp_px);
+          const double qn = det_q(tc, H.px_am256, nd_lib, T), qc = det_q(tc, H.am256[H.px_lib], nd_lib, T);
+          d = det_log_product(qn, T.log_t) - det_log_product(qc, T.log_t);
+        } else if (nd_lib) d = NAN;                                      // log(0) - log(0): a state the chain cannot be in
+        if (live_f) {
+          if (H.beta == 0.0) d = 0;                                      // P:121-125
+          pxbad = !isfinite(d);
+          if (pxbad) d = 0;
+          pxd = H.beta * d;
+          ga.dlt[i] = d;                                                 // the increment of A(y) if the move is accepted
+        }
+      }
+      // ---- sufficient statistics, fixed point
+      {
+        long long *col = acc + threadIdx.x;
+        const bool act = f & F_ACTIVE, sp = f & F_INSPIKE;
+        const int comp = act ? flag_k(f) : 0;                               // Pr:415 all_allocations
+        const long long fy = to_fx(ys), fy2 = to_fx(ys * ys);
+        col[comp * SWEEP_BLOCK] += FX_ONE;
+        if (act || !sp) { col[(K1 + comp) * SWEEP_BLOCK] += fy; col[(2 * K1 + comp) * SWEEP_BLOCK] += fy2; }
+        long long *q = col + 3 * K1 * SWEEP_BLOCK;
+        if (sp) q[0] += FX_ONE;
+        else {
+          q[1 * SWEEP_BLOCK] += FX_ONE; q[2 * SWEEP_BLOCK] += to_fx(lvs); q[3 * SWEEP_BLOCK] += to_fx(lvs * lvs); q[4 * SWEEP_BLOCK] += fy;
+          q[5 * SWEEP_BLOCK] += fy2; q[6 * SWEEP_BLOCK] += to_fx(ys * lvs);
+          if (px_on) q[FXS_PXDELTA * SWEEP_BLOCK] += to_fx(pxd);
+        }
+        if (pxbad) q[FXS_PXBAD * SWEEP_BLOCK] += FX_ONE;
+        if (!finite_state) q[9 * SWEEP_BLOCK] += FX_ONE;
+      }
+      }   // valid
+      int t_nn = -1;
+      if (asked) {
+        unsigned tk = __shfl_sync(0xffffffffu, ticket, 0);
+        for (;;) {
+          const int cnt = n_dyn > tq ? (n_dyn - tq + GEN_NQ - 1) / GEN_NQ : 0;           // tiles in queue tq
+          if (tk < (unsigned)cnt) { t_nn = n_static + tq + GEN_NQ * (int)tk; break; }
+          tq = (tq + 1) % GEN_NQ;                                                        // exhausted: steal from the next queue
+          if (++tq_tries >= GEN_NQ) break;
+          if (lane == 0) ticket = atomicAdd(&ctl->tile_q[tq * 32], 1u);
+          tk = __shfl_sync(0xffffffffu, ticket, 0);
+        }
+      } else if (!ga.dyn_tiles && t_n >= 0 && t_n + nwarps < ntiles) t_nn = t_n + nwarps;
+      t_ = t_n; t_n = t_nn;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+    // ---- 3. the CTA's column sums -> the chain's accumulators (integer atomics: order-free)
+    __syncthreads();
+    for (int s = wid; s < nstat; s += SWEEP_BLOCK / 32) {
+      long long v = 0;
+#pragma unroll
+      for (int j = 0; j < SWEEP_BLOCK / 32; ++j) { v += acc[s * SWEEP_BLOCK + j * 32 + lane]; acc[s * SWEEP_BLOCK + j * 32 + lane] = 0; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && v != 0) atomicAdd(reinterpret_cast<unsigned long long *>(gacc + s), (unsigned long long)v);
+    }
+    __threadfence();
+    __syncthreads();
+    // ---- 4. ticket; the last CTA of the chain runs the scalar half of the generation
+    if (threadIdx.x == 0) sh_ticket = atomicAdd(&ctl->arrive, 1u);
+    __syncthreads();
+    if (sh_ticket != (gen_no + 1u) * n_cta - 1u) continue;
+    __threadfence();
+    const unsigned long long t_lead0 = globaltimer_ns();
+    unsigned long long t_stage0 = t_lead0;
+    {
+      // the statistic columns are zero again: that memory is the stage's scratch (zeroed again below)
+      char *scr = reinterpret_cast<char *>(dyn_smem);
+      long long *ivec = reinterpret_cast<long long *>(scr);                          // [nstat] totals, fixed point
+      double *st = reinterpret_cast<double *>(scr + 512);                            // [nstat] the totals as doubles
+      double *gam = reinterpret_cast<double *>(scr + 1024);                          // [K + 3] gamma draws
+      double *vg_s = reinterpret_cast<double *>(scr + 1152);                         // (s0, s1, tau) after warp 2
+      int *acc_s = reinterpret_cast<int *>(scr + 1184);                              // accept bits of warp 2 / warp 3
+      L2Params &l2_s = *reinterpret_cast<L2Params *>(scr + 1280);
+      zz_hyper &h_s = *reinterpret_cast<zz_hyper *>(scr + 1536);
+      ChainDev &c_s = *reinterpret_cast<ChainDev *>(scr + 2560);
+      constexpr int MD_OFF = (2560 + (int)sizeof(ChainDev) + 127) / 128 * 128;
+      MoveDraws *md_s = reinterpret_cast<MoveDraws *>(scr + MD_OFF);                 // [MD_MAX] the prepared draws of the Metropolis moves
+      constexpr int SCR_BYTES = MD_OFF + MD_MAX * (int)sizeof(MoveDraws);
+      static_assert(MAX_NSTAT_ * 8 <= 512 && sizeof(L2Params) <= 256 && sizeof(zz_hyper) <= 1024, "stage scratch layout");
+      static_assert(SCR_BYTES <= 8 * SWEEP_BLOCK * 3, "the scratch must fit in the first statistic columns");
+      if ((int)threadIdx.x < nstat) { ivec[threadIdx.x] = (long long)__ldcg(reinterpret_cast<const unsigned long long *>(gacc + threadIdx.x)); gacc[threadIdx.x] = 0; }
+      if (threadIdx.x < GEN_NQ) ctl->tile_q[threadIdx.x * 32] = 0;
+      __syncthreads();
+      bool ok = true;
+      if (ga.do_allreduce) {
+        CommArgs cm = ga.cm;
+        cm.epoch += (unsigned long long)gi + 1ull;
+        cm.base += (int64_t)chain * 2 * cm.world * cm.stride;
+        ok = allreduce_exchange_i64(ivec, nstat, cm, ga.timeout_ns);
+      }
+      if ((int)threadIdx.x < nstat) {
+        st[threadIdx.x] = ok ? (double)ivec[threadIdx.x] * (1.0 / FX_SCALE) : NAN;
+        if (ga.stats_out) ga.stats_out[(int64_t)chain * nstat + threadIdx.x] = st[threadIdx.x];
+      }
+      if (!ok) {                                            // a peer never showed up: fail-stop (flag bit 2), nobody consumes the stale words
+        if (threadIdx.x == 0) { atomicOr(a.nan_flag, 4); __threadfence(); st_release_u32(&ctl->release, GEN_ABORT); }
+        break;
+      }
+      t_stage0 = globaltimer_ns();
+      if (ga.hyper_moves) {
+        static_assert(sizeof(ChainDev) % 8 == 0 && sizeof(zz_hyper) % 8 == 0, "copied as 64-bit words");
+        {
+          const uint64_t *s0 = reinterpret_cast<const uint64_t *>(ga.chain + chain), *s1 = reinterpret_cast<const uint64_t *>(ga.hyper + chain);
+          uint64_t *d0 = reinterpret_cast<uint64_t *>(&c_s), *d1 = reinterpret_cast<uint64_t *>(&h_s);
+          for (int j = threadIdx.x; j < (int)(sizeof(ChainDev) / 8); j += blockDim.x) d0[j] = __ldcg(s0 + j);   // written by another SM
+          for (int j = threadIdx.x; j < (int)(sizeof(zz_hyper) / 8); j += blockDim.x) d1[j] = __ldcg(s1 + j);
+        }
+        __syncthreads();
+        const int K = a.K, R = a.R, tune = a.tune;
+        const bool last = gi == ga.ngen - 1;
+        const SMath sm{&T};
+        // phase A: every random draw of the generation, one lane per draw
+        if (wid == 0) {
+          stage_gibbs_draws(sm, c_s, h_s, a.seed, step, st, K, lane, gam);
+          __syncwarp();
+          if (lane == 0) stage_gibbs_combine(h_s, K, gam);
+        } else if (wid == 4 && lane < MD_AMD + K) make_move_draws(sm, md_s[lane], a.seed, (uint32_t)c_s.chain, step, lane);
+        __syncthreads();
+        // phase B: the three chains of moves side by side
+        if (wid == 1 && lane == 0) stage_level2(sm, c_s, h_s, md_s, st, K, tune, l2_s);
+        else if (wid == 2 && lane == 0) stage_varg(sm, c_s, h_s, md_s, st, K, tune, vg_s[0], vg_s[1], vg_s[2]);
+        else if (wid == 3 && lane == 0) acc_s[1] = px_decide(c_s, h_s, a.seed, step, st[3 * K1 + FXS_PXDELTA], st[3 * K1 + FXS_PXBAD], tune);
+        __syncthreads();
+        // every group worked on fields of its own (warp 0: weights and spike probability in h_s; warps 1, 2: private copies): install
+        if (threadIdx.x == 0) {
+          h_s.inactive_means = l2_s.im; h_s.inactive_variances = l2_s.iv;
+          for (int k = 0; k < K; ++k) { h_s.active_means[k] = l2_s.am[k]; h_s.active_variances[k] = l2_s.av[k]; }
+          h_s.s0 = vg_s[0]; h_s.s1 = vg_s[1]; h_s.tau = vg_s[2];
+          if (acc_s[1]) h_s.alpha_r[c_s.px_lib] = c_s.px_alpha;         // Pr:234-239
+          c_s.px_prev_acc = acc_s[1];
+          c_s.step += (uint64_t)ga.step_stride; c_s.gen += 1;
+          c_s.px_valid = 0;
+        }
+        __syncthreads();
+        if (last && ga.do_tune_all_last)                                 // B:146 tune_all, scalar part (the per-gene part follows the launch)
+          for (int l = threadIdx.x; l < R + K + 6; l += blockDim.x) tune_all_scalars(c_s, ga.target, K, R, l);
+        // the next generation's constants, one group of fields per thread, while warp 3 proposes its mhP_x (after a segment: k_gen_prepare)
+        FastH &F = ga.fasth_rw[chain];
+        if (wid != 3) derive_fast_par(F, &h_s, threadIdx.x < 96 ? threadIdx.x : threadIdx.x + 1000);
+        else if (lane == 0 && !last) px_propose(c_s, h_s, a.seed, step + (uint64_t)ga.step_stride, tune, R);
+        __syncthreads();
+        if (threadIdx.x == 0) { derive_fin(F, &h_s); set_px(F, h_s, c_s); }
+        __syncthreads();
+        {
+          uint64_t *d0 = reinterpret_cast<uint64_t *>(ga.chain + chain), *d1 = reinterpret_cast<uint64_t *>(ga.hyper + chain);
+          const uint64_t *s0 = reinterpret_cast<const uint64_t *>(&c_s), *s1 = reinterpret_cast<const uint64_t *>(&h_s);
+          for (int j = threadIdx.x; j < (int)(sizeof(ChainDev) / 8); j += blockDim.x) d0[j] = s0[j];
+          for (int j = threadIdx.x; j < (int)(sizeof(zz_hyper) / 8); j += blockDim.x) d1[j] = s1[j];
+        }
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned long long t1 = globaltimer_ns();
+        ctl->ns_leader += t1 - t_lead0; ctl->ns_stage += t1 - t_stage0;
+        st_release_u32(&ctl->release, gen_no + 1u);
+      }
+      // the columns this CTA borrowed must be zero again before its next tile
+      for (int j = threadIdx.x; j < (SCR_BYTES + 7) / 8; j += blockDim.x) dyn_smem[j] = 0.0;
+      __syncthreads();
+    }
+  }
+  if (saw_nan) atomicOr(a.nan_flag, 1);
+}
+
+}  // namespace
