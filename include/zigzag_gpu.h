@@ -230,7 +230,7 @@ int zz_run_generations(zz_handle *h, int ngen, int tune, int sample_frequency, d
    — all-reduced over the ranks once zz_comm_connect is done — are left in the buffer of zz_set_stats_output_dev, if any
    (zz_suffstats layout, except that entries 3(K+1)+7 and +8, the sums of the two likelihood caches, are 0 here).  Asynchronous. */
 int zz_run_sweeps(zz_handle *h, uint64_t step, int nsweeps, int tune);
-int zz_debug_gen_times(zz_handle *h, double *out2);   /* diagnostic: ns the releasing CTA spent in the last device-resident launch {ticket -> release, scalar stage} */
+int zz_debug_gen_times(zz_handle *h, double *out8);   /* diagnostic: ns the releasing CTA spent in the last device-resident launch {ticket -> release, scalar stage, 6 phases of the stage} */
 /* waits for the device, returns the scalar state and the hyper-parameters of every chain ([num_chains] each; either may be NULL) */
 int zz_chain_read(zz_handle *h, zz_chain_scalars *scalars, zz_hyper *hyper);
 

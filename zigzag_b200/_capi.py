@@ -462,7 +462,7 @@ class Handle:
         self._ck(self.L.zz_run_sweeps(self.h, int(step), int(nsweeps), int(tune)))
 
     def debug_gen_times(self):
-        out = np.zeros(2)
+        out = np.zeros(8)
         self._ck(self.L.zz_debug_gen_times(self.h, _ptr(out)))
         return out
 

@@ -99,7 +99,7 @@ __device__ inline double gamma_slot(const SMath &m, uint64_t seed, uint32_t chai
     double v = 1 + cc * x;
     if (v <= 0) continue;
     v = v * v * v;
-    if (m.log(u32_open(o[2])) < 0.5 * x * x + d - d * v + d * m.log(v)) return d * v / rate * boost;
+    if (m.log(u32_open(o[2])) < 0.5 * x * x + d - d * v + d * m.log(v)) return rate == 1.0 ? d * v * boost : d * v / rate * boost;
   }
   return d / rate * boost;
 }
@@ -131,31 +131,39 @@ __device__ inline void l2_current(L2Params &p, const zz_hyper &h, int K) {
   p.im = h.inactive_means; p.iv = h.inactive_variances;
   for (int k = 0; k < K; ++k) { p.am[k] = h.active_means[k]; p.av[k] = h.active_variances[k]; }
 }
-// r[0] = inactive part, r[1] = active part of (sum at p) - (sum at c)
-__device__ inline void closed_level2_diff(const SMath &m, const double *st, int K, const L2Params &p, const L2Params &c, double *r) {
+// A single lane pays ~25 dependent FP64 instructions (0.12 us) per division: the moves carry the reciprocals 1 / (2 variance) of the
+// CURRENT parameters along (RcpL2, refreshed when a variance is accepted) and divide only for a proposed variance.
+struct RcpL2 { double iv, av[ZZ_MAX_COMP]; };           // 1 / (2 inactive_variances), 1 / (2 active_variances[k])
+// inactive part of (sum at p) - (sum at c): computeInactiveLikelihood over the inactive genes (P:210-238)
+__device__ inline double closed_inactive_diff(const SMath &m, const double *st, int K, double imp, double ivp, double rivp, double imc, double ivc, double rivc) {
   const int K1 = K + 1;
   const double n0out = st[0] - st[3 * K1];
-  const double qp = st[2 * K1] - 2 * p.im * st[K1] + n0out * p.im * p.im, qc = st[2 * K1] - 2 * c.im * st[K1] + n0out * c.im * c.im;
-  double li = -(qp / (2 * p.iv) - qc / (2 * c.iv));
-  const double ldi = (p.iv != c.iv) ? m.log(p.iv) - m.log(c.iv) : 0.0;
-  li += -0.5 * n0out * ldi;
+  const double qp = st[2 * K1] - 2 * imp * st[K1] + n0out * imp * imp, qc = st[2 * K1] - 2 * imc * st[K1] + n0out * imc * imc;
+  double li = -(qp * rivp - qc * rivc);
+  if (ivp != ivc) li += -0.5 * n0out * (m.log(ivp) - m.log(ivc));
+  return li;
+}
+// active part: computeActiveLikelihood over the active genes (P:240-273); `ldv` = log(vp) - log(vc) when every component shares them
+template <int K>
+__device__ inline double closed_active_diff(const double *st, const double *amp, const double *rvp, const double *amc, const double *rvc, double ldv) {
+  constexpr int K1 = K + 1;
   double la = 0;
+#pragma unroll
   for (int k = 1; k <= K; ++k) {
     const double n = st[k], sy = st[K1 + k], sy2 = st[2 * K1 + k];
-    const double ap = p.am[k - 1], ac = c.am[k - 1], vp = p.av[k - 1], vc = c.av[k - 1];
-    la += -((sy2 - 2 * ap * sy + n * ap * ap) / (2 * vp) - (sy2 - 2 * ac * sy + n * ac * ac) / (2 * vc));
-    if (vp != vc) la += -0.5 * n * ((vp == p.iv && vc == c.iv) ? ldi : m.log(vp) - m.log(vc));   // shared variance: one pair of logarithms
+    const double ap = amp[k - 1], ac = amc[k - 1];
+    la += -((sy2 - 2 * ap * sy + n * ap * ap) * rvp[k - 1] - (sy2 - 2 * ac * sy + n * ac * ac) * rvc[k - 1]) - 0.5 * n * ldv;
   }
-  r[0] = li; r[1] = la;
+  return la;
 }
-// (sum of computeVarianceGPriorProbability at (s0p, s1p, taup)) - (the same at (s0, s1, tau))
-__device__ inline double closed_varg_diff(const SMath &m, const double *st, int K, double s0p, double s1p, double taup, double s0, double s1, double tau) {
+// (sum of computeVarianceGPriorProbability at (s0p, s1p, taup)) - (the same at (s0, s1, tau)); rtp = 1 / (2 taup), rt = 1 / (2 tau)
+__device__ inline double closed_varg_diff(const SMath &m, const double *st, int K, double s0p, double s1p, double taup, double rtp, double s0, double s1, double tau, double rt) {
   const double *fx = st + 3 * (K + 1);
   const double n = fx[1], sz = fx[2], sz2 = fx[3], syo = fx[4], sy2o = fx[5], syz = fx[6];
   const double cp = s0p + taup, cc = s0 + tau;
   const double qp = sz2 + n * cp * cp + s1p * s1p * sy2o - 2 * cp * sz - 2 * s1p * syz + 2 * cp * s1p * syo;
   const double qc = sz2 + n * cc * cc + s1 * s1 * sy2o - 2 * cc * sz - 2 * s1 * syz + 2 * cc * s1 * syo;
-  double d = -(qp / (2 * taup) - qc / (2 * tau));
+  double d = -(qp * rtp - qc * rt);
   if (taup != tau) d += -0.5 * n * (m.log(taup) - m.log(tau));           // -n log(sqrt(tau) sqrt(2 pi)), P:20
   return d;
 }
@@ -180,82 +188,105 @@ __device__ inline void stage_gibbs_draws(const SMath &m, const ChainDev &c, cons
   g[lane] = gamma_slot(m, seed, (uint32_t)c.chain, step, slot, shape, 1.0);
 }
 __device__ inline void stage_gibbs_combine(zz_hyper &h, int K, const double *g) {
-  double tot = 0;
+  double tot = 0, act = 0;
   for (int k = 0; k <= K; ++k) tot += g[k];
-  const double nw0 = g[0] / tot;
+  for (int k = 1; k <= K; ++k) act += g[k];
+  const double nw0 = g[0] / tot;                                          // rdirichlet: gamma draws over their sum (Pr:420-428)
   if (!isnan(nw0)) {
     h.weight_active = 1 - nw0;
-    double s = 0;
-    for (int k = 1; k <= K; ++k) s += g[k] / tot;
-    for (int k = 1; k <= K; ++k) h.weight_within_active[k - 1] = (g[k] / tot) / s;
+    const double ract = 1.0 / act;                                        // (g_k / tot) / (sum_{j >= 1} g_j / tot)
+    for (int k = 1; k <= K; ++k) h.weight_within_active[k - 1] = g[k] * ract;
   }
-  const double ns = g[K + 1] / (g[K + 1] + g[K + 2]);
+  const double ns = g[K + 1] / (g[K + 1] + g[K + 2]);                     // rbeta as a ratio of gammas
   if (!isnan(ns)) h.spike_probability = ns;
 }
 
 // warp 1: mhInactiveMeans (Pr:433-471), mhActiveMeansDif x K (Pr:640-705), mhSharedVariance (Pr:768-803).  Works on private copies
 // of the level-2 parameters; the caller installs `cur` and the scalar state afterwards.
-__device__ inline void stage_level2(const SMath &m, ChainDev &c, const zz_hyper &h, const MoveDraws *md, const double *st, int K, int tune, L2Params &cur) {
-  double r[2];
-  L2Params p;
-  l2_current(cur, h, K);
-  {                                                                       // mhInactiveMeans: z = (w0, w1), accept w2
-    const MoveDraws &d = md[MD_IM];
-    const double thr = c.pr.threshold_i, im = cur.im;
-    const double imp = thr - fabs(thr - im - c.t_im * d.n01);
-    const double pp = dgamma_log_diff(m, thr - imp, thr - im, c.pr.inactive_means_prior_shape, c.pr.inactive_means_prior_rate);
-    p = cur; p.im = imp;
-    closed_level2_diff(m, st, K, p, cur, r);
-    const double Rr = h.temperature * (r[0] + pp);
-    if (tune) win_push0(c.w_im);
-    if (d.l2 < Rr) { cur.im = imp; if (tune) win_set_last(c.w_im); }
-  }
-  for (int it = 0; it < K; ++it) {                                        // mhActiveMeansDif round `it`: k = w0, z = (w1, w2), accept w3
+// mhInactiveMeans (Pr:433-471): z = (w0, w1), accept w2.  Touches inactive_means only — independent of the active means.
+__device__ inline double stage_im(const SMath &m, ChainDev &c, const zz_hyper &h, const MoveDraws *md, const double *st, int K, int tune) {
+  const MoveDraws &d = md[MD_IM];
+  const double thr = c.pr.threshold_i, im = h.inactive_means, iv = h.inactive_variances, riv = 1.0 / (2 * iv);
+  const double imp = thr - fabs(thr - im - c.t_im * d.n01);
+  const double pp = dgamma_log_diff(m, thr - imp, thr - im, c.pr.inactive_means_prior_shape, c.pr.inactive_means_prior_rate);
+  const double Rr = h.temperature * (closed_inactive_diff(m, st, K, imp, iv, riv, im, iv, riv) + pp);
+  if (tune) win_push0(c.w_im);
+  if (d.l2 < Rr) { if (tune) win_set_last(c.w_im); return imp; }
+  return im;
+}
+// mhActiveMeansDif x K (Pr:640-705): round `it`: k = w0, z = (w1, w2), accept w3.  Touches the active means only.
+template <int K>
+__device__ inline void stage_amd(const SMath &m, ChainDev &c, const zz_hyper &h, const MoveDraws *md, const double *st, int tune, double *am_out /* [K] */) {
+  double rav[K], amp[K], am[K], dif[K];                                   // registers: every index below is a compile-time constant
+#pragma unroll
+  for (int k = 0; k < K; ++k) { am[k] = h.active_means[k]; rav[k] = 1.0 / (2 * h.active_variances[k]); dif[k] = c.active_means_dif[k]; }
+#pragma unroll
+  for (int it = 0; it < K; ++it) {
     const MoveDraws &d = md[MD_AMD + it];
     int k = (int)(d.u[0] * K); if (k >= K) k = K - 1;
-    const double difp = fabs(c.active_means_dif[k] + c.t_am[k] * d.n12);
-    p = cur;
-    for (int j = 0; j < K; ++j) p.am[j] = (j == k ? difp : c.active_means_dif[j]) + c.pr.threshold_a[j];
-    const double pp = dgamma_log_diff(m, difp, c.active_means_dif[k], c.pr.active_means_dif_prior_shape, c.pr.active_means_dif_prior_rate);
-    closed_level2_diff(m, st, K, p, cur, r);
-    const double Rr = h.temperature * (r[1] + pp);
+    double dk = dif[0];
+#pragma unroll
+    for (int j = 1; j < K; ++j) if (j == k) dk = dif[j];
+    const double difp = fabs(dk + c.t_am[k] * d.n12);
+#pragma unroll
+    for (int j = 0; j < K; ++j) amp[j] = (j == k ? difp : dif[j]) + c.pr.threshold_a[j];
+    const double pp = dgamma_log_diff(m, difp, dk, c.pr.active_means_dif_prior_shape, c.pr.active_means_dif_prior_rate);
+    const double Rr = h.temperature * (closed_active_diff<K>(st, amp, rav, am, rav, 0.0) + pp);
     if (tune) win_push0(c.w_am[k]);
     if (d.l3 < Rr) {
-      c.active_means_dif[k] = difp; if (tune) win_set_last(c.w_am[k]);
-      for (int j = 0; j < K; ++j) cur.am[j] = p.am[j];
+      if (tune) win_set_last(c.w_am[k]);
+#pragma unroll
+      for (int j = 0; j < K; ++j) { am[j] = amp[j]; if (j == k) dif[j] = difp; }
     }
   }
-  {                                                                       // mhSharedVariance: slide w0, accept w1
-    const MoveDraws &d = md[MD_SV];
-    const double lo = c.pr.variances_prior_log_min, hi = c.pr.variances_prior_log_max;
-    const double LN10 = 2.302585092994045684, pv = m.log(cur.av[0]) * (1.0 / LN10), t = c.t_av;   // log10
-    double np = (pv - t) + ((pv + t) - (pv - t)) * d.u[0];                // two_boundary_slide_move, MP:29-46
-    if (np > hi) np = 2 * hi - np;
-    np = lo + fabs(np - lo);
-    const double avp1 = m.exp(np * LN10);                                 // 10^np
-    if (tune) win_push0(c.w_av);
-    p = cur; p.iv = avp1;
-    for (int k = 0; k < K; ++k) p.av[k] = avp1;
-    closed_level2_diff(m, st, K, p, cur, r);
-    // Pr:786-787 dunif(log10(.), lo, hi, log = TRUE): np is inside [lo, hi] by construction, pv unless the chain started outside
-    const double Rr = h.temperature * (r[1] + r[0] + dunif_log_rel(np, lo, hi) - dunif_log_rel(pv, lo, hi));
-    if (d.l1 < Rr) {
-      for (int k = 0; k < K; ++k) cur.av[k] = avp1;
-      cur.iv = avp1; if (tune) win_set_last(c.w_av);
-    }
+#pragma unroll
+  for (int k = 0; k < K; ++k) { am_out[k] = am[k]; c.active_means_dif[k] = dif[k]; }
+}
+// mhSharedVariance (Pr:768-803) at the means the two moves above left: slide w0, accept w1.  Returns the (shared) variance.
+template <int K>
+__device__ inline double stage_sv(const SMath &m, ChainDev &c, const zz_hyper &h, const MoveDraws *md, const double *st, int tune, double im, const double *am_in) {
+  const MoveDraws &d = md[MD_SV];
+  const double lo = c.pr.variances_prior_log_min, hi = c.pr.variances_prior_log_max;
+  const double avc = h.active_variances[0], ivc = h.inactive_variances;
+  const double LN10 = 2.302585092994045684, lavc = m.log(avc), pv = lavc * (1.0 / LN10), t = c.t_av;   // log10
+  double np = (pv - t) + ((pv + t) - (pv - t)) * d.u[0];                  // two_boundary_slide_move, MP:29-46
+  if (np > hi) np = 2 * hi - np;
+  np = lo + fabs(np - lo);
+  const double avp1 = m.exp(np * LN10), rp1 = 1.0 / (2 * avp1);           // 10^np
+  if (tune) win_push0(c.w_av);
+  double rvp[K], rvc[K], am[K];
+  bool shared = true;
+  const double rvc0 = 1.0 / (2 * avc);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    am[k] = am_in[k]; rvp[k] = rp1;
+    const bool same = h.active_variances[k] == avc;
+    rvc[k] = same ? rvc0 : 1.0 / (2 * h.active_variances[k]); shared = shared && same;
   }
+  double la;
+  if (shared) la = closed_active_diff<K>(st, am, rvp, am, rvc, np * LN10 - lavc);     // log(avp1) - log(avc), one pair of logarithms
+  else {                                                                  // (a state set from outside with unequal variances)
+    la = closed_active_diff<K>(st, am, rvp, am, rvc, 0.0);
+    for (int k = 1; k <= K; ++k) la += -0.5 * st[k] * (np * LN10 - m.log(h.active_variances[k - 1]));
+  }
+  const double li = closed_inactive_diff(m, st, K, im, avp1, rp1, im, ivc, ivc == avc ? rvc0 : 1.0 / (2 * ivc));
+  // Pr:786-787 dunif(log10(.), lo, hi, log = TRUE): np is inside [lo, hi] by construction, pv unless the chain started outside
+  const double Rr = h.temperature * (la + li + dunif_log_rel(np, lo, hi) - dunif_log_rel(pv, lo, hi));
+  if (d.l1 < Rr) { if (tune) win_set_last(c.w_av); return avp1; }
+  return NAN;                                                             // rejected: the caller keeps the current variances
 }
 
 // warp 2: mhTau (Pr:119-152), mhSg (Pr:58-117), mhS0Tau (Pr:154-191) on private (s0, s1, tau)
 __device__ inline void stage_varg(const SMath &m, ChainDev &c, const zz_hyper &h, const MoveDraws *md, const double *st, int K, int tune, double &s0, double &s1, double &tau) {
   s0 = h.s0; s1 = h.s1; tau = h.tau;
+  double rt = 1.0 / (2 * tau);
   {                                                                       // mhTau: scale w0, accept w1
     const MoveDraws &d = md[MD_TAU];
-    const double HR = c.t_tau * (d.u[0] - 0.5), taup = tau * m.exp(HR);                     // scale_move, MP:3-13; HR = log(sf)
+    const double HR = c.t_tau * (d.u[0] - 0.5), taup = tau * m.exp(HR), rtp = 1.0 / (2 * taup);   // scale_move, MP:3-13; HR = log(sf)
     const double pp = dgamma_log_diff(m, taup, tau, c.pr.tau_shape, c.pr.tau_rate);         // P:3-9
-    const double Rr = h.temperature * (closed_varg_diff(m, st, K, s0, s1, taup, s0, s1, tau) + pp) + HR;
+    const double Rr = h.temperature * (closed_varg_diff(m, st, K, s0, s1, taup, rtp, s0, s1, tau, rt) + pp) + HR;
     if (tune) win_push0(c.w_tau);
-    if (d.l1 < Rr) { tau = taup; if (tune) win_set_last(c.w_tau); }
+    if (d.l1 < Rr) { tau = taup; rt = rtp; if (tune) win_set_last(c.w_tau); }
   }
   {                                                                       // mhSg: selector w0; s0: z = (w1, w2), accept w3; s1: scale w1, accept w2
     const MoveDraws &d = md[MD_SG];
@@ -266,7 +297,7 @@ __device__ inline void stage_varg(const SMath &m, ChainDev &c, const zz_hyper &h
       HR = c.t_s1 * (d.u[1] - 0.5); s1p = s1 * m.exp(HR); if (tune) win_push0(c.w_s1);
       pp = dgamma_log_diff(m, fabs(s1p), fabs(s1), c.pr.s1_shape, c.pr.s1_rate);           // P:41-47 (the unchanged s0 term cancels)
     }
-    const double Rr = h.temperature * (closed_varg_diff(m, st, K, s0p, s1p, tau, s0, s1, tau) + pp) + HR;
+    const double Rr = h.temperature * (closed_varg_diff(m, st, K, s0p, s1p, tau, rt, s0, s1, tau, rt) + pp) + HR;
     if ((sel == 1 ? d.l3 : d.l2) < Rr) {
       s0 = s0p; s1 = s1p;
       if (tune) { if (sel == 1) win_set_last(c.w_s0); else win_set_last(c.w_s1); }
@@ -274,10 +305,10 @@ __device__ inline void stage_varg(const SMath &m, ChainDev &c, const zz_hyper &h
   }
   {                                                                       // mhS0Tau: scale w0, accept w1
     const MoveDraws &d = md[MD_S0TAU];
-    const double HR = c.t_s0tau * (d.u[0] - 0.5), taup = tau * m.exp(HR), s0p = s0 - HR;
+    const double HR = c.t_s0tau * (d.u[0] - 0.5), taup = tau * m.exp(HR), s0p = s0 - HR, rtp = 1.0 / (2 * taup);
     if (tune) win_push0(c.w_s0tau);
     const double pp = s0_prior_rel(c.pr, s0p) - s0_prior_rel(c.pr, s0) + dgamma_log_diff(m, taup, tau, c.pr.tau_shape, c.pr.tau_rate);
-    const double Rr = h.temperature * (closed_varg_diff(m, st, K, s0p, s1, taup, s0, s1, tau) + pp) + HR;
+    const double Rr = h.temperature * (closed_varg_diff(m, st, K, s0p, s1, taup, rtp, s0, s1, tau, rt) + pp) + HR;
     if (d.l1 < Rr) { s0 = s0p; tau = taup; if (tune) win_set_last(c.w_s0tau); }
   }
 }

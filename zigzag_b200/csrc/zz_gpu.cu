@@ -2282,13 +2282,14 @@ int launch_generations(zz_handle *h, uint64_t step0, int ngen, int tune, int hyp
 }  // namespace
 extern "C" {
 
-int zz_debug_gen_times(zz_handle *h, double *out2) {   // diagnostic: ns the releasing CTA of chain 0 spent per launch {ticket -> release, scalar stage}
+int zz_debug_gen_times(zz_handle *h, double *out2) {   // diagnostic: ns the releasing CTA of chain 0 spent in the last launch {ticket -> release, scalar stage, its 6 phases}
   ZZ_CHECK(h);
   if (!h->genctl || !out2) return fail(h, ZZ_ERR_STATE, "no device-resident launch yet");
   GenCtl c;
   ZZ_CUDA(h, cudaMemcpyAsync(&c, h->genctl, sizeof c, cudaMemcpyDeviceToHost, h->stream));
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
   out2[0] = (double)c.ns_leader; out2[1] = (double)c.ns_stage;
+  for (int j = 0; j < 6; ++j) out2[2 + j] = (double)c.ns_phase[j];
   return ZZ_OK;
 }
 

@@ -35,7 +35,8 @@ struct GenCtl {                     // one per chain, device memory
   unsigned arrive;                  // tickets taken (monotone across launches)
   unsigned release;                 // generations published (monotone); GEN_ABORT = give up (time-out)
   unsigned long long ns_leader, ns_stage;   // diagnostics (zz_debug_gen_times): time the last CTA spent between its ticket and the release / in the scalar stage
-  unsigned pad_[26];
+  unsigned long long ns_phase[6];           // ... and in its phases: load, draws, chains of moves, install + tune_all, derive + propose, write-back
+  unsigned pad_[14];
   unsigned tile_q[GEN_NQ * 32];     // dynamic tile scheduling: tickets handed out by each tile queue in the current generation, one
                                     // 128-byte line per counter (same-line atomics serialise in one L2 slice)
 };
@@ -395,9 +396,11 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
       ChainDev &c_s = *reinterpret_cast<ChainDev *>(scr + 2560);
       constexpr int MD_OFF = (2560 + (int)sizeof(ChainDev) + 127) / 128 * 128;
       MoveDraws *md_s = reinterpret_cast<MoveDraws *>(scr + MD_OFF);                 // [MD_MAX] the prepared draws of the Metropolis moves
-      constexpr int SCR_BYTES = MD_OFF + MD_MAX * (int)sizeof(MoveDraws);
+      constexpr int FH_OFF = (MD_OFF + MD_MAX * (int)sizeof(MoveDraws) + 127) / 128 * 128;
+      FastH &F_s = *reinterpret_cast<FastH *>(scr + FH_OFF);                         // the next generation's constants, staged (no global read-backs)
+      constexpr int SCR_BYTES = FH_OFF + (int)sizeof(FastH);
       static_assert(MAX_NSTAT_ * 8 <= 512 && sizeof(L2Params) <= 256 && sizeof(zz_hyper) <= 1024, "stage scratch layout");
-      static_assert(SCR_BYTES <= 8 * SWEEP_BLOCK * 3, "the scratch must fit in the first statistic columns");
+      static_assert(SCR_BYTES <= 8 * SWEEP_BLOCK * 5, "the scratch must fit in the first statistic columns (nstat >= 13 of them)");
       if ((int)threadIdx.x < nstat) { ivec[threadIdx.x] = (long long)__ldcg(reinterpret_cast<const unsigned long long *>(gacc + threadIdx.x)); gacc[threadIdx.x] = 0; }
       if (threadIdx.x < GEN_NQ) ctl->tile_q[threadIdx.x * 32] = 0;
       __syncthreads();
@@ -426,6 +429,13 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
           for (int j = threadIdx.x; j < (int)(sizeof(zz_hyper) / 8); j += blockDim.x) d1[j] = __ldcg(s1 + j);
         }
         __syncthreads();
+        unsigned long long tp0 = globaltimer_ns(), tp1;
+#ifdef ZZ_GEN_PROFILE   /* per-phase times of the stage (each probe costs a global read-modify-write, ~0.5 us) */
+#define ZZ_PHASE(j) do { if (threadIdx.x == 0) { tp1 = globaltimer_ns(); ctl->ns_phase[j] += tp1 - tp0; tp0 = tp1; } } while (0)
+        if (threadIdx.x == 0) { ctl->ns_phase[0] += tp0 - t_stage0; }
+#else
+#define ZZ_PHASE(j) do { (void)tp0; (void)tp1; } while (0)
+#endif
         const int K = a.K, R = a.R, tune = a.tune;
         const bool last = gi == ga.ngen - 1;
         const SMath sm{&T};
@@ -436,37 +446,50 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
           if (lane == 0) stage_gibbs_combine(h_s, K, gam);
         } else if (wid == 4 && lane < MD_AMD + K) make_move_draws(sm, md_s[lane], a.seed, (uint32_t)c_s.chain, step, lane);
         __syncthreads();
-        // phase B: the three chains of moves side by side
-        if (wid == 1 && lane == 0) stage_level2(sm, c_s, h_s, md_s, st, K, tune, l2_s);
+        ZZ_PHASE(1);
+        // phase B: the chains of moves side by side (mhInactiveMeans and mhActiveMeansDif touch disjoint parameters)
+        if (wid == 1 && lane == 0) stage_amd<KT>(sm, c_s, h_s, md_s, st, tune, l2_s.am);
+        else if (wid == 5 && lane == 0) l2_s.im = stage_im(sm, c_s, h_s, md_s, st, K, tune);
         else if (wid == 2 && lane == 0) stage_varg(sm, c_s, h_s, md_s, st, K, tune, vg_s[0], vg_s[1], vg_s[2]);
-        else if (wid == 3 && lane == 0) acc_s[1] = px_decide(c_s, h_s, a.seed, step, st[3 * K1 + FXS_PXDELTA], st[3 * K1 + FXS_PXBAD], tune);
+        else if (wid == 3 && lane == 0) {
+          const int acc = px_decide(c_s, h_s, a.seed, step, st[3 * K1 + FXS_PXDELTA], st[3 * K1 + FXS_PXBAD], tune);
+          if (acc) h_s.alpha_r[c_s.px_lib] = c_s.px_alpha;               // Pr:234-239
+          c_s.px_prev_acc = acc; c_s.px_valid = 0;
+          if (!last) px_propose(c_s, h_s, a.seed, step + (uint64_t)ga.step_stride, tune, R);   // the next generation's mhP_x (after a segment: k_gen_prepare)
+        }
         __syncthreads();
-        // every group worked on fields of its own (warp 0: weights and spike probability in h_s; warps 1, 2: private copies): install
-        if (threadIdx.x == 0) {
-          h_s.inactive_means = l2_s.im; h_s.inactive_variances = l2_s.iv;
-          for (int k = 0; k < K; ++k) { h_s.active_means[k] = l2_s.am[k]; h_s.active_variances[k] = l2_s.av[k]; }
+        ZZ_PHASE(2);
+        if (threadIdx.x == 0) {                                          // mhSharedVariance at the means just decided; install everything
+          const double av = stage_sv<KT>(sm, c_s, h_s, md_s, st, tune, l2_s.im, l2_s.am);
+          h_s.inactive_means = l2_s.im;
+          for (int k = 0; k < K; ++k) h_s.active_means[k] = l2_s.am[k];
+          if (!isnan(av)) { h_s.inactive_variances = av; for (int k = 0; k < K; ++k) h_s.active_variances[k] = av; }
           h_s.s0 = vg_s[0]; h_s.s1 = vg_s[1]; h_s.tau = vg_s[2];
-          if (acc_s[1]) h_s.alpha_r[c_s.px_lib] = c_s.px_alpha;         // Pr:234-239
-          c_s.px_prev_acc = acc_s[1];
           c_s.step += (uint64_t)ga.step_stride; c_s.gen += 1;
-          c_s.px_valid = 0;
         }
         __syncthreads();
         if (last && ga.do_tune_all_last)                                 // B:146 tune_all, scalar part (the per-gene part follows the launch)
           for (int l = threadIdx.x; l < R + K + 6; l += blockDim.x) tune_all_scalars(c_s, ga.target, K, R, l);
-        // the next generation's constants, one group of fields per thread, while warp 3 proposes its mhP_x (after a segment: k_gen_prepare)
-        FastH &F = ga.fasth_rw[chain];
-        if (wid != 3) derive_fast_par(F, &h_s, threadIdx.x < 96 ? threadIdx.x : threadIdx.x + 1000);
-        else if (lane == 0 && !last) px_propose(c_s, h_s, a.seed, step + (uint64_t)ga.step_stride, tune, R);
+        ZZ_PHASE(3);
+        // the next generation's constants, one group of fields per thread
+        derive_fast_par(F_s, &h_s, threadIdx.x);
         __syncthreads();
-        if (threadIdx.x == 0) { derive_fin(F, &h_s); set_px(F, h_s, c_s); }
+        if (threadIdx.x == 0) { derive_fin(F_s, &h_s); set_px(F_s, h_s, c_s); }
         __syncthreads();
+        {
+          uint64_t *dF = reinterpret_cast<uint64_t *>(ga.fasth_rw + chain);
+          const uint64_t *sF = reinterpret_cast<const uint64_t *>(&F_s);
+          for (int j = threadIdx.x; j < (int)(sizeof(FastH) / 8); j += blockDim.x) dF[j] = sF[j];
+        }
+        ZZ_PHASE(4);
         {
           uint64_t *d0 = reinterpret_cast<uint64_t *>(ga.chain + chain), *d1 = reinterpret_cast<uint64_t *>(ga.hyper + chain);
           const uint64_t *s0 = reinterpret_cast<const uint64_t *>(&c_s), *s1 = reinterpret_cast<const uint64_t *>(&h_s);
           for (int j = threadIdx.x; j < (int)(sizeof(ChainDev) / 8); j += blockDim.x) d0[j] = s0[j];
           for (int j = threadIdx.x; j < (int)(sizeof(zz_hyper) / 8); j += blockDim.x) d1[j] = s1[j];
         }
+        ZZ_PHASE(5);
+#undef ZZ_PHASE
       }
       __threadfence();
       __syncthreads();
