@@ -1,4 +1,4 @@
-"""Multi-GPU check of the device-resident generation loop (not collected by pytest: needs >= 2 GPUs).
+"""Multi-GPU check of the device-resident generation loop (run by tests/test_multi_gpu.py under torchrun when the box has >= 2 GPUs).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 tests/multi_gpu_chain_check.py
 

@@ -63,6 +63,60 @@ def test_two_rank_shards_reduce_to_the_single_rank_result():
     assert a[2] == b[2] and a[3] == b[3]                                # replicated hyper decision is identical
 
 
+def _product_worker(rank, world, port, G, R, outdir, out):
+    """The PRODUCT's host mirror on gene shards: zigzag(shard=...), its _allreduce / _gather_genes and the sample-time file writing
+    under gloo.  The device is replaced by the oracle-backed test double (no GPU in the CPU suite)."""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from zigzag_b200 import _capi, synth, zigzag as Z
+    from _oracle_handle import OracleHandle
+    _capi.Handle = OracleHandle
+    X, gl, _ = synth.simulate(G, R, 77)
+    data = np.where(np.isneginf(X), 0.0, np.exp(X))
+    z = Z.zigzag(data, gl, threshold_i=-1.0, threshold_a=(1.0, 6.0), seed=5, output_directory=outdir,
+                 candidate_gene_list=[f"gene_{i}" for i in (1, G // 2, G // 2 + 1, G)], shard=(rank, world),
+                 process_group=dist.group.WORLD, write_settings=(rank == 0))
+    assert isinstance(z.h, OracleHandle) and z.h.G == z.g1 - z.g0
+    # sampling points at i = 300, 400 (B:116: i > 2 * sample_frequency), candidate-gene rows at i = 400 ((i / sf) % 4 == 0): the
+    # gather over the shards is a collective and must be entered by every rank
+    z.burnin(sample_frequency=100, ngen=420, write_to_files=True, burninprefix="t", schedule="fused")
+    z.mcmc(sample_frequency=10, ngen=40, write_to_files=True, mcmcprefix="t", schedule="reference")
+    st = z.state()
+    out[rank] = dict(hyper=z._hyper_dict(), lnl=list(z.lnl_trace), gen=z.gen, n_samples=z.n_samples,
+                     yg=st["Yg"].copy(), spike=st["inactive_spike_allocation"].copy(), g=(z.g0, z.g1),
+                     tune=(z.tuningParam_tau, z.inactive_mean_tuningParam), launches=z.h.launch_count)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_product_host_path_on_two_gene_shards_with_file_writing(tmp_path):
+    G, R, world = 600, 4, 2
+    out = mp.Manager().dict()
+    port = 30100 + (os.getpid() % 500)
+    mp.spawn(_product_worker, args=(world, port, G, R, str(tmp_path), out), nprocs=world, join=True)
+    a, b = out[0], out[1]
+    assert a["g"] == (0, G // 2) and b["g"] == (G // 2, G) and a["launches"] > 0
+    for k, v in a["hyper"].items():                                       # replicated hyper-parameters stay bit-identical
+        assert np.array_equal(np.asarray(v), np.asarray(b["hyper"][k])), k
+    assert a["lnl"] == b["lnl"] and a["gen"] == b["gen"] and a["n_samples"] == b["n_samples"] and a["tune"] == b["tune"]
+    assert a["tune"][0] != 0.05                                            # tune_all ran (generation 400)
+    rows = lambda f: [l.rstrip("\n").split("\t") for l in open(os.path.join(str(tmp_path), f))]
+    par = rows("t_burnin/t_model_parameters.log")
+    assert [r[0] for r in par[1:]] == ["300", "400"] and len(par[0]) == 5 + R + 3 + 2 * 2 + 1 + 2
+    yg = rows("t_burnin/t_yg_candidate_genes.log")
+    assert yg[0] == ["gen", "gene_1", f"gene_{G // 2}", f"gene_{G // 2 + 1}", f"gene_{G}"] and [r[0] for r in yg[1:]] == ["400"]
+    par = rows("t_mcmc_output/t_model_parameters.log")
+    assert len(par) - 1 == a["n_samples"] - 1 and all(len(r) == len(par[0]) for r in par)
+    yg = rows("t_mcmc_output/t_yg_candidate_genes.log")
+    last = [float(x) for x in yg[-1][1:]]                                  # the last row holds genes of BOTH shards, from the final state
+    full_y = np.concatenate([a["yg"], b["yg"]]); full_s = np.concatenate([a["spike"], b["spike"]])
+    want = [(-10.0 if full_s[i] else round(float(full_y[i]), 3)) for i in (0, G // 2 - 1, G // 2, G - 1)]
+    assert last == want
+    pa = rows("t_mcmc_output/t_probability_active.tab")
+    assert len(pa) == G + 1 and all(0.0 <= float(r[1]) <= 1.0 for r in pa[1:])
+
+
 def test_shard_ranges_partition_the_genes():
     for G in (10, 3001, 1_000_000):
         for world in (1, 2, 4, 8):

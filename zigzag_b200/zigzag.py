@@ -568,10 +568,8 @@ class zigzag:
                 i = self.gen - 1
                 if i % sample_frequency == 0 and i > 2 * sample_frequency:
                     self.lnl_trace.append(self.calculate_lnl())
-                    if write_to_files and self.temperature == 1 and self.rank == 0:
-                        self.writeToOutputFiles(pdir + "/" + prefix, i)
-                        if (i // sample_frequency) % 4 == 0:
-                            self.writeToYgVariancegOutputFiles(pdir + "/" + prefix, i)
+                    if write_to_files and self.temperature == 1:
+                        self._write_sample(pdir + "/" + prefix, i, (i // sample_frequency) % 4 == 0)
             self.lnl_trace = self.lnl_trace[-1:]
             return
         i, j = self.gen, 0
@@ -581,10 +579,8 @@ class zigzag:
             j = i
             if i % sample_frequency == 0 and i > 2 * sample_frequency:
                 self.lnl_trace.append(self.calculate_lnl())
-                if write_to_files and self.temperature == 1 and self.rank == 0:
-                    self.writeToOutputFiles(pdir + "/" + prefix, i)
-                    if (i // sample_frequency) % 4 == 0:
-                        self.writeToYgVariancegOutputFiles(pdir + "/" + prefix, i)
+                if write_to_files and self.temperature == 1:
+                    self._write_sample(pdir + "/" + prefix, i, (i // sample_frequency) % 4 == 0)
             i += 1
             self.gen = i
             if self.gen % 400 == 0:
@@ -641,10 +637,8 @@ class zigzag:
                 g = self.gen - 1
                 if g % sample_frequency == 0:
                     self.lnl_trace.append(self.calculate_lnl())
-                    if write_to_files and write_yv and self.temperature == 1 and self.rank == 0:
-                        self.writeToOutputFiles(pdir + "/" + prefix, g)
-                        if (g // sample_frequency) % yv_freq == 0:
-                            self.writeToYgVariancegOutputFiles(pdir + "/" + prefix, g)
+                    if write_to_files and write_yv and self.temperature == 1:
+                        self._write_sample(pdir + "/" + prefix, g, (g // sample_frequency) % yv_freq == 0)
                         if (g - starting_gen) / (yv_freq * sample_frequency) > 500:
                             write_yv = False
                 if run_posterior_predictive and g % postpred_every == 0:                          # M:250-252
@@ -660,10 +654,8 @@ class zigzag:
                 if self.temperature == 1:
                     self.h.accumulate_alloc_trace(); self.n_samples += 1                          # M:194-199
                 self.lnl_trace.append(self.calculate_lnl())                                       # M:202
-                if write_to_files and write_yv and self.temperature == 1 and self.rank == 0:
-                    self.writeToOutputFiles(pdir + "/" + prefix, self.gen)
-                    if (self.gen // sample_frequency) % yv_freq == 0:
-                        self.writeToYgVariancegOutputFiles(pdir + "/" + prefix, self.gen)
+                if write_to_files and write_yv and self.temperature == 1:
+                    self._write_sample(pdir + "/" + prefix, self.gen, (self.gen // sample_frequency) % yv_freq == 0)
                     if (self.gen - starting_gen) / (yv_freq * sample_frequency) > 500:
                         write_yv = False
             if run_posterior_predictive and self.gen % postpred_every == 0:                       # M:250-252
@@ -740,6 +732,14 @@ class zigzag:
             with open(self._path(prefix, ".library_specific_post_predictive_output.log"), "a") as f:   # PostPred:86-88
                 f.write("\t".join(_rnum(x) for x in (g, *out["W_L_r"], *out["B_r"])) + "\n")
         return out
+
+    def _write_sample(self, prefix, gen, yv_row):
+        """The rows of one sampling point.  Called on EVERY rank with identical arguments: the candidate-gene rows are gathered
+        over the gene shards (a collective); only rank 0 touches the files."""
+        if self.rank == 0:
+            self.writeToOutputFiles(prefix, gen)
+        if yv_row:
+            self.writeToYgVariancegOutputFiles(prefix, gen)
 
     def writeToOutputFiles(self, prefix, gen):                                           # FileWriting:60-86
         row = [self.lnl_trace[-1], self.s0, self.s1, self.tau, *self.alpha_r, self.spike_probability, self.inactive_means,
