@@ -47,8 +47,9 @@ constexpr int MAX_NSTAT = 3 * (ZZ_MAX_COMP + 1) + NSTAT_FIXED;
 // inbox[slot][my_rank] of every peer (remote stores ride NVLink/NVSwitch), (2) polls its own inbox until the words of every peer
 // show the epoch, (3) adds the `world` vectors in RANK ORDER (its own straight from shared memory), so every rank obtains the
 // bit-identical sum (replicated hyper moves cannot diverge).  Slots alternate with the epoch; a rank cannot lap another by more
-// than one epoch because it needs everybody's words first.  The poll is bounded (~2 s of clock64): on timeout bit 2 of the
-// NaN/err flag is raised instead of hanging.  (The first version — plain stores, __threadfence_system, a flag per peer, a
+// than one epoch because it needs everybody's words first.  The poll is bounded (cm.timeout_ns of %globaltimer): on time-out the
+// exchange is FAIL-STOP — bit 2 of the NaN/err flag is raised and every entry of `out` is NaN, so nothing downstream (the
+// replicated scalar stage, the host's hyper moves) can consume words of an earlier epoch and let the ranks diverge silently.  (The first version — plain stores, __threadfence_system, a flag per peer, a
 // second fence — cost 11-16 us per step at N = 2..8.)
 struct CommArgs {
   int rank, world, nvec;                 // nvec = nval * C doubles per rank
@@ -58,7 +59,9 @@ struct CommArgs {
   int64_t base;                          // first word of the inbox region used by this exchange (statistics: 0; small gene sums: behind them)
   int stride;                            // words per (slot, rank) block of that region: fixed per region, so exchanges of different
                                          // lengths in the same region never overlap each other's slots
+  long long timeout_ns;                  // bound of the poll (ZZ_COMM_TIMEOUT_S, default 20 s)
 };
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 // all threads of the CTA must call it; `vec` = the local vector in shared memory (complete: the caller has synchronised)
 __device__ __forceinline__ void allreduce_exchange(const double *vec, const CommArgs &cm, double *out, int *err_flag) {
@@ -78,7 +81,7 @@ __device__ __forceinline__ void allreduce_exchange(const double *vec, const Comm
     }
   }
   const unsigned long long *in = reinterpret_cast<const unsigned long long *>(cm.inbox[cm.rank]) + cm.base + (int64_t)slot * cm.world * cm.stride;
-  const long long t0 = clock64();
+  const unsigned long long t0 = globaltimer_ns();
   for (int idx = threadIdx.x; idx < cm.nvec; idx += blockDim.x) {
     double v = 0;
     for (int r = 0; r < cm.world; ++r) {
@@ -87,7 +90,7 @@ __device__ __forceinline__ void allreduce_exchange(const double *vec, const Comm
         const volatile unsigned long long *p = in + (int64_t)r * cm.stride + 2 * idx;
         unsigned long long a = p[0], b = p[1];
         while ((unsigned)(a >> 32) != ep || (unsigned)(b >> 32) != ep) {
-          if (clock64() - t0 > 4000000000LL) { timed_out = 1; break; }
+          if ((long long)(globaltimer_ns() - t0) > cm.timeout_ns) { timed_out = 1; break; }
           a = p[0]; b = p[1];
         }
         x = __hiloint2double((int)(unsigned)b, (int)(unsigned)a);
@@ -97,7 +100,10 @@ __device__ __forceinline__ void allreduce_exchange(const double *vec, const Comm
     out[idx] = v;
   }
   __syncthreads();
-  if (timed_out && threadIdx.x == 0) atomicOr(err_flag, 4);
+  if (timed_out) {                       // a peer never showed up: poison the result, raise the flag
+    for (int idx = threadIdx.x; idx < cm.nvec; idx += blockDim.x) out[idx] = __longlong_as_double(0x7ff8000000000000LL);
+    if (threadIdx.x == 0) atomicOr(err_flag, 4);
+  }
 }
 
 // Fixed-order reduction of the per-CTA rows [C][nblk][nval] into `vec` (shared memory, nvec = nval*C doubles, followed by
@@ -1127,7 +1133,7 @@ struct zz_handle {
   uint64_t *nd_mask; double *xbar, *xss;   // per-gene data statistics (k_prepare_data)
   FastH *fasth; bool fasth_valid;           // derived hyper-parameters of the production kernels
   // peer-memory all-reduce of the statistics vector (zz_comm_*)
-  int comm_rank, comm_world; unsigned long long comm_epoch, comm_epoch_small; bool comm_ready;
+  int comm_rank, comm_world; unsigned long long comm_epoch, comm_epoch_small; bool comm_ready; long long comm_timeout_ns;
   double *comm_inbox; unsigned long long *comm_flags;        // this rank's inbox / flags (device memory, exported through CUDA IPC)
   double *peer_inbox[8]; unsigned long long *peer_flags[8];  // every rank's buffers as mapped here (own entry = local pointers)
   unsigned *tile_counter; int persist_blocks;       // tile_counter: ticket of the "last CTA done" epilogue
@@ -1151,6 +1157,26 @@ namespace {
 int fail(zz_handle *h, int code, const std::string &msg) {
   if (h) { h->err = msg; if (code == ZZ_ERR_CUDA) h->sticky = true; }
   return code;
+}
+
+// Takes `n` consecutive exchange epochs; returns the one BEFORE the first.  The low 32 bits travel with every word and mark it
+// valid, so they must never be 0 (the zero-initialised inbox): a range that would cross a multiple of 2^32 is moved behind it,
+// keeping the slot parity alternating (slot = epoch & 1; two exchanges in a row on one slot could overwrite unread words).
+// Every rank calls this with the same sequence of `n`, so the epochs stay in step.
+unsigned long long comm_take_epochs(zz_handle *h, unsigned long long n) {
+  if ((h->comm_epoch & 0xFFFFFFFFull) + n > 0xFFFFFFFFull) {
+    const unsigned long long last = h->comm_epoch;
+    h->comm_epoch = (h->comm_epoch | 0xFFFFFFFFull) + 1ull;          // low half 0: the first epoch used is this + 1
+    if (((h->comm_epoch + 1ull) & 1ull) == (last & 1ull)) h->comm_epoch += 1ull;
+  }
+  const unsigned long long before = h->comm_epoch;
+  h->comm_epoch += n;
+  return before;
+}
+void fill_comm(zz_handle *h, CommArgs &cm, int nvec, unsigned long long epoch) {
+  cm.rank = h->comm_rank; cm.world = h->comm_world; cm.nvec = nvec; cm.epoch = epoch; cm.base = 0; cm.stride = 2 * nvec;
+  cm.timeout_ns = h->comm_timeout_ns;
+  for (int r = 0; r < 8; ++r) { cm.inbox[r] = h->peer_inbox[r]; cm.flags[r] = h->peer_flags[r]; }
 }
 #define ZZ_CUDA(h, expr)                                                                         \
   do {                                                                                           \
@@ -1377,12 +1403,11 @@ int launch_sweep_fast(zz_handle *h, uint64_t step, int tune, uint32_t moves, con
   fa.rows_per_chain = per_chain;
   fa.do_spike_move = (moves & ZZ_MOVE_SPIKE) ? 1 : 0;
   h->stats_fresh = false;
-  if (full && h->stats_target) {
+  if (full && h->stats_target && (size_t)nstat * h->C <= (size_t)MAX_NSTAT * 8) {
     fa.stats_out = h->stats_target;
     if (h->stats_allreduce && h->comm_ready) {
       fa.do_allreduce = 1;
-      fa.cm.rank = h->comm_rank; fa.cm.world = h->comm_world; fa.cm.nvec = nstat * h->C; fa.cm.epoch = ++h->comm_epoch; fa.cm.base = 0; fa.cm.stride = 2 * fa.cm.nvec;
-      for (int r = 0; r < 8; ++r) { fa.cm.inbox[r] = h->peer_inbox[r]; fa.cm.flags[r] = h->peer_flags[r]; }
+      fill_comm(h, fa.cm, nstat * h->C, comm_take_epochs(h, 1) + 1ull);
     }
   }
   const bool prod = !draws_dev[0] && !draws_dev[2] && !draws_dev[4] && !draws_dev[6] && !dec_dev[0] && !dec_dev[1] && !dec_dev[2] && !dec_dev[3];
@@ -1547,7 +1572,8 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   for (int64_t g = 0; g < G; ++g) h->perm_h[g] = (int32_t)g;
   ZZ_CUDA(h, cudaMemcpyAsync(h->perm, h->perm_h.data(), sizeof(int32_t) * G, cudaMemcpyHostToDevice, h->stream));
   h->stats_target = nullptr; h->stats_allreduce = 0;
-  h->comm_rank = 0; h->comm_world = 1; h->comm_epoch = 0; h->comm_epoch_small = 0; h->comm_ready = false; h->comm_inbox = nullptr; h->comm_flags = nullptr;
+  h->comm_rank = 0; h->comm_world = 1; h->comm_epoch = 0; h->comm_epoch_small = 0; h->comm_ready = false;
+  h->comm_timeout_ns = (getenv("ZZ_COMM_TIMEOUT_S") ? atoll(getenv("ZZ_COMM_TIMEOUT_S")) : 20) * 1000000000LL; h->comm_inbox = nullptr; h->comm_flags = nullptr;
   for (int r = 0; r < 8; ++r) { h->peer_inbox[r] = nullptr; h->peer_flags[r] = nullptr; }
   h->n_allzero = 0; h->lps_valid = false; h->stats_fresh = false; h->persist_blocks = 0; h->sw_rows = 0;
   ZZ_CUDA(h, cudaMalloc(&h->fasth, sizeof(FastH) * h->C));
@@ -1888,7 +1914,8 @@ int zz_comm_connect(zz_handle *h, const void *all_handles) {
 int zz_set_stats_output_dev(zz_handle *h, double *out_dev, int allreduce) {
   ZZ_CHECK(h);
   if (allreduce && !h->comm_ready) return fail(h, ZZ_ERR_STATE, "zz_set_stats_output_dev: all-reduce requested before zz_comm_connect");
-  if ((size_t)zz_suffstats_len(h->K) * h->C > (size_t)MAX_NSTAT * 8) return fail(h, ZZ_ERR_INVALID, "too many chains for the fused statistics epilogue");
+  // (the epilogue of k_sweep_fast holds at most MAX_NSTAT * 8 values: a handle with more chains gets its statistics from
+  //  zz_run_sweeps / zz_run_generations, whose kernel writes them chain by chain, or from zz_suffstats)
   h->stats_target = out_dev; h->stats_allreduce = allreduce ? 1 : 0;
   return ZZ_OK;
 }
@@ -1910,8 +1937,7 @@ int zz_suffstats_allreduce_dev(zz_handle *h, double *out_dev) {
     partials = h->partials;
   }
   CommArgs cm;
-  cm.rank = h->comm_rank; cm.world = h->comm_world; cm.nvec = nstat * h->C; cm.epoch = ++h->comm_epoch; cm.base = 0; cm.stride = 2 * cm.nvec;
-  for (int r = 0; r < 8; ++r) { cm.inbox[r] = h->peer_inbox[r]; cm.flags[r] = h->peer_flags[r]; }
+  fill_comm(h, cm, nstat * h->C, comm_take_epochs(h, 1) + 1ull);
   k_reduce_allreduce<<<1, BLOCK, 0, h->stream>>>(partials, nblk, nstat, h->C, out_dev, cm, h->nan_flag);
   ZZ_LAUNCHED(h);
   return ZZ_OK;
@@ -2250,13 +2276,10 @@ int launch_generations(zz_handle *h, uint64_t step0, int ngen, int tune, int hyp
   static const int dyn_tiles = getenv("ZZ_GEN_STATIC_TILES") ? 0 : 1;   // measurement switch (profiles/r2_summary.md)
   ga.dyn_tiles = dyn_tiles;
   static const long long timeout_s = getenv("ZZ_GEN_TIMEOUT_S") ? atoll(getenv("ZZ_GEN_TIMEOUT_S")) : 20;
-  ga.timeout_ns = timeout_s * 1000000000LL;
+  ga.timeout_ns = timeout_s * 1000000000LL;                          // grid barrier of one chain; the peer exchange: ZZ_COMM_TIMEOUT_S
   if (h->comm_ready && h->comm_world > 1) {
     ga.do_allreduce = 1;
-    ga.cm.rank = h->comm_rank; ga.cm.world = h->comm_world; ga.cm.nvec = nstat; ga.cm.epoch = h->comm_epoch; ga.cm.base = 0; ga.cm.stride = 2 * nstat;
-    for (int r = 0; r < 8; ++r) { ga.cm.inbox[r] = h->peer_inbox[r]; ga.cm.flags[r] = h->peer_flags[r]; }
-    h->comm_epoch += (unsigned long long)ngen;
-    if ((unsigned)h->comm_epoch < (unsigned)ngen) h->comm_epoch += (unsigned long long)ngen + 1;   // keep the 32-bit epoch away from 0 (the zero-initialised inbox)
+    fill_comm(h, ga.cm, nstat, comm_take_epochs(h, (unsigned long long)ngen));   // generation gi exchanges under epoch ga.cm.epoch + gi + 1
   }
   ZZ_CUDA(h, cudaMemsetAsync(h->genctl, 0, sizeof(GenCtl) * C, h->stream));
   ZZ_CUDA(h, cudaMemsetAsync(h->genacc, 0, sizeof(long long) * (size_t)C * nstat, h->stream));

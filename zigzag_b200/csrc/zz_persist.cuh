@@ -55,7 +55,6 @@ struct GenArgs {
   int dyn_tiles;                    // 0: static tile assignment (warp w: tiles w, w + W, ...); 1: static for two rounds, then from the queues
 };
 
-__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
@@ -409,7 +408,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
         CommArgs cm = ga.cm;
         cm.epoch += (unsigned long long)gi + 1ull;
         cm.base += (int64_t)chain * 2 * cm.world * cm.stride;
-        ok = allreduce_exchange_i64(ivec, nstat, cm, ga.timeout_ns);
+        ok = allreduce_exchange_i64(ivec, nstat, cm, cm.timeout_ns);
       }
       if ((int)threadIdx.x < nstat) {
         st[threadIdx.x] = ok ? (double)ivec[threadIdx.x] * (1.0 / FX_SCALE) : NAN;
