@@ -104,6 +104,35 @@ __device__ inline double gamma_slot(const SMath &m, uint64_t seed, uint32_t chai
   return d / rate * boost;
 }
 
+// The shape-independent part of attempts 0 and 1 of gamma_slot — the normal x and the logarithm of the accept uniform — can be
+// drawn before the shape (a gene count) is known: GammaPre holds them, gamma_slot_fin finishes the draw with the same arithmetic.
+struct GammaPre { double x[2], lu[2]; };
+__device__ inline void gamma_predraw(const SMath &m, uint64_t seed, uint32_t chain, uint64_t step, uint32_t slot, int j, GammaPre &g) {
+  uint32_t o[4];
+  philox_block(seed, chain, step, (uint32_t)j, 0xFFFFFF00ull + slot, o);
+  g.x[j] = sqrt(-2.0 * m.log(u32_open(o[0]))) * cospi(2.0 * u32_open(o[1]));
+  g.lu[j] = m.log(u32_open(o[2]));
+}
+__device__ inline double gamma_slot_fin(const SMath &m, uint64_t seed, uint32_t chain, uint64_t step, uint32_t slot, double shape, double rate, const GammaPre &g) {
+  if (shape < 1) return gamma_slot(m, seed, chain, step, slot, shape, rate);      // boosted draw: rare (beta = 0 with a small prior shape)
+  const double d = shape - 1.0 / 3, cc = 1 / sqrt(9 * d);
+  for (uint32_t j = 0; j < 255; ++j) {
+    double x, lu;
+    if (j < 2) { x = g.x[j]; lu = g.lu[j]; }
+    else {
+      uint32_t o[4];
+      philox_block(seed, chain, step, j, 0xFFFFFF00ull + slot, o);
+      x = sqrt(-2.0 * m.log(u32_open(o[0]))) * cospi(2.0 * u32_open(o[1]));
+      lu = m.log(u32_open(o[2]));
+    }
+    double v = 1 + cc * x;
+    if (v <= 0) continue;
+    v = v * v * v;
+    if (lu < 0.5 * x * x + d - d * v + d * m.log(v)) return rate == 1.0 ? d * v : d * v / rate;
+  }
+  return d / rate;
+}
+
 // dgamma_log(xp) - dgamma_log(xc): the normalising constant (lgamma, log rate) cancels; -Inf proposal outside the support
 template <class M>
 __device__ inline double dgamma_log_diff(const M &m, double xp, double xc, double shape, double rate) {
@@ -176,16 +205,21 @@ __device__ inline double s0_prior_rel(const zz_priors &pr, double x) {   // P:33
 
 // warp 0, lanes 0 .. K + 2: the gamma draws of gibbsMixtureWeights (Pr:412-431) and gibbsSpikeProb (Pr:511-526); `g` is a
 // shared-memory array of K + 3 doubles that lane 0 combines afterwards (stage_gibbs_combine)
-__device__ inline void stage_gibbs_draws(const SMath &m, const ChainDev &c, const zz_hyper &h, uint64_t seed, uint64_t step, const double *stats, int K, int lane, double *g) {
+__device__ inline uint32_t gibbs_slot(int idx, int K) { return idx <= K ? (uint32_t)(SUB_MIXW + idx) : idx == K + 1 ? (uint32_t)SUB_SP0 : (uint32_t)SUB_SP1; }
+// the part that does not need the statistics: lanes 0 .. 2 (K + 3) - 1, lane = 2 * draw + attempt
+__device__ inline void stage_gibbs_predraw(const SMath &m, const ChainDev &c, uint64_t seed, uint64_t step, int K, int lane, GammaPre *gp) {
+  if (lane >= 2 * (K + 3)) return;
+  gamma_predraw(m, seed, (uint32_t)c.chain, step, gibbs_slot(lane >> 1, K), lane & 1, gp[lane >> 1]);
+}
+__device__ inline void stage_gibbs_draws(const SMath &m, const ChainDev &c, const zz_hyper &h, uint64_t seed, uint64_t step, const double *stats, int K, int lane, const GammaPre *gp, double *g) {
   if (lane > K + 2) return;
-  double shape; uint32_t slot;
-  if (lane <= K) { shape = (lane == 0 ? c.pr.weight_active_shape_2 : c.pr.weight_active_shape_1 / K) + stats[lane] * h.beta; slot = SUB_MIXW + lane; }
+  double shape;
+  if (lane <= K) shape = (lane == 0 ? c.pr.weight_active_shape_2 : c.pr.weight_active_shape_1 / K) + stats[lane] * h.beta;
   else {
     const double nin = stats[3 * (K + 1) + 0], ninact = stats[0];
     shape = lane == K + 1 ? nin + c.pr.spike_prior_shape_1 : (ninact - nin) + c.pr.spike_prior_shape_2;
-    slot = lane == K + 1 ? SUB_SP0 : SUB_SP1;
   }
-  g[lane] = gamma_slot(m, seed, (uint32_t)c.chain, step, slot, shape, 1.0);
+  g[lane] = gamma_slot_fin(m, seed, (uint32_t)c.chain, step, gibbs_slot(lane, K), shape, 1.0, gp[lane]);
 }
 __device__ inline void stage_gibbs_combine(zz_hyper &h, int K, const double *g) {
   double tot = 0, act = 0;
@@ -326,11 +360,14 @@ __device__ inline void px_propose(ChainDev &c, const zz_hyper &h, uint64_t seed,
   c.px_HR = HR; c.px_lib = lib; c.px_alpha = ap; c.px_valid = 1;
 }
 // second half, after the sweep: `delta` = sum over genes of ll(alpha') - ll(alpha) of the one library, `bad` = non-finite terms seen
-__device__ inline int px_decide(ChainDev &c, const zz_hyper &h, uint64_t seed, uint64_t step, double delta, double bad, int tune) {
+__device__ inline double px_log_u(const ChainDev &c, uint64_t seed, uint64_t step) {   // log of the move's accept uniform (needs no statistics)
   uint32_t o[4];
   philox_block(seed, (uint32_t)c.chain, step, 0, 0xFFFFFF00ull + SUB_PX, o);
+  return log(u32_open(o[2]));
+}
+__device__ inline int px_decide(ChainDev &c, const zz_hyper &h, double log_u, double delta, double bad, int tune) {
   const double Rr = h.temperature * (delta + c.px_pp) + c.px_HR;
-  const int acc = c.px_valid && bad == 0.0 && (log(u32_open(o[2])) < Rr) && Rr != INFINITY;
+  const int acc = c.px_valid && bad == 0.0 && (log_u < Rr) && Rr != INFINITY;
   if (acc && tune) win_set_last(c.w_alpha[c.px_lib]);
   return acc;
 }

@@ -366,6 +366,18 @@ __device__ __forceinline__ void stage_tile(const SweepArgs &a, const FastArgs &f
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 9 * 256), "l"(a.perm + g) : "memory");
 }
 
+// the same with an L2 evict-first policy: the per-gene arrays of a sweep are touched once per generation and are larger than L2
+// together, so they should not displace what IS reused between generations (the scalar stage's code and state, the constants)
+__device__ __forceinline__ uint64_t l2_evict_first_policy() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ void stage_tile_ef(const SweepArgs &a, const FastArgs &fa, int chain, int64_t g, double *stg, uint64_t pol) {
+  const int64_t i = (int64_t)chain * a.G + g;
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stg);
+  const void *src[9] = {a.Yg + i, a.vg + i, fa.lps + i, a.ty + i, a.tv + i, a.gl + g, fa.xbar + g, fa.xss + g, fa.nd_mask + g};
+#pragma unroll
+  for (int j = 0; j < 9; ++j) asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(dst + j * 256), "l"(src[j]), "l"(pol) : "memory");
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(dst + 9 * 256), "l"(a.perm + g), "l"(pol) : "memory");
+}
+
 template <int RT>
 __device__ __noinline__ double detect_logsum_slow(const FastH &H, const MathTabs &T, uint64_t nd_mask, double t) { return detect_logsum<RT>(H, T, nd_mask, t); }
 
@@ -2260,9 +2272,13 @@ int launch_generations(zz_handle *h, uint64_t step0, int ngen, int tune, int hyp
     if (const char *e2 = getenv("ZZ_GEN_BLOCKS")) { const int n = atoi(e2); if (n >= 1 && n < h->gen_blocks) h->gen_blocks = n; }   // tests: a smaller grid
   }
   const int64_t ntiles = (h->G + 31) / 32, need = (ntiles + SWEEP_BLOCK / 32 - 1) / (SWEEP_BLOCK / 32);
+  // one chain: one more CTA, the steward of the scalar stage (zz_persist.cuh); batched chains overlap each other's scalar stages
+  // instead, the last CTA of a chain to finish its tiles runs that chain's stage
+  static const int no_steward = getenv("ZZ_GEN_NO_STEWARD") ? 1 : 0;   // measurement switch
+  const int steward = (C == 1 && !no_steward && h->gen_blocks >= 2) ? 1 : 0;
   int64_t per_chain = h->gen_blocks / C;
   if (per_chain < 1) return fail(h, ZZ_ERR_INVALID, "too many chains for the co-resident grid of the device-resident loop");
-  if (per_chain > need) per_chain = need;
+  if (per_chain > need + steward) per_chain = need + steward;
   GenArgs ga;
   memset(&ga, 0, sizeof ga);
   const double *no_draws[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -2275,6 +2291,7 @@ int launch_generations(zz_handle *h, uint64_t step0, int ngen, int tune, int hyp
   ga.stats_out = h->stats_target;
   static const int dyn_tiles = getenv("ZZ_GEN_STATIC_TILES") ? 0 : 1;   // measurement switch (profiles/r2_summary.md)
   ga.dyn_tiles = dyn_tiles;
+  ga.steward = steward;
   static const long long timeout_s = getenv("ZZ_GEN_TIMEOUT_S") ? atoll(getenv("ZZ_GEN_TIMEOUT_S")) : 20;
   ga.timeout_ns = timeout_s * 1000000000LL;                          // grid barrier of one chain; the peer exchange: ZZ_COMM_TIMEOUT_S
   if (h->comm_ready && h->comm_world > 1) {

@@ -31,12 +31,15 @@ constexpr int FXS_PXDELTA = 7, FXS_PXBAD = 8;
 // One shared counter cannot serve 31 250 tickets per 50 us sweep (1.2 ns per same-address atomic, measured: profiles/r2_ubench.txt),
 // so the dynamic tiles are dealt round-robin into GEN_NQ queues with a counter each; a warp drains its home queue, then the others.
 constexpr int GEN_NQ = 16;
+constexpr int GEN_NREL = 16;
 struct GenCtl {                     // one per chain, device memory
   unsigned arrive;                  // tickets taken (monotone across launches)
   unsigned release;                 // generations published (monotone); GEN_ABORT = give up (time-out)
   unsigned long long ns_leader, ns_stage;   // diagnostics (zz_debug_gen_times): time the last CTA spent between its ticket and the release / in the scalar stage
   unsigned long long ns_phase[6];           // ... and in its phases: load, draws, chains of moves, install + tune_all, derive + propose, write-back
   unsigned pad_[14];
+  unsigned rel[GEN_NREL * 32];      // copies of `release`, one 128-byte line each: CTA b polls rel[b % GEN_NREL], so the 444 pollers of a chain
+                                    // spread over 16 L2 lines (measured: no effect on the stage's duration; kept, it costs 16 stores)
   unsigned tile_q[GEN_NQ * 32];     // dynamic tile scheduling: tickets handed out by each tile queue in the current generation, one
                                     // 128-byte line per counter (same-line atomics serialise in one L2 slice)
 };
@@ -52,6 +55,7 @@ struct GenArgs {
   double *stats_out;                // [C][nstat] or NULL: the (all-reduced) statistics of the last generation run, as doubles
   int do_allreduce; CommArgs cm;    // cm.epoch = epoch of the first generation - 1
   long long timeout_ns;
+  int steward;                      // 1: the last CTA of the (single) chain is the steward of the scalar stage (see k_generations)
   int dyn_tiles;                    // 0: static tile assignment (warp w: tiles w, w + W, ...); 1: static for two rounds, then from the queues
 };
 
@@ -97,6 +101,184 @@ __device__ __forceinline__ bool allreduce_exchange_i64(long long *vec /* shared 
   if (idx < n) vec[idx] = mine;
   __syncthreads();
   return timed_out == 0;
+}
+
+
+// ---- the scalar half of a generation (zz_chain.cuh) as the persistent kernel runs it ------------------------------------------
+// Scratch layout (shared memory; in the last-arriver mode it aliases the first statistic columns of the CTA, which are zero then)
+struct StageScr {
+  long long *ivec; double *st, *gam, *vg_s, *px_lu; L2Params *l2; zz_hyper *h; ChainDev *c; MoveDraws *md; FastH *F; GammaPre *gp;
+};
+constexpr int MAX_NSTAT_P = 3 * (ZZ_MAX_COMP + 1) + 10;
+constexpr int SCR_MD = (2560 + (int)sizeof(ChainDev) + 127) / 128 * 128;
+constexpr int SCR_FH = (SCR_MD + MD_MAX * (int)sizeof(MoveDraws) + 127) / 128 * 128;
+constexpr int SCR_GP = (SCR_FH + (int)sizeof(FastH) + 127) / 128 * 128;
+constexpr int SCR_BYTES = SCR_GP + (ZZ_MAX_COMP + 3) * (int)sizeof(GammaPre);
+static_assert(MAX_NSTAT_P * 8 <= 512 && sizeof(L2Params) <= 256 && sizeof(zz_hyper) <= 1024, "stage scratch layout");
+static_assert(SCR_BYTES <= 8 * SWEEP_BLOCK * 5, "the scratch must fit in the first statistic columns (nstat >= 13 of them)");
+static_assert(sizeof(ChainDev) % 8 == 0 && sizeof(zz_hyper) % 8 == 0 && sizeof(FastH) % 8 == 0, "copied as 64-bit words");
+__device__ __forceinline__ StageScr stage_scr(char *scr) {
+  StageScr S;
+  S.ivec = reinterpret_cast<long long *>(scr);                 // [nstat] totals, fixed point
+  S.st = reinterpret_cast<double *>(scr + 512);                // [nstat] the totals as doubles
+  S.gam = reinterpret_cast<double *>(scr + 1024);              // [K + 3] gamma draws
+  S.vg_s = reinterpret_cast<double *>(scr + 1152);             // (s0, s1, tau) after the variance-prior moves
+  S.px_lu = reinterpret_cast<double *>(scr + 1184);            // log of mhP_x's accept uniform
+  S.l2 = reinterpret_cast<L2Params *>(scr + 1280);
+  S.h = reinterpret_cast<zz_hyper *>(scr + 1536);
+  S.c = reinterpret_cast<ChainDev *>(scr + 2560);
+  S.md = reinterpret_cast<MoveDraws *>(scr + SCR_MD);          // [MD_MAX] the prepared draws of the Metropolis moves
+  S.F = reinterpret_cast<FastH *>(scr + SCR_FH);               // the next generation's constants, staged (no global read-backs)
+  S.gp = reinterpret_cast<GammaPre *>(scr + SCR_GP);           // [K + 3] the statistics-independent part of the gamma draws
+  return S;
+}
+// totals of the generation -> S.st (all-reduced over the gene shards); whole CTA.  false: a peer timed out (fail-stop)
+__device__ __forceinline__ bool stage_totals(const StageScr &S, const GenArgs &ga, GenCtl *ctl, long long *gacc, int nstat, int chain, int gi) {
+  if ((int)threadIdx.x < nstat) { S.ivec[threadIdx.x] = (long long)__ldcg(reinterpret_cast<const unsigned long long *>(gacc + threadIdx.x)); gacc[threadIdx.x] = 0; }
+  if (threadIdx.x < GEN_NQ) ctl->tile_q[threadIdx.x * 32] = 0;
+  __syncthreads();
+  bool ok = true;
+  if (ga.do_allreduce) {
+    CommArgs cm = ga.cm;
+    cm.epoch += (unsigned long long)gi + 1ull;
+    cm.base += (int64_t)chain * 2 * cm.world * cm.stride;
+    ok = allreduce_exchange_i64(S.ivec, nstat, cm, cm.timeout_ns);
+  }
+  if ((int)threadIdx.x < nstat) {
+    S.st[threadIdx.x] = ok ? (double)S.ivec[threadIdx.x] * (1.0 / FX_SCALE) : NAN;
+    if (ga.stats_out) ga.stats_out[(int64_t)chain * nstat + threadIdx.x] = S.st[threadIdx.x];
+  }
+  if (!ok) {                                            // a peer never showed up: fail-stop (flag bit 2), nobody consumes the stale words
+    if (threadIdx.x == 0) { atomicOr(ga.fa.s.nan_flag, 4); __threadfence(); }
+    __syncthreads();
+    if (threadIdx.x < GEN_NREL) st_release_u32(&ctl->rel[threadIdx.x * 32], GEN_ABORT);
+    if (threadIdx.x == 0) st_release_u32(&ctl->release, GEN_ABORT);
+  }
+  __syncthreads();
+  return ok;
+}
+__device__ __forceinline__ void stage_load(const StageScr &S, const GenArgs &ga, int chain) {      // written by another SM / kernel: through L2
+  const uint64_t *s0 = reinterpret_cast<const uint64_t *>(ga.chain + chain), *s1 = reinterpret_cast<const uint64_t *>(ga.hyper + chain);
+  uint64_t *d0 = reinterpret_cast<uint64_t *>(S.c), *d1 = reinterpret_cast<uint64_t *>(S.h);
+  for (int j = threadIdx.x; j < (int)(sizeof(ChainDev) / 8); j += blockDim.x) d0[j] = __ldcg(s0 + j);
+  for (int j = threadIdx.x; j < (int)(sizeof(zz_hyper) / 8); j += blockDim.x) d1[j] = __ldcg(s1 + j);
+}
+__device__ __forceinline__ void stage_store(const StageScr &S, const GenArgs &ga, int chain) {
+  uint64_t *d0 = reinterpret_cast<uint64_t *>(ga.chain + chain), *d1 = reinterpret_cast<uint64_t *>(ga.hyper + chain);
+  const uint64_t *s0 = reinterpret_cast<const uint64_t *>(S.c), *s1 = reinterpret_cast<const uint64_t *>(S.h);
+  for (int j = threadIdx.x; j < (int)(sizeof(ChainDev) / 8); j += blockDim.x) d0[j] = s0[j];
+  for (int j = threadIdx.x; j < (int)(sizeof(zz_hyper) / 8); j += blockDim.x) d1[j] = s1[j];
+}
+// everything of the generation's scalar stage that needs no statistics: every random draw, one lane per draw
+__device__ __forceinline__ void stage_pre(const StageScr &S, const MathTabs &T, const SweepArgs &a, uint64_t step) {
+  const int K = a.K, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const SMath sm{&T};
+  if (wid == 0) stage_gibbs_predraw(sm, *S.c, a.seed, step, K, lane, S.gp);
+  else if (wid == 4 && lane < MD_AMD + K) make_move_draws(sm, S.md[lane], a.seed, (uint32_t)S.c->chain, step, lane);
+  else if (wid == 3 && lane == 0) *S.px_lu = px_log_u(*S.c, a.seed, step);
+}
+// the moves themselves, from the totals in S.st: new hyper-parameters in S.h, scalar state in S.c, the next sweep's constants in
+// S.F and in global memory.  Whole CTA; the caller fences and releases the grid afterwards.
+template <int KT>
+__device__ __forceinline__ void stage_post(const StageScr &S, const MathTabs &T, const GenArgs &ga, GenCtl *ctl, uint64_t step, bool last, int chain) {
+  const SweepArgs &a = ga.fa.s;
+  const int K = a.K, R = a.R, K1 = K + 1, tune = a.tune, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const SMath sm{&T};
+  ChainDev &c_s = *S.c; zz_hyper &h_s = *S.h; FastH &F_s = *S.F; L2Params &l2_s = *S.l2;
+  const double *st = S.st;
+  unsigned long long tp0 = globaltimer_ns(), tp1;
+#ifdef ZZ_GEN_PROFILE   /* per-phase times of the stage (each probe costs a global read-modify-write, ~0.5 us) */
+#define ZZ_PHASE(j) do { if (threadIdx.x == 0) { tp1 = globaltimer_ns(); ctl->ns_phase[j] += tp1 - tp0; tp0 = tp1; } } while (0)
+#else
+#define ZZ_PHASE(j) do { (void)tp0; (void)tp1; (void)ctl; } while (0)
+#endif
+  // phase A: the Gibbs draws (gamma variates at the counts just reduced)
+  if (wid == 0) {
+    stage_gibbs_draws(sm, c_s, h_s, a.seed, step, st, K, lane, S.gp, S.gam);
+    __syncwarp();
+    if (lane == 0) stage_gibbs_combine(h_s, K, S.gam);
+  }
+  // phase B (does not read what phase A writes): the chains of moves side by side (mhInactiveMeans and mhActiveMeansDif touch disjoint parameters)
+  else if (wid == 1 && lane == 0) stage_amd<KT>(sm, c_s, h_s, S.md, st, tune, l2_s.am);
+  else if (wid == 5 && lane == 0) l2_s.im = stage_im(sm, c_s, h_s, S.md, st, K, tune);
+  else if (wid == 2 && lane == 0) stage_varg(sm, c_s, h_s, S.md, st, K, tune, S.vg_s[0], S.vg_s[1], S.vg_s[2]);
+  else if (wid == 3 && lane == 0) {
+    const int acc = px_decide(c_s, h_s, *S.px_lu, st[3 * K1 + FXS_PXDELTA], st[3 * K1 + FXS_PXBAD], tune);
+    if (acc) h_s.alpha_r[c_s.px_lib] = c_s.px_alpha;               // Pr:234-239
+    c_s.px_prev_acc = acc; c_s.px_valid = 0;
+    if (!last) px_propose(c_s, h_s, a.seed, step + (uint64_t)ga.step_stride, tune, R);   // the next generation's mhP_x (after a segment: k_gen_prepare)
+  }
+  __syncthreads();
+  ZZ_PHASE(2);
+  if (threadIdx.x == 0) {                                          // mhSharedVariance at the means just decided; install everything
+    const double av = stage_sv<KT>(sm, c_s, h_s, S.md, st, tune, l2_s.im, l2_s.am);
+    h_s.inactive_means = l2_s.im;
+    for (int k = 0; k < K; ++k) h_s.active_means[k] = l2_s.am[k];
+    if (!isnan(av)) { h_s.inactive_variances = av; for (int k = 0; k < K; ++k) h_s.active_variances[k] = av; }
+    h_s.s0 = S.vg_s[0]; h_s.s1 = S.vg_s[1]; h_s.tau = S.vg_s[2];
+    c_s.step += (uint64_t)ga.step_stride; c_s.gen += 1;
+  }
+  __syncthreads();
+  if (last && ga.do_tune_all_last)                                 // B:146 tune_all, scalar part (the per-gene part follows the launch)
+    for (int l = threadIdx.x; l < R + K + 6; l += blockDim.x) tune_all_scalars(c_s, ga.target, K, R, l);
+  ZZ_PHASE(3);
+  // the next generation's constants, one group of fields per thread
+  derive_fast_par(F_s, &h_s, threadIdx.x);
+  __syncthreads();
+  if (threadIdx.x == 0) { derive_fin(F_s, &h_s); set_px(F_s, h_s, c_s); }
+  __syncthreads();
+  {
+    uint64_t *dF = reinterpret_cast<uint64_t *>(ga.fasth_rw + chain);
+    const uint64_t *sF = reinterpret_cast<const uint64_t *>(&F_s);
+    for (int j = threadIdx.x; j < (int)(sizeof(FastH) / 8); j += blockDim.x) dF[j] = sF[j];
+  }
+  ZZ_PHASE(4);
+#undef ZZ_PHASE
+}
+
+// The steward CTA of a one-chain launch (see k_generations).  Critical path per generation: last ticket -> totals -> stage_post ->
+// release; the state load, every draw and the write-back of the state are off it.
+template <int KT>
+__device__ __noinline__ void steward_loop(const GenArgs &ga, const MathTabs &T, char *scr, GenCtl *ctl, long long *gacc, int nstat, int chain, unsigned n_workers) {
+  __shared__ unsigned sh_ok;
+  const SweepArgs &a = ga.fa.s;
+  const StageScr S = stage_scr(scr);
+  if (ga.hyper_moves) stage_load(S, ga, chain);
+  __syncthreads();
+  for (int gi = 0; gi < ga.ngen; ++gi) {
+    const uint64_t step = a.step + (uint64_t)ga.step_stride * (uint64_t)gi;
+    if (ga.hyper_moves) stage_pre(S, T, a, step);
+    if (threadIdx.x == 0) {                                          // all tickets of this generation
+      const unsigned want = ((unsigned)gi + 1u) * n_workers;
+      const unsigned long long t0 = globaltimer_ns();
+      unsigned ok = 1;
+      while (ld_acquire_u32(&ctl->arrive) < want)
+        if ((long long)(globaltimer_ns() - t0) > ga.timeout_ns) { ok = 0; break; }
+      sh_ok = ok;
+    }
+    __syncthreads();
+    if (!sh_ok) {
+      if (threadIdx.x == 0) { atomicOr(a.nan_flag, 8); __threadfence(); }
+      __syncthreads();
+      if (threadIdx.x < GEN_NREL) st_release_u32(&ctl->rel[threadIdx.x * 32], GEN_ABORT);
+      if (threadIdx.x == 0) st_release_u32(&ctl->release, GEN_ABORT);
+      break;
+    }
+    const unsigned long long t_lead0 = globaltimer_ns();
+    if (!stage_totals(S, ga, ctl, gacc, nstat, chain, gi)) break;
+    const unsigned long long t_stage0 = globaltimer_ns();
+    if (ga.hyper_moves) stage_post<KT>(S, T, ga, ctl, step, gi == ga.ngen - 1, chain);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x < GEN_NREL) st_release_u32(&ctl->rel[threadIdx.x * 32], (unsigned)gi + 1u);
+    if (threadIdx.x == 0) {
+      const unsigned long long t1 = globaltimer_ns();
+      ctl->ns_leader += t1 - t_lead0; ctl->ns_stage += t1 - t_stage0;
+      st_release_u32(&ctl->release, (unsigned)gi + 1u);
+    }
+    if (ga.hyper_moves) stage_store(S, ga, chain);                   // for the host and the kernels after the launch
+    __syncthreads();
+  }
 }
 
 // mhSpikeAllocation (Pr:528-638) for one all-zero, inactive gene of the persistent kernel.  Works on the gene's global-memory
@@ -162,22 +344,33 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
   long long *gacc = ga.acc + (int64_t)chain * nstat;
   for (int s = 0; s < nstat; ++s) acc[s * SWEEP_BLOCK + threadIdx.x] = 0;
   load_tabs(T, fa.exp_tab, fa.log_tab);
+  // steward mode (one chain): the LAST CTA sweeps no tiles — it keeps the chain's scalar state in its shared memory for the whole
+  // launch, prepares everything of the coming scalar stage that needs no statistics while the others sweep, and counts tickets
+  const unsigned n_cta = gridDim.x - (ga.steward ? 1u : 0u);           // CTAs that sweep tiles
+  if (ga.steward && blockIdx.x == n_cta) {
+    __syncthreads();
+    steward_loop<KT>(ga, T, reinterpret_cast<char *>(dyn_smem), ctl, gacc, nstat, chain, n_cta);
+    return;
+  }
   const int ntiles = (int)((a.g_end - a.g_begin + 31) / 32);
-  const int warp0 = (int)blockIdx.x * (SWEEP_BLOCK / 32) + wid, nwarps = (int)gridDim.x * (SWEEP_BLOCK / 32);
+  const int warp0 = (int)blockIdx.x * (SWEEP_BLOCK / 32) + wid, nwarps = (int)n_cta * (SWEEP_BLOCK / 32);
   double *stg = dyn_smem + (int64_t)nstat * SWEEP_BLOCK + wid * 320 + lane;
   bool saw_nan = false;
-  const unsigned n_cta = gridDim.x;
+  const uint64_t pol = l2_evict_first_policy();
 
   for (int gi = 0; gi < ga.ngen; ++gi) {
     const unsigned gen_no = (unsigned)gi;
     // ---- 1. this generation's hyper-parameters are published once release >= gen_no
     if (threadIdx.x == 0) {
-      unsigned r = ld_acquire_u32(&ctl->release);
+      const unsigned *relp = &ctl->rel[(blockIdx.x % GEN_NREL) * 32];
+      unsigned r = ld_acquire_u32(relp);
       if (r < gen_no) {
         const unsigned long long t0 = globaltimer_ns();
-        while ((r = ld_acquire_u32(&ctl->release)) < gen_no) {
+        unsigned ns = 32;
+        while ((r = ld_acquire_u32(relp)) < gen_no) {
           if ((long long)(globaltimer_ns() - t0) > ga.timeout_ns) { r = GEN_ABORT; break; }
-          __nanosleep(40);
+          __nanosleep(ns);
+          if (ns < 256) ns += ns;                                       // back off: the scalar stage lasts microseconds
         }
       }
       sh_rel = r;
@@ -203,7 +396,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
     unsigned ticket = 0;
     if (t_ >= 0) {
       const int64_t g0 = a.g_begin + (int64_t)(ntiles - 1 - t_) * 32 + lane;
-      if (g0 < a.g_end) { stage_tile(a, fa, chain, g0, stg); f_next = a.flags[(int64_t)chain * a.G + g0]; }
+      if (g0 < a.g_end) { stage_tile_ef(a, fa, chain, g0, stg, pol); f_next = a.flags[(int64_t)chain * a.G + g0]; }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     while (t_ >= 0) {
@@ -226,7 +419,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
       }
       // every staged word of this tile is in registers: refill the slots with the warp's next tile, whose HBM latency then hides
       // behind this tile's ~1300 instructions (also for the lanes beyond the end of a ragged tile: their next tile is a full one)
-      if (next_valid) stage_tile(a, fa, chain, g_n, stg);
+      if (next_valid) stage_tile_ef(a, fa, chain, g_n, stg, pol);
       asm volatile("cp.async.commit_group;" ::: "memory");
       // the tile after the next one: ask the home queue now, read the answer when this tile is done
       // (inline asm: the compiler would otherwise sink the atomic down to the shuffle that reads it and expose its whole latency)
@@ -292,10 +485,10 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
       if (a_new && row_ok) f = flag_set_k(f, kn);
       // ---- stores (the two likelihood caches of the reference are not maintained inside a device-resident segment)
       a.flags[i] = (uint16_t)f;
-      if (live) { a.Yg[i] = y1; a.vg[i] = v1; fa.lps[i] = A1; }
+      if (live) { __stcs(a.Yg + i, y1); __stcs(a.vg + i, v1); __stcs(fa.lps + i, A1); }   // streaming stores (L2 evict-first)
       if (a.tune && live) {                                              // Pr:312-322, Pr:40-50
-        ulonglong2 w = a.win_y[i]; window_push(w, acc_y); a.win_y[i] = w;
-        w = a.win_v[i]; window_push(w, acc_v); a.win_v[i] = w;
+        ulonglong2 w = __ldcs(a.win_y + i); window_push(w, acc_y); __stcs(a.win_y + i, w);
+        w = __ldcs(a.win_v + i); window_push(w, acc_v); __stcs(a.win_v + i, w);
       }
       saw_nan |= live && (isnan(ratio_y) || isnan(ratio_v) || bad);
       double ys = y1, lvs = lv1;
@@ -375,132 +568,38 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
     }
     __threadfence();
     __syncthreads();
-    // ---- 4. ticket; the last CTA of the chain runs the scalar half of the generation
+    // ---- 4. ticket.  Steward mode: done, the steward CTA counts the tickets.  Otherwise the last CTA of the chain to arrive runs the
+    // scalar half of the generation.
     if (threadIdx.x == 0) sh_ticket = atomicAdd(&ctl->arrive, 1u);
+    if (ga.steward) continue;
     __syncthreads();
     if (sh_ticket != (gen_no + 1u) * n_cta - 1u) continue;
     __threadfence();
     const unsigned long long t_lead0 = globaltimer_ns();
-    unsigned long long t_stage0 = t_lead0;
-    {
-      // the statistic columns are zero again: that memory is the stage's scratch (zeroed again below)
-      char *scr = reinterpret_cast<char *>(dyn_smem);
-      long long *ivec = reinterpret_cast<long long *>(scr);                          // [nstat] totals, fixed point
-      double *st = reinterpret_cast<double *>(scr + 512);                            // [nstat] the totals as doubles
-      double *gam = reinterpret_cast<double *>(scr + 1024);                          // [K + 3] gamma draws
-      double *vg_s = reinterpret_cast<double *>(scr + 1152);                         // (s0, s1, tau) after warp 2
-      int *acc_s = reinterpret_cast<int *>(scr + 1184);                              // accept bits of warp 2 / warp 3
-      L2Params &l2_s = *reinterpret_cast<L2Params *>(scr + 1280);
-      zz_hyper &h_s = *reinterpret_cast<zz_hyper *>(scr + 1536);
-      ChainDev &c_s = *reinterpret_cast<ChainDev *>(scr + 2560);
-      constexpr int MD_OFF = (2560 + (int)sizeof(ChainDev) + 127) / 128 * 128;
-      MoveDraws *md_s = reinterpret_cast<MoveDraws *>(scr + MD_OFF);                 // [MD_MAX] the prepared draws of the Metropolis moves
-      constexpr int FH_OFF = (MD_OFF + MD_MAX * (int)sizeof(MoveDraws) + 127) / 128 * 128;
-      FastH &F_s = *reinterpret_cast<FastH *>(scr + FH_OFF);                         // the next generation's constants, staged (no global read-backs)
-      constexpr int SCR_BYTES = FH_OFF + (int)sizeof(FastH);
-      static_assert(MAX_NSTAT_ * 8 <= 512 && sizeof(L2Params) <= 256 && sizeof(zz_hyper) <= 1024, "stage scratch layout");
-      static_assert(SCR_BYTES <= 8 * SWEEP_BLOCK * 5, "the scratch must fit in the first statistic columns (nstat >= 13 of them)");
-      if ((int)threadIdx.x < nstat) { ivec[threadIdx.x] = (long long)__ldcg(reinterpret_cast<const unsigned long long *>(gacc + threadIdx.x)); gacc[threadIdx.x] = 0; }
-      if (threadIdx.x < GEN_NQ) ctl->tile_q[threadIdx.x * 32] = 0;
+    // the statistic columns are zero again: that memory is the stage's scratch (zeroed again below)
+    const StageScr S = stage_scr(reinterpret_cast<char *>(dyn_smem));
+    const bool ok = stage_totals(S, ga, ctl, gacc, nstat, chain, gi);
+    if (!ok) break;
+    const unsigned long long t_stage0 = globaltimer_ns();
+    if (ga.hyper_moves) {
+      stage_load(S, ga, chain);
       __syncthreads();
-      bool ok = true;
-      if (ga.do_allreduce) {
-        CommArgs cm = ga.cm;
-        cm.epoch += (unsigned long long)gi + 1ull;
-        cm.base += (int64_t)chain * 2 * cm.world * cm.stride;
-        ok = allreduce_exchange_i64(ivec, nstat, cm, cm.timeout_ns);
-      }
-      if ((int)threadIdx.x < nstat) {
-        st[threadIdx.x] = ok ? (double)ivec[threadIdx.x] * (1.0 / FX_SCALE) : NAN;
-        if (ga.stats_out) ga.stats_out[(int64_t)chain * nstat + threadIdx.x] = st[threadIdx.x];
-      }
-      if (!ok) {                                            // a peer never showed up: fail-stop (flag bit 2), nobody consumes the stale words
-        if (threadIdx.x == 0) { atomicOr(a.nan_flag, 4); __threadfence(); st_release_u32(&ctl->release, GEN_ABORT); }
-        break;
-      }
-      t_stage0 = globaltimer_ns();
-      if (ga.hyper_moves) {
-        static_assert(sizeof(ChainDev) % 8 == 0 && sizeof(zz_hyper) % 8 == 0, "copied as 64-bit words");
-        {
-          const uint64_t *s0 = reinterpret_cast<const uint64_t *>(ga.chain + chain), *s1 = reinterpret_cast<const uint64_t *>(ga.hyper + chain);
-          uint64_t *d0 = reinterpret_cast<uint64_t *>(&c_s), *d1 = reinterpret_cast<uint64_t *>(&h_s);
-          for (int j = threadIdx.x; j < (int)(sizeof(ChainDev) / 8); j += blockDim.x) d0[j] = __ldcg(s0 + j);   // written by another SM
-          for (int j = threadIdx.x; j < (int)(sizeof(zz_hyper) / 8); j += blockDim.x) d1[j] = __ldcg(s1 + j);
-        }
-        __syncthreads();
-        unsigned long long tp0 = globaltimer_ns(), tp1;
-#ifdef ZZ_GEN_PROFILE   /* per-phase times of the stage (each probe costs a global read-modify-write, ~0.5 us) */
-#define ZZ_PHASE(j) do { if (threadIdx.x == 0) { tp1 = globaltimer_ns(); ctl->ns_phase[j] += tp1 - tp0; tp0 = tp1; } } while (0)
-        if (threadIdx.x == 0) { ctl->ns_phase[0] += tp0 - t_stage0; }
-#else
-#define ZZ_PHASE(j) do { (void)tp0; (void)tp1; } while (0)
-#endif
-        const int K = a.K, R = a.R, tune = a.tune;
-        const bool last = gi == ga.ngen - 1;
-        const SMath sm{&T};
-        // phase A: every random draw of the generation, one lane per draw
-        if (wid == 0) {
-          stage_gibbs_draws(sm, c_s, h_s, a.seed, step, st, K, lane, gam);
-          __syncwarp();
-          if (lane == 0) stage_gibbs_combine(h_s, K, gam);
-        } else if (wid == 4 && lane < MD_AMD + K) make_move_draws(sm, md_s[lane], a.seed, (uint32_t)c_s.chain, step, lane);
-        __syncthreads();
-        ZZ_PHASE(1);
-        // phase B: the chains of moves side by side (mhInactiveMeans and mhActiveMeansDif touch disjoint parameters)
-        if (wid == 1 && lane == 0) stage_amd<KT>(sm, c_s, h_s, md_s, st, tune, l2_s.am);
-        else if (wid == 5 && lane == 0) l2_s.im = stage_im(sm, c_s, h_s, md_s, st, K, tune);
-        else if (wid == 2 && lane == 0) stage_varg(sm, c_s, h_s, md_s, st, K, tune, vg_s[0], vg_s[1], vg_s[2]);
-        else if (wid == 3 && lane == 0) {
-          const int acc = px_decide(c_s, h_s, a.seed, step, st[3 * K1 + FXS_PXDELTA], st[3 * K1 + FXS_PXBAD], tune);
-          if (acc) h_s.alpha_r[c_s.px_lib] = c_s.px_alpha;               // Pr:234-239
-          c_s.px_prev_acc = acc; c_s.px_valid = 0;
-          if (!last) px_propose(c_s, h_s, a.seed, step + (uint64_t)ga.step_stride, tune, R);   // the next generation's mhP_x (after a segment: k_gen_prepare)
-        }
-        __syncthreads();
-        ZZ_PHASE(2);
-        if (threadIdx.x == 0) {                                          // mhSharedVariance at the means just decided; install everything
-          const double av = stage_sv<KT>(sm, c_s, h_s, md_s, st, tune, l2_s.im, l2_s.am);
-          h_s.inactive_means = l2_s.im;
-          for (int k = 0; k < K; ++k) h_s.active_means[k] = l2_s.am[k];
-          if (!isnan(av)) { h_s.inactive_variances = av; for (int k = 0; k < K; ++k) h_s.active_variances[k] = av; }
-          h_s.s0 = vg_s[0]; h_s.s1 = vg_s[1]; h_s.tau = vg_s[2];
-          c_s.step += (uint64_t)ga.step_stride; c_s.gen += 1;
-        }
-        __syncthreads();
-        if (last && ga.do_tune_all_last)                                 // B:146 tune_all, scalar part (the per-gene part follows the launch)
-          for (int l = threadIdx.x; l < R + K + 6; l += blockDim.x) tune_all_scalars(c_s, ga.target, K, R, l);
-        ZZ_PHASE(3);
-        // the next generation's constants, one group of fields per thread
-        derive_fast_par(F_s, &h_s, threadIdx.x);
-        __syncthreads();
-        if (threadIdx.x == 0) { derive_fin(F_s, &h_s); set_px(F_s, h_s, c_s); }
-        __syncthreads();
-        {
-          uint64_t *dF = reinterpret_cast<uint64_t *>(ga.fasth_rw + chain);
-          const uint64_t *sF = reinterpret_cast<const uint64_t *>(&F_s);
-          for (int j = threadIdx.x; j < (int)(sizeof(FastH) / 8); j += blockDim.x) dF[j] = sF[j];
-        }
-        ZZ_PHASE(4);
-        {
-          uint64_t *d0 = reinterpret_cast<uint64_t *>(ga.chain + chain), *d1 = reinterpret_cast<uint64_t *>(ga.hyper + chain);
-          const uint64_t *s0 = reinterpret_cast<const uint64_t *>(&c_s), *s1 = reinterpret_cast<const uint64_t *>(&h_s);
-          for (int j = threadIdx.x; j < (int)(sizeof(ChainDev) / 8); j += blockDim.x) d0[j] = s0[j];
-          for (int j = threadIdx.x; j < (int)(sizeof(zz_hyper) / 8); j += blockDim.x) d1[j] = s1[j];
-        }
-        ZZ_PHASE(5);
-#undef ZZ_PHASE
-      }
-      __threadfence();
+      stage_pre(S, T, a, step);
       __syncthreads();
-      if (threadIdx.x == 0) {
-        const unsigned long long t1 = globaltimer_ns();
-        ctl->ns_leader += t1 - t_lead0; ctl->ns_stage += t1 - t_stage0;
-        st_release_u32(&ctl->release, gen_no + 1u);
-      }
-      // the columns this CTA borrowed must be zero again before its next tile
-      for (int j = threadIdx.x; j < (SCR_BYTES + 7) / 8; j += blockDim.x) dyn_smem[j] = 0.0;
-      __syncthreads();
+      stage_post<KT>(S, T, ga, ctl, step, gi == ga.ngen - 1, chain);
+      stage_store(S, ga, chain);
     }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x < GEN_NREL) st_release_u32(&ctl->rel[threadIdx.x * 32], gen_no + 1u);
+    if (threadIdx.x == 0) {
+      const unsigned long long t1 = globaltimer_ns();
+      ctl->ns_leader += t1 - t_lead0; ctl->ns_stage += t1 - t_stage0;
+      st_release_u32(&ctl->release, gen_no + 1u);
+    }
+    // the columns this CTA borrowed must be zero again before its next tile
+    for (int j = threadIdx.x; j < (SCR_BYTES + 7) / 8; j += blockDim.x) dyn_smem[j] = 0.0;
+    __syncthreads();
   }
   if (saw_nan) atomicOr(a.nan_flag, 1);
 }
