@@ -1,19 +1,43 @@
-# zigzagGPU.R — overlay for the zigzag R package: after `gpu_attach()` the five per-gene entries of `proposal_list`
-# (R/zigzagInitialize.R:207-221) and the O(G) sums inside the hyper-parameter moves run on the GPU through src/zz_shim.c.
-# zigzag$new()/burnin()/mcmc(), the output files and mcmc_report are untouched: they read the same fields, which
-# `gpu_pull()` refreshes from the device at sample time.  Needs `useDynLib(zigzag, .registration = TRUE)` in NAMESPACE.
+# zigzagGPU.R — GPU drop-in for the zigzag R package (add this file as R/zigzagGPU.R, r_overlay/src/zz_shim.c as src/zz_shim.c,
+# `useDynLib(zigzag, .registration = TRUE)` to NAMESPACE and link -lzigzag_gpu).
+#
+# `zigzagGPU` is a subclass of the reference class `zigzag` (R/zigzag.R:113): zigzagGPU$new(...) takes the same arguments,
+# burnin() / mcmc() / the output files / mcmc_report are the reference's own code.  What changes:
+#   * the five per-gene entries of `proposal_list` (R/zigzagInitialize.R:207-221) are kernel launches on device-resident state;
+#   * the ten hyper-parameter moves are overridden below: same proposals, priors, accept rule and trace bookkeeping as
+#     R/zigzagProposals.R, but every sum over genes comes from the device (the R copies of Yg, variance_g, the allocations and the
+#     two likelihood caches are NOT current between sampling points, so nothing may read them inside a move);
+#   * at every sampling point of burnin() (R/zigzagBurnin.R:88-131) and mcmc() (R/zigzagMCMC.R:188-217) the per-gene fields are
+#     refreshed from the device BEFORE the reference's sample block reads them: each move ends with gpu_after_move(), which pulls
+#     when the current generation is a sampling generation and a per-gene move has run since the last pull;
+#   * tune_all (R/zigzagUtilities.R:183-240): scalar parameters by the reference's code, per-gene ones on the device (zz_tune).
+# Only the default model (shared_variance = TRUE, shared_active_variance = TRUE) is covered: the weight-0 moves
+# mhInactiveVariances / mhActiveVariances are not overridden.
+# Every .Call below is registered in src/zz_shim.c; tests/test_r_overlay.py checks names and argument counts of both files.
 
-zigzag$methods(
+zigzagGPU <- setRefClass(
+  "zigzagGPU",
+  contains = "zigzag",
+  fields = list(gpu = "ANY", gpu_step = "numeric", gpu_dirty = "logical", gpu_sample_frequency = "numeric",
+                gpu_in_burnin = "logical", gpu_hyper_ctr = "numeric", gpu_hyper_buf = "numeric", gpu_n_samples = "numeric"),
+  methods = list(
+
+  initialize = function(..., gpu_seed = 1, gpu_device = 0){
+    callSuper(...)
+    if(!shared_variance || !shared_active_variance) stop("zigzagGPU covers the default shared-variance model only")
+    .self$gpu_attach(gpu_seed, gpu_device)
+  },
 
   gpu_attach = function(seed = 1, device = 0){
     .self$gpu <- .Call("zzR_create", Xg, gene_lengths, as.integer(num_active_components), as.numeric(seed), as.integer(device))
-    .self$gpu_step <- 0
+    .self$gpu_step <- 0; .self$gpu_dirty <- FALSE; .self$gpu_sample_frequency <- Inf; .self$gpu_in_burnin <- FALSE
+    .self$gpu_hyper_ctr <- 0; .self$gpu_hyper_buf <- numeric(4); .self$gpu_n_samples <- 0
     pinned <- NULL
-    if(!is.null(active_gene_set)){ pinned <- integer(num_transcripts); pinned[active_gene_set_idx] <- 1L }
+    if(length(active_gene_set_idx) > 0){ pinned <- integer(num_transcripts); pinned[active_gene_set_idx] <- 1L }
     .Call("zzR_set_state", gpu, Yg, variance_g, as.integer(allocation_active_inactive), as.integer(allocation_within_active[[1]]),
           as.integer(inactive_spike_allocation), XgLikelihood, variance_g_probability, tuningParam_yg, tuningParam_variance_g, pinned)
     .self$gpu_push_hyper()
-    # swap the per-gene table entries (same signature: function(recover_x = FALSE, tune = FALSE))
+    # the per-gene table entries (same signature: function(recover_x = FALSE, tune = FALSE))
     .self$proposal_list[[2]]  <- .self$gpu_gibbsAllocationActiveInactive
     .self$proposal_list[[3]]  <- .self$gpu_gibbsAllocationWithinActive
     .self$proposal_list[[9]]  <- .self$gpu_mhSpikeAllocation
@@ -28,7 +52,7 @@ zigzag$methods(
 
   gpu_next = function(){ .self$gpu_step <- gpu_step + 1; gpu_step },
 
-  # device -> fields; called where the drivers read per-gene state (R/zigzagBurnin.R:116-131, R/zigzagMCMC.R:194-217)
+  # device -> fields (everything the reference's sample blocks, file writers and reports read)
   gpu_pull = function(){
     st <- .Call("zzR_get_state", gpu, num_transcripts)
     .self$Yg <- st$Yg; .self$variance_g <- st$variance_g
@@ -38,20 +62,140 @@ zigzag$methods(
     .self$XgLikelihood <- st$XgLikelihood; .self$variance_g_probability <- st$variance_g_probability
     .self$tuningParam_yg <- st$tuningParam_yg; .self$tuningParam_variance_g <- st$tuningParam_variance_g
     .self$setActiveInactive_idx(); .self$setInSpike_idx(); .self$set_sigmaX_pX()
+    .self$gpu_dirty <- FALSE
   },
 
-  gpu_mhYg = function(recover_x = FALSE, tune = FALSE) .Call("zzR_mh_yg", gpu, gpu_next(), tune),
-  gpu_mhVariance_g = function(recover_x = FALSE, tune = FALSE) .Call("zzR_mh_variance_g", gpu, gpu_next(), tune),
-  gpu_gibbsAllocationActiveInactive = function(recover_x = FALSE, tune = FALSE) .Call("zzR_gibbs_alloc", gpu, gpu_next()),
-  gpu_gibbsAllocationWithinActive = function(recover_x = FALSE, tune = FALSE) .Call("zzR_gibbs_alloc_within", gpu, gpu_next()),
-  gpu_mhSpikeAllocation = function(recover_x = FALSE, tune = FALSE) .Call("zzR_mh_spike_alloc", gpu, gpu_next()),
+  # called at the end of EVERY move: the last move of a sampling generation leaves current fields behind for the sample block
+  # (burnin samples when i %% sample_frequency == 0 & i > 2 * sample_frequency with i == gen, B:88; mcmc when gen %% sample_frequency == 0, M:188)
+  gpu_after_move = function(){
+    if(gpu_dirty && is.finite(gpu_sample_frequency) && gen %% gpu_sample_frequency == 0 &&
+       (!gpu_in_burnin || gen > 2 * gpu_sample_frequency)) .self$gpu_pull()
+    if(.Call("zzR_nan_flag", gpu)) .self$Yg[1] <- NA          # trips the reference's NA guard (B:69-78)
+  },
 
-  # example of a hyper-parameter move whose sums come from the device (R/zigzagProposals.R:119-152); the others follow suit
-  mhTau = function(recover_x = FALSE, tune = FALSE){
+  burnin = function(sample_frequency = 100, ...){
+    .self$gpu_sample_frequency <- sample_frequency; .self$gpu_in_burnin <- TRUE
+    on.exit({ .self$gpu_in_burnin <- FALSE; .self$gpu_pull() })
+    callSuper(sample_frequency = sample_frequency, ...)
+  },
+
+  mcmc = function(sample_frequency = 100, ...){
+    .self$gpu_sample_frequency <- sample_frequency; .self$gpu_in_burnin <- FALSE
+    .self$gpu_pull()                                            # M:142-145 starts allocation_trace from the current allocation
+    on.exit(.self$gpu_pull())
+    callSuper(sample_frequency = sample_frequency, ...)
+  },
+
+  # ---- the five per-gene moves --------------------------------------------------------------------------------------------
+  gpu_mhYg = function(recover_x = FALSE, tune = FALSE){
+    .Call("zzR_mh_yg", gpu, gpu_next(), tune); .self$gpu_dirty <- TRUE; .self$gpu_after_move() },
+  gpu_mhVariance_g = function(recover_x = FALSE, tune = FALSE){
+    .Call("zzR_mh_variance_g", gpu, gpu_next(), tune); .self$gpu_dirty <- TRUE; .self$gpu_after_move() },
+  gpu_gibbsAllocationActiveInactive = function(recover_x = FALSE, tune = FALSE){
+    .Call("zzR_gibbs_alloc", gpu, gpu_next()); .self$gpu_dirty <- TRUE; .self$gpu_after_move() },
+  gpu_gibbsAllocationWithinActive = function(recover_x = FALSE, tune = FALSE){
+    .Call("zzR_gibbs_alloc_within", gpu, gpu_next()); .self$gpu_dirty <- TRUE; .self$gpu_after_move() },
+  gpu_mhSpikeAllocation = function(recover_x = FALSE, tune = FALSE){
+    .Call("zzR_mh_spike_alloc", gpu, gpu_next()); .self$gpu_dirty <- TRUE; .self$gpu_after_move() },
+
+  # ---- hyper-parameter moves: R/zigzagProposals.R with the gene sums taken from the device ---------------------------------------
+  # counts and sums per component: zz_suffstats (layout in include/zigzag_gpu.h)
+  gpu_counts = function(){
+    st <- .Call("zzR_suffstats", gpu, as.integer(num_active_components))
+    K1 <- num_active_components + 1
+    list(n = st[seq(K1)], n_inspike = st[3 * K1 + 1])
+  },
+
+  gibbsMixtureWeights = function(recover_x = FALSE, tune = FALSE){                       # Pr:412-431
+    num_in_components <- .self$gpu_counts()$n * beta
+    new_weights <- r_dirichlet(c(weight_active_shape_2, weight_within_active_alpha) + num_in_components)
+    if(! is.nan(new_weights[1])){
+      .self$weight_active <- 1 - new_weights[1]
+      .self$weight_within_active <- new_weights[-1]/sum(new_weights[-1])
+      .self$gpu_push_hyper()
+    }
+    .self$gpu_after_move()
+  },
+
+  gibbsSpikeProb = function(recover_x = FALSE, tune = FALSE){                            # Pr:511-526
+    cn <- .self$gpu_counts()
+    num_inspike <- cn$n_inspike
+    num_outspike <- cn$n[1] - num_inspike
+    new_spike_probability <- rbeta(1, num_inspike + spike_prior_shape_1, num_outspike + spike_prior_shape_2)
+    if(! is.nan(new_spike_probability)){
+      .self$spike_probability <- new_spike_probability
+      .self$gpu_push_hyper()
+    }
+    .self$gpu_after_move()
+  },
+
+  mhInactiveMeans = function(recover_x = FALSE, tune = FALSE){                           # Pr:433-471
+    .self$inactive_means_proposed <- threshold_i - abs(threshold_i - inactive_means - rnorm(1, 0, inactive_mean_tuningParam[[1]]))
+    pp = .self$computeInactiveMeansPriorProbability(inactive_means_proposed)
+    pc = .self$computeInactiveMeansPriorProbability(inactive_means)
+    # sums of computeInactiveLikelihood over the inactive genes (0 when there are none)
+    Lp = .Call("zzR_level2_sums", gpu, inactive_means_proposed, inactive_variances, active_means, active_variances)[1]
+    Lc = .Call("zzR_level2_sums", gpu, inactive_means, inactive_variances, active_means, active_variances)[1]
+    R = temperature * (Lp - Lc + pp - pc)
+    if(tune) .self$inactive_means_trace[[1]][[1]] <- c(inactive_means_trace[[1]][[1]][-1],0)
+    if(log(runif(1)) < R){
+      .self$inactive_means <- inactive_means_proposed
+      if(tune) .self$inactive_means_trace[[1]][[1]][100] <- 1
+      .self$gpu_push_hyper()
+    }
+    .self$gpu_after_move()
+  },
+
+  mhActiveMeansDif = function(recover_x = FALSE, tune = FALSE){                          # Pr:640-705
+    for(k in sample(num_active_components, num_active_components, replace = TRUE)){
+      .self$active_means_dif_proposed <- active_means_dif
+      .self$active_means_dif_proposed[k] <- abs(active_means_dif[k] + rnorm(1,0,active_mean_tuningParam[k]))
+      mp = .self$calculate_active_means(active_means_dif_proposed)
+      mc = active_means
+      # sums of computeActiveLikelihood over the active genes (0 when there are none: the reference's second branch)
+      Lp <- .Call("zzR_level2_sums", gpu, inactive_means, inactive_variances, mp, active_variances)[2]
+      Lc <- .Call("zzR_level2_sums", gpu, inactive_means, inactive_variances, mc, active_variances)[2]
+      pp = computeActiveMeansDifPriorProbability(active_means_dif_proposed[k])
+      pc = computeActiveMeansDifPriorProbability(active_means_dif[k])
+      R = temperature * (Lp + pp - Lc - pc)
+      if(tune) .self$active_means_trace[[1]][[1]][k,] <- c(active_means_trace[[1]][[1]][k,-1],0)
+      if(log(runif(1)) < R){
+        .self$active_means_dif[k] <- active_means_dif_proposed[k]
+        if(tune) .self$active_means_trace[[1]][[1]][k,100] <- 1
+        .self$active_means <- .self$calculate_active_means(active_means_dif_proposed)
+        .self$gpu_push_hyper()
+      }
+    }
+    .self$gpu_after_move()
+  },
+
+  mhSharedVariance = function(recover_x = FALSE, tune = FALSE){                          # Pr:768-803
+    .self$active_variances_proposed <- rep(10^(.self$two_boundary_slide_move(log(active_variances[1], 10), active_variances_prior_log_min,
+                                                                             active_variances_prior_log_max, active_variance_tuningParam[1])),
+                                           num_active_components)
+    if(tune) .self$active_variances_trace[[1]][[1]][1,] <- c(active_variances_trace[[1]][[1]][1,-1],0)
+    Lp <- .Call("zzR_level2_sums", gpu, inactive_means, active_variances_proposed[1], active_means, active_variances_proposed)   # c(inactive, active)
+    Lc <- .Call("zzR_level2_sums", gpu, inactive_means, inactive_variances, active_means, active_variances)
+    active_pp = .self$computeActiveVariancesPriorProbability(active_variances_proposed[1])
+    active_pc = .self$computeActiveVariancesPriorProbability(active_variances[1])
+    R = temperature * (Lp[2] + Lp[1] + active_pp - Lc[2] - Lc[1] - active_pc)
+    if(log(runif(1)) < R){
+      .self$active_variances <- rep(active_variances_proposed[1], num_active_components)
+      .self$inactive_variances <- active_variances_proposed[1]
+      if(tune) .self$active_variances_trace[[1]][[1]][1,100] <- 1
+      .self$gpu_push_hyper()
+    }
+    .self$gpu_after_move()
+  },
+
+  # after an accepted move on (s0, s1, tau): new constants to the device, variance_g_probability[out_spike_idx] rewritten there (Pr:113,147,187)
+  gpu_commit_varg = function(){ .self$gpu_push_hyper(); .Call("zzR_commit_varg_hyper", gpu); .self$gpu_dirty <- TRUE },
+
+  mhTau = function(recover_x = FALSE, tune = FALSE){                                     # Pr:119-152
     proposal <- .self$scale_move(tau, tuningParam_tau)
     proposed_tau <- proposal[[1]]
     HR <- log(proposal[[2]])
-    L <- .Call("zzR_varg_hyper_sum", gpu, s0, s1, proposed_tau)          # c(Lp, Lc)
+    L <- .Call("zzR_varg_hyper_sum", gpu, s0, s1, proposed_tau)                          # c(Lp, Lc) over out_spike_idx
     pp <- .self$computeTauPriorProbability(proposed_tau)
     pc <- .self$computeTauPriorProbability(tau)
     R <- temperature * (L[1] - L[2] + pp - pc) + HR
@@ -59,34 +203,114 @@ zigzag$methods(
     if(log(runif(1)) < R){
       .self$tau <- proposed_tau
       if(tune) .self$tau_trace[[1]][[1]][100] <- 1
-      .self$gpu_push_hyper()
-      .Call("zzR_commit_varg_hyper", gpu)
+      .self$gpu_commit_varg()
     }
+    .self$gpu_after_move()
   },
 
-  calculate_lnl = function(num_libs) .Call("zzR_lnl", gpu),
+  mhSg = function(recover_x = FALSE, tune = FALSE){                                      # Pr:58-117
+    HR = 0
+    selection = sample(seq(2), 1, prob = c(1,1))
+    if(selection == 1){
+      proposed_s0 <- s0 + rnorm(1, 0, tuningParam_s0)
+      proposed_s1 <- s1
+      if(tune) .self$s0_trace[[1]][[1]] <- c(s0_trace[[1]][[1]][-1], 0)
+    }else{
+      proposed_s0 <- s0
+      proposal <- .self$scale_move(s1, tuningParam_s1)
+      proposed_s1 <- proposal[[1]]
+      HR <- log(proposal[[2]])
+      if(tune) .self$s1_trace[[1]][[1]] <- c(s1_trace[[1]][[1]][-1], 0)
+    }
+    L <- .Call("zzR_varg_hyper_sum", gpu, proposed_s0, proposed_s1, tau)
+    pp <- .self$computeS0PriorProbability(proposed_s0) + .self$computeS1PriorProbability(proposed_s1)
+    pc <- .self$computeS0PriorProbability(s0) + .self$computeS1PriorProbability(s1)
+    R <- temperature * (L[1] - L[2] + pp - pc) + HR
+    if(log(runif(1)) < R){
+      .self$s0 <- proposed_s0
+      .self$s1 <- proposed_s1
+      if(selection == 1){ if(tune) .self$s0_trace[[1]][[1]][100] <- 1 } else { if(tune) .self$s1_trace[[1]][[1]][100] <- 1 }
+      .self$gpu_commit_varg()
+    }
+    .self$gpu_after_move()
+  },
+
+  mhS0Tau = function(recover_x = FALSE, tune = FALSE){                                   # Pr:154-191
+    proposal <- .self$scale_move(tau, tuningParam_s0tau)
+    proposed_s0 <- s0 - log(proposal[[2]])
+    proposed_tau <- proposal[[1]]
+    HR <- log(proposal[[2]])
+    if(tune) .self$s0tau_trace[[1]][[1]] <- c(s0tau_trace[[1]][[1]][-1], 0)
+    L <- .Call("zzR_varg_hyper_sum", gpu, proposed_s0, s1, proposed_tau)
+    pp <- .self$computeS0PriorProbability(proposed_s0) + .self$computeTauPriorProbability(proposed_tau)
+    pc <- .self$computeS0PriorProbability(s0) + .self$computeTauPriorProbability(tau)
+    R <- temperature * (L[1] - L[2] + pp - pc) + HR
+    if(log(runif(1)) < R){
+      .self$s0 <- proposed_s0
+      .self$tau <- proposed_tau
+      if(tune) .self$s0tau_trace[[1]][[1]][100] <- 1
+      .self$gpu_commit_varg()
+    }
+    .self$gpu_after_move()
+  },
+
+  mhP_x = function(recover_x = FALSE, tune = FALSE){                                     # Pr:193-243
+    randlib = sample(num_libraries, 1)
+    proposed_alpha_r <- alpha_r
+    proposal <- .self$scale_move(alpha_r[randlib], tuningParam_alpha_r[randlib])
+    proposed_alpha_r[randlib] <- proposal[[1]]
+    if(tune) .self$alpha_r_trace[[1]][[1]][randlib,] <- c(alpha_r_trace[[1]][[1]][randlib, -1], 0)
+    HR <- log(proposal[[2]])
+    # Lp - Lc: the sum over genes of the one library's term at alpha' minus the same at alpha (for num_libraries == 2 the reference
+    # recomputes the whole likelihood; the other library's terms cancel in the difference)
+    delta <- .Call("zzR_px_delta", gpu, proposed_alpha_r, as.integer(randlib))[randlib]
+    pp <- .self$computeAlphaRPriorProbability(proposed_alpha_r)
+    pc <- .self$computeAlphaRPriorProbability(alpha_r)
+    R <- temperature * (delta + pp - pc) + HR
+    if(log(runif(1)) < R & R != Inf){
+      .self$alpha_r[randlib] <- proposed_alpha_r[randlib]
+      if(tune) .self$alpha_r_trace[[1]][[1]][randlib,100] <- 1
+      .Call("zzR_px_commit", gpu, as.integer(randlib), proposed_alpha_r[randlib])       # alpha_r, p_x and XgLikelihood on the device
+      .self$gpu_dirty <- TRUE
+    }
+    .self$gpu_after_move()
+  },
+
+  calculate_lnl = function(num_libs) .Call("zzR_lnl", gpu),                               # U:70-75
+
+  tune_all = function(burnin_target_acceptance_rate){                                    # U:183-240
+    callSuper(burnin_target_acceptance_rate)        # scalar parameters: the reference's own code on the R-side traces
+    .Call("zzR_tune", gpu, burnin_target_acceptance_rate)     # tuningParam_yg / tuningParam_variance_g from the device-side windows (U:202-206)
+    .self$gpu_dirty <- TRUE                          # the per-gene tuning parameters the super call derived from stale traces are replaced at the next pull
+  },
+
+  # posterior-predictive discrepancies of one simulated data set, computed on the device (R/zigzagPostPredictiveSimulation.R:3-156)
+  gpu_post_predictive = function(bins){
+    out <- .Call("zzR_post_predictive", gpu, gpu_next(), as.numeric(bins), as.integer(num_libraries))
+    R <- num_libraries
+    list(W_L = out[1], W_U = out[2], B = out[3], W_L_r = out[3 + seq(R)], B_r = out[3 + R + seq(R)])
+  },
 
   # ---- device-resident segments: n generations (fused sweep + every hyper move + tune_all + allocation trace) without returning
-  # to R between moves (zz_run_generations).  burnin()/mcmc() call this between two sampling points instead of looping over
-  # proposal_list; the fields the hyper moves mutate travel once per segment.
+  # to R between moves (zz_run_generations).  The scalar state travels once per segment; per-gene fields through gpu_pull().
   gpu_run_generations = function(n, tune = FALSE, sample_frequency = 1, target = 0.44){
     pri <- c(weight_active_shape_1, weight_active_shape_2, spike_prior_shape_1, spike_prior_shape_2,
              active_means_dif_prior_shape, active_means_dif_prior_rate, inactive_means_prior_shape, inactive_means_prior_rate,
-             shared_variance_prior_log_min, shared_variance_prior_log_max, tau_shape, tau_rate, s0_mu, s0_sigma, s1_shape, s1_rate,
+             active_variances_prior_log_min, active_variances_prior_log_max, tau_shape, tau_rate, s0_mu, s0_sigma, s1_shape, s1_rate,
              alpha_r_shape, alpha_r_rate, threshold_i, threshold_a)
     K <- num_active_components; R <- num_libraries
-    sc <- list(active_means_dif = active_means_dif, t_im = inactive_mean_tuningParam, t_av = active_variance_tuningParam[1],
+    sc <- list(active_means_dif = active_means_dif, t_im = inactive_mean_tuningParam[[1]], t_av = active_variance_tuningParam[1],
                t_am = active_mean_tuningParam, t_s0 = tuningParam_s0, t_s1 = tuningParam_s1, t_tau = tuningParam_tau,
                t_s0tau = tuningParam_s0tau, t_alpha = tuningParam_alpha_r,
-               w_im = as.integer(inactive_means_trace[[1]][[1]]), w_av = as.integer(active_variances_trace[[1]][[1]]),
-               w_am = lapply(seq(K), function(k) as.integer(active_means_trace[[k]][[1]])),
+               w_im = as.integer(inactive_means_trace[[1]][[1]]), w_av = as.integer(active_variances_trace[[1]][[1]][1,]),
+               w_am = lapply(seq(K), function(k) as.integer(active_means_trace[[1]][[1]][k,])),
                w_s0 = as.integer(s0_trace[[1]][[1]]), w_s1 = as.integer(s1_trace[[1]][[1]]), w_tau = as.integer(tau_trace[[1]][[1]]),
                w_s0tau = as.integer(s0tau_trace[[1]][[1]]),
-               w_alpha = lapply(seq(R), function(r) as.integer(alpha_r_trace[[r]][[1]])),
+               w_alpha = lapply(seq(R), function(r) as.integer(alpha_r_trace[[1]][[1]][r,])),
                hyper_ctr = gpu_hyper_ctr, hyper_buf = gpu_hyper_buf, step = gpu_step + 1, gen = gen, n_samples = gpu_n_samples)
-    .Call("zzR_chain_begin", gpu, pri, sc, K, R)
+    .Call("zzR_chain_begin", gpu, pri, sc, as.integer(K), as.integer(R))
     .Call("zzR_run_generations", gpu, as.integer(n), tune, as.integer(sample_frequency), target)
-    out <- .Call("zzR_chain_read", gpu, K, R)
+    out <- .Call("zzR_chain_read", gpu, as.integer(K), as.integer(R))
     .self$s0 <- out[1]; .self$s1 <- out[2]; .self$tau <- out[3]; .self$spike_probability <- out[4]
     .self$inactive_means <- out[5]; .self$inactive_variances <- out[6]; .self$weight_active <- out[7]
     .self$gen <- out[8]; .self$gpu_step <- out[9] - 1; .self$gpu_n_samples <- out[10]; .self$gpu_hyper_ctr <- out[11]
@@ -101,6 +325,14 @@ zigzag$methods(
     .self$tuningParam_s0tau <- out[j + 6]; j <- j + 6
     .self$active_mean_tuningParam <- out[j + seq(K)]; j <- j + K
     .self$tuningParam_alpha_r <- out[j + seq(R)]
-    # (the *_trace windows come back the same way through zzR_chain_windows; per-gene fields through gpu_pull())
-  }
-)
+    w <- .Call("zzR_chain_windows", gpu, as.integer(K), as.integer(R))                   # the *_trace windows of the scalar moves
+    .self$inactive_means_trace[[1]][[1]] <- w$w_im; .self$active_variances_trace[[1]][[1]][1,] <- w$w_av
+    .self$s0_trace[[1]][[1]] <- w$w_s0; .self$s1_trace[[1]][[1]] <- w$w_s1; .self$tau_trace[[1]][[1]] <- w$w_tau
+    .self$s0tau_trace[[1]][[1]] <- w$w_s0tau
+    .self$active_means_trace[[1]][[1]][seq(K),] <- w$w_am; .self$alpha_r_trace[[1]][[1]][seq(R),] <- w$w_alpha
+    .self$gpu_dirty <- TRUE
+  },
+
+  # the allocation counts the device accumulated during device-resident sampling segments, in the shape of the field (M:194-199)
+  gpu_allocation_trace = function() .Call("zzR_get_alloc_trace", gpu, num_transcripts, as.integer(num_active_components))
+))

@@ -1,7 +1,9 @@
 /*
  * zz_shim.c — the `.Call` shim an R maintainer adds to the zigzag package (as src/zz_shim.c) to run the per-gene moves on
- * the GPU through the C ABI of include/zigzag_gpu.h.  It cannot be compiled in this image (no R headers); it is the
- * reference-side binding described in INTEGRATION.md.  Link with -lzigzag_gpu.
+ * the GPU through the C ABI of include/zigzag_gpu.h: the reference-side binding described in INTEGRATION.md.  Link with
+ * -lzigzag_gpu.  R is not installed in this image; tests/test_r_overlay.py compiles this file against minimal stand-ins of the R
+ * headers (tests/r_stub/) and checks every entry of the registration table against its definition and against every .Call in
+ * r_overlay/R/zigzagGPU.R (names and argument counts).
  *
  * Conventions: R numeric = double, R integer/logical = int32, matrices column-major (Xg goes through unchanged), the
  * handle lives in an external pointer whose finalizer calls zz_destroy.  Errors are raised with Rf_error only after every
@@ -181,8 +183,8 @@ SEXP zzR_run_generations(SEXP ptr, SEXP ngen, SEXP tune, SEXP sample_frequency, 
   return R_NilValue;
 }
 /* returns c(s0, s1, tau, spike_probability, inactive_means, inactive_variances, weight_active, gen, step, n_samples, hyper_ctr,
-   alpha_r[R], active_means[K], active_variances[K], weight_within_active[K], active_means_dif[K], scalar tuning parameters ...);
-   the windows come back through zzR_chain_windows (omitted here: same pattern) */
+   alpha_r[R], active_means[K], active_variances[K], weight_within_active[K], active_means_dif[K], t_im, t_av, t_s0, t_s1, t_tau,
+   t_s0tau, t_am[K], t_alpha[R]); the windows come back through zzR_chain_windows */
 SEXP zzR_chain_read(SEXP ptr, SEXP K_, SEXP R_) {
   zz_handle *h = H(ptr);
   const int K = Rf_asInteger(K_), R = Rf_asInteger(R_);
@@ -206,9 +208,168 @@ SEXP zzR_chain_read(SEXP ptr, SEXP K_, SEXP R_) {
   return out;
 }
 
+
+/* the 100-wide accept windows of the scalar moves after a device-resident segment: a named list of integer vectors (w_im, w_av,
+   w_s0, w_s1, w_tau, w_s0tau), a K x 100 matrix w_am and an R x 100 matrix w_alpha — the shapes of the *_trace[[1]][[1]] fields */
+static SEXP win_vec(const uint8_t *w) { SEXP v = PROTECT(Rf_allocVector(INTSXP, 100)); for (int i = 0; i < 100; ++i) INTEGER(v)[i] = w[i]; UNPROTECT(1); return v; }
+SEXP zzR_chain_windows(SEXP ptr, SEXP K_, SEXP R_) {
+  zz_handle *h = H(ptr);
+  const int K = Rf_asInteger(K_), R = Rf_asInteger(R_);
+  zz_chain_scalars s; zz_hyper hy;
+  chk(h, zz_chain_read(h, &s, &hy));
+  const char *names[] = {"w_im", "w_av", "w_s0", "w_s1", "w_tau", "w_s0tau", "w_am", "w_alpha", ""};
+  SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+  const uint8_t *single[6] = {s.w_im, s.w_av, s.w_s0, s.w_s1, s.w_tau, s.w_s0tau};
+  for (int i = 0; i < 6; ++i) SET_VECTOR_ELT(out, i, win_vec(single[i]));
+  SEXP am = PROTECT(Rf_allocMatrix(INTSXP, K, 100)), al = PROTECT(Rf_allocMatrix(INTSXP, R, 100));
+  for (int k = 0; k < K; ++k) for (int i = 0; i < 100; ++i) INTEGER(am)[k + (size_t)K * i] = s.w_am[k][i];
+  for (int r = 0; r < R; ++r) for (int i = 0; i < 100; ++i) INTEGER(al)[r + (size_t)R * i] = s.w_alpha[r][i];
+  SET_VECTOR_ELT(out, 6, am); SET_VECTOR_ELT(out, 7, al);
+  UNPROTECT(3);
+  return out;
+}
+SEXP zzR_run_sweeps(SEXP ptr, SEXP step, SEXP nsweeps, SEXP tune) {
+  zz_handle *h = H(ptr);
+  chk(h, zz_run_sweeps(h, (uint64_t)Rf_asReal(step), Rf_asInteger(nsweeps), Rf_asLogical(tune)));
+  return R_NilValue;
+}
+
+/* ---- the remaining entry points of include/zigzag_gpu.h ------------------------------------------------------------------ */
+SEXP zzR_sync(SEXP ptr) { zz_handle *h = H(ptr); chk(h, zz_sync(h)); return R_NilValue; }
+SEXP zzR_launch_count(SEXP ptr) { return Rf_ScalarReal((double)zz_launch_count(H(ptr))); }
+SEXP zzR_refresh_caches(SEXP ptr) { zz_handle *h = H(ptr); chk(h, zz_refresh_caches(h)); return R_NilValue; }
+SEXP zzR_reset_windows(SEXP ptr) { zz_handle *h = H(ptr); chk(h, zz_reset_windows(h)); return R_NilValue; }
+/* list(yg = rowSums(Yg_trace), vg = rowSums(variance_g_trace)) of the device-side windows */
+SEXP zzR_window_sums(SEXP ptr, SEXP G_) {
+  zz_handle *h = H(ptr);
+  const int G = Rf_asInteger(G_);
+  const char *names[] = {"yg", "vg", ""};
+  SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+  SET_VECTOR_ELT(out, 0, Rf_allocVector(INTSXP, G)); SET_VECTOR_ELT(out, 1, Rf_allocVector(INTSXP, G));
+  int rc = zz_get_window_sums(h, 0, INTEGER(VECTOR_ELT(out, 0)), INTEGER(VECTOR_ELT(out, 1)));
+  UNPROTECT(1); chk(h, rc);
+  return out;
+}
+/* c(s0, s1, tau, spike_probability, inactive_means, inactive_variances, weight_active, beta, temperature, variance_g_upper_bound,
+   alpha_r[R], active_means[K], active_variances[K], weight_within_active[K]) as the device holds them */
+SEXP zzR_get_hyper(SEXP ptr) {
+  zz_handle *h = H(ptr);
+  zz_hyper hy;
+  chk(h, zz_get_hyper(h, 0, &hy));
+  const int R = hy.num_libraries, K = hy.num_active_components;
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, 10 + R + 3 * K));
+  double *o = REAL(out); int j = 0;
+  o[j++] = hy.s0; o[j++] = hy.s1; o[j++] = hy.tau; o[j++] = hy.spike_probability; o[j++] = hy.inactive_means; o[j++] = hy.inactive_variances;
+  o[j++] = hy.weight_active; o[j++] = hy.beta; o[j++] = hy.temperature; o[j++] = hy.variance_g_upper_bound;
+  for (int r = 0; r < R; ++r) o[j++] = hy.alpha_r[r];
+  for (int k = 0; k < K; ++k) o[j++] = hy.active_means[k];
+  for (int k = 0; k < K; ++k) o[j++] = hy.active_variances[k];
+  for (int k = 0; k < K; ++k) o[j++] = hy.weight_within_active[k];
+  UNPROTECT(1);
+  return out;
+}
+/* the three per-gene evaluators (which = 1: computeXgLikelihood, 2: computeVarianceGPriorProbability, 3: level-2 likelihood) */
+SEXP zzR_eval(SEXP ptr, SEXP which, SEXP G_) {
+  zz_handle *h = H(ptr);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, Rf_asInteger(G_)));
+  const int w = Rf_asInteger(which);
+  int rc = w == 1 ? zz_eval_xg_loglik(h, 0, REAL(out)) : w == 2 ? zz_eval_varg_logprior(h, 0, REAL(out)) : zz_eval_level2_loglik(h, 0, REAL(out));
+  UNPROTECT(1); chk(h, rc);
+  return out;
+}
+/* the uniforms / normals move `slot` consumes at `step` (north-star check 2: identical draws on both sides) */
+SEXP zzR_philox_draws(SEXP ptr, SEXP step, SEXP slot, SEXP n_, SEXP G_) {
+  zz_handle *h = H(ptr);
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, Rf_asInteger(G_), Rf_asInteger(n_)));
+  int rc = zz_philox_draws(h, (uint64_t)Rf_asReal(step), Rf_asInteger(slot), REAL(out));
+  UNPROTECT(1); chk(h, rc);
+  return out;
+}
+/* zz_sweep_host: the fused sweep on state that lives in R vectors (updated IN PLACE: the caller must own unshared copies) */
+SEXP zzR_sweep_host(SEXP ptr, SEXP step, SEXP tune, SEXP Yg, SEXP vg, SEXP ai, SEXP within, SEXP spike, SEXP xglik, SEXP vgprob, SEXP ty, SEXP tv) {
+  zz_handle *h = H(ptr);
+  int64_t up = 0, down = 0;
+  chk(h, zz_sweep_host(h, (uint64_t)Rf_asReal(step), Rf_asLogical(tune), REAL(Yg), REAL(vg), INTEGER(ai), INTEGER(within), INTEGER(spike),
+                       REAL(xglik), REAL(vgprob), REAL(ty), REAL(tv), &up, &down));
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, 2));
+  REAL(out)[0] = (double)up; REAL(out)[1] = (double)down;
+  UNPROTECT(1);
+  return out;
+}
+/* posterior-predictive simulation on the device (R/zigzagPostPred.R:3-156): c(W_L, W_U, B, W_L_r[R], B_r[R]) */
+SEXP zzR_post_predictive(SEXP ptr, SEXP step, SEXP bins, SEXP R_) {
+  zz_handle *h = H(ptr);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, 3 + 2 * Rf_asInteger(R_)));
+  int rc = zz_post_predictive(h, (uint64_t)Rf_asReal(step), REAL(bins), LENGTH(bins), REAL(out));
+  UNPROTECT(1); chk(h, rc);
+  return out;
+}
+/* sample sink: the device appends the log rows of every sampling point of a device-resident segment to pinned host rings.
+   The rings belong to the shim (one sink per process is enough for the drop-in: one zigzag object runs at a time). */
+static struct { zz_sample_sink sk; int32_t *cand; int plen, ncand; } g_sink;
+static void sink_free(zz_handle *h) {
+  if (h) zz_set_sample_sink(h, NULL);
+  zz_pinned_free(g_sink.sk.param_rows); zz_pinned_free(g_sink.sk.yg_rows); zz_pinned_free(g_sink.sk.vg_rows);
+  memset(&g_sink, 0, sizeof g_sink);
+}
+SEXP zzR_set_sample_sink(SEXP ptr, SEXP param_capacity, SEXP candidates /* 1-based gene indices or NULL */, SEXP yv_capacity, SEXP yv_every, SEXP R_, SEXP K_) {
+  zz_handle *h = H(ptr);
+  sink_free(h);
+  const int pc = Rf_asInteger(param_capacity), yc = Rf_isNull(candidates) ? 0 : Rf_asInteger(yv_capacity);
+  g_sink.plen = zz_param_row_len(Rf_asInteger(R_), Rf_asInteger(K_));
+  g_sink.sk.param_rows = (double *)zz_pinned_alloc(sizeof(double) * (size_t)(pc > 0 ? pc : 1) * g_sink.plen);
+  g_sink.sk.param_capacity = pc;
+  if (!g_sink.sk.param_rows) { sink_free(NULL); Rf_error("zz_pinned_alloc failed"); }
+  if (yc > 0) {
+    g_sink.ncand = LENGTH(candidates);
+    g_sink.cand = (int32_t *)R_alloc((size_t)g_sink.ncand, sizeof(int32_t));
+    for (int i = 0; i < g_sink.ncand; ++i) g_sink.cand[i] = INTEGER(candidates)[i] - 1;
+    g_sink.sk.yg_rows = (double *)zz_pinned_alloc(sizeof(double) * (size_t)yc * (1 + g_sink.ncand));
+    g_sink.sk.vg_rows = (double *)zz_pinned_alloc(sizeof(double) * (size_t)yc * (1 + g_sink.ncand));
+    if (!g_sink.sk.yg_rows || !g_sink.sk.vg_rows) { sink_free(NULL); Rf_error("zz_pinned_alloc failed"); }
+    g_sink.sk.yv_capacity = yc; g_sink.sk.candidates = g_sink.cand; g_sink.sk.n_candidates = g_sink.ncand; g_sink.sk.yv_every = Rf_asInteger(yv_every);
+  }
+  int rc = zz_set_sample_sink(h, &g_sink.sk);          /* copies the candidate list to the device */
+  g_sink.sk.candidates = NULL; g_sink.cand = NULL;   /* R_alloc memory: gone when this call returns */
+  if (rc != ZZ_OK) { sink_free(NULL); chk(h, rc); }
+  return R_NilValue;
+}
+/* list(param = rows x plen, yg = rows x (1 + ncand), vg = ...) written so far, then detaches and frees the rings */
+SEXP zzR_sample_rows(SEXP ptr) {
+  zz_handle *h = H(ptr);
+  int64_t np = 0, ny = 0;
+  chk(h, zz_sync(h));
+  chk(h, zz_sample_rows_written(h, &np, &ny));
+  const char *names[] = {"param", "yg", "vg", ""};
+  SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+  SEXP p = PROTECT(Rf_allocMatrix(REALSXP, (int)np, g_sink.plen));
+  for (int64_t r = 0; r < np; ++r) for (int c = 0; c < g_sink.plen; ++c) REAL(p)[r + np * c] = g_sink.sk.param_rows[r * g_sink.plen + c];
+  SET_VECTOR_ELT(out, 0, p);
+  if (g_sink.sk.yg_rows) {
+    const int w = 1 + g_sink.ncand;
+    SEXP y = PROTECT(Rf_allocMatrix(REALSXP, (int)ny, w)), v = PROTECT(Rf_allocMatrix(REALSXP, (int)ny, w));
+    for (int64_t r = 0; r < ny; ++r) for (int c = 0; c < w; ++c) { REAL(y)[r + ny * c] = g_sink.sk.yg_rows[r * w + c]; REAL(v)[r + ny * c] = g_sink.sk.vg_rows[r * w + c]; }
+    SET_VECTOR_ELT(out, 1, y); SET_VECTOR_ELT(out, 2, v);
+    UNPROTECT(2);
+  }
+  sink_free(h);
+  UNPROTECT(2);
+  return out;
+}
+/* gene shards over several R processes (one per GPU): the CUDA IPC blob of this rank's inbox as a raw vector; connect takes the
+   blobs of all ranks concatenated in rank order (exchanged by the caller, e.g. through Rmpi or files) */
+SEXP zzR_comm_init(SEXP ptr, SEXP rank, SEXP world) {
+  zz_handle *h = H(ptr);
+  SEXP out = PROTECT(Rf_allocVector(RAWSXP, zz_comm_handle_bytes()));
+  int rc = zz_comm_init(h, Rf_asInteger(rank), Rf_asInteger(world), RAW(out));
+  UNPROTECT(1); chk(h, rc);
+  return out;
+}
+SEXP zzR_comm_connect(SEXP ptr, SEXP all_handles) { zz_handle *h = H(ptr); chk(h, zz_comm_connect(h, RAW(all_handles))); return R_NilValue; }
+
 static const R_CallMethodDef calls[] = {
   {"zzR_chain_begin", (DL_FUNC)&zzR_chain_begin, 5}, {"zzR_run_generations", (DL_FUNC)&zzR_run_generations, 5},
-  {"zzR_chain_read", (DL_FUNC)&zzR_chain_read, 3},
+  {"zzR_chain_read", (DL_FUNC)&zzR_chain_read, 3}, {"zzR_chain_windows", (DL_FUNC)&zzR_chain_windows, 3}, {"zzR_run_sweeps", (DL_FUNC)&zzR_run_sweeps, 4},
   {"zzR_create", (DL_FUNC)&zzR_create, 5}, {"zzR_set_state", (DL_FUNC)&zzR_set_state, 11}, {"zzR_get_state", (DL_FUNC)&zzR_get_state, 2},
   {"zzR_set_hyper", (DL_FUNC)&zzR_set_hyper, 15}, {"zzR_mh_yg", (DL_FUNC)&zzR_mh_yg, 3}, {"zzR_mh_variance_g", (DL_FUNC)&zzR_mh_variance_g, 3},
   {"zzR_gibbs_alloc", (DL_FUNC)&zzR_gibbs_alloc, 2}, {"zzR_gibbs_alloc_within", (DL_FUNC)&zzR_gibbs_alloc_within, 2},
@@ -217,6 +378,12 @@ static const R_CallMethodDef calls[] = {
   {"zzR_level2_sums", (DL_FUNC)&zzR_level2_sums, 5}, {"zzR_px_delta", (DL_FUNC)&zzR_px_delta, 3}, {"zzR_px_commit", (DL_FUNC)&zzR_px_commit, 3},
   {"zzR_lnl", (DL_FUNC)&zzR_lnl, 1}, {"zzR_tune", (DL_FUNC)&zzR_tune, 2}, {"zzR_nan_flag", (DL_FUNC)&zzR_nan_flag, 1},
   {"zzR_accumulate_alloc_trace", (DL_FUNC)&zzR_accumulate_alloc_trace, 1}, {"zzR_reset_alloc_trace", (DL_FUNC)&zzR_reset_alloc_trace, 1},
-  {"zzR_get_alloc_trace", (DL_FUNC)&zzR_get_alloc_trace, 3}, {NULL, NULL, 0}};
+  {"zzR_get_alloc_trace", (DL_FUNC)&zzR_get_alloc_trace, 3},
+  {"zzR_sync", (DL_FUNC)&zzR_sync, 1}, {"zzR_launch_count", (DL_FUNC)&zzR_launch_count, 1}, {"zzR_refresh_caches", (DL_FUNC)&zzR_refresh_caches, 1},
+  {"zzR_reset_windows", (DL_FUNC)&zzR_reset_windows, 1}, {"zzR_window_sums", (DL_FUNC)&zzR_window_sums, 2}, {"zzR_get_hyper", (DL_FUNC)&zzR_get_hyper, 1},
+  {"zzR_eval", (DL_FUNC)&zzR_eval, 3}, {"zzR_philox_draws", (DL_FUNC)&zzR_philox_draws, 5}, {"zzR_sweep_host", (DL_FUNC)&zzR_sweep_host, 12},
+  {"zzR_post_predictive", (DL_FUNC)&zzR_post_predictive, 4}, {"zzR_set_sample_sink", (DL_FUNC)&zzR_set_sample_sink, 7},
+  {"zzR_sample_rows", (DL_FUNC)&zzR_sample_rows, 1}, {"zzR_comm_init", (DL_FUNC)&zzR_comm_init, 3}, {"zzR_comm_connect", (DL_FUNC)&zzR_comm_connect, 2},
+  {NULL, NULL, 0}};
 
 void R_init_zigzag(DllInfo *dll) { R_registerRoutines(dll, NULL, calls, NULL, NULL); R_useDynamicSymbols(dll, FALSE); }
