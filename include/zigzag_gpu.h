@@ -169,6 +169,17 @@ int zz_lnl(zz_handle *h, int chain, double *out);                /* calculate_ln
 int zz_reset_alloc_trace(zz_handle *h);                          /* allocation_trace <- one-hot(current) is reset+accumulate (R/zigzagMCMC.R:142-145) */
 int zz_accumulate_alloc_trace(zz_handle *h);                     /* allocation_trace += one-hot(allocation), R/zigzagMCMC.R:194-199 */
 int zz_get_alloc_trace(zz_handle *h, int chain, uint32_t *out);  /* [K+1][G] */
+/* tempering on the chain axis (mc3, R/zigzagDevelopment.R:9-139): the chain at temperature 1 changes slots when a swap is accepted —
+   its samples go to ONE trace (allocation_trace[dst] += one-hot(allocation of chain src)), and the slot that becomes cold inherits the
+   cold chain's per-gene tuning parameters (set_tuningParam_fields, R/zigzagDevelopment.R:118) */
+int zz_accumulate_alloc_trace_from(zz_handle *h, int src_chain, int dst_chain);
+int zz_copy_chain_tuning(zz_handle *h, int src_chain, int dst_chain);
+/* Constructor-side initialisation on the device, R/zigzagInitialize.R:416-504, for every chain from its own hyper-parameters
+   (zz_set_hyper first): allocations, rwm / rwv from the data, Yg, variance_g, the re-draw loop of genes with zero likelihood, tuning
+   parameters 0.5, the 100-wide windows, then both likelihood caches.  rowvar_log_mean / rowvar_sd = log(mean(v)), sd(v) of the row
+   variances v of the fully detected genes of the whole data set (I:446).  Philox-keyed by the global gene index: a sharded
+   initialisation equals the single-GPU one. */
+int zz_init_state(zz_handle *h, uint64_t step, double rowvar_log_mean, double rowvar_sd);
 int zz_tune(zz_handle *h, double target);                        /* x_tune on Yg_trace / variance_g_trace, R/zigzagUtilities.R:161-181, 202-206 */
 int zz_nan_flag(zz_handle *h, int *flag);                        /* replaces the NA guard R/zigzagBurnin.R:69-78 */
 

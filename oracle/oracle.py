@@ -263,6 +263,22 @@ def tune_per_gene(s, target=0.44):
     lib().zzo_tune_per_gene(s.c(), C.c_double(target))
 
 
+def init_state(h, s, seed, chain, step, gene0, rv_m, rv_s):
+    """zzo_init_state: the constructor-side initial state (I:416-504) written into State `s` in place."""
+    L = lib()
+    L.zzo_init_state.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_void_p]
+    L.zzo_init_state.restype = None
+    L.zzo_init_state(C.byref(h), s.c(), seed, chain, step, gene0, rv_m, rv_s, None)
+
+
+def rowvar_moments(X):
+    """(log(mean(v)), sd(v)) of the row variances v of the fully detected genes (I:446)."""
+    X = np.asarray(X)
+    full = ~np.isneginf(X).any(1)
+    v = X[full].var(axis=1, ddof=1)
+    return float(np.log(v.mean())), float(np.sqrt(v.var(ddof=1)))
+
+
 def philox4x32_10(ctr, key):
     c = (C.c_uint32 * 4)(*ctr); k = (C.c_uint32 * 2)(*key); o = (C.c_uint32 * 4)()
     lib().zzo_philox4x32_10(c, k, o); return list(o)

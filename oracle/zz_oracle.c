@@ -538,6 +538,61 @@ void zzo_sweep_draws(uint64_t seed, uint32_t chain, uint64_t step, uint64_t gene
   }
 }
 
+/* Constructor-side initial state, R/zigzagInitialize.R:416-504, with the draw map of include/zigzag_gpu.h:zz_init_state (Philox
+   keyed by the global gene index gene0 + g): block 0 = {u of allocation_active_inactive (I:367), u of allocation_within_active
+   (I:372), pair (z of rwm for an all-zero gene, z of rwv for a gene with < 2 detected libraries)}, block 1 = pair (z of Yg, z of
+   variance_g), block 2 + j = pair of re-draw j.  rv_m, rv_s: log(mean), sd of the row variances of the fully detected genes (I:446).
+   The reference re-draws every gene whose likelihood is still -Inf, round by round (I:480-502): gene by gene that is a loop of
+   its own per gene.  Tuning parameters 0.5, windows c(rep(0,77), rep(1,23)), both caches refreshed (I:473, I:504). */
+void zzo_init_state(const zzo_hyper *h, zzo_state *s, uint64_t seed, uint32_t chain, uint64_t step, uint64_t gene0, double rv_m, double rv_s,
+                    int32_t *no_detect_spike_out) {
+  const int R = h->num_libraries, K = h->num_active_components;
+  const int64_t G = s->G;
+  for (int64_t g = 0; g < G; ++g) {
+    int n_det = 0; long double sum = 0;
+    for (int r = 0; r < R; ++r) { const double x = s->Xg[(int64_t)r * G + g]; if (x != -INFINITY) { ++n_det; sum += x; } }
+    const int allzero = n_det == 0;
+    if (no_detect_spike_out) no_detect_spike_out[g] = allzero;        /* I:415 */
+    s->inactive_spike_allocation[g] = allzero;                        /* I:418 */
+    double a[4], b[4], n0[2], n1[2];
+    zzo_uniform4(seed, chain, step, 0, gene0 + g, a);
+    zzo_box_muller(a[2], a[3], n0);
+    const int pinned = s->pinned_active && s->pinned_active[g];
+    s->alloc_active_inactive[g] = ((pinned || a[0] < h->weight_active) && !allzero) ? 1 : 0;   /* I:367-369, I:422 */
+    int k = 1; double cum = 0;
+    for (int j = 0; j < K - 1; ++j) { cum += h->weight_within_active[j]; k += (cum <= a[1]); }   /* I:372 */
+    s->alloc_within_active[g] = k;
+    zzo_uniform4(seed, chain, step, 1, gene0 + g, b);
+    zzo_box_muller(b[0], b[1], n1);
+    const double sd_i = sqrt(h->inactive_variances);
+    double rwm, rwv;
+    if (n_det > 0) rwm = (double)(sum / n_det); else rwm = h->inactive_means + sd_i * n0[0];      /* I:431-438 */
+    if (n_det >= 2) {                                                                            /* I:441-448: var() */
+      long double ss = 0;
+      for (int r = 0; r < R; ++r) { const double x = s->Xg[(int64_t)r * G + g]; if (x != -INFINITY) ss += ((long double)x - rwm) * ((long double)x - rwm); }
+      rwv = (double)(ss / (n_det - 1));
+    } else rwv = exp(rv_m + rv_s * n0[1]);
+    double y = rwm + sqrt(rwv) * n1[0];                               /* I:449 */
+    double v = exp(0.5 + 0.2 * n1[1]);                                /* I:465 */
+    if (v > h->variance_g_upper_bound) v = h->variance_g_upper_bound; /* I:468 */
+    double px[ZZO_MAX_LIBS];
+    if (!allzero)
+      for (uint32_t j = 0; j < 1000; ++j) {                           /* I:480-502 */
+        zzo_get_px(h, y, s->gene_lengths[g], px);
+        if (zzo_xg_lik(h, s->Xg + g, G, y, v, px, 0, 0) != -INFINITY) break;
+        double c[4], n2[2];
+        zzo_uniform4(seed, chain, step, 2 + j, gene0 + g, c);
+        zzo_box_muller(c[0], c[1], n2);
+        y = h->inactive_means + sd_i * n2[0];
+        v = exp(log(zzo_get_sigmax(h->s0, h->s1, y)) + h->tau + sqrt(h->tau) * n2[1]);
+        if (v > h->variance_g_upper_bound) v = h->variance_g_upper_bound;
+      }
+    s->Yg[g] = y; s->variance_g[g] = v; s->tuningParam_yg[g] = 0.5; s->tuningParam_variance_g[g] = 0.5;
+  }
+  zzo_window_init(s->Yg_trace, G); zzo_window_init(s->variance_g_trace, G);
+  zzo_refresh_caches(h, s);
+}
+
 /* ------------------------------------------------------------------ schedule-faithful chain */
 
 struct zzo_chain {

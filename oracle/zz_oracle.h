@@ -114,6 +114,9 @@ double zzo_lnl(const zzo_hyper *h, const zzo_state *s);                         
 
 /* ---- tuning (burn-in) ---- */
 void zzo_window_init(uint64_t *win, int64_t G);                    /* 77 zeros + 23 ones, I:460,466 */
+/* constructor-side initial state (I:416-504) with the draw map of zz_init_state; no_detect_spike_out may be NULL */
+void zzo_init_state(const zzo_hyper *h, zzo_state *s, uint64_t seed, uint32_t chain, uint64_t step, uint64_t gene0, double rv_m, double rv_s,
+                    int32_t *no_detect_spike_out);
 double zzo_x_tune(double accept_sum_over_100, double tuning, double target, double lo, double hi);  /* U:161-181 */
 void zzo_tune_per_gene(zzo_state *s, double target);               /* U:202-206 */
 

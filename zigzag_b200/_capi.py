@@ -160,6 +160,9 @@ _SIG = {
     "zz_reset_alloc_trace": (C.c_int, [_P]),
     "zz_accumulate_alloc_trace": (C.c_int, [_P]),
     "zz_get_alloc_trace": (C.c_int, [_P, C.c_int, _P]),
+    "zz_accumulate_alloc_trace_from": (C.c_int, [_P, C.c_int, C.c_int]),
+    "zz_copy_chain_tuning": (C.c_int, [_P, C.c_int, C.c_int]),
+    "zz_init_state": (C.c_int, [_P, C.c_uint64, C.c_double, C.c_double]),
     "zz_tune": (C.c_int, [_P, C.c_double]),
     "zz_nan_flag": (C.c_int, [_P, _P]),
     "zz_sweep_host": (C.c_int, [_P, C.c_uint64, C.c_int] + [_P] * 11),
@@ -433,6 +436,16 @@ class Handle:
         out = np.empty((self.K + 1, self.G), np.uint32)
         self._ck(self.L.zz_get_alloc_trace(self.h, chain, _ptr(out)))
         return out
+
+    def accumulate_alloc_trace_from(self, src_chain, dst_chain=0):
+        self._ck(self.L.zz_accumulate_alloc_trace_from(self.h, int(src_chain), int(dst_chain)))
+
+    def copy_chain_tuning(self, src_chain, dst_chain):
+        self._ck(self.L.zz_copy_chain_tuning(self.h, int(src_chain), int(dst_chain)))
+
+    def init_state(self, step, rowvar_log_mean, rowvar_sd):
+        """Constructor-side initial state on the device (R/zigzagInitialize.R:416-504), every chain from its own hyper-parameters."""
+        self._ck(self.L.zz_init_state(self.h, int(step), float(rowvar_log_mean), float(rowvar_sd)))
 
     def tune(self, target=0.44):
         self._ck(self.L.zz_tune(self.h, float(target)))

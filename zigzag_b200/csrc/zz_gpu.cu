@@ -1054,6 +1054,60 @@ __global__ void __launch_bounds__(BLOCK) k_alloc_trace(int64_t G, int K, const u
   trace[((int64_t)chain * (K + 1) + comp) * G + g] += 1u;
 }
 
+// Constructor-side initialisation of the per-gene state, R/zigzagInitialize.R:416-504, for every chain of the handle from that
+// chain's hyper-parameters.  Draw map (Philox, step = the caller's): block 0 = {u of the active/inactive allocation (I:367), u of
+// the within-active allocation (I:372), Box-Muller pair (z for rwm of an all-zero gene I:431-438, z for rwv of a gene with < 2
+// detected libraries I:441-448)}; block 1 = pair (z of Yg I:449, z of variance_g I:465); block 2 + j = pair of re-draw j of a gene
+// whose likelihood is 0 (I:480-502; each gene repeats on its own until its likelihood is positive, at most 1000 times — the
+// reference's loop re-draws exactly the genes that are still at -Inf, so the per-gene loop visits the same states).
+// rwm / rwv come from the per-gene data statistics (xbar, xss, nd_mask); `rv_m`, `rv_s` = log(mean) and sd of the row variances of
+// the fully detected genes of the WHOLE data set (host, I:446).
+__global__ void __launch_bounds__(BLOCK) k_init_state(int64_t G, int64_t gene_offset, uint64_t seed, uint64_t step, double rv_m, double rv_s,
+                                                       const double *__restrict__ Xg, const double *__restrict__ gl, const int32_t *__restrict__ perm,
+                                                       const uint64_t *__restrict__ nd_mask, const double *__restrict__ xbar, const double *__restrict__ xss,
+                                                       const zz_hyper *hyper, double *Yg, double *vg, double *ty, double *tv, uint16_t *flags) {
+  __shared__ HyperS H;
+  const int chain = blockIdx.y;
+  load_hyper(H, hyper + chain);
+  __syncthreads();
+  const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (g >= G) return;
+  const int64_t i = (int64_t)chain * G + g;
+  const uint64_t gid = (uint64_t)(gene_offset + perm[g]);
+  const int n_det = H.R - __popcll(nd_mask[g]);
+  const bool allzero = n_det == 0;
+  uint32_t f = flags[i] & F_PINNED;
+  if (allzero) f |= F_ALLZERO | F_INSPIKE;                            // I:415-418
+  uint32_t b[4];
+  philox_block(seed, chain, step, 0, gid, b);
+  const double u_ai = u32_open(b[0]), u_w = u32_open(b[1]);
+  double z_m, z_v0, z_y, z_v;
+  box_muller(u32_open(b[2]), u32_open(b[3]), z_m, z_v0);
+  if (((f & F_PINNED) || u_ai < H.wa) && !allzero) f |= F_ACTIVE;     // I:367-369, I:422
+  int k = 1; double cum = 0;
+  for (int j = 0; j < H.K - 1; ++j) { cum += H.w[j]; k += (cum <= u_w); }   // I:372
+  f = flag_set_k(f, k);
+  philox_block(seed, chain, step, 1, gid, b);
+  box_muller(u32_open(b[0]), u32_open(b[1]), z_y, z_v);
+  const double rwm = n_det > 0 ? xbar[g] : H.im + H.sd_i * z_m;       // I:431-438
+  const double rwv = n_det >= 2 ? xss[g] / (n_det - 1) : exp(rv_m + rv_s * z_v0);   // I:441-448
+  double y = rwm + sqrt(rwv) * z_y;                                   // I:449
+  double v = exp(0.5 + 0.2 * z_v);                                    // I:465
+  if (v > H.vub) v = H.vub;                                           // I:468
+  if (!allzero) {                                                     // I:480-502
+    for (uint32_t j = 0; j < 1000 && xg_lik_out(H, Xg + g, G, y, v, gl[g]) == -INFINITY; ++j) {
+      double z1, z2;
+      philox_block(seed, chain, step, 2 + j, gid, b);
+      box_muller(u32_open(b[0]), u32_open(b[1]), z1, z2);
+      y = H.im + H.sd_i * z1;
+      v = exp(log(exp(H.s0 + H.s1 * y)) + H.tau + H.rtau * z2);
+      if (v > H.vub) v = H.vub;
+    }
+  }
+  Yg[i] = y; vg[i] = v; ty[i] = 0.5; tv[i] = 0.5;                      // tuning parameters I:185-199
+  flags[i] = (uint16_t)f;
+}
+
 // x_tune on the per-gene windows, U:161-181 with the clamps of U:202-206
 __device__ __forceinline__ double x_tune(double wsum, double t, double target, double lo, double hi) {
   const double pjump = wsum / 100;
@@ -2038,6 +2092,40 @@ int zz_accumulate_alloc_trace(zz_handle *h) {
   k_alloc_trace<<<gene_grid(h, h->G, h->C), BLOCK, 0, h->stream>>>(h->G, h->K, h->flags, h->trace);
   ZZ_LAUNCHED(h);
   return ZZ_OK;
+}
+
+int zz_accumulate_alloc_trace_from(zz_handle *h, int src_chain, int dst_chain) {
+  ZZ_CHECK(h);
+  if (int rc = chain_ok(h, src_chain)) return rc;
+  if (int rc = chain_ok(h, dst_chain)) return rc;
+  k_alloc_trace<<<gene_grid(h, h->G, 1), BLOCK, 0, h->stream>>>(h->G, h->K, h->flags + (int64_t)src_chain * h->G,
+                                                                 h->trace + (int64_t)dst_chain * (h->K + 1) * h->G);
+  ZZ_LAUNCHED(h);
+  return ZZ_OK;
+}
+
+int zz_copy_chain_tuning(zz_handle *h, int src_chain, int dst_chain) {
+  ZZ_CHECK(h);
+  if (int rc = chain_ok(h, src_chain)) return rc;
+  if (int rc = chain_ok(h, dst_chain)) return rc;
+  if (src_chain == dst_chain) return ZZ_OK;
+  const int64_t G = h->G;
+  ZZ_CUDA(h, cudaMemcpyAsync(h->ty + dst_chain * G, h->ty + src_chain * G, sizeof(double) * G, cudaMemcpyDeviceToDevice, h->stream));
+  ZZ_CUDA(h, cudaMemcpyAsync(h->tv + dst_chain * G, h->tv + src_chain * G, sizeof(double) * G, cudaMemcpyDeviceToDevice, h->stream));
+  return ZZ_OK;
+}
+
+int zz_init_state(zz_handle *h, uint64_t step, double rowvar_log_mean, double rowvar_sd) {
+  ZZ_CHECK(h);
+  if (!h->have_data) return fail(h, ZZ_ERR_STATE, "zz_upload_data has not been called");
+  const int64_t CG = (int64_t)h->C * h->G;
+  k_init_state<<<gene_grid(h, h->G, h->C), BLOCK, 0, h->stream>>>(h->G, h->cfg.gene_offset, h->cfg.seed, step, rowvar_log_mean, rowvar_sd, h->Xg,
+                                                                  h->gl, h->perm, h->nd_mask, h->xbar, h->xss, h->hyper, h->Yg, h->vg, h->ty, h->tv, h->flags);
+  ZZ_LAUNCHED(h);
+  k_window_init<<<gene_grid(h, CG), BLOCK, 0, h->stream>>>(CG, h->win_y, h->win_v);     // Yg_trace, variance_g_trace: I:460, I:466
+  ZZ_LAUNCHED(h);
+  h->lps_valid = false; h->stats_fresh = false; h->caches_valid = false;
+  return zz_refresh_caches(h);                                        // I:473, I:504
 }
 
 int zz_get_alloc_trace(zz_handle *h, int chain, uint32_t *out) {

@@ -84,7 +84,10 @@ def initial_state(X, gl, hyper, seed):
         d2 = np.where(det, (X - rwm[:, None]) ** 2, 0.0).sum(1)
         full = ndet == R
         rv_full = d2[full] / (R - 1)
-        m, s = np.log(rv_full.mean()), np.sqrt(rv_full.var(ddof=1))         # I:446
+        if len(rv_full) > 1:
+            m, s = np.log(rv_full.mean()), np.sqrt(rv_full.var(ddof=1))     # I:446
+        else:                                                               # data without detections: Yg = rwm (I:452-455)
+            m, s = -np.inf, 0.0
         rwv = np.where(ndet >= 2, d2 / np.maximum(ndet - 1, 1), np.exp(m + s * rng.standard_normal(G)))        # I:441-448
     Yg = rwm + np.sqrt(rwv) * rng.standard_normal(G)                        # I:449
     vg = np.exp(0.5 + 0.2 * rng.standard_normal(G))                         # I:465

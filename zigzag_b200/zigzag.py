@@ -73,7 +73,7 @@ class zigzag:
                  shared_variance=True, output_directory="output", threshold_a=None, threshold_i=None, beta=1, temperature=1,
                  tau_shape=1, tau_rate=1, s0_mu=-1, s0_sigma=2, s1_shape=1, s1_rate=2, variance_g_upper_bound=math.inf,
                  alpha_r_shape=1, alpha_r_rate=1 / 10, active_gene_set=None, gene_names=None, seed=0, device=0,
-                 shard=None, process_group=None, write_settings=True):
+                 shard=None, process_group=None, write_settings=True, init="host"):
         if not shared_variance or not shared_active_variance:
             raise NotImplementedError("only the reference's default shared_variance=TRUE model is wired up")
         if threshold_a is None or threshold_i is None or isinstance(num_active_components, str):
@@ -151,20 +151,32 @@ class zigzag:
         self._step = 0
         self.lnl_trace = []
         self.n_samples = 0
-        # ---- per-gene initial state (I:416-504), drawn per shard
-        st = synth.initial_state(Xl, self.gene_lengths, self._hyper_dict(), seed + 7919 * (self.rank + 1))
+        # ---- per-gene initial state (I:416-504): init="host" draws it per shard with NumPy (synth.initial_state), init="device" runs
+        # the same recipe on the GPU (zz_init_state: Philox keyed by the global gene index, so it does not depend on the sharding)
         pinned = None
         if active_gene_set is not None:
             idx = [self.gene_names.index(g) for g in active_gene_set]
             pinned = np.zeros(G, np.int32); pinned[idx] = 1
             pinned = pinned[self.g0:self.g1]
-            st["alloc_active_inactive"][pinned == 1] = 1                                                       # I:369
-        # ---- device
+        self._seed, self._device = seed, device
         self.h = _capi.Handle(self.g1 - self.g0, R, K, num_chains=1, device=device, seed=seed, gene_offset=self.g0)
         self.h.upload_data(Xl, self.gene_lengths)
         self._push_hyper()
-        self.h.set_state(0, pinned_active=pinned, **st)
-        self.h.refresh_caches()                                                                                # I:473, I:504
+        if init == "device":
+            full = ~np.isneginf(self.Xg).any(1)
+            rv = self.Xg[full].var(axis=1, ddof=1)                                                             # I:446, whole data set
+            # fewer than two fully detected genes: rwv = 0, i.e. Yg = rwm (the reference's branch for data without any detection, I:452-455)
+            rv_m, rv_s = (math.log(rv.mean()), math.sqrt(rv.var(ddof=1))) if len(rv) > 1 else (-math.inf, 0.0)
+            if pinned is not None:
+                self.h.set_state(0, pinned_active=pinned)
+            self.h.init_state(0, rv_m, rv_s)
+        else:
+            st = synth.initial_state(Xl, self.gene_lengths, self._hyper_dict(), seed + 7919 * (self.rank + 1))
+            if pinned is not None:
+                st["alloc_active_inactive"][pinned == 1] = 1                                                   # I:369
+            self.h.set_state(0, pinned_active=pinned, **st)
+            self.h.refresh_caches()                                                                            # I:473, I:504
+        self._pinned = pinned
         self._state_cache = None
         # gene shards on several GPUs of one node: peer-memory all-reduce inside the kernels (needed by schedule="device")
         self._p2p = False
@@ -664,6 +676,170 @@ class zigzag:
         self._check_nan()
         if compute_probs and write_to_files:
             self.computeGeneExpressionProbs_writeToFile(pdir + "/" + prefix)
+
+    # ------------------------------------------------------------------ the chain axis: tempering and stepping stones
+    def _batched_handle(self, nchains, temperatures=None, betas=None):
+        """A handle with `nchains` chains over the same data, every chain a copy of this object's state and hyper-parameters except
+        for its temperature / beta, plus the per-chain scalar state in the layout of zz_chain_begin."""
+        if self.world != 1:
+            raise NotImplementedError("batched chains live on one GPU (shard chains, not genes, over several GPUs)")
+        hb = _capi.Handle(self.num_transcripts, self.num_libraries, self.num_active_components, num_chains=nchains, device=self._device,
+                          seed=self._seed + 104729, gene_offset=0)
+        hb.upload_data(np.asfortranarray(self.Xg), self.gene_lengths)
+        st = self.h.get_state(0)
+        d = self._hyper_dict()
+        for c in range(nchains):
+            dc = dict(d)
+            if temperatures is not None:
+                dc["temperature"] = float(temperatures[c])
+            if betas is not None:
+                dc["beta"] = float(betas[c])
+            hb.set_hyper(_capi.Hyper.make(dc["alpha_r"], dc["active_means"], dc["active_variances"], dc["weight_within_active"],
+                                          **{k: float(dc[k]) for k in ("s0", "s1", "tau", "spike_probability", "inactive_means", "inactive_variances",
+                                                                       "weight_active", "beta", "temperature", "variance_g_upper_bound")}), c)
+            hb.set_state(c, pinned_active=self._pinned, **{k: st[k] for k in ("Yg", "variance_g", "alloc_active_inactive", "alloc_within_active",
+                                                                             "inactive_spike_allocation", "tuningParam_yg", "tuningParam_variance_g")})
+        hb.refresh_caches()
+        hb.chain_begin(self._priors_struct(), [self._chain_scalars() for _ in range(nchains)])
+        return hb
+
+    def _log_prior(self, hy, sc):
+        """lnPrior of get_logPosterior (R/zigzagUtilities.R:249-254) without its per-gene term, from zz_hyper + zz_chain_scalars."""
+        p, K, R = self.pri, self.num_active_components, self.num_libraries
+        lbeta = lambda a, b: math.lgamma(a) + math.lgamma(b) - math.lgamma(a + b)
+        dbeta = lambda x, a, b: (a - 1) * math.log(x) + (b - 1) * math.log1p(-x) - lbeta(a, b)
+        ww, al = list(hy.weight_within_active[:K]), self.weight_within_active_alpha
+        ddir = sum((a - 1) * math.log(x) for a, x in zip(al, ww)) + math.lgamma(sum(al)) - sum(math.lgamma(a) for a in al)
+        return (dbeta(hy.spike_probability, p["spike_prior_shape_1"], p["spike_prior_shape_2"])
+                + sum(_dgamma_log(a, p["alpha_r_shape"], p["alpha_r_rate"]) for a in hy.alpha_r[:R])
+                + dbeta(hy.weight_active, p["weight_active_shape_1"], p["weight_active_shape_2"]) + ddir
+                + sum(_dgamma_log(x, p["active_means_dif_prior_shape"], p["active_means_dif_prior_rate"]) for x in sc.active_means_dif[:K])
+                + sum(_dunif_log(math.log10(v), p["var_log_min"], p["var_log_max"]) for v in hy.active_variances[:K])
+                + _dgamma_log(self.threshold_i - hy.inactive_means, p["inactive_means_prior_shape"], p["inactive_means_prior_rate"])
+                + _dunif_log(math.log10(hy.inactive_variances), p["var_log_min"], p["var_log_max"])
+                + _dgamma_log(hy.tau, p["tau_shape"], p["tau_rate"]) + _dnorm_log(hy.s0, p["s0_mu"], p["s0_sigma"])
+                + _dgamma_log(abs(hy.s1), p["s1_shape"], p["s1_rate"]))
+
+    def _log_posterior_untempered(self, stats, hy, sc):
+        """get_logPosterior(t = 1) of one chain (U:241-263): data likelihood + level-2 likelihoods + variance prior (gene sums, from the
+        chain's sufficient statistics) + the scalar priors."""
+        K1 = self.num_active_components + 1
+        st = dict(n=stats[:K1], sy=stats[K1:2 * K1], sy2=stats[2 * K1:3 * K1], n_inspike=stats[3 * K1])
+        n0out = st["n"][0] - st["n_inspike"]
+        iv, im, sp = hy.inactive_variances, hy.inactive_means, hy.spike_probability
+        li = st["n_inspike"] * math.log(sp) + n0out * (math.log(1 - sp) - math.log(SQRT2PI * math.sqrt(iv))) \
+            - (st["sy2"][0] - 2 * im * st["sy"][0] + n0out * im * im) / (2 * iv)
+        la = 0.0
+        for k in range(self.num_active_components):
+            n, sy, sy2, am, av = st["n"][k + 1], st["sy"][k + 1], st["sy2"][k + 1], hy.active_means[k], hy.active_variances[k]
+            la += -n * math.log(SQRT2PI * math.sqrt(av)) - (sy2 - 2 * am * sy + n * am * am) / (2 * av)
+        return float(stats[3 * K1 + 7] + stats[3 * K1 + 8] + li + la) + self._log_prior(hy, sc)
+
+    def mc3(self, nchains=4, burnin_ngen=1000, mcmc_ngen=10000, sample_frequency=20, dT=0.025, swap_every=1, write_to_files=True,
+            mcmcprefix="mc3_out", compute_probs=True):
+        """Metropolis-coupled chains (R/zigzagDevelopment.R:9-139) on the CHAIN AXIS of one batched handle: chain c runs at temperature
+        1 / (1 + dT c); after every `swap_every` generations (the reference: 1) each neighbouring pair proposes to exchange temperatures
+        with ratio posterior1(T2) + posterior2(T1) - posterior1(T1) - posterior2(T2) (get_logPosterior, U:241-263).  States stay in
+        their slots, temperatures move; the slot that becomes cold inherits the cold chain's tuning parameters (R/zigzagDevelopment.R:
+        113-120) and the cold chain's samples accumulate in ONE allocation trace.  Returns (swaps accepted, swaps proposed)."""
+        temps = [1.0 / (1.0 + dT * c) for c in range(nchains)]
+        hb = self._batched_handle(nchains, temperatures=temps)
+        K1 = self.num_active_components + 1
+        hb.run_generations(burnin_ngen, tune=True, target=0.23)                                   # R/zigzagDevelopment.R:44-52
+        prefix, pdir = mcmcprefix.split("/")[-1], mcmcprefix + "_mcmc_output"
+        if write_to_files:
+            os.makedirs(os.path.join(self.output_directory, pdir), exist_ok=True)
+            self.initializeOutputFiles(pdir + "/" + prefix)
+        slot = list(range(nchains))                                                                # slot[i] = chain slot at temperature temps[i]
+        acc = prop = 0
+        n_samples, gen0 = 0, self.gen
+        for cycle in range(mcmc_ngen // swap_every):
+            hb.run_generations(swap_every, tune=False, sample_frequency=1 << 30)
+            sc, hy = hb.chain_read()
+            stats = hb.suffstats()
+            L = [self._log_posterior_untempered(stats[c], hy[c], sc[c]) for c in range(nchains)]
+            changed = False
+            for i in range(nchains - 1):                                                           # every neighbouring pair, in order (:75)
+                a, b = slot[i], slot[i + 1]
+                prop += 1
+                if self._accept((temps[i + 1] - temps[i]) * (L[a] - L[b])):                        # t2 L1 + t1 L2 - t1 L1 - t2 L2
+                    acc += 1; changed = True
+                    slot[i], slot[i + 1] = b, a
+                    if i == 0:                                                                     # the cold chain moves to slot b (:107-120)
+                        hb.copy_chain_tuning(a, b)
+                        for name in ("t_im", "t_av", "t_s0", "t_s1", "t_tau", "t_s0tau"):
+                            setattr(sc[b], name, getattr(sc[a], name))
+                        sc[b].t_am, sc[b].t_alpha = sc[a].t_am, sc[a].t_alpha
+            if changed:
+                for i, c in enumerate(slot):
+                    hy[c].temperature = temps[i]
+                    hb.set_hyper(hy[c], c)
+                hb.chain_begin(self._priors_struct(), sc)
+            g = gen0 + (cycle + 1) * swap_every
+            if g % sample_frequency < swap_every:                                                  # sample the cold chain (M:188-217)
+                cold = slot[0]
+                hb.accumulate_alloc_trace_from(cold, 0)
+                n_samples += 1
+                self.lnl_trace.append(float(stats[cold][3 * K1 + 7]))
+                if write_to_files:
+                    h0 = hy[cold]
+                    row = [self.lnl_trace[-1], h0.s0, h0.s1, h0.tau, *h0.alpha_r[:self.num_libraries], h0.spike_probability, h0.inactive_means,
+                           h0.inactive_variances, *h0.active_means[:K1 - 1], *h0.active_variances[:K1 - 1], h0.weight_active,
+                           *h0.weight_within_active[:K1 - 1]]
+                    with open(self._path(pdir + "/" + prefix, "_model_parameters.log"), "a") as f:
+                        f.write("\t".join([_rnum(g)] + [_rnum(round(float(x), 4)) for x in row]) + "\n")
+        # the cold chain becomes this object's state
+        sc, hy = hb.chain_read()
+        cold = slot[0]
+        st = hb.get_state(cold)
+        self._adopt_chain(sc[cold], hy[cold])
+        self.temperature = 1.0
+        self.h.set_state(0, **st)
+        self._push_hyper()
+        self.h.refresh_caches()
+        tr = hb.get_alloc_trace(0).T.astype(np.float64)
+        self.mc3_prob_active = 1 - np.round(tr[:, 0] / max(tr[0].sum(), 1.0), 3)
+        self.mc3_temperatures, self.mc3_slots = temps, slot
+        if write_to_files and compute_probs:
+            with open(self._path(pdir + "/" + prefix, "_probability_active.tab"), "w") as f:
+                f.write("gene\tprob_active\n")
+                for gname, pa in zip(self.gene_names, self.mc3_prob_active):
+                    f.write(f"{gname}\t{_rfmt3(pa)}\n")
+        hb.close()
+        return acc, prop
+
+    def estimateMarginalLikelihood(self, burnin_gen=1000, mcmc_gen=10000, ss_sample_frequency=10, power_alpha=0.2, stones=10):
+        """Stepping-stone estimate of the log marginal likelihood (R/zigzagDevelopment.R:142-208).  The reference runs the stones
+        as parallel R processes; here every stone k = 1 .. stones - 1 is one chain of a batched handle at power beta_k =
+        (k / stones)^(1 / power_alpha): all of them burn in and sample side by side in the same launches.  Stone k contributes
+        (b_{k+1} - b_k) max + log mean exp((b_{k+1} - b_k)(lnl / b_k - max)) over its sampled lnl (:161-165).
+        Returns (sum over stones, per-stone terms, betas)."""
+        ssbeta = (np.arange(1, stones + 1) / stones) ** (1.0 / power_alpha)
+        C = stones - 1
+        hb = self._batched_handle(C, betas=ssbeta[:C])
+        K1 = self.num_active_components + 1
+        hb.run_generations(burnin_gen, tune=True)
+        lnl = [[] for _ in range(C)]
+        stats = hb.suffstats()
+        for c in range(C):
+            lnl[c].append(float(stats[c][3 * K1 + 7]))                                            # M:145: the trace starts at the current state
+        done = 0
+        while done < mcmc_gen:
+            n = min(ss_sample_frequency, mcmc_gen - done)
+            hb.run_generations(n, tune=False, sample_frequency=1 << 30)
+            done += n
+            stats = hb.suffstats()
+            for c in range(C):
+                lnl[c].append(float(stats[c][3 * K1 + 7]))
+        terms = []
+        for k in range(C):
+            ss = np.array(lnl[k]) / ssbeta[k]                                                      # :161 (lnl_trace holds beta * lnl, P:125)
+            db, mx = ssbeta[k + 1] - ssbeta[k], ss.max()
+            terms.append(float(db * mx + np.log(np.mean(np.exp(db * (ss - mx))))))
+        if hb.nan_flag():
+            raise FloatingPointError("an NA or NaN somewhere! (device NaN flag raised)")
+        hb.close()
+        return float(np.sum(terms)), terms, ssbeta
 
     def allocation_trace(self):
         """G_shard x (K+1) counts, R/zigzagMCMC.R:194-199."""
