@@ -3,6 +3,7 @@
 positions in the two Philox streams; afterwards every hyper-parameter, every scalar tuning parameter and window, the number of
 uniforms consumed by the hyper moves, the per-gene state and the allocation trace must agree."""
 import ctypes as C
+import math
 import numpy as np
 import pytest
 from oracle import oracle as O
@@ -246,32 +247,45 @@ def test_device_loop_reproduces_the_golden_chain_trajectory():
     assert np.array_equal(h.get_alloc_trace(0).sum(axis=1), want["trace"])
 
 
-def test_device_loop_full_size_invariants():
-    """BASELINE.json's 1 M x 16 workload through the device-resident loop: counts add up, nothing non-finite, hyper-parameters stay in
-    the neighbourhood of the simulation truth they started from, the allocation trace counts every gene once per sample."""
-    X, gl, hd, st, _ = synth.make_config("1m_x16")
+@pytest.mark.parametrize("name", ["1m_x16", "200k_x8", "20k_x2", "64ch_60k_x4"])
+def test_device_loop_full_size_invariants(name):
+    """Every BASELINE.json workload at its full size through the device-resident loop (1 M x 16; 200 k x 8 with gene-length-dependent
+    detection; 20 k x 2; 64 batched chains x 60 k x 4): counts add up, nothing non-finite, every chain's hyper-parameters stay in the
+    neighbourhood of the simulation truth they started from, the allocation trace counts every gene once per sample."""
+    X, gl, hd, st, C_ = synth.make_config(name)
     G, R = X.shape
     hg = _capi.Hyper.make(hd["alpha_r"], hd["active_means"], hd["active_variances"], hd["weight_within_active"],
                           **{k: float(hd[k]) for k in ("s0", "s1", "tau", "spike_probability", "inactive_means", "inactive_variances",
                                                        "weight_active", "beta", "temperature", "variance_g_upper_bound")})
-    h = _capi.Handle(G, R, 2, seed=8)
-    h.upload_data(X, gl); h.set_hyper(hg, 0); h.set_state(0, **st); h.refresh_caches(); h.reset_alloc_trace()
+    h = _capi.Handle(G, R, 2, num_chains=C_, seed=8)
+    h.upload_data(X, gl)
+    for c in range(C_):
+        h.set_hyper(hg, c); h.set_state(c, **st)
+    h.refresh_caches(); h.reset_alloc_trace()
     thr_a = (1.0, 6.0)
-    h.chain_begin(_capi.Priors.defaults(-1.0, thr_a), _capi.ChainScalars.initial(hd["active_means"], thr_a, R))
+    h.chain_begin(_capi.Priors.defaults(-1.0, thr_a), [_capi.ChainScalars.initial(hd["active_means"], thr_a, R) for _ in range(C_)])
     h.run_sweeps(1 << 40, 400)                      # the per-gene state equilibrates under the true hyper-parameters first
     h.run_generations(30, tune=True)
     h.run_generations(10, tune=False, sample_frequency=2)
-    sc, hy = h.chain_read()
-    assert sc.gen == 40 and sc.n_samples == 1 + 5 and h.nan_flag() == 0
-    # 1 M genes pin every hyper-parameter tightly: started at the simulation truth with an equilibrated per-gene state, the chain
-    # stays there (a wrong gene sum in any hyper move would let it walk away at once)
-    assert abs(hy.tau - hd["tau"]) < 0.03 and abs(hy.s0 - hd["s0"]) < 0.03 and abs(hy.s1 - hd["s1"]) < 0.01, (hy.tau, hy.s0, hy.s1)
-    assert abs(hy.weight_active - hd["weight_active"]) < 0.005 and abs(hy.spike_probability - hd["spike_probability"]) < 0.005
-    assert np.allclose(hy.alpha_r[:R], hd["alpha_r"], rtol=0.01) and abs(hy.inactive_means - hd["inactive_means"]) < 0.02
-    assert np.allclose(hy.active_means[:2], hd["active_means"], atol=0.05) and abs(hy.inactive_variances - 2.0) < 0.05
-    s = h.get_state(0)
-    assert np.isfinite(s["Yg"]).all() and (s["variance_g"] > 0).all()
-    tr = h.get_alloc_trace(0)
-    assert tr.sum() == 6 * G and np.array_equal(tr.sum(axis=0), np.full(G, 6))
-    st_ = h.suffstats()[0]
-    assert st_[:3].sum() == G
+    scs, hys = h.chain_read()
+    if C_ == 1:
+        scs, hys = [scs], [hys]
+    assert h.nan_flag() == 0
+    # the genes pin every hyper-parameter (posterior sd ~ 1 / sqrt(G)): started at the simulation truth with an equilibrated per-gene
+    # state, a chain stays there — a wrong gene sum in any hyper move would let it walk away at once
+    f = min(10.0, math.sqrt(1e6 / G)) * (2.0 if R == 2 else 1.0)
+    for sc, hy in zip(scs, hys):
+        assert sc.gen == 40 and sc.n_samples == 1 + 5
+        assert abs(hy.tau - hd["tau"]) < 0.03 * f and abs(hy.s0 - hd["s0"]) < 0.03 * f and abs(hy.s1 - hd["s1"]) < 0.01 * f, (hy.tau, hy.s0, hy.s1)
+        assert abs(hy.weight_active - hd["weight_active"]) < 0.005 * f and abs(hy.spike_probability - hd["spike_probability"]) < 0.005 * f
+        assert np.allclose(hy.alpha_r[:R], hd["alpha_r"], rtol=0.01 * f) and abs(hy.inactive_means - hd["inactive_means"]) < 0.02 * f
+        assert np.allclose(hy.active_means[:2], hd["active_means"], atol=0.05 * f) and abs(hy.inactive_variances - 2.0) < 0.05 * f
+    if C_ > 1:                                       # independent chains: distinct Philox streams, so distinct trajectories
+        assert len({hy.tau for hy in hys}) == C_
+    for c in (0, C_ - 1):
+        s = h.get_state(c)
+        assert np.isfinite(s["Yg"]).all() and (s["variance_g"] > 0).all()
+        tr = h.get_alloc_trace(c)
+        assert tr.sum() == 6 * G and np.array_equal(tr.sum(axis=0), np.full(G, 6))
+    st_ = h.suffstats()
+    assert all(st_[c][:3].sum() == G for c in range(C_))

@@ -117,3 +117,20 @@ def test_posterior_predictive_logs(tmp_path, schedule):
     # realised minus simulated discrepancies of an (almost) converged chain scatter around zero, far from the scale of the data
     assert np.abs(rows[:, 1]).max() < 1.0 and np.abs(rows[:, 2]).max() < 1.0 and np.abs(rows[:, 3]).max() < 0.1
     assert np.std(rows[:, 1]) > 0
+
+
+def test_lung_prob_active_full_length_device_schedule(tmp_path):
+    """North-star check (3) at the tutorial's full length and beyond: 5 000 burn-in + 100 000 sampling generations (the tutorial:
+    20 000) through the device-resident loop, 10 000 samples of the allocation — Monte-Carlo error ~0.006 per probability, so the
+    ten published values must be met within 0.03 (the oracle's own long runs: tests/golden/lung_long_run_oracle.json)."""
+    d, tpm, gl, names = lung()
+    worst = []
+    for seed in (3, 4):
+        mm = zigzag(tpm, gl, num_active_components=2, threshold_i=float(d["threshold_i"]), threshold_a=d["threshold_a"],
+                    output_directory=str(tmp_path), gene_names=names, seed=seed, write_settings=False)
+        mm.burnin(sample_frequency=50, ngen=5000, write_to_files=False, schedule="device")
+        mm.mcmc(sample_frequency=10, ngen=100000, write_to_files=False, compute_probs=False, schedule="device")
+        pa = mm.prob_active()
+        worst.append(float(np.abs(pa[:10] - d["tutorial_prob_active_first10"]).max()))
+        assert mm.n_samples > 9990 and -10900 < mm.lnl_trace[-1] < -10100
+    assert max(worst) < 0.03, worst
