@@ -235,40 +235,175 @@ __device__ inline void stage_gibbs_combine(zz_hyper &h, int K, const double *g) 
   if (!isnan(ns)) h.spike_probability = ns;
 }
 
-// warp 1: mhInactiveMeans (Pr:433-471), mhActiveMeansDif x K (Pr:640-705), mhSharedVariance (Pr:768-803).  Works on private copies
-// of the level-2 parameters; the caller installs `cur` and the scalar state afterwards.
-// mhInactiveMeans (Pr:433-471): z = (w0, w1), accept w2.  Touches inactive_means only — independent of the active means.
-__device__ inline double stage_im(const SMath &m, ChainDev &c, const zz_hyper &h, const MoveDraws *md, const double *st, int K, int tune) {
-  const MoveDraws &d = md[MD_IM];
-  const double thr = c.pr.threshold_i, im = h.inactive_means, iv = h.inactive_variances, riv = 1.0 / (2 * iv);
-  const double imp = thr - fabs(thr - im - c.t_im * d.n01);
-  const double pp = dgamma_log_diff(m, thr - imp, thr - im, c.pr.inactive_means_prior_shape, c.pr.inactive_means_prior_rate);
-  const double Rr = h.temperature * (closed_inactive_diff(m, st, K, imp, iv, riv, im, iv, riv) + pp);
-  if (tune) win_push0(c.w_im);
-  if (d.l2 < Rr) { if (tune) win_set_last(c.w_im); return imp; }
-  return im;
+// ---- the Metropolis moves, split in two -----------------------------------------------------------------------------------
+// Everything of a move except its gene sum — proposal, Hastings ratio, prior ratio, the logarithms of a changed variance — depends
+// only on the draws and on parameters that are known BEFORE the sweep's statistics are: stage_*_pre computes it (on the steward CTA:
+// while the other CTAs sweep), stage_*_post adds the closed-form gene sum and decides.  Moves later in a chain depend on whether
+// earlier ones were accepted: their pre-parts are tabulated for every outcome that can reach them.  The arithmetic of each
+// expression is unchanged (same operands, same order), so the decisions are those of the one-piece moves.
+
+// closed_varg_diff with the variance logarithms handed in: ldt = m.log(taup) - m.log(tau)
+__device__ inline double closed_varg_diff_pre(const double *st, int K, double s0p, double s1p, double taup, double rtp, double s0, double s1, double tau, double rt, double ldt) {
+  const double *fx = st + 3 * (K + 1);
+  const double n = fx[1], sz = fx[2], sz2 = fx[3], syo = fx[4], sy2o = fx[5], syz = fx[6];
+  const double cp = s0p + taup, cc = s0 + tau;
+  const double qp = sz2 + n * cp * cp + s1p * s1p * sy2o - 2 * cp * sz - 2 * s1p * syz + 2 * cp * s1p * syo;
+  const double qc = sz2 + n * cc * cc + s1 * s1 * sy2o - 2 * cc * sz - 2 * s1 * syz + 2 * cc * s1 * syo;
+  double d = -(qp * rtp - qc * rt);
+  if (taup != tau) d += -0.5 * n * ldt;                                  // -n log(sqrt(tau) sqrt(2 pi)), P:20
+  return d;
 }
-// mhActiveMeansDif x K (Pr:640-705): round `it`: k = w0, z = (w1, w2), accept w3.  Touches the active means only.
+
+// mhTau (Pr:119-152) -> mhSg (Pr:58-117) -> mhS0Tau (Pr:154-191)
+struct PreVarg {
+  double rt0;                                            // 1 / (2 tau)
+  double t_HR, t_taup, t_rtp, t_pp, t_ldt;               // mhTau: scale w0, accept w1
+  int g_sel, pad_; double g_s0p, g_s1p, g_HR, g_pp;      // mhSg: selector w0; s0: z = (w1, w2), accept w3; s1: scale w1, accept w2
+  // mhS0Tau: scale w0, accept w1; [v]: tau is still h.tau (0) / mhTau was accepted (1); [w]: s0 is still h.s0 (0) / mhSg moved it (1)
+  double z_HR, z_taup[2], z_rtp[2], z_dgam[2], z_ldt[2], z_s0p[2], z_s0rel[2];
+};
+__device__ inline void stage_varg_pre(const SMath &m, const ChainDev &c, const zz_hyper &h, const MoveDraws *md, PreVarg &P) {
+  const double s0 = h.s0, s1 = h.s1, tau = h.tau;
+  P.rt0 = 1.0 / (2 * tau);
+  {
+    const MoveDraws &d = md[MD_TAU];
+    P.t_HR = c.t_tau * (d.u[0] - 0.5); P.t_taup = tau * m.exp(P.t_HR); P.t_rtp = 1.0 / (2 * P.t_taup);   // scale_move, MP:3-13; HR = log(sf)
+    P.t_pp = dgamma_log_diff(m, P.t_taup, tau, c.pr.tau_shape, c.pr.tau_rate);                            // P:3-9
+    P.t_ldt = m.log(P.t_taup) - m.log(tau);
+  }
+  {
+    const MoveDraws &d = md[MD_SG];
+    P.g_s0p = s0; P.g_s1p = s1; P.g_HR = 0;
+    P.g_sel = (d.u[0] < 0.5) ? 1 : 2;
+    if (P.g_sel == 1) { P.g_s0p = s0 + c.t_s0 * d.n12; P.g_pp = s0_prior_rel(c.pr, P.g_s0p) - s0_prior_rel(c.pr, s0); }
+    else {
+      P.g_HR = c.t_s1 * (d.u[1] - 0.5); P.g_s1p = s1 * m.exp(P.g_HR);
+      P.g_pp = dgamma_log_diff(m, fabs(P.g_s1p), fabs(s1), c.pr.s1_shape, c.pr.s1_rate);                  // P:41-47 (the unchanged s0 term cancels)
+    }
+  }
+  {
+    const MoveDraws &d = md[MD_S0TAU];
+    P.z_HR = c.t_s0tau * (d.u[0] - 0.5);
+    const double e = m.exp(P.z_HR);
+    for (int v = 0; v < 2; ++v) {
+      const double tv = v ? P.t_taup : tau;
+      P.z_taup[v] = tv * e; P.z_rtp[v] = 1.0 / (2 * P.z_taup[v]);
+      P.z_dgam[v] = dgamma_log_diff(m, P.z_taup[v], tv, c.pr.tau_shape, c.pr.tau_rate);
+      P.z_ldt[v] = m.log(P.z_taup[v]) - m.log(tv);
+    }
+    for (int w = 0; w < 2; ++w) {
+      const double sw = w ? P.g_s0p : s0;
+      P.z_s0p[w] = sw - P.z_HR; P.z_s0rel[w] = s0_prior_rel(c.pr, P.z_s0p[w]) - s0_prior_rel(c.pr, sw);
+    }
+  }
+}
+__device__ inline void stage_varg_post(const PreVarg &P, ChainDev &c, const zz_hyper &h, const MoveDraws *md, const double *st, int K, int tune, double &s0, double &s1, double &tau) {
+  s0 = h.s0; s1 = h.s1; tau = h.tau;
+  double rt = P.rt0;
+  int v = 0, w = 0;
+  {
+    const double Rr = h.temperature * (closed_varg_diff_pre(st, K, s0, s1, P.t_taup, P.t_rtp, s0, s1, tau, rt, P.t_ldt) + P.t_pp) + P.t_HR;
+    if (tune) win_push0(c.w_tau);
+    if (md[MD_TAU].l1 < Rr) { tau = P.t_taup; rt = P.t_rtp; v = 1; if (tune) win_set_last(c.w_tau); }
+  }
+  {
+    const MoveDraws &d = md[MD_SG];
+    const int sel = P.g_sel;
+    if (tune) { if (sel == 1) win_push0(c.w_s0); else win_push0(c.w_s1); }
+    const double Rr = h.temperature * (closed_varg_diff_pre(st, K, P.g_s0p, P.g_s1p, tau, rt, s0, s1, tau, rt, 0.0) + P.g_pp) + P.g_HR;
+    if ((sel == 1 ? d.l3 : d.l2) < Rr) {
+      s0 = P.g_s0p; s1 = P.g_s1p; w = sel == 1;
+      if (tune) { if (sel == 1) win_set_last(c.w_s0); else win_set_last(c.w_s1); }
+    }
+  }
+  {
+    if (tune) win_push0(c.w_s0tau);
+    const double pp = P.z_s0rel[w] + P.z_dgam[v];
+    const double Rr = h.temperature * (closed_varg_diff_pre(st, K, P.z_s0p[w], s1, P.z_taup[v], P.z_rtp[v], s0, s1, tau, rt, P.z_ldt[v]) + pp) + P.z_HR;
+    if (md[MD_S0TAU].l1 < Rr) { s0 = P.z_s0p[w]; tau = P.z_taup[v]; if (tune) win_set_last(c.w_s0tau); }
+  }
+}
+
+// mhInactiveMeans (Pr:433-471): z = (w0, w1), accept w2 | mhActiveMeansDif x K (Pr:640-705): round `it`: k = w0, z = (w1, w2), accept w3 |
+// mhSharedVariance (Pr:768-803): slide w0, accept w1.  The first two touch disjoint parameters; the third runs at the means they left.
+struct PreL2 {
+  double riv, imp, im_pp;                                // mhInactiveMeans
+  double rav[ZZ_MAX_COMP];                               // 1 / (2 active_variances[k])
+  int amd_k[ZZ_MAX_COMP];                                // component of round it
+  // round it, given the set `mask` of earlier rounds that were accepted (only those on the same component matter): proposed dif, prior ratio
+  double amd_difp[3][4], amd_pp[3][4];
+  double sv_np, sv_pv, sv_avp1, sv_rp1, sv_ldv, sv_ldi, sv_rvc0, sv_rivc, sv_prior; int sv_shared, pad_;
+};
 template <int K>
-__device__ inline void stage_amd(const SMath &m, ChainDev &c, const zz_hyper &h, const MoveDraws *md, const double *st, int tune, double *am_out /* [K] */) {
-  double rav[K], amp[K], am[K], dif[K];                                   // registers: every index below is a compile-time constant
-#pragma unroll
-  for (int k = 0; k < K; ++k) { am[k] = h.active_means[k]; rav[k] = 1.0 / (2 * h.active_variances[k]); dif[k] = c.active_means_dif[k]; }
-#pragma unroll
+__device__ inline void stage_l2_pre(const SMath &m, const ChainDev &c, const zz_hyper &h, const MoveDraws *md, PreL2 &P) {
+  static_assert(K <= 3, "the outcome tables of mhActiveMeansDif hold three rounds");
+  {
+    const MoveDraws &d = md[MD_IM];
+    const double thr = c.pr.threshold_i, im = h.inactive_means;
+    P.riv = 1.0 / (2 * h.inactive_variances);
+    P.imp = thr - fabs(thr - im - c.t_im * d.n01);
+    P.im_pp = dgamma_log_diff(m, thr - P.imp, thr - im, c.pr.inactive_means_prior_shape, c.pr.inactive_means_prior_rate);
+  }
+  for (int k = 0; k < K; ++k) P.rav[k] = 1.0 / (2 * h.active_variances[k]);
   for (int it = 0; it < K; ++it) {
     const MoveDraws &d = md[MD_AMD + it];
     int k = (int)(d.u[0] * K); if (k >= K) k = K - 1;
-    double dk = dif[0];
+    P.amd_k[it] = k;
+    for (int mask = 0; mask < (1 << it); ++mask) {
+      double dk = c.active_means_dif[k];                                  // the current dif[k]: the proposal of the latest accepted round on k
+      for (int j = it - 1; j >= 0; --j) if (((mask >> j) & 1) && P.amd_k[j] == k) { dk = P.amd_difp[j][mask & ((1 << j) - 1)]; break; }
+      const double difp = fabs(dk + c.t_am[k] * d.n12);
+      P.amd_difp[it][mask] = difp;
+      P.amd_pp[it][mask] = dgamma_log_diff(m, difp, dk, c.pr.active_means_dif_prior_shape, c.pr.active_means_dif_prior_rate);
+    }
+  }
+  {
+    const MoveDraws &d = md[MD_SV];
+    const double lo = c.pr.variances_prior_log_min, hi = c.pr.variances_prior_log_max;
+    const double avc = h.active_variances[0], ivc = h.inactive_variances;
+    const double LN10 = 2.302585092994045684, lavc = m.log(avc), pv = lavc * (1.0 / LN10), t = c.t_av;   // log10
+    double np = (pv - t) + ((pv + t) - (pv - t)) * d.u[0];                // two_boundary_slide_move, MP:29-46
+    if (np > hi) np = 2 * hi - np;
+    np = lo + fabs(np - lo);
+    P.sv_np = np; P.sv_pv = pv;
+    P.sv_avp1 = m.exp(np * LN10); P.sv_rp1 = 1.0 / (2 * P.sv_avp1);      // 10^np
+    P.sv_rvc0 = 1.0 / (2 * avc);
+    bool shared = true;
+    for (int k = 0; k < K; ++k) shared = shared && h.active_variances[k] == avc;
+    P.sv_shared = shared;
+    P.sv_ldv = np * LN10 - lavc;                                          // log(avp1) - log(avc), one pair of logarithms
+    P.sv_rivc = ivc == avc ? P.sv_rvc0 : 1.0 / (2 * ivc);
+    P.sv_ldi = P.sv_avp1 != ivc ? m.log(P.sv_avp1) - m.log(ivc) : 0.0;
+    // Pr:786-787 dunif(log10(.), lo, hi, log = TRUE): np is inside [lo, hi] by construction, pv unless the chain started outside
+    P.sv_prior = dunif_log_rel(np, lo, hi) - dunif_log_rel(pv, lo, hi);
+  }
+}
+__device__ inline double stage_im_post(const PreL2 &P, ChainDev &c, const zz_hyper &h, const MoveDraws *md, const double *st, int K, int tune) {
+  const int K1 = K + 1;
+  const double im = h.inactive_means, imp = P.imp, n0out = st[0] - st[3 * K1];
+  const double qp = st[2 * K1] - 2 * imp * st[K1] + n0out * imp * imp, qc = st[2 * K1] - 2 * im * st[K1] + n0out * im * im;
+  const double Rr = h.temperature * (-(qp * P.riv - qc * P.riv) + P.im_pp);       // closed_inactive_diff at equal variances
+  if (tune) win_push0(c.w_im);
+  if (md[MD_IM].l2 < Rr) { if (tune) win_set_last(c.w_im); return imp; }
+  return im;
+}
+template <int K>
+__device__ inline void stage_amd_post(const PreL2 &P, ChainDev &c, const zz_hyper &h, const MoveDraws *md, const double *st, int tune, double *am_out /* [K] */) {
+  double amp[K], am[K], dif[K], rav[K];                                   // registers: every index below is a compile-time constant
 #pragma unroll
-    for (int j = 1; j < K; ++j) if (j == k) dk = dif[j];
-    const double difp = fabs(dk + c.t_am[k] * d.n12);
+  for (int k = 0; k < K; ++k) { am[k] = h.active_means[k]; dif[k] = c.active_means_dif[k]; rav[k] = P.rav[k]; }
+  int mask = 0;
+#pragma unroll
+  for (int it = 0; it < K; ++it) {
+    const int k = P.amd_k[it];
+    const double difp = P.amd_difp[it][mask], pp = P.amd_pp[it][mask];
 #pragma unroll
     for (int j = 0; j < K; ++j) amp[j] = (j == k ? difp : dif[j]) + c.pr.threshold_a[j];
-    const double pp = dgamma_log_diff(m, difp, dk, c.pr.active_means_dif_prior_shape, c.pr.active_means_dif_prior_rate);
     const double Rr = h.temperature * (closed_active_diff<K>(st, amp, rav, am, rav, 0.0) + pp);
     if (tune) win_push0(c.w_am[k]);
-    if (d.l3 < Rr) {
+    if (md[MD_AMD + it].l3 < Rr) {
       if (tune) win_set_last(c.w_am[k]);
+      mask |= 1 << it;
 #pragma unroll
       for (int j = 0; j < K; ++j) { am[j] = amp[j]; if (j == k) dif[j] = difp; }
     }
@@ -276,75 +411,28 @@ __device__ inline void stage_amd(const SMath &m, ChainDev &c, const zz_hyper &h,
 #pragma unroll
   for (int k = 0; k < K; ++k) { am_out[k] = am[k]; c.active_means_dif[k] = dif[k]; }
 }
-// mhSharedVariance (Pr:768-803) at the means the two moves above left: slide w0, accept w1.  Returns the (shared) variance.
+// returns the accepted (shared) variance, NaN when the move was rejected
 template <int K>
-__device__ inline double stage_sv(const SMath &m, ChainDev &c, const zz_hyper &h, const MoveDraws *md, const double *st, int tune, double im, const double *am_in) {
-  const MoveDraws &d = md[MD_SV];
-  const double lo = c.pr.variances_prior_log_min, hi = c.pr.variances_prior_log_max;
-  const double avc = h.active_variances[0], ivc = h.inactive_variances;
-  const double LN10 = 2.302585092994045684, lavc = m.log(avc), pv = lavc * (1.0 / LN10), t = c.t_av;   // log10
-  double np = (pv - t) + ((pv + t) - (pv - t)) * d.u[0];                  // two_boundary_slide_move, MP:29-46
-  if (np > hi) np = 2 * hi - np;
-  np = lo + fabs(np - lo);
-  const double avp1 = m.exp(np * LN10), rp1 = 1.0 / (2 * avp1);           // 10^np
+__device__ inline double stage_sv_post(const SMath &m, const PreL2 &P, ChainDev &c, const zz_hyper &h, const MoveDraws *md, const double *st, int tune, double im, const double *am_in) {
+  constexpr int K1 = K + 1;
+  const double LN10 = 2.302585092994045684;
   if (tune) win_push0(c.w_av);
   double rvp[K], rvc[K], am[K];
-  bool shared = true;
-  const double rvc0 = 1.0 / (2 * avc);
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    am[k] = am_in[k]; rvp[k] = rp1;
-    const bool same = h.active_variances[k] == avc;
-    rvc[k] = same ? rvc0 : 1.0 / (2 * h.active_variances[k]); shared = shared && same;
-  }
+  for (int k = 0; k < K; ++k) { am[k] = am_in[k]; rvp[k] = P.sv_rp1; rvc[k] = (h.active_variances[k] == h.active_variances[0]) ? P.sv_rvc0 : 1.0 / (2 * h.active_variances[k]); }
   double la;
-  if (shared) la = closed_active_diff<K>(st, am, rvp, am, rvc, np * LN10 - lavc);     // log(avp1) - log(avc), one pair of logarithms
+  if (P.sv_shared) la = closed_active_diff<K>(st, am, rvp, am, rvc, P.sv_ldv);
   else {                                                                  // (a state set from outside with unequal variances)
     la = closed_active_diff<K>(st, am, rvp, am, rvc, 0.0);
-    for (int k = 1; k <= K; ++k) la += -0.5 * st[k] * (np * LN10 - m.log(h.active_variances[k - 1]));
+    for (int k = 1; k <= K; ++k) la += -0.5 * st[k] * (P.sv_np * LN10 - m.log(h.active_variances[k - 1]));
   }
-  const double li = closed_inactive_diff(m, st, K, im, avp1, rp1, im, ivc, ivc == avc ? rvc0 : 1.0 / (2 * ivc));
-  // Pr:786-787 dunif(log10(.), lo, hi, log = TRUE): np is inside [lo, hi] by construction, pv unless the chain started outside
-  const double Rr = h.temperature * (la + li + dunif_log_rel(np, lo, hi) - dunif_log_rel(pv, lo, hi));
-  if (d.l1 < Rr) { if (tune) win_set_last(c.w_av); return avp1; }
+  const double n0out = st[0] - st[3 * K1];
+  const double q = st[2 * K1] - 2 * im * st[K1] + n0out * im * im;       // the same quadratic on both sides: the means do not move
+  double li = -(q * P.sv_rp1 - q * P.sv_rivc);
+  if (P.sv_avp1 != h.inactive_variances) li += -0.5 * n0out * P.sv_ldi;
+  const double Rr = h.temperature * (la + li + P.sv_prior);
+  if (md[MD_SV].l1 < Rr) { if (tune) win_set_last(c.w_av); return P.sv_avp1; }
   return NAN;                                                             // rejected: the caller keeps the current variances
-}
-
-// warp 2: mhTau (Pr:119-152), mhSg (Pr:58-117), mhS0Tau (Pr:154-191) on private (s0, s1, tau)
-__device__ inline void stage_varg(const SMath &m, ChainDev &c, const zz_hyper &h, const MoveDraws *md, const double *st, int K, int tune, double &s0, double &s1, double &tau) {
-  s0 = h.s0; s1 = h.s1; tau = h.tau;
-  double rt = 1.0 / (2 * tau);
-  {                                                                       // mhTau: scale w0, accept w1
-    const MoveDraws &d = md[MD_TAU];
-    const double HR = c.t_tau * (d.u[0] - 0.5), taup = tau * m.exp(HR), rtp = 1.0 / (2 * taup);   // scale_move, MP:3-13; HR = log(sf)
-    const double pp = dgamma_log_diff(m, taup, tau, c.pr.tau_shape, c.pr.tau_rate);         // P:3-9
-    const double Rr = h.temperature * (closed_varg_diff(m, st, K, s0, s1, taup, rtp, s0, s1, tau, rt) + pp) + HR;
-    if (tune) win_push0(c.w_tau);
-    if (d.l1 < Rr) { tau = taup; rt = rtp; if (tune) win_set_last(c.w_tau); }
-  }
-  {                                                                       // mhSg: selector w0; s0: z = (w1, w2), accept w3; s1: scale w1, accept w2
-    const MoveDraws &d = md[MD_SG];
-    double s0p = s0, s1p = s1, HR = 0, pp;
-    const int sel = (d.u[0] < 0.5) ? 1 : 2;
-    if (sel == 1) { s0p = s0 + c.t_s0 * d.n12; if (tune) win_push0(c.w_s0); pp = s0_prior_rel(c.pr, s0p) - s0_prior_rel(c.pr, s0); }
-    else {
-      HR = c.t_s1 * (d.u[1] - 0.5); s1p = s1 * m.exp(HR); if (tune) win_push0(c.w_s1);
-      pp = dgamma_log_diff(m, fabs(s1p), fabs(s1), c.pr.s1_shape, c.pr.s1_rate);           // P:41-47 (the unchanged s0 term cancels)
-    }
-    const double Rr = h.temperature * (closed_varg_diff(m, st, K, s0p, s1p, tau, rt, s0, s1, tau, rt) + pp) + HR;
-    if ((sel == 1 ? d.l3 : d.l2) < Rr) {
-      s0 = s0p; s1 = s1p;
-      if (tune) { if (sel == 1) win_set_last(c.w_s0); else win_set_last(c.w_s1); }
-    }
-  }
-  {                                                                       // mhS0Tau: scale w0, accept w1
-    const MoveDraws &d = md[MD_S0TAU];
-    const double HR = c.t_s0tau * (d.u[0] - 0.5), taup = tau * m.exp(HR), s0p = s0 - HR, rtp = 1.0 / (2 * taup);
-    if (tune) win_push0(c.w_s0tau);
-    const double pp = s0_prior_rel(c.pr, s0p) - s0_prior_rel(c.pr, s0) + dgamma_log_diff(m, taup, tau, c.pr.tau_shape, c.pr.tau_rate);
-    const double Rr = h.temperature * (closed_varg_diff(m, st, K, s0p, s1, taup, rtp, s0, s1, tau, rt) + pp) + HR;
-    if (d.l1 < Rr) { s0 = s0p; tau = taup; if (tune) win_set_last(c.w_s0tau); }
-  }
 }
 
 // mhP_x (Pr:193-243), first half: library, proposed alpha, Hastings and prior ratios — before the sweep that accumulates its gene sum.
@@ -358,6 +446,27 @@ __device__ inline void px_propose(ChainDev &c, const zz_hyper &h, uint64_t seed,
   // prior ratio: the reference sums dgamma over all R libraries for both vectors; the R - 1 unchanged terms are identical
   c.px_pp = dgamma_log_diff(LibM(), ap, h.alpha_r[lib], c.pr.alpha_r_shape, c.pr.alpha_r_rate);
   c.px_HR = HR; c.px_lib = lib; c.px_alpha = ap; c.px_valid = 1;
+}
+// the same in two pieces for the device-resident loop: the NEXT generation's proposal is prepared while the current sweep runs,
+// for both values alpha_r[lib] can have by then (unchanged / the pending proposal on the same library was accepted)
+struct PrePx { int lib, same; double HR, ap[2], pp[2]; };
+__device__ inline void px_propose_pre(const ChainDev &c, const zz_hyper &h, uint64_t seed, uint64_t step, int R, PrePx &P) {
+  uint32_t o[4];
+  philox_block(seed, (uint32_t)c.chain, step, 0, 0xFFFFFF00ull + SUB_PX, o);
+  int lib = (int)(u32_open(o[0]) * R); if (lib >= R) lib = R - 1;
+  P.lib = lib; P.same = c.px_valid && lib == c.px_lib;
+  P.HR = c.t_alpha[lib] * (u32_open(o[1]) - 0.5);
+  const double e = exp(P.HR);
+  for (int v = 0; v < 2; ++v) {
+    const double ac = (v && P.same) ? c.px_alpha : h.alpha_r[lib];
+    P.ap[v] = ac * e;
+    P.pp[v] = dgamma_log_diff(LibM(), P.ap[v], ac, c.pr.alpha_r_shape, c.pr.alpha_r_rate);
+  }
+}
+__device__ inline void px_propose_post(const PrePx &P, ChainDev &c, int accepted_now, int tune) {
+  const int v = (accepted_now && P.same) ? 1 : 0;
+  if (tune) win_push0(c.w_alpha[P.lib]);
+  c.px_pp = P.pp[v]; c.px_HR = P.HR; c.px_lib = P.lib; c.px_alpha = P.ap[v]; c.px_valid = 1;
 }
 // second half, after the sweep: `delta` = sum over genes of ll(alpha') - ll(alpha) of the one library, `bad` = non-finite terms seen
 __device__ inline double px_log_u(const ChainDev &c, uint64_t seed, uint64_t step) {   // log of the move's accept uniform (needs no statistics)

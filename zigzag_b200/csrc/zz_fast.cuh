@@ -103,11 +103,30 @@ __device__ __forceinline__ void derive_fast(FastH &H, const zz_hyper *hy) {
   derive_fin(H, hy);
 }
 // the same by a whole CTA: call, __syncthreads(), then one thread calls derive_fin
+// (one libm logarithm per thread: on a single lane it is a chain of ~120 dependent instructions, 0.7 us; the expressions are those
+//  of derive_scalars, evaluated on the same operands, so the constants are bit-identical)
 __device__ __forceinline__ void derive_fast_par(FastH &H, const zz_hyper *hy, int tid) {
-  if (tid < 3) derive_scalars(H, hy, tid);
-  else if (tid >= 8 && tid < 8 + hy->num_active_components) derive_comp(H, hy, tid - 8);
-  else if (tid >= 32 && tid < 32 + hy->num_libraries) derive_lib(H, hy, tid - 32);
+  const double s2p = sqrt(2 * PI_D);
+  const int w = tid >> 5, lane = tid & 31;
+  if (lane == 0) {                          // one task per WARP: different tasks on the lanes of one warp would run one after the other
+    switch (w) {
+      case 0: H.R = hy->num_libraries; H.K = hy->num_active_components; H.s0 = hy->s0; H.s1 = hy->s1; H.tau = hy->tau;
+              H.rtau = sqrt(hy->tau); H.irt = 1.0 / H.rtau; break;
+      case 1: H.c1 = log(sqrt(hy->tau) * s2p); break;
+      case 2: H.sp = hy->spike_probability; H.log_sp = log(hy->spike_probability); H.wa = hy->weight_active; H.one_m_wa = 1 - hy->weight_active;
+              H.beta = (hy->beta < 0.0000001) ? 0.0 : hy->beta; H.temp = hy->temperature; H.vub = hy->variance_g_upper_bound; H.one_hi = 0x3FF00000; break;
+      case 3: H.log_1msp = log(1 - hy->spike_probability); break;
+      case 4: H.im = hy->inactive_means; H.sd_i = sqrt(hy->inactive_variances); H.inv2iv = 1.0 / (2 * hy->inactive_variances); break;
+      case 5: H.log_norm_i = log(s2p * sqrt(hy->inactive_variances)); break;
+      case 6: H.c0 = (1 - hy->spike_probability) / (s2p * sqrt(hy->inactive_variances)); break;
+      default: break;
+    }
+  } else if (w < 3) {                       // lanes 1.. of warps 0-2: the per-library constants (three multiplications each)
+    const int r = w * 31 + lane - 1;
+    if (r < hy->num_libraries) derive_lib(H, hy, r);
+  } else if (w == 7 && lane <= hy->num_active_components) derive_comp(H, hy, lane - 1);
 }
+constexpr int DERIVE_FIN_THREAD = 7 * 32;   // derive_fin (+ set_px) runs here, beside derive_fast_par (it reads the hyper-parameters only)
 
 __device__ __forceinline__ void load_tabs(MathTabs &T, const double *__restrict__ exp_tab, const double2 *__restrict__ log_tab) {
   const int t = threadIdx.x, nt = blockDim.x;

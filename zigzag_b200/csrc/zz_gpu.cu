@@ -2386,6 +2386,16 @@ int launch_generations(zz_handle *h, uint64_t step0, int ngen, int tune, int hyp
     ga.do_allreduce = 1;
     fill_comm(h, ga.cm, nstat, comm_take_epochs(h, (unsigned long long)ngen));   // generation gi exchanges under epoch ga.cm.epoch + gi + 1
   }
+  // diagnostics: ZZ_GEN_TRACE=<file> dumps per-CTA time stamps of the first 16 generations of every launch (this call then waits for the launch)
+  static const char *trace_path = getenv("ZZ_GEN_TRACE");
+  unsigned long long *trace_dev = nullptr;
+  const int trace_gens = ngen < 16 ? ngen : 16;
+  const size_t trace_words = (size_t)trace_gens * per_chain * 4;
+  if (trace_path && C == 1) {
+    ZZ_CUDA(h, cudaMalloc(&trace_dev, trace_words * 8));
+    ZZ_CUDA(h, cudaMemsetAsync(trace_dev, 0, trace_words * 8, h->stream));
+    ga.trace = trace_dev; ga.trace_gens = trace_gens;
+  }
   ZZ_CUDA(h, cudaMemsetAsync(h->genctl, 0, sizeof(GenCtl) * C, h->stream));
   ZZ_CUDA(h, cudaMemsetAsync(h->genacc, 0, sizeof(long long) * (size_t)C * nstat, h->stream));
   const dim3 grid((unsigned)per_chain, (unsigned)C);
@@ -2404,6 +2414,16 @@ int launch_generations(zz_handle *h, uint64_t step0, int ngen, int tune, int hyp
   ZZ_CUDA(h, e);
   h->launches++;
   h->caches_valid = false; h->stats_fresh = false;
+  if (trace_dev) {
+    std::vector<unsigned long long> buf(trace_words);
+    ZZ_CUDA(h, cudaMemcpyAsync(buf.data(), trace_dev, trace_words * 8, cudaMemcpyDeviceToHost, h->stream));
+    ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(trace_dev);
+    if (FILE *f = fopen(trace_path, "ab")) {
+      const unsigned long long hdr[4] = {0x7a7a747261636531ull, (unsigned long long)trace_gens, (unsigned long long)per_chain, (unsigned long long)steward};
+      fwrite(hdr, 8, 4, f); fwrite(buf.data(), 8, trace_words, f); fclose(f);
+    }
+  }
   return ZZ_OK;
 }
 

@@ -55,6 +55,7 @@ struct GenArgs {
   double *stats_out;                // [C][nstat] or NULL: the (all-reduced) statistics of the last generation run, as doubles
   int do_allreduce; CommArgs cm;    // cm.epoch = epoch of the first generation - 1
   long long timeout_ns;
+  unsigned long long *trace; int trace_gens;   // diagnostics (ZZ_GEN_TRACE): [gen][CTA][4] globaltimer stamps {release seen, tiles start, tiles done, ticket}
   int steward;                      // 1: the last CTA of the (single) chain is the steward of the scalar stage (see k_generations)
   int dyn_tiles;                    // 0: static tile assignment (warp w: tiles w, w + W, ...); 1: static for two rounds, then from the queues
 };
@@ -107,13 +108,16 @@ __device__ __forceinline__ bool allreduce_exchange_i64(long long *vec /* shared 
 // ---- the scalar half of a generation (zz_chain.cuh) as the persistent kernel runs it ------------------------------------------
 // Scratch layout (shared memory; in the last-arriver mode it aliases the first statistic columns of the CTA, which are zero then)
 struct StageScr {
-  long long *ivec; double *st, *gam, *vg_s, *px_lu; L2Params *l2; zz_hyper *h; ChainDev *c; MoveDraws *md; FastH *F; GammaPre *gp;
+  long long *ivec; double *st, *gam, *vg_s, *px_lu; L2Params *l2; zz_hyper *h; ChainDev *c; MoveDraws *md; FastH *F; GammaPre *gp; PreVarg *pv; PreL2 *pl; PrePx *pp;
 };
 constexpr int MAX_NSTAT_P = 3 * (ZZ_MAX_COMP + 1) + 10;
 constexpr int SCR_MD = (2560 + (int)sizeof(ChainDev) + 127) / 128 * 128;
 constexpr int SCR_FH = (SCR_MD + MD_MAX * (int)sizeof(MoveDraws) + 127) / 128 * 128;
 constexpr int SCR_GP = (SCR_FH + (int)sizeof(FastH) + 127) / 128 * 128;
-constexpr int SCR_BYTES = SCR_GP + (ZZ_MAX_COMP + 3) * (int)sizeof(GammaPre);
+constexpr int SCR_PV = (SCR_GP + (ZZ_MAX_COMP + 3) * (int)sizeof(GammaPre) + 127) / 128 * 128;
+constexpr int SCR_PL = (SCR_PV + (int)sizeof(PreVarg) + 127) / 128 * 128;
+constexpr int SCR_PP = (SCR_PL + (int)sizeof(PreL2) + 127) / 128 * 128;
+constexpr int SCR_BYTES = SCR_PP + (int)sizeof(PrePx);
 static_assert(MAX_NSTAT_P * 8 <= 512 && sizeof(L2Params) <= 256 && sizeof(zz_hyper) <= 1024, "stage scratch layout");
 static_assert(SCR_BYTES <= 8 * SWEEP_BLOCK * 5, "the scratch must fit in the first statistic columns (nstat >= 13 of them)");
 static_assert(sizeof(ChainDev) % 8 == 0 && sizeof(zz_hyper) % 8 == 0 && sizeof(FastH) % 8 == 0, "copied as 64-bit words");
@@ -130,6 +134,9 @@ __device__ __forceinline__ StageScr stage_scr(char *scr) {
   S.md = reinterpret_cast<MoveDraws *>(scr + SCR_MD);          // [MD_MAX] the prepared draws of the Metropolis moves
   S.F = reinterpret_cast<FastH *>(scr + SCR_FH);               // the next generation's constants, staged (no global read-backs)
   S.gp = reinterpret_cast<GammaPre *>(scr + SCR_GP);           // [K + 3] the statistics-independent part of the gamma draws
+  S.pv = reinterpret_cast<PreVarg *>(scr + SCR_PV);            // the statistics-independent parts of the Metropolis moves
+  S.pl = reinterpret_cast<PreL2 *>(scr + SCR_PL);
+  S.pp = reinterpret_cast<PrePx *>(scr + SCR_PP);              // the next generation's mhP_x proposal
   return S;
 }
 // totals of the generation -> S.st (all-reduced over the gene shards); whole CTA.  false: a peer timed out (fail-stop)
@@ -170,12 +177,18 @@ __device__ __forceinline__ void stage_store(const StageScr &S, const GenArgs &ga
   for (int j = threadIdx.x; j < (int)(sizeof(zz_hyper) / 8); j += blockDim.x) d1[j] = s1[j];
 }
 // everything of the generation's scalar stage that needs no statistics: every random draw, one lane per draw
-__device__ __forceinline__ void stage_pre(const StageScr &S, const MathTabs &T, const SweepArgs &a, uint64_t step) {
+template <int KT>
+__device__ __forceinline__ void stage_pre(const StageScr &S, const MathTabs &T, const SweepArgs &a, uint64_t step, uint64_t next_step) {
   const int K = a.K, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const SMath sm{&T};
   if (wid == 0) stage_gibbs_predraw(sm, *S.c, a.seed, step, K, lane, S.gp);
   else if (wid == 4 && lane < MD_AMD + K) make_move_draws(sm, S.md[lane], a.seed, (uint32_t)S.c->chain, step, lane);
   else if (wid == 3 && lane == 0) *S.px_lu = px_log_u(*S.c, a.seed, step);
+  else if (wid == 5 && lane == 0) px_propose_pre(*S.c, *S.h, a.seed, next_step, a.R, *S.pp);
+  __syncthreads();
+  // proposals, Hastings and prior ratios of the Metropolis moves for every outcome of the moves before them
+  if (wid == 1 && lane == 0) stage_l2_pre<KT>(sm, *S.c, *S.h, S.md, *S.pl);
+  else if (wid == 2 && lane == 0) stage_varg_pre(sm, *S.c, *S.h, S.md, *S.pv);
 }
 // the moves themselves, from the totals in S.st: new hyper-parameters in S.h, scalar state in S.c, the next sweep's constants in
 // S.F and in global memory.  Whole CTA; the caller fences and releases the grid afterwards.
@@ -199,19 +212,19 @@ __device__ __forceinline__ void stage_post(const StageScr &S, const MathTabs &T,
     if (lane == 0) stage_gibbs_combine(h_s, K, S.gam);
   }
   // phase B (does not read what phase A writes): the chains of moves side by side (mhInactiveMeans and mhActiveMeansDif touch disjoint parameters)
-  else if (wid == 1 && lane == 0) stage_amd<KT>(sm, c_s, h_s, S.md, st, tune, l2_s.am);
-  else if (wid == 5 && lane == 0) l2_s.im = stage_im(sm, c_s, h_s, S.md, st, K, tune);
-  else if (wid == 2 && lane == 0) stage_varg(sm, c_s, h_s, S.md, st, K, tune, S.vg_s[0], S.vg_s[1], S.vg_s[2]);
+  else if (wid == 1 && lane == 0) stage_amd_post<KT>(*S.pl, c_s, h_s, S.md, st, tune, l2_s.am);
+  else if (wid == 5 && lane == 0) l2_s.im = stage_im_post(*S.pl, c_s, h_s, S.md, st, K, tune);
+  else if (wid == 2 && lane == 0) stage_varg_post(*S.pv, c_s, h_s, S.md, st, K, tune, S.vg_s[0], S.vg_s[1], S.vg_s[2]);
   else if (wid == 3 && lane == 0) {
     const int acc = px_decide(c_s, h_s, *S.px_lu, st[3 * K1 + FXS_PXDELTA], st[3 * K1 + FXS_PXBAD], tune);
     if (acc) h_s.alpha_r[c_s.px_lib] = c_s.px_alpha;               // Pr:234-239
     c_s.px_prev_acc = acc; c_s.px_valid = 0;
-    if (!last) px_propose(c_s, h_s, a.seed, step + (uint64_t)ga.step_stride, tune, R);   // the next generation's mhP_x (after a segment: k_gen_prepare)
+    if (!last) px_propose_post(*S.pp, c_s, acc, tune);             // the next generation's mhP_x (after a segment: k_gen_prepare)
   }
   __syncthreads();
   ZZ_PHASE(2);
   if (threadIdx.x == 0) {                                          // mhSharedVariance at the means just decided; install everything
-    const double av = stage_sv<KT>(sm, c_s, h_s, S.md, st, tune, l2_s.im, l2_s.am);
+    const double av = stage_sv_post<KT>(sm, *S.pl, c_s, h_s, S.md, st, tune, l2_s.im, l2_s.am);
     h_s.inactive_means = l2_s.im;
     for (int k = 0; k < K; ++k) h_s.active_means[k] = l2_s.am[k];
     if (!isnan(av)) { h_s.inactive_variances = av; for (int k = 0; k < K; ++k) h_s.active_variances[k] = av; }
@@ -223,9 +236,8 @@ __device__ __forceinline__ void stage_post(const StageScr &S, const MathTabs &T,
     for (int l = threadIdx.x; l < R + K + 6; l += blockDim.x) tune_all_scalars(c_s, ga.target, K, R, l);
   ZZ_PHASE(3);
   // the next generation's constants, one group of fields per thread
-  derive_fast_par(F_s, &h_s, threadIdx.x);
-  __syncthreads();
-  if (threadIdx.x == 0) { derive_fin(F_s, &h_s); set_px(F_s, h_s, c_s); }
+  if (threadIdx.x == DERIVE_FIN_THREAD) { derive_fin(F_s, &h_s); set_px(F_s, h_s, c_s); }
+  else derive_fast_par(F_s, &h_s, threadIdx.x);
   __syncthreads();
   {
     uint64_t *dF = reinterpret_cast<uint64_t *>(ga.fasth_rw + chain);
@@ -247,7 +259,7 @@ __device__ __noinline__ void steward_loop(const GenArgs &ga, const MathTabs &T, 
   __syncthreads();
   for (int gi = 0; gi < ga.ngen; ++gi) {
     const uint64_t step = a.step + (uint64_t)ga.step_stride * (uint64_t)gi;
-    if (ga.hyper_moves) stage_pre(S, T, a, step);
+    if (ga.hyper_moves) stage_pre<KT>(S, T, a, step, step + (uint64_t)ga.step_stride);
     if (threadIdx.x == 0) {                                          // all tickets of this generation
       const unsigned want = ((unsigned)gi + 1u) * n_workers;
       const unsigned long long t0 = globaltimer_ns();
@@ -273,6 +285,7 @@ __device__ __noinline__ void steward_loop(const GenArgs &ga, const MathTabs &T, 
     if (threadIdx.x < GEN_NREL) st_release_u32(&ctl->rel[threadIdx.x * 32], (unsigned)gi + 1u);
     if (threadIdx.x == 0) {
       const unsigned long long t1 = globaltimer_ns();
+      if (ga.trace && gi < ga.trace_gens) { unsigned long long *tr = ga.trace + ((size_t)gi * gridDim.x + blockIdx.x) * 4; tr[0] = t_lead0; tr[1] = t_stage0; tr[2] = t1; tr[3] = t1; }
       ctl->ns_leader += t1 - t_lead0; ctl->ns_stage += t1 - t_stage0;
       st_release_u32(&ctl->release, (unsigned)gi + 1u);
     }
@@ -377,6 +390,9 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
     }
     __syncthreads();
     if (sh_rel == GEN_ABORT) break;
+    const bool tracing = ga.trace && gi < ga.trace_gens && threadIdx.x == 0;
+    unsigned long long *trow = ga.trace + ((size_t)gi * gridDim.x + blockIdx.x) * 4;
+    if (tracing) trow[0] = globaltimer_ns();
     {   // FastH was written by another SM: read it through L2
       const uint64_t *src = reinterpret_cast<const uint64_t *>(fa.fasth + chain);
       uint64_t *dst = reinterpret_cast<uint64_t *>(&H);
@@ -385,18 +401,35 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
     }
     const uint64_t step = a.step + (uint64_t)ga.step_stride * (uint64_t)gi;
     const bool px_on = H.px_on != 0;
+    if (tracing) trow[1] = globaltimer_ns();
 
     // ---- 2. the sweep: tiles are taken from the END of the sorted gene order first (the all-zero genes with their extra move and
     // the weakly expressed genes with the full detection loop run while every warp is busy)
     uint32_t f_next = 0;
-    const int n_static = 2 * nwarps, n_dyn = ntiles > n_static ? ntiles - n_static : 0;
+    // two static rounds when there are at least two FULL rounds of tiles; with fewer, one: a partial second round is dealt
+    // dynamically, so the first warps to finish take it wherever they are — static, it would double the load of the first CTAs only
+    // (125 k genes, the 8-GPU shard of the 1 M workload: 3 907 tiles on 3 544 warps; the 46 CTAs that owned the 363 extra tiles
+    // finished at 19 us, everybody else at 8 us)
+    const bool two_static = !ga.dyn_tiles || ntiles >= 2 * nwarps;
+    const int n_static = two_static ? 2 * nwarps : nwarps, n_dyn = ntiles > n_static ? ntiles - n_static : 0;
     int tq = warp0 % GEN_NQ, tq_tries = 0;
     int t_ = warp0 < ntiles ? warp0 : -1;
-    int t_n = (t_ >= 0 && warp0 + nwarps < ntiles) ? warp0 + nwarps : -1;
+    int t_n = (two_static && t_ >= 0 && warp0 + nwarps < ntiles) ? warp0 + nwarps : -1;
     unsigned ticket = 0;
+    // one static round: every warp asks its home queue ONCE for a second tile, before it stages its first one (the answer arrives
+    // while those copies are in flight).  n_dyn < nwarps, so queue q (tiles j = q mod GEN_NQ) has at least as many askers (warps
+    // w = q mod GEN_NQ) as tiles: every tile is claimed, nobody needs to try a second queue
+    const bool ask_first = !two_static && t_ >= 0 && n_dyn > 0;
+    if (ask_first && lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(&ctl->tile_q[tq * 32]) : "memory");
     if (t_ >= 0) {
       const int64_t g0 = a.g_begin + (int64_t)(ntiles - 1 - t_) * 32 + lane;
       if (g0 < a.g_end) { stage_tile_ef(a, fa, chain, g0, stg, pol); f_next = a.flags[(int64_t)chain * a.G + g0]; }
+    }
+    if (ask_first) {
+      const unsigned tk = __shfl_sync(0xffffffffu, ticket, 0);
+      const int cnt = n_dyn > tq ? (n_dyn - tq + GEN_NQ - 1) / GEN_NQ : 0;
+      if (tk < (unsigned)cnt) t_n = n_static + tq + GEN_NQ * (int)tk;
+      tq_tries = GEN_NQ;                                                 // no further requests in this sweep
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     while (t_ >= 0) {
@@ -423,7 +456,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
       asm volatile("cp.async.commit_group;" ::: "memory");
       // the tile after the next one: ask the home queue now, read the answer when this tile is done
       // (inline asm: the compiler would otherwise sink the atomic down to the shuffle that reads it and expose its whole latency)
-      const bool asked = ga.dyn_tiles && t_n >= 0 && n_dyn > 0 && tq_tries < GEN_NQ;
+      const bool asked = ga.dyn_tiles && n_dyn > 0 && tq_tries < GEN_NQ;
       if (asked && lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(&ctl->tile_q[tq * 32]) : "memory");
       if (valid) {
       const double nd_d = (double)((RT > 0 ? RT : H.R) - __popcll(mask));
@@ -542,22 +575,37 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
       }   // valid
       int t_nn = -1;
       if (asked) {
-        unsigned tk = __shfl_sync(0xffffffffu, ticket, 0);
-        for (;;) {
-          const int cnt = n_dyn > tq ? (n_dyn - tq + GEN_NQ - 1) / GEN_NQ : 0;           // tiles in queue tq
-          if (tk < (unsigned)cnt) { t_nn = n_static + tq + GEN_NQ * (int)tk; break; }
-          tq = (tq + 1) % GEN_NQ;                                                        // exhausted: steal from the next queue
-          if (++tq_tries >= GEN_NQ) break;
-          if (lane == 0) ticket = atomicAdd(&ctl->tile_q[tq * 32], 1u);
-          tk = __shfl_sync(0xffffffffu, ticket, 0);
-        }
+        const unsigned tk = __shfl_sync(0xffffffffu, ticket, 0);
+        const int cnt = n_dyn > tq ? (n_dyn - tq + GEN_NQ - 1) / GEN_NQ : 0;             // tiles in queue tq
+        if (tk < (unsigned)cnt) t_nn = n_static + tq + GEN_NQ * (int)tk;
+        else { tq = (tq + 1) % GEN_NQ; ++tq_tries; }      // exhausted: the request issued with the next tile goes to the next queue
       } else if (!ga.dyn_tiles && t_n >= 0 && t_n + nwarps < ntiles) t_nn = t_n + nwarps;
       t_ = t_n; t_n = t_nn;
+      bool stage_now = false;
+      if (t_ < 0 && t_n >= 0) { t_ = t_n; t_n = -1; stage_now = true; }   // granted while nothing was queued behind the finished tile
+      // Out of tiles while other queues may still hold some: only now — with nothing in hand — go round the remaining queues and
+      // wait for the answers (trying them all as soon as the home queue ran dry cost every warp up to 16 round trips of ~0.7 us in
+      // front of its last tile: 6 % of the sweep's warp stalls, profiles/r2_summary.md)
+      if (t_ < 0 && ga.dyn_tiles && n_dyn > 0) {
+        while (tq_tries < GEN_NQ) {
+          if (lane == 0) ticket = atomicAdd(&ctl->tile_q[tq * 32], 1u);
+          const unsigned tk = __shfl_sync(0xffffffffu, ticket, 0);
+          const int cnt = n_dyn > tq ? (n_dyn - tq + GEN_NQ - 1) / GEN_NQ : 0;
+          if (tk < (unsigned)cnt) { t_ = n_static + tq + GEN_NQ * (int)tk; stage_now = true; break; }
+          tq = (tq + 1) % GEN_NQ; ++tq_tries;
+        }
+      }
+      if (stage_now) {                                      // not prefetched: stage it now
+        const int64_t g0 = a.g_begin + (int64_t)(ntiles - 1 - t_) * 32 + lane;
+        if (g0 < a.g_end) { stage_tile_ef(a, fa, chain, g0, stg, pol); f_next = a.flags[(int64_t)chain * a.G + g0]; }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 
     // ---- 3. the CTA's column sums -> the chain's accumulators (integer atomics: order-free)
     __syncthreads();
+    if (tracing) trow[2] = globaltimer_ns();
     for (int s = wid; s < nstat; s += SWEEP_BLOCK / 32) {
       long long v = 0;
 #pragma unroll
@@ -566,11 +614,11 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == 0 && v != 0) atomicAdd(reinterpret_cast<unsigned long long *>(gacc + s), (unsigned long long)v);
     }
-    __threadfence();
     __syncthreads();
     // ---- 4. ticket.  Steward mode: done, the steward CTA counts the tickets.  Otherwise the last CTA of the chain to arrive runs the
     // scalar half of the generation.
-    if (threadIdx.x == 0) sh_ticket = atomicAdd(&ctl->arrive, 1u);
+    if (threadIdx.x == 0) { __threadfence(); sh_ticket = atomicAdd(&ctl->arrive, 1u); }   // cumulative: orders the CTA's reductions (barrier above) before the ticket
+    if (tracing) trow[3] = globaltimer_ns();
     if (ga.steward) continue;
     __syncthreads();
     if (sh_ticket != (gen_no + 1u) * n_cta - 1u) continue;
@@ -584,7 +632,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
     if (ga.hyper_moves) {
       stage_load(S, ga, chain);
       __syncthreads();
-      stage_pre(S, T, a, step);
+      stage_pre<KT>(S, T, a, step, step + (uint64_t)ga.step_stride);
       __syncthreads();
       stage_post<KT>(S, T, ga, ctl, step, gi == ga.ngen - 1, chain);
       stage_store(S, ga, chain);
