@@ -197,7 +197,7 @@ __device__ __forceinline__ void stage_post(const StageScr &S, const MathTabs &T,
   const SweepArgs &a = ga.fa.s;
   const int K = a.K, R = a.R, K1 = K + 1, tune = a.tune, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const SMath sm{&T};
-  ChainDev &c_s = *S.c; zz_hyper &h_s = *S.h; FastH &F_s = *S.F; L2Params &l2_s = *S.l2;
+  ChainDev &c_s = *S.c; zz_hyper &h_s = *S.h; FastH &F_s = *S.F;
   const double *st = S.st;
   unsigned long long tp0 = globaltimer_ns(), tp1;
 #ifdef ZZ_GEN_PROFILE   /* per-phase times of the stage (each probe costs a global read-modify-write, ~0.5 us) */
@@ -211,27 +211,33 @@ __device__ __forceinline__ void stage_post(const StageScr &S, const MathTabs &T,
     __syncwarp();
     if (lane == 0) stage_gibbs_combine(h_s, K, S.gam);
   }
-  // phase B (does not read what phase A writes): the chains of moves side by side (mhInactiveMeans and mhActiveMeansDif touch disjoint parameters)
-  else if (wid == 1 && lane == 0) stage_amd_post<KT>(*S.pl, c_s, h_s, S.md, st, tune, l2_s.am);
-  else if (wid == 5 && lane == 0) l2_s.im = stage_im_post(*S.pl, c_s, h_s, S.md, st, K, tune);
-  else if (wid == 2 && lane == 0) stage_varg_post(*S.pv, c_s, h_s, S.md, st, K, tune, S.vg_s[0], S.vg_s[1], S.vg_s[2]);
+  // phase B (does not read what phase A writes): three chains of moves side by side, each on parameters of its own, each installing
+  // its results at its end — mhInactiveMeans -> mhActiveMeansDif -> mhSharedVariance (at the means the first two left) | mhTau ->
+  // mhSg -> mhS0Tau | the decision of the pending mhP_x and the proposal of the next one
+  else if (wid == 1 && lane == 0) {
+    double am[KT];
+    const double im = stage_im_post(*S.pl, c_s, h_s, S.md, st, K, tune);
+    stage_amd_post<KT>(*S.pl, c_s, h_s, S.md, st, tune, am);
+    const double av = stage_sv_post<KT>(sm, *S.pl, c_s, h_s, S.md, st, tune, im, am);
+    h_s.inactive_means = im;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) h_s.active_means[k] = am[k];
+    if (!isnan(av)) { h_s.inactive_variances = av; for (int k = 0; k < K; ++k) h_s.active_variances[k] = av; }
+  }
+  else if (wid == 2 && lane == 0) {
+    double s0, s1, tau;
+    stage_varg_post(*S.pv, c_s, h_s, S.md, st, K, tune, s0, s1, tau);
+    h_s.s0 = s0; h_s.s1 = s1; h_s.tau = tau;
+  }
   else if (wid == 3 && lane == 0) {
     const int acc = px_decide(c_s, h_s, *S.px_lu, st[3 * K1 + FXS_PXDELTA], st[3 * K1 + FXS_PXBAD], tune);
     if (acc) h_s.alpha_r[c_s.px_lib] = c_s.px_alpha;               // Pr:234-239
     c_s.px_prev_acc = acc; c_s.px_valid = 0;
     if (!last) px_propose_post(*S.pp, c_s, acc, tune);             // the next generation's mhP_x (after a segment: k_gen_prepare)
-  }
-  __syncthreads();
-  ZZ_PHASE(2);
-  if (threadIdx.x == 0) {                                          // mhSharedVariance at the means just decided; install everything
-    const double av = stage_sv_post<KT>(sm, *S.pl, c_s, h_s, S.md, st, tune, l2_s.im, l2_s.am);
-    h_s.inactive_means = l2_s.im;
-    for (int k = 0; k < K; ++k) h_s.active_means[k] = l2_s.am[k];
-    if (!isnan(av)) { h_s.inactive_variances = av; for (int k = 0; k < K; ++k) h_s.active_variances[k] = av; }
-    h_s.s0 = S.vg_s[0]; h_s.s1 = S.vg_s[1]; h_s.tau = S.vg_s[2];
     c_s.step += (uint64_t)ga.step_stride; c_s.gen += 1;
   }
   __syncthreads();
+  ZZ_PHASE(2);
   if (last && ga.do_tune_all_last)                                 // B:146 tune_all, scalar part (the per-gene part follows the launch)
     for (int l = threadIdx.x; l < R + K + 6; l += blockDim.x) tune_all_scalars(c_s, ga.target, K, R, l);
   ZZ_PHASE(3);
