@@ -44,3 +44,17 @@ def test_oracle_chain_reproduces_tutorial_prob_active():
     assert 2.2 < h.active_means[0] < 3.1 and 5.5 < h.active_means[1] < 9.5 and 0.64 < h.weight_active < 0.8
     assert all(8 < h.alpha_r[r] < 25 for r in range(4))
     assert 0.55 < pa.mean() < 0.8
+
+
+def test_committed_full_length_runs_meet_the_tutorial_within_0_03():
+    """The full-length runs (tests/golden/make_lung_long_run.py, ~4 minutes of CPU, so not repeated here; ZZ_LONG_TESTS=1 repeats one):
+    three seeds of the oracle chain at the tutorial's 5 000 + 20 000 generations, every one within 0.03 of the ten published values."""
+    import json
+    a = json.load(open(os.path.join(HERE, "golden", "lung_long_run_oracle.json")))
+    d, _, _ = lung()
+    assert np.allclose(a["tutorial_first10"], d["tutorial_prob_active_first10"])
+    assert len(a["runs"]) == 3
+    for r in a["runs"]:
+        assert np.abs(np.array(r["prob_active_first10"]) - d["tutorial_prob_active_first10"]).max() < 0.03
+        assert abs(r["max_abs_diff_vs_tutorial"] - np.abs(np.array(r["prob_active_first10"]) - d["tutorial_prob_active_first10"]).max()) < 1e-3
+        assert -10900 < r["lnl"] < -10100 and -2.4 < r["s0"] < -1.7 and 0.7 < r["tau"] < 1.05

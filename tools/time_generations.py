@@ -29,8 +29,8 @@ for tune in (True, False):
     print(f"{name}: device-resident {'burn-in' if tune else 'sampling'} generation {dt*1e6:.1f} us "
           f"({(h.launch_count-l0)/ngen:.1f} launches, {chains} chain(s)) -> {1/dt:.0f} generations/s, {G*chains/dt/1e9:.2f} G gene-updates/s inside full chains")
     tl = h.debug_gen_times() / (ngen if tune else 10) / 1e3
-    print(f"   last segment: releasing CTA {tl[0]:.1f} us per generation between its ticket and the release, {tl[1]:.1f} us of it in the scalar stage "
-          f"(load {tl[2]:.1f}, draws {tl[3]:.1f}, move chains {tl[4]:.1f}, install {tl[5]:.1f}, derive+propose {tl[6]:.1f}, write-back {tl[7]:.1f})")
+    print(f"   last segment: {tl[0]:.1f} us per generation between the last ticket and the release, {tl[1]:.1f} us of it in the scalar stage"
+          + (f" (Gibbs draws + move chains {tl[4]:.1f}, tune_all {tl[5]:.1f}, derive + publish {tl[6]:.1f}; -DZZ_GEN_PROFILE build)" if tl[4] > 0 else ""))
 h.run_sweeps(10**6, 20); h.sync()
 t0 = time.perf_counter(); h.run_sweeps(10**6 + 20, ngen); h.sync(); dt = (time.perf_counter() - t0) / ngen
 print(f"{name}: zz_run_sweeps (fixed hyper-parameters, statistics every sweep) {dt*1e6:.1f} us per sweep -> {G*chains/dt/1e9:.2f} G gene-updates/s; releasing CTA {h.debug_gen_times()[0]/ngen/1e3:.1f} us")
