@@ -169,3 +169,35 @@ def test_parameters_are_recovered_from_simulated_data(tmp_path):
     print(f"classification accuracy {acc:.4f}, Bayes rule on the true Yg {bayes_acc:.4f}")
     assert acc > bayes_acc - 0.03 and acc > 0.9
     assert mm.h.nan_flag() == 0
+
+
+def test_non_shared_variance_model_recovers_its_priors(tmp_path):
+    """shared_variance = FALSE, shared_active_variance = FALSE (R/zigzagProposals.R:473-509 mhInactiveVariances, 707-766 mhActiveVariances;
+    slot weights I:228-237), host-driven fused schedule.  Same recipe as above: beta = 0, one gene without detections — the three
+    variances must reproduce their three independent log10-uniform priors."""
+    mm = zigzag(np.zeros((1, 2)), None, num_active_components=2, threshold_i=0.0, threshold_a=(0.0, 5.0), beta=0, seed=14, shared_variance=False,
+                shared_active_variance=False, inactive_variances_prior_min=0.1, inactive_variances_prior_max=10.0, active_variances_prior_min=0.01,
+                active_variances_prior_max=2.0, output_directory=str(tmp_path), write_settings=True)
+    assert mm.proposal_list[4] == mm.mhInactiveVariances and mm.proposal_list[6] == mm.mhActiveVariances
+    assert mm.proposal_probs[4] == 7 and mm.proposal_probs[6] == 7 and len(set(mm.active_variances)) == 2
+    rows = dict(l.rstrip("\n").split("\t") for l in open(tmp_path / "hyperparameter_settings.txt"))
+    assert rows["inactive_variances_prior_max"] == "10" and rows["active_variances_prior_min"] == "0.01" and "shared_variance_prior_min" not in rows
+    with pytest.raises(NotImplementedError):
+        mm.burnin(ngen=10, write_to_files=False, schedule="device")
+    mm.burnin(sample_frequency=100, ngen=1200, write_to_files=False, schedule="fused")
+    assert mm.inactive_variance_tuningParam != 0.5                       # tune_all reached the new parameters
+    x = []
+    for i in range(12000):
+        mm._generation(False, "fused")
+        if i % 4 == 0:
+            x.append([math.log10(mm.inactive_variances), math.log10(mm.active_variances[0]), math.log10(mm.active_variances[1])])
+    x = np.array(x)
+    for j, (lo, hi) in enumerate([(-1.0, 1.0), (-2.0, math.log10(2.0)), (-2.0, math.log10(2.0))]):
+        mu, sd = (lo + hi) / 2, (hi - lo) / math.sqrt(12)
+        ess = max(_ess(x[:, j]), 20.0)
+        assert abs(x[:, j].mean() - mu) < 4.5 * sd / math.sqrt(ess), (j, x[:, j].mean(), mu, ess)
+        assert 0.8 < x[:, j].std() / sd < 1.2 and x[:, j].min() >= lo and x[:, j].max() <= hi
+    assert abs(np.corrcoef(x[:, 1], x[:, 2])[0, 1]) < 0.15              # the two active variances move independently
+    # the reference schedule draws the two moves with their weights
+    mm.burnin(sample_frequency=100, ngen=200, write_to_files=False, schedule="reference")
+    assert mm.h.nan_flag() == 0

@@ -70,12 +70,13 @@ class zigzag:
                  weight_active_shape_1=2, weight_active_shape_2=2, shared_variance_prior_min=0.01, shared_variance_prior_max=5,
                  inactive_means_prior_shape=1, inactive_means_prior_rate=1 / 3, spike_prior_shape_1=1, spike_prior_shape_2=1,
                  active_means_dif_prior_shape=1, active_means_dif_prior_rate=1 / 3, shared_active_variance=True,
-                 shared_variance=True, output_directory="output", threshold_a=None, threshold_i=None, beta=1, temperature=1,
+                 shared_variance=True, inactive_variances_prior_min=None, inactive_variances_prior_max=None,
+                 active_variances_prior_min=None, active_variances_prior_max=None, output_directory="output", threshold_a=None, threshold_i=None, beta=1, temperature=1,
                  tau_shape=1, tau_rate=1, s0_mu=-1, s0_sigma=2, s1_shape=1, s1_rate=2, variance_g_upper_bound=math.inf,
                  alpha_r_shape=1, alpha_r_rate=1 / 10, active_gene_set=None, gene_names=None, seed=0, device=0,
                  shard=None, process_group=None, write_settings=True, init="host"):
-        if not shared_variance or not shared_active_variance:
-            raise NotImplementedError("only the reference's default shared_variance=TRUE model is wired up")
+        self.shared_variance = bool(shared_variance)
+        self.shared_active_variance = True if shared_variance else bool(shared_active_variance)                # I:43-45
         if threshold_a is None or threshold_i is None or isinstance(num_active_components, str):
             raise NotImplementedError('threshold_a / threshold_i / num_active_components = "auto" rely on R\'s density() and loess() '
                                       "(R/zigzagPriorThresholdUtils.R, out of scope): pass them explicitly")
@@ -114,23 +115,34 @@ class zigzag:
                         tau_shape=tau_shape, tau_rate=tau_rate, s0_mu=s0_mu, s0_sigma=s0_sigma, s1_shape=s1_shape, s1_rate=s1_rate,
                         alpha_r_shape=alpha_r_shape, alpha_r_rate=alpha_r_rate,
                         shared_variance_prior_min=shared_variance_prior_min, shared_variance_prior_max=shared_variance_prior_max)
+        # separate bounds of the two variance priors when the variance is not shared (I:296-349); shared: both are the shared bounds
+        _b = lambda v, d: d if (v is None or self.shared_variance) else v
+        self.pri.update(inactive_variances_prior_min=_b(inactive_variances_prior_min, shared_variance_prior_min),
+                        inactive_variances_prior_max=_b(inactive_variances_prior_max, shared_variance_prior_max),
+                        active_variances_prior_min=_b(active_variances_prior_min, shared_variance_prior_min),
+                        active_variances_prior_max=_b(active_variances_prior_max, shared_variance_prior_max))
+        self.pri.update(ivar_log_min=math.log10(self.pri["inactive_variances_prior_min"]), ivar_log_max=math.log10(self.pri["inactive_variances_prior_max"]),
+                        avar_log_min=math.log10(self.pri["active_variances_prior_min"]), avar_log_max=math.log10(self.pri["active_variances_prior_max"]))
         self.weight_within_active_alpha = np.full(K, weight_active_shape_1 / K)                                # I:358
         # ---- tuning parameters (I:185-199) and their windows
         self.inactive_mean_tuningParam = 0.5
+        self.inactive_variance_tuningParam = 0.5
         self.active_mean_tuningParam = np.full(K, 0.5)
         self.active_variance_tuningParam = np.full(K, 0.5)
         self.tuningParam_s0 = self.tuningParam_s1 = self.tuningParam_tau = self.tuningParam_s0tau = 0.05
         self.tuningParam_alpha_r = np.full(self.num_libraries, 0.5)
-        self._win = dict(im=_Window(), av=_Window(), s0=_Window(), s1=_Window(), tau=_Window(), s0tau=_Window(),
+        self._win = dict(im=_Window(), iv=_Window(), avk=[_Window() for _ in range(K)], av=_Window(), s0=_Window(), s1=_Window(), tau=_Window(), s0tau=_Window(),
                          am=[_Window() for _ in range(K)], alpha=[_Window() for _ in range(self.num_libraries)])
         # ---- proposal table (I:207-237)
         R = self.num_libraries
         self.proposal_list = [self.gibbsMixtureWeights, self.gibbsAllocationActiveInactive, self.gibbsAllocationWithinActive,
-                              self.mhInactiveMeans, self.mhInactiveVariances, self.mhActiveMeansDif, self.mhSharedVariance,
+                              self.mhInactiveMeans, self.mhInactiveVariances, self.mhActiveMeansDif,
+                              self.mhSharedVariance if self.shared_variance else self.mhActiveVariances,                # I:223
                               self.gibbsSpikeProb, self.mhSpikeAllocation, self.mhYg, self.mhVariance_g, self.mhTau, self.mhSg,
                               self.mhS0Tau, self.mhP_x]
         yw = 1 + (R == 2) * 0.5 + 1 * (G < 15000)
-        self.proposal_probs = np.array([4, 30, 5, 6, 7 * 0, 5, 5, 2, 5, yw, yw, 8, 10, 8, R * 1.1], dtype=np.float64)
+        self.proposal_probs = np.array([4, 30, 5, 6, 7 * (1 - self.shared_variance), 5, 5 + 2 * (1 - self.shared_active_variance), 2, 5, yw, yw,
+                                        8, 10, 8, R * 1.1], dtype=np.float64)                                          # I:228-237
         # ---- initial hyper-parameters: the same draws on every rank (I:263-408)
         self.rng = np.random.Generator(np.random.PCG64(seed))
         r = self.rng
@@ -138,10 +150,14 @@ class zigzag:
         self.spike_probability = r.beta(spike_prior_shape_1, spike_prior_shape_2)
         self.active_means_dif = r.gamma(active_means_dif_prior_rate, 1 / active_means_dif_prior_rate, K)       # I:282 (shape = rate, sic)
         self.active_means = self.calculate_active_means(self.active_means_dif)
-        av = 10 ** r.uniform(self.pri["var_log_min"], self.pri["var_log_max"])
+        av = 10 ** r.uniform(self.pri["avar_log_min"], self.pri["avar_log_max"])                               # I:296-323
         self.active_variances = np.full(K, av)
         self.inactive_means = self.threshold_i - r.gamma(1, 1)
         self.inactive_variances = av
+        if not self.shared_variance:
+            if not self.shared_active_variance:
+                self.active_variances = 10 ** r.uniform(self.pri["avar_log_min"], self.pri["avar_log_max"], K)
+            self.inactive_variances = 10 ** r.uniform(self.pri["ivar_log_min"], self.pri["ivar_log_max"])      # I:343-349
         self.weight_within_active = r.dirichlet(self.weight_within_active_alpha)
         self.alpha_r = r.gamma(1, 1, R)
         self.s0 = r.normal(0, 0.1)
@@ -278,6 +294,9 @@ class zigzag:
         allocation trace on the device; the host reads the scalar state back once per segment."""
         if self.world != 1 and not self._p2p:
             raise NotImplementedError('schedule="device" on gene shards needs the peer-memory all-reduce (one node, NCCL process group)')
+        if not self.shared_variance:
+            raise NotImplementedError('schedule="device" runs the default shared-variance model (its scalar stage holds mhSharedVariance); '
+                                      'use schedule="fused" or "reference" with shared_variance=False')
         self.h.chain_begin(self._priors_struct(), self._chain_scalars())
         self.h.run_generations(ngen, tune=tune, sample_frequency=sample_frequency, target=target)
         self._adopt_chain(*self.h.chain_read())
@@ -380,8 +399,43 @@ class zigzag:
                 self._win["im"].accept()
             self._push_hyper()
 
-    def mhInactiveVariances(self, tune=False, st=None):                                  # Pr:473-509: weight 7*(1-shared_variance) = 0
-        return
+    def mhInactiveVariances(self, tune=False, st=None):                                  # Pr:473-509 (weight 7 * (1 - shared_variance))
+        if self.shared_variance:
+            return                                                                       # weight 0 in the default model
+        lo, hi = self.pri["ivar_log_min"], self.pri["ivar_log_max"]
+        ivp = 10 ** self._two_boundary_slide_move(math.log10(self.inactive_variances), lo, hi, self.inactive_variance_tuningParam)
+        if tune:
+            self._win["iv"].push0()
+        pp, pc = _dunif_log(math.log10(ivp), lo, hi), _dunif_log(math.log10(self.inactive_variances), lo, hi)
+        Lp = self._level2_sums(self.inactive_means, ivp, self.active_means, self.active_variances, st)[0]
+        Lc = self._level2_sums(self.inactive_means, self.inactive_variances, self.active_means, self.active_variances, st)[0]
+        if self._accept(self.temperature * (Lp - Lc + pp - pc)):
+            self.inactive_variances = ivp
+            if tune:
+                self._win["iv"].accept()
+            self._push_hyper()
+
+    def mhActiveVariances(self, tune=False, st=None):                                    # Pr:707-766
+        K = self.num_active_components
+        lo, hi = self.pri["avar_log_min"], self.pri["avar_log_max"]
+        k = int(self.rng.integers(0, K))
+        avp = np.array(self.active_variances, dtype=np.float64)
+        if self.shared_active_variance:
+            avp[:] = 10 ** self._two_boundary_slide_move(math.log10(self.active_variances[0]), lo, hi, self.active_variance_tuningParam[0])
+            win = self._win["av"]
+        else:
+            avp[k] = 10 ** self._two_boundary_slide_move(math.log10(self.active_variances[k]), lo, hi, self.active_variance_tuningParam[k])
+            win = self._win["avk"][k]
+        if tune:
+            win.push0()
+        Lp = self._level2_sums(self.inactive_means, self.inactive_variances, self.active_means, avp, st)[1]
+        Lc = self._level2_sums(self.inactive_means, self.inactive_variances, self.active_means, self.active_variances, st)[1]
+        pp, pc = _dunif_log(math.log10(avp[k]), lo, hi), _dunif_log(math.log10(self.active_variances[k]), lo, hi)
+        if self._accept(self.temperature * (Lp + pp - Lc - pc)):
+            self.active_variances = avp
+            if tune:
+                win.accept()
+            self._push_hyper()
 
     def mhActiveMeansDif(self, tune=False, st=None):                                     # Pr:640-705
         K = self.num_active_components
@@ -538,8 +592,14 @@ class zigzag:
         self.inactive_mean_tuningParam = x_tune(w["im"].sum(), self.inactive_mean_tuningParam, target, 0.001, 10)
         self.active_mean_tuningParam = np.array([x_tune(w["am"][k].sum(), self.active_mean_tuningParam[k], target, 0.01, 10)
                                                  for k in range(self.num_active_components)])
-        span = self.pri["var_log_max"] - self.pri["var_log_min"]
-        self.active_variance_tuningParam = np.full(self.num_active_components, x_tune(w["av"].sum(), self.active_variance_tuningParam[0], target, 0.01, span))
+        self.inactive_variance_tuningParam = x_tune(w["iv"].sum(), self.inactive_variance_tuningParam, target, 0.01,
+                                                    self.pri["ivar_log_max"] - self.pri["ivar_log_min"])          # U:215-217
+        span = self.pri["avar_log_max"] - self.pri["avar_log_min"]
+        if self.shared_active_variance:                                                                        # U:224-237
+            self.active_variance_tuningParam = np.full(self.num_active_components, x_tune(w["av"].sum(), self.active_variance_tuningParam[0], target, 0.01, span))
+        else:
+            self.active_variance_tuningParam = np.array([x_tune(w["avk"][k].sum(), self.active_variance_tuningParam[k], target, 0.01, span)
+                                                         for k in range(self.num_active_components)])
 
     def calculate_lnl(self):                                                             # U:70-75
         return float(self._allreduce([self.h.lnl()])[0])
@@ -556,7 +616,8 @@ class zigzag:
         else:
             self.h.sweep(self._next_step(), tune=tune)
             st = self._stats()
-            for mv in (self.gibbsMixtureWeights, self.mhInactiveMeans, self.mhActiveMeansDif, self.mhSharedVariance, self.gibbsSpikeProb,
+            var_moves = (self.mhSharedVariance,) if self.shared_variance else (self.mhInactiveVariances, self.mhActiveVariances)
+            for mv in (self.gibbsMixtureWeights, self.mhInactiveMeans, self.mhActiveMeansDif, *var_moves, self.gibbsSpikeProb,
                        self.mhTau, self.mhSg, self.mhS0Tau):
                 mv(tune=tune, st=st)
             self.mhP_x(tune=tune)
@@ -865,6 +926,11 @@ class zigzag:
                 ("inactive_means_prior_rate", round(p["inactive_means_prior_rate"], 3)), ("shared_variance_prior_min", p["shared_variance_prior_min"]),
                 ("shared_variance_prior_max", p["shared_variance_prior_max"]), ("threshold_i", round(self.threshold_i, 2)),
                 ("threshold_a", ", ".join(_rnum(round(t, 2)) for t in self.threshold_a))]
+        if not self.shared_variance:                                                     # I:522-536: the bounds of the two variance priors instead
+            i_act = [k for k, _ in rows].index("active_meaans_dif_prior_rate") + 1
+            rows[i_act:i_act] = [("active_variances_prior_min", p["active_variances_prior_min"]), ("active_variances_prior_max", p["active_variances_prior_max"])]
+            i_sh = [k for k, _ in rows].index("shared_variance_prior_min")
+            rows[i_sh:i_sh + 2] = [("inactive_variances_prior_min", p["inactive_variances_prior_min"]), ("inactive_variances_prior_max", p["inactive_variances_prior_max"])]
         with open(os.path.join(self.output_directory, "hyperparameter_settings.txt"), "w") as f:
             for k, v in rows:
                 f.write(f"{k}\t{v if isinstance(v, str) else _rnum(v)}\n")
