@@ -284,6 +284,13 @@ zigzagGPU <- setRefClass(
     .self$gpu_dirty <- TRUE                          # the per-gene tuning parameters the super call derived from stale traces are replaced at the next pull
   },
 
+  # re-draws the per-gene state on the device by the constructor's recipe (R/zigzagInitialize.R:416-504) from the current hyper-parameters
+  gpu_init_state = function(){
+    rv <- matrixStats::rowVars(Xg); rv <- rv[is.finite(rv)]
+    .Call("zzR_init_state", gpu, 0, c(log(mean(rv)), sqrt(var(rv))))
+    .self$gpu_dirty <- TRUE; .self$gpu_pull()
+  },
+
   # posterior-predictive discrepancies of one simulated data set, computed on the device (R/zigzagPostPredictiveSimulation.R:3-156)
   gpu_post_predictive = function(bins){
     out <- .Call("zzR_post_predictive", gpu, gpu_next(), as.numeric(bins), as.integer(num_libraries))

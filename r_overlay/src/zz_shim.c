@@ -235,6 +235,16 @@ SEXP zzR_run_sweeps(SEXP ptr, SEXP step, SEXP nsweeps, SEXP tune) {
 }
 
 /* ---- the remaining entry points of include/zigzag_gpu.h ------------------------------------------------------------------ */
+/* constructor-side initial state on the device (R/zigzagInitialize.R:416-504): rowvar = c(log(mean(v)), sd(v)) of the row variances of
+   the fully detected genes; the fields come back with gpu_pull() */
+SEXP zzR_init_state(SEXP ptr, SEXP step, SEXP rowvar) {
+  zz_handle *h = H(ptr);
+  chk(h, zz_init_state(h, (uint64_t)Rf_asReal(step), REAL(rowvar)[0], REAL(rowvar)[1]));
+  return R_NilValue;
+}
+/* chain-axis bookkeeping of tempered chains (handles created with more than one chain; 0-based chain slots) */
+SEXP zzR_accumulate_alloc_trace_from(SEXP ptr, SEXP src, SEXP dst) { zz_handle *h = H(ptr); chk(h, zz_accumulate_alloc_trace_from(h, Rf_asInteger(src), Rf_asInteger(dst))); return R_NilValue; }
+SEXP zzR_copy_chain_tuning(SEXP ptr, SEXP src, SEXP dst) { zz_handle *h = H(ptr); chk(h, zz_copy_chain_tuning(h, Rf_asInteger(src), Rf_asInteger(dst))); return R_NilValue; }
 SEXP zzR_sync(SEXP ptr) { zz_handle *h = H(ptr); chk(h, zz_sync(h)); return R_NilValue; }
 SEXP zzR_launch_count(SEXP ptr) { return Rf_ScalarReal((double)zz_launch_count(H(ptr))); }
 SEXP zzR_refresh_caches(SEXP ptr) { zz_handle *h = H(ptr); chk(h, zz_refresh_caches(h)); return R_NilValue; }
@@ -379,6 +389,8 @@ static const R_CallMethodDef calls[] = {
   {"zzR_lnl", (DL_FUNC)&zzR_lnl, 1}, {"zzR_tune", (DL_FUNC)&zzR_tune, 2}, {"zzR_nan_flag", (DL_FUNC)&zzR_nan_flag, 1},
   {"zzR_accumulate_alloc_trace", (DL_FUNC)&zzR_accumulate_alloc_trace, 1}, {"zzR_reset_alloc_trace", (DL_FUNC)&zzR_reset_alloc_trace, 1},
   {"zzR_get_alloc_trace", (DL_FUNC)&zzR_get_alloc_trace, 3},
+  {"zzR_init_state", (DL_FUNC)&zzR_init_state, 3}, {"zzR_accumulate_alloc_trace_from", (DL_FUNC)&zzR_accumulate_alloc_trace_from, 3},
+  {"zzR_copy_chain_tuning", (DL_FUNC)&zzR_copy_chain_tuning, 3},
   {"zzR_sync", (DL_FUNC)&zzR_sync, 1}, {"zzR_launch_count", (DL_FUNC)&zzR_launch_count, 1}, {"zzR_refresh_caches", (DL_FUNC)&zzR_refresh_caches, 1},
   {"zzR_reset_windows", (DL_FUNC)&zzR_reset_windows, 1}, {"zzR_window_sums", (DL_FUNC)&zzR_window_sums, 2}, {"zzR_get_hyper", (DL_FUNC)&zzR_get_hyper, 1},
   {"zzR_eval", (DL_FUNC)&zzR_eval, 3}, {"zzR_philox_draws", (DL_FUNC)&zzR_philox_draws, 5}, {"zzR_sweep_host", (DL_FUNC)&zzR_sweep_host, 12},
