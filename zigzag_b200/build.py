@@ -29,11 +29,22 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+DBG_OUT = os.path.join(HERE, "libzigzag_gpu_dbg.so")   # the same sources with -DZZ_BOUNDS_CHECK (device-side index asserts), tests only
+
+
+def build_debug(force=False):
+    """The bounds-checked build the GPU suite runs once (tests/test_gpu_debug_build.py)."""
+    if not force and os.path.exists(DBG_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(DBG_OUT) for d in DEPS):
+        return DBG_OUT
+    return build(force=True, out=DBG_OUT, extra=["-DZZ_BOUNDS_CHECK"])
+
+
+def build(force=False, verbose=False, out=None, extra=None):
+    out = out or OUT
+    if out == OUT and not force and not needs_build():
         return OUT
-    extra = os.environ.get("ZZ_NVCC_EXTRA", "").split()     # e.g. -DZZ_ILP=4 for kernel-tuning experiments
-    cmd = [nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
+    extra = (extra or []) + os.environ.get("ZZ_NVCC_EXTRA", "").split()     # e.g. -DZZ_ILP=4 for kernel-tuning experiments
+    cmd = [nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SRC
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)  # the image's $CC points at a gcc without the host libs nvcc needs
     r = subprocess.run(cmd, capture_output=True, text=True, env=env)
@@ -41,7 +52,7 @@ def build(force=False, verbose=False):
         sys.stderr.write(r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -29,6 +29,15 @@ constexpr int BLOCK = 256;
 #ifndef ZZ_SWEEP_BLOCK
 #define ZZ_SWEEP_BLOCK 256
 #endif
+// -DZZ_BOUNDS_CHECK (zigzag_b200/libzigzag_gpu_dbg.so, tests/test_gpu_debug_build.py): every index that is READ from memory before it
+// addresses memory — the gene permutation, its inverse, slot lists, candidate slots, tile tickets, component numbers — is checked on
+// the device; a violation prints its location and traps the kernel, which the next API call reports (compute-sanitizer is closed on
+// the GPU pool this was developed on).
+#ifdef ZZ_BOUNDS_CHECK
+#define ZZ_DEV_ASSERT(cond) do { if (!(cond)) { printf("zigzag_gpu: device assert '%s' failed at %s:%d\n", #cond, __FILE__, __LINE__); __trap(); } } while (0)
+#else
+#define ZZ_DEV_ASSERT(cond) ((void)0)
+#endif
 constexpr int SWEEP_BLOCK = ZZ_SWEEP_BLOCK;   // threads per CTA of the persistent sweep kernel
 constexpr int RED_BLOCKS = 148 * 4;  // persistent-style reduction grid: 4 CTAs per SM
 
@@ -534,6 +543,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_sweep_fast(const
     if (g >= a.g_end) continue;
     const int64_t pos = g;
     if (fa.slot_list) g = fa.slot_list[g];            // a chunk of genes in the caller's order: scattered slots
+    ZZ_DEV_ASSERT(g >= 0 && g < a.G);
     const int64_t i = (int64_t)chain * a.G + g;
     if (fa.host_io) {
       // The gene's state comes straight from the caller's (pinned, device-mapped) arrays: PCIe reads issued by this warp while
@@ -710,6 +720,7 @@ __global__ void __launch_bounds__(BLOCK) k_host_in(const FastArgs fa, const Host
   const int64_t j = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (j >= hc.n) return;
   const int64_t c = hc.c0 + j, i = hc.inv[c];
+  ZZ_DEV_ASSERT(i >= 0 && i < a.G);
   const double y = hc.sYg[c];
   a.Yg[i] = y; a.vg[i] = hc.svg[c]; hc.ty[i] = hc.sty[c]; hc.tv[i] = hc.stv[c];
   uint32_t f = a.flags[i];
@@ -728,6 +739,7 @@ __global__ void __launch_bounds__(BLOCK) k_host_out(const SweepArgs a, const Hos
   const int64_t j = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (j >= hc.n) return;
   const int64_t c = hc.c0 + j, i = hc.inv[c];
+  ZZ_DEV_ASSERT(i >= 0 && i < a.G);
   hc.dYg[c] = a.Yg[i]; hc.dvg[c] = a.vg[i]; hc.dxl[c] = a.xglik[i]; hc.dvp[c] = a.vgprob[i];
   const uint32_t f = a.flags[i];
   hc.dai[c] = (f & F_ACTIVE) ? 1 : 0; hc.dw[c] = flag_k(f); hc.ds[c] = (f & F_INSPIKE) ? 1 : 0;
@@ -954,6 +966,7 @@ __global__ void __launch_bounds__(BLOCK) k_sample_row(double gen, const zz_hyper
   if (!ygrow) return;
   for (int64_t c = (int64_t)blockIdx.x * BLOCK + threadIdx.x; c < n_cand; c += (int64_t)gridDim.x * BLOCK) {
     const int64_t i = cand_slots[c];
+    ZZ_DEV_ASSERT(i >= 0);
     const bool sp = flags[i] & F_INSPIKE;
     ygrow[1 + c] = sp ? -10.0 : Yg[i];                  // FileWriting:93: Yg * (1 - spike) + (-10) * spike
     vgrow[1 + c] = sp ? 0.0 : vg[i];                    // FileWriting:100
@@ -1051,6 +1064,7 @@ __global__ void __launch_bounds__(BLOCK) k_alloc_trace(int64_t G, int K, const u
   if (g >= G) return;
   const uint32_t f = flags[(int64_t)chain * G + g];
   const int comp = (f & F_ACTIVE) ? flag_k(f) : 0;
+  ZZ_DEV_ASSERT(comp >= 0 && comp <= K);
   trace[((int64_t)chain * (K + 1) + comp) * G + g] += 1u;
 }
 
@@ -1139,12 +1153,12 @@ __global__ void __launch_bounds__(BLOCK) k_window_sums(int64_t n, const ulonglon
 template <class T>
 __global__ void __launch_bounds__(BLOCK) k_gather(int64_t n, const int32_t *__restrict__ perm, const T *__restrict__ src, T *__restrict__ dst) {
   const int64_t j = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (j < n) dst[(int64_t)blockIdx.y * n + j] = src[(int64_t)blockIdx.y * n + perm[j]];
+  if (j < n) { ZZ_DEV_ASSERT(perm[j] >= 0 && perm[j] < n); dst[(int64_t)blockIdx.y * n + j] = src[(int64_t)blockIdx.y * n + perm[j]]; }
 }
 template <class T>
 __global__ void __launch_bounds__(BLOCK) k_scatter(int64_t n, const int32_t *__restrict__ perm, const T *__restrict__ src, T *__restrict__ dst) {
   const int64_t j = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (j < n) dst[(int64_t)blockIdx.y * n + perm[j]] = src[(int64_t)blockIdx.y * n + j];
+  if (j < n) { ZZ_DEV_ASSERT(perm[j] >= 0 && perm[j] < n); dst[(int64_t)blockIdx.y * n + perm[j]] = src[(int64_t)blockIdx.y * n + j]; }
 }
 
 // int32 R-style allocation vectors (caller order) <-> packed flag word (device order)
@@ -1153,6 +1167,7 @@ __global__ void __launch_bounds__(BLOCK) k_pack_flags(int64_t n, const int32_t *
   const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (i >= n) return;
   const int32_t o = perm[i];
+  ZZ_DEV_ASSERT(o >= 0 && o < n);
   uint32_t f = flags[i];
   if (ai) f = (f & ~F_ACTIVE) | (ai[o] ? F_ACTIVE : 0u);
   if (within) f = flag_set_k(f, within[o] < 1 ? 1 : within[o]);
@@ -1164,6 +1179,7 @@ __global__ void __launch_bounds__(BLOCK) k_unpack_flags(int64_t n, const int32_t
   const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (i >= n) return;
   const int32_t o = perm[i];
+  ZZ_DEV_ASSERT(o >= 0 && o < n);
   const uint32_t f = flags[i];
   if (ai) ai[o] = (f & F_ACTIVE) ? 1 : 0;
   if (within) within[o] = flag_k(f);

@@ -441,6 +441,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
     while (t_ >= 0) {
       const int64_t g = a.g_begin + (int64_t)(ntiles - 1 - t_) * 32 + lane;
       const int64_t i = (int64_t)chain * a.G + g;
+      ZZ_DEV_ASSERT(t_ < ntiles && (t_n < 0 || (t_n < ntiles && t_n != t_)) && g >= a.g_begin);
       asm volatile("cp.async.wait_group 0;" ::: "memory");            // this lane's copies of the current tile have landed
       const bool valid = g < a.g_end;                                  // only the last (first processed) tile can be ragged
       const double y0 = stg[0 * 32], v0 = stg[1 * 32], ty = stg[3 * 32], tv = stg[4 * 32], gl = stg[5 * 32];
@@ -565,6 +566,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
         long long *col = acc + threadIdx.x;
         const bool act = f & F_ACTIVE, sp = f & F_INSPIKE;
         const int comp = act ? flag_k(f) : 0;                               // Pr:415 all_allocations
+        ZZ_DEV_ASSERT(comp >= 0 && comp <= a.K && kn >= 1 && kn <= KT && gid - (uint64_t)a.gene_offset < (uint64_t)a.G);
         const long long fy = to_fx(ys), fy2 = to_fx(ys * ys);
         col[comp * SWEEP_BLOCK] += FX_ONE;
         if (act || !sp) { col[(K1 + comp) * SWEEP_BLOCK] += fy; col[(2 * K1 + comp) * SWEEP_BLOCK] += fy2; }
