@@ -352,7 +352,7 @@ template <int RT, int KT>
 __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(const __grid_constant__ GenArgs ga) {
   __shared__ FastH H;
   __shared__ MathTabs T;
-  __shared__ unsigned sh_rel, sh_ticket;
+  __shared__ unsigned sh_rel, sh_ticket, sh_qdone;
   extern __shared__ double dyn_smem[];                 // [nstat][BLOCK] int64 statistic columns, then [8 warps][10][32] staging
   const FastArgs &fa = ga.fa;
   const SweepArgs &a = fa.s;
@@ -392,13 +392,17 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
           if (ns < 256) ns += ns;                                       // back off: the scalar stage lasts microseconds
         }
       }
-      sh_rel = r;
+      sh_rel = r; sh_qdone = 0;
     }
     __syncthreads();
     if (sh_rel == GEN_ABORT) break;
-    const bool tracing = ga.trace && gi < ga.trace_gens && threadIdx.x == 0;
-    unsigned long long *trow = ga.trace + ((size_t)gi * gridDim.x + blockIdx.x) * 4;
-    if (tracing) trow[0] = globaltimer_ns();
+    // per-CTA timeline (tools/gen_trace.py); compiled in only with -DZZ_GEN_TRACE_BUILD: two more live values in the tile loop cost spills
+#ifdef ZZ_GEN_TRACE_BUILD
+#define ZZ_TRACE(slot) do { if (ga.trace && threadIdx.x == 0 && gi < ga.trace_gens) ga.trace[((size_t)gi * gridDim.x + blockIdx.x) * 4 + (slot)] = globaltimer_ns(); } while (0)
+#else
+#define ZZ_TRACE(slot) ((void)0)
+#endif
+    ZZ_TRACE(0);
     {   // FastH was written by another SM: read it through L2
       const uint64_t *src = reinterpret_cast<const uint64_t *>(fa.fasth + chain);
       uint64_t *dst = reinterpret_cast<uint64_t *>(&H);
@@ -407,7 +411,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
     }
     const uint64_t step = a.step + (uint64_t)ga.step_stride * (uint64_t)gi;
     const bool px_on = H.px_on != 0;
-    if (tracing) trow[1] = globaltimer_ns();
+    ZZ_TRACE(1);
 
     // ---- 2. the sweep: tiles are taken from the END of the sorted gene order first (the all-zero genes with their extra move and
     // the weakly expressed genes with the full detection loop run while every warp is busy)
@@ -463,7 +467,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
       asm volatile("cp.async.commit_group;" ::: "memory");
       // the tile after the next one: ask the home queue now, read the answer when this tile is done
       // (inline asm: the compiler would otherwise sink the atomic down to the shuffle that reads it and expose its whole latency)
-      const bool asked = ga.dyn_tiles && n_dyn > 0 && tq_tries < GEN_NQ;
+      const bool asked = ga.dyn_tiles && t_n >= 0 && n_dyn > 0 && tq_tries < GEN_NQ;
       if (asked && lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(&ctl->tile_q[tq * 32]) : "memory");
       if (valid) {
       const double nd_d = (double)((RT > 0 ? RT : H.R) - __popcll(mask));
@@ -583,37 +587,28 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
       }   // valid
       int t_nn = -1;
       if (asked) {
-        const unsigned tk = __shfl_sync(0xffffffffu, ticket, 0);
-        const int cnt = n_dyn > tq ? (n_dyn - tq + GEN_NQ - 1) / GEN_NQ : 0;             // tiles in queue tq
-        if (tk < (unsigned)cnt) t_nn = n_static + tq + GEN_NQ * (int)tk;
-        else { tq = (tq + 1) % GEN_NQ; ++tq_tries; }      // exhausted: the request issued with the next tile goes to the next queue
+        // The ticket asked for when this tile began.  Home queue exhausted: go round the others NOW, so that the next tile is known
+        // before the one in hand starts and its loads hide behind it (deferring the search until the warp is out of tiles exposed
+        // every later tile's load latency: +2.5 us per sweep, measured).  Queues found empty are remembered per CTA (sh_qdone), so at
+        // the end of a sweep a CTA pays at most GEN_NQ failed round trips in all, not GEN_NQ per warp.
+        unsigned tk = __shfl_sync(0xffffffffu, ticket, 0);
+        for (;;) {
+          const int cnt = n_dyn > tq ? (n_dyn - tq + GEN_NQ - 1) / GEN_NQ : 0;           // tiles in queue tq
+          if (tk < (unsigned)cnt) { t_nn = n_static + tq + GEN_NQ * (int)tk; break; }
+          if (lane == 0) atomicOr(&sh_qdone, 1u << tq);
+          do { tq = (tq + 1) % GEN_NQ; ++tq_tries; } while (tq_tries < GEN_NQ && ((*(volatile unsigned *)&sh_qdone >> tq) & 1u));
+          if (tq_tries >= GEN_NQ) break;
+          if (lane == 0) ticket = atomicAdd(&ctl->tile_q[tq * 32], 1u);
+          tk = __shfl_sync(0xffffffffu, ticket, 0);
+        }
       } else if (!ga.dyn_tiles && t_n >= 0 && t_n + nwarps < ntiles) t_nn = t_n + nwarps;
       t_ = t_n; t_n = t_nn;
-      bool stage_now = false;
-      if (t_ < 0 && t_n >= 0) { t_ = t_n; t_n = -1; stage_now = true; }   // granted while nothing was queued behind the finished tile
-      // Out of tiles while other queues may still hold some: only now — with nothing in hand — go round the remaining queues and
-      // wait for the answers (trying them all as soon as the home queue ran dry cost every warp up to 16 round trips of ~0.7 us in
-      // front of its last tile: 6 % of the sweep's warp stalls, profiles/r2_summary.md)
-      if (t_ < 0 && ga.dyn_tiles && n_dyn > 0) {
-        while (tq_tries < GEN_NQ) {
-          if (lane == 0) ticket = atomicAdd(&ctl->tile_q[tq * 32], 1u);
-          const unsigned tk = __shfl_sync(0xffffffffu, ticket, 0);
-          const int cnt = n_dyn > tq ? (n_dyn - tq + GEN_NQ - 1) / GEN_NQ : 0;
-          if (tk < (unsigned)cnt) { t_ = n_static + tq + GEN_NQ * (int)tk; stage_now = true; break; }
-          tq = (tq + 1) % GEN_NQ; ++tq_tries;
-        }
-      }
-      if (stage_now) {                                      // not prefetched: stage it now
-        const int64_t g0 = a.g_begin + (int64_t)(ntiles - 1 - t_) * 32 + lane;
-        if (g0 < a.g_end) { stage_tile_ef(a, fa, chain, g0, stg, pol); f_next = a.flags[(int64_t)chain * a.G + g0]; }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 
     // ---- 3. the CTA's column sums -> the chain's accumulators (integer atomics: order-free)
     __syncthreads();
-    if (tracing) trow[2] = globaltimer_ns();
+    ZZ_TRACE(2);
     for (int s = wid; s < nstat; s += SWEEP_BLOCK / 32) {
       long long v = 0;
 #pragma unroll
@@ -626,7 +621,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
     // ---- 4. ticket.  Steward mode: done, the steward CTA counts the tickets.  Otherwise the last CTA of the chain to arrive runs the
     // scalar half of the generation.
     if (threadIdx.x == 0) { __threadfence(); sh_ticket = atomicAdd(&ctl->arrive, 1u); }   // cumulative: orders the CTA's reductions (barrier above) before the ticket
-    if (tracing) trow[3] = globaltimer_ns();
+    ZZ_TRACE(3);
     if (ga.steward) continue;
     __syncthreads();
     if (sh_ticket != (gen_no + 1u) * n_cta - 1u) continue;
