@@ -64,42 +64,46 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) { unsigned
 __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // integer all-reduce of `n` 64-bit values over the peer inboxes (see allreduce_exchange): every value travels as two words
-// {half | epoch << 32}; the sum is exact, so the order of the ranks does not matter.  Returns false on time-out.
-__device__ __forceinline__ bool allreduce_exchange_i64(long long *vec /* shared memory, in/out */, int n, const CommArgs &cm, long long timeout_ns) {
+// {half | epoch << 32}; the sum is exact, so the order of the ranks does not matter.  One thread per (peer, value) polls — a thread
+// walking over the peers one after the other paid one L2 round trip per peer AFTER the words had arrived (6 us at 8 GPUs).
+// `xch`: shared memory, world * n values.  Returns false on time-out.
+__device__ __forceinline__ bool allreduce_exchange_i64(long long *vec /* shared memory, in/out */, long long *xch, int n, const CommArgs &cm, long long timeout_ns) {
   __shared__ int timed_out;
   if (threadIdx.x == 0) timed_out = 0;
   __syncthreads();
   const int slot = (int)(cm.epoch & 1ull), nw = 2 * n;
   const unsigned ep = (unsigned)cm.epoch;
-  for (int w = threadIdx.x; w < nw; w += blockDim.x) {
+  for (int t = threadIdx.x; t < nw * cm.world; t += blockDim.x) {       // one store per thread: (peer, word)
+    const int r = t / nw, w = t - r * nw;
+    if (r == cm.rank) continue;
     const unsigned long long v = (unsigned long long)vec[w >> 1];
     const unsigned half = (w & 1) ? (unsigned)(v >> 32) : (unsigned)v;
     const unsigned long long word = ((unsigned long long)ep << 32) | half;
-    for (int r = 0; r < cm.world; ++r) {
-      if (r == cm.rank) continue;
-      unsigned long long *dst = reinterpret_cast<unsigned long long *>(cm.inbox[r]) + cm.base + ((int64_t)slot * cm.world + cm.rank) * cm.stride + w;
-      asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
-    }
+    unsigned long long *dst = reinterpret_cast<unsigned long long *>(cm.inbox[r]) + cm.base + ((int64_t)slot * cm.world + cm.rank) * cm.stride + w;
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
   }
   const unsigned long long *in = reinterpret_cast<const unsigned long long *>(cm.inbox[cm.rank]) + cm.base + (int64_t)slot * cm.world * cm.stride;
   const unsigned long long t0 = globaltimer_ns();
-  long long mine = 0;
-  const int idx = threadIdx.x;
-  if (idx < n) {
-    mine = vec[idx];
-    for (int r = 0; r < cm.world; ++r) {
-      if (r == cm.rank) continue;
+  for (int t = threadIdx.x; t < n * cm.world; t += blockDim.x) {
+    const int r = t / n, idx = t - r * n;
+    long long v = vec[idx];
+    if (r != cm.rank) {
       const volatile unsigned long long *p = in + (int64_t)r * cm.stride + 2 * idx;
       unsigned long long a = p[0], b = p[1];
       while ((unsigned)(a >> 32) != ep || (unsigned)(b >> 32) != ep) {
         if ((long long)(globaltimer_ns() - t0) > timeout_ns) { timed_out = 1; break; }
         a = p[0]; b = p[1];
       }
-      mine += (long long)(((b & 0xFFFFFFFFull) << 32) | (a & 0xFFFFFFFFull));
+      v = (long long)(((b & 0xFFFFFFFFull) << 32) | (a & 0xFFFFFFFFull));
     }
+    xch[t] = v;
   }
   __syncthreads();
-  if (idx < n) vec[idx] = mine;
+  if ((int)threadIdx.x < n) {
+    long long sum = 0;
+    for (int r = 0; r < cm.world; ++r) sum += xch[r * n + threadIdx.x];
+    vec[threadIdx.x] = sum;
+  }
   __syncthreads();
   return timed_out == 0;
 }
@@ -108,7 +112,7 @@ __device__ __forceinline__ bool allreduce_exchange_i64(long long *vec /* shared 
 // ---- the scalar half of a generation (zz_chain.cuh) as the persistent kernel runs it ------------------------------------------
 // Scratch layout (shared memory; in the last-arriver mode it aliases the first statistic columns of the CTA, which are zero then)
 struct StageScr {
-  long long *ivec; double *st, *gam, *vg_s, *px_lu; L2Params *l2; zz_hyper *h; ChainDev *c; MoveDraws *md; FastH *F; GammaPre *gp; PreVarg *pv; PreL2 *pl; PrePx *pp;
+  long long *ivec; double *st, *gam, *vg_s, *px_lu; L2Params *l2; zz_hyper *h; ChainDev *c; MoveDraws *md; FastH *F; GammaPre *gp; PreVarg *pv; PreL2 *pl; PrePx *pp; long long *xch;
 };
 constexpr int MAX_NSTAT_P = 3 * (ZZ_MAX_COMP + 1) + 10;
 constexpr int SCR_MD = (2560 + (int)sizeof(ChainDev) + 127) / 128 * 128;
@@ -117,9 +121,10 @@ constexpr int SCR_GP = (SCR_FH + (int)sizeof(FastH) + 127) / 128 * 128;
 constexpr int SCR_PV = (SCR_GP + (ZZ_MAX_COMP + 3) * (int)sizeof(GammaPre) + 127) / 128 * 128;
 constexpr int SCR_PL = (SCR_PV + (int)sizeof(PreVarg) + 127) / 128 * 128;
 constexpr int SCR_PP = (SCR_PL + (int)sizeof(PreL2) + 127) / 128 * 128;
-constexpr int SCR_BYTES = SCR_PP + (int)sizeof(PrePx);
+constexpr int SCR_XCH = (SCR_PP + (int)sizeof(PrePx) + 127) / 128 * 128;     // [8 ranks][nstat] parts of the all-reduce
+constexpr int SCR_BYTES = SCR_XCH + 8 * MAX_NSTAT_P * 8;
 static_assert(MAX_NSTAT_P * 8 <= 512 && sizeof(L2Params) <= 256 && sizeof(zz_hyper) <= 1024, "stage scratch layout");
-static_assert(SCR_BYTES <= 8 * SWEEP_BLOCK * 5, "the scratch must fit in the first statistic columns (nstat >= 13 of them)");
+static_assert(SCR_BYTES <= 8 * SWEEP_BLOCK * 6, "the scratch must fit in the first statistic columns (nstat >= 13 of them)");
 static_assert(sizeof(ChainDev) % 8 == 0 && sizeof(zz_hyper) % 8 == 0 && sizeof(FastH) % 8 == 0, "copied as 64-bit words");
 __device__ __forceinline__ StageScr stage_scr(char *scr) {
   StageScr S;
@@ -137,6 +142,7 @@ __device__ __forceinline__ StageScr stage_scr(char *scr) {
   S.pv = reinterpret_cast<PreVarg *>(scr + SCR_PV);            // the statistics-independent parts of the Metropolis moves
   S.pl = reinterpret_cast<PreL2 *>(scr + SCR_PL);
   S.pp = reinterpret_cast<PrePx *>(scr + SCR_PP);              // the next generation's mhP_x proposal
+  S.xch = reinterpret_cast<long long *>(scr + SCR_XCH);
   return S;
 }
 // totals of the generation -> S.st (all-reduced over the gene shards); whole CTA.  false: a peer timed out (fail-stop)
@@ -149,7 +155,7 @@ __device__ __forceinline__ bool stage_totals(const StageScr &S, const GenArgs &g
     CommArgs cm = ga.cm;
     cm.epoch += (unsigned long long)gi + 1ull;
     cm.base += (int64_t)chain * 2 * cm.world * cm.stride;
-    ok = allreduce_exchange_i64(S.ivec, nstat, cm, cm.timeout_ns);
+    ok = allreduce_exchange_i64(S.ivec, S.xch, nstat, cm, cm.timeout_ns);
   }
   if ((int)threadIdx.x < nstat) {
     S.st[threadIdx.x] = ok ? (double)S.ivec[threadIdx.x] * (1.0 / FX_SCALE) : NAN;
