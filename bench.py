@@ -409,6 +409,35 @@ def main():
         except Exception as e:
             extras["data_dependence"] = {"error": str(e)[:200]}
 
+    # ---- L2 check: the per-gene state the production sweep touches (Xg enters through per-gene sufficient statistics) can be smaller
+    # than the 126 MB L2 and then stays there between the steps of a block, as it does between the generations of a real chain.
+    # Timed here: isolated single-sweep launches, L2-warm and with a 512 MB buffer rewritten before every launch.
+    l2_check = None
+    if not args.no_extras:
+        try:
+            flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+            res = {}
+            for cold in (False, True):
+                ts = []
+                for i in range(24):
+                    if cold:
+                        flush.fill_(i & 255)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); h.run_sweeps(step, 1); e1.record(); step += 1
+                    torch.cuda.synchronize()
+                    if i >= 4:
+                        ts.append(e0.elapsed_time(e1))
+                res["l2_flushed_ms" if cold else "l2_warm_ms"] = float(np.median(maxr(ts)) if world == 1 else np.median(ts))
+            del flush
+            touched = G * chains * 50 + G * 36
+            res["touched_mb_per_sweep"] = touched / 1e6
+            res["what"] = ("median of 20 isolated one-sweep launches of the timed kernel (each bracketed by events, a device synchronisation between launches, so the "
+                           "per-launch ramp-up is included and the figures are larger than ms_per_step), without and with a 512 MB buffer rewritten before "
+                           "every launch: the sweep is bound by instruction latency, its loads are staged one tile ahead, the L2 state makes no difference")
+            l2_check = res
+        except Exception as e:
+            l2_check = {"error": repr(e)[:200]}
+
     # ---- e2e: the same sweep through the host-buffer entry point (mutable state in pinned host memory, H2D + D2H every step)
     e2e = None
     if chains_cfg == 1:
@@ -505,6 +534,8 @@ def main():
         try:
             with open(tp) as f:
                 traffic = json.load(f).get(("k_generations:" if persistent else "k_sweep:") + args.workload)
+            if isinstance(traffic, dict):        # persistent kernel: per launch of K sweeps, from the 2-sweep and 20-sweep captures
+                traffic = traffic["first_sweep_bytes"] + traffic["per_additional_sweep_bytes"] * (args.steps - 1)
         except Exception:
             traffic = None
     cpu = None
@@ -531,7 +562,11 @@ def main():
                        "timing": f"{args.blocks} blocks x {args.steps} steps, CUDA events per block on the launching stream, max over ranks per block, median block reported; "
                                  f"an untimed 2-step launch of the same kernel precedes every timed block on the same stream ({passes} pass(es) of the protocol, last one reported)",
                        "ms_blocks": ms_blocks,
-                       "l2": f"working set {(G * (8 * R + 8) + G * chains * 50) / 1e6:.0f} MB per GPU vs 126 MB L2: " + ("inputs larger than L2, no flush" if G * (8 * R + 8) + G * chains * 50 > 126e6 else "fits in L2 (state stays L2-resident between steps; reported as-is)")},
+                       "l2": f"inputs {(G * (8 * R + 8) + G * chains * 50) / 1e6:.0f} MB per GPU (data matrix + gene lengths + per-gene state) vs 126 MB L2; the sweep itself touches "
+                             f"{(G * chains * 50 + G * 36) / 1e6:.0f} MB per step (the data matrix enters through per-gene sufficient statistics), which "
+                             + ("exceeds L2" if G * chains * 50 + G * 36 > 126e6 else "fits in L2 and stays there between steps, as between the generations of a real chain")
+                             + "; no flush between steps — l2_check times the kernel with and without an L2 flush before every launch",
+                       "l2_check": l2_check},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": kernel, "kernel_ms": sweep_ms * (args.steps if persistent else 1), "sweeps_per_launch": args.steps if persistent else 1,
                          "bytes_per_gene_update": balg, "peak_source": peak_src},
