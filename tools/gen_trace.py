@@ -1,5 +1,7 @@
-"""Per-CTA timeline of the persistent kernel (ZZ_GEN_TRACE): where the time of a sweep / generation goes.
-Usage: ZZ_GEN_TRACE=/tmp/t.bin python tools/gen_trace.py [workload] [genes]   (prints a summary per launch kind)"""
+"""Per-CTA timeline of the persistent kernel: where the time of a sweep / generation goes.  Needs a build with the stamps compiled in
+(they cost registers in the tile loop, so the product build has none):
+    ZZ_BUILD_OUT=$PWD/scratch/lib_trace.so ZZ_NVCC_EXTRA=-DZZ_GEN_TRACE_BUILD python zigzag_b200/build.py --force
+    ZIGZAG_GPU_LIB=$PWD/scratch/lib_trace.so python tools/gen_trace.py [workload] [genes]   (prints a summary per launch kind)"""
 import os, sys, numpy as np
 sys.path.insert(0, ".")
 path = os.environ.setdefault("ZZ_GEN_TRACE", "/tmp/zz_gen_trace.bin")

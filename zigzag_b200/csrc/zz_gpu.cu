@@ -72,39 +72,50 @@ struct CommArgs {
 };
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
-// all threads of the CTA must call it; `vec` = the local vector in shared memory (complete: the caller has synchronised)
+// all threads of the CTA must call it; `vec` = the local vector in shared memory (complete: the caller has synchronised).
+// One thread per (peer, word) sends; one thread per value polls its peers in RANK ORDER (the sum must be bit-identical on every
+// rank) — but it first waits for ALL its words with the loads of the different peers in flight together, instead of paying one L2
+// round trip per peer after the words have arrived.
 __device__ __forceinline__ void allreduce_exchange(const double *vec, const CommArgs &cm, double *out, int *err_flag) {
   __shared__ int timed_out;
   if (threadIdx.x == 0) timed_out = 0;
   __syncthreads();
   const int slot = (int)(cm.epoch & 1ull), nw = 2 * cm.nvec;
   const unsigned ep = (unsigned)cm.epoch;
-  for (int w = threadIdx.x; w < nw; w += blockDim.x) {
+  for (int t = threadIdx.x; t < nw * cm.world; t += blockDim.x) {
+    const int r = t / nw, w = t - r * nw;
+    if (r == cm.rank) continue;
     const double v = vec[w >> 1];
     const unsigned half = (w & 1) ? (unsigned)__double2hiint(v) : (unsigned)__double2loint(v);
     const unsigned long long word = ((unsigned long long)ep << 32) | half;
-    for (int r = 0; r < cm.world; ++r) {
-      if (r == cm.rank) continue;
-      unsigned long long *dst = reinterpret_cast<unsigned long long *>(cm.inbox[r]) + cm.base + ((int64_t)slot * cm.world + cm.rank) * cm.stride + w;
-      asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
-    }
+    unsigned long long *dst = reinterpret_cast<unsigned long long *>(cm.inbox[r]) + cm.base + ((int64_t)slot * cm.world + cm.rank) * cm.stride + w;
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
   }
   const unsigned long long *in = reinterpret_cast<const unsigned long long *>(cm.inbox[cm.rank]) + cm.base + (int64_t)slot * cm.world * cm.stride;
   const unsigned long long t0 = globaltimer_ns();
   for (int idx = threadIdx.x; idx < cm.nvec; idx += blockDim.x) {
-    double v = 0;
-    for (int r = 0; r < cm.world; ++r) {
-      double x = vec[idx];
-      if (r != cm.rank) {
+    unsigned long long a[8], b[8];
+    bool all;
+    do {                                   // the 2 (world - 1) loads of one round are independent: one round trip per round
+      all = true;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (r >= cm.world || r == cm.rank) continue;
         const volatile unsigned long long *p = in + (int64_t)r * cm.stride + 2 * idx;
-        unsigned long long a = p[0], b = p[1];
-        while ((unsigned)(a >> 32) != ep || (unsigned)(b >> 32) != ep) {
-          if ((long long)(globaltimer_ns() - t0) > cm.timeout_ns) { timed_out = 1; break; }
-          a = p[0]; b = p[1];
-        }
-        x = __hiloint2double((int)(unsigned)b, (int)(unsigned)a);
+        a[r] = p[0]; b[r] = p[1];
       }
-      v += x;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (r >= cm.world || r == cm.rank) continue;
+        all = all && (unsigned)(a[r] >> 32) == ep && (unsigned)(b[r] >> 32) == ep;
+      }
+      if (!all && (long long)(globaltimer_ns() - t0) > cm.timeout_ns) { timed_out = 1; break; }
+    } while (!all);
+    double v = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r >= cm.world) continue;
+      v += (r == cm.rank) ? vec[idx] : __hiloint2double((int)(unsigned)b[r], (int)(unsigned)a[r]);
     }
     out[idx] = v;
   }
