@@ -98,182 +98,158 @@ zigzagGPU <- setRefClass(
   gpu_mhSpikeAllocation = function(recover_x = FALSE, tune = FALSE){
     .Call("zzR_mh_spike_alloc", gpu, gpu_next()); .self$gpu_dirty <- TRUE; .self$gpu_after_move() },
 
-  # ---- hyper-parameter moves: R/zigzagProposals.R with the gene sums taken from the device ---------------------------------------
-  # counts and sums per component: zz_suffstats (layout in include/zigzag_gpu.h)
+  # ---- hyper-parameter moves: the moves of R/zigzagProposals.R with every gene sum taken from the device ------------------------
+  # Shared pieces.  A trace is the 100-wide 0/1 accept window of a move: `*_trace[[1]][[1]]`, a vector, or one row of a matrix.
+  gpu_win = function(name, row = NA, hit = FALSE){
+    tr <- .self$field(name)
+    w <- tr[[1]][[1]]
+    if(is.na(row)){ if(hit) w[100] <- 1 else w <- c(w[-1], 0) }
+    else          { if(hit) w[row, 100] <- 1 else w[row, ] <- c(w[row, -1], 0) }
+    tr[[1]][[1]] <- w
+    .self$field(name, tr)
+  },
+  gpu_mh_accept = function(log_ratio) log(runif(1)) < log_ratio,
+  # counts per component and in the spike (zz_suffstats, layout in include/zigzag_gpu.h)
   gpu_counts = function(){
     st <- .Call("zzR_suffstats", gpu, as.integer(num_active_components))
     K1 <- num_active_components + 1
     list(n = st[seq(K1)], n_inspike = st[3 * K1 + 1])
   },
+  # c(sum over inactive genes of computeInactiveLikelihood, sum over active genes of computeActiveLikelihood) at the given parameters
+  gpu_l2 = function(im = inactive_means, iv = inactive_variances, am = active_means, av = active_variances)
+    .Call("zzR_level2_sums", gpu, im, iv, am, av),
+  # after an accepted move on (s0, s1, tau): constants to the device, variance_g_probability[out_spike_idx] rewritten there (Pr:113,147,187)
+  gpu_commit_varg = function(){ .self$gpu_push_hyper(); .Call("zzR_commit_varg_hyper", gpu); .self$gpu_dirty <- TRUE },
 
   gibbsMixtureWeights = function(recover_x = FALSE, tune = FALSE){                       # Pr:412-431
-    num_in_components <- .self$gpu_counts()$n * beta
-    new_weights <- r_dirichlet(c(weight_active_shape_2, weight_within_active_alpha) + num_in_components)
-    if(! is.nan(new_weights[1])){
-      .self$weight_active <- 1 - new_weights[1]
-      .self$weight_within_active <- new_weights[-1]/sum(new_weights[-1])
-      .self$gpu_push_hyper()
+    w <- r_dirichlet(c(weight_active_shape_2, weight_within_active_alpha) + gpu_counts()$n * beta)
+    if(!is.nan(w[1])){
+      .self$weight_active <- 1 - w[1]
+      .self$weight_within_active <- w[-1] / sum(w[-1])
+      gpu_push_hyper()
     }
-    .self$gpu_after_move()
+    gpu_after_move()
   },
 
   gibbsSpikeProb = function(recover_x = FALSE, tune = FALSE){                            # Pr:511-526
-    cn <- .self$gpu_counts()
-    num_inspike <- cn$n_inspike
-    num_outspike <- cn$n[1] - num_inspike
-    new_spike_probability <- rbeta(1, num_inspike + spike_prior_shape_1, num_outspike + spike_prior_shape_2)
-    if(! is.nan(new_spike_probability)){
-      .self$spike_probability <- new_spike_probability
-      .self$gpu_push_hyper()
-    }
-    .self$gpu_after_move()
+    cn <- gpu_counts()
+    p <- rbeta(1, cn$n_inspike + spike_prior_shape_1, (cn$n[1] - cn$n_inspike) + spike_prior_shape_2)
+    if(!is.nan(p)){ .self$spike_probability <- p; gpu_push_hyper() }
+    gpu_after_move()
   },
 
   mhInactiveMeans = function(recover_x = FALSE, tune = FALSE){                           # Pr:433-471
     .self$inactive_means_proposed <- threshold_i - abs(threshold_i - inactive_means - rnorm(1, 0, inactive_mean_tuningParam[[1]]))
-    pp = .self$computeInactiveMeansPriorProbability(inactive_means_proposed)
-    pc = .self$computeInactiveMeansPriorProbability(inactive_means)
-    # sums of computeInactiveLikelihood over the inactive genes (0 when there are none)
-    Lp = .Call("zzR_level2_sums", gpu, inactive_means_proposed, inactive_variances, active_means, active_variances)[1]
-    Lc = .Call("zzR_level2_sums", gpu, inactive_means, inactive_variances, active_means, active_variances)[1]
-    R = temperature * (Lp - Lc + pp - pc)
-    if(tune) .self$inactive_means_trace[[1]][[1]] <- c(inactive_means_trace[[1]][[1]][-1],0)
-    if(log(runif(1)) < R){
+    dL <- gpu_l2(im = inactive_means_proposed)[1] - gpu_l2()[1]          # zero when no gene is inactive, as in the reference
+    dP <- computeInactiveMeansPriorProbability(inactive_means_proposed) - computeInactiveMeansPriorProbability(inactive_means)
+    if(tune) gpu_win("inactive_means_trace")
+    if(gpu_mh_accept(temperature * (dL + dP))){
       .self$inactive_means <- inactive_means_proposed
-      if(tune) .self$inactive_means_trace[[1]][[1]][100] <- 1
-      .self$gpu_push_hyper()
+      if(tune) gpu_win("inactive_means_trace", hit = TRUE)
+      gpu_push_hyper()
     }
-    .self$gpu_after_move()
+    gpu_after_move()
   },
 
-  mhActiveMeansDif = function(recover_x = FALSE, tune = FALSE){                          # Pr:640-705
+  mhActiveMeansDif = function(recover_x = FALSE, tune = FALSE){                          # Pr:640-705 (both branches: the sums are 0 without active genes)
     for(k in sample(num_active_components, num_active_components, replace = TRUE)){
-      .self$active_means_dif_proposed <- active_means_dif
-      .self$active_means_dif_proposed[k] <- abs(active_means_dif[k] + rnorm(1,0,active_mean_tuningParam[k]))
-      mp = .self$calculate_active_means(active_means_dif_proposed)
-      mc = active_means
-      # sums of computeActiveLikelihood over the active genes (0 when there are none: the reference's second branch)
-      Lp <- .Call("zzR_level2_sums", gpu, inactive_means, inactive_variances, mp, active_variances)[2]
-      Lc <- .Call("zzR_level2_sums", gpu, inactive_means, inactive_variances, mc, active_variances)[2]
-      pp = computeActiveMeansDifPriorProbability(active_means_dif_proposed[k])
-      pc = computeActiveMeansDifPriorProbability(active_means_dif[k])
-      R = temperature * (Lp + pp - Lc - pc)
-      if(tune) .self$active_means_trace[[1]][[1]][k,] <- c(active_means_trace[[1]][[1]][k,-1],0)
-      if(log(runif(1)) < R){
-        .self$active_means_dif[k] <- active_means_dif_proposed[k]
-        if(tune) .self$active_means_trace[[1]][[1]][k,100] <- 1
-        .self$active_means <- .self$calculate_active_means(active_means_dif_proposed)
-        .self$gpu_push_hyper()
+      dif <- active_means_dif
+      dif[k] <- abs(dif[k] + rnorm(1, 0, active_mean_tuningParam[k]))
+      .self$active_means_dif_proposed <- dif
+      means_p <- calculate_active_means(dif)
+      Lp <- gpu_l2(am = means_p)[2]
+      Lc <- gpu_l2()[2]
+      pp <- computeActiveMeansDifPriorProbability(dif[k])
+      pc <- computeActiveMeansDifPriorProbability(active_means_dif[k])
+      if(tune) gpu_win("active_means_trace", row = k)
+      if(gpu_mh_accept(temperature * (Lp + pp - Lc - pc))){
+        .self$active_means_dif[k] <- dif[k]
+        .self$active_means <- means_p
+        if(tune) gpu_win("active_means_trace", row = k, hit = TRUE)
+        gpu_push_hyper()
       }
     }
-    .self$gpu_after_move()
+    gpu_after_move()
   },
 
   mhSharedVariance = function(recover_x = FALSE, tune = FALSE){                          # Pr:768-803
-    .self$active_variances_proposed <- rep(10^(.self$two_boundary_slide_move(log(active_variances[1], 10), active_variances_prior_log_min,
-                                                                             active_variances_prior_log_max, active_variance_tuningParam[1])),
-                                           num_active_components)
-    if(tune) .self$active_variances_trace[[1]][[1]][1,] <- c(active_variances_trace[[1]][[1]][1,-1],0)
-    Lp <- .Call("zzR_level2_sums", gpu, inactive_means, active_variances_proposed[1], active_means, active_variances_proposed)   # c(inactive, active)
-    Lc <- .Call("zzR_level2_sums", gpu, inactive_means, inactive_variances, active_means, active_variances)
-    active_pp = .self$computeActiveVariancesPriorProbability(active_variances_proposed[1])
-    active_pc = .self$computeActiveVariancesPriorProbability(active_variances[1])
-    R = temperature * (Lp[2] + Lp[1] + active_pp - Lc[2] - Lc[1] - active_pc)
-    if(log(runif(1)) < R){
-      .self$active_variances <- rep(active_variances_proposed[1], num_active_components)
-      .self$inactive_variances <- active_variances_proposed[1]
-      if(tune) .self$active_variances_trace[[1]][[1]][1,100] <- 1
-      .self$gpu_push_hyper()
+    v <- 10^two_boundary_slide_move(log(active_variances[1], 10), active_variances_prior_log_min, active_variances_prior_log_max,
+                                    active_variance_tuningParam[1])
+    .self$active_variances_proposed <- rep(v, num_active_components)
+    if(tune) gpu_win("active_variances_trace", row = 1)
+    Lp <- gpu_l2(iv = v, av = active_variances_proposed)                 # c(inactive, active) at the proposed shared variance
+    Lc <- gpu_l2()
+    dP <- computeActiveVariancesPriorProbability(v) - computeActiveVariancesPriorProbability(active_variances[1])
+    if(gpu_mh_accept(temperature * (sum(Lp) - sum(Lc) + dP))){
+      .self$active_variances <- active_variances_proposed
+      .self$inactive_variances <- v
+      if(tune) gpu_win("active_variances_trace", row = 1, hit = TRUE)
+      gpu_push_hyper()
     }
-    .self$gpu_after_move()
+    gpu_after_move()
   },
 
-  # after an accepted move on (s0, s1, tau): new constants to the device, variance_g_probability[out_spike_idx] rewritten there (Pr:113,147,187)
-  gpu_commit_varg = function(){ .self$gpu_push_hyper(); .Call("zzR_commit_varg_hyper", gpu); .self$gpu_dirty <- TRUE },
-
   mhTau = function(recover_x = FALSE, tune = FALSE){                                     # Pr:119-152
-    proposal <- .self$scale_move(tau, tuningParam_tau)
-    proposed_tau <- proposal[[1]]
-    HR <- log(proposal[[2]])
-    L <- .Call("zzR_varg_hyper_sum", gpu, s0, s1, proposed_tau)                          # c(Lp, Lc) over out_spike_idx
-    pp <- .self$computeTauPriorProbability(proposed_tau)
-    pc <- .self$computeTauPriorProbability(tau)
-    R <- temperature * (L[1] - L[2] + pp - pc) + HR
-    if(tune) .self$tau_trace[[1]][[1]] <- c(tau_trace[[1]][[1]][-1], 0)
-    if(log(runif(1)) < R){
-      .self$tau <- proposed_tau
-      if(tune) .self$tau_trace[[1]][[1]][100] <- 1
-      .self$gpu_commit_varg()
+    mv <- scale_move(tau, tuningParam_tau)                               # list(proposed value, scaling factor)
+    L <- .Call("zzR_varg_hyper_sum", gpu, s0, s1, mv[[1]])               # c(sum at the proposal, sum at the current values) over out_spike_idx
+    dP <- computeTauPriorProbability(mv[[1]]) - computeTauPriorProbability(tau)
+    if(tune) gpu_win("tau_trace")
+    if(gpu_mh_accept(temperature * (L[1] - L[2] + dP) + log(mv[[2]]))){
+      .self$tau <- mv[[1]]
+      if(tune) gpu_win("tau_trace", hit = TRUE)
+      gpu_commit_varg()
     }
-    .self$gpu_after_move()
+    gpu_after_move()
   },
 
   mhSg = function(recover_x = FALSE, tune = FALSE){                                      # Pr:58-117
-    HR = 0
-    selection = sample(seq(2), 1, prob = c(1,1))
-    if(selection == 1){
-      proposed_s0 <- s0 + rnorm(1, 0, tuningParam_s0)
-      proposed_s1 <- s1
-      if(tune) .self$s0_trace[[1]][[1]] <- c(s0_trace[[1]][[1]][-1], 0)
-    }else{
-      proposed_s0 <- s0
-      proposal <- .self$scale_move(s1, tuningParam_s1)
-      proposed_s1 <- proposal[[1]]
-      HR <- log(proposal[[2]])
-      if(tune) .self$s1_trace[[1]][[1]] <- c(s1_trace[[1]][[1]][-1], 0)
+    on_s0 <- sample(seq(2), 1, prob = c(1, 1)) == 1
+    new_s0 <- s0; new_s1 <- s1; log_hastings <- 0
+    if(on_s0) new_s0 <- s0 + rnorm(1, 0, tuningParam_s0)
+    else { mv <- scale_move(s1, tuningParam_s1); new_s1 <- mv[[1]]; log_hastings <- log(mv[[2]]) }
+    trace <- if(on_s0) "s0_trace" else "s1_trace"
+    if(tune) gpu_win(trace)
+    L <- .Call("zzR_varg_hyper_sum", gpu, new_s0, new_s1, tau)
+    dP <- computeS0PriorProbability(new_s0) + computeS1PriorProbability(new_s1) - computeS0PriorProbability(s0) - computeS1PriorProbability(s1)
+    if(gpu_mh_accept(temperature * (L[1] - L[2] + dP) + log_hastings)){
+      .self$s0 <- new_s0; .self$s1 <- new_s1
+      if(tune) gpu_win(trace, hit = TRUE)
+      gpu_commit_varg()
     }
-    L <- .Call("zzR_varg_hyper_sum", gpu, proposed_s0, proposed_s1, tau)
-    pp <- .self$computeS0PriorProbability(proposed_s0) + .self$computeS1PriorProbability(proposed_s1)
-    pc <- .self$computeS0PriorProbability(s0) + .self$computeS1PriorProbability(s1)
-    R <- temperature * (L[1] - L[2] + pp - pc) + HR
-    if(log(runif(1)) < R){
-      .self$s0 <- proposed_s0
-      .self$s1 <- proposed_s1
-      if(selection == 1){ if(tune) .self$s0_trace[[1]][[1]][100] <- 1 } else { if(tune) .self$s1_trace[[1]][[1]][100] <- 1 }
-      .self$gpu_commit_varg()
-    }
-    .self$gpu_after_move()
+    gpu_after_move()
   },
 
-  mhS0Tau = function(recover_x = FALSE, tune = FALSE){                                   # Pr:154-191
-    proposal <- .self$scale_move(tau, tuningParam_s0tau)
-    proposed_s0 <- s0 - log(proposal[[2]])
-    proposed_tau <- proposal[[1]]
-    HR <- log(proposal[[2]])
-    if(tune) .self$s0tau_trace[[1]][[1]] <- c(s0tau_trace[[1]][[1]][-1], 0)
-    L <- .Call("zzR_varg_hyper_sum", gpu, proposed_s0, s1, proposed_tau)
-    pp <- .self$computeS0PriorProbability(proposed_s0) + .self$computeTauPriorProbability(proposed_tau)
-    pc <- .self$computeS0PriorProbability(s0) + .self$computeTauPriorProbability(tau)
-    R <- temperature * (L[1] - L[2] + pp - pc) + HR
-    if(log(runif(1)) < R){
-      .self$s0 <- proposed_s0
-      .self$tau <- proposed_tau
-      if(tune) .self$s0tau_trace[[1]][[1]][100] <- 1
-      .self$gpu_commit_varg()
+  mhS0Tau = function(recover_x = FALSE, tune = FALSE){                                   # Pr:154-191: tau scales, s0 compensates
+    mv <- scale_move(tau, tuningParam_s0tau)
+    log_sf <- log(mv[[2]])
+    new_s0 <- s0 - log_sf
+    if(tune) gpu_win("s0tau_trace")
+    L <- .Call("zzR_varg_hyper_sum", gpu, new_s0, s1, mv[[1]])
+    dP <- computeS0PriorProbability(new_s0) + computeTauPriorProbability(mv[[1]]) - computeS0PriorProbability(s0) - computeTauPriorProbability(tau)
+    if(gpu_mh_accept(temperature * (L[1] - L[2] + dP) + log_sf)){
+      .self$s0 <- new_s0; .self$tau <- mv[[1]]
+      if(tune) gpu_win("s0tau_trace", hit = TRUE)
+      gpu_commit_varg()
     }
-    .self$gpu_after_move()
+    gpu_after_move()
   },
 
   mhP_x = function(recover_x = FALSE, tune = FALSE){                                     # Pr:193-243
-    randlib = sample(num_libraries, 1)
-    proposed_alpha_r <- alpha_r
-    proposal <- .self$scale_move(alpha_r[randlib], tuningParam_alpha_r[randlib])
-    proposed_alpha_r[randlib] <- proposal[[1]]
-    if(tune) .self$alpha_r_trace[[1]][[1]][randlib,] <- c(alpha_r_trace[[1]][[1]][randlib, -1], 0)
-    HR <- log(proposal[[2]])
+    lib <- sample(num_libraries, 1)
+    mv <- scale_move(alpha_r[lib], tuningParam_alpha_r[lib])
+    alpha_p <- alpha_r; alpha_p[lib] <- mv[[1]]
+    if(tune) gpu_win("alpha_r_trace", row = lib)
     # Lp - Lc: the sum over genes of the one library's term at alpha' minus the same at alpha (for num_libraries == 2 the reference
     # recomputes the whole likelihood; the other library's terms cancel in the difference)
-    delta <- .Call("zzR_px_delta", gpu, proposed_alpha_r, as.integer(randlib))[randlib]
-    pp <- .self$computeAlphaRPriorProbability(proposed_alpha_r)
-    pc <- .self$computeAlphaRPriorProbability(alpha_r)
-    R <- temperature * (delta + pp - pc) + HR
-    if(log(runif(1)) < R & R != Inf){
-      .self$alpha_r[randlib] <- proposed_alpha_r[randlib]
-      if(tune) .self$alpha_r_trace[[1]][[1]][randlib,100] <- 1
-      .Call("zzR_px_commit", gpu, as.integer(randlib), proposed_alpha_r[randlib])       # alpha_r, p_x and XgLikelihood on the device
+    dL <- .Call("zzR_px_delta", gpu, alpha_p, as.integer(lib))[lib]
+    log_ratio <- temperature * (dL + computeAlphaRPriorProbability(alpha_p) - computeAlphaRPriorProbability(alpha_r)) + log(mv[[2]])
+    if(gpu_mh_accept(log_ratio) & log_ratio != Inf){
+      .self$alpha_r[lib] <- mv[[1]]
+      if(tune) gpu_win("alpha_r_trace", row = lib, hit = TRUE)
+      .Call("zzR_px_commit", gpu, as.integer(lib), mv[[1]])             # alpha_r, p_x and XgLikelihood on the device
       .self$gpu_dirty <- TRUE
     }
-    .self$gpu_after_move()
+    gpu_after_move()
   },
 
   calculate_lnl = function(num_libs) .Call("zzR_lnl", gpu),                               # U:70-75
