@@ -276,6 +276,14 @@ int zz_sample_rows_written(zz_handle *h, int64_t *param_rows, int64_t *yv_rows);
    `bins` = seq(min(ranges) - 2, max(ranges) + 2, by = 0.1) as posteriorPredictiveSimulation builds it (PostPred:9-17).
    Chain 0; synchronous (the histograms come back to the host, where the per-bin functionals are formed). */
 int zz_post_predictive(zz_handle *h, uint64_t step, const double *bins, int nbins, double *out);
+/* The same on gene shards: `allreduce(ctx, buf, n, dtype)` sums a HOST buffer of n elements in place over the shards (dtype: 0 =
+   double, 1 = uint32, 2 = uint64); it is called four times per data set (library sums + gene count, detected-value counts, all
+   histograms, the fixed-point model weights).  NULL: one shard holds every gene (zz_post_predictive). */
+#define ZZ_DTYPE_F64 0
+#define ZZ_DTYPE_U32 1
+#define ZZ_DTYPE_U64 2
+typedef void (*zz_allreduce_fn)(void *ctx, void *buf, int64_t n, int dtype);
+int zz_post_predictive_sharded(zz_handle *h, uint64_t step, const double *bins, int nbins, zz_allreduce_fn allreduce, void *ctx, double *out);
 
 #ifdef __cplusplus
 }

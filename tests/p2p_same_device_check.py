@@ -73,3 +73,31 @@ def worker(rank, world, port, mode, out):
     out[rank] = res
     dist.barrier()
     dist.destroy_process_group()
+
+
+def postpred_worker(rank, world, port, out):
+    """Posterior-predictive statistics on two gene shards (zz_post_predictive_sharded through the host mirror's all-reduce, gloo) against
+    the same call on one handle holding every gene."""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    import torch
+    import torch.distributed as dist
+    from zigzag_b200 import synth
+    from zigzag_b200.zigzag import zigzag
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(0)
+    G, R = 6000, 4
+    X, gl, _ = synth.simulate(G, R, config_id=778)
+    data = np.where(np.isneginf(X), 0.0, np.exp(X))
+    kw = dict(threshold_i=-1.0, threshold_a=(1.0, 6.0), seed=17, write_settings=False, output_directory="/tmp/zz_pp_check", init="device")
+    mm = zigzag(data, gl, shard=(rank, world), process_group=dist.group.WORLD, **kw)
+    mm.burnin(sample_frequency=50, ngen=60, write_to_files=False, schedule="fused")
+    pp = mm.posteriorPredictiveSimulation()
+    res = dict(pp={k: np.asarray(v).tolist() for k, v in pp.items()}, tau=mm.tau)
+    if rank == 0:
+        one = zigzag(data, gl, **kw)
+        one.burnin(sample_frequency=50, ngen=60, write_to_files=False, schedule="fused")
+        res["one"] = {k: np.asarray(v).tolist() for k, v in one.posteriorPredictiveSimulation().items()}
+        res["one_tau"] = one.tau
+    out[rank] = res
+    dist.barrier()
+    dist.destroy_process_group()

@@ -37,3 +37,18 @@ def test_a_missing_peer_is_fail_stop():
     assert r["flag"] & 4, r                       # bit 2: the exchange timed out
     assert r["all_nan"], "the statistics of a timed-out exchange must be poisoned, not stale"
     assert 1.5 < r["seconds"] < 30, r
+
+
+@pytest.mark.timeout(600)
+def test_posterior_predictive_statistics_on_gene_shards():
+    """zz_post_predictive_sharded: the histograms of two shards, summed inside the call, give the statistics of the whole gene set.
+    (init="device" + Philox keyed by the global gene index: the two-shard chain IS the one-handle chain, so the states agree too.)"""
+    from p2p_same_device_check import postpred_worker
+    out = mp.Manager().dict()
+    mp.spawn(postpred_worker, args=(2, 31800 + os.getpid() % 300, out), nprocs=2, join=True)
+    a, b = out[0], out[1]
+    assert a["pp"] == b["pp"], "the ranks hold different statistics"
+    assert abs(a["tau"] - a["one_tau"]) < 1e-9 * abs(a["one_tau"])
+    for k, v in a["one"].items():
+        assert np.allclose(a["pp"][k], v, rtol=1e-7, atol=1e-9), (k, a["pp"][k], v)
+    assert np.isfinite(a["pp"]["W_L"]) and np.isfinite(a["pp"]["B"])

@@ -177,6 +177,7 @@ _SIG = {
     "zz_set_sample_sink": (C.c_int, [_P, _P]),
     "zz_sample_rows_written": (C.c_int, [_P, _P, _P]),
     "zz_post_predictive": (C.c_int, [_P, C.c_uint64, _P, C.c_int, _P]),
+    "zz_post_predictive_sharded": (C.c_int, [_P, C.c_uint64, _P, C.c_int, _P, _P, _P]),
 }
 EXPORTS = tuple(_SIG)
 
@@ -489,11 +490,21 @@ class Handle:
             return sc[0], hy[0]
         return list(sc), list(hy)
 
-    def post_predictive(self, step, bins):
-        """Realised discrepancies of one simulated data set: dict(W_L, W_U, B, W_L_r[R], B_r[R]) (PostPred:3-156)."""
+    def post_predictive(self, step, bins, allreduce=None):
+        """Realised discrepancies of one simulated data set: dict(W_L, W_U, B, W_L_r[R], B_r[R]) (PostPred:3-156).  On gene shards pass
+        `allreduce(array)`: sums a numpy array in place over the shards (called with float64 / uint32 / uint64 arrays)."""
         bins = np.ascontiguousarray(bins, dtype=np.float64)
         out = np.empty(3 + 2 * self.R)
-        self._ck(self.L.zz_post_predictive(self.h, step, _ptr(bins), len(bins), _ptr(out)))
+        if allreduce is None:
+            self._ck(self.L.zz_post_predictive(self.h, step, _ptr(bins), len(bins), _ptr(out)))
+        else:
+            types = {0: (C.c_double, np.float64), 1: (C.c_uint32, np.uint32), 2: (C.c_uint64, np.uint64)}
+
+            @C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int64, C.c_int)
+            def cb(_ctx, buf, n, dtype):
+                ct, _ = types[dtype]
+                allreduce(np.ctypeslib.as_array(C.cast(buf, C.POINTER(ct)), (n,)))
+            self._ck(self.L.zz_post_predictive_sharded(self.h, step, _ptr(bins), len(bins), C.cast(cb, C.c_void_p), None, _ptr(out)))
         return dict(W_L=out[0], W_U=out[1], B=out[2], W_L_r=out[3:3 + self.R].copy(), B_r=out[3 + self.R:].copy())
 
     # ---- sample-time rows written by the device

@@ -2632,6 +2632,13 @@ int zz_sample_rows_written(zz_handle *h, int64_t *param_rows, int64_t *yv_rows) 
 
 // ---- posterior-predictive discrepancies (k_post_pred) ---------------------------------------------------------------
 int zz_post_predictive(zz_handle *h, uint64_t step, const double *bins, int nbins, double *out) {
+  return zz_post_predictive_sharded(h, step, bins, nbins, nullptr, nullptr, out);
+}
+
+// The statistics are functionals of histograms over ALL genes: with gene shards the per-shard histograms (integer counts, fixed-point
+// model weights) and the per-library sums are summed over the shards by the caller's `allreduce` (host buffers, in place) — once after
+// pass 1 (the library means that centre pass 2 are global) and once after pass 2.  Every rank then holds the same statistics.
+int zz_post_predictive_sharded(zz_handle *h, uint64_t step, const double *bins, int nbins, zz_allreduce_fn allreduce, void *ctx, double *out) {
   ZZ_CHECK(h);
   if (!h->have_data) return fail(h, ZZ_ERR_STATE, "zz_upload_data has not been called");
   if (!bins || !out || nbins < 3 || nbins > 1400) return fail(h, ZZ_ERR_INVALID, "zz_post_predictive: need 3 <= nbins <= 1400 (shared-memory histograms)");
@@ -2669,6 +2676,13 @@ int zz_post_predictive(zz_handle *h, uint64_t step, const double *bins, int nbin
   ZZ_CUDA(h, cudaMemcpyAsync(sums.data(), h->red_out, sizeof(double) * 4 * R, cudaMemcpyDeviceToHost, h->stream));
   ZZ_CUDA(h, cudaMemcpyAsync(hu.data(), u32, sizeof(unsigned) * ((size_t)2 * R * Hn), cudaMemcpyDeviceToHost, h->stream));   // cd, cs
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  double G_all = (double)G;
+  if (allreduce) {
+    sums.push_back(G_all);
+    allreduce(ctx, sums.data(), (int64_t)sums.size(), ZZ_DTYPE_F64);
+    G_all = sums.back(); sums.pop_back();
+    allreduce(ctx, hu.data(), (int64_t)2 * R * Hn, ZZ_DTYPE_U32);
+  }
   // library means of the detected values (PostPred:52-57) -> pass 2 bins the mean-centred copies
   std::vector<double> ndd(R), nds(R);
   double gmd = 0, gms = 0, lmd[ZZ_MAX_LIBS], lms[ZZ_MAX_LIBS];
@@ -2685,6 +2699,10 @@ int zz_post_predictive(zz_handle *h, uint64_t step, const double *bins, int nbin
   ZZ_CUDA(h, cudaMemcpyAsync(hu.data(), u32, sizeof(unsigned) * n_u32, cudaMemcpyDeviceToHost, h->stream));
   ZZ_CUDA(h, cudaMemcpyAsync(hm.data(), md, sizeof(unsigned long long) * n_u64, cudaMemcpyDeviceToHost, h->stream));
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (allreduce) {
+    allreduce(ctx, hu.data(), (int64_t)n_u32, ZZ_DTYPE_U32);
+    allreduce(ctx, hm.data(), (int64_t)n_u64, ZZ_DTYPE_U64);
+  }
   // ---- the functionals of the histograms (small: R x nbins), as the reference forms them
   const zz_hyper &hy = h->hyper_host[0];
   const unsigned *cd = hu.data(), *cs = cd + (size_t)R * Hn, *cds = cs + (size_t)R * Hn, *css = cds + (size_t)R * Hn, *hyh = css + (size_t)R * Hn, *hsy = hyh + Hn;
@@ -2708,7 +2726,7 @@ int zz_post_predictive(zz_handle *h, uint64_t step, const double *bins, int nbin
     double md_ = 0, ms_ = 0;
     for (int r = 0; r < R; ++r) {
       const double model = (1 - c) * (sums[4 * r + 2] / n_out) + c;
-      const double dd = fabs(((double)G - ndd[r]) / (double)G - model), ds = fabs(((double)G - nds[r]) / (double)G - model);
+      const double dd = fabs((G_all - ndd[r]) / G_all - model), ds = fabs((G_all - nds[r]) / G_all - model);
       md_ += dd / R; ms_ += ds / R; out[3 + R + r] = dd - ds;
     }
     out[2] = md_ - ms_;

@@ -222,8 +222,8 @@ class zigzag:
                                                           "weight_active", "beta", "temperature", "variance_g_upper_bound")})
         self.h.set_hyper(hy, 0)
 
-    def _allreduce(self, v):
-        """Sum of a small float64 vector over the gene shards (identical on every rank afterwards)."""
+    def _allreduce(self, v, op="sum"):
+        """Sum (or maximum) of a small float64 vector over the gene shards (identical on every rank afterwards)."""
         v = np.asarray(v, dtype=np.float64)
         if self.world == 1:
             return v
@@ -232,8 +232,17 @@ class zigzag:
         t = torch.from_numpy(v.copy())
         if dist.get_backend(self.pg) == "nccl":
             t = t.cuda()
-        dist.all_reduce(t, group=self.pg)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM, group=self.pg)
         return t.cpu().numpy()
+
+    def _allreduce_inplace(self, a):
+        """In-place sum of a numpy array (float64 / uint32 / uint64: counts travel as float64, exact below 2^53) over the gene shards."""
+        if a.dtype == np.uint64:          # exact: the two 32-bit halves are summed separately (each sum stays below 2^53) and recombined
+            lo = self._allreduce((a & np.uint64(0xFFFFFFFF)).astype(np.float64)).astype(np.uint64)
+            hi = self._allreduce((a >> np.uint64(32)).astype(np.float64)).astype(np.uint64)
+            a[...] = (hi << np.uint64(32)) + lo
+        else:
+            a[...] = self._allreduce(a.astype(np.float64)).astype(a.dtype)
 
     # ------------------------------------------------------------------ schedule="device": whole generations on the GPU
     def _priors_struct(self):
@@ -956,18 +965,20 @@ class zigzag:
         """Simulates one data set from the current state on the device and returns / logs the realised discrepancy statistics
         (lower- and upper-level Wasserstein distances, Rumsfeld zero-fraction discrepancy, and their per-library versions)."""
         from statistics import NormalDist
-        if self.world != 1:
-            raise NotImplementedError("posterior-predictive statistics are functionals of global histograms: one GPU in this round")
         K = self.num_active_components
         st = self.state()
         yo = st["Yg"][st["inactive_spike_allocation"] == 0]
         xf = self.Xg[np.isfinite(self.Xg)]
+        y_lo, y_hi = (yo.min(), yo.max()) if len(yo) else (math.inf, -math.inf)
+        if self.world > 1:                                                               # the range of Yg over ALL shards
+            y_lo, y_hi = -self._allreduce([-y_lo], "max")[0], self._allreduce([y_hi], "max")[0]
         rng_ = [NormalDist(self.inactive_means, math.sqrt(self.inactive_variances)).inv_cdf(0.000001),
                 NormalDist(self.active_means[K - 1], math.sqrt(self.active_variances[K - 1])).inv_cdf(0.999999),
-                yo.min(), yo.max(), xf.min(), xf.max()]                                  # PostPred:9-15
+                y_lo, y_hi, xf.min(), xf.max()]                                          # PostPred:9-15
         bins = np.arange(min(rng_) - 2, max(rng_) + 2, 0.1)                              # PostPred:17 (binwidth 0.1)
-        out = self.h.post_predictive(self._next_step(), bins)
-        if prefix is not None:
+        # gene shards: the histograms are summed over the shards inside the call (zz_post_predictive_sharded), every rank gets the statistics
+        out = self.h.post_predictive(self._next_step(), bins, allreduce=self._allreduce_inplace if self.world > 1 else None)
+        if prefix is not None and self.rank == 0:
             g = self.gen if gen is None else gen
             with open(self._path(prefix, ".post_predictive_output.log"), "a") as f:      # PostPred:82-84
                 f.write("\t".join(_rnum(x) for x in (g, out["W_L"], out["W_U"], out["B"])) + "\n")
