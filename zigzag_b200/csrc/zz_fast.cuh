@@ -24,7 +24,7 @@
 #define ZZ_ILP 4
 #endif
 #ifndef ZZ_SWEEP_MINB
-#define ZZ_SWEEP_MINB 3
+#define ZZ_SWEEP_MINB 1
 #endif
 
 namespace zz {

@@ -27,7 +27,7 @@ namespace {
 
 constexpr int BLOCK = 256;
 #ifndef ZZ_SWEEP_BLOCK
-#define ZZ_SWEEP_BLOCK 256
+#define ZZ_SWEEP_BLOCK 512
 #endif
 // -DZZ_BOUNDS_CHECK (zigzag_b200/libzigzag_gpu_dbg.so, tests/test_gpu_debug_build.py): every index that is READ from memory before it
 // addresses memory — the gene permutation, its inverse, slot lists, candidate slots, tile tickets, component numbers — is checked on
@@ -1240,7 +1240,7 @@ struct zz_handle {
   bool sink_on; zz_sample_sink sink; double *sink_p, *sink_y, *sink_v; int32_t *cand_slots; int64_t sink_prow, sink_yrow;   // zz_set_sample_sink
   bool hyper_host_stale;                   // zz_run_generations moved the hyper-parameters on the device; hyper_host is refreshed by zz_chain_read
   ChainDev *devchain; double *chain_stats; bool chain_ready; int64_t chain_gen, chain_samples; uint64_t chain_step;   // zz_run_generations
-  double *dlt; GenCtl *genctl; long long *genacc; int gen_blocks;   // k_generations: per-gene mhP_x terms, grid-barrier words, fixed-point totals
+  double *dlt; GenCtl *genctl; long long *genacc; int gen_blocks, gen_blocks_l;   // k_generations: per-gene mhP_x terms, grid-barrier words, fixed-point totals
   bool caches_valid;                       // XgLikelihood / variance_g_probability are current (device-resident segments do not maintain them)
   int32_t *inv_perm; cudaStream_t s_up, s_down; cudaEvent_t ev_entry, ev_up[ZZ_HOST_MAX_CHUNKS], ev_done[ZZ_HOST_MAX_CHUNKS]; bool pipe_ready;
 };
@@ -1623,7 +1623,7 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   h->sink_on = false; h->cand_slots = nullptr; h->sink_prow = h->sink_yrow = 0;
   h->hyper_host_stale = false;
   h->devchain = nullptr; h->chain_stats = nullptr; h->chain_ready = false; h->chain_gen = 0; h->chain_samples = 0; h->chain_step = 0;
-  h->dlt = nullptr; h->genctl = nullptr; h->genacc = nullptr; h->gen_blocks = 0; h->caches_valid = true;
+  h->dlt = nullptr; h->genctl = nullptr; h->genacc = nullptr; h->gen_blocks = 0; h->gen_blocks_l = 0; h->caches_valid = true;
   *out = h;  // returned even on failure so the caller can read zz_last_error and must zz_destroy
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -2332,18 +2332,24 @@ int zz_chain_begin(zz_handle *h, const zz_priors *priors, const zz_chain_scalars
 }  // extern "C"
 namespace {
 
-template <int RT> cudaError_t launch_generations_k(int K, dim3 grid, size_t smem, cudaStream_t st, GenArgs &ga) {
-  void *args[] = {&ga};
-  const void *fn = nullptr;
+// the two CTA shapes of k_generations (see the kernel): 512 threads for shards up to GEN_LARGE_MIN genes and for batched chains, 640 above
+constexpr int GEN_BLK_S = SWEEP_BLOCK, GEN_BLK_L = 640;
+template <int RT, int BLK> const void *generations_fn(int K) {
   switch (K) {
-    case 1: fn = (const void *)k_generations<RT, 1>; break;
-    case 2: fn = (const void *)k_generations<RT, 2>; break;
-    case 3: fn = (const void *)k_generations<RT, 3>; break;
-    default: return cudaErrorInvalidValue;
+    case 1: return (const void *)k_generations<RT, 1, BLK>;
+    case 2: return (const void *)k_generations<RT, 2, BLK>;
+    case 3: return (const void *)k_generations<RT, 3, BLK>;
+    default: return nullptr;
   }
-  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  return cudaLaunchCooperativeKernel(fn, grid, dim3(SWEEP_BLOCK), args, smem, st);
+}
+const void *generations_fn(int R, int K, int blk) {
+#ifdef ZZ_DEV_R16
+  return blk == GEN_BLK_L ? generations_fn<16, GEN_BLK_L>(K) : generations_fn<16, GEN_BLK_S>(K);
+#else
+#define ZZ_GEN_FN(RT_) (blk == GEN_BLK_L ? generations_fn<RT_, GEN_BLK_L>(K) : generations_fn<RT_, GEN_BLK_S>(K))
+  switch (R) { case 2: return ZZ_GEN_FN(2); case 4: return ZZ_GEN_FN(4); case 8: return ZZ_GEN_FN(8); case 16: return ZZ_GEN_FN(16); default: return ZZ_GEN_FN(0); }
+#undef ZZ_GEN_FN
+#endif
 }
 
 // whether k_generations serves this handle: straight-line tile (K <= 3, no variance_g upper bound), library loop unrolled
@@ -2367,31 +2373,27 @@ int launch_generations(zz_handle *h, uint64_t step0, int ngen, int tune, int hyp
     ZZ_CUDA(h, cudaMemsetAsync(h->dlt, 0, sizeof(double) * (size_t)C * h->G, h->stream));
   }
   if (int rc = ensure_lps(h)) return rc;
-  const size_t smem = sizeof(double) * (nstat + 10) * SWEEP_BLOCK;
-  if (h->gen_blocks == 0) {    // co-resident CTAs of k_generations (cooperative launch): from the occupancy calculator
+  static const int64_t large_min = getenv("ZZ_GEN_LARGE_MIN") ? atoll(getenv("ZZ_GEN_LARGE_MIN")) : 700000;
+  const int blk = (C == 1 && h->G >= large_min) ? GEN_BLK_L : GEN_BLK_S;
+  const size_t smem = sizeof(double) * (nstat + 10) * blk;
+  const void *fn = generations_fn(h->R, h->K, blk);
+  if (!fn) return fail(h, ZZ_ERR_INVALID, "k_generations: more than 3 active components");
+  ZZ_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int &gen_blocks = blk == GEN_BLK_L ? h->gen_blocks_l : h->gen_blocks;
+  if (gen_blocks == 0) {    // co-resident CTAs of k_generations (cooperative launch): from the occupancy calculator
     int per_sm = 0, sms = 0;
-    cudaError_t e = cudaSuccess;
-#define ZZ_OCC(RT_) { const void *fn = h->K == 1 ? (const void *)k_generations<RT_, 1> : h->K == 2 ? (const void *)k_generations<RT_, 2> : (const void *)k_generations<RT_, 3>; \
-      e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SWEEP_BLOCK, smem); }
-#ifdef ZZ_DEV_R16
-    ZZ_OCC(16)
-#else
-    switch (h->R) { case 2: ZZ_OCC(2) break; case 4: ZZ_OCC(4) break; case 8: ZZ_OCC(8) break; case 16: ZZ_OCC(16) break; default: ZZ_OCC(0) break; }
-#endif
-#undef ZZ_OCC
-    ZZ_CUDA(h, e);
+    ZZ_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, blk, smem));
     ZZ_CUDA(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
     if (per_sm < 1) return fail(h, ZZ_ERR_CUDA, "k_generations does not fit on an SM");
-    h->gen_blocks = per_sm * sms;
-    if (const char *e2 = getenv("ZZ_GEN_BLOCKS")) { const int n = atoi(e2); if (n >= 1 && n < h->gen_blocks) h->gen_blocks = n; }   // tests: a smaller grid
+    gen_blocks = per_sm * sms;
+    if (const char *e2 = getenv("ZZ_GEN_BLOCKS")) { const int n = atoi(e2); if (n >= 1 && n < gen_blocks) gen_blocks = n; }   // tests: a smaller grid
   }
-  const int64_t ntiles = (h->G + 31) / 32, need = (ntiles + SWEEP_BLOCK / 32 - 1) / (SWEEP_BLOCK / 32);
+  const int64_t ntiles = (h->G + 31) / 32, need = (ntiles + blk / 32 - 1) / (blk / 32);
   // one chain: one more CTA, the steward of the scalar stage (zz_persist.cuh); batched chains overlap each other's scalar stages
   // instead, the last CTA of a chain to finish its tiles runs that chain's stage
   static const int no_steward = getenv("ZZ_GEN_NO_STEWARD") ? 1 : 0;   // measurement switch
-  const int steward = (C == 1 && !no_steward && h->gen_blocks >= 2) ? 1 : 0;
-  int64_t per_chain = h->gen_blocks / C;
+  const int steward = (C == 1 && !no_steward && gen_blocks >= 2) ? 1 : 0;
+  int64_t per_chain = gen_blocks / C;
   if (per_chain < 1) return fail(h, ZZ_ERR_INVALID, "too many chains for the co-resident grid of the device-resident loop");
   if (per_chain > need + steward) per_chain = need + steward;
   GenArgs ga;
@@ -2426,18 +2428,8 @@ int launch_generations(zz_handle *h, uint64_t step0, int ngen, int tune, int hyp
   ZZ_CUDA(h, cudaMemsetAsync(h->genctl, 0, sizeof(GenCtl) * C, h->stream));
   ZZ_CUDA(h, cudaMemsetAsync(h->genacc, 0, sizeof(long long) * (size_t)C * nstat, h->stream));
   const dim3 grid((unsigned)per_chain, (unsigned)C);
-  cudaError_t e;
-#ifdef ZZ_DEV_R16
-  e = launch_generations_k<16>(h->K, grid, smem, h->stream, ga);
-#else
-  switch (h->R) {
-    case 2: e = launch_generations_k<2>(h->K, grid, smem, h->stream, ga); break;
-    case 4: e = launch_generations_k<4>(h->K, grid, smem, h->stream, ga); break;
-    case 8: e = launch_generations_k<8>(h->K, grid, smem, h->stream, ga); break;
-    case 16: e = launch_generations_k<16>(h->K, grid, smem, h->stream, ga); break;
-    default: e = launch_generations_k<0>(h->K, grid, smem, h->stream, ga); break;
-  }
-#endif
+  void *kargs[] = {&ga};
+  cudaError_t e = cudaLaunchCooperativeKernel(fn, grid, dim3(blk), kargs, smem, h->stream);
   ZZ_CUDA(h, e);
   h->launches++;
   h->caches_valid = false; h->stats_fresh = false;

@@ -1,7 +1,7 @@
 // zz_persist.cuh — k_generations: whole segments of burnin() / mcmc() generations in ONE cooperative launch (SURVEY §8 f1;
 // R/zigzagBurnin.R:64-148, R/zigzagMCMC.R:169-229).  Included by zz_gpu.cu after the sweep kernels (uses their argument structs).
 //
-// Per generation, every persistent CTA (3 per SM, co-resident by cooperative launch):
+// Per generation, every persistent CTA (one per SM, 512 or 640 threads, co-resident by cooperative launch):
 //   1. waits until the hyper-parameters of this generation are published, copies the derived constants (FastH) to shared memory;
 //   2. sweeps its 32-gene tiles: mhYg -> mhVariance_g -> allocation Gibbs -> mhSpikeAllocation as one straight-line block per
 //      tile (same arithmetic as k_sweep_fast's production tile), plus the gene's term of the pending mhP_x likelihood ratio
@@ -124,7 +124,7 @@ constexpr int SCR_PP = (SCR_PL + (int)sizeof(PreL2) + 127) / 128 * 128;
 constexpr int SCR_XCH = (SCR_PP + (int)sizeof(PrePx) + 127) / 128 * 128;     // [8 ranks][nstat] parts of the all-reduce
 constexpr int SCR_BYTES = SCR_XCH + 8 * MAX_NSTAT_P * 8;
 static_assert(MAX_NSTAT_P * 8 <= 512 && sizeof(L2Params) <= 256 && sizeof(zz_hyper) <= 1024, "stage scratch layout");
-static_assert(SCR_BYTES <= 8 * SWEEP_BLOCK * 6, "the scratch must fit in the first statistic columns (nstat >= 13 of them)");
+static_assert(SCR_BYTES <= 8 * 256 * 6, "the scratch must fit in the first statistic columns (nstat >= 13 of them, CTAs of >= 256 threads)");
 static_assert(sizeof(ChainDev) % 8 == 0 && sizeof(zz_hyper) % 8 == 0 && sizeof(FastH) % 8 == 0, "copied as 64-bit words");
 __device__ __forceinline__ StageScr stage_scr(char *scr) {
   StageScr S;
@@ -354,8 +354,12 @@ __device__ __noinline__ void spike_move_p(const FastH &H, const MathTabs &T, con
   o.finite_state = isfinite(y) && isfinite(v);
 }
 
-template <int RT, int KT>
-__global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(const __grid_constant__ GenArgs ga) {
+// BLK threads per CTA, ONE CTA per SM (co-resident by cooperative launch).  Measured at 1 M x 16 (profiles/r2_summary.md): 3 CTAs x 256
+// threads at 80 registers 66.0 us per sweep; 1 x 768 (the same 24 warps, a third of the CTAs) 62.4; 1 x 512 at 128 registers 60.2;
+// 1 x 640 at 96 registers 58.7; 576, 608, 672, 704 in between or worse.  Fewer, fatter warps win: a 32-gene tile takes a warp 7 us
+// at 80 registers and ~4 us at 128, so rounds are finer and the tail shorter; 512 is best for shards up to ~0.5 M genes, 640 above.
+template <int RT, int KT, int BLK>
+__global__ void __launch_bounds__(BLK, 1) k_generations(const __grid_constant__ GenArgs ga) {
   __shared__ FastH H;
   __shared__ MathTabs T;
   __shared__ unsigned sh_rel, sh_ticket, sh_qdone;
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
   long long *acc = reinterpret_cast<long long *>(dyn_smem);
   GenCtl *ctl = ga.ctl + chain;
   long long *gacc = ga.acc + (int64_t)chain * nstat;
-  for (int s = 0; s < nstat; ++s) acc[s * SWEEP_BLOCK + threadIdx.x] = 0;
+  for (int s = 0; s < nstat; ++s) acc[s * BLK + threadIdx.x] = 0;
   load_tabs(T, fa.exp_tab, fa.log_tab);
   // steward mode (one chain): the LAST CTA sweeps no tiles — it keeps the chain's scalar state in its shared memory for the whole
   // launch, prepares everything of the coming scalar stage that needs no statistics while the others sweep, and counts tickets
@@ -378,8 +382,8 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
     return;
   }
   const int ntiles = (int)((a.g_end - a.g_begin + 31) / 32);
-  const int warp0 = (int)blockIdx.x * (SWEEP_BLOCK / 32) + wid, nwarps = (int)n_cta * (SWEEP_BLOCK / 32);
-  double *stg = dyn_smem + (int64_t)nstat * SWEEP_BLOCK + wid * 320 + lane;
+  const int warp0 = (int)blockIdx.x * (BLK / 32) + wid, nwarps = (int)n_cta * (BLK / 32);
+  double *stg = dyn_smem + (int64_t)nstat * BLK + wid * 320 + lane;
   bool saw_nan = false;
   const uint64_t pol = l2_evict_first_policy();
 
@@ -578,17 +582,17 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
         const int comp = act ? flag_k(f) : 0;                               // Pr:415 all_allocations
         ZZ_DEV_ASSERT(comp >= 0 && comp <= a.K && kn >= 1 && kn <= KT && gid - (uint64_t)a.gene_offset < (uint64_t)a.G);
         const long long fy = to_fx(ys), fy2 = to_fx(ys * ys);
-        col[comp * SWEEP_BLOCK] += FX_ONE;
-        if (act || !sp) { col[(K1 + comp) * SWEEP_BLOCK] += fy; col[(2 * K1 + comp) * SWEEP_BLOCK] += fy2; }
-        long long *q = col + 3 * K1 * SWEEP_BLOCK;
+        col[comp * BLK] += FX_ONE;
+        if (act || !sp) { col[(K1 + comp) * BLK] += fy; col[(2 * K1 + comp) * BLK] += fy2; }
+        long long *q = col + 3 * K1 * BLK;
         if (sp) q[0] += FX_ONE;
         else {
-          q[1 * SWEEP_BLOCK] += FX_ONE; q[2 * SWEEP_BLOCK] += to_fx(lvs); q[3 * SWEEP_BLOCK] += to_fx(lvs * lvs); q[4 * SWEEP_BLOCK] += fy;
-          q[5 * SWEEP_BLOCK] += fy2; q[6 * SWEEP_BLOCK] += to_fx(ys * lvs);
-          if (px_on) q[FXS_PXDELTA * SWEEP_BLOCK] += to_fx(pxd);
+          q[1 * BLK] += FX_ONE; q[2 * BLK] += to_fx(lvs); q[3 * BLK] += to_fx(lvs * lvs); q[4 * BLK] += fy;
+          q[5 * BLK] += fy2; q[6 * BLK] += to_fx(ys * lvs);
+          if (px_on) q[FXS_PXDELTA * BLK] += to_fx(pxd);
         }
-        if (pxbad) q[FXS_PXBAD * SWEEP_BLOCK] += FX_ONE;
-        if (!finite_state) q[9 * SWEEP_BLOCK] += FX_ONE;
+        if (pxbad) q[FXS_PXBAD * BLK] += FX_ONE;
+        if (!finite_state) q[9 * BLK] += FX_ONE;
       }
       }   // valid
       int t_nn = -1;
@@ -615,10 +619,10 @@ __global__ void __launch_bounds__(SWEEP_BLOCK, ZZ_SWEEP_MINB) k_generations(cons
     // ---- 3. the CTA's column sums -> the chain's accumulators (integer atomics: order-free)
     __syncthreads();
     ZZ_TRACE(2);
-    for (int s = wid; s < nstat; s += SWEEP_BLOCK / 32) {
+    for (int s = wid; s < nstat; s += BLK / 32) {
       long long v = 0;
 #pragma unroll
-      for (int j = 0; j < SWEEP_BLOCK / 32; ++j) { v += acc[s * SWEEP_BLOCK + j * 32 + lane]; acc[s * SWEEP_BLOCK + j * 32 + lane] = 0; }
+      for (int j = 0; j < BLK / 32; ++j) { v += acc[s * BLK + j * 32 + lane]; acc[s * BLK + j * 32 + lane] = 0; }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == 0 && v != 0) atomicAdd(reinterpret_cast<unsigned long long *>(gacc + s), (unsigned long long)v);
