@@ -1240,7 +1240,7 @@ struct zz_handle {
   bool sink_on; zz_sample_sink sink; double *sink_p, *sink_y, *sink_v; int32_t *cand_slots; int64_t sink_prow, sink_yrow;   // zz_set_sample_sink
   bool hyper_host_stale;                   // zz_run_generations moved the hyper-parameters on the device; hyper_host is refreshed by zz_chain_read
   ChainDev *devchain; double *chain_stats; bool chain_ready; int64_t chain_gen, chain_samples; uint64_t chain_step;   // zz_run_generations
-  double *dlt; GenCtl *genctl; long long *genacc; int gen_blocks, gen_blocks_l;   // k_generations: per-gene mhP_x terms, grid-barrier words, fixed-point totals
+  double *dlt; GenCtl *genctl; long long *genacc; int gen_blocks, gen_blocks_l, gen_blocks_c;   // k_generations: per-gene mhP_x terms, grid-barrier words, fixed-point totals
   bool caches_valid;                       // XgLikelihood / variance_g_probability are current (device-resident segments do not maintain them)
   int32_t *inv_perm; cudaStream_t s_up, s_down; cudaEvent_t ev_entry, ev_up[ZZ_HOST_MAX_CHUNKS], ev_done[ZZ_HOST_MAX_CHUNKS]; bool pipe_ready;
 };
@@ -1623,7 +1623,7 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   h->sink_on = false; h->cand_slots = nullptr; h->sink_prow = h->sink_yrow = 0;
   h->hyper_host_stale = false;
   h->devchain = nullptr; h->chain_stats = nullptr; h->chain_ready = false; h->chain_gen = 0; h->chain_samples = 0; h->chain_step = 0;
-  h->dlt = nullptr; h->genctl = nullptr; h->genacc = nullptr; h->gen_blocks = 0; h->gen_blocks_l = 0; h->caches_valid = true;
+  h->dlt = nullptr; h->genctl = nullptr; h->genacc = nullptr; h->gen_blocks = 0; h->gen_blocks_l = 0; h->gen_blocks_c = 0; h->caches_valid = true;
   *out = h;  // returned even on failure so the caller can read zz_last_error and must zz_destroy
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -2333,7 +2333,10 @@ int zz_chain_begin(zz_handle *h, const zz_priors *priors, const zz_chain_scalars
 namespace {
 
 // the two CTA shapes of k_generations (see the kernel): 512 threads for shards up to GEN_LARGE_MIN genes and for batched chains, 640 above
-constexpr int GEN_BLK_S = SWEEP_BLOCK, GEN_BLK_L = 640;
+// CTA shapes of k_generations (profiles/r2_summary.md): one CTA per SM of 512 threads (128 registers), of 640 threads (96 registers)
+// for one chain over a large shard, and three CTAs per SM of 256 threads (80 registers) for whole generations of batched chains,
+// whose scalar stages then overlap other chains' tiles on the same SM
+constexpr int GEN_BLK_S = SWEEP_BLOCK, GEN_BLK_L = 640, GEN_BLK_C = 256;
 template <int RT, int BLK> const void *generations_fn(int K) {
   switch (K) {
     case 1: return (const void *)k_generations<RT, 1, BLK>;
@@ -2344,9 +2347,9 @@ template <int RT, int BLK> const void *generations_fn(int K) {
 }
 const void *generations_fn(int R, int K, int blk) {
 #ifdef ZZ_DEV_R16
-  return blk == GEN_BLK_L ? generations_fn<16, GEN_BLK_L>(K) : generations_fn<16, GEN_BLK_S>(K);
+  return blk == GEN_BLK_L ? generations_fn<16, GEN_BLK_L>(K) : blk == GEN_BLK_C ? generations_fn<16, GEN_BLK_C>(K) : generations_fn<16, GEN_BLK_S>(K);
 #else
-#define ZZ_GEN_FN(RT_) (blk == GEN_BLK_L ? generations_fn<RT_, GEN_BLK_L>(K) : generations_fn<RT_, GEN_BLK_S>(K))
+#define ZZ_GEN_FN(RT_) (blk == GEN_BLK_L ? generations_fn<RT_, GEN_BLK_L>(K) : blk == GEN_BLK_C ? generations_fn<RT_, GEN_BLK_C>(K) : generations_fn<RT_, GEN_BLK_S>(K))
   switch (R) { case 2: return ZZ_GEN_FN(2); case 4: return ZZ_GEN_FN(4); case 8: return ZZ_GEN_FN(8); case 16: return ZZ_GEN_FN(16); default: return ZZ_GEN_FN(0); }
 #undef ZZ_GEN_FN
 #endif
@@ -2374,12 +2377,13 @@ int launch_generations(zz_handle *h, uint64_t step0, int ngen, int tune, int hyp
   }
   if (int rc = ensure_lps(h)) return rc;
   static const int64_t large_min = getenv("ZZ_GEN_LARGE_MIN") ? atoll(getenv("ZZ_GEN_LARGE_MIN")) : 700000;
-  const int blk = (C == 1 && h->G >= large_min) ? GEN_BLK_L : GEN_BLK_S;
+  static const int no_blk_c = getenv("ZZ_GEN_NO_BLK_C") ? 1 : 0;   // measurement switch
+  const int blk = (C == 1 && h->G >= large_min) ? GEN_BLK_L : (C > 1 && hyper_moves && !no_blk_c && GEN_BLK_C != GEN_BLK_S) ? GEN_BLK_C : GEN_BLK_S;
   const size_t smem = sizeof(double) * (nstat + 10) * blk;
   const void *fn = generations_fn(h->R, h->K, blk);
   if (!fn) return fail(h, ZZ_ERR_INVALID, "k_generations: more than 3 active components");
   ZZ_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int &gen_blocks = blk == GEN_BLK_L ? h->gen_blocks_l : h->gen_blocks;
+  int &gen_blocks = blk == GEN_BLK_L ? h->gen_blocks_l : blk == GEN_BLK_C ? h->gen_blocks_c : h->gen_blocks;
   if (gen_blocks == 0) {    // co-resident CTAs of k_generations (cooperative launch): from the occupancy calculator
     int per_sm = 0, sms = 0;
     ZZ_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, blk, smem));
@@ -2395,7 +2399,8 @@ int launch_generations(zz_handle *h, uint64_t step0, int ngen, int tune, int hyp
   const int steward = (C == 1 && !no_steward && gen_blocks >= 2) ? 1 : 0;
   int64_t per_chain = gen_blocks / C;
   if (per_chain < 1) return fail(h, ZZ_ERR_INVALID, "too many chains for the co-resident grid of the device-resident loop");
-  if (per_chain > need + steward) per_chain = need + steward;
+  (void)need;
+  if (per_chain > ntiles + steward) per_chain = ntiles + steward;   // never more worker CTAs than tiles (tiles are dealt CTA-minor)
   GenArgs ga;
   memset(&ga, 0, sizeof ga);
   const double *no_draws[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -359,7 +359,7 @@ __device__ __noinline__ void spike_move_p(const FastH &H, const MathTabs &T, con
 // 1 x 640 at 96 registers 58.7; 576, 608, 672, 704 in between or worse.  Fewer, fatter warps win: a 32-gene tile takes a warp 7 us
 // at 80 registers and ~4 us at 128, so rounds are finer and the tail shorter; 512 is best for shards up to ~0.5 M genes, 640 above.
 template <int RT, int KT, int BLK>
-__global__ void __launch_bounds__(BLK, 1) k_generations(const __grid_constant__ GenArgs ga) {
+__global__ void __launch_bounds__(BLK, BLK <= 256 ? 3 : 1) k_generations(const __grid_constant__ GenArgs ga) {
   __shared__ FastH H;
   __shared__ MathTabs T;
   __shared__ unsigned sh_rel, sh_ticket, sh_qdone;
@@ -382,7 +382,9 @@ __global__ void __launch_bounds__(BLK, 1) k_generations(const __grid_constant__ 
     return;
   }
   const int ntiles = (int)((a.g_end - a.g_begin + 31) / 32);
-  const int warp0 = (int)blockIdx.x * (BLK / 32) + wid, nwarps = (int)n_cta * (BLK / 32);
+  // warp w of CTA b is global warp w * n_cta + b: consecutive tiles go to DIFFERENT CTAs, so a sweep with fewer tiles than warps
+  // spreads over all SMs instead of filling the first CTAs (a tile runs faster the fewer warps share its SM)
+  const int warp0 = wid * (int)n_cta + (int)blockIdx.x, nwarps = (int)n_cta * (BLK / 32);
   double *stg = dyn_smem + (int64_t)nstat * BLK + wid * 320 + lane;
   bool saw_nan = false;
   const uint64_t pol = l2_evict_first_policy();
