@@ -530,7 +530,7 @@ def main():
     achieved = G * chains * balg / (sweep_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1:   # the captures are of the one-GPU launch; a shard's launch moves less and was not captured
         try:
             with open(tp) as f:
                 traffic = json.load(f).get(("k_generations:" if persistent else "k_sweep:") + args.workload)
