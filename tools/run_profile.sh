@@ -1,3 +1,4 @@
+# how profiles/r2_bench_n1_*.json, r2_launches.csv and r2_kgen_raw.csv were produced: gpurun -- 'bash tools/run_profile.sh'
 mkdir -p gpurun_out
 python bench.py > gpurun_out/r2f_n1_1m_x16.out 2> gpurun_out/r2f_n1_1m_x16.err; echo rc=$?; tail -1 gpurun_out/r2f_n1_1m_x16.out > gpurun_out/r2f_n1_1m_x16.json
 for w in 200k_x8 20k_x2 64ch_60k_x4; do python bench.py --workload $w > gpurun_out/r2f_n1_$w.out 2> gpurun_out/r2f_n1_$w.err; echo rc=$?; tail -1 gpurun_out/r2f_n1_$w.out > gpurun_out/r2f_n1_$w.json; done

@@ -1,3 +1,4 @@
+# how profiles/r2_bench_n2/4/8*.json were produced: gpurun --gpus 8 -- 'bash tools/run_scaling.sh'
 set -x
 mkdir -p gpurun_out
 python -m pytest tests/test_multi_gpu.py -m gpu -q -x 2>&1 | tail -2 > gpurun_out/r2s_multigpu_test.log; cat gpurun_out/r2s_multigpu_test.log
