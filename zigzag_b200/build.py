@@ -12,7 +12,7 @@ OUT = os.environ.get("ZZ_BUILD_OUT", os.path.join(HERE, "libzigzag_gpu.so"))   #
 
 # -fmad=false: the kernels keep the reference's operation order (a*b+c is not contracted), see DESIGN.md "Numerics"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
-              "--shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
+              "--shared", "-Xcompiler", "-fPIC,-pthread", "-cudart", "static"]
 
 
 def nvcc():

@@ -17,6 +17,7 @@
 #include <vector>
 #include <new>
 #include <algorithm>
+#include <thread>
 #include "zz_device.cuh"
 #include "zz_fast.cuh"
 #include "zz_chain.cuh"
@@ -1235,6 +1236,8 @@ struct zz_handle {
   bool lps_valid;                          // lps == A(current Yg, alpha_r) for every out-of-spike gene
   std::vector<zz_hyper> hyper_host;
   double *pinned;                          // small pinned staging for reduction results
+  char *bounce; size_t bounce_cap;         // pinned bounce region for state downloads into pageable caller memory (zz_get_state)
+  cudaEvent_t bounce_ev[9]; bool bounce_ev_ok;
   // zz_sweep_host pipeline (created on first use)
   void *pp_buf; int pp_nb;                 // zz_post_predictive: histograms + bins on the device
   bool sink_on; zz_sample_sink sink; double *sink_p, *sink_y, *sink_v; int32_t *cand_slots; int64_t sink_prow, sink_yrow;   // zz_set_sample_sink
@@ -1623,7 +1626,7 @@ int zz_create(const zz_config *cfg, zz_handle **out) {
   h->sink_on = false; h->cand_slots = nullptr; h->sink_prow = h->sink_yrow = 0;
   h->hyper_host_stale = false;
   h->devchain = nullptr; h->chain_stats = nullptr; h->chain_ready = false; h->chain_gen = 0; h->chain_samples = 0; h->chain_step = 0;
-  h->dlt = nullptr; h->genctl = nullptr; h->genacc = nullptr; h->gen_blocks = 0; h->gen_blocks_l = 0; h->gen_blocks_c = 0; h->caches_valid = true;
+  h->dlt = nullptr; h->genctl = nullptr; h->genacc = nullptr; h->gen_blocks = 0; h->gen_blocks_l = 0; h->gen_blocks_c = 0; h->bounce = nullptr; h->bounce_cap = 0; h->bounce_ev_ok = false; h->caches_valid = true;
   *out = h;  // returned even on failure so the caller can read zz_last_error and must zz_destroy
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1704,6 +1707,8 @@ void zz_destroy(zz_handle *h) {
                   h->log_tab, h->perm, h->stage, h->nd_mask, h->xbar, h->xss, h->tile_counter, h->sw_partials, h->fasth};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->bounce) cudaFreeHost(h->bounce);
+  if (h->bounce_ev_ok) for (cudaEvent_t e : h->bounce_ev) cudaEventDestroy(e);
   if (h->inv_perm) cudaFree(h->inv_perm);
   if (h->devchain) cudaFree(h->devchain);
   if (h->cand_slots) cudaFree(h->cand_slots);
@@ -1817,14 +1822,68 @@ int zz_get_state(zz_handle *h, int chain, double *Yg, double *variance_g, int32_
   const int64_t G = h->G, off = (int64_t)chain * G;
   int rc;
   if ((XgLikelihood || variance_g_probability) && (rc = ensure_caches(h))) return rc;
-  if ((rc = down_g(h, Yg, h->Yg + off, G)) || (rc = down_g(h, variance_g, h->vg + off, G)) || (rc = down_g(h, XgLikelihood, h->xglik + off, G)) ||
-      (rc = down_g(h, variance_g_probability, h->vgprob + off, G)) || (rc = down_g(h, ty, h->ty + off, G)) || (rc = down_g(h, tv, h->tv + off, G)))
-    return rc;
+  // Every requested array is scattered into the caller's gene order in its own part of the device staging buffer and copied down
+  // asynchronously.  A destination in pinned memory receives the copy directly.  A PAGEABLE destination (an R vector, a NumPy
+  // array) would make the driver stage the copy at ~6 GB/s: those land in a pinned bounce region of the handle at PCIe speed and are
+  // copied out (and their fresh pages faulted in) by four host threads while the following arrays are still in flight.
+  struct Out { void *dst; const void *dev; size_t bytes, boff; bool direct; };
+  Out outs[9];
+  int n_out = 0;
+  size_t need = 0;
+  double *st = h->stage;                                             // 9 * C * G doubles
+  const double *src8[6] = {h->Yg + off, h->vg + off, h->xglik + off, h->vgprob + off, h->ty + off, h->tv + off};
+  double *dst8[6] = {Yg, variance_g, XgLikelihood, variance_g_probability, ty, tv};
+  auto is_pinned = [](const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  for (int j = 0; j < 6; ++j) {
+    if (!dst8[j]) continue;
+    double *part = st + (int64_t)j * G;
+    k_scatter<double><<<dim3((unsigned)((G + BLOCK - 1) / BLOCK), 1), BLOCK, 0, h->stream>>>(G, h->perm, src8[j], part);
+    ZZ_LAUNCHED(h);
+    outs[n_out++] = Out{dst8[j], part, sizeof(double) * (size_t)G, 0, is_pinned(dst8[j])};
+  }
   if (ai || within || spike) {
     int32_t *d_ai = h->iscratch, *d_w = h->iscratch + G, *d_s = h->iscratch + 2 * G;
     k_unpack_flags<<<gene_grid(h, G), BLOCK, 0, h->stream>>>(G, h->perm, h->flags + off, d_ai, d_w, d_s);
     ZZ_LAUNCHED(h);
-    if ((rc = down(h, ai, d_ai, G)) || (rc = down(h, within, d_w, G)) || (rc = down(h, spike, d_s, G))) return rc;
+    int32_t *dsti[3] = {ai, within, spike}, *srci[3] = {d_ai, d_w, d_s};
+    for (int j = 0; j < 3; ++j) if (dsti[j]) outs[n_out++] = Out{dsti[j], srci[j], sizeof(int32_t) * (size_t)G, 0, is_pinned(dsti[j])};
+  }
+  for (int j = 0; j < n_out; ++j) if (!outs[j].direct) { outs[j].boff = need; need += (outs[j].bytes + 255) & ~(size_t)255; }
+  if (need > h->bounce_cap) {
+    if (h->bounce) { ZZ_CUDA(h, cudaStreamSynchronize(h->stream)); cudaFreeHost(h->bounce); h->bounce = nullptr; h->bounce_cap = 0; }
+    ZZ_CUDA(h, cudaHostAlloc(reinterpret_cast<void **>(&h->bounce), need, cudaHostAllocDefault));
+    h->bounce_cap = need;
+  }
+  if (need && !h->bounce_ev_ok) {
+    for (cudaEvent_t &e : h->bounce_ev) ZZ_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->bounce_ev_ok = true;
+  }
+  for (int j = 0; j < n_out; ++j) {
+    void *to = outs[j].direct ? outs[j].dst : static_cast<void *>(h->bounce + outs[j].boff);
+    ZZ_CUDA(h, cudaMemcpyAsync(to, outs[j].dev, outs[j].bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (!outs[j].direct) ZZ_CUDA(h, cudaEventRecord(h->bounce_ev[j], h->stream));
+  }
+  for (int j = 0; j < n_out; ++j) {
+    if (outs[j].direct) continue;
+    ZZ_CUDA(h, cudaEventSynchronize(h->bounce_ev[j]));
+    const char *from = h->bounce + outs[j].boff;
+    char *to = static_cast<char *>(outs[j].dst);
+    const size_t n = outs[j].bytes;
+    static const int nt_env = getenv("ZZ_HOST_COPY_THREADS") ? atoi(getenv("ZZ_HOST_COPY_THREADS")) : 4;
+    const int nt = n >= ((size_t)2 << 20) ? std::max(1, std::min(nt_env, 16)) : 1;   // host threads per array
+    if (nt == 1) { memcpy(to, from, n); continue; }
+    const size_t per = ((n / nt) + 4095) & ~(size_t)4095;
+    std::thread th[15];
+    for (int t = 1; t < nt; ++t) {
+      const size_t b = per * t, e = std::min(n, per * (t + 1));
+      if (b < e) th[t - 1] = std::thread([=] { memcpy(to + b, from + b, e - b); });
+    }
+    memcpy(to, from, std::min(n, per));
+    for (std::thread &t : th) if (t.joinable()) t.join();
   }
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
   return ZZ_OK;
