@@ -99,6 +99,8 @@ int zz_set_state(zz_handle *h, int chain, const double *Yg, const double *varian
                  const int32_t *alloc_within_active, const int32_t *inactive_spike_allocation, const double *XgLikelihood,
                  const double *variance_g_probability, const double *tuningParam_yg, const double *tuningParam_variance_g,
                  const int32_t *pinned_active);
+/* zz_get_state: any pointer may be NULL (that field is skipped).  Destinations may be pageable (R vectors, NumPy arrays) or pinned:
+   pageable ones are filled through a pinned bounce region of the handle by ZZ_HOST_COPY_THREADS host threads (default 4). */
 int zz_get_state(zz_handle *h, int chain, double *Yg, double *variance_g, int32_t *alloc_active_inactive,
                  int32_t *alloc_within_active, int32_t *inactive_spike_allocation, double *XgLikelihood,
                  double *variance_g_probability, double *tuningParam_yg, double *tuningParam_variance_g);

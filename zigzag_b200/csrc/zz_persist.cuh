@@ -354,10 +354,12 @@ __device__ __noinline__ void spike_move_p(const FastH &H, const MathTabs &T, con
   o.finite_state = isfinite(y) && isfinite(v);
 }
 
-// BLK threads per CTA, ONE CTA per SM (co-resident by cooperative launch).  Measured at 1 M x 16 (profiles/r2_summary.md): 3 CTAs x 256
-// threads at 80 registers 66.0 us per sweep; 1 x 768 (the same 24 warps, a third of the CTAs) 62.4; 1 x 512 at 128 registers 60.2;
-// 1 x 640 at 96 registers 58.7; 576, 608, 672, 704 in between or worse.  Fewer, fatter warps win: a 32-gene tile takes a warp 7 us
-// at 80 registers and ~4 us at 128, so rounds are finer and the tail shorter; 512 is best for shards up to ~0.5 M genes, 640 above.
+// BLK threads per CTA (co-resident by cooperative launch).  Measured at 1 M x 16 (profiles/r2_summary.md): 3 CTAs x 256 threads at
+// 80 registers 66.0 us per sweep; 1 x 768 (the same 24 warps, a third of the CTAs) 62.4; 1 x 512 at 128 registers 60.2; 1 x 640 at
+// 96 registers 58.7; 576, 608, 672, 704 in between or worse.  Fewer, fatter warps win: a 32-gene tile takes a warp 7 us at 80
+// registers and ~5 us at 96-128, so rounds are finer and the tail shorter.  launch_generations picks 640 for one chain over a
+// large shard, 512 otherwise, and 3 x 256 for whole generations of batched chains (another chain's tiles fill the SM while the
+// last CTA of a chain runs its scalar stage).  Results do not depend on the shape.
 template <int RT, int KT, int BLK>
 __global__ void __launch_bounds__(BLK, BLK <= 256 ? 3 : 1) k_generations(const __grid_constant__ GenArgs ga) {
   __shared__ FastH H;
