@@ -500,24 +500,28 @@ def main():
             # gpu_pull at the sample point, R/zigzagMCMC.R:194-217) — sample_frequency generations on the device, then the WHOLE mutable
             # state (52 B per gene), the hyper-parameters and the allocation-trace update, into pageable host arrays through the C ABI
             if chains_cfg == 1:
-                sf, n_int = 100, 3                    # the reference's default sample_frequency (R/zigzagBurnin.R:21)
-                h.run_generations(sf, tune=False, sample_frequency=sf); h.get_state(0); torch.cuda.synchronize()
-                if world > 1:
-                    dist.barrier()
-                t0 = time.perf_counter()
-                for _ in range(n_int):
-                    h.run_generations(sf, tune=False, sample_frequency=sf)
-                    h.accumulate_alloc_trace()
-                    pulled = h.get_state(0)
-                    h.get_hyper(0)
-                dt = maxr([time.perf_counter() - t0])[0]
-                chain["e2e_sampling_interval"] = {
-                    "value": G_tot * sf * n_int / dt, "unit": UNIT, "sample_frequency": sf, "intervals": n_int, "us_per_generation": dt / (sf * n_int) * 1e6,
-                    "d2h_bytes_per_interval": int(sum(v.nbytes for v in pulled.values())) * (world if not shard_chains else 1),
-                    "what": "wall clock (max over ranks) of 3 sampling intervals: 100 device-resident generations (zz_run_generations), then "
-                            "zz_accumulate_alloc_trace + zz_get_state of every per-gene field + zz_get_hyper into pageable host arrays — what the "
-                            "R drop-in does per sample; the state never goes up again because it lives on the device between samples"}
-                del pulled
+                try:
+                    sf, n_int = 100, 3                    # the reference's default sample_frequency (R/zigzagBurnin.R:21)
+                    h.run_generations(sf, tune=False, sample_frequency=sf); h.get_state(0); torch.cuda.synchronize()
+                    if world > 1:
+                        dist.barrier()
+                    t0 = time.perf_counter()
+                    for _ in range(n_int):
+                        h.run_generations(sf, tune=False, sample_frequency=sf)
+                        h.accumulate_alloc_trace()
+                        pulled = h.get_state(0)
+                        h.get_hyper(0)
+                    dt = maxr([time.perf_counter() - t0])[0]
+                    chain["e2e_sampling_interval"] = {
+                        "value": G_tot * sf * n_int / dt, "unit": UNIT, "sample_frequency": sf, "intervals": n_int,
+                        "us_per_generation": dt / (sf * n_int) * 1e6,
+                        "d2h_bytes_per_interval": int(sum(v.nbytes for v in pulled.values())) * world,
+                        "what": "wall clock (max over ranks) of 3 sampling intervals: 100 device-resident generations (zz_run_generations), then "
+                                "zz_accumulate_alloc_trace + zz_get_state of every per-gene field + zz_get_hyper into pageable host arrays — what the "
+                                "R drop-in does per sample; the state never goes up again because it lives on the device between samples"}
+                    del pulled
+                except Exception as e:
+                    chain["e2e_sampling_interval"] = {"error": repr(e)[:200]}
             chain["nan_flag"] = h.nan_flag()
         except Exception as e:      # never let the informational leg break the contract line
             chain = {"error": repr(e)[:200]}
