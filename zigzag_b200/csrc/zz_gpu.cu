@@ -1878,11 +1878,14 @@ int zz_get_state(zz_handle *h, int chain, double *Yg, double *variance_g, int32_
     if (nt == 1) { memcpy(to, from, n); continue; }
     const size_t per = ((n / nt) + 4095) & ~(size_t)4095;
     std::thread th[15];
+    size_t done_to = std::min(n, per);                              // this thread's own part; grows if a helper cannot be started
     for (int t = 1; t < nt; ++t) {
       const size_t b = per * t, e = std::min(n, per * (t + 1));
-      if (b < e) th[t - 1] = std::thread([=] { memcpy(to + b, from + b, e - b); });
+      if (b >= e) break;
+      try { th[t - 1] = std::thread([=] { memcpy(to + b, from + b, e - b); }); }
+      catch (...) { memcpy(to + b, from + b, e - b); }               // no thread to be had (resource limits): copy that part here
     }
-    memcpy(to, from, std::min(n, per));
+    memcpy(to, from, done_to);
     for (std::thread &t : th) if (t.joinable()) t.join();
   }
   ZZ_CUDA(h, cudaStreamSynchronize(h->stream));
