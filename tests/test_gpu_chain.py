@@ -80,6 +80,18 @@ def test_device_resident_generations_match_the_oracle_chain(G, R, K, thr_a):
     assert np.array_equal(h.get_alloc_trace(0), ch.alloc_trace(K))
 
 
+@pytest.mark.parametrize("G,R,K,thr_a", [(1, 2, 2, (1.0, 6.0)), (7, 3, 1, (1.0,)), (33, 4, 2, (1.0, 6.0)), (64, 16, 2, (1.0, 6.0)), (97, 8, 3, (0.5, 3.0, 6.0))])
+def test_device_resident_generations_on_tiny_gene_sets(G, R, K, thr_a):
+    """Fewer tiles than warps, down to one gene: the grid shrinks to one worker CTA per tile (+ the steward), most lanes of the only
+    tile are idle, every queue is empty from the start.  Same comparison with the CPU chain as above."""
+    ch, h = _start_pair(G, R, K, 17, thr_a)
+    ch.run_fused(40, tune=True); h.run_generations(40, tune=True)
+    _compare(ch, h, K, R)
+    ch.run_fused(12, sample_frequency=3, tune=False); h.run_generations(12, tune=False, sample_frequency=3)
+    _compare(ch, h, K, R)
+    assert np.array_equal(h.get_alloc_trace(0), ch.alloc_trace(K))
+
+
 def test_device_resident_generations_on_a_small_grid(monkeypatch):
     """The same comparison with 2 CTAs (16 warps) for 94 tiles: several tiles per warp, two static rounds and then the dynamic
     tile queues — the paths a 1 M-gene shard takes on the full grid."""
