@@ -360,18 +360,6 @@ __device__ __noinline__ void spike_move_p(const FastH &H, const MathTabs &T, con
 // registers and ~5 us at 96-128, so rounds are finer and the tail shorter.  launch_generations picks 640 for one chain over a
 // large shard, 512 otherwise, and 3 x 256 for whole generations of batched chains (another chain's tiles fill the SM while the
 // last CTA of a chain runs its scalar stage).  Results do not depend on the shape.
-// The per-gene words that are NOT staged through shared memory — the two 100-wide accept windows (when tuning) and the pending mhP_x
-// increment (when the previous proposal was accepted) — are asked for one tile ahead as well.  With them a generation's footprint
-// (122 B per gene at 1 M genes) no longer stays in L2 (ncu: 136 MB of DRAM traffic per burn-in generation against 17 MB per
-// frozen-parameter sweep), so the read-modify-write of the windows would otherwise wait for DRAM.  Worth 0.7 us of a 75.9 us burn-in
-// generation at 1 M x 16 and 2.4 of 264 us for 64 batched chains.  The lines are only touched by this warp within a generation and
-// every generation begins with an acquire that orders the previous owner's stores before these loads.
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_tile_extras(const SweepArgs &a, const GenArgs &ga, const FastH &H, int64_t i) {
-  if (a.tune) { prefetch_l1(a.win_y + i); prefetch_l1(a.win_v + i); }
-  if (H.px_prev_acc) prefetch_l1(ga.dlt + i);
-}
-
 template <int RT, int KT, int BLK>
 __global__ void __launch_bounds__(BLK, BLK <= 256 ? 3 : 1) k_generations(const __grid_constant__ GenArgs ga) {
   __shared__ FastH H;
@@ -459,7 +447,7 @@ __global__ void __launch_bounds__(BLK, BLK <= 256 ? 3 : 1) k_generations(const _
     if (ask_first && lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(&ctl->tile_q[tq * 32]) : "memory");
     if (t_ >= 0) {
       const int64_t g0 = a.g_begin + (int64_t)(ntiles - 1 - t_) * 32 + lane;
-      if (g0 < a.g_end) { stage_tile_ef(a, fa, chain, g0, stg, pol); prefetch_tile_extras(a, ga, H, (int64_t)chain * a.G + g0); f_next = a.flags[(int64_t)chain * a.G + g0]; }
+      if (g0 < a.g_end) { stage_tile_ef(a, fa, chain, g0, stg, pol); f_next = a.flags[(int64_t)chain * a.G + g0]; }
     }
     if (ask_first) {
       const unsigned tk = __shfl_sync(0xffffffffu, ticket, 0);
@@ -489,7 +477,7 @@ __global__ void __launch_bounds__(BLK, BLK <= 256 ? 3 : 1) k_generations(const _
       }
       // every staged word of this tile is in registers: refill the slots with the warp's next tile, whose HBM latency then hides
       // behind this tile's ~1300 instructions (also for the lanes beyond the end of a ragged tile: their next tile is a full one)
-      if (next_valid) { stage_tile_ef(a, fa, chain, g_n, stg, pol); prefetch_tile_extras(a, ga, H, (int64_t)chain * a.G + g_n); }
+      if (next_valid) stage_tile_ef(a, fa, chain, g_n, stg, pol);
       asm volatile("cp.async.commit_group;" ::: "memory");
       // the tile after the next one: ask the home queue now, read the answer when this tile is done
       // (inline asm: the compiler would otherwise sink the atomic down to the shuffle that reads it and expose its whole latency)
@@ -557,8 +545,8 @@ __global__ void __launch_bounds__(BLK, BLK <= 256 ? 3 : 1) k_generations(const _
       a.flags[i] = (uint16_t)f;
       if (live) { __stcs(a.Yg + i, y1); __stcs(a.vg + i, v1); __stcs(fa.lps + i, A1); }   // streaming stores (L2 evict-first)
       if (a.tune && live) {                                              // Pr:312-322, Pr:40-50
-        ulonglong2 w = a.win_y[i]; window_push(w, acc_y); __stcs(a.win_y + i, w);   // prefetched into L1 one tile ahead
-        w = a.win_v[i]; window_push(w, acc_v); __stcs(a.win_v + i, w);
+        ulonglong2 w = __ldcs(a.win_y + i); window_push(w, acc_y); __stcs(a.win_y + i, w);
+        w = __ldcs(a.win_v + i); window_push(w, acc_v); __stcs(a.win_v + i, w);
       }
       saw_nan |= live && (isnan(ratio_y) || isnan(ratio_v) || bad);
       double ys = y1, lvs = lv1;
