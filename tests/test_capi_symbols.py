@@ -57,3 +57,11 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "libzzoracle" not in txt and "zz_oracle" not in txt, f
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_the_library_is_not_older_than_its_sources():
+    """A failed nvcc run leaves the previous library in place and every later measurement silently uses it: the CPU suite (which
+    the driver runs right after build()) refuses a library that is older than any file of csrc/ or the ABI header."""
+    from zigzag_b200 import build as zb
+    assert os.path.exists(zb.OUT), "build the library first: python -m zigzag_b200.build"
+    assert not zb.needs_build(), "zigzag_b200/libzigzag_gpu.so is older than its sources: the last build failed or was not run"
