@@ -360,6 +360,16 @@ __device__ __noinline__ void spike_move_p(const FastH &H, const MathTabs &T, con
 // registers and ~5 us at 96-128, so rounds are finer and the tail shorter.  launch_generations picks 640 for one chain over a
 // large shard, 512 otherwise, and 3 x 256 for whole generations of batched chains (another chain's tiles fill the SM while the
 // last CTA of a chain runs its scalar stage).  Results do not depend on the shape.
+// The 256-thread shape only ever runs tuning generations (launch_generations): there the two accept windows, which are read where the
+// tuning decision falls and come from DRAM (a burn-in generation touches 122 B per gene), are prefetched into L1 with the next tile's
+// staged words — 264 -> 258.5 us per burn-in generation of 64 chains x 60 k x 4.  In the shapes that also run without tuning the same
+// change costs those launches 0.3-0.6 us (register allocation) for 2 us per burn-in generation, and is left out.  The lines are
+// only touched by this warp within a generation, and the generation's acquire orders the previous owner's stores before these loads.
+constexpr int GEN_BLK_TUNED = 256;
+template <int BLK> __device__ __forceinline__ void prefetch_windows(const SweepArgs &a, int64_t i) {
+  if (BLK == GEN_BLK_TUNED && a.tune) { prefetch_l1(a.win_y + i); prefetch_l1(a.win_v + i); }
+}
+
 template <int RT, int KT, int BLK>
 __global__ void __launch_bounds__(BLK, BLK <= 256 ? 3 : 1) k_generations(const __grid_constant__ GenArgs ga) {
   __shared__ FastH H;
@@ -447,7 +457,7 @@ __global__ void __launch_bounds__(BLK, BLK <= 256 ? 3 : 1) k_generations(const _
     if (ask_first && lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(&ctl->tile_q[tq * 32]) : "memory");
     if (t_ >= 0) {
       const int64_t g0 = a.g_begin + (int64_t)(ntiles - 1 - t_) * 32 + lane;
-      if (g0 < a.g_end) { stage_tile_ef(a, fa, chain, g0, stg, pol); f_next = a.flags[(int64_t)chain * a.G + g0]; }
+      if (g0 < a.g_end) { stage_tile_ef(a, fa, chain, g0, stg, pol); prefetch_windows<BLK>(a, (int64_t)chain * a.G + g0); f_next = a.flags[(int64_t)chain * a.G + g0]; }
     }
     if (ask_first) {
       const unsigned tk = __shfl_sync(0xffffffffu, ticket, 0);
@@ -477,7 +487,7 @@ __global__ void __launch_bounds__(BLK, BLK <= 256 ? 3 : 1) k_generations(const _
       }
       // every staged word of this tile is in registers: refill the slots with the warp's next tile, whose HBM latency then hides
       // behind this tile's ~1300 instructions (also for the lanes beyond the end of a ragged tile: their next tile is a full one)
-      if (next_valid) stage_tile_ef(a, fa, chain, g_n, stg, pol);
+      if (next_valid) { stage_tile_ef(a, fa, chain, g_n, stg, pol); prefetch_windows<BLK>(a, (int64_t)chain * a.G + g_n); }
       asm volatile("cp.async.commit_group;" ::: "memory");
       // the tile after the next one: ask the home queue now, read the answer when this tile is done
       // (inline asm: the compiler would otherwise sink the atomic down to the shuffle that reads it and expose its whole latency)
@@ -545,8 +555,8 @@ __global__ void __launch_bounds__(BLK, BLK <= 256 ? 3 : 1) k_generations(const _
       a.flags[i] = (uint16_t)f;
       if (live) { __stcs(a.Yg + i, y1); __stcs(a.vg + i, v1); __stcs(fa.lps + i, A1); }   // streaming stores (L2 evict-first)
       if (a.tune && live) {                                              // Pr:312-322, Pr:40-50
-        ulonglong2 w = __ldcs(a.win_y + i); window_push(w, acc_y); __stcs(a.win_y + i, w);
-        w = __ldcs(a.win_v + i); window_push(w, acc_v); __stcs(a.win_v + i, w);
+        ulonglong2 w = BLK == GEN_BLK_TUNED ? a.win_y[i] : __ldcs(a.win_y + i); window_push(w, acc_y); __stcs(a.win_y + i, w);
+        w = BLK == GEN_BLK_TUNED ? a.win_v[i] : __ldcs(a.win_v + i); window_push(w, acc_v); __stcs(a.win_v + i, w);
       }
       saw_nan |= live && (isnan(ratio_y) || isnan(ratio_v) || bad);
       double ys = y1, lvs = lv1;
