@@ -37,6 +37,11 @@ for G in (777, 262144 + 3, 300001):                       # one thread; exactly 
     pin["XgLikelihood"].zero_()
     h._ck(h.L.zz_get_state(h.h, 0, *args))
     assert np.array_equal(y, a["Yg"]) and np.array_equal(w, a["alloc_within_active"]) and np.array_equal(pin["XgLikelihood"].numpy(), a["XgLikelihood"])
+    # a device pointer where a host pointer belongs is handed to the copy as it is (unified addressing): no host-side memcpy into it
+    dev = torch.zeros(G, dtype=torch.float64, device="cuda")
+    rc = h.L.zz_get_state(h.h, 0, *([dev.data_ptr()] + [None] * 8))
+    torch.cuda.synchronize()
+    assert rc != 0 or np.array_equal(dev.cpu().numpy(), a["Yg"]), "device destination: neither refused nor filled"
     h.close()
 print("state pull OK")
 '''

@@ -1836,7 +1836,7 @@ int zz_get_state(zz_handle *h, int chain, double *Yg, double *variance_g, int32_
   auto is_pinned = [](const void *p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost;
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice;   // a device pointer is handed to the copy as it is (and refused there), not to memcpy
   };
   for (int j = 0; j < 6; ++j) {
     if (!dst8[j]) continue;
